@@ -1,0 +1,201 @@
+/*
+ * mulls_b200 C-ABI — the drop-in boundary of the MULLS registration hot path on B200.
+ *
+ * Every entry point below is what a reference-side binding for this path would call. The
+ * reference interface each one replaces is cited as file:line relative to the MULLS tree
+ * (YuePanEdward/MULLS @ b275607):
+ *
+ *   mulls_icp_run            <- lo::CRegistration<PointT>::mm_lls_icp
+ *                               include/common/cregistration.hpp:1114-1440
+ *                               (determine_corres :1701-1835, multi_metrics_lls_tran_estimation
+ *                                :1869-1967, pt2pl/pt2li/pt2pt_lls_summation :1976-2275,
+ *                                get_multi_metrics_lls_residual :2518-2677, the per-class PCL kd-tree
+ *                                build :1209-1232, intersection_filter :2894-2922)
+ *   mulls_icp_run_batch      <- the same call made for N independent scan pairs (BASELINE config 4)
+ *   mulls_batch_upload /
+ *   mulls_batch_run_resident <- same, split so that inputs can stay resident in HBM between runs
+ *   mulls_icp_run_sharded    <- the same call with the source clouds sharded over ranks
+ *                               (BASELINE config 5); the per-iteration exchange is delegated to a
+ *                               caller-supplied all-reduce (NCCL in production)
+ *   mulls_pca_features       <- lo::PrincipleComponentAnalysis<PointT>::get_pc_pca_feature
+ *                               include/common/pca.hpp:294-354 (+ get_pca_feature :390-434)
+ *
+ * Plain C, plain pointers and sizes. No torch / Eigen / PCL types cross this boundary; the C++ shim
+ * in include/common/cregistration.hpp converts Eigen/PCL objects to these PODs.
+ *
+ * Return convention: every function returns 0 on success or a negative MULLS_E_* code for
+ * *infrastructure* errors (CUDA failure, bad argument, unsupported option). The *algorithmic* status
+ * of a registration (1, -1, -2, -3 exactly as cregistration.hpp:1131-1136) is in mulls_icp_result.code.
+ * There is no CPU fallback: without a CUDA device mulls_create fails with MULLS_E_CUDA.
+ */
+#ifndef MULLS_B200_ABI_H
+#define MULLS_B200_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MULLS_NUM_CLASSES 6
+/* Order of the feature classes everywhere in this ABI == the index order of `used_feature_type`
+ * inside mm_lls_icp (cregistration.hpp:1196-1232): ground, pillar, facade, beam, roof, vertex. */
+enum {
+    MULLS_GROUND = 0,
+    MULLS_PILLAR = 1,
+    MULLS_FACADE = 2,
+    MULLS_BEAM = 3,
+    MULLS_ROOF = 4,
+    MULLS_VERTEX = 5
+};
+
+/* infrastructure error codes */
+enum {
+    MULLS_OK = 0,
+    MULLS_E_CUDA = -100,        /* CUDA runtime error, see mulls_last_error */
+    MULLS_E_ARG = -101,         /* invalid argument */
+    MULLS_E_CAPACITY = -102,    /* more points / pairs than the context was created for */
+    MULLS_E_UNSUPPORTED = -103, /* option of mm_lls_icp that this build does not implement */
+    MULLS_E_COMM = -104         /* the caller's all-reduce callback failed */
+};
+
+#define MULLS_MAX_TRACE_ITERS 64
+
+/* Zero-copy view of pcl::PointCloud<pcl::PointXYZINormal>::points (utility.hpp:40):
+ * 12 floats (48 bytes) per point: x y z _ | normal_x normal_y normal_z _ | intensity curvature _ _ .
+ * For pillar/beam clouds normal_* holds the principal direction (pca.hpp:437-454). Host pointer. */
+typedef struct mulls_cloud_view {
+    const float *aos48;
+    size_t n;
+} mulls_cloud_view;
+
+/* The 21 scalar/string arguments of mm_lls_icp (cregistration.hpp:1114-1123), same names, same
+ * defaults (see mulls_icp_default_params), plus the target block's bounding box that the function
+ * reads from registration_cons.block1->local_bound (cregistration.hpp:2916). */
+typedef struct mulls_icp_params {
+    int32_t max_iter_num;
+    float dis_thre_unit;
+    float converge_translation;
+    float converge_rotation_d;
+    float dis_thre_min;
+    float dis_thre_update_rate;
+    char used_feature_type[8]; /* "111110" + NUL; order ground,pillar,facade,beam,roof,vertex */
+    char weight_strategy[8];   /* "1101" + NUL; balance,residual,distance,intensity */
+    float z_xy_balanced_ratio;
+    float pt2pt_residual_window;
+    float pt2pl_residual_window;
+    float pt2li_residual_window;
+    int32_t apply_intersection_filter;
+    int32_t apply_motion_undistortion_while_registration; /* must be 0 (MULLS_E_UNSUPPORTED) */
+    int32_t normal_shooting_on;                           /* must be 0 (MULLS_E_UNSUPPORTED) */
+    float normal_bearing;
+    int32_t use_more_points; /* informational: the caller already chose pc_* vs pc_*_down */
+    int32_t keep_less_source_points; /* must be 0 (MULLS_E_UNSUPPORTED; time-seeded RNG upstream) */
+    float sigma_thre;
+    float min_neccessary_corr_ratio;
+    float max_bearable_rotation_d;
+    double target_bound[6]; /* block1->local_bound: min_x min_y min_z max_x max_y max_z */
+} mulls_icp_params;
+
+/* Outputs of mm_lls_icp: constraint_t::Trans1_2 / information_matrix / sigma / confidence
+ * (cregistration.hpp:1405, :1418-1420) and the return code (:1439). Matrices are ROW-major. */
+typedef struct mulls_icp_result {
+    double T[16];
+    double info[36];
+    float sigma;
+    float confidence;
+    int32_t code;  /* 1 ok, -1 step too large, -2 too few correspondences, -3 sigma too large, 0 no iteration */
+    int32_t iters; /* number of loop bodies entered (the failing / converging one included) */
+    uint32_t n_corr[MULLS_NUM_CLASSES]; /* |Corr_f| per class in the last executed iteration */
+    uint32_t n_src[MULLS_NUM_CLASSES];  /* source points per class left after the last executed iteration */
+} mulls_icp_result;
+
+/* Optional per-iteration trace (parity tests): what the reference would LOG(INFO) per iteration. */
+typedef struct mulls_icp_trace {
+    int32_t n_iter;
+    int32_t _pad;
+    double atpa[MULLS_MAX_TRACE_ITERS][36]; /* row-major, symmetrised as at cregistration.hpp:1924-1938 */
+    double atpb[MULLS_MAX_TRACE_ITERS][6];
+    double x[MULLS_MAX_TRACE_ITERS][6];
+    uint32_t n_corr[MULLS_MAX_TRACE_ITERS][MULLS_NUM_CLASSES];
+    uint32_t n_src[MULLS_MAX_TRACE_ITERS][MULLS_NUM_CLASSES]; /* source sizes after determine_corres */
+} mulls_icp_trace;
+
+typedef struct mulls_ctx mulls_ctx;
+
+/* Create a context on CUDA device `device` able to hold `max_pairs` scan pairs of at most
+ * `max_src_pts` source and `max_tgt_pts` target points each (sum over the six classes). */
+mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t max_tgt_pts);
+void mulls_destroy(mulls_ctx *ctx);
+const char *mulls_last_error(const mulls_ctx *ctx); /* ctx may be NULL: error of the failed create */
+
+/* Fill `p` with the default arguments of mm_lls_icp (cregistration.hpp:1115-1123). */
+void mulls_icp_default_params(mulls_icp_params *p);
+
+/* One registration: host clouds in, host result out (H2D + all iterations + D2H inside). */
+int mulls_icp_run(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
+                  const mulls_cloud_view src[MULLS_NUM_CLASSES], const mulls_icp_params *params,
+                  const double init_guess[16] /* row-major 4x4 */, mulls_icp_result *out,
+                  mulls_icp_trace *trace /* may be NULL */);
+
+/* n_pairs independent registrations in one call. tgt/src are [n_pairs][6]. */
+int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt,
+                        const mulls_cloud_view *src, const mulls_icp_params *params /* [n_pairs] */,
+                        const double *init_guess /* [n_pairs][16] */, mulls_icp_result *out /* [n_pairs] */,
+                        mulls_icp_trace *trace /* [n_pairs] or NULL */);
+
+/* Split form: copy the inputs to HBM once, then run the whole path (ingest: filter, spatial sort,
+ * grid build; all iterations; posterior) any number of times from the resident copies. */
+int mulls_batch_upload(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt,
+                       const mulls_cloud_view *src, const mulls_icp_params *params,
+                       const double *init_guess);
+int mulls_batch_run_resident(mulls_ctx *ctx, mulls_icp_result *out /* [n_pairs] or NULL */,
+                             mulls_icp_trace *trace /* [n_pairs] or NULL */);
+
+/* Statistics of the last run on this context (for bench.py). */
+typedef struct mulls_run_stats {
+    uint64_t kernel_launches;   /* kernels of this library launched by the last run */
+    uint64_t algorithmic_bytes; /* sum over pairs and executed iterations of 28*(N_s,active + N_t) */
+    uint64_t iterations;        /* sum over pairs of executed iterations */
+    float ms_ingest;            /* device time of the ingest phase (CUDA events) */
+    float ms_iterate;           /* device time of the iteration kernels */
+    float ms_search;            /* device time of the fused transform+NN+claim kernel only */
+    float ms_total;
+} mulls_run_stats;
+int mulls_get_stats(const mulls_ctx *ctx, mulls_run_stats *out);
+
+/* Source-sharded single registration (BASELINE config 5): every rank holds the full target and a
+ * contiguous slice of every source class starting at global index src_index_base[c]. The caller
+ * supplies the all-reduce used once (sum, doubles) or twice (+ min, int32 claim table) per
+ * iteration on device buffers; with NCCL: ncclAllReduce(buf, buf, count, type, op, comm, stream). */
+typedef int (*mulls_allreduce_fn)(void *user, void *device_buf, size_t count,
+                                  int dtype /* 0 = float64, 1 = int32 */, int op /* 0 = sum, 1 = min */,
+                                  void *cuda_stream);
+int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
+                          const mulls_cloud_view src_shard[MULLS_NUM_CLASSES],
+                          const uint32_t src_index_base[MULLS_NUM_CLASSES],
+                          const uint32_t src_global_n[MULLS_NUM_CLASSES],
+                          const mulls_icp_params *params, const double init_guess[16],
+                          mulls_allreduce_fn allreduce, void *user, mulls_icp_result *out,
+                          mulls_icp_trace *trace);
+
+/* PCA neighbourhood features (pca.hpp:294-354): for every `stride`-th point of `cloud` take the
+ * at most `k` nearest neighbours within `radius` (the point itself included), and return
+ * eigenvalues (descending), principal direction, normal direction, and the neighbour count. */
+typedef struct mulls_pca_out {
+    float *eigenvalues; /* [n][3] lambda1 >= lambda2 >= lambda3 (pcl::PCA convention) */
+    float *principal;   /* [n][3] unit principal direction (eigenvector of lambda1) */
+    float *normal;      /* [n][3] unit normal direction (col0 x col1, pcl::PCA convention) */
+    int32_t *pt_num;    /* [n] neighbours used (0 for points skipped by the stride) */
+} mulls_pca_out;
+int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride,
+                       mulls_pca_out *out);
+
+/* Runtime tunables (integers), e.g. "start_level", "pairs_in_flight". Returns MULLS_E_ARG if unknown. */
+int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULLS_B200_ABI_H */

@@ -1,0 +1,245 @@
+"""ctypes mirror of include/mulls_b200/abi.h (the C-ABI of the B200 registration hot path).
+
+The PODs here are byte-for-byte the structs of abi.h; `load_library()` opens the in-tree
+`mulls_b200/csrc/libmulls_b200.so` and fails loudly when it is missing — there is no CPU fallback
+in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+NUM_CLASSES = 6
+GROUND, PILLAR, FACADE, BEAM, ROOF, VERTEX = range(6)
+CLASS_NAMES = ("ground", "pillar", "facade", "beam", "roof", "vertex")
+MAX_TRACE_ITERS = 64
+
+E_CUDA, E_ARG, E_CAPACITY, E_UNSUPPORTED, E_COMM = -100, -101, -102, -103, -104
+
+
+class CloudView(C.Structure):
+    _fields_ = [("aos48", C.POINTER(C.c_float)), ("n", C.c_size_t)]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [
+        ("max_iter_num", C.c_int32),
+        ("dis_thre_unit", C.c_float),
+        ("converge_translation", C.c_float),
+        ("converge_rotation_d", C.c_float),
+        ("dis_thre_min", C.c_float),
+        ("dis_thre_update_rate", C.c_float),
+        ("used_feature_type", C.c_char * 8),
+        ("weight_strategy", C.c_char * 8),
+        ("z_xy_balanced_ratio", C.c_float),
+        ("pt2pt_residual_window", C.c_float),
+        ("pt2pl_residual_window", C.c_float),
+        ("pt2li_residual_window", C.c_float),
+        ("apply_intersection_filter", C.c_int32),
+        ("apply_motion_undistortion_while_registration", C.c_int32),
+        ("normal_shooting_on", C.c_int32),
+        ("normal_bearing", C.c_float),
+        ("use_more_points", C.c_int32),
+        ("keep_less_source_points", C.c_int32),
+        ("sigma_thre", C.c_float),
+        ("min_neccessary_corr_ratio", C.c_float),
+        ("max_bearable_rotation_d", C.c_float),
+        ("target_bound", C.c_double * 6),
+    ]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [
+        ("T", C.c_double * 16),
+        ("info", C.c_double * 36),
+        ("sigma", C.c_float),
+        ("confidence", C.c_float),
+        ("code", C.c_int32),
+        ("iters", C.c_int32),
+        ("n_corr", C.c_uint32 * 6),
+        ("n_src", C.c_uint32 * 6),
+    ]
+
+
+class IcpTrace(C.Structure):
+    _fields_ = [
+        ("n_iter", C.c_int32),
+        ("_pad", C.c_int32),
+        ("atpa", (C.c_double * 36) * MAX_TRACE_ITERS),
+        ("atpb", (C.c_double * 6) * MAX_TRACE_ITERS),
+        ("x", (C.c_double * 6) * MAX_TRACE_ITERS),
+        ("n_corr", (C.c_uint32 * 6) * MAX_TRACE_ITERS),
+        ("n_src", (C.c_uint32 * 6) * MAX_TRACE_ITERS),
+    ]
+
+
+class RunStats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64),
+        ("algorithmic_bytes", C.c_uint64),
+        ("iterations", C.c_uint64),
+        ("ms_ingest", C.c_float),
+        ("ms_iterate", C.c_float),
+        ("ms_search", C.c_float),
+        ("ms_total", C.c_float),
+    ]
+
+
+class PcaOut(C.Structure):
+    _fields_ = [
+        ("eigenvalues", C.POINTER(C.c_float)),
+        ("principal", C.POINTER(C.c_float)),
+        ("normal", C.POINTER(C.c_float)),
+        ("pt_num", C.POINTER(C.c_int32)),
+    ]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
+
+# every symbol include/mulls_b200/abi.h declares
+EXPORTED_SYMBOLS = (
+    "mulls_create",
+    "mulls_destroy",
+    "mulls_last_error",
+    "mulls_icp_default_params",
+    "mulls_icp_run",
+    "mulls_icp_run_batch",
+    "mulls_batch_upload",
+    "mulls_batch_run_resident",
+    "mulls_get_stats",
+    "mulls_icp_run_sharded",
+    "mulls_pca_features",
+    "mulls_set_tunable",
+)
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmulls_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """Open the CUDA library. Raises (never falls back) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C mulls_b200/csrc`). mulls_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.mulls_create.restype = vp
+    lib.mulls_create.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t]
+    lib.mulls_destroy.restype = None
+    lib.mulls_destroy.argtypes = [vp]
+    lib.mulls_last_error.restype = C.c_char_p
+    lib.mulls_last_error.argtypes = [vp]
+    lib.mulls_icp_default_params.restype = None
+    lib.mulls_icp_default_params.argtypes = [C.POINTER(IcpParams)]
+    lib.mulls_icp_run.restype = C.c_int
+    lib.mulls_icp_run.argtypes = [vp, C.POINTER(CloudView), C.POINTER(CloudView), C.POINTER(IcpParams),
+                                  C.POINTER(C.c_double), C.POINTER(IcpResult), C.POINTER(IcpTrace)]
+    lib.mulls_icp_run_batch.restype = C.c_int
+    lib.mulls_icp_run_batch.argtypes = [vp, C.c_size_t, C.POINTER(CloudView), C.POINTER(CloudView),
+                                        C.POINTER(IcpParams), C.POINTER(C.c_double), C.POINTER(IcpResult),
+                                        C.POINTER(IcpTrace)]
+    lib.mulls_batch_upload.restype = C.c_int
+    lib.mulls_batch_upload.argtypes = [vp, C.c_size_t, C.POINTER(CloudView), C.POINTER(CloudView),
+                                       C.POINTER(IcpParams), C.POINTER(C.c_double)]
+    lib.mulls_batch_run_resident.restype = C.c_int
+    lib.mulls_batch_run_resident.argtypes = [vp, C.POINTER(IcpResult), C.POINTER(IcpTrace)]
+    lib.mulls_get_stats.restype = C.c_int
+    lib.mulls_get_stats.argtypes = [vp, C.POINTER(RunStats)]
+    lib.mulls_icp_run_sharded.restype = C.c_int
+    lib.mulls_icp_run_sharded.argtypes = [vp, C.POINTER(CloudView), C.POINTER(CloudView),
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(IcpParams),
+                                          C.POINTER(C.c_double), ALLREDUCE_FN, vp, C.POINTER(IcpResult),
+                                          C.POINTER(IcpTrace)]
+    lib.mulls_pca_features.restype = C.c_int
+    lib.mulls_pca_features.argtypes = [vp, CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(PcaOut)]
+    lib.mulls_set_tunable.restype = C.c_int
+    lib.mulls_set_tunable.argtypes = [vp, C.c_char_p, C.c_int]
+    _LIB = lib
+    return lib
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers shared by the host-side mirror, the tests and the bench
+# ---------------------------------------------------------------------------------------------
+def as_aos48(points: np.ndarray) -> np.ndarray:
+    """(n,7) [x y z nx ny nz intensity] or (n,12) float32 -> C-contiguous (n,12) pcl::PointXYZINormal rows."""
+    points = np.asarray(points, dtype=np.float32)
+    if points.ndim != 2:
+        raise ValueError("point array must be 2-D")
+    if points.shape[1] == 12:
+        return np.ascontiguousarray(points)
+    if points.shape[1] != 7:
+        raise ValueError("expected (n,7) or (n,12) float32")
+    out = np.zeros((points.shape[0], 12), dtype=np.float32)
+    out[:, 0:3] = points[:, 0:3]
+    out[:, 3] = 1.0
+    out[:, 4:7] = points[:, 3:6]
+    out[:, 8] = points[:, 6]
+    return out
+
+
+def cloud_view(arr: np.ndarray) -> CloudView:
+    """View of an (n,12) float32 C-contiguous array (keep `arr` alive while the view is in use)."""
+    assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"] and (arr.size == 0 or arr.shape[1] == 12)
+    return CloudView(arr.ctypes.data_as(C.POINTER(C.c_float)), arr.shape[0])
+
+
+def default_params() -> IcpParams:
+    """The defaults of mm_lls_icp (cregistration.hpp:1115-1123) — pure Python, no library needed."""
+    p = IcpParams()
+    p.max_iter_num = 20
+    p.dis_thre_unit = 1.5
+    p.converge_translation = 0.002
+    p.converge_rotation_d = 0.01
+    p.dis_thre_min = 0.4
+    p.dis_thre_update_rate = 1.1
+    p.used_feature_type = b"111110"
+    p.weight_strategy = b"1101"
+    p.z_xy_balanced_ratio = 1.0
+    p.pt2pt_residual_window = 0.1
+    p.pt2pl_residual_window = 0.1
+    p.pt2li_residual_window = 0.1
+    p.apply_intersection_filter = 1
+    p.apply_motion_undistortion_while_registration = 0
+    p.normal_shooting_on = 0
+    p.normal_bearing = 45.0
+    p.use_more_points = 0
+    p.keep_less_source_points = 0
+    p.sigma_thre = 0.5
+    p.min_neccessary_corr_ratio = 0.03
+    p.max_bearable_rotation_d = 45.0
+    big = 1.7976931348623157e308
+    p.target_bound[:] = [-big, -big, -big, big, big, big]
+    return p
+
+
+def result_to_dict(r: IcpResult) -> dict:
+    return {
+        "T": np.array(r.T[:], dtype=np.float64).reshape(4, 4),
+        "info": np.array(r.info[:], dtype=np.float64).reshape(6, 6),
+        "sigma": float(r.sigma),
+        "confidence": float(r.confidence),
+        "code": int(r.code),
+        "iters": int(r.iters),
+        "n_corr": [int(v) for v in r.n_corr],
+        "n_src": [int(v) for v in r.n_src],
+    }
+
+
+def trace_to_dict(t: IcpTrace) -> dict:
+    n = int(t.n_iter)
+    return {
+        "n_iter": n,
+        "atpa": np.ctypeslib.as_array(t.atpa)[:n].reshape(n, 6, 6).copy(),
+        "atpb": np.ctypeslib.as_array(t.atpb)[:n].copy(),
+        "x": np.ctypeslib.as_array(t.x)[:n].copy(),
+        "n_corr": np.ctypeslib.as_array(t.n_corr)[:n].copy(),
+        "n_src": np.ctypeslib.as_array(t.n_src)[:n].copy(),
+    }

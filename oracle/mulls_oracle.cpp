@@ -1,0 +1,1213 @@
+// ============================================================================================
+// oracle/mulls_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the MULLS registration hot path (YuePanEdward/MULLS @ b275607), used ONLY
+//   * by tests/ as the parity checker for the CUDA path,
+//   * by __graft_entry__.smoke() as the checker of the one smoke invocation,
+//   * by bench.py for the `cpu_baseline` leg and for `--impl reference`.
+// Nothing under mulls_b200/ may include, link or call this file.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or expected outputs for this path
+//  and cannot be compiled in this container (PCL, Eigen, FLANN, glog, gflags
+// are absent, no network). This restatement follows the reference source line by line; every
+// function cites the lines it restates. Third-party semantics (PCL 1.10 / FLANN 1.9.1 /
+// Eigen 3.3.7 — not vendored in the reference) are restated from their published behaviour and
+// marked [3P]. It is cross-checked by an independent numpy/scipy restatement in
+// tests/test_oracle_crosscheck.py and by ground-truth recovery tests, not by the reference binary.
+//
+// Arithmetic fidelity: the reference mixes float and double exactly as written in its source; the
+// expressions below keep the same operand types so that the compiler applies the same conversions.
+// Build with -ffp-contract=off (the reference's distro build has no FMA contraction).
+// Places where a third-party summation order cannot be known to the last ulp are marked [ORDER].
+// ============================================================================================
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/mulls_b200/abi.h"
+
+namespace {
+
+struct Pt {
+    float x, y, z;
+    float nx, ny, nz;
+    float intensity;
+};
+typedef std::vector<Pt> Cloud;
+
+// pcl::Correspondence [3P]: {index_query, index_match, union{distance, weight}}
+struct Corr {
+    int q;
+    int m;
+    float dw; // squared NN distance, later overwritten by the LLS weight (same storage in PCL)
+};
+typedef std::vector<Corr> Corrs;
+
+// ---------------------------------------------------------------------------------------------
+// exact 1-NN kd-tree, standing in for pcl::search::KdTree -> FLANN KDTreeSingleIndex, leaf 15,
+// L2_Simple<float> [3P]. Distance is the FLANN accumulation: result=0; result += d*d per dim, in
+// float. Ties on the float distance are broken towards the lower target index (FLANN's tie
+// behaviour depends on its traversal order and is not specified; this is the oracle's convention
+// and the CUDA path follows it).
+// ---------------------------------------------------------------------------------------------
+struct KdNode {
+    int left, right; // inner: children; leaf: [left,right) range into idx
+    int dim;         // -1 for leaf
+    float lo, hi;    // max of left child / min of right child along dim
+};
+
+struct KdTree {
+    const Cloud *pts = nullptr;
+    std::vector<int> idx;
+    std::vector<KdNode> nodes;
+    float bmin[3], bmax[3];
+
+    static inline float coord(const Pt &p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
+
+    void build(const Cloud &c) {
+        pts = &c;
+        const int n = (int)c.size();
+        idx.resize(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        nodes.clear();
+        nodes.reserve(n / 4 + 16);
+        for (int d = 0; d < 3; ++d) {
+            bmin[d] = std::numeric_limits<float>::max();
+            bmax[d] = -std::numeric_limits<float>::max();
+        }
+        for (int i = 0; i < n; ++i)
+            for (int d = 0; d < 3; ++d) {
+                float v = coord(c[i], d);
+                bmin[d] = std::min(bmin[d], v);
+                bmax[d] = std::max(bmax[d], v);
+            }
+        if (n > 0) build_rec(0, n);
+    }
+
+    int build_rec(int b, int e) {
+        int me = (int)nodes.size();
+        nodes.push_back(KdNode());
+        if (e - b <= 15) {
+            nodes[me].left = b;
+            nodes[me].right = e;
+            nodes[me].dim = -1;
+            return me;
+        }
+        float mn[3], mx[3];
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = std::numeric_limits<float>::max();
+            mx[d] = -std::numeric_limits<float>::max();
+        }
+        for (int i = b; i < e; ++i)
+            for (int d = 0; d < 3; ++d) {
+                float v = coord((*pts)[idx[i]], d);
+                mn[d] = std::min(mn[d], v);
+                mx[d] = std::max(mx[d], v);
+            }
+        int dim = 0;
+        if (mx[1] - mn[1] > mx[dim] - mn[dim]) dim = 1;
+        if (mx[2] - mn[2] > mx[dim] - mn[dim]) dim = 2;
+        int mid = (b + e) / 2;
+        const Cloud &P = *pts;
+        std::nth_element(idx.begin() + b, idx.begin() + mid, idx.begin() + e,
+                         [&](int a, int c2) { return coord(P[a], dim) < coord(P[c2], dim); });
+        float lo = -std::numeric_limits<float>::max(), hi = std::numeric_limits<float>::max();
+        for (int i = b; i < mid; ++i) lo = std::max(lo, coord(P[idx[i]], dim));
+        for (int i = mid; i < e; ++i) hi = std::min(hi, coord(P[idx[i]], dim));
+        int l = build_rec(b, mid);
+        int r = build_rec(mid, e);
+        nodes[me].left = l;
+        nodes[me].right = r;
+        nodes[me].dim = dim;
+        nodes[me].lo = lo;
+        nodes[me].hi = hi;
+        return me;
+    }
+
+    struct Best {
+        float d2;
+        int i;
+    };
+
+    static inline float flann_l2(const float q[3], const Pt &p) {
+        float result = 0.0f, diff;
+        diff = q[0] - p.x;
+        result += diff * diff;
+        diff = q[1] - p.y;
+        result += diff * diff;
+        diff = q[2] - p.z;
+        result += diff * diff;
+        return result;
+    }
+
+    void search_rec(int node, const float q[3], float mindist, float dists[3], Best &best) const {
+        const KdNode &nd = nodes[node];
+        if (nd.dim < 0) {
+            for (int k = nd.left; k < nd.right; ++k) {
+                int i = idx[k];
+                float d2 = flann_l2(q, (*pts)[i]);
+                if (d2 < best.d2 || (d2 == best.d2 && i < best.i)) {
+                    best.d2 = d2;
+                    best.i = i;
+                }
+            }
+            return;
+        }
+        float val = q[nd.dim];
+        float diff1 = val - nd.lo, diff2 = val - nd.hi;
+        int first, second;
+        float cut;
+        if (diff1 + diff2 < 0) {
+            first = nd.left;
+            second = nd.right;
+            cut = diff2 * diff2;
+        } else {
+            first = nd.right;
+            second = nd.left;
+            cut = diff1 * diff1;
+        }
+        search_rec(first, q, mindist, dists, best);
+        float saved = dists[nd.dim];
+        float md = mindist + cut - saved;
+        dists[nd.dim] = cut;
+        // conservative (<=, with a rounding margin) so that exact ties are still visited
+        if (md * 0.99999f <= best.d2) search_rec(second, q, md, dists, best);
+        dists[nd.dim] = saved;
+    }
+
+    // exact nearest neighbour; returns false on an empty tree
+    bool nearest(const float q[3], int &index, float &d2) const {
+        if (idx.empty()) return false;
+        float dists[3] = {0, 0, 0};
+        float mind = 0;
+        for (int d = 0; d < 3; ++d) {
+            if (q[d] < bmin[d]) dists[d] = (q[d] - bmin[d]) * (q[d] - bmin[d]);
+            if (q[d] > bmax[d]) dists[d] = (q[d] - bmax[d]) * (q[d] - bmax[d]);
+            mind += dists[d];
+        }
+        Best best = {std::numeric_limits<float>::infinity(), -1};
+        search_rec(0, q, mind, dists, best);
+        index = best.i;
+        d2 = best.d2;
+        return best.i >= 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// small dense double algebra standing in for Eigen [3P]
+// ---------------------------------------------------------------------------------------------
+struct Mat6 {
+    double a[6][6];
+};
+struct Mat4 {
+    double a[4][4];
+};
+
+// Eigen::Matrix<double,6,6>::inverse() [3P] == PartialPivLU(m).inverse() == lu.solve(Identity)
+static bool inverse6(const Mat6 &in, Mat6 &out) {
+    double lu[6][6];
+    int perm[6];
+    std::memcpy(lu, in.a, sizeof(lu));
+    for (int i = 0; i < 6; ++i) perm[i] = i;
+    for (int k = 0; k < 6; ++k) {
+        int piv = k;
+        double best = std::fabs(lu[k][k]);
+        for (int r = k + 1; r < 6; ++r)
+            if (std::fabs(lu[r][k]) > best) {
+                best = std::fabs(lu[r][k]);
+                piv = r;
+            }
+        if (piv != k) {
+            for (int c = 0; c < 6; ++c) std::swap(lu[k][c], lu[piv][c]);
+            std::swap(perm[k], perm[piv]);
+        }
+        double d = lu[k][k];
+        for (int r = k + 1; r < 6; ++r) lu[r][k] /= d;
+        for (int r = k + 1; r < 6; ++r)
+            for (int c = k + 1; c < 6; ++c) lu[r][c] -= lu[r][k] * lu[k][c];
+    }
+    for (int col = 0; col < 6; ++col) {
+        double y[6];
+        for (int r = 0; r < 6; ++r) {
+            double s = (perm[r] == col) ? 1.0 : 0.0;
+            for (int c = 0; c < r; ++c) s -= lu[r][c] * y[c];
+            y[r] = s;
+        }
+        for (int r = 5; r >= 0; --r) {
+            double s = y[r];
+            for (int c = r + 1; c < 6; ++c) s -= lu[r][c] * out.a[c][col];
+            out.a[r][col] = s / lu[r][r];
+        }
+    }
+    return true;
+}
+
+static Mat4 mul4(const Mat4 &A, const Mat4 &B) { // [ORDER] sequential over k
+    Mat4 C;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = A.a[i][0] * B.a[0][j];
+            for (int k = 1; k < 4; ++k) s += A.a[i][k] * B.a[k][j];
+            C.a[i][j] = s;
+        }
+    return C;
+}
+static Mat4 ident4() {
+    Mat4 m;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) m.a[i][j] = (i == j) ? 1.0 : 0.0;
+    return m;
+}
+
+// Eigen::AngleAxisd(Matrix3d).angle() [3P]: matrix -> quaternion -> 2*atan2(|vec|, |w|)
+static double rotation_angle(const Mat4 &T) {
+    const double(*m)[4] = T.a;
+    double w, x, y, z;
+    double t = m[0][0] + m[1][1] + m[2][2];
+    if (t > 0.0) {
+        t = std::sqrt(t + 1.0);
+        w = 0.5 * t;
+        t = 0.5 / t;
+        x = (m[2][1] - m[1][2]) * t;
+        y = (m[0][2] - m[2][0]) * t;
+        z = (m[1][0] - m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+        double q[3];
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        w = (m[k][j] - m[j][k]) * t;
+        q[j] = (m[j][i] + m[i][j]) * t;
+        q[k] = (m[k][i] + m[i][k]) * t;
+        x = q[0];
+        y = q[1];
+        z = q[2];
+    }
+    double n = std::sqrt(x * x + y * y + z * z);
+    if (n != 0.0) return 2.0 * std::atan2(n, std::fabs(w));
+    return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cregistration.hpp:1685-1696 batch_transform_feature_points -> pcl::transformPointCloudWithNormals
+// [3P PCL 1.10 transforms.hpp]: per point, double math, each component static_cast<float>.
+// ---------------------------------------------------------------------------------------------
+static void transform_cloud(Cloud &c, const Mat4 &T) {
+    const double(*t)[4] = T.a;
+    for (size_t i = 0; i < c.size(); ++i) {
+        Pt &p = c[i];
+        const double px = p.x, py = p.y, pz = p.z;
+        const double qx = p.nx, qy = p.ny, qz = p.nz;
+        p.x = static_cast<float>(t[0][0] * px + t[0][1] * py + t[0][2] * pz + t[0][3]);
+        p.y = static_cast<float>(t[1][0] * px + t[1][1] * py + t[1][2] * pz + t[1][3]);
+        p.z = static_cast<float>(t[2][0] * px + t[2][1] * py + t[2][2] * pz + t[2][3]);
+        p.nx = static_cast<float>(t[0][0] * qx + t[0][1] * qy + t[0][2] * qz);
+        p.ny = static_cast<float>(t[1][0] * qx + t[1][1] * qy + t[1][2] * qz);
+        p.nz = static_cast<float>(t[2][0] * qx + t[2][1] * qy + t[2][2] * qz);
+    }
+}
+
+// utility.hpp:101-136 bounds_t, :817-848 get_cloud_bbx
+struct Bounds {
+    double min_x, min_y, min_z, max_x, max_y, max_z;
+};
+static Bounds cloud_bbx(const Cloud &c) {
+    Bounds b = {1.7976931348623157e308,  1.7976931348623157e308,  1.7976931348623157e308,
+                -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+    for (size_t i = 0; i < c.size(); ++i) {
+        if (b.min_x > c[i].x) b.min_x = c[i].x;
+        if (b.min_y > c[i].y) b.min_y = c[i].y;
+        if (b.min_z > c[i].z) b.min_z = c[i].z;
+        if (b.max_x < c[i].x) b.max_x = c[i].x;
+        if (b.max_y < c[i].y) b.max_y = c[i].y;
+        if (b.max_z < c[i].z) b.max_z = c[i].z;
+    }
+    return b;
+}
+// cfilter.hpp:950-981 bbx_filter (keep strictly-inside points, order preserved)
+static void bbx_filter(Cloud &c, const Bounds &b) {
+    Cloud out;
+    out.reserve(c.size());
+    for (size_t i = 0; i < c.size(); ++i)
+        if (c[i].x > b.min_x && c[i].x < b.max_x && c[i].y > b.min_y && c[i].y < b.max_y &&
+            c[i].z > b.min_z && c[i].z < b.max_z)
+            out.push_back(c[i]);
+    c.swap(out);
+}
+
+// cregistration.hpp:2686-2692
+static inline float weight_by_dist_adaptive(float dist, int iter_num) {
+    const float unit_dist = 30.0f, b_min = 0.7f, b_max = 1.3f, b_step = 0.05f;
+    float b_current = ((b_min + b_step * iter_num) < (b_max)) ? (b_min + b_step * iter_num) : (b_max);
+    float temp_weight = b_current + (1.0 - b_current) * dist / unit_dist;
+    temp_weight = ((temp_weight) > (0.01)) ? (temp_weight) : (0.01);
+    return temp_weight;
+}
+// cregistration.hpp:2701-2707
+static inline float weight_by_intensity(float intensity_1, float intensity_2) {
+    const float intensity_scale = 255.0f;
+    float ratio = std::fabs(intensity_1 - intensity_2) / intensity_scale;
+    float w = std::exp(-1.0 * ratio);
+    return w;
+}
+// cregistration.hpp:2710-2722 (delta = 1)
+static inline float weight_by_residual(float res, float huber_thre) {
+    const int delta = 1;
+    return ((res > huber_thre)
+                ? ((2 * res * huber_thre + (delta * delta - 2 * delta) * (huber_thre * huber_thre)) / res / res)
+                : (1.0));
+}
+
+struct Normal {
+    double A[6][6]; // lower triangle + diagonal filled by pt2pl/pt2pt, diagonal by pt2li (Q1)
+    double b[6];
+};
+
+// cregistration.hpp:2066-2156 pt2pl_lls_summation. A[r][c] with r>=c == ATPA.coeffRef(r + 6*c).
+static void pt2pl_sum(const Cloud &S, const Cloud &T, Corrs &C, Normal &N, int iter_num, float weight,
+                      bool dist_w, bool resid_w, bool inten_w, float window) {
+    for (size_t i = 0; i < C.size(); ++i) {
+        const Pt &p = S[C[i].q];
+        const Pt &q = T[C[i].m];
+        float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+        float ntx = q.nx, nty = q.ny, ntz = q.nz;
+        float pi = p.intensity, qi = q.intensity;
+        float w = weight;
+        float a = ntz * py - nty * pz;
+        float b = ntx * pz - ntz * px;
+        float c = nty * px - ntx * py;
+        float d = ntx * qx + nty * qy + ntz * qz - ntx * px - nty * py - ntz * pz;
+        float dist = std::sqrt(qx * qx + qy * qy + qz * qz);
+        if (dist_w) w = w * weight_by_dist_adaptive(dist, iter_num);
+        if (resid_w) w = w * weight_by_residual(std::abs(d), window);
+        if (inten_w) w = w * weight_by_intensity(pi + 0.0001, qi + 0.0001);
+        C[i].dw = w;
+        N.A[0][0] += w * ntx * ntx;
+        N.A[1][0] += w * ntx * nty;
+        N.A[2][0] += w * ntx * ntz;
+        N.A[3][0] += w * a * ntx;
+        N.A[4][0] += w * b * ntx;
+        N.A[5][0] += w * c * ntx;
+        N.A[1][1] += w * nty * nty;
+        N.A[2][1] += w * nty * ntz;
+        N.A[3][1] += w * a * nty;
+        N.A[4][1] += w * b * nty;
+        N.A[5][1] += w * c * nty;
+        N.A[2][2] += w * ntz * ntz;
+        N.A[3][2] += w * a * ntz;
+        N.A[4][2] += w * b * ntz;
+        N.A[5][2] += w * c * ntz;
+        N.A[3][3] += w * a * a;
+        N.A[4][3] += w * a * b;
+        N.A[5][3] += w * a * c;
+        N.A[4][4] += w * b * b;
+        N.A[5][4] += w * b * c;
+        N.A[5][5] += w * c * c;
+        N.b[0] += w * d * ntx;
+        N.b[1] += w * d * nty;
+        N.b[2] += w * d * ntz;
+        N.b[3] += w * d * a;
+        N.b[4] += w * d * b;
+        N.b[5] += w * d * c;
+    }
+}
+
+// cregistration.hpp:2160-2275 pt2li_lls_pri_direction_summation.
+// The reference adds into ATPA(j,k), k>=j (upper triangle); the symmetrisation at :1924-1938 then
+// copies lower -> upper, so only the diagonal of these contributions survives.
+static void pt2li_sum(const Cloud &S, const Cloud &T, Corrs &C, Normal &N, int iter_num, float weight,
+                      bool dist_w, bool resid_w, bool inten_w, float window) {
+    for (size_t i = 0; i < C.size(); ++i) {
+        const Pt &p = S[C[i].q];
+        const Pt &q = T[C[i].m];
+        float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+        float vx = q.nx, vy = q.ny, vz = q.nz;
+        float pi = p.intensity, qi = q.intensity;
+        float dx = px - qx, dy = py - qy, dz = pz - qz;
+        double A[3][6], bv[3];
+        A[0][0] = 0;
+        A[0][1] = -vz;
+        A[0][2] = vy;
+        A[0][3] = vy * py + vz * pz;
+        A[0][4] = -vy * px;
+        A[0][5] = -vz * px;
+        A[1][0] = vz;
+        A[1][1] = 0;
+        A[1][2] = -vx;
+        A[1][3] = -vx * py;
+        A[1][4] = vz * pz + vx * px;
+        A[1][5] = -vz * py;
+        A[2][0] = -vy;
+        A[2][1] = vx;
+        A[2][2] = 0;
+        A[2][3] = -vx * pz;
+        A[2][4] = -vy * pz;
+        A[2][5] = vx * px + vy * py;
+        bv[0] = -vy * dz + vz * dy;
+        bv[1] = -vz * dx + vx * dz;
+        bv[2] = -vx * dy + vy * dx;
+        float ex = std::abs(bv[0]), ey = std::abs(bv[1]), ez = std::abs(bv[2]);
+        float ed = std::sqrt(ex * ex + ey * ey + ez * ez);
+        float wx = weight;
+        float dist = std::sqrt(qx * qx + qy * qy + qz * qz);
+        if (dist_w) wx *= weight_by_dist_adaptive(dist, iter_num);
+        if (inten_w) wx *= weight_by_intensity(pi + 0.0001, qi + 0.0001);
+        if (resid_w) wx = wx * weight_by_residual(ed, window);
+        C[i].dw = wx;
+        const double sw = std::sqrt(wx); // std::sqrt(float) -> float, stored into a double matrix
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 6; ++c) A[r][c] = sw * A[r][c];
+            bv[r] = sw * bv[r];
+        }
+        for (int j = 0; j < 6; ++j) {
+            N.A[j][j] += A[0][j] * A[0][j] + (A[1][j] * A[1][j] + A[2][j] * A[2][j]); // [ORDER] Eigen 3-redux
+            N.b[j] += A[0][j] * bv[0] + (A[1][j] * bv[1] + A[2][j] * bv[2]);
+        }
+    }
+}
+
+// cregistration.hpp:1976-2063 pt2pt_lls_summation (does NOT store a weight into Corr: Q2)
+static void pt2pt_sum(const Cloud &S, const Cloud &T, Corrs &C, Normal &N, int iter_num, float weight,
+                      bool dist_w, bool resid_w, bool inten_w, float window) {
+    for (size_t i = 0; i < C.size(); ++i) {
+        const Pt &p = S[C[i].q];
+        const Pt &q = T[C[i].m];
+        float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+        float pi = p.intensity, qi = q.intensity;
+        float dx = px - qx, dy = py - qy, dz = pz - qz;
+        float wx, wy, wz;
+        wx = weight;
+        float dist = std::sqrt(qx * qx + qy * qy + qz * qz);
+        if (dist_w) wx = wx * weight_by_dist_adaptive(dist, iter_num);
+        if (resid_w) wx = wx * weight_by_residual(std::sqrt(dx * dx + dy * dy + dz * dz), window);
+        if (inten_w) wx = wx * weight_by_intensity(pi + 0.0001, qi + 0.0001);
+        wy = wx;
+        wz = wx;
+        N.A[0][0] += wx;
+        N.A[4][0] += wx * pz;
+        N.A[5][0] += (-wx * py);
+        N.A[1][1] += wy;
+        N.A[3][1] += (-wy * pz);
+        N.A[5][1] += wy * px;
+        N.A[2][2] += wz;
+        N.A[3][2] += wz * py;
+        N.A[4][2] += (-wz * px);
+        N.A[3][3] += wy * pz * pz + wz * py * py;
+        N.A[4][3] += (-wz * px * py);
+        N.A[5][3] += (-wy * px * pz);
+        N.A[4][4] += wx * pz * pz + wz * px * px;
+        N.A[5][4] += (-wx * py * pz);
+        N.A[5][5] += wx * py * py + wy * px * px;
+        N.b[0] += (-wx * dx);
+        N.b[1] += (-wy * dy);
+        N.b[2] += (-wz * dz);
+        N.b[3] += wy * pz * dy - wz * py * dz;
+        N.b[4] += wz * px * dz - wx * pz * dx;
+        N.b[5] += wx * py * dx - wy * px * dy;
+    }
+}
+
+// cregistration.hpp:2590-2628
+static void pt2pl_residual(const Cloud &S, const Cloud &T, const Corrs &C, const double x[6], double &VTPV, int &nobs) {
+    for (size_t i = 0; i < C.size(); ++i) {
+        const Pt &p = S[C[i].q];
+        const Pt &q = T[C[i].m];
+        float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+        float ntx = q.nx, nty = q.ny, ntz = q.nz;
+        float a = ntz * py - nty * pz;
+        float b = ntx * pz - ntz * px;
+        float c = nty * px - ntx * py;
+        float d = ntx * qx + nty * qy + ntz * qz - ntx * px - nty * py - ntz * pz;
+        float residual = ntx * x[0] + nty * x[1] + ntz * x[2] + a * x[3] + b * x[4] + c * x[5] - d;
+        VTPV += C[i].dw * residual * residual;
+        nobs++;
+    }
+}
+// cregistration.hpp:2631-2677
+static void pt2li_residual(const Cloud &S, const Cloud &T, const Corrs &C, const double x[6], double &VTPV, int &nobs) {
+    for (size_t i = 0; i < C.size(); ++i) {
+        const Pt &p = S[C[i].q];
+        const Pt &q = T[C[i].m];
+        float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+        float vx = q.nx, vy = q.ny, vz = q.nz;
+        float dx = px - qx, dy = py - qy, dz = pz - qz;
+        double A[3][6] = {{0, vz, -vy, -vz * pz - vy * py, vy * px, vz * px},
+                          {-vz, 0, vx, vx * py, -vx * px - vz * pz, vz * py},
+                          {vy, -vx, 0, vx * pz, vy * pz, -vy * py - vx * px}};
+        double bv[3] = {-vz * dy + vy * dz, -vx * dz + vz * dx, -vy * dx + vx * dy};
+        double r[3];
+        for (int k = 0; k < 3; ++k) { // [ORDER] Eigen 3x6 * 6x1 product, sequential here
+            double s = A[k][0] * x[0];
+            for (int j = 1; j < 6; ++j) s += A[k][j] * x[j];
+            r[k] = s - bv[k];
+        }
+        VTPV += C[i].dw * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        nobs += 3;
+    }
+}
+// cregistration.hpp:2546-2588 (the weight read here is the squared NN distance: Q2)
+static void pt2pt_residual(const Cloud &S, const Cloud &T, const Corrs &C, const double x[6], double &VTPV, int &nobs) {
+    for (size_t i = 0; i < C.size(); ++i) {
+        const Pt &p = S[C[i].q];
+        const Pt &q = T[C[i].m];
+        float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+        float dx = px - qx, dy = py - qy, dz = pz - qz;
+        double A[3][6] = {{1, 0, 0, 0, pz, -py}, {0, 1, 0, -pz, 0, px}, {0, 0, 1, py, -px, 0}};
+        double bv[3] = {-dx, -dy, -dz};
+        double r[3];
+        for (int k = 0; k < 3; ++k) {
+            double s = A[k][0] * x[0];
+            for (int j = 1; j < 6; ++j) s += A[k][j] * x[j];
+            r[k] = s - bv[k];
+        }
+        VTPV += C[i].dw * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        nobs += 3;
+    }
+}
+
+// cregistration.hpp:2740-2764 construct_trans_a
+static Mat4 construct_trans_a(double tx, double ty, double tz, double alpha, double beta, double gamma) {
+    Mat4 T;
+    std::memset(&T, 0, sizeof(T));
+    T.a[0][0] = std::cos(gamma) * std::cos(beta);
+    T.a[0][1] = -std::sin(gamma) * std::cos(alpha) + std::cos(gamma) * std::sin(beta) * std::sin(alpha);
+    T.a[0][2] = std::sin(gamma) * std::sin(alpha) + std::cos(gamma) * std::sin(beta) * std::cos(alpha);
+    T.a[1][0] = std::sin(gamma) * std::cos(beta);
+    T.a[1][1] = std::cos(gamma) * std::cos(alpha) + std::sin(gamma) * std::sin(beta) * std::sin(alpha);
+    T.a[1][2] = -std::cos(gamma) * std::sin(alpha) + std::sin(gamma) * std::sin(beta) * std::cos(alpha);
+    T.a[2][0] = -std::sin(beta);
+    T.a[2][1] = std::cos(beta) * std::sin(alpha);
+    T.a[2][2] = std::cos(beta) * std::cos(alpha);
+    T.a[0][3] = tx;
+    T.a[1][3] = ty;
+    T.a[2][3] = tz;
+    T.a[3][3] = 1.0;
+    return T;
+}
+
+// cregistration.hpp:2795-2836 get_quat_euler_jacobi (xyz sequence); half-angle sines/cosines in FLOAT
+static void quat_euler_jacobi(const double e[3], double J[3][3]) {
+    float sr = std::sin(0.5 * e[0]), sp = std::sin(0.5 * e[1]), sy = std::sin(0.5 * e[2]);
+    float cr = std::cos(0.5 * e[0]), cp = std::cos(0.5 * e[1]), cy = std::cos(0.5 * e[2]);
+    J[0][0] = 0.5 * (cr * cp * cy + sr * sp * sy);
+    J[0][1] = 0.5 * (-sr * sp * cy - cr * cp * sy);
+    J[0][2] = 0.5 * (-sr * cp * sy - cr * sp * cy);
+    J[1][0] = 0.5 * (-sr * sp * cy + cr * cp * sy);
+    J[1][1] = 0.5 * (cr * cp * cy - sr * sp * sy);
+    J[1][2] = 0.5 * (-cr * sp * sy + sr * cp * cy);
+    J[2][0] = 0.5 * (-sr * cp * sy - cr * sp * cy);
+    J[2][1] = 0.5 * (-cr * sp * sy - sr * cp * cy);
+    J[2][2] = 0.5 * (cr * cp * cy + sr * sp * sy);
+}
+
+struct Timers {
+    double kd_build = 0, update = 0, search = 0, estimate = 0, total = 0;
+};
+
+// cregistration.hpp:1701-1835 determine_corres (nearest-neighbour branch)
+static bool determine_corres(Cloud &S, const Cloud &T, const KdTree &tree, float dis_thre, Corrs &Corr_f,
+                             bool normal_check, float angle_thre_degree, int nn_threads) {
+    const int K_min = 3;
+    const float filter_dis_times = 2.5f;
+    const int K_filter_distant_point = 500;
+    if (!((int)S.size() >= K_min && (int)T.size() >= K_min)) return false;
+
+    // CorrespondenceEstimation::determineCorrespondences(Corr, filter_dis_times * dis_thre) [3P]
+    const double max_distance = filter_dis_times * dis_thre; // float product widened
+    const double max_dist_sqr = max_distance * max_distance;
+    const int ns = (int)S.size();
+    std::vector<int> nn_i(ns);
+    std::vector<float> nn_d(ns);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nn_threads) if (nn_threads > 1)
+    for (int i = 0; i < ns; ++i) {
+        float q[3] = {S[i].x, S[i].y, S[i].z};
+        int j = -1;
+        float d2 = 0;
+        tree.nearest(q, j, d2);
+        nn_i[i] = j;
+        nn_d[i] = d2;
+    }
+    Corrs Cc;
+    Cc.reserve(ns);
+    for (int i = 0; i < ns; ++i) {
+        if (nn_i[i] < 0) continue;
+        if (nn_d[i] > max_dist_sqr) continue;
+        Corr c = {i, nn_i[i], nn_d[i]};
+        Cc.push_back(c);
+    }
+
+    // :1755-1792 duplicate check + permanent source shrinking
+    if ((int)S.size() >= K_filter_distant_point) {
+        std::vector<unsigned int> table(T.size(), 0);
+        Cloud Sf;
+        Sf.reserve(Cc.size());
+        Corrs kept;
+        kept.reserve(Cc.size());
+        int count = 0;
+        for (size_t k = 0; k < Cc.size(); ++k) {
+            int s_index = Cc[k].q, t_index = Cc[k].m;
+            if (table[t_index] > 0) continue; // erased
+            table[t_index]++;
+            Sf.push_back(S[s_index]);
+            Corr c = Cc[k];
+            c.q = count;
+            kept.push_back(c);
+            count++;
+        }
+        Cc.swap(kept);
+        S.swap(Sf);
+    }
+
+    // :1794-1796 CorrespondenceRejectorDistance [3P]: max_distance_ = d*d (float); keep distance < max
+    const float max_rej = dis_thre * dis_thre;
+    Corr_f.clear();
+    Corr_f.reserve(Cc.size());
+    for (size_t k = 0; k < Cc.size(); ++k)
+        if (Cc[k].dw < max_rej) Corr_f.push_back(Cc[k]);
+
+    // :1798-1830 normal / principal-direction consistency
+    if (normal_check) {
+        const double cos_thre = std::cos(angle_thre_degree / 180.0 * M_PI);
+        Corrs out;
+        out.reserve(Corr_f.size());
+        for (size_t k = 0; k < Corr_f.size(); ++k) {
+            const Pt &p = S[Corr_f[k].q];
+            const Pt &q = T[Corr_f[k].m];
+            double dot = (double)p.nx * (double)q.nx + (double)p.ny * (double)q.ny + (double)p.nz * (double)q.nz; // [ORDER] Eigen 3-dot
+            float cos_intersection_angle = std::abs(dot);
+            if (cos_intersection_angle < cos_thre) continue;
+            out.push_back(Corr_f[k]);
+        }
+        Corr_f.swap(out);
+    }
+    return true;
+}
+
+static void load_cloud(const mulls_cloud_view &v, Cloud &c) {
+    c.resize(v.n);
+    for (size_t i = 0; i < v.n; ++i) {
+        const float *f = v.aos48 + 12 * i;
+        Pt p = {f[0], f[1], f[2], f[4], f[5], f[6], f[8]};
+        c[i] = p;
+    }
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// cregistration.hpp:1114-1440 mm_lls_icp
+// threads: 0 => reference-shaped (3 OpenMP sections for tree build and search, :1209-1230, :1268-1288)
+//          n>0 => classes in sequence, the NN loop of each class split over n threads ("all cores")
+// ---------------------------------------------------------------------------------------------
+static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view srcv[6], const mulls_icp_params &P,
+                      const double init_guess_rm[16], mulls_icp_result *out, mulls_icp_trace *trace, int threads,
+                      Timers *tm) {
+    const double t_begin = now_s();
+    enum { G = 0, PL = 1, F = 2, B = 3, R = 4, V = 5 };
+    int process_code = 0;
+    const int min_total_corr_num = 40;
+    const int min_neccessary_corr_num = 20;
+    float neccessary_corr_ratio = 1.0;
+
+    Mat4 initial_guess;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) initial_guess.a[i][j] = init_guess_rm[4 * i + j];
+    Mat6 cofactor, information;
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) cofactor.a[i][j] = information.a[i][j] = (i == j) ? 1.0 : 0.0;
+    double sigma_square_post = 1.0;
+    Mat4 TempTran = ident4();
+    double transform_x[6] = {0, 0, 0, 0, 0, 0};
+
+    float dis_thre[6];
+    for (int c = 0; c < 6; ++c) dis_thre[c] = P.dis_thre_unit;
+    float max_bearable_translation = 2.0 * P.dis_thre_unit;
+    float converge_rotation = P.converge_rotation_d / 180.0 * M_PI;
+    float max_bearable_rotation = P.max_bearable_rotation_d / 180.0 * M_PI;
+    bool used[6];
+    for (int c = 0; c < 6; ++c) used[c] = (P.used_feature_type[c] == '1');
+
+    // :1180-1181 clone
+    Cloud tc[6], sc[6];
+    for (int c = 0; c < 6; ++c) {
+        load_cloud(tgtv[c], tc[c]);
+        load_cloud(srcv[c], sc[c]);
+    }
+    // :1183 apply initial guess
+    for (int c = 0; c < 6; ++c) transform_cloud(sc[c], initial_guess);
+
+    // :1186-1188, :2894-2922 intersection filter (utility.hpp:858-890)
+    if (P.apply_intersection_filter && !P.apply_motion_undistortion_while_registration) {
+        Bounds bb[3] = {cloud_bbx(sc[G]), cloud_bbx(sc[PL]), cloud_bbx(sc[F])};
+        Bounds m = {1.7976931348623157e308,  1.7976931348623157e308,  1.7976931348623157e308,
+                    -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+        for (int i = 0; i < 3; ++i) {
+            m.min_x = std::min(m.min_x, bb[i].min_x);
+            m.min_y = std::min(m.min_y, bb[i].min_y);
+            m.min_z = std::min(m.min_z, bb[i].min_z);
+            m.max_x = std::max(m.max_x, bb[i].max_x);
+            m.max_y = std::max(m.max_y, bb[i].max_y);
+            m.max_z = std::max(m.max_z, bb[i].max_z);
+        }
+        const float pad = 1.0f;
+        const double *tb = P.target_bound;
+        Bounds ib;
+        ib.min_x = std::max(tb[0], m.min_x) - pad;
+        ib.min_y = std::max(tb[1], m.min_y) - pad;
+        ib.min_z = std::max(tb[2], m.min_z) - pad;
+        ib.max_x = std::min(tb[3], m.max_x) + pad;
+        ib.max_y = std::min(tb[4], m.max_y) + pad;
+        ib.max_z = std::min(tb[5], m.max_z) + pad;
+        for (int c = 0; c < 6; ++c) bbx_filter(tc[c], ib);
+        for (int c = 0; c < 6; ++c) bbx_filter(sc[c], ib);
+    }
+
+    // :1195-1201
+    int source_feature_points_count = 0;
+    if (used[PL]) source_feature_points_count += (int)sc[PL].size();
+    if (used[F]) source_feature_points_count += (int)sc[F].size();
+    if (used[B]) source_feature_points_count += (int)sc[B].size();
+
+    Corrs corrs[6];
+
+    // :1209-1232 kd-trees on the target clones
+    double t0 = now_s();
+    KdTree tree[6];
+    if (threads == 0) {
+#pragma omp parallel sections num_threads(3)
+        {
+#pragma omp section
+            {
+                if (used[G] && tc[G].size() > 0) tree[G].build(tc[G]);
+                if (used[R] && tc[R].size() > 0) tree[R].build(tc[R]);
+            }
+#pragma omp section
+            {
+                if (used[PL] && tc[PL].size() > 0) tree[PL].build(tc[PL]);
+                if (used[B] && tc[B].size() > 0) tree[B].build(tc[B]);
+            }
+#pragma omp section
+            {
+                if (used[F] && tc[F].size() > 0) tree[F].build(tc[F]);
+            }
+        }
+    } else {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
+        for (int c = 0; c < 5; ++c)
+            if (used[c] && tc[c].size() > 0) tree[c].build(tc[c]);
+    }
+    if (used[V] && tc[V].size() > 0) tree[V].build(tc[V]);
+    if (tm) tm->kd_build += now_s() - t0;
+
+    const float nb = P.normal_bearing;
+    const std::string ws(P.weight_strategy);
+    int iters_entered = 0;
+    if (trace) trace->n_iter = 0;
+
+    for (int i = 0; i < P.max_iter_num; i++) {
+        iters_entered = i + 1;
+        double t1 = now_s();
+        // :1260 incremental in-place update of the float source clouds
+        for (int c = 0; c < 6; ++c) transform_cloud(sc[c], TempTran);
+        double t2 = now_s();
+        if (tm) tm->update += t2 - t1;
+
+        // :1268-1292
+        if (threads == 0) {
+#pragma omp parallel sections num_threads(3)
+            {
+#pragma omp section
+                {
+                    if (used[G] && sc[G].size() > 0)
+                        if (!determine_corres(sc[G], tc[G], tree[G], dis_thre[G], corrs[G], true, nb, 1)) corrs[G].clear();
+                }
+#pragma omp section
+                {
+                    if (used[PL] && sc[PL].size() > 0)
+                        if (!determine_corres(sc[PL], tc[PL], tree[PL], dis_thre[PL], corrs[PL], true, nb, 1)) corrs[PL].clear();
+                }
+#pragma omp section
+                {
+                    if (used[F] && sc[F].size() > 0)
+                        if (!determine_corres(sc[F], tc[F], tree[F], dis_thre[F], corrs[F], true, nb, 1)) corrs[F].clear();
+                    if (used[B] && sc[B].size() > 0)
+                        if (!determine_corres(sc[B], tc[B], tree[B], dis_thre[B], corrs[B], true, nb, 1)) corrs[B].clear();
+                }
+            }
+        } else {
+            for (int c = 0; c < 4; ++c)
+                if (used[c] && sc[c].size() > 0)
+                    if (!determine_corres(sc[c], tc[c], tree[c], dis_thre[c], corrs[c], true, nb, threads)) corrs[c].clear();
+        }
+        if (used[R] && sc[R].size() > 0)
+            if (!determine_corres(sc[R], tc[R], tree[R], dis_thre[R], corrs[R], true, nb, threads ? threads : 1)) corrs[R].clear();
+        if (used[V] && sc[V].size() > 0)
+            if (!determine_corres(sc[V], tc[V], tree[V], dis_thre[V], corrs[V], false, nb, threads ? threads : 1)) corrs[V].clear();
+        // Q12: where the reference would re-use a stale list (class emptied, or
+        // < 3 points) the oracle defines "class contributes nothing this iteration".
+        for (int c = 0; c < 6; ++c)
+            if (!(used[c] && sc[c].size() > 0)) corrs[c].clear();
+        double t3 = now_s();
+        if (tm) tm->search += t3 - t2;
+
+        if (trace && i < MULLS_MAX_TRACE_ITERS) {
+            trace->n_iter = i + 1;
+            for (int c = 0; c < 6; ++c) {
+                trace->n_corr[i][c] = (uint32_t)corrs[c].size();
+                trace->n_src[i][c] = (uint32_t)sc[c].size();
+            }
+            std::memset(trace->atpa[i], 0, sizeof(trace->atpa[i]));
+            std::memset(trace->atpb[i], 0, sizeof(trace->atpb[i]));
+            std::memset(trace->x[i], 0, sizeof(trace->x[i]));
+        }
+
+        // :1301-1311
+        int total_corr_num = 0;
+        for (int c = 0; c < 6; ++c) total_corr_num += (int)corrs[c].size();
+        int neccessary_corr_num = (int)(corrs[PL].size() + corrs[B].size() + corrs[F].size());
+        neccessary_corr_ratio = 1.0 * neccessary_corr_num / source_feature_points_count;
+        if (total_corr_num < min_total_corr_num || neccessary_corr_num < min_neccessary_corr_num ||
+            neccessary_corr_ratio < P.min_neccessary_corr_ratio) {
+            process_code = -2;
+            TempTran = ident4();
+            break;
+        }
+
+        // :1314-1315, :1855-1866
+        for (int c = 0; c < 6; ++c)
+            dis_thre[c] = ((1.0 * dis_thre[c] / P.dis_thre_update_rate) > (P.dis_thre_min))
+                              ? (1.0 * dis_thre[c] / P.dis_thre_update_rate)
+                              : (P.dis_thre_min);
+
+        // :1869-1967 multi_metrics_lls_tran_estimation
+        Normal N;
+        std::memset(&N, 0, sizeof(N));
+        float w_ground = 1.0, w_facade = 1.0, w_roof = 1.0, w_pillar = 1.0, w_beam = 1.0, w_vertex = 1.0;
+        int m1 = (int)(corrs[G].size() + corrs[R].size());
+        int m2 = (int)corrs[F].size();
+        int m3 = (int)corrs[PL].size();
+        int m4 = (int)corrs[B].size();
+        if (ws.size() > 0 && ws[0] == '1') {
+            w_ground = ((0.01) > (P.z_xy_balanced_ratio * (m2 + 2 * m3 - m4) / (0.0001 + 2.0 * m1)))
+                           ? (0.01)
+                           : (P.z_xy_balanced_ratio * (m2 + 2 * m3 - m4) / (0.0001 + 2.0 * m1));
+            w_roof = w_ground;
+        }
+        bool dist_weight = false, residual_weight = false, intensity_weight = false;
+        const int iter_thre = 2;
+        if (ws.size() > 1 && ws[1] == '1' && i > iter_thre) residual_weight = true;
+        if (ws.size() > 2 && ws[2] == '1') dist_weight = true;
+        if (ws.size() > 3 && ws[3] == '1') intensity_weight = true;
+
+        pt2pl_sum(sc[G], tc[G], corrs[G], N, i, w_ground, dist_weight, residual_weight, intensity_weight, P.pt2pl_residual_window);
+        pt2pl_sum(sc[F], tc[F], corrs[F], N, i, w_facade, dist_weight, residual_weight, intensity_weight, P.pt2pl_residual_window);
+        pt2pl_sum(sc[R], tc[R], corrs[R], N, i, w_roof, dist_weight, residual_weight, intensity_weight, P.pt2pl_residual_window);
+        pt2li_sum(sc[PL], tc[PL], corrs[PL], N, i, w_pillar, dist_weight, residual_weight, intensity_weight, P.pt2li_residual_window);
+        pt2li_sum(sc[B], tc[B], corrs[B], N, i, w_beam, dist_weight, residual_weight, intensity_weight, P.pt2li_residual_window);
+        pt2pt_sum(sc[V], tc[V], corrs[V], N, i, w_vertex, dist_weight, residual_weight, intensity_weight, P.pt2pt_residual_window);
+
+        Mat6 ATPA;
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c <= r; ++c) ATPA.a[r][c] = ATPA.a[c][r] = N.A[r][c]; // :1924-1938 lower -> upper
+        Mat6 inv;
+        inverse6(ATPA, inv);
+        double x[6];
+        for (int r = 0; r < 6; ++r) {
+            double s = inv.a[r][0] * N.b[0];
+            for (int c = 1; c < 6; ++c) s += inv.a[r][c] * N.b[c];
+            x[r] = s;
+        }
+        for (int r = 0; r < 6; ++r) transform_x[r] = x[r];
+        double J[3][3];
+        quat_euler_jacobi(&x[3], J);
+        cofactor = inv;
+        {
+            double C33[3][3], C03[3][3], C30[3][3], tmp[3][3];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    C33[r][c] = inv.a[3 + r][3 + c];
+                    C03[r][c] = inv.a[r][3 + c];
+                    C30[r][c] = inv.a[3 + r][c];
+                }
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) tmp[r][c] = J[r][0] * C33[0][c] + J[r][1] * C33[1][c] + J[r][2] * C33[2][c];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    cofactor.a[3 + r][3 + c] = tmp[r][0] * J[c][0] + tmp[r][1] * J[c][1] + tmp[r][2] * J[c][2];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    cofactor.a[r][3 + c] = C03[r][0] * J[c][0] + C03[r][1] * J[c][1] + C03[r][2] * J[c][2];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    cofactor.a[3 + r][c] = J[r][0] * C30[0][c] + J[r][1] * C30[1][c] + J[r][2] * C30[2][c];
+        }
+        if (trace && i < MULLS_MAX_TRACE_ITERS) {
+            for (int r = 0; r < 6; ++r) {
+                for (int c = 0; c < 6; ++c) trace->atpa[i][6 * r + c] = ATPA.a[r][c];
+                trace->atpb[i][r] = N.b[r];
+                trace->x[i][r] = x[r];
+            }
+        }
+
+        // :1333
+        TempTran = construct_trans_a(x[0], x[1], x[2], x[3], x[4], x[5]);
+        double t4 = now_s();
+        if (tm) tm->estimate += t4 - t3;
+
+        // :1344-1354
+        double ts_norm = std::sqrt(TempTran.a[0][3] * TempTran.a[0][3] + TempTran.a[1][3] * TempTran.a[1][3] +
+                                   TempTran.a[2][3] * TempTran.a[2][3]);
+        double rs_angle = rotation_angle(TempTran);
+        if (ts_norm > max_bearable_translation || std::abs(rs_angle) > max_bearable_rotation) {
+            process_code = -1;
+            TempTran = ident4();
+            break;
+        }
+
+        // :1357-1395
+        if (i == P.max_iter_num - 1 ||
+            (i > 2 && ts_norm < P.converge_translation && std::abs(rs_angle) < converge_rotation)) {
+            double VTPV = 0;
+            int nobs = 0;
+            pt2pl_residual(sc[G], tc[G], corrs[G], transform_x, VTPV, nobs);
+            pt2pl_residual(sc[F], tc[F], corrs[F], transform_x, VTPV, nobs);
+            pt2pl_residual(sc[R], tc[R], corrs[R], transform_x, VTPV, nobs);
+            pt2li_residual(sc[PL], tc[PL], corrs[PL], transform_x, VTPV, nobs);
+            pt2li_residual(sc[B], tc[B], corrs[B], transform_x, VTPV, nobs);
+            pt2pt_residual(sc[V], tc[V], corrs[V], transform_x, VTPV, nobs);
+            sigma_square_post = VTPV / (nobs - 6);
+            const double sigma_thre = P.sigma_thre;
+            process_code = (std::sqrt(sigma_square_post) < sigma_thre) ? 1 : -3;
+            Mat6 cinv;
+            inverse6(cofactor, cinv);
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) information.a[r][c] = (1.0 / sigma_square_post) * cinv.a[r][c];
+            break;
+        }
+        // :1400
+        initial_guess = mul4(TempTran, initial_guess);
+    }
+    // :1403
+    initial_guess = mul4(TempTran, initial_guess);
+
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) out->T[4 * r + c] = initial_guess.a[r][c];
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) out->info[6 * r + c] = information.a[r][c];
+    out->sigma = std::sqrt(sigma_square_post);
+    out->confidence = neccessary_corr_ratio;
+    out->code = process_code;
+    out->iters = iters_entered;
+    for (int c = 0; c < 6; ++c) {
+        out->n_corr[c] = (uint32_t)corrs[c].size();
+        out->n_src[c] = (uint32_t)sc[c].size();
+    }
+    if (tm) tm->total += now_s() - t_begin;
+    return process_code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pca.hpp:294-354 get_pc_pca_feature + :390-434 get_pca_feature, with
+// pcl::KdTreeFLANN::radiusSearch [3P] (all d2 <= r*r, ascending, truncated to max_nn, self included)
+// and pcl::PCA [3P] (centroid; cov = sum (p-mu)(p-mu)^T / (n-1) in float; eigen-pairs descending;
+// third eigenvector replaced by col0 x col1). The eigen-decomposition here is a cyclic Jacobi in
+// double on the float covariance; Eigen's SelfAdjointEigenSolver<Matrix3f> (tridiagonal QL) agrees
+// to float rounding, which is the tolerance the PCA parity tests state.
+// ---------------------------------------------------------------------------------------------
+static void jacobi_eig3(const double Ain[3][3], double w[3], double V[3][3]) {
+    double A[3][3];
+    std::memcpy(A, Ain, sizeof(A));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 50; ++sweep) {
+        double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == 0.0) continue;
+                double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                double t = ((theta >= 0) ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+} // namespace
+
+extern "C" {
+
+// Run one registration on the CPU. threads: 0 = reference-shaped (3 OpenMP sections), n>0 = n threads.
+// timings (may be NULL): [kd_build, source_update, corr_search, estimation, total] seconds, accumulated.
+int orc_icp_run(const mulls_cloud_view tgt[6], const mulls_cloud_view src[6], const mulls_icp_params *params,
+                const double init_guess[16], mulls_icp_result *out, mulls_icp_trace *trace, int threads,
+                double *timings) {
+    Timers tm;
+    mm_lls_icp(tgt, src, *params, init_guess, out, trace, threads, &tm);
+    if (timings) {
+        timings[0] += tm.kd_build;
+        timings[1] += tm.update;
+        timings[2] += tm.search;
+        timings[3] += tm.estimate;
+        timings[4] += tm.total;
+    }
+    return 0;
+}
+
+// exact radius-bounded 1-NN for a whole cloud (checker for the NN kernel): out_idx[i] = -1 if the
+// nearest target is farther than max_dist (d2 > max_dist^2 in double), else its index; out_d2 = float d2.
+int orc_nn(const mulls_cloud_view tgt, const mulls_cloud_view src, double max_dist, int32_t *out_idx, float *out_d2) {
+    Cloud T, S;
+    load_cloud(tgt, T);
+    load_cloud(src, S);
+    KdTree tree;
+    tree.build(T);
+    const double md2 = max_dist * max_dist;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)S.size(); ++i) {
+        float q[3] = {S[i].x, S[i].y, S[i].z};
+        int j = -1;
+        float d2 = 0;
+        bool ok = tree.nearest(q, j, d2);
+        if (!ok || d2 > md2) {
+            out_idx[i] = -1;
+            out_d2[i] = d2;
+        } else {
+            out_idx[i] = j;
+            out_d2[i] = d2;
+        }
+    }
+    return 0;
+}
+
+// pca.hpp:294-354. Outputs as mulls_pca_out; points skipped by the stride get pt_num = 0.
+int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
+    Cloud C;
+    load_cloud(cloud, C);
+    const long n = (long)C.size();
+    const float r2 = radius * radius;
+    // brute force through a uniform grid (oracle: clarity over speed)
+    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+    for (long i = 0; i < n; ++i) {
+        mn[0] = std::min(mn[0], C[i].x);
+        mn[1] = std::min(mn[1], C[i].y);
+        mn[2] = std::min(mn[2], C[i].z);
+        mx[0] = std::max(mx[0], C[i].x);
+        mx[1] = std::max(mx[1], C[i].y);
+        mx[2] = std::max(mx[2], C[i].z);
+    }
+    const float h = radius * 1.0001f;
+    int dims[3];
+    for (int d = 0; d < 3; ++d) dims[d] = std::max(1, (int)std::floor((mx[d] - mn[d]) / h) + 1);
+    std::vector<std::vector<int>> cells((size_t)dims[0] * dims[1] * dims[2]);
+    auto cell_of = [&](const Pt &p, int c[3]) {
+        c[0] = std::min(dims[0] - 1, std::max(0, (int)std::floor((p.x - mn[0]) / h)));
+        c[1] = std::min(dims[1] - 1, std::max(0, (int)std::floor((p.y - mn[1]) / h)));
+        c[2] = std::min(dims[2] - 1, std::max(0, (int)std::floor((p.z - mn[2]) / h)));
+    };
+    for (long i = 0; i < n; ++i) {
+        int c[3];
+        cell_of(C[i], c);
+        cells[((size_t)c[2] * dims[1] + c[1]) * dims[0] + c[0]].push_back((int)i);
+    }
+    for (long i = 0; i < n; ++i) {
+        out->pt_num[i] = 0;
+        for (int d = 0; d < 3; ++d) out->eigenvalues[3 * i + d] = out->principal[3 * i + d] = out->normal[3 * i + d] = 0.f;
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < n; i += stride) {
+        int c[3];
+        cell_of(C[i], c);
+        std::vector<std::pair<float, int>> nb;
+        float q[3] = {C[i].x, C[i].y, C[i].z};
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    int cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
+                    if (cx < 0 || cy < 0 || cz < 0 || cx >= dims[0] || cy >= dims[1] || cz >= dims[2]) continue;
+                    const std::vector<int> &cell = cells[((size_t)cz * dims[1] + cy) * dims[0] + cx];
+                    for (size_t t = 0; t < cell.size(); ++t) {
+                        float d2 = KdTree::flann_l2(q, C[cell[t]]);
+                        if (d2 <= r2) nb.push_back(std::make_pair(d2, cell[t]));
+                    }
+                }
+        std::sort(nb.begin(), nb.end());
+        if (k > 0 && (int)nb.size() > k) nb.resize(k);
+        const int m = (int)nb.size();
+        out->pt_num[i] = m;
+        if (m <= 3) continue; // pca.hpp:396-397
+        // pcl::PCA [3P]: float centroid, float covariance / (n-1)
+        float mu[3] = {0, 0, 0};
+        for (int t = 0; t < m; ++t) {
+            mu[0] += C[nb[t].second].x;
+            mu[1] += C[nb[t].second].y;
+            mu[2] += C[nb[t].second].z;
+        }
+        mu[0] /= (float)m;
+        mu[1] /= (float)m;
+        mu[2] /= (float)m;
+        float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int t = 0; t < m; ++t) {
+            float d[3] = {C[nb[t].second].x - mu[0], C[nb[t].second].y - mu[1], C[nb[t].second].z - mu[2]};
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) cov[a][b] += d[a] * d[b];
+        }
+        double A[3][3], w[3], V[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) A[a][b] = (double)(cov[a][b] / (float)(m - 1));
+        jacobi_eig3(A, w, V);
+        int ord[3] = {0, 1, 2};
+        std::sort(ord, ord + 3, [&](int a, int b) { return w[a] > w[b]; });
+        double e0[3] = {V[0][ord[0]], V[1][ord[0]], V[2][ord[0]]};
+        double e1[3] = {V[0][ord[1]], V[1][ord[1]], V[2][ord[1]]};
+        double e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+        double n0 = std::sqrt(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]);
+        double n2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+        for (int d = 0; d < 3; ++d) {
+            out->eigenvalues[3 * i + d] = (float)w[ord[d]];
+            out->principal[3 * i + d] = (float)(e0[d] / n0);
+            out->normal[3 * i + d] = (float)(e2[d] / n2);
+        }
+    }
+    return 0;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+} // extern "C"

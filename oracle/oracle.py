@@ -1,0 +1,95 @@
+"""ctypes wrapper of oracle/libmulls_oracle.so (TEST INFRASTRUCTURE — never imported by mulls_b200/).
+
+PARITY UNPINNED: see the header of mulls_oracle.cpp. The oracle re-uses the POD structs of the
+public ABI (include/mulls_b200/abi.h via mulls_b200.abi) so that inputs/outputs are interchangeable
+with the CUDA path's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mulls_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmulls_oracle.so")
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mulls_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "mulls_b200", "abi.h")
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in (src, hdr) if os.path.exists(f))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        lib = C.CDLL(LIB_PATH)
+        lib.orc_icp_run.restype = C.c_int
+        lib.orc_icp_run.argtypes = [C.POINTER(abi.CloudView), C.POINTER(abi.CloudView), C.POINTER(abi.IcpParams),
+                                    C.POINTER(C.c_double), C.POINTER(abi.IcpResult), C.POINTER(abi.IcpTrace),
+                                    C.c_int, C.POINTER(C.c_double)]
+        lib.orc_nn.restype = C.c_int
+        lib.orc_nn.argtypes = [abi.CloudView, abi.CloudView, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        lib.orc_pca_features.restype = C.c_int
+        lib.orc_pca_features.argtypes = [abi.CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(abi.PcaOut)]
+        lib.orc_num_threads.restype = C.c_int
+        _LIB = lib
+    return _LIB
+
+
+def views(clouds):
+    arr = (abi.CloudView * abi.NUM_CLASSES)()
+    for c in range(abi.NUM_CLASSES):
+        arr[c] = abi.cloud_view(clouds[c])
+    return arr
+
+
+def icp_run(tgt, src, params: abi.IcpParams, init_guess: np.ndarray, threads: int = 0, want_trace: bool = True,
+            timings: np.ndarray | None = None):
+    """tgt/src: six (n,12) float32 arrays. threads: 0 = reference-shaped (3 OpenMP sections), n>0 = n threads.
+    Returns (result dict, trace dict or None)."""
+    lib = load()
+    res = abi.IcpResult()
+    trace = abi.IcpTrace() if want_trace else None
+    init = np.ascontiguousarray(init_guess, dtype=np.float64).reshape(16)
+    tptr = timings.ctypes.data_as(C.POINTER(C.c_double)) if timings is not None else None
+    lib.orc_icp_run(views(tgt), views(src), C.byref(params), init.ctypes.data_as(C.POINTER(C.c_double)),
+                    C.byref(res), C.byref(trace) if trace is not None else None, threads, tptr)
+    return abi.result_to_dict(res), (abi.trace_to_dict(trace) if trace is not None else None)
+
+
+def nn(tgt: np.ndarray, src: np.ndarray, max_dist: float):
+    lib = load()
+    idx = np.empty(src.shape[0], dtype=np.int32)
+    d2 = np.empty(src.shape[0], dtype=np.float32)
+    lib.orc_nn(abi.cloud_view(tgt), abi.cloud_view(src), float(max_dist),
+               idx.ctypes.data_as(C.POINTER(C.c_int32)), d2.ctypes.data_as(C.POINTER(C.c_float)))
+    return idx, d2
+
+
+def pca_features(cloud: np.ndarray, radius: float, k: int, stride: int = 1):
+    lib = load()
+    n = cloud.shape[0]
+    ev = np.zeros((n, 3), np.float32)
+    pr = np.zeros((n, 3), np.float32)
+    nr = np.zeros((n, 3), np.float32)
+    cnt = np.zeros(n, np.int32)
+    out = abi.PcaOut(ev.ctypes.data_as(C.POINTER(C.c_float)), pr.ctypes.data_as(C.POINTER(C.c_float)),
+                     nr.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+    lib.orc_pca_features(abi.cloud_view(cloud), float(radius), int(k), int(stride), C.byref(out))
+    return {"eigenvalues": ev, "principal": pr, "normal": nr, "pt_num": cnt}
+
+
+def num_threads() -> int:
+    return int(load().orc_num_threads())
