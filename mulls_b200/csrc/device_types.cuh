@@ -1,0 +1,125 @@
+// Device-side data model of the B200 registration path (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mulls_b200/abi.h"
+
+namespace mulls {
+
+constexpr int kNumClasses = MULLS_NUM_CLASSES;
+constexpr int kNumSegs = 2 * kNumClasses; // seg = side*6 + class; side 0 = target, 1 = source
+constexpr int kIterBlock = 128;           // threads (= source points) per iteration-kernel block
+constexpr int kIngestBlock = 256;         // input points per ingest block
+constexpr int kTerms = 28;                // 21 lower-tri ATPA + 6 ATPb (+1 pad) per class partial
+constexpr int kMaxLevels = 12;
+constexpr int kCoordBits = 12;            // Morton bits per axis
+constexpr int kDedupMinSrc = 500;         // K_filter_distant_point (cregistration.hpp:1704)
+constexpr unsigned kClaimFree = 0x7f7f7f7fu;
+
+enum PairStatus : int { kRunning = 0, kNeedPosterior = 1, kDone = 2 };
+
+// Work descriptor of one block: which pair / segment (or class) and the first local point index.
+struct ChunkDesc {
+    uint32_t pair;
+    uint32_t seg;
+    uint32_t first;
+};
+
+// Immutable per-pair description, written by the host at upload time.
+struct PairConst {
+    // arguments of mm_lls_icp (cregistration.hpp:1114-1123) in device-friendly form
+    int max_iter;
+    int used[kNumClasses];
+    int w_balance, w_residual, w_dist, w_intensity; // weight_strategy[0..3]
+    float z_xy_ratio;
+    float win_pt2pt, win_pt2pl, win_pt2li;
+    float thre_unit, thre_min, thre_rate;
+    float conv_t, conv_r;       // converge_translation, converge_rotation (rad, float as :1163)
+    float max_t, max_r;         // max_bearable_translation / rotation (float as :1162,:1164)
+    float min_ratio;            // min_neccessary_corr_ratio
+    int apply_filter;
+    double cos_thre;            // cos(normal_bearing/180*pi), :1818
+    double sigma_thre;          // :2524
+    double init[16];            // initial guess, row-major
+    double tbound[6];           // block1->local_bound
+    // layout
+    uint32_t in_off[kNumSegs];  // offset (points) of each input cloud in the AoS48 staging array
+    uint32_t in_n[kNumSegs];
+    uint32_t tgt_base[kNumClasses]; // base of each class in the target SoA arrays (capacity = in_n)
+    uint32_t src_base[kNumClasses]; // base of each class in the source SoA arrays
+    uint32_t chunk_begin;            // iteration chunks of this pair: [chunk_begin, chunk_end)
+    uint32_t chunk_end;
+    uint32_t class_chunk_begin[kNumClasses + 1];
+    // source sharding (mulls_icp_run_sharded): global index base and global size of each source class
+    uint32_t src_index_base[kNumClasses];
+    uint32_t src_global_n[kNumClasses];
+    int sharded;
+};
+
+// Mutable per-pair state, lives in HBM for the whole run; updated by the last block of each phase.
+struct PairState {
+    double T_total[16]; // accumulated initial_guess (cregistration.hpp:1400,:1403)
+    double T_inc[16];   // TempTran to be applied at the start of the next iteration (:1260)
+    double x[6];
+    double cofactor[36];
+    double info[36];
+    double sigma2;
+    double ibb[6];      // intersection bounding box (utility.hpp:858-866)
+    float thre;         // dis_thre_* (all six evolve identically, :1155-1160, :1855-1866)
+    float confidence;
+    float origin[3];    // grid origin
+    float h0, inv_h0;
+    int n_levels;
+    int status, code, iter, iters_entered, final_buf;
+    int source_feature_points_count;
+    int n_src[kNumClasses];
+    int n_tgt[kNumClasses];
+    uint32_t n_corr[kNumClasses];      // |Corr_f| of the current iteration (atomics in k_resolve)
+    uint32_t n_corr_last[kNumClasses]; // same, frozen for the result
+    uint32_t seg_count[kNumSegs];      // valid points per segment after the intersection filter
+    uint32_t seg_start[kNumSegs];      // start of the segment in the sorted order
+    uint32_t hash_entries[kNumClasses]; // cells (all levels) of each target class
+    uint32_t hash_base[kNumClasses];    // table of each class inside the hash pool
+    uint32_t hash_mask[kNumClasses];    // capacity-1 (power of two, load factor <= 0.5)
+    uint32_t arrive_acc;               // block arrival counter of k_accumulate
+    uint32_t arrive_post;              // block arrival counter of k_posterior
+    int bb_src[6];                     // ordered-int encoded bbox of source ground/pillar/facade
+    int bb_tgt[6];                     // ordered-int encoded bbox of all target points
+    uint64_t alg_bytes;                // 28*(N_s,active + N_t) summed over executed iterations
+};
+
+struct HashEntry { // 16 B, one LDG.128 per probe
+    uint32_t key_lo, key_hi, start, count;
+};
+
+// All device pointers of a context, passed by value to the kernels.
+struct DeviceArrays {
+    const float4 *in_aos;   // input clouds, 3 float4 per point (pcl::PointXYZINormal)
+    float4 *stg_pos;        // staging (input order): x y z intensity  (source: initial guess applied)
+    float4 *stg_nrm;        // staging: nx ny nz orig_index(bits)
+    uint64_t *keys_a, *keys_b;
+    uint32_t *vals_a, *vals_b;
+    float4 *tgt_pos, *tgt_nrm;       // target SoA, Morton-sorted inside each (pair,class) slice
+    float4 *src_pos[2], *src_nrm[2]; // source SoA ping-pong
+    float *src_hint[2];              // previous NN distance^2 (search start-level hint)
+    int *nn_idx;                     // per source: matched target (index inside its class slice) or -1
+    float *nn_d2;
+    uint8_t *flags;                  // bit0 kept as source point, bit1 correspondence passes rejectors
+    int *corr_j;                     // compacted: matched target of a surviving correspondence, else -1
+    float *corr_w;                   // compacted: LLS weight stored back into Corr (:2114, :2256)
+    unsigned *claim;                 // duplicate_check_table (:1760) as an atomicMin table of source indices
+    HashEntry *hash;                 // pool; per-class tables are laid out on the device each run
+    uint32_t hash_pool_entries;
+    uint32_t *hash_used;             // [0] entries laid out this run, [1] overflow flag
+    uint32_t *blk_kept;              // per iteration chunk: sources kept by the block
+    double *partials;                // per iteration chunk: kTerms doubles
+    double *post_partials;           // per iteration chunk: VTPV, n_obs
+    PairConst *pc;
+    PairState *ps;
+    ChunkDesc *in_chunks;
+    ChunkDesc *it_chunks;
+    mulls_icp_trace *trace; // may be null
+};
+
+} // namespace mulls

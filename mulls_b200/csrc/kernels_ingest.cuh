@@ -1,0 +1,381 @@
+// Ingest phase: what mm_lls_icp does before its iteration loop (cregistration.hpp:1180-1232) —
+// clone + apply initial guess, intersection filter, and (instead of six FLANN kd-trees) a spatial
+// sort of every cloud plus a multi-level hashed grid over each target class.
+#pragma once
+#include "device_math.cuh"
+#include "device_types.cuh"
+
+namespace mulls {
+
+// ---- k_ingest_transform: AoS48 -> staging SoA; source gets the initial guess (double math, float store,
+//      pcl::transformPointCloudWithNormals semantics); bbox reductions for the intersection filter.
+__global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays A) {
+    const ChunkDesc cd = A.in_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    const uint32_t seg = cd.seg;
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = local < pc.in_n[seg];
+    const bool is_src = seg >= kNumClasses;
+    const int cls = seg % kNumClasses;
+    float x = 0, y = 0, z = 0;
+    if (valid) {
+        const size_t gi = (size_t)pc.in_off[seg] + local;
+        const float4 a = A.in_aos[3 * gi + 0]; // x y z _
+        const float4 b = A.in_aos[3 * gi + 1]; // nx ny nz _
+        const float4 c = A.in_aos[3 * gi + 2]; // intensity curvature _ _
+        x = a.x, y = a.y, z = a.z;
+        float nx = b.x, ny = b.y, nz = b.z;
+        if (is_src) {
+            const double *t = pc.init;
+            const double px = x, py = y, pz = z, qx = nx, qy = ny, qz = nz;
+            x = (float)(t[0] * px + t[1] * py + t[2] * pz + t[3]);
+            y = (float)(t[4] * px + t[5] * py + t[6] * pz + t[7]);
+            z = (float)(t[8] * px + t[9] * py + t[10] * pz + t[11]);
+            nx = (float)(t[0] * qx + t[1] * qy + t[2] * qz);
+            ny = (float)(t[4] * qx + t[5] * qy + t[6] * qz);
+            nz = (float)(t[8] * qx + t[9] * qy + t[10] * qz);
+        }
+        A.stg_pos[gi] = make_float4(x, y, z, c.x);
+        A.stg_nrm[gi] = make_float4(nx, ny, nz, __int_as_float((int)local));
+    }
+    // bbox: source ground/pillar/facade (cregistration.hpp:2912-2915) and all target points (grid extent)
+    const bool want = is_src ? (cls == MULLS_GROUND || cls == MULLS_PILLAR || cls == MULLS_FACADE) : true;
+    if (!want) return; // block-uniform
+    float mn[3] = {valid ? x : FLT_MAX, valid ? y : FLT_MAX, valid ? z : FLT_MAX};
+    float mx[3] = {valid ? x : -FLT_MAX, valid ? y : -FLT_MAX, valid ? z : -FLT_MAX};
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+        int *bb = is_src ? A.ps[cd.pair].bb_src : A.ps[cd.pair].bb_tgt;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&bb[d], float_to_ordered(mn[d]));
+            atomicMax(&bb[3 + d], float_to_ordered(mx[d]));
+        }
+    }
+}
+
+// ---- k_pair_setup: one thread per pair. Intersection bbox (utility.hpp:858-866, pad 1.0,
+//      cregistration.hpp:2907-2916), grid geometry, initial state (:1144-1164).
+__global__ void k_pair_setup(DeviceArrays A, int n_pairs, float h0_min) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairConst &pc = A.pc[p];
+    PairState &ps = A.ps[p];
+    double smin[3], smax[3], tmin[3], tmax[3];
+    for (int d = 0; d < 3; ++d) {
+        smin[d] = (double)ordered_to_float(ps.bb_src[d]);
+        smax[d] = (double)ordered_to_float(ps.bb_src[3 + d]);
+        tmin[d] = (double)ordered_to_float(ps.bb_tgt[d]);
+        tmax[d] = (double)ordered_to_float(ps.bb_tgt[3 + d]);
+    }
+    const double big = 1.7976931348623157e308;
+    double gmin[3], gmax[3];
+    if (pc.apply_filter) {
+        const float pad = 1.0f;
+        for (int d = 0; d < 3; ++d) {
+            // an empty source bbox stays at +/-FLT_MAX here (DBL_MAX in the reference): either way
+            // the intersection is empty and every point is filtered out.
+            double lo = (pc.tbound[d] > smin[d]) ? pc.tbound[d] : smin[d];
+            double hi = (pc.tbound[3 + d] < smax[d]) ? pc.tbound[3 + d] : smax[d];
+            ps.ibb[d] = lo - (double)pad;
+            ps.ibb[3 + d] = hi + (double)pad;
+            gmin[d] = fmax(tmin[d], ps.ibb[d]);
+            gmax[d] = fmin(tmax[d], ps.ibb[3 + d]);
+        }
+    } else {
+        for (int d = 0; d < 3; ++d) {
+            ps.ibb[d] = -big;
+            ps.ibb[3 + d] = big;
+            gmin[d] = tmin[d];
+            gmax[d] = tmax[d];
+        }
+    }
+    double ext = 0.0;
+    for (int d = 0; d < 3; ++d) {
+        if (!(gmax[d] >= gmin[d])) {
+            gmin[d] = 0.0;
+            gmax[d] = 0.0;
+        }
+        ext = fmax(ext, gmax[d] - gmin[d]);
+    }
+    const int ncell = 1 << kCoordBits;
+    float h0 = h0_min;
+    while ((ext + 8.0 * h0) * 1.001 > (double)h0 * (ncell - 4)) h0 *= 2.0f;
+    ps.h0 = h0;
+    ps.inv_h0 = 1.0f / h0; // power of two times h0_min: exact when h0_min is a power of two
+    for (int d = 0; d < 3; ++d) ps.origin[d] = (float)gmin[d] - 2.0f * h0;
+    // number of levels: the top level's guaranteed coverage 0.999*h must reach the largest search
+    // radius 2.5*dis_thre_unit (filter_dis_times, cregistration.hpp:1707)
+    const float rmax = 2.5f * pc.thre_unit * 1.0001f;
+    int L = 1;
+    while (L < kMaxLevels && 0.999f * h0 * (float)(1 << (L - 1)) < rmax) ++L;
+    ps.n_levels = L;
+
+    for (int i = 0; i < 16; ++i) {
+        ps.T_total[i] = pc.init[i];
+        ps.T_inc[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    }
+    for (int i = 0; i < 36; ++i) ps.cofactor[i] = ps.info[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 6; ++i) ps.x[i] = 0.0;
+    ps.sigma2 = 1.0;
+    ps.thre = pc.thre_unit;
+    ps.confidence = 1.0f;
+    ps.status = kRunning;
+    ps.code = 0;
+    ps.iter = 0;
+    ps.iters_entered = 0;
+    ps.final_buf = 0;
+    ps.alg_bytes = 0;
+    if (pc.max_iter <= 0) ps.status = kDone;
+}
+
+// ---- k_make_keys: intersection filter (cfilter.hpp:950-981: strictly inside) + 64-bit sort key
+//      [pair*12+seg | morton36(cell)]; filtered-out points sort to the very end.
+__global__ void __launch_bounds__(kIngestBlock) k_make_keys(DeviceArrays A) {
+    const ChunkDesc cd = A.in_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    PairState &ps = A.ps[cd.pair];
+    const uint32_t seg = cd.seg;
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = local < pc.in_n[seg];
+    bool inside = false;
+    if (valid) {
+        const size_t gi = (size_t)pc.in_off[seg] + local;
+        const float4 p = A.stg_pos[gi];
+        const double *b = ps.ibb;
+        inside = (double)p.x > b[0] && (double)p.x < b[3] && (double)p.y > b[1] && (double)p.y < b[4] &&
+                 (double)p.z > b[2] && (double)p.z < b[5];
+        uint64_t key = ~0ull;
+        if (inside) {
+            const int hi = (1 << kCoordBits) - 1;
+            int cx = (int)floorf((p.x - ps.origin[0]) * ps.inv_h0);
+            int cy = (int)floorf((p.y - ps.origin[1]) * ps.inv_h0);
+            int cz = (int)floorf((p.z - ps.origin[2]) * ps.inv_h0);
+            // targets are inside the grid by construction; sources may stick out (clamped: the
+            // source key only orders threads for locality, it never enters a distance decision)
+            cx = min(max(cx, 0), hi);
+            cy = min(max(cy, 0), hi);
+            cz = min(max(cz, 0), hi);
+            key = ((uint64_t)(cd.pair * kNumSegs + seg) << 36) | morton36((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+        }
+        A.keys_a[gi] = key;
+        A.vals_a[gi] = (uint32_t)gi;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, inside);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&ps.seg_count[seg], (unsigned)__popc(ballot));
+}
+
+// ---- k_seg_offsets: single block; exclusive scan of the valid counts in (pair, seg) order gives the
+//      start of every segment in the sorted array; also per-class sizes and :1195-1201.
+__global__ void k_seg_offsets(DeviceArrays A, int n_pairs) {
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warp_sums[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int total = n_pairs * kNumSegs;
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < total) v = A.ps[i / kNumSegs].seg_count[i % kNumSegs];
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0;
+            uint32_t wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            warp_sums[threadIdx.x] = wi - w; // exclusive
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+        if (i < total) A.ps[i / kNumSegs].seg_start[i % kNumSegs] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+        PairState &ps = A.ps[p];
+        const PairConst &pc = A.pc[p];
+        for (int c = 0; c < kNumClasses; ++c) {
+            ps.n_tgt[c] = (int)ps.seg_count[c];
+            ps.n_src[c] = (int)ps.seg_count[kNumClasses + c];
+            ps.n_corr[c] = 0;
+            ps.n_corr_last[c] = 0;
+        }
+        int cnt = 0;
+        if (pc.used[MULLS_PILLAR]) cnt += ps.n_src[MULLS_PILLAR];
+        if (pc.used[MULLS_FACADE]) cnt += ps.n_src[MULLS_FACADE];
+        if (pc.used[MULLS_BEAM]) cnt += ps.n_src[MULLS_BEAM];
+        ps.source_feature_points_count = cnt;
+    }
+}
+
+// ---- k_gather: sorted order -> final SoA slices (targets, and source buffer 0)
+__global__ void __launch_bounds__(256) k_gather(DeviceArrays A, const uint64_t *keys, const uint32_t *vals, uint32_t n_total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const uint64_t key = keys[i];
+    if (key == ~0ull) return;
+    const uint32_t sg = (uint32_t)(key >> 36);
+    const uint32_t pair = sg / kNumSegs, seg = sg % kNumSegs;
+    const PairConst &pc = A.pc[pair];
+    const uint32_t local = i - A.ps[pair].seg_start[seg];
+    const uint32_t v = vals[i];
+    const float4 pos = A.stg_pos[v];
+    const float4 nrm = A.stg_nrm[v];
+    if (seg < kNumClasses) {
+        const uint32_t d = pc.tgt_base[seg] + local;
+        A.tgt_pos[d] = pos;
+        A.tgt_nrm[d] = nrm;
+    } else {
+        const uint32_t d = pc.src_base[seg - kNumClasses] + local;
+        float4 n2 = nrm;
+        if (pc.sharded) n2.w = __int_as_float(__float_as_int(nrm.w) + (int)pc.src_index_base[seg - kNumClasses]);
+        A.src_pos[0][d] = pos;
+        A.src_nrm[0][d] = n2;
+        A.src_hint[0][d] = -1.0f;
+    }
+}
+
+// ---- hashed multi-level grid over a target class --------------------------------------------
+// key of the level-l cell containing Morton code m:  ((l+1) << 40) | (m >> 3l); 0 marks an empty slot.
+__device__ __forceinline__ uint64_t cell_key(int level, uint64_t code_at_level) {
+    return ((uint64_t)(level + 1) << 40) | code_at_level;
+}
+
+__device__ __forceinline__ void hash_insert(HashEntry *table, uint32_t mask, uint64_t key, uint32_t start) {
+    uint32_t slot = hash_key(key) & mask;
+    const unsigned long long packed = key;
+    while (true) {
+        unsigned long long *kp = reinterpret_cast<unsigned long long *>(&table[slot]);
+        unsigned long long old = atomicCAS(kp, 0ull, packed);
+        if (old == 0ull) {
+            table[slot].start = start;
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+__device__ __forceinline__ HashEntry *hash_find(HashEntry *table, uint32_t mask, uint64_t key) {
+    uint32_t slot = hash_key(key) & mask;
+    while (true) {
+        const unsigned long long k = *reinterpret_cast<const unsigned long long *>(&table[slot]);
+        if (k == key) return &table[slot];
+        if (k == 0ull) return nullptr;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// k_hash_build: thread i looks at the boundary between sorted elements i-1 and i. Where the Morton
+// prefix changes, a new cell starts at every level up to the highest differing one.
+//   mode 0: count the cells per (pair, class)          -> PairState::hash_entries
+//   mode 1: open cells: insert {key, start}
+//   mode 2: close cells: write the count of every cell the previous point ended
+__global__ void __launch_bounds__(256) k_hash_build(DeviceArrays A, const uint64_t *keys, uint32_t n_total, int mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i <= n_total;
+    const uint64_t kcur = (in_range && i < n_total) ? keys[i] : ~0ull;
+    const uint64_t kprev = (in_range && i > 0) ? keys[i - 1] : ~0ull;
+    const bool cur_t = kcur != ~0ull && ((uint32_t)(kcur >> 36) % kNumSegs) < kNumClasses;
+    const bool prev_t = kprev != ~0ull && ((uint32_t)(kprev >> 36) % kNumSegs) < kNumClasses;
+    const bool same_seg = cur_t && prev_t && (kcur >> 36) == (kprev >> 36);
+    const uint64_t mmask = (1ull << 36) - 1;
+    int top = kMaxLevels - 1; // highest level at which the cell changes
+    bool boundary = true;
+    if (same_seg) {
+        const uint64_t diff = (kcur ^ kprev) & mmask;
+        if (diff == 0) boundary = false; // same finest cell: no boundary at any level
+        else top = (63 - __clzll((long long)diff)) / 3;
+    }
+    if (mode == 0) {
+        uint32_t sg = cur_t ? (uint32_t)(kcur >> 36) : 0xffffffffu;
+        int cnt = 0;
+        if (cur_t && boundary) {
+            const int L = A.ps[sg / kNumSegs].n_levels;
+            cnt = min(top, L - 1) + 1;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, sg);
+        if (grp == 0xffffffffu) {
+            const int tot = __reduce_add_sync(0xffffffffu, cnt);
+            if ((threadIdx.x & 31) == 0 && tot > 0 && cur_t)
+                atomicAdd(&A.ps[sg / kNumSegs].hash_entries[sg % kNumSegs], (unsigned)tot);
+        } else if (cnt > 0) {
+            atomicAdd(&A.ps[sg / kNumSegs].hash_entries[sg % kNumSegs], (unsigned)cnt);
+        }
+        return;
+    }
+    if (!boundary || A.hash_used[1]) return;
+    if (mode == 1) {
+        if (!cur_t) return;
+        const uint32_t sg = (uint32_t)(kcur >> 36);
+        const uint32_t pair = sg / kNumSegs, cls = sg % kNumSegs;
+        const PairState &ps = A.ps[pair];
+        const int L = ps.n_levels;
+        const uint32_t local = i - ps.seg_start[cls];
+        HashEntry *table = A.hash + ps.hash_base[cls];
+        const uint64_t m = kcur & mmask;
+        for (int l = 0; l <= top && l < L; ++l) hash_insert(table, ps.hash_mask[cls], cell_key(l, m >> (3 * l)), local);
+    } else {
+        if (!prev_t) return;
+        const uint32_t sg = (uint32_t)(kprev >> 36);
+        const uint32_t pair = sg / kNumSegs, cls = sg % kNumSegs;
+        const PairState &ps = A.ps[pair];
+        const int L = ps.n_levels;
+        const uint32_t local_end = i - ps.seg_start[cls];
+        HashEntry *table = A.hash + ps.hash_base[cls];
+        const uint64_t m = kprev & mmask;
+        for (int l = 0; l <= top && l < L; ++l) {
+            HashEntry *e = hash_find(table, ps.hash_mask[cls], cell_key(l, m >> (3 * l)));
+            if (e) e->count = local_end - e->start;
+        }
+    }
+}
+
+// k_hash_layout: single block. Power-of-two table per (pair, class) with load factor <= 0.5, carved out
+// of the pool in order; flags overflow instead of writing out of bounds.
+__global__ void k_hash_layout(DeviceArrays A, int n_pairs) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t used = 0;
+    bool overflow = false;
+    for (int p = 0; p < n_pairs; ++p) {
+        PairState &ps = A.ps[p];
+        for (int c = 0; c < kNumClasses; ++c) {
+            uint32_t cap = 16;
+            while (cap < 2u * ps.hash_entries[c]) cap <<= 1;
+            if (used + cap > A.hash_pool_entries) {
+                overflow = true;
+                cap = 16;
+                ps.hash_base[c] = 0;
+                ps.hash_mask[c] = 0; // degenerate, never searched: the run is reported as failed
+                continue;
+            }
+            ps.hash_base[c] = (uint32_t)used;
+            ps.hash_mask[c] = cap - 1;
+            used += cap;
+        }
+    }
+    A.hash_used[0] = (uint32_t)used;
+    A.hash_used[1] = overflow ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_hash_clear(DeviceArrays A) {
+    const uint32_t used = A.hash_used[0];
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < used; i += gridDim.x * blockDim.x)
+        reinterpret_cast<uint4 *>(A.hash)[i] = z;
+}
+
+} // namespace mulls

@@ -1,0 +1,835 @@
+// Iteration phase: one pass of the loop body of mm_lls_icp (cregistration.hpp:1239-1401) as three
+// kernels over (pair, class, 128-source chunk) work items:
+//   k_search      I1+I2a  apply the previous increment to the source (:1260), exact radius-bounded
+//                         1-NN on the hashed grid (replaces the kd-tree query of :1745), claim the target
+//   k_resolve     I2b     duplicate check (:1755-1792), distance rejector (:1794-1796), normal check
+//                         (:1798-1830), per-class correspondence counts
+//   k_accumulate  I3-I9   order-preserving source compaction (:1776-1789), 21+6 normal-equation terms
+//                         per correspondence (:1976-2275), deterministic block->pair reduction; the last
+//                         block of a pair solves the 6x6 system and advances the pair state (:1301-1400)
+//   k_posterior   I8      residuals of the converged iteration (:2518-2677), sigma, information matrix
+#pragma once
+#include "device_math.cuh"
+#include "device_types.cuh"
+#include "kernels_ingest.cuh"
+
+namespace mulls {
+
+// ------------------------------------------------------------------------------------------------
+// exact 1-NN within radius on the multi-level hashed grid of one target class
+// ------------------------------------------------------------------------------------------------
+struct GridView {
+    const HashEntry *table;
+    uint32_t mask;
+    const float4 *pos; // class slice
+    const float4 *nrm; // class slice (w = original index, for tie-breaks)
+    float ox, oy, oz, h0, inv_h0;
+    int n_levels;
+};
+
+__device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t &start, uint32_t &count) {
+    uint32_t slot = hash_key(key) & g.mask;
+    while (true) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(&g.table[slot]));
+        const uint64_t k = (uint64_t)e.x | ((uint64_t)e.y << 32);
+        if (k == key) {
+            start = e.z;
+            count = e.w;
+            return true;
+        }
+        if (k == 0ull) return false;
+        slot = (slot + 1) & g.mask;
+    }
+}
+
+// Returns the nearest target (index within the class slice) under the total order (d2, original index),
+// among all targets with d2 <= r2_prune; exact for every target within the radius.
+__device__ __forceinline__ void nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
+                                          int start_level, float &best_d2, int &best_j) {
+    best_d2 = INFINITY;
+    best_j = -1;
+    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
+    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
+    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
+    const int L = g.n_levels;
+    int l = min(max(start_level, 0), L - 1);
+    for (;; ++l) {
+        const float hl = g.h0 * (float)(1 << l);
+        const int ncell = (1 << kCoordBits) >> l;
+        const int cx = c0x >> l, cy = c0y >> l, cz = c0z >> l;
+        const float margin = 1e-3f * g.h0;
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= ncell) continue;
+            const float zlo = g.oz + (float)z * hl - margin, zhi = g.oz + (float)(z + 1) * hl + margin;
+            const float ez = fmaxf(0.0f, fmaxf(zlo - pz, pz - zhi));
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= ncell) continue;
+                const float ylo = g.oy + (float)y * hl - margin, yhi = g.oy + (float)(y + 1) * hl + margin;
+                const float ey = fmaxf(0.0f, fmaxf(ylo - py, py - yhi));
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int x = cx + dx;
+                    if (x < 0 || x >= ncell) continue;
+                    const float xlo = g.ox + (float)x * hl - margin, xhi = g.ox + (float)(x + 1) * hl + margin;
+                    const float ex = fmaxf(0.0f, fmaxf(xlo - px, px - xhi));
+                    // a cell farther than the best so far (or than the radius) cannot change the result
+                    if (ex * ex + ey * ey + ez * ez > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                    uint32_t start, count;
+                    if (!probe(g, cell_key(l, morton36((uint32_t)x, (uint32_t)y, (uint32_t)z)), start, count)) continue;
+                    for (uint32_t j = start; j < start + count; ++j) {
+                        const float4 q = __ldg(&g.pos[j]);
+                        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
+                        if (d2 < best_d2) {
+                            best_d2 = d2;
+                            best_j = (int)j;
+                        } else if (d2 == best_d2 && (int)j != best_j) {
+                            const int oj = __float_as_int(__ldg(&g.nrm[j]).w);
+                            const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
+                            if (oj < ob) best_j = (int)j;
+                        }
+                    }
+                }
+            }
+        }
+        const float cover = 0.999f * hl; // every target closer than this has been examined
+        const float cover2 = cover * cover;
+        if (best_d2 <= cover2) break;   // the best found is the global nearest
+        if (cover2 >= r2_prune) break;  // whole search radius examined
+        if (l == L - 1) break;          // (n_levels is chosen so that the line above fires first)
+    }
+}
+
+// ---- k_search ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0) {
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    const PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning || A.hash_used[1]) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c];
+    const uint32_t local = cd.first + threadIdx.x;
+    if ((int)local >= ns) return;
+    const uint32_t gi = pc.src_base[c] + local;
+    float4 p = A.src_pos[buf][gi];
+    float4 n = A.src_nrm[buf][gi];
+    if (ps.iter > 0) {
+        // cregistration.hpp:1260 — incremental in-place update of the float source cloud
+        const double *t = ps.T_inc;
+        const double px = p.x, py = p.y, pz = p.z, qx = n.x, qy = n.y, qz = n.z;
+        p.x = (float)(t[0] * px + t[1] * py + t[2] * pz + t[3]);
+        p.y = (float)(t[4] * px + t[5] * py + t[6] * pz + t[7]);
+        p.z = (float)(t[8] * px + t[9] * py + t[10] * pz + t[11]);
+        n.x = (float)(t[0] * qx + t[1] * qy + t[2] * qz);
+        n.y = (float)(t[4] * qx + t[5] * qy + t[6] * qz);
+        n.z = (float)(t[8] * qx + t[9] * qy + t[10] * qz);
+        A.src_pos[buf][gi] = p;
+        A.src_nrm[buf][gi] = n;
+    }
+    int best_j = -1;
+    float best_d2 = INFINITY;
+    // determine_corres needs >= 3 points on both sides (:1727-1728)
+    if (pc.used[c] && ns >= 3 && nt >= 3) {
+        GridView g;
+        g.table = A.hash + ps.hash_base[c];
+        g.mask = ps.hash_mask[c];
+        g.pos = A.tgt_pos + pc.tgt_base[c];
+        g.nrm = A.tgt_nrm + pc.tgt_base[c];
+        g.ox = ps.origin[0], g.oy = ps.origin[1], g.oz = ps.origin[2];
+        g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
+        g.n_levels = ps.n_levels;
+        // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
+        const float max_distance_f = 2.5f * ps.thre;
+        const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
+        const float r2_prune = (float)max_dist_sqr * 1.0001f;
+        int sl = start_level0;
+        const float hint = A.src_hint[buf][gi];
+        if (hint >= 0.0f) {
+            // smallest level whose guaranteed coverage exceeds 1.3x the previous NN distance
+            const float need = 1.3f * sqrtf(hint) / (0.999f * g.h0);
+            sl = (need <= 1.0f) ? 0 : (ilogbf(need) + 1);
+        }
+        nn_search(g, p.x, p.y, p.z, r2_prune, sl, best_d2, best_j);
+        if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
+        if (best_j >= 0) {
+            // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
+            atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
+        }
+    }
+    A.nn_idx[gi] = best_j;
+    A.nn_d2[gi] = best_d2;
+}
+
+// ---- k_resolve ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) {
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c];
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ns;
+    const bool active = pc.used[c] && ns >= 3 && nt >= 3; // determine_corres ran for this class
+    const bool dedup = active && ns >= kDedupMinSrc;
+    bool kept = false, pass = false;
+    if (valid) {
+        const uint32_t gi = pc.src_base[c] + local;
+        const int j = A.nn_idx[gi];
+        const bool matched = active && j >= 0;
+        bool corr = matched;
+        kept = true;
+        if (dedup) {
+            const float4 n = A.src_nrm[buf][gi];
+            const bool winner = matched && A.claim[pc.tgt_base[c] + j] == (unsigned)__float_as_int(n.w);
+            kept = winner;
+            corr = winner;
+        }
+        if (corr) {
+            // CorrespondenceRejectorDistance: distance < thre*thre, both float (:1794-1796, PCL)
+            const float d2 = A.nn_d2[gi];
+            pass = d2 < ps.thre * ps.thre;
+            if (pass && c != MULLS_VERTEX) {
+                const float4 n = A.src_nrm[buf][gi];
+                const float4 m = A.tgt_nrm[pc.tgt_base[c] + j];
+                const double dot = (double)n.x * (double)m.x + (double)n.y * (double)m.y + (double)n.z * (double)m.z;
+                const float cos_angle = (float)fabs(dot);
+                if ((double)cos_angle < pc.cos_thre) pass = false;
+            }
+        }
+        A.flags[gi] = (uint8_t)((kept ? 1 : 0) | (pass ? 2 : 0));
+    }
+    const unsigned kb = __ballot_sync(0xffffffffu, kept);
+    const unsigned pb = __ballot_sync(0xffffffffu, pass);
+    __shared__ unsigned s_kept[kIterBlock / 32], s_pass[kIterBlock / 32];
+    if ((threadIdx.x & 31) == 0) {
+        s_kept[threadIdx.x >> 5] = __popc(kb);
+        s_pass[threadIdx.x >> 5] = __popc(pb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned k = 0, p = 0;
+        for (int w = 0; w < kIterBlock / 32; ++w) {
+            k += s_kept[w];
+            p += s_pass[w];
+        }
+        A.blk_kept[blockIdx.x] = k;
+        if (p) atomicAdd(&ps.n_corr[c], p);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-correspondence normal-equation terms. Layout of the kTerms doubles of a partial:
+//   [0..20]  lower triangle of ATPA, column by column: (0,0)(1,0)..(5,0)(1,1)(2,1)..(5,5)
+//   [21..26] ATPb
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void terms_pt2pl(const float4 p, const float pi, const float4 q, const float4 qn,
+                                            float weight, int iter_num, bool dist_w, bool resid_w, bool inten_w,
+                                            float window, double *t, float &w_out) {
+    // cregistration.hpp:2080-2151
+    const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+    const float ntx = qn.x, nty = qn.y, ntz = qn.z;
+    float w = weight;
+    const float a = ntz * py - nty * pz;
+    const float b = ntx * pz - ntz * px;
+    const float c = nty * px - ntx * py;
+    const float d = ntx * qx + nty * qy + ntz * qz - ntx * px - nty * py - ntz * pz;
+    const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
+    if (dist_w) w = w * weight_by_dist_adaptive(dist, iter_num);
+    if (resid_w) w = w * weight_by_residual(fabsf(d), window);
+    if (inten_w) w = w * weight_by_intensity((float)((double)pi + 0.0001), (float)((double)q.w + 0.0001));
+    w_out = w;
+    t[0] = w * ntx * ntx;
+    t[1] = w * ntx * nty;
+    t[2] = w * ntx * ntz;
+    t[3] = w * a * ntx;
+    t[4] = w * b * ntx;
+    t[5] = w * c * ntx;
+    t[6] = w * nty * nty;
+    t[7] = w * nty * ntz;
+    t[8] = w * a * nty;
+    t[9] = w * b * nty;
+    t[10] = w * c * nty;
+    t[11] = w * ntz * ntz;
+    t[12] = w * a * ntz;
+    t[13] = w * b * ntz;
+    t[14] = w * c * ntz;
+    t[15] = w * a * a;
+    t[16] = w * a * b;
+    t[17] = w * a * c;
+    t[18] = w * b * b;
+    t[19] = w * b * c;
+    t[20] = w * c * c;
+    t[21] = w * d * ntx;
+    t[22] = w * d * nty;
+    t[23] = w * d * ntz;
+    t[24] = w * d * a;
+    t[25] = w * d * b;
+    t[26] = w * d * c;
+}
+
+// diagonal index of column j in the lower-triangle layout
+__device__ __forceinline__ int diag_index(int j) {
+    const int d[6] = {0, 6, 11, 15, 18, 20};
+    return d[j];
+}
+
+__device__ __forceinline__ void terms_pt2li(const float4 p, const float pi, const float4 q, const float4 qv,
+                                            float weight, int iter_num, bool dist_w, bool resid_w, bool inten_w,
+                                            float window, double *t, float &w_out) {
+    // cregistration.hpp:2174-2271; only the diagonal of this block survives the symmetrisation (Q1)
+    const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+    const float vx = qv.x, vy = qv.y, vz = qv.z;
+    const float dx = px - qx, dy = py - qy, dz = pz - qz;
+    double Am[3][6], bv[3];
+    Am[0][0] = 0;
+    Am[0][1] = (double)(-vz);
+    Am[0][2] = (double)vy;
+    Am[0][3] = (double)(vy * py + vz * pz);
+    Am[0][4] = (double)(-vy * px);
+    Am[0][5] = (double)(-vz * px);
+    Am[1][0] = (double)vz;
+    Am[1][1] = 0;
+    Am[1][2] = (double)(-vx);
+    Am[1][3] = (double)(-vx * py);
+    Am[1][4] = (double)(vz * pz + vx * px);
+    Am[1][5] = (double)(-vz * py);
+    Am[2][0] = (double)(-vy);
+    Am[2][1] = (double)vx;
+    Am[2][2] = 0;
+    Am[2][3] = (double)(-vx * pz);
+    Am[2][4] = (double)(-vy * pz);
+    Am[2][5] = (double)(vx * px + vy * py);
+    bv[0] = (double)(-vy * dz + vz * dy);
+    bv[1] = (double)(-vz * dx + vx * dz);
+    bv[2] = (double)(-vx * dy + vy * dx);
+    const float ex = (float)fabs(bv[0]), ey = (float)fabs(bv[1]), ez = (float)fabs(bv[2]);
+    const float ed = sqrtf(ex * ex + ey * ey + ez * ez);
+    float wx = weight;
+    const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
+    if (dist_w) wx = wx * weight_by_dist_adaptive(dist, iter_num);
+    if (inten_w) wx = wx * weight_by_intensity((float)((double)pi + 0.0001), (float)((double)q.w + 0.0001));
+    if (resid_w) wx = wx * weight_by_residual(ed, window);
+    w_out = wx;
+    const double sw = (double)sqrtf(wx);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) Am[r][cc] = sw * Am[r][cc];
+        bv[r] = sw * bv[r];
+    }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) t[k] = 0.0;
+    const int dg[6] = {0, 6, 11, 15, 18, 20};
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        t[dg[j]] = Am[0][j] * Am[0][j] + (Am[1][j] * Am[1][j] + Am[2][j] * Am[2][j]);
+        t[21 + j] = Am[0][j] * bv[0] + (Am[1][j] * bv[1] + Am[2][j] * bv[2]);
+    }
+}
+
+__device__ __forceinline__ void terms_pt2pt(const float4 p, const float pi, const float4 q, float weight,
+                                            int iter_num, bool dist_w, bool resid_w, bool inten_w, float window,
+                                            double *t) {
+    // cregistration.hpp:1991-2058
+    const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+    const float dx = px - qx, dy = py - qy, dz = pz - qz;
+    float wx = weight;
+    const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
+    if (dist_w) wx = wx * weight_by_dist_adaptive(dist, iter_num);
+    if (resid_w) wx = wx * weight_by_residual(sqrtf(dx * dx + dy * dy + dz * dz), window);
+    if (inten_w) wx = wx * weight_by_intensity((float)((double)pi + 0.0001), (float)((double)q.w + 0.0001));
+    const float wy = wx, wz = wx;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) t[k] = 0.0;
+    t[0] = wx;
+    t[4] = wx * pz;
+    t[5] = (-wx * py);
+    t[6] = wy;
+    t[8] = (-wy * pz);
+    t[10] = wy * px;
+    t[11] = wz;
+    t[12] = wz * py;
+    t[13] = (-wz * px);
+    t[15] = wy * pz * pz + wz * py * py;
+    t[16] = (-wz * px * py);
+    t[17] = (-wy * px * pz);
+    t[18] = wx * pz * pz + wz * px * px;
+    t[19] = (-wx * py * pz);
+    t[20] = wx * py * py + wy * px * px;
+    t[21] = (-wx * dx);
+    t[22] = (-wy * dy);
+    t[23] = (-wz * dz);
+    t[24] = wy * pz * dy - wz * py * dz;
+    t[25] = wz * px * dz - wx * pz * dx;
+    t[26] = wx * py * dx - wy * px * dy;
+}
+
+// w_ground of cregistration.hpp:1892-1900 from the per-class correspondence counts
+__device__ __forceinline__ float balanced_ground_weight(const PairConst &pc, const uint32_t *n_corr) {
+    if (!pc.w_balance) return 1.0f;
+    const int m1 = (int)(n_corr[MULLS_GROUND] + n_corr[MULLS_ROOF]);
+    const int m2 = (int)n_corr[MULLS_FACADE], m3 = (int)n_corr[MULLS_PILLAR], m4 = (int)n_corr[MULLS_BEAM];
+    const float num = pc.z_xy_ratio * (float)(m2 + 2 * m3 - m4);
+    const double v = (double)num / (0.0001 + 2.0 * (double)m1);
+    return (float)((0.01 > v) ? 0.01 : v);
+}
+
+// :1301-1305 — too few correspondences?
+__device__ __forceinline__ bool too_few(const PairConst &pc, const PairState &ps, const uint32_t *n_corr, float &ratio) {
+    int total = 0;
+    for (int c = 0; c < kNumClasses; ++c) total += (int)n_corr[c];
+    const int nec = (int)(n_corr[MULLS_PILLAR] + n_corr[MULLS_BEAM] + n_corr[MULLS_FACADE]);
+    ratio = (float)(1.0 * (double)nec / (double)ps.source_feature_points_count);
+    return total < 40 || nec < 20 || ratio < pc.min_ratio;
+}
+
+// Solve + state update of one pair; executed by thread 0 of the last block of k_accumulate
+// (cregistration.hpp:1301-1400 after the summations). S = per-class sums [6][kTerms] in shared memory.
+__device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *S, double *sm /*>= 150 doubles*/,
+                                  int buf_written) {
+    const PairConst &pc = A.pc[pair];
+    PairState &ps = A.ps[pair];
+    const int i = ps.iter;
+    ps.iters_entered = i + 1;
+    for (int c = 0; c < kNumClasses; ++c) ps.n_corr_last[c] = ps.n_corr[c];
+    // bytes touched by this iteration's correspondence search: 28 B per active source and target point
+    {
+        uint64_t pts = 0;
+        for (int c = 0; c < kNumClasses; ++c)
+            if (pc.used[c]) pts += (uint64_t)ps.n_tgt[c];
+        ps.alg_bytes += 28ull * pts; // sources added by the caller of this function (pre-compaction counts)
+    }
+    mulls_icp_trace *tr = A.trace ? &A.trace[pair] : nullptr;
+    if (tr && i < MULLS_MAX_TRACE_ITERS) {
+        tr->n_iter = i + 1;
+        for (int c = 0; c < kNumClasses; ++c) tr->n_corr[i][c] = ps.n_corr[c];
+        for (int k = 0; k < 36; ++k) tr->atpa[i][k] = 0.0;
+        for (int k = 0; k < 6; ++k) tr->atpb[i][k] = tr->x[i][k] = 0.0;
+    }
+    float ratio;
+    const bool few = too_few(pc, ps, ps.n_corr, ratio);
+    ps.confidence = ratio;
+    double *I4 = sm; // scratch
+    if (few) {
+        ps.code = -2;
+        ps.status = kDone;
+        return; // TempTran = identity: T_total stays (:1307-1310, :1403)
+    }
+    // :1314-1315 threshold update
+    {
+        const double t = 1.0 * (double)ps.thre / (double)pc.thre_rate;
+        ps.thre = (t > (double)pc.thre_min) ? (float)t : pc.thre_min;
+    }
+    // ATPA/ATPb: classes in the order of :1914-1921 (ground, facade, roof, pillar, beam, vertex)
+    double *ATPA = sm;       // 36
+    double *ATPb = sm + 36;  // 6
+    double *inv = sm + 42;   // 36
+    double *lu = sm + 78;    // 36
+    double *Tmp = sm + 114;  // 16
+    double low[21];
+    for (int k = 0; k < 21; ++k) low[k] = 0.0;
+    for (int k = 0; k < 6; ++k) ATPb[k] = 0.0;
+    const int order[6] = {MULLS_GROUND, MULLS_FACADE, MULLS_ROOF, MULLS_PILLAR, MULLS_BEAM, MULLS_VERTEX};
+    for (int o = 0; o < 6; ++o) {
+        const double *s = S + order[o] * kTerms;
+        for (int k = 0; k < 21; ++k) low[k] += s[k];
+        for (int k = 0; k < 6; ++k) ATPb[k] += s[21 + k];
+    }
+    {
+        int k = 0;
+        for (int col = 0; col < 6; ++col)
+            for (int row = col; row < 6; ++row, ++k) {
+                ATPA[6 * row + col] = low[k];
+                ATPA[6 * col + row] = low[k]; // :1924-1938 lower -> upper
+            }
+    }
+    inverse6(ATPA, inv, lu);
+    double x[6];
+    for (int r = 0; r < 6; ++r) {
+        double s = inv[6 * r] * ATPb[0];
+        for (int cc = 1; cc < 6; ++cc) s = s + inv[6 * r + cc] * ATPb[cc];
+        x[r] = s;
+        ps.x[r] = s;
+    }
+    if (tr && i < MULLS_MAX_TRACE_ITERS) {
+        for (int k = 0; k < 36; ++k) tr->atpa[i][k] = ATPA[k];
+        for (int k = 0; k < 6; ++k) {
+            tr->atpb[i][k] = ATPb[k];
+            tr->x[i][k] = x[k];
+        }
+    }
+    // :1953-1964 cofactor with the Euler->quaternion Jacobian (half-angle sines/cosines in FLOAT, :2797)
+    {
+        const float sr = (float)sin(0.5 * x[3]), sp = (float)sin(0.5 * x[4]), sy = (float)sin(0.5 * x[5]);
+        const float cr = (float)cos(0.5 * x[3]), cp = (float)cos(0.5 * x[4]), cy = (float)cos(0.5 * x[5]);
+        double J[3][3];
+        J[0][0] = 0.5 * (double)(cr * cp * cy + sr * sp * sy);
+        J[0][1] = 0.5 * (double)(-sr * sp * cy - cr * cp * sy);
+        J[0][2] = 0.5 * (double)(-sr * cp * sy - cr * sp * cy);
+        J[1][0] = 0.5 * (double)(-sr * sp * cy + cr * cp * sy);
+        J[1][1] = 0.5 * (double)(cr * cp * cy - sr * sp * sy);
+        J[1][2] = 0.5 * (double)(-cr * sp * sy + sr * cp * cy);
+        J[2][0] = 0.5 * (double)(-sr * cp * sy - cr * sp * cy);
+        J[2][1] = 0.5 * (double)(-cr * sp * sy - sr * cp * cy);
+        J[2][2] = 0.5 * (double)(cr * cp * cy + sr * sp * sy);
+        double *cof = ps.cofactor;
+        for (int k = 0; k < 36; ++k) cof[k] = inv[k];
+        double tmp[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc)
+                tmp[r][cc] = J[r][0] * inv[6 * 3 + 3 + cc] + J[r][1] * inv[6 * 4 + 3 + cc] + J[r][2] * inv[6 * 5 + 3 + cc];
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc)
+                cof[6 * (3 + r) + 3 + cc] = tmp[r][0] * J[cc][0] + tmp[r][1] * J[cc][1] + tmp[r][2] * J[cc][2];
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc)
+                cof[6 * r + 3 + cc] = inv[6 * r + 3] * J[cc][0] + inv[6 * r + 4] * J[cc][1] + inv[6 * r + 5] * J[cc][2];
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc)
+                cof[6 * (3 + r) + cc] = J[r][0] * inv[6 * 3 + cc] + J[r][1] * inv[6 * 4 + cc] + J[r][2] * inv[6 * 5 + cc];
+    }
+    // :1333 TempTran
+    double *Tt = ps.T_inc;
+    construct_trans_a(x, Tt);
+    const double ts_norm = sqrt(Tt[3] * Tt[3] + Tt[7] * Tt[7] + Tt[11] * Tt[11]);
+    const double rs_angle = fabs(rotation_angle(Tt));
+    if (ts_norm > (double)pc.max_t || rs_angle > (double)pc.max_r) { // :1348-1354
+        ps.code = -1;
+        ps.status = kDone;
+        return;
+    }
+    // :1400 / :1403 — the increment is always folded into the accumulated transform
+    mat4_mul(Tt, ps.T_total, Tmp);
+    for (int k = 0; k < 16; ++k) ps.T_total[k] = Tmp[k];
+    if (i == pc.max_iter - 1 || (i > 2 && ts_norm < (double)pc.conv_t && rs_angle < (double)pc.conv_r)) { // :1357
+        ps.status = kNeedPosterior;
+        ps.final_buf = buf_written;
+        return;
+    }
+    ps.iter = i + 1;
+    (void)I4;
+}
+
+// ---- k_accumulate ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) {
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c];
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ns;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kIterBlock / 32;
+    __shared__ double s_red[kWarps][kTerms];
+    __shared__ uint32_t s_off[kWarps + 1];
+    __shared__ uint32_t s_base;
+    __shared__ bool s_last;
+
+    // (1) destination of the kept sources: blocks before this one in the same (pair, class)
+    {
+        uint32_t acc = 0;
+        const uint32_t first_chunk = pc.class_chunk_begin[c];
+        for (uint32_t b = first_chunk + threadIdx.x; b < blockIdx.x; b += kIterBlock) acc += A.blk_kept[b];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_off[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kWarps; ++w) t += s_off[w];
+            s_base = t;
+        }
+        __syncthreads();
+    }
+    uint8_t fl = 0;
+    uint32_t gi = 0;
+    if (valid) {
+        gi = pc.src_base[c] + local;
+        fl = A.flags[gi];
+    }
+    const bool kept = (fl & 1) != 0, pass = (fl & 2) != 0;
+    const unsigned kb = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) s_off[warp] = __popc(kb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t t = s_off[w];
+            s_off[w] = run;
+            run += t;
+        }
+        s_off[kWarps] = run;
+    }
+    __syncthreads();
+    const uint32_t dst_local = s_base + s_off[warp] + __popc(kb & ((1u << lane) - 1u));
+
+    // (2) terms of the surviving correspondences
+    double t[kTerms];
+#pragma unroll
+    for (int k = 0; k < kTerms; ++k) t[k] = 0.0;
+    float w_store = 0.0f;
+    int j = -1;
+    float4 p = make_float4(0, 0, 0, 0), n = make_float4(0, 0, 0, 0);
+    float d2 = 0.0f;
+    if (valid) {
+        p = A.src_pos[buf][gi];
+        n = A.src_nrm[buf][gi];
+        j = A.nn_idx[gi];
+        d2 = A.nn_d2[gi];
+        if (j >= 0) A.claim[pc.tgt_base[c] + j] = kClaimFree; // reset the table for the next iteration
+    }
+    float ratio_unused;
+    const bool few = too_few(pc, ps, ps.n_corr, ratio_unused);
+    if (pass && !few) {
+        const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
+        const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
+        const int it = ps.iter;
+        const bool resid_w = pc.w_residual && it > 2; // :1905-1907
+        const bool dist_w = pc.w_dist != 0, inten_w = pc.w_intensity != 0;
+        if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) {
+            const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, ps.n_corr);
+            terms_pt2pl(p, p.w, q, qn, wc, it, dist_w, resid_w, inten_w, pc.win_pt2pl, t, w_store);
+        } else if (c == MULLS_PILLAR || c == MULLS_BEAM) {
+            terms_pt2li(p, p.w, q, qn, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2li, t, w_store);
+        } else {
+            terms_pt2pt(p, p.w, q, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2pt, t);
+            w_store = d2; // pt2pt never stores a weight: the posterior reads the squared NN distance (Q2)
+        }
+    }
+    // (3) compaction into the other buffer (order preserved: :1776-1789)
+    if (kept) {
+        const uint32_t gd = pc.src_base[c] + dst_local;
+        A.src_pos[buf ^ 1][gd] = p;
+        A.src_nrm[buf ^ 1][gd] = n;
+        A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
+        A.corr_j[gd] = pass ? j : -1;
+        A.corr_w[gd] = w_store;
+    }
+    // (4) block reduction in a fixed order
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        double v = t[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double v = 0.0;
+        for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
+        A.partials[(size_t)blockIdx.x * kTerms + threadIdx.x] = v;
+    }
+    // (5) last block of the pair: reduce all partials, solve, advance
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned nblk = pc.chunk_end - pc.chunk_begin;
+        const unsigned prev = atomicAdd(&ps.arrive_acc, 1u);
+        s_last = (prev == nblk - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ double s_S[kNumClasses][kTerms];
+    __shared__ double s_scratch[160];
+    __shared__ int s_newn[kNumClasses];
+    // per class: sum the partials of its chunks in chunk order (fixed order => deterministic)
+    for (int cc = 0; cc < kNumClasses; ++cc) {
+        const uint32_t b0 = pc.class_chunk_begin[cc], b1 = pc.class_chunk_begin[cc + 1];
+        // 4 threads per term, strided, then combined in a fixed order
+        const int term = threadIdx.x >> 2, sub = threadIdx.x & 3;
+        double v = 0.0;
+        if (term < 27)
+            for (uint32_t b = b0 + sub; b < b1; b += 4) v += A.partials[(size_t)b * kTerms + term];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (term < 27 && sub == 0) s_S[cc][term] = v;
+        // kept sources of the class = its new size
+        uint32_t acc = 0;
+        for (uint32_t b = b0 + threadIdx.x; b < b1; b += kIterBlock) acc += A.blk_kept[b];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __syncthreads();
+        if (lane == 0) s_off[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < kWarps; ++w) tot += s_off[w];
+            s_newn[cc] = (int)tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint64_t srcpts = 0;
+        for (int cc = 0; cc < kNumClasses; ++cc)
+            if (pc.used[cc]) srcpts += (uint64_t)ps.n_src[cc];
+        ps.alg_bytes += 28ull * srcpts;
+        mulls_icp_trace *tr = A.trace ? &A.trace[cd.pair] : nullptr;
+        const bool dedup_any = true;
+        (void)dedup_any;
+        for (int cc = 0; cc < kNumClasses; ++cc) {
+            const bool active = pc.used[cc] && ps.n_src[cc] >= 3 && ps.n_tgt[cc] >= 3;
+            // classes that did not run determine_corres keep their cloud untouched
+            if (active) ps.n_src[cc] = s_newn[cc];
+            if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src[cc];
+        }
+        solve_and_advance(A, cd.pair, &s_S[0][0], s_scratch, buf ^ 1);
+        for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+        ps.arrive_acc = 0;
+        __threadfence();
+    }
+}
+
+// ---- k_posterior -------------------------------------------------------------------------------
+// cregistration.hpp:2518-2544: VTPV and observation count over the correspondences of the converged
+// iteration with its estimate x; sigma^2, code 1 / -3, information matrix (:1386).
+__global__ void __launch_bounds__(kIterBlock) k_posterior(DeviceArrays A) {
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    PairState &ps = A.ps[cd.pair];
+    if (ps.status != kNeedPosterior) return;
+    const int c = (int)cd.seg;
+    const int buf = ps.final_buf;
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ps.n_src[c];
+    double vtpv = 0.0;
+    int nobs = 0;
+    if (valid) {
+        const uint32_t gi = pc.src_base[c] + local;
+        const int j = A.corr_j[gi];
+        if (j >= 0) {
+            const float4 p = A.src_pos[buf][gi];
+            const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
+            const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
+            const float w = A.corr_w[gi];
+            const double *x = ps.x;
+            const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
+            if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) { // :2602-2623
+                const float ntx = qn.x, nty = qn.y, ntz = qn.z;
+                const float a = ntz * py - nty * pz;
+                const float b = ntx * pz - ntz * px;
+                const float cc = nty * px - ntx * py;
+                const float d = ntx * qx + nty * qy + ntz * qz - ntx * px - nty * py - ntz * pz;
+                const float residual = (float)((double)ntx * x[0] + (double)nty * x[1] + (double)ntz * x[2] +
+                                               (double)a * x[3] + (double)b * x[4] + (double)cc * x[5] - (double)d);
+                vtpv = (double)(w * residual * residual);
+                nobs = 1;
+            } else {
+                const float dx = px - qx, dy = py - qy, dz = pz - qz;
+                double Am[3][6], bv[3];
+                if (c == MULLS_PILLAR || c == MULLS_BEAM) { // :2643-2673
+                    const float vx = qn.x, vy = qn.y, vz = qn.z;
+                    Am[0][0] = 0, Am[0][1] = (double)vz, Am[0][2] = (double)(-vy), Am[0][3] = (double)(-vz * pz - vy * py),
+                    Am[0][4] = (double)(vy * px), Am[0][5] = (double)(vz * px);
+                    Am[1][0] = (double)(-vz), Am[1][1] = 0, Am[1][2] = (double)vx, Am[1][3] = (double)(vx * py),
+                    Am[1][4] = (double)(-vx * px - vz * pz), Am[1][5] = (double)(vz * py);
+                    Am[2][0] = (double)vy, Am[2][1] = (double)(-vx), Am[2][2] = 0, Am[2][3] = (double)(vx * pz),
+                    Am[2][4] = (double)(vy * pz), Am[2][5] = (double)(-vy * py - vx * px);
+                    bv[0] = (double)(-vz * dy + vy * dz);
+                    bv[1] = (double)(-vx * dz + vz * dx);
+                    bv[2] = (double)(-vy * dx + vx * dy);
+                } else { // :2559-2583
+                    Am[0][0] = 1, Am[0][1] = 0, Am[0][2] = 0, Am[0][3] = 0, Am[0][4] = (double)pz, Am[0][5] = (double)(-py);
+                    Am[1][0] = 0, Am[1][1] = 1, Am[1][2] = 0, Am[1][3] = (double)(-pz), Am[1][4] = 0, Am[1][5] = (double)px;
+                    Am[2][0] = 0, Am[2][1] = 0, Am[2][2] = 1, Am[2][3] = (double)py, Am[2][4] = (double)(-px), Am[2][5] = 0;
+                    bv[0] = (double)(-dx), bv[1] = (double)(-dy), bv[2] = (double)(-dz);
+                }
+                double r[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    double s = Am[k][0] * x[0];
+#pragma unroll
+                    for (int jj = 1; jj < 6; ++jj) s = s + Am[k][jj] * x[jj];
+                    r[k] = s - bv[k];
+                }
+                vtpv = (double)w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                nobs = 3;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kIterBlock / 32;
+    __shared__ double s_v[kWarps];
+    __shared__ int s_n[kWarps];
+    __shared__ bool s_last;
+    for (int o = 16; o > 0; o >>= 1) {
+        vtpv += __shfl_xor_sync(0xffffffffu, vtpv, o);
+        nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
+    }
+    if (lane == 0) {
+        s_v[warp] = vtpv;
+        s_n[warp] = nobs;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        int n = 0;
+        for (int w = 0; w < kWarps; ++w) {
+            v += s_v[w];
+            n += s_n[w];
+        }
+        A.post_partials[2 * (size_t)blockIdx.x] = v;
+        A.post_partials[2 * (size_t)blockIdx.x + 1] = (double)n;
+        __threadfence();
+        const unsigned nblk = pc.chunk_end - pc.chunk_begin;
+        s_last = atomicAdd(&ps.arrive_post, 1u) == nblk - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        // class order of :2529-2534: ground, facade, roof, pillar, beam, vertex; chunk order inside
+        const int order[6] = {MULLS_GROUND, MULLS_FACADE, MULLS_ROOF, MULLS_PILLAR, MULLS_BEAM, MULLS_VERTEX};
+        double VTPV = 0.0;
+        long long nob = 0;
+        for (int o = 0; o < 6; ++o)
+            for (uint32_t b = pc.class_chunk_begin[order[o]]; b < pc.class_chunk_begin[order[o] + 1]; ++b) {
+                VTPV += A.post_partials[2 * (size_t)b];
+                nob += (long long)A.post_partials[2 * (size_t)b + 1];
+            }
+        const double sigma2 = VTPV / (double)((int)nob - 6);
+        ps.sigma2 = sigma2;
+        ps.code = (sqrt(sigma2) < pc.sigma_thre) ? 1 : -3;
+        __shared__ double s_inv[36], s_lu[36];
+        inverse6(ps.cofactor, s_inv, s_lu);
+        for (int k = 0; k < 36; ++k) ps.info[k] = (1.0 / sigma2) * s_inv[k];
+        ps.status = kDone;
+        ps.arrive_post = 0;
+    }
+}
+
+// ---- k_state_init: reset the per-pair accumulators that the ingest kernels update atomically
+__global__ void k_state_init(DeviceArrays A, int n_pairs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    PairState &ps = A.ps[p];
+    for (int d = 0; d < 3; ++d) {
+        ps.bb_src[d] = ps.bb_tgt[d] = 0x7fffffff;
+        ps.bb_src[3 + d] = ps.bb_tgt[3 + d] = (int)0x80000000;
+    }
+    for (int s = 0; s < kNumSegs; ++s) ps.seg_count[s] = ps.seg_start[s] = 0;
+    for (int c = 0; c < kNumClasses; ++c) ps.hash_entries[c] = ps.n_corr[c] = 0;
+    ps.arrive_acc = ps.arrive_post = 0;
+    ps.status = kRunning;
+}
+
+// ---- k_collect: pair state -> mulls_icp_result (device copy, then one D2H)
+__global__ void k_collect(DeviceArrays A, int n_pairs, mulls_icp_result *out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairState &ps = A.ps[p];
+    mulls_icp_result &r = out[p];
+    for (int k = 0; k < 16; ++k) r.T[k] = ps.T_total[k];
+    for (int k = 0; k < 36; ++k) r.info[k] = ps.info[k];
+    r.sigma = (float)sqrt(ps.sigma2);
+    r.confidence = ps.confidence;
+    r.code = ps.code;
+    r.iters = ps.iters_entered;
+    for (int c = 0; c < kNumClasses; ++c) {
+        r.n_corr[c] = ps.n_corr_last[c];
+        r.n_src[c] = (uint32_t)ps.n_src[c];
+    }
+}
+
+} // namespace mulls

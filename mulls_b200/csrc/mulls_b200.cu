@@ -1,0 +1,521 @@
+// libmulls_b200.so — host side of the C-ABI (include/mulls_b200/abi.h) and kernel launch sequence.
+// CUDA runtime only: no torch, no PCL/Eigen. One context = one device, one stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "device_types.cuh"
+#include "kernels_ingest.cuh"
+#include "kernels_iterate.cuh"
+#include "kernels_pca.cuh"
+
+using namespace mulls;
+
+namespace {
+std::string g_create_error;
+}
+
+struct mulls_ctx {
+    int device = 0;
+    size_t max_pairs = 0, max_src = 0, max_tgt = 0;
+    size_t cap_src = 0, cap_tgt = 0, cap_in = 0, cap_it_chunks = 0, cap_in_chunks = 0;
+    cudaStream_t stream = nullptr;
+    DeviceArrays A{};
+    void *cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+    mulls_icp_result *d_results = nullptr;
+    mulls_icp_result *h_results = nullptr; // pinned
+    uint32_t *h_flags = nullptr;           // pinned copy of hash_used
+    mulls_icp_trace *d_trace = nullptr;
+    std::vector<PairConst> h_pc;
+    std::vector<ChunkDesc> h_in_chunks, h_it_chunks;
+    size_t n_pairs = 0, n_in = 0, n_src_total = 0, n_tgt_total = 0;
+    int max_iter_max = 0;
+    bool uploaded = false;
+    // tunables
+    int start_level0 = 1;
+    float h0_min = 0.125f;
+    int want_trace = 0;
+    // timing
+    cudaEvent_t ev_begin = nullptr, ev_ingest = nullptr, ev_iter = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_search; // 2 per iteration
+    mulls_run_stats stats{};
+    std::vector<void *> allocs;
+    std::string err;
+    // PCA scratch
+    void *pca_buf = nullptr;
+    size_t pca_buf_bytes = 0;
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return MULLS_E_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(mulls_ctx *ctx, T **p, size_t n) {
+    void *v = nullptr;
+    cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) {
+        ctx->allocs.push_back(v);
+        *p = (T *)v;
+    }
+    return e;
+}
+
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+extern "C" {
+
+void mulls_icp_default_params(mulls_icp_params *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->max_iter_num = 20;
+    p->dis_thre_unit = 1.5f;
+    p->converge_translation = 0.002f;
+    p->converge_rotation_d = 0.01f;
+    p->dis_thre_min = 0.4f;
+    p->dis_thre_update_rate = 1.1f;
+    std::strcpy(p->used_feature_type, "111110");
+    std::strcpy(p->weight_strategy, "1101");
+    p->z_xy_balanced_ratio = 1.0f;
+    p->pt2pt_residual_window = 0.1f;
+    p->pt2pl_residual_window = 0.1f;
+    p->pt2li_residual_window = 0.1f;
+    p->apply_intersection_filter = 1;
+    p->normal_bearing = 45.0f;
+    p->sigma_thre = 0.5f;
+    p->min_neccessary_corr_ratio = 0.03f;
+    p->max_bearable_rotation_d = 45.0f;
+    const double big = 1.7976931348623157e308;
+    for (int d = 0; d < 3; ++d) {
+        p->target_bound[d] = -big;
+        p->target_bound[3 + d] = big;
+    }
+}
+
+const char *mulls_last_error(const mulls_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void mulls_destroy(mulls_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->cub_temp) cudaFree(ctx->cub_temp);
+    if (ctx->pca_buf) cudaFree(ctx->pca_buf);
+    if (ctx->h_results) cudaFreeHost(ctx->h_results);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    for (cudaEvent_t e : ctx->ev_search) cudaEventDestroy(e);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_ingest) cudaEventDestroy(ctx->ev_ingest);
+    if (ctx->ev_iter) cudaEventDestroy(ctx->ev_iter);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t max_tgt_pts) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("mulls_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); mulls_b200 has no CPU fallback";
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev || max_pairs == 0) {
+        g_create_error = "mulls_create: bad device index or max_pairs";
+        return nullptr;
+    }
+    mulls_ctx *ctx = new mulls_ctx();
+    ctx->device = device;
+    ctx->max_pairs = max_pairs;
+    ctx->max_src = max_src_pts;
+    ctx->max_tgt = max_tgt_pts;
+    auto fail = [&](const char *what, cudaError_t err) -> mulls_ctx * {
+        g_create_error = std::string("mulls_create: ") + what + ": " + cudaGetErrorString(err);
+        mulls_destroy(ctx);
+        return nullptr;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    const size_t cs = ctx->cap_src = max_pairs * max_src_pts;
+    const size_t ct = ctx->cap_tgt = max_pairs * max_tgt_pts;
+    const size_t cin = ctx->cap_in = cs + ct;
+    if (cin >= (1ull << 31)) {
+        g_create_error = "mulls_create: more than 2^31 points per context";
+        mulls_destroy(ctx);
+        return nullptr;
+    }
+    // every cloud adds at most one partial chunk
+    ctx->cap_it_chunks = ceil_div(cs, kIterBlock) + max_pairs * kNumClasses;
+    ctx->cap_in_chunks = ceil_div(cin, kIngestBlock) + max_pairs * kNumSegs;
+    DeviceArrays &A = ctx->A;
+    float4 *in = nullptr;
+#define ALLOC(ptr, n)                                                   \
+    if ((e = dev_alloc(ctx, &(ptr), (n))) != cudaSuccess) return fail(#ptr, e)
+    ALLOC(in, 3 * cin);
+    A.in_aos = in;
+    ALLOC(A.stg_pos, cin);
+    ALLOC(A.stg_nrm, cin);
+    ALLOC(A.keys_a, cin);
+    ALLOC(A.keys_b, cin);
+    ALLOC(A.vals_a, cin);
+    ALLOC(A.vals_b, cin);
+    ALLOC(A.tgt_pos, ct);
+    ALLOC(A.tgt_nrm, ct);
+    for (int b = 0; b < 2; ++b) {
+        ALLOC(A.src_pos[b], cs);
+        ALLOC(A.src_nrm[b], cs);
+        ALLOC(A.src_hint[b], cs);
+    }
+    ALLOC(A.nn_idx, cs);
+    ALLOC(A.nn_d2, cs);
+    ALLOC(A.flags, cs);
+    ALLOC(A.corr_j, cs);
+    ALLOC(A.corr_w, cs);
+    ALLOC(A.claim, ct);
+    // hash pool: every class table has a power-of-two capacity >= 2x its cells; cells are typically
+    // 2-3 per target point, so 12 entries per point (192 B) leave room for the rounding.
+    {
+        size_t pool = 12 * ct + 64 * max_pairs * kNumClasses;
+        if (pool >= (1ull << 32)) pool = (1ull << 32) - 1;
+        A.hash_pool_entries = (uint32_t)pool;
+        ALLOC(A.hash, pool);
+    }
+    ALLOC(A.hash_used, 2);
+    ALLOC(A.blk_kept, ctx->cap_it_chunks);
+    ALLOC(A.partials, ctx->cap_it_chunks * kTerms);
+    ALLOC(A.post_partials, ctx->cap_it_chunks * 2);
+    ALLOC(A.pc, max_pairs);
+    ALLOC(A.ps, max_pairs);
+    ALLOC(A.in_chunks, ctx->cap_in_chunks);
+    ALLOC(A.it_chunks, ctx->cap_it_chunks);
+    ALLOC(ctx->d_results, max_pairs);
+    ALLOC(ctx->d_trace, max_pairs);
+#undef ALLOC
+    A.trace = nullptr;
+    if ((e = cudaMallocHost((void **)&ctx->h_results, max_pairs * sizeof(mulls_icp_result))) != cudaSuccess)
+        return fail("pinned results", e);
+    if ((e = cudaMallocHost((void **)&ctx->h_flags, 2 * sizeof(uint32_t))) != cudaSuccess) return fail("pinned flags", e);
+    // radix-sort temp storage for the largest possible sort
+    {
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, A.keys_a, A.keys_b, A.vals_a, A.vals_b, (int)cin, 0, 64,
+                                        ctx->stream);
+        ctx->cub_temp_bytes = bytes;
+        if ((e = cudaMalloc(&ctx->cub_temp, std::max<size_t>(bytes, 16))) != cudaSuccess) return fail("cub temp", e);
+    }
+    cudaEventCreate(&ctx->ev_begin);
+    cudaEventCreate(&ctx->ev_ingest);
+    cudaEventCreate(&ctx->ev_iter);
+    cudaEventCreate(&ctx->ev_end);
+    ctx->ev_search.resize(2 * MULLS_MAX_TRACE_ITERS);
+    for (auto &ev : ctx->ev_search) cudaEventCreate(&ev);
+    if ((e = cudaMemsetAsync(A.ps, 0, max_pairs * sizeof(PairState), ctx->stream)) != cudaSuccess) return fail("memset", e);
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("sync", e);
+    return ctx;
+}
+
+int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return MULLS_E_ARG;
+    std::string n(name);
+    if (n == "start_level") ctx->start_level0 = value;
+    else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
+    else return MULLS_E_ARG;
+    return MULLS_OK;
+}
+
+int mulls_get_stats(const mulls_ctx *ctx, mulls_run_stats *out) {
+    if (!ctx || !out) return MULLS_E_ARG;
+    *out = ctx->stats;
+    return MULLS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const double *init, PairConst &pc) {
+    if (P.normal_shooting_on) {
+        ctx->err = "normal_shooting_on is not implemented (SURVEY 8f rank 4)";
+        return MULLS_E_UNSUPPORTED;
+    }
+    if (P.apply_motion_undistortion_while_registration) {
+        ctx->err = "apply_motion_undistortion_while_registration is not implemented";
+        return MULLS_E_UNSUPPORTED;
+    }
+    if (P.keep_less_source_points) {
+        ctx->err = "keep_less_source_points is not implemented (time-seeded pcl::RandomSample upstream)";
+        return MULLS_E_UNSUPPORTED;
+    }
+    if (P.max_iter_num > MULLS_MAX_TRACE_ITERS) {
+        ctx->err = "max_iter_num > 64";
+        return MULLS_E_ARG;
+    }
+    std::memset(&pc, 0, sizeof(pc));
+    pc.max_iter = P.max_iter_num;
+    const size_t nu = strnlen(P.used_feature_type, 8), nw = strnlen(P.weight_strategy, 8);
+    for (int c = 0; c < kNumClasses; ++c) pc.used[c] = (c < (int)nu && P.used_feature_type[c] == '1') ? 1 : 0;
+    pc.w_balance = (nw > 0 && P.weight_strategy[0] == '1');
+    pc.w_residual = (nw > 1 && P.weight_strategy[1] == '1');
+    pc.w_dist = (nw > 2 && P.weight_strategy[2] == '1');
+    pc.w_intensity = (nw > 3 && P.weight_strategy[3] == '1');
+    pc.z_xy_ratio = P.z_xy_balanced_ratio;
+    pc.win_pt2pt = P.pt2pt_residual_window;
+    pc.win_pt2pl = P.pt2pl_residual_window;
+    pc.win_pt2li = P.pt2li_residual_window;
+    pc.thre_unit = P.dis_thre_unit;
+    pc.thre_min = P.dis_thre_min;
+    pc.thre_rate = P.dis_thre_update_rate;
+    pc.conv_t = P.converge_translation;
+    // the float/double mix of cregistration.hpp:1162-1164
+    pc.conv_r = (float)(P.converge_rotation_d / 180.0 * M_PI);
+    pc.max_t = (float)(2.0 * P.dis_thre_unit);
+    pc.max_r = (float)(P.max_bearable_rotation_d / 180.0 * M_PI);
+    pc.min_ratio = P.min_neccessary_corr_ratio;
+    pc.apply_filter = P.apply_intersection_filter ? 1 : 0;
+    pc.cos_thre = std::cos(P.normal_bearing / 180.0 * M_PI);
+    pc.sigma_thre = (double)P.sigma_thre;
+    for (int i = 0; i < 16; ++i) pc.init[i] = init[i];
+    for (int i = 0; i < 6; ++i) pc.tbound[i] = P.target_bound[i];
+    return MULLS_OK;
+}
+
+static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
+                       const mulls_icp_params *params, const double *init_guess, const uint32_t *src_index_base,
+                       const uint32_t *src_global_n) {
+    if (!ctx || !tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
+    if (n_pairs > ctx->max_pairs) {
+        ctx->err = "more pairs than the context was created for";
+        return MULLS_E_CAPACITY;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->uploaded = false;
+    ctx->h_pc.assign(n_pairs, PairConst());
+    ctx->h_in_chunks.clear();
+    ctx->h_it_chunks.clear();
+    size_t in_off = 0, s_off = 0, t_off = 0;
+    int max_iter_max = 0;
+    for (size_t p = 0; p < n_pairs; ++p) {
+        PairConst &pc = ctx->h_pc[p];
+        int rc = build_pair_const(ctx, params[p], init_guess + 16 * p, pc);
+        if (rc != MULLS_OK) return rc;
+        max_iter_max = std::max(max_iter_max, pc.max_iter);
+        size_t ns = 0, nt = 0;
+        for (int c = 0; c < kNumClasses; ++c) {
+            nt += tgt[p * kNumClasses + c].n;
+            ns += src[p * kNumClasses + c].n;
+        }
+        if (ns > ctx->max_src || nt > ctx->max_tgt) {
+            ctx->err = "pair exceeds max_src_pts / max_tgt_pts of the context";
+            return MULLS_E_CAPACITY;
+        }
+        for (int s = 0; s < kNumSegs; ++s) {
+            const mulls_cloud_view &v = (s < kNumClasses) ? tgt[p * kNumClasses + s] : src[p * kNumClasses + (s - kNumClasses)];
+            if (v.n > 0 && !v.aos48) return MULLS_E_ARG;
+            pc.in_off[s] = (uint32_t)in_off;
+            pc.in_n[s] = (uint32_t)v.n;
+            for (size_t f = 0; f < v.n; f += kIngestBlock)
+                ctx->h_in_chunks.push_back(ChunkDesc{(uint32_t)p, (uint32_t)s, (uint32_t)f});
+            in_off += v.n;
+        }
+        pc.chunk_begin = (uint32_t)ctx->h_it_chunks.size();
+        for (int c = 0; c < kNumClasses; ++c) {
+            pc.tgt_base[c] = (uint32_t)t_off;
+            pc.src_base[c] = (uint32_t)s_off;
+            t_off += tgt[p * kNumClasses + c].n;
+            const size_t n = src[p * kNumClasses + c].n;
+            s_off += n;
+            pc.class_chunk_begin[c] = (uint32_t)ctx->h_it_chunks.size();
+            for (size_t f = 0; f < n; f += kIterBlock) ctx->h_it_chunks.push_back(ChunkDesc{(uint32_t)p, (uint32_t)c, (uint32_t)f});
+            pc.src_index_base[c] = src_index_base ? src_index_base[c] : 0;
+            pc.src_global_n[c] = src_global_n ? src_global_n[c] : (uint32_t)n;
+        }
+        pc.class_chunk_begin[kNumClasses] = (uint32_t)ctx->h_it_chunks.size();
+        pc.chunk_end = (uint32_t)ctx->h_it_chunks.size();
+        pc.sharded = src_index_base ? 1 : 0;
+    }
+    if (ctx->h_in_chunks.size() > ctx->cap_in_chunks || ctx->h_it_chunks.size() > ctx->cap_it_chunks) {
+        ctx->err = "internal: chunk table capacity";
+        return MULLS_E_CAPACITY;
+    }
+    // H2D: the clouds (zero-copy views of the caller's buffers; pinned buffers copy asynchronously)
+    for (size_t p = 0; p < n_pairs; ++p) {
+        const PairConst &pc = ctx->h_pc[p];
+        for (int s = 0; s < kNumSegs; ++s) {
+            const mulls_cloud_view &v = (s < kNumClasses) ? tgt[p * kNumClasses + s] : src[p * kNumClasses + (s - kNumClasses)];
+            if (v.n == 0) continue;
+            CK(cudaMemcpyAsync((void *)(ctx->A.in_aos + 3 * (size_t)pc.in_off[s]), v.aos48, v.n * 48, cudaMemcpyHostToDevice,
+                               ctx->stream));
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->A.pc, ctx->h_pc.data(), n_pairs * sizeof(PairConst), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->h_in_chunks.empty())
+        CK(cudaMemcpyAsync(ctx->A.in_chunks, ctx->h_in_chunks.data(), ctx->h_in_chunks.size() * sizeof(ChunkDesc),
+                           cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->h_it_chunks.empty())
+        CK(cudaMemcpyAsync(ctx->A.it_chunks, ctx->h_it_chunks.data(), ctx->h_it_chunks.size() * sizeof(ChunkDesc),
+                           cudaMemcpyHostToDevice, ctx->stream));
+    // the host vectors above are pageable: make sure the copies are done before they can change
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_pairs = n_pairs;
+    ctx->n_in = in_off;
+    ctx->n_src_total = s_off;
+    ctx->n_tgt_total = t_off;
+    ctx->max_iter_max = max_iter_max;
+    ctx->uploaded = true;
+    return MULLS_OK;
+}
+
+// Launch the whole path on the resident inputs. If `hook` is given (sharded mode) it is called between
+// the phases that need a cross-rank exchange.
+static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
+    if (!ctx || !ctx->uploaded) return MULLS_E_ARG;
+    if (hook) {
+        ctx->err = "sharded mode is not available in this build";
+        return MULLS_E_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DeviceArrays A = ctx->A;
+    A.trace = trace ? ctx->d_trace : nullptr;
+    const int np = (int)ctx->n_pairs;
+    const uint32_t n_in = (uint32_t)ctx->n_in;
+    uint64_t launches = 0;
+    CK(cudaEventRecord(ctx->ev_begin, st));
+    if (trace) CK(cudaMemsetAsync(ctx->d_trace, 0, np * sizeof(mulls_icp_trace), st));
+    CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
+    k_state_init<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np);
+    ++launches;
+    const unsigned n_inc = (unsigned)ctx->h_in_chunks.size(), n_itc = (unsigned)ctx->h_it_chunks.size();
+    if (n_inc) {
+        k_ingest_transform<<<n_inc, kIngestBlock, 0, st>>>(A);
+        ++launches;
+    }
+    k_pair_setup<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->h0_min);
+    ++launches;
+    if (n_inc) {
+        k_make_keys<<<n_inc, kIngestBlock, 0, st>>>(A);
+        ++launches;
+        int seg_bits = 1;
+        while ((1ull << seg_bits) <= (uint64_t)np * kNumSegs) ++seg_bits;
+        size_t bytes = ctx->cub_temp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, bytes, A.keys_a, A.keys_b, A.vals_a, A.vals_b, (int)n_in, 0,
+                                           36 + seg_bits, st));
+        launches += 5; // CUB onesweep: histogram + one pass per digit (library kernels, not ours)
+    }
+    k_seg_offsets<<<1, 256, 0, st>>>(A, np);
+    ++launches;
+    if (n_in) {
+        k_gather<<<(unsigned)ceil_div(n_in, 256), 256, 0, st>>>(A, A.keys_b, A.vals_b, n_in);
+        const unsigned hb = (unsigned)ceil_div((size_t)n_in + 1, 256);
+        k_hash_build<<<hb, 256, 0, st>>>(A, A.keys_b, n_in, 0);
+        k_hash_layout<<<1, 32, 0, st>>>(A, np);
+        k_hash_clear<<<1184, 256, 0, st>>>(A);
+        k_hash_build<<<hb, 256, 0, st>>>(A, A.keys_b, n_in, 1);
+        k_hash_build<<<hb, 256, 0, st>>>(A, A.keys_b, n_in, 2);
+        launches += 6;
+    } else {
+        k_hash_layout<<<1, 32, 0, st>>>(A, np);
+        ++launches;
+    }
+    CK(cudaEventRecord(ctx->ev_ingest, st));
+    int n_search_ev = 0;
+    if (n_itc) {
+        for (int it = 0; it < ctx->max_iter_max; ++it) {
+            const int buf = it & 1;
+            CK(cudaEventRecord(ctx->ev_search[2 * it], st));
+            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0);
+            CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
+            k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            launches += 3;
+            n_search_ev = it + 1;
+        }
+        k_posterior<<<n_itc, kIterBlock, 0, st>>>(A);
+        ++launches;
+    }
+    CK(cudaEventRecord(ctx->ev_iter, st));
+    k_collect<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->d_results);
+    ++launches;
+    CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, np * sizeof(mulls_icp_result), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (trace) CK(cudaMemcpyAsync(trace, ctx->d_trace, np * sizeof(mulls_icp_trace), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev_end, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (ctx->h_flags[1]) {
+        ctx->err = "hash pool exhausted (target clouds produce more grid cells than the context reserves)";
+        return MULLS_E_CAPACITY;
+    }
+    if (out) std::memcpy(out, ctx->h_results, np * sizeof(mulls_icp_result));
+    // statistics
+    mulls_run_stats &S = ctx->stats;
+    S = mulls_run_stats();
+    S.kernel_launches = launches;
+    cudaEventElapsedTime(&S.ms_ingest, ctx->ev_begin, ctx->ev_ingest);
+    cudaEventElapsedTime(&S.ms_iterate, ctx->ev_ingest, ctx->ev_iter);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev_begin, ctx->ev_end);
+    float ms = 0.f;
+    for (int it = 0; it < n_search_ev; ++it) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->ev_search[2 * it], ctx->ev_search[2 * it + 1]);
+        ms += t;
+    }
+    S.ms_search = ms;
+    for (int p = 0; p < np; ++p) S.iterations += (uint64_t)ctx->h_results[p].iters;
+    // algorithmic bytes are accumulated on the device per executed iteration
+    {
+        std::vector<PairState> hs(np);
+        CK(cudaMemcpy(hs.data(), A.ps, np * sizeof(PairState), cudaMemcpyDeviceToHost));
+        for (int p = 0; p < np; ++p) S.algorithmic_bytes += hs[p].alg_bytes;
+    }
+    return MULLS_OK;
+}
+
+int mulls_batch_upload(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
+                       const mulls_icp_params *params, const double *init_guess) {
+    return upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr);
+}
+
+int mulls_batch_run_resident(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace) {
+    return run_impl(ctx, out, trace, nullptr, nullptr);
+}
+
+int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
+                        const mulls_icp_params *params, const double *init_guess, mulls_icp_result *out,
+                        mulls_icp_trace *trace) {
+    int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr);
+    if (rc != MULLS_OK) return rc;
+    return run_impl(ctx, out, trace, nullptr, nullptr);
+}
+
+int mulls_icp_run(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES], const mulls_cloud_view src[MULLS_NUM_CLASSES],
+                  const mulls_icp_params *params, const double init_guess[16], mulls_icp_result *out,
+                  mulls_icp_trace *trace) {
+    return mulls_icp_run_batch(ctx, 1, tgt, src, params, init_guess, out, trace);
+}
+
+int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
+                          const mulls_cloud_view src_shard[MULLS_NUM_CLASSES],
+                          const uint32_t src_index_base[MULLS_NUM_CLASSES], const uint32_t src_global_n[MULLS_NUM_CLASSES],
+                          const mulls_icp_params *params, const double init_guess[16], mulls_allreduce_fn allreduce,
+                          void *user, mulls_icp_result *out, mulls_icp_trace *trace) {
+    if (!ctx || !allreduce) return MULLS_E_ARG;
+    int rc = upload_impl(ctx, 1, tgt, src_shard, params, init_guess, src_index_base, src_global_n);
+    if (rc != MULLS_OK) return rc;
+    return run_impl(ctx, out, trace, allreduce, user);
+}
+
+int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
+    if (!ctx || !out) return MULLS_E_ARG;
+    ctx->err = "mulls_pca_features is not available in this build";
+    return MULLS_E_UNSUPPORTED;
+}
+
+} // extern "C"

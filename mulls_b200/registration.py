@@ -1,0 +1,219 @@
+"""Host-side mirror of the reference's registration interface over the C-ABI.
+
+`CRegistration.mm_lls_icp` has the argument list, defaults, outputs and return codes of
+lo::CRegistration<PointT>::mm_lls_icp (include/common/cregistration.hpp:1114-1123, :1131-1136,
+:1405, :1418-1420); `CloudBlock` / `Constraint` carry the members of cloudblock_t / constraint_t
+that the function touches (include/common/utility.hpp:233-553, :561-590). Clouds are (n,7)
+[x y z nx ny nz intensity] or (n,12) pcl::PointXYZINormal-row float32 arrays.
+
+Everything here runs on the GPU through libmulls_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi
+
+_FEATURES = ("ground", "pillar", "facade", "beam", "roof", "vertex")  # used_feature_type order
+
+
+def _empty() -> np.ndarray:
+    return np.zeros((0, 12), dtype=np.float32)
+
+
+@dataclass
+class CloudBlock:
+    """cloudblock_t: per feature class a dense cloud (pc_*) and a down-sampled one (pc_*_down)."""
+
+    pc_ground: np.ndarray = field(default_factory=_empty)
+    pc_pillar: np.ndarray = field(default_factory=_empty)
+    pc_facade: np.ndarray = field(default_factory=_empty)
+    pc_beam: np.ndarray = field(default_factory=_empty)
+    pc_roof: np.ndarray = field(default_factory=_empty)
+    pc_vertex: np.ndarray = field(default_factory=_empty)
+    pc_ground_down: np.ndarray = field(default_factory=_empty)
+    pc_pillar_down: np.ndarray = field(default_factory=_empty)
+    pc_facade_down: np.ndarray = field(default_factory=_empty)
+    pc_beam_down: np.ndarray = field(default_factory=_empty)
+    pc_roof_down: np.ndarray = field(default_factory=_empty)
+    # bounds_t local_bound: min_x min_y min_z max_x max_y max_z (utility.hpp:101-136)
+    local_bound: tuple = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+
+    def clone_feature(self, get_feature_down: bool):
+        """cloudblock_t::clone_feature (utility.hpp:524-550): the six clouds mm_lls_icp works on."""
+        if get_feature_down:
+            src = (self.pc_ground_down, self.pc_pillar_down, self.pc_facade_down, self.pc_beam_down,
+                   self.pc_roof_down, self.pc_vertex)
+        else:
+            src = (self.pc_ground, self.pc_pillar, self.pc_facade, self.pc_beam, self.pc_roof, self.pc_vertex)
+        return [abi.as_aos48(c) for c in src]
+
+    @staticmethod
+    def from_class_list(clouds, down=None, local_bound=None) -> "CloudBlock":
+        """clouds/down: six arrays in used_feature_type order (ground, pillar, facade, beam, roof, vertex)."""
+        b = CloudBlock()
+        for name, arr in zip(_FEATURES, clouds):
+            setattr(b, f"pc_{name}", abi.as_aos48(arr))
+        for name, arr in zip(_FEATURES[:5], (down if down is not None else clouds)[:5]):
+            setattr(b, f"pc_{name}_down", abi.as_aos48(arr))
+        if local_bound is None:
+            pts = [abi.as_aos48(c)[:, :3] for c in clouds if len(c)]
+            if pts:
+                allp = np.concatenate(pts, axis=0).astype(np.float64)
+                local_bound = tuple(allp.min(0)) + tuple(allp.max(0))
+            else:
+                local_bound = (0.0,) * 6
+        b.local_bound = tuple(float(v) for v in local_bound)
+        return b
+
+
+@dataclass
+class Constraint:
+    """constraint_t: block1 = target, block2 = source; outputs of mm_lls_icp."""
+
+    block1: CloudBlock = field(default_factory=CloudBlock)
+    block2: CloudBlock = field(default_factory=CloudBlock)
+    Trans1_2: np.ndarray = field(default_factory=lambda: np.eye(4))
+    information_matrix: np.ndarray = field(default_factory=lambda: np.eye(6))
+    sigma: float = float(np.finfo(np.float32).max)
+    confidence: float = 0.0
+
+
+class Context:
+    """Thin RAII wrapper of a mulls_ctx (one CUDA device, one stream)."""
+
+    def __init__(self, device: int = 0, max_pairs: int = 1, max_src_pts: int = 150000, max_tgt_pts: int = 150000):
+        self.lib = abi.load_library()
+        self.handle = self.lib.mulls_create(device, max_pairs, max_src_pts, max_tgt_pts)
+        if not self.handle:
+            raise RuntimeError(self.lib.mulls_last_error(None).decode())
+        self.max_pairs = max_pairs
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mulls_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(f"mulls_b200 error {rc}: {self.lib.mulls_last_error(self.handle).decode()}")
+
+    def set_tunable(self, name: str, value: int):
+        self._check(self.lib.mulls_set_tunable(self.handle, name.encode(), int(value)))
+
+    @staticmethod
+    def _pack(pairs):
+        n = len(pairs)
+        tv = (abi.CloudView * (6 * n))()
+        sv = (abi.CloudView * (6 * n))()
+        pa = (abi.IcpParams * n)()
+        init = np.zeros((n, 16), dtype=np.float64)
+        keep = []
+        for i, pr in enumerate(pairs):
+            for c in range(6):
+                t = abi.as_aos48(pr["tgt"][c])
+                s = abi.as_aos48(pr["src"][c])
+                keep += [t, s]
+                tv[6 * i + c] = abi.cloud_view(t)
+                sv[6 * i + c] = abi.cloud_view(s)
+            pa[i] = pr["params"]
+            init[i] = np.asarray(pr["init_guess"], dtype=np.float64).reshape(16)
+        return tv, sv, pa, init, keep
+
+    def upload(self, pairs):
+        """pairs: list of dict(tgt=[6 arrays], src=[6 arrays], params=IcpParams, init_guess=4x4)."""
+        tv, sv, pa, init, keep = self._pack(pairs)
+        self._keep = (tv, sv, pa, init, keep)
+        self._n = len(pairs)
+        self._check(self.lib.mulls_batch_upload(self.handle, len(pairs), tv, sv, pa,
+                                                init.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def run_resident(self, want_trace: bool = False):
+        n = self._n
+        res = (abi.IcpResult * n)()
+        tr = (abi.IcpTrace * n)() if want_trace else None
+        self._check(self.lib.mulls_batch_run_resident(self.handle, res, tr))
+        out = [abi.result_to_dict(r) for r in res]
+        return (out, [abi.trace_to_dict(t) for t in tr]) if want_trace else (out, None)
+
+    def run_batch(self, pairs, want_trace: bool = False):
+        """Host buffers in, results out: H2D + ingest + iterations + D2H in one call."""
+        tv, sv, pa, init, keep = self._pack(pairs)
+        n = len(pairs)
+        res = (abi.IcpResult * n)()
+        tr = (abi.IcpTrace * n)() if want_trace else None
+        self._check(self.lib.mulls_icp_run_batch(self.handle, n, tv, sv, pa,
+                                                 init.ctypes.data_as(C.POINTER(C.c_double)), res, tr))
+        out = [abi.result_to_dict(r) for r in res]
+        return (out, [abi.trace_to_dict(t) for t in tr]) if want_trace else (out, None)
+
+    def stats(self) -> dict:
+        s = abi.RunStats()
+        self._check(self.lib.mulls_get_stats(self.handle, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in abi.RunStats._fields_}
+
+
+class CRegistration:
+    """lo::CRegistration<PointT> — the part of its public surface on the hot path."""
+
+    def __init__(self, device: int = 0, max_src_pts: int = 700000, max_tgt_pts: int = 700000):
+        self._ctx = Context(device, 1, max_src_pts, max_tgt_pts)
+        self.last_trace = None
+
+    def mm_lls_icp(self, registration_cons: Constraint, max_iter_num: int = 20, dis_thre_unit: float = 1.5,
+                   converge_translation: float = 0.002, converge_rotation_d: float = 0.01, dis_thre_min: float = 0.4,
+                   dis_thre_update_rate: float = 1.1, used_feature_type: str = "111110", weight_strategy: str = "1101",
+                   z_xy_balanced_ratio: float = 1.0, pt2pt_residual_window: float = 0.1,
+                   pt2pl_residual_window: float = 0.1, pt2li_residual_window: float = 0.1, initial_guess=None,
+                   apply_intersection_filter: bool = True, apply_motion_undistortion_while_registration: bool = False,
+                   normal_shooting_on: bool = False, normal_bearing: float = 45.0, use_more_points: bool = False,
+                   keep_less_source_points: bool = False, sigma_thre: float = 0.5,
+                   min_neccessary_corr_ratio: float = 0.03, max_bearable_rotation_d: float = 45.0) -> int:
+        p = abi.default_params()
+        p.max_iter_num = max_iter_num
+        p.dis_thre_unit = dis_thre_unit
+        p.converge_translation = converge_translation
+        p.converge_rotation_d = converge_rotation_d
+        p.dis_thre_min = dis_thre_min
+        p.dis_thre_update_rate = dis_thre_update_rate
+        p.used_feature_type = used_feature_type.encode()[:7]
+        p.weight_strategy = weight_strategy.encode()[:7]
+        p.z_xy_balanced_ratio = z_xy_balanced_ratio
+        p.pt2pt_residual_window = pt2pt_residual_window
+        p.pt2pl_residual_window = pt2pl_residual_window
+        p.pt2li_residual_window = pt2li_residual_window
+        p.apply_intersection_filter = int(apply_intersection_filter)
+        p.apply_motion_undistortion_while_registration = int(apply_motion_undistortion_while_registration)
+        p.normal_shooting_on = int(normal_shooting_on)
+        p.normal_bearing = normal_bearing
+        p.use_more_points = int(use_more_points)
+        p.keep_less_source_points = int(keep_less_source_points)
+        p.sigma_thre = sigma_thre
+        p.min_neccessary_corr_ratio = min_neccessary_corr_ratio
+        p.max_bearable_rotation_d = max_bearable_rotation_d
+        p.target_bound[:] = list(registration_cons.block1.local_bound)
+        init = np.eye(4) if initial_guess is None else np.asarray(initial_guess, dtype=np.float64)
+        pair = {
+            "tgt": registration_cons.block1.clone_feature(False),               # :1180
+            "src": registration_cons.block2.clone_feature(not use_more_points),  # :1181
+            "params": p,
+            "init_guess": init,
+        }
+        res, tr = self._ctx.run_batch([pair], want_trace=True)
+        r = res[0]
+        self.last_trace = tr[0]
+        registration_cons.Trans1_2 = r["T"]
+        registration_cons.information_matrix = r["info"]
+        registration_cons.sigma = r["sigma"]
+        registration_cons.confidence = r["confidence"]
+        return r["code"]
