@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — registrations/s of the MULLS registration hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the whole path (ingest: intersection filter, spatial sort, grid build; all
+ICP iterations; posterior) over one batch of synthetic 120k-point 64-beam scan pairs (BASELINE
+config 2) per GPU. Per-GPU work is fixed as N grows (weak scaling): every rank registers its own
+batch, there is no data-path collective (independent pairs).
+
+  value  registrations/s with the inputs already resident in HBM (CUDA-event time of the library's
+         stream, max over ranks)
+  e2e    the same through the C-ABI call with HOST (pinned) buffers: H2D of the clouds and D2H of the
+         results inside the timed region
+  --impl reference   the CPU restatement of the reference's algorithm (oracle) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scan-pair registrations/sec (120k-pt 64-beam)"
+UNIT = "registrations/s"
+
+
+def _gen_one(args):
+    seed, config = args
+    from mulls_b200 import synth
+
+    p = synth.make_pair(seed, config)
+    return {"tgt": p["tgt"], "src": p["src"], "params": bytes(p["params"]), "init_guess": p["init_guess"], "T_gt": p["T_gt"]}
+
+
+def make_pairs(seeds, config):
+    from concurrent.futures import ProcessPoolExecutor
+
+    from mulls_b200 import abi
+
+    workers = max(1, min(len(seeds), (os.cpu_count() or 8) // 2, 16))
+    if workers > 1:
+        with ProcessPoolExecutor(workers) as ex:
+            raw = list(ex.map(_gen_one, [(s, config) for s in seeds]))
+    else:
+        raw = [_gen_one((s, config)) for s in seeds]
+    for r in raw:
+        r["params"] = abi.IcpParams.from_buffer_copy(r["params"])
+    return raw
+
+
+def pin_pairs(pairs):
+    """Move the clouds into pinned host memory (the e2e leg copies from there every step)."""
+    import torch
+
+    keep = []
+    for p in pairs:
+        for side in ("tgt", "src"):
+            new = []
+            for a in p[side]:
+                t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                keep.append(t)
+                new.append(t.numpy())
+            p[side] = new
+    return keep
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(pairs, budget_s, max_regs):
+    """The oracle (CPU restatement of the reference's algorithm, reference-shaped: kd-tree per class and
+    3 OpenMP sections per registration) on the host cores: cores//3 registrations in flight."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle
+
+    oracle.load()
+    cores = os.cpu_count() or 1
+    workers = max(1, cores // 3)
+    n = min(max_regs, max(workers, 1) * 4)
+    jobs = [pairs[i % len(pairs)] for i in range(n)]
+
+    def one(p):
+        oracle.icp_run(p["tgt"], p["src"], p["params"], p["init_guess"], threads=0, want_trace=False)
+        return 1
+
+    t0 = time.perf_counter()
+    done = 0
+    with ThreadPoolExecutor(workers) as ex:
+        for r in ex.map(one, jobs):
+            done += r
+            if time.perf_counter() - t0 > budget_s and done >= workers:
+                break
+    dt = time.perf_counter() - t0
+    return done / dt, min(cores, workers * 3), done, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=16, help="scan pairs per GPU per step")
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = {"c2": "synthetic KITTI-shape 64-beam 120k-pt scan-to-scan ICP, max 20 iters (BASELINE configs[1])",
+                "c3": "120k-pt source vs 600k-pt submap (BASELINE configs[2])"}.get(args.config, args.config)
+    config = {"workload": workload, "pairs_per_gpu_per_step": args.pairs, "l2_policy": "inputs larger than L2 "
+              f"({args.pairs} pairs x 11.5 MB of input clouds per GPU per step)", "parallelism": f"independent pairs x{world}"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        pairs = make_pairs([1000 + i for i in range(min(args.pairs, 8))], args.config)
+        per_step_budget = 8.0
+        for _ in range(args.warmup):
+            cpu_reference_rate(pairs, 1.0, 8)
+        t0 = time.perf_counter()
+        regs = 0
+        cores = 1
+        for _ in range(args.steps):
+            rate, cores, done, dt = cpu_reference_rate(pairs, per_step_budget, 10 ** 9)
+            regs += done
+        total = time.perf_counter() - t0
+        value = regs / total
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 accumulation",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{regs} registrations of the workload's pairs, reference-shaped "
+                                           f"(3 OpenMP sections each), {cores // 3} in flight"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+
+    from mulls_b200 import synth
+    from mulls_b200.registration import Context
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seeds = [1000 + rank * args.pairs + i for i in range(args.pairs)]
+    pairs = make_pairs(seeds, args.config)
+    keep = pin_pairs(pairs)  # noqa: F841
+    max_src = max(sum(len(s) for s in p["src"]) for p in pairs)
+    max_tgt = max(sum(len(t) for t in p["tgt"]) for p in pairs)
+    ctx = Context(local_rank, args.pairs, max_src, max_tgt)
+
+    # ---- device-resident throughput -----------------------------------------------------------
+    ctx.upload(pairs)
+    res = None
+    for _ in range(args.warmup):
+        res, _ = ctx.run_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms = 0.0
+    search_ms = 0.0
+    alg_bytes = 0
+    launches = 0
+    iters = 0
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        res, _ = ctx.run_resident()
+        st = ctx.stats()
+        dev_ms += st["ms_total"]
+        search_ms += st["ms_search"]
+        alg_bytes += st["algorithmic_bytes"]
+        launches += st["kernel_launches"]
+        iters += st["iterations"]
+    barrier()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    n_search_launches = args.steps * max(p["params"].max_iter_num for p in pairs)
+
+    # ---- end to end through the C-ABI with host buffers ------------------------------------------
+    for _ in range(2):
+        ctx.run_batch(pairs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e, _ = ctx.run_batch(pairs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(a.nbytes for p in pairs for side in ("tgt", "src") for a in p[side])
+    from mulls_b200 import abi
+    import ctypes
+
+    d2h = args.pairs * ctypes.sizeof(abi.IcpResult)
+
+    # quality gate: every registration must have converged onto the ground truth
+    errs = [synth.pose_error(r["T"], p["T_gt"]) for r, p in zip(res, pairs)]
+    ok = all(r["code"] == 1 for r in res) and max(e[0] for e in errs) < 0.05
+    assert ok, ("registration failed inside the benchmark", [r["code"] for r in res], errs)
+
+    # ---- reduce over ranks -------------------------------------------------------------------
+    dev_s = dev_ms / 1e3
+    if dist is not None:
+        t = torch.tensor([dev_s, e2e_s, wall_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, wall_s = [float(v) for v in t.tolist()]
+        s = torch.tensor([float(launches), float(alg_bytes), float(search_ms)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        launches = int(s[0].item())
+    total_regs = args.pairs * world * args.steps
+    value = total_regs / dev_s
+    e2e_value = total_regs / e2e_s
+
+    line = None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            try:
+                peak = float(json.load(open(peaks_path))["hbm_gbs"])
+                peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+            except Exception:
+                pass
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_search_dram_bytes_per_launch")
+            except Exception:
+                pass
+        # rank-0 figures for the dominant kernel (k_search): algorithmic bytes per launch / mean launch time
+        st_alg = alg_bytes if dist is None else alg_bytes  # rank 0's own launches
+        achieved = (st_alg / 1e9) / (search_ms / 1e3) if search_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 geometry / f64 accumulation", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "timing": "host clock around the synchronous C-ABI calls (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_search (transform + NN + claim)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": st_alg / max(n_search_launches, 1),
+                         "ms_per_launch": search_ms / max(n_search_launches, 1),
+                         "whole_path_frac": (alg_bytes / 1e9) / (dev_ms / 1e3) / peak},
+            "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "mean_iterations": iters / max(args.pairs * args.steps, 1),
+            "max_pose_err_vs_gt_m": max(e[0] for e in errs),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, done, dt = cpu_reference_rate(pairs, 12.0, 10 ** 9)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{done} registrations of the same pairs in {dt:.1f} s, oracle "
+                                              f"reference-shaped (3 OpenMP sections each), {max(1, cores // 3)} in flight"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -162,6 +162,7 @@ typedef struct mulls_run_stats {
     float ms_iterate;           /* device time of the iteration kernels */
     float ms_search;            /* device time of the fused transform+NN+claim kernel only */
     float ms_total;
+    float ms_search_iter[MULLS_MAX_TRACE_ITERS]; /* per-iteration device time of the search kernel */
 } mulls_run_stats;
 int mulls_get_stats(const mulls_ctx *ctx, mulls_run_stats *out);
 

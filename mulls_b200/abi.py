@@ -84,6 +84,7 @@ class RunStats(C.Structure):
         ("ms_iterate", C.c_float),
         ("ms_search", C.c_float),
         ("ms_total", C.c_float),
+        ("ms_search_iter", C.c_float * MAX_TRACE_ITERS),
     ]
 
 

@@ -25,6 +25,7 @@ struct GridView {
     const float4 *nrm; // class slice (w = original index, for tie-breaks)
     float ox, oy, oz, h0, inv_h0;
     int n_levels;
+    int leaf_count; // cells with at most this many points are scanned, larger ones are descended
 };
 
 __device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t &start, uint32_t &count) {
@@ -42,8 +43,29 @@ __device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t 
     }
 }
 
+// squared distance from p to the (slightly inflated) box of cell (x,y,z) at a level with cell size hl
+__device__ __forceinline__ float cell_dist2(const GridView &g, float px, float py, float pz, float hl, int x, int y,
+                                            int z) {
+    const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
+    const float xlo = g.ox + (float)x * hl - margin, xhi = g.ox + (float)(x + 1) * hl + margin;
+    const float ylo = g.oy + (float)y * hl - margin, yhi = g.oy + (float)(y + 1) * hl + margin;
+    const float zlo = g.oz + (float)z * hl - margin, zhi = g.oz + (float)(z + 1) * hl + margin;
+    const float ex = fmaxf(0.0f, fmaxf(xlo - px, px - xhi));
+    const float ey = fmaxf(0.0f, fmaxf(ylo - py, py - yhi));
+    const float ez = fmaxf(0.0f, fmaxf(zlo - pz, pz - zhi));
+    return ex * ex + ey * ey + ez * ez;
+}
+
+constexpr int kStackDepth = 96; // 7 pushes per descended level at most
+
 // Returns the nearest target (index within the class slice) under the total order (d2, original index),
 // among all targets with d2 <= r2_prune; exact for every target within the radius.
+//
+// Ascend: the 3x3x3 block of level-l cells around p contains every target closer than 0.999*h_l, so the
+// search stops at the first level whose block has been examined and whose coverage exceeds the best
+// distance found (or the search radius). Descend: a cell of the block holding many points is not scanned
+// but split into its 8 children (one hash probe each), nearest child first, each pruned by its box
+// distance against the best so far — the octree analogue of the kd-tree descent it replaces.
 __device__ __forceinline__ void nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
                                           int start_level, float &best_d2, int &best_j) {
     best_d2 = INFINITY;
@@ -52,31 +74,30 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
     const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
     const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
     const int L = g.n_levels;
+    uint32_t stack[kStackDepth]; // level(4) | x(12) | y(12) ... packed in two words would not fit: see pack()
+    uint32_t stack_z[kStackDepth];
     int l = min(max(start_level, 0), L - 1);
     for (;; ++l) {
-        const float hl = g.h0 * (float)(1 << l);
         const int ncell = (1 << kCoordBits) >> l;
         const int cx = c0x >> l, cy = c0y >> l, cz = c0z >> l;
-        const float margin = 1e-3f * g.h0;
-        for (int dz = -1; dz <= 1; ++dz) {
-            const int z = cz + dz;
-            if (z < 0 || z >= ncell) continue;
-            const float zlo = g.oz + (float)z * hl - margin, zhi = g.oz + (float)(z + 1) * hl + margin;
-            const float ez = fmaxf(0.0f, fmaxf(zlo - pz, pz - zhi));
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= ncell) continue;
-                const float ylo = g.oy + (float)y * hl - margin, yhi = g.oy + (float)(y + 1) * hl + margin;
-                const float ey = fmaxf(0.0f, fmaxf(ylo - py, py - yhi));
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int x = cx + dx;
-                    if (x < 0 || x >= ncell) continue;
-                    const float xlo = g.ox + (float)x * hl - margin, xhi = g.ox + (float)(x + 1) * hl + margin;
-                    const float ex = fmaxf(0.0f, fmaxf(xlo - px, px - xhi));
-                    // a cell farther than the best so far (or than the radius) cannot change the result
-                    if (ex * ex + ey * ey + ez * ez > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
-                    uint32_t start, count;
-                    if (!probe(g, cell_key(l, morton36((uint32_t)x, (uint32_t)y, (uint32_t)z)), start, count)) continue;
+        for (int k = 0; k < 27; ++k) {
+            // centre cell first: a good candidate early makes the box-distance test prune the rest
+            const int x = cx + ((k % 3) + 1) % 3 - 1, y = cy + ((k / 3) % 3 + 1) % 3 - 1, z = cz + ((k / 9) + 1) % 3 - 1;
+            if (x < 0 || y < 0 || z < 0 || x >= ncell || y >= ncell || z >= ncell) continue;
+            int sp = 0;
+            stack[0] = ((uint32_t)l << 24) | ((uint32_t)x << 12) | (uint32_t)y;
+            stack_z[0] = (uint32_t)z;
+            sp = 1;
+            while (sp > 0) {
+                --sp;
+                const uint32_t w = stack[sp];
+                const int lv = (int)(w >> 24), vx = (int)((w >> 12) & 0xfff), vy = (int)(w & 0xfff), vz = (int)stack_z[sp];
+                const float hl = g.h0 * (float)(1 << lv);
+                // a cell farther than the best so far (or than the radius) cannot change the result
+                if (cell_dist2(g, px, py, pz, hl, vx, vy, vz) > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                uint32_t start, count;
+                if (!probe(g, cell_key(lv, morton36((uint32_t)vx, (uint32_t)vy, (uint32_t)vz)), start, count)) continue;
+                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStackDepth) {
                     for (uint32_t j = start; j < start + count; ++j) {
                         const float4 q = __ldg(&g.pos[j]);
                         const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
@@ -89,10 +110,25 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
                             if (oj < ob) best_j = (int)j;
                         }
                     }
+                } else {
+                    // push the 8 children, the one nearest to p last (popped first)
+                    const float hc = 0.5f * hl;
+                    const int ox = (px >= g.ox + ((float)vx + 0.5f) * hl) ? 1 : 0;
+                    const int oy = (py >= g.oy + ((float)vy + 0.5f) * hl) ? 1 : 0;
+                    const int oz = (pz >= g.oz + ((float)vz + 0.5f) * hl) ? 1 : 0;
+                    const int near_child = ox | (oy << 1) | (oz << 2);
+                    (void)hc;
+                    for (int c = 7; c >= 0; --c) {
+                        const int ch = c ^ near_child; // c = 0 -> nearest octant, pushed last
+                        stack[sp] = ((uint32_t)(lv - 1) << 24) | ((uint32_t)(2 * vx + (ch & 1)) << 12) |
+                                    (uint32_t)(2 * vy + ((ch >> 1) & 1));
+                        stack_z[sp] = (uint32_t)(2 * vz + ((ch >> 2) & 1));
+                        ++sp;
+                    }
                 }
             }
         }
-        const float cover = 0.999f * hl; // every target closer than this has been examined
+        const float cover = 0.999f * g.h0 * (float)(1 << l); // every target closer than this has been examined
         const float cover2 = cover * cover;
         if (best_d2 <= cover2) break;   // the best found is the global nearest
         if (cover2 >= r2_prune) break;  // whole search radius examined
@@ -101,7 +137,7 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
 }
 
 // ---- k_search ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0) {
+__global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count) {
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
@@ -138,6 +174,7 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
         g.ox = ps.origin[0], g.oy = ps.origin[1], g.oz = ps.origin[2];
         g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
         g.n_levels = ps.n_levels;
+        g.leaf_count = leaf_count;
         // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
         const float max_distance_f = 2.5f * ps.thre;
         const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;

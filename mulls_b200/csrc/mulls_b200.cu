@@ -39,6 +39,7 @@ struct mulls_ctx {
     bool uploaded = false;
     // tunables
     int start_level0 = 1;
+    int leaf_count = 24;
     float h0_min = 0.125f;
     int want_trace = 0;
     // timing
@@ -228,6 +229,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return MULLS_E_ARG;
     std::string n(name);
     if (n == "start_level") ctx->start_level0 = value;
+    else if (n == "leaf_count") ctx->leaf_count = value;
     else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
     else return MULLS_E_ARG;
     return MULLS_OK;
@@ -407,7 +409,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
         size_t bytes = ctx->cub_temp_bytes;
         CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, bytes, A.keys_a, A.keys_b, A.vals_a, A.vals_b, (int)n_in, 0,
                                            36 + seg_bits, st));
-        launches += 5; // CUB onesweep: histogram + one pass per digit (library kernels, not ours)
+        // (CUB's radix-sort kernels are library launches and are not counted in kernel_launches)
     }
     k_seg_offsets<<<1, 256, 0, st>>>(A, np);
     ++launches;
@@ -430,7 +432,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
         for (int it = 0; it < ctx->max_iter_max; ++it) {
             const int buf = it & 1;
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0);
+            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
             k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
             k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
@@ -465,6 +467,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
     for (int it = 0; it < n_search_ev; ++it) {
         float t = 0.f;
         cudaEventElapsedTime(&t, ctx->ev_search[2 * it], ctx->ev_search[2 * it + 1]);
+        S.ms_search_iter[it] = t;
         ms += t;
     }
     S.ms_search = ms;

@@ -160,7 +160,9 @@ class Context:
     def stats(self) -> dict:
         s = abi.RunStats()
         self._check(self.lib.mulls_get_stats(self.handle, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in abi.RunStats._fields_}
+        d = {k: getattr(s, k) for k, _ in abi.RunStats._fields_}
+        d["ms_search_iter"] = [float(v) for v in s.ms_search_iter]
+        return d
 
 
 class CRegistration:

@@ -146,8 +146,9 @@ def scan(scene: dict, pose: np.ndarray, seed: int, n_points: int = 120000, beams
         ok = (disc > 0) & (a > 1e-12)
         sq = np.sqrt(np.where(ok, disc, 0.0))
         t = np.where(ok, (-b - sq) / (2 * np.where(ok, a, 1.0)), np.inf)
-        z = o[2] + t * d[:, 2]
-        t = np.where((t > 1e-6) & (z >= 0.0) & (z <= h), t, np.inf)
+        with np.errstate(invalid="ignore"):
+            z = o[2] + t * d[:, 2]
+            t = np.where((t > 1e-6) & (z >= 0.0) & (z <= h), t, np.inf)
         m = t < best_t
         best_t[m], best_cls[m] = t[m], abi.PILLAR
         best_vec[m] = (0.0, 0.0, 1.0)
@@ -164,8 +165,9 @@ def scan(scene: dict, pose: np.ndarray, seed: int, n_points: int = 120000, beams
         ok = (disc > 0) & (a > 1e-12)
         sq = np.sqrt(np.where(ok, disc, 0.0))
         t = np.where(ok, (-b - sq) / (2 * np.where(ok, a, 1.0)), np.inf)
-        al = o[axis] + t * d[:, axis]
-        t = np.where((t > 1e-6) & (al >= a0) & (al <= a1), t, np.inf)
+        with np.errstate(invalid="ignore"):
+            al = o[axis] + t * d[:, axis]
+            t = np.where((t > 1e-6) & (al >= a0) & (al <= a1), t, np.inf)
         m = t < best_t
         best_t[m], best_cls[m] = t[m], abi.BEAM
         vec = np.zeros(3)
