@@ -120,6 +120,8 @@ struct DeviceArrays {
     ChunkDesc *in_chunks;
     ChunkDesc *it_chunks;
     mulls_icp_trace *trace; // may be null
+    int *running;           // pairs still iterating (device counter)
+    volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop
 };
 
 } // namespace mulls

@@ -113,8 +113,8 @@ __global__ void k_pair_setup(DeviceArrays A, int n_pairs, float h0_min) {
     // number of levels: the top level's guaranteed coverage 0.999*h must reach the largest search
     // radius 2.5*dis_thre_unit (filter_dis_times, cregistration.hpp:1707)
     const float rmax = 2.5f * pc.thre_unit * 1.0001f;
-    int L = 1;
-    while (L < kMaxLevels && 0.999f * h0 * (float)(1 << (L - 1)) < rmax) ++L;
+    int L = 2; // level l's 2x2x2 block covers 0.999 * h0 * 2^(l-1) (see nn_search)
+    while (L < kMaxLevels && 0.999f * 0.5f * h0 * (float)(1 << (L - 1)) < rmax) ++L;
     ps.n_levels = L;
 
     for (int i = 0; i < 16; ++i) {
@@ -132,7 +132,12 @@ __global__ void k_pair_setup(DeviceArrays A, int n_pairs, float h0_min) {
     ps.iters_entered = 0;
     ps.final_buf = 0;
     ps.alg_bytes = 0;
-    if (pc.max_iter <= 0) ps.status = kDone;
+    if (pc.max_iter <= 0) {
+        ps.status = kDone;
+        const int left = atomicSub(A.running, 1) - 1;
+        *A.h_running = left;
+        __threadfence_system();
+    }
 }
 
 // ---- k_make_keys: intersection filter (cfilter.hpp:950-981: strictly inside) + 64-bit sort key
@@ -269,12 +274,16 @@ __device__ __forceinline__ void hash_insert(HashEntry *table, uint32_t mask, uin
         slot = (slot + 1) & mask;
     }
 }
+// key_hi carries, above the 16 key bits, the 8-bit mask of existing children (set while closing cells)
+constexpr uint32_t kKeyHiMask = 0xffffu;
 __device__ __forceinline__ HashEntry *hash_find(HashEntry *table, uint32_t mask, uint64_t key) {
     uint32_t slot = hash_key(key) & mask;
+    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
     while (true) {
-        const unsigned long long k = *reinterpret_cast<const unsigned long long *>(&table[slot]);
-        if (k == key) return &table[slot];
-        if (k == 0ull) return nullptr;
+        const uint32_t lo = *reinterpret_cast<volatile uint32_t *>(&table[slot].key_lo);
+        const uint32_t hi = *reinterpret_cast<volatile uint32_t *>(&table[slot].key_hi);
+        if (lo == klo && (hi & kKeyHiMask) == khi) return &table[slot];
+        if (lo == 0u && hi == 0u) return nullptr;
         slot = (slot + 1) & mask;
     }
 }
@@ -338,8 +347,13 @@ __global__ void __launch_bounds__(256) k_hash_build(DeviceArrays A, const uint64
         HashEntry *table = A.hash + ps.hash_base[cls];
         const uint64_t m = kprev & mmask;
         for (int l = 0; l <= top && l < L; ++l) {
-            HashEntry *e = hash_find(table, ps.hash_mask[cls], cell_key(l, m >> (3 * l)));
+            const uint64_t code = m >> (3 * l);
+            HashEntry *e = hash_find(table, ps.hash_mask[cls], cell_key(l, code));
             if (e) e->count = local_end - e->start;
+            if (l + 1 < L) { // tell the parent which of its 8 children exists
+                HashEntry *par = hash_find(table, ps.hash_mask[cls], cell_key(l + 1, code >> 3));
+                if (par) atomicOr(&par->key_hi, 1u << (16 + (uint32_t)(code & 7)));
+            }
         }
     }
 }

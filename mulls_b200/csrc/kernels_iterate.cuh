@@ -28,44 +28,43 @@ struct GridView {
     int leaf_count; // cells with at most this many points are scanned, larger ones are descended
 };
 
-__device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t &start, uint32_t &count) {
+__device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t &start, uint32_t &count,
+                                      uint32_t &child_mask) {
     uint32_t slot = hash_key(key) & g.mask;
+    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
     while (true) {
         const uint4 e = __ldg(reinterpret_cast<const uint4 *>(&g.table[slot]));
-        const uint64_t k = (uint64_t)e.x | ((uint64_t)e.y << 32);
-        if (k == key) {
+        if (e.x == klo && (e.y & kKeyHiMask) == khi) {
             start = e.z;
             count = e.w;
+            child_mask = e.y >> 16;
             return true;
         }
-        if (k == 0ull) return false;
+        if (e.x == 0u && e.y == 0u) return false;
         slot = (slot + 1) & g.mask;
     }
 }
 
-// squared distance from p to the (slightly inflated) box of cell (x,y,z) at a level with cell size hl
-__device__ __forceinline__ float cell_dist2(const GridView &g, float px, float py, float pz, float hl, int x, int y,
-                                            int z) {
-    const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment (DESIGN.md)
-    const float xlo = g.ox + (float)x * hl - margin, xhi = g.ox + (float)(x + 1) * hl + margin;
-    const float ylo = g.oy + (float)y * hl - margin, yhi = g.oy + (float)(y + 1) * hl + margin;
-    const float zlo = g.oz + (float)z * hl - margin, zhi = g.oz + (float)(z + 1) * hl + margin;
-    const float ex = fmaxf(0.0f, fmaxf(xlo - px, px - xhi));
-    const float ey = fmaxf(0.0f, fmaxf(ylo - py, py - yhi));
-    const float ez = fmaxf(0.0f, fmaxf(zlo - pz, pz - zhi));
-    return ex * ex + ey * ey + ez * ez;
+// distance along one axis from p to the (slightly inflated) extent of cell x at a level with cell size H
+__device__ __forceinline__ float axis_dist(float o, float H, int x, float p, float margin) {
+    const float lo = o + (float)x * H - margin, hi = o + (float)(x + 1) * H + margin;
+    return fmaxf(0.0f, fmaxf(lo - p, p - hi));
 }
 
-constexpr int kStackDepth = 96; // 7 pushes per descended level at most
+constexpr int kStackDepth = 48; // DFS entries: at most 7 stay behind per descended level
 
-// Returns the nearest target (index within the class slice) under the total order (d2, original index),
-// among all targets with d2 <= r2_prune; exact for every target within the radius.
+// Exact nearest target (index within the class slice) under the total order (d2, original index) among
+// all targets with d2 <= r2_prune.
 //
-// Ascend: the 3x3x3 block of level-l cells around p contains every target closer than 0.999*h_l, so the
-// search stops at the first level whose block has been examined and whose coverage exceeds the best
-// distance found (or the search radius). Descend: a cell of the block holding many points is not scanned
-// but split into its 8 children (one hash probe each), nearest child first, each pruned by its box
-// distance against the best so far — the octree analogue of the kd-tree descent it replaces.
+// Ascend: at level l >= 1 the 2x2x2 block of cells that contains p's own cell and, along every axis, the
+// neighbour on the side of the half of the cell p lies in, covers the 3x3x3 block of level l-1 around p.
+// Every target closer than cover_l = 0.999 * h_(l-1) is therefore inside the block (the 0.1% absorbs the
+// float rounding of the cell assignment), and the search stops at the first level whose block has been
+// examined with best <= cover_l or cover_l >= radius. 8 probes per level instead of 27.
+// Descend: a cell holding more than leaf_count points is not scanned but split: its entry carries the
+// mask of existing children, the per-axis distances to the two child slabs are computed once, and only
+// children that exist and can still beat the best distance are pushed (nearest octant last = popped first;
+// Morton code = parent code << 3 | child) — the octree analogue of the kd-tree descent it replaces.
 __device__ __forceinline__ void nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
                                           int start_level, float &best_d2, int &best_j) {
     best_d2 = INFINITY;
@@ -74,65 +73,105 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
     const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
     const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
     const int L = g.n_levels;
-    uint32_t stack[kStackDepth]; // level(4) | x(12) | y(12) ... packed in two words would not fit: see pack()
-    uint32_t stack_z[kStackDepth];
-    int l = min(max(start_level, 0), L - 1);
+    const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment (DESIGN.md)
+    uint32_t st_code[kStackDepth], st_meta[kStackDepth], st_z[kStackDepth];
+    float st_d2[kStackDepth];
+    int l = min(max(start_level, 1), L - 1);
     for (;; ++l) {
+        const float H = g.h0 * (float)(1 << l);
         const int ncell = (1 << kCoordBits) >> l;
-        const int cx = c0x >> l, cy = c0y >> l, cz = c0z >> l;
-        for (int k = 0; k < 27; ++k) {
-            // centre cell first: a good candidate early makes the box-distance test prune the rest
-            const int x = cx + ((k % 3) + 1) % 3 - 1, y = cy + ((k / 3) % 3 + 1) % 3 - 1, z = cz + ((k / 9) + 1) % 3 - 1;
-            if (x < 0 || y < 0 || z < 0 || x >= ncell || y >= ncell || z >= ncell) continue;
+        int xs[2], ys[2], zs[2];
+        xs[0] = c0x >> l, ys[0] = c0y >> l, zs[0] = c0z >> l;
+        xs[1] = xs[0] + (((c0x >> (l - 1)) & 1) ? 1 : -1);
+        ys[1] = ys[0] + (((c0y >> (l - 1)) & 1) ? 1 : -1);
+        zs[1] = zs[0] + (((c0z >> (l - 1)) & 1) ? 1 : -1);
+        float ex[2], ey[2], ez[2];
+        uint64_t sx[2], sy[2], sz[2];
+        bool vx[2], vy[2], vz[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            vx[i] = xs[i] >= 0 && xs[i] < ncell;
+            vy[i] = ys[i] >= 0 && ys[i] < ncell;
+            vz[i] = zs[i] >= 0 && zs[i] < ncell;
+            ex[i] = axis_dist(g.ox, H, xs[i], px, margin);
+            ey[i] = axis_dist(g.oy, H, ys[i], py, margin);
+            ez[i] = axis_dist(g.oz, H, zs[i], pz, margin);
+            ex[i] *= ex[i], ey[i] *= ey[i], ez[i] *= ez[i];
+            sx[i] = spread12((uint32_t)xs[i]);
+            sy[i] = spread12((uint32_t)ys[i]) << 1;
+            sz[i] = spread12((uint32_t)zs[i]) << 2;
+        }
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) { // k = 0: p's own cell first
+            const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
+            if (!(vx[i] && vy[j] && vz[m])) continue;
             int sp = 0;
-            stack[0] = ((uint32_t)l << 24) | ((uint32_t)x << 12) | (uint32_t)y;
-            stack_z[0] = (uint32_t)z;
-            sp = 1;
+            {
+                const uint64_t code = sx[i] | sy[j] | sz[m];
+                st_code[0] = (uint32_t)code;
+                st_meta[0] = (uint32_t)(code >> 32) | ((uint32_t)l << 4) | ((uint32_t)xs[i] << 8) | ((uint32_t)ys[j] << 20);
+                st_z[0] = (uint32_t)zs[m];
+                st_d2[0] = ex[i] + ey[j] + ez[m];
+                sp = 1;
+            }
             while (sp > 0) {
                 --sp;
-                const uint32_t w = stack[sp];
-                const int lv = (int)(w >> 24), vx = (int)((w >> 12) & 0xfff), vy = (int)(w & 0xfff), vz = (int)stack_z[sp];
-                const float hl = g.h0 * (float)(1 << lv);
                 // a cell farther than the best so far (or than the radius) cannot change the result
-                if (cell_dist2(g, px, py, pz, hl, vx, vy, vz) > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
-                uint32_t start, count;
-                if (!probe(g, cell_key(lv, morton36((uint32_t)vx, (uint32_t)vy, (uint32_t)vz)), start, count)) continue;
+                if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                const uint32_t meta = st_meta[sp];
+                const uint64_t code = (uint64_t)st_code[sp] | ((uint64_t)(meta & 0xf) << 32);
+                const int lv = (int)((meta >> 4) & 0xf);
+                uint32_t start, count, cmask;
+                if (!probe(g, cell_key(lv, code), start, count, cmask)) continue;
                 if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStackDepth) {
-                    for (uint32_t j = start; j < start + count; ++j) {
-                        const float4 q = __ldg(&g.pos[j]);
+                    for (uint32_t jj = start; jj < start + count; ++jj) {
+                        const float4 q = __ldg(&g.pos[jj]);
                         const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
                         if (d2 < best_d2) {
                             best_d2 = d2;
-                            best_j = (int)j;
-                        } else if (d2 == best_d2 && (int)j != best_j) {
-                            const int oj = __float_as_int(__ldg(&g.nrm[j]).w);
+                            best_j = (int)jj;
+                        } else if (d2 == best_d2 && (int)jj != best_j) {
+                            const int oj = __float_as_int(__ldg(&g.nrm[jj]).w);
                             const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
-                            if (oj < ob) best_j = (int)j;
+                            if (oj < ob) best_j = (int)jj;
                         }
                     }
                 } else {
-                    // push the 8 children, the one nearest to p last (popped first)
-                    const float hc = 0.5f * hl;
-                    const int ox = (px >= g.ox + ((float)vx + 0.5f) * hl) ? 1 : 0;
-                    const int oy = (py >= g.oy + ((float)vy + 0.5f) * hl) ? 1 : 0;
-                    const int oz = (pz >= g.oz + ((float)vz + 0.5f) * hl) ? 1 : 0;
-                    const int near_child = ox | (oy << 1) | (oz << 2);
-                    (void)hc;
+                    const int cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)st_z[sp];
+                    const float hc = 0.5f * g.h0 * (float)(1 << lv);
+                    float ax[2], ay[2], az[2];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        ax[b] = axis_dist(g.ox, hc, 2 * cx + b, px, margin);
+                        ay[b] = axis_dist(g.oy, hc, 2 * cy + b, py, margin);
+                        az[b] = axis_dist(g.oz, hc, 2 * cz + b, pz, margin);
+                        ax[b] *= ax[b], ay[b] *= ay[b], az[b] *= az[b];
+                    }
+                    // octant of p relative to the cell centre: the child with zero (or least) distance
+                    const int near_child = (ax[1] < ax[0] ? 1 : 0) | (ay[1] < ay[0] ? 2 : 0) | (az[1] < az[0] ? 4 : 0);
+                    const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+#pragma unroll 1
                     for (int c = 7; c >= 0; --c) {
-                        const int ch = c ^ near_child; // c = 0 -> nearest octant, pushed last
-                        stack[sp] = ((uint32_t)(lv - 1) << 24) | ((uint32_t)(2 * vx + (ch & 1)) << 12) |
-                                    (uint32_t)(2 * vy + ((ch >> 1) & 1));
-                        stack_z[sp] = (uint32_t)(2 * vz + ((ch >> 2) & 1));
+                        const int ch = c ^ near_child; // c = 0 -> nearest octant, pushed last (popped first)
+                        if (!((cmask >> ch) & 1u)) continue;
+                        const float d2c = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
+                        if (d2c > bound) continue;
+                        const uint64_t cc = (code << 3) | (uint64_t)ch;
+                        st_code[sp] = (uint32_t)cc;
+                        st_meta[sp] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) |
+                                      ((uint32_t)(2 * cx + (ch & 1)) << 8) | ((uint32_t)(2 * cy + ((ch >> 1) & 1)) << 20);
+                        st_z[sp] = (uint32_t)(2 * cz + (ch >> 2));
+                        st_d2[sp] = d2c;
                         ++sp;
                     }
                 }
             }
         }
-        const float cover = 0.999f * g.h0 * (float)(1 << l); // every target closer than this has been examined
+        const float cover = 0.999f * 0.5f * H; // every target closer than this has been examined
         const float cover2 = cover * cover;
-        if (best_d2 <= cover2) break;   // the best found is the global nearest
-        if (cover2 >= r2_prune) break;  // whole search radius examined
-        if (l == L - 1) break;          // (n_levels is chosen so that the line above fires first)
+        if (best_d2 <= cover2) break;  // the best found is the global nearest
+        if (cover2 >= r2_prune) break; // whole search radius examined
+        if (l == L - 1) break;         // (n_levels is chosen so that the line above fires first)
     }
 }
 
@@ -183,7 +222,7 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
         const float hint = A.src_hint[buf][gi];
         if (hint >= 0.0f) {
             // smallest level whose guaranteed coverage exceeds 1.3x the previous NN distance
-            const float need = 1.3f * sqrtf(hint) / (0.999f * g.h0);
+            const float need = 1.3f * sqrtf(hint) / (0.999f * 0.5f * g.h0); // cover_l = 0.999 * h0 * 2^(l-1)
             sl = (need <= 1.0f) ? 0 : (ilogbf(need) + 1);
         }
         nn_search(g, p.x, p.y, p.z, r2_prune, sl, best_d2, best_j);
@@ -421,6 +460,13 @@ __device__ __forceinline__ bool too_few(const PairConst &pc, const PairState &ps
     return total < 40 || nec < 20 || ratio < pc.min_ratio;
 }
 
+// A pair stops iterating: publish the number of pairs still running to the host's launch loop.
+__device__ __forceinline__ void pair_left_running(DeviceArrays &A) {
+    const int left = atomicSub(A.running, 1) - 1;
+    *A.h_running = left;
+    __threadfence_system();
+}
+
 // Solve + state update of one pair; executed by thread 0 of the last block of k_accumulate
 // (cregistration.hpp:1301-1400 after the summations). S = per-class sums [6][kTerms] in shared memory.
 __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *S, double *sm /*>= 150 doubles*/,
@@ -451,6 +497,7 @@ __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *
     if (few) {
         ps.code = -2;
         ps.status = kDone;
+        pair_left_running(A);
         return; // TempTran = identity: T_total stays (:1307-1310, :1403)
     }
     // :1314-1315 threshold update
@@ -534,6 +581,7 @@ __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *
     if (ts_norm > (double)pc.max_t || rs_angle > (double)pc.max_r) { // :1348-1354
         ps.code = -1;
         ps.status = kDone;
+        pair_left_running(A);
         return;
     }
     // :1400 / :1403 — the increment is always folded into the accumulated transform
@@ -542,6 +590,7 @@ __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *
     if (i == pc.max_iter - 1 || (i > 2 && ts_norm < (double)pc.conv_t && rs_angle < (double)pc.conv_r)) { // :1357
         ps.status = kNeedPosterior;
         ps.final_buf = buf_written;
+        pair_left_running(A);
         return;
     }
     ps.iter = i + 1;
@@ -565,97 +614,110 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
     __shared__ uint32_t s_base;
     __shared__ bool s_last;
 
-    // (1) destination of the kept sources: blocks before this one in the same (pair, class)
-    {
-        uint32_t acc = 0;
-        const uint32_t first_chunk = pc.class_chunk_begin[c];
-        for (uint32_t b = first_chunk + threadIdx.x; b < blockIdx.x; b += kIterBlock) acc += A.blk_kept[b];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_off[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-            for (int w = 0; w < kWarps; ++w) t += s_off[w];
-            s_base = t;
-        }
-        __syncthreads();
-    }
+    // blocks entirely past the live part of the class only report an empty partial
+    const bool dead_block = (int)cd.first >= ns;
+    uint32_t dst_local = 0;
     uint8_t fl = 0;
     uint32_t gi = 0;
-    if (valid) {
-        gi = pc.src_base[c] + local;
-        fl = A.flags[gi];
-    }
-    const bool kept = (fl & 1) != 0, pass = (fl & 2) != 0;
-    const unsigned kb = __ballot_sync(0xffffffffu, kept);
-    if (lane == 0) s_off[warp] = __popc(kb);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t t = s_off[w];
-            s_off[w] = run;
-            run += t;
+    bool kept = false, pass = false;
+    double t[32];
+    if (!dead_block) {
+        // (1) destination of the kept sources: blocks before this one in the same (pair, class)
+        {
+            uint32_t acc = 0;
+            const uint32_t first_chunk = pc.class_chunk_begin[c];
+            for (uint32_t b = first_chunk + threadIdx.x; b < blockIdx.x; b += kIterBlock) acc += A.blk_kept[b];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_off[warp] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t tt = 0;
+                for (int w = 0; w < kWarps; ++w) tt += s_off[w];
+                s_base = tt;
+            }
+            __syncthreads();
         }
-        s_off[kWarps] = run;
-    }
-    __syncthreads();
-    const uint32_t dst_local = s_base + s_off[warp] + __popc(kb & ((1u << lane) - 1u));
+        if (valid) {
+            gi = pc.src_base[c] + local;
+            fl = A.flags[gi];
+        }
+        kept = (fl & 1) != 0, pass = (fl & 2) != 0;
+        const unsigned kb = __ballot_sync(0xffffffffu, kept);
+        if (lane == 0) s_off[warp] = __popc(kb);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t tt = s_off[w];
+                s_off[w] = run;
+                run += tt;
+            }
+            s_off[kWarps] = run;
+        }
+        __syncthreads();
+        dst_local = s_base + s_off[warp] + __popc(kb & ((1u << lane) - 1u));
 
-    // (2) terms of the surviving correspondences
-    double t[kTerms];
+        // (2) terms of the surviving correspondences
 #pragma unroll
-    for (int k = 0; k < kTerms; ++k) t[k] = 0.0;
-    float w_store = 0.0f;
-    int j = -1;
-    float4 p = make_float4(0, 0, 0, 0), n = make_float4(0, 0, 0, 0);
-    float d2 = 0.0f;
-    if (valid) {
-        p = A.src_pos[buf][gi];
-        n = A.src_nrm[buf][gi];
-        j = A.nn_idx[gi];
-        d2 = A.nn_d2[gi];
-        if (j >= 0) A.claim[pc.tgt_base[c] + j] = kClaimFree; // reset the table for the next iteration
-    }
-    float ratio_unused;
-    const bool few = too_few(pc, ps, ps.n_corr, ratio_unused);
-    if (pass && !few) {
-        const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
-        const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
-        const int it = ps.iter;
-        const bool resid_w = pc.w_residual && it > 2; // :1905-1907
-        const bool dist_w = pc.w_dist != 0, inten_w = pc.w_intensity != 0;
-        if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) {
-            const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, ps.n_corr);
-            terms_pt2pl(p, p.w, q, qn, wc, it, dist_w, resid_w, inten_w, pc.win_pt2pl, t, w_store);
-        } else if (c == MULLS_PILLAR || c == MULLS_BEAM) {
-            terms_pt2li(p, p.w, q, qn, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2li, t, w_store);
-        } else {
-            terms_pt2pt(p, p.w, q, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2pt, t);
-            w_store = d2; // pt2pt never stores a weight: the posterior reads the squared NN distance (Q2)
+        for (int k = 0; k < 32; ++k) t[k] = 0.0;
+        float w_store = 0.0f;
+        int j = -1;
+        float4 p = make_float4(0, 0, 0, 0), n = make_float4(0, 0, 0, 0);
+        float d2 = 0.0f;
+        if (valid) {
+            p = A.src_pos[buf][gi];
+            n = A.src_nrm[buf][gi];
+            j = A.nn_idx[gi];
+            d2 = A.nn_d2[gi];
+            if (j >= 0) A.claim[pc.tgt_base[c] + j] = kClaimFree; // reset the table for the next iteration
         }
-    }
-    // (3) compaction into the other buffer (order preserved: :1776-1789)
-    if (kept) {
-        const uint32_t gd = pc.src_base[c] + dst_local;
-        A.src_pos[buf ^ 1][gd] = p;
-        A.src_nrm[buf ^ 1][gd] = n;
-        A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
-        A.corr_j[gd] = pass ? j : -1;
-        A.corr_w[gd] = w_store;
-    }
-    // (4) block reduction in a fixed order
+        float ratio_unused;
+        const bool few = too_few(pc, ps, ps.n_corr, ratio_unused);
+        if (pass && !few) {
+            const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
+            const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
+            const int it = ps.iter;
+            const bool resid_w = pc.w_residual && it > 2; // :1905-1907
+            const bool dist_w = pc.w_dist != 0, inten_w = pc.w_intensity != 0;
+            if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) {
+                const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, ps.n_corr);
+                terms_pt2pl(p, p.w, q, qn, wc, it, dist_w, resid_w, inten_w, pc.win_pt2pl, t, w_store);
+            } else if (c == MULLS_PILLAR || c == MULLS_BEAM) {
+                terms_pt2li(p, p.w, q, qn, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2li, t, w_store);
+            } else {
+                terms_pt2pt(p, p.w, q, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2pt, t);
+                w_store = d2; // pt2pt never stores a weight: the posterior reads the squared NN distance (Q2)
+            }
+        }
+        // (3) compaction into the other buffer (order preserved: :1776-1789)
+        if (kept) {
+            const uint32_t gd = pc.src_base[c] + dst_local;
+            A.src_pos[buf ^ 1][gd] = p;
+            A.src_nrm[buf ^ 1][gd] = n;
+            A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
+            A.corr_j[gd] = pass ? j : -1;
+            A.corr_w[gd] = w_store;
+        }
+        // (4) block reduction in a fixed order. Warp level: reduce-scatter butterfly — at every step a
+        // lane keeps half of the terms and receives the partner's sums of that half, so after 5 steps
+        // lane i holds the warp total of term i (31 shuffles instead of 27 x 5).
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        double v = t[k];
+        for (int half = 16; half >= 1; half >>= 1) {
+            const bool upper = (lane & half) != 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][k] = v;
+            for (int k = 0; k < half; ++k) {
+                const double send = upper ? t[k] : t[k + half];
+                const double keep = upper ? t[k + half] : t[k];
+                t[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+            }
+        }
+        if (lane < kTerms) s_red[warp][lane] = t[0];
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x < 27) {
         double v = 0.0;
-        for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
+        if (!dead_block)
+            for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
         A.partials[(size_t)blockIdx.x * kTerms + threadIdx.x] = v;
     }
     // (5) last block of the pair: reduce all partials, solve, advance
@@ -849,6 +911,10 @@ __global__ void k_state_init(DeviceArrays A, int n_pairs) {
     for (int c = 0; c < kNumClasses; ++c) ps.hash_entries[c] = ps.n_corr[c] = 0;
     ps.arrive_acc = ps.arrive_post = 0;
     ps.status = kRunning;
+    if (p == 0) {
+        *A.running = n_pairs;
+        *A.h_running = n_pairs;
+    }
 }
 
 // ---- k_collect: pair state -> mulls_icp_result (device copy, then one D2H)

@@ -31,6 +31,8 @@ struct mulls_ctx {
     mulls_icp_result *d_results = nullptr;
     mulls_icp_result *h_results = nullptr; // pinned
     uint32_t *h_flags = nullptr;           // pinned copy of hash_used
+    int *h_running = nullptr;              // mapped pinned: pairs still iterating
+    std::vector<cudaEvent_t> ev_done;      // one per iteration (launch-loop flow control)
     mulls_icp_trace *d_trace = nullptr;
     std::vector<PairConst> h_pc;
     std::vector<ChunkDesc> h_in_chunks, h_it_chunks;
@@ -38,8 +40,8 @@ struct mulls_ctx {
     int max_iter_max = 0;
     bool uploaded = false;
     // tunables
-    int start_level0 = 1;
-    int leaf_count = 24;
+    int start_level0 = 5;
+    int leaf_count = 32;
     float h0_min = 0.125f;
     int want_trace = 0;
     // timing
@@ -114,6 +116,8 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->pca_buf) cudaFree(ctx->pca_buf);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->h_running) cudaFreeHost(ctx->h_running);
+    for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_search) cudaEventDestroy(e);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_ingest) cudaEventDestroy(ctx->ev_ingest);
@@ -156,7 +160,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
         return nullptr;
     }
     // every cloud adds at most one partial chunk
-    ctx->cap_it_chunks = ceil_div(cs, kIterBlock) + max_pairs * kNumClasses;
+    ctx->cap_it_chunks = ceil_div(cs, kIterBlock) + max_pairs * (kNumClasses + 1);
     ctx->cap_in_chunks = ceil_div(cin, kIngestBlock) + max_pairs * kNumSegs;
     DeviceArrays &A = ctx->A;
     float4 *in = nullptr;
@@ -201,7 +205,17 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ALLOC(A.it_chunks, ctx->cap_it_chunks);
     ALLOC(ctx->d_results, max_pairs);
     ALLOC(ctx->d_trace, max_pairs);
+    ALLOC(A.running, 1);
 #undef ALLOC
+    if ((e = cudaHostAlloc((void **)&ctx->h_running, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
+        return fail("mapped flag", e);
+    {
+        int *dptr = nullptr;
+        if ((e = cudaHostGetDevicePointer((void **)&dptr, ctx->h_running, 0)) != cudaSuccess) return fail("mapped flag", e);
+        A.h_running = dptr;
+    }
+    ctx->ev_done.resize(MULLS_MAX_TRACE_ITERS);
+    for (auto &ev : ctx->ev_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     A.trace = nullptr;
     if ((e = cudaMallocHost((void **)&ctx->h_results, max_pairs * sizeof(mulls_icp_result))) != cudaSuccess)
         return fail("pinned results", e);
@@ -334,7 +348,10 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
             const size_t n = src[p * kNumClasses + c].n;
             s_off += n;
             pc.class_chunk_begin[c] = (uint32_t)ctx->h_it_chunks.size();
-            for (size_t f = 0; f < n; f += kIterBlock) ctx->h_it_chunks.push_back(ChunkDesc{(uint32_t)p, (uint32_t)c, (uint32_t)f});
+            // class 0 always owns at least one chunk so that the per-pair "last block" logic (status
+            // codes, iteration counter) also runs for pairs without any source point
+            const size_t n_eff = (c == 0 && n == 0) ? 1 : n;
+            for (size_t f = 0; f < n_eff; f += kIterBlock) ctx->h_it_chunks.push_back(ChunkDesc{(uint32_t)p, (uint32_t)c, (uint32_t)f});
             pc.src_index_base[c] = src_index_base ? src_index_base[c] : 0;
             pc.src_global_n[c] = src_global_n ? src_global_n[c] : (uint32_t)n;
         }
@@ -430,12 +447,20 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
     int n_search_ev = 0;
     if (n_itc) {
         for (int it = 0; it < ctx->max_iter_max; ++it) {
+            // flow control: stay at most two iterations ahead of the device and stop launching as soon
+            // as every pair has converged or failed (the device mirrors its counter into mapped memory)
+            if (it >= 2) {
+                while (cudaEventQuery(ctx->ev_done[it - 2]) == cudaErrorNotReady) {
+                }
+                if (*(volatile int *)ctx->h_running <= 0) break;
+            }
             const int buf = it & 1;
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
             k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
             k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
             k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            CK(cudaEventRecord(ctx->ev_done[it], st));
             launches += 3;
             n_search_ev = it + 1;
         }

@@ -9,9 +9,9 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 pair = synth.make_pair(1000, cfg)
 ctx = Context(0, 2, 700000, 700000)
 ref = None
-for h0 in (125, 62, 250):
-    for sl in (0, 1, 2, 3):
-        for leaf in (8, 24, 64):
+for h0 in (125, 250):
+    for sl in (2, 4, 5, 6):
+        for leaf in (16, 32, 64, 128):
             ctx.set_tunable("h0_min_mm", h0); ctx.set_tunable("start_level", sl); ctx.set_tunable("leaf_count", leaf)
             ctx.upload([pair])
             best = None
