@@ -30,6 +30,24 @@ METRIC = "scan-pair registrations/sec (120k-pt 64-beam)"
 UNIT = "registrations/s"
 
 
+def rank_seeds(rank, pairs_per_gpu):
+    """Independent scan pairs shard across ranks with no exchange: rank r owns seeds 1000 + r*P .. 1000 + (r+1)*P - 1."""
+    return [1000 + rank * pairs_per_gpu + i for i in range(pairs_per_gpu)]
+
+
+def reduce_over_ranks(dist, device, times, sums):
+    """Timing = max over ranks, counters = sum over ranks (dist is torch.distributed or None)."""
+    if dist is None:
+        return list(times), list(sums)
+    import torch
+
+    t = torch.tensor(list(times), device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = torch.tensor(list(sums), device=device, dtype=torch.float64)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()], [float(v) for v in s.tolist()]
+
+
 def _gen_one(args):
     seed, config = args
     from mulls_b200 import synth
@@ -205,7 +223,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seeds = [1000 + rank * args.pairs + i for i in range(args.pairs)]
+    seeds = rank_seeds(rank, args.pairs)
     pairs = make_pairs(seeds, args.config)
     keep = pin_pairs(pairs)  # noqa: F841
     max_src = max(sum(len(s) for s in p["src"]) for p in pairs)
@@ -261,13 +279,9 @@ def main():
 
     # ---- reduce over ranks -------------------------------------------------------------------
     dev_s = dev_ms / 1e3
-    if dist is not None:
-        t = torch.tensor([dev_s, e2e_s, wall_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s, wall_s = [float(v) for v in t.tolist()]
-        s = torch.tensor([float(launches), float(alg_bytes), float(search_ms)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        launches = int(s[0].item())
+    (dev_s, e2e_s, wall_s), (launches_all, _, _) = reduce_over_ranks(dist, "cuda", [dev_s, e2e_s, wall_s],
+                                                                   [float(launches), float(alg_bytes), float(search_ms)])
+    launches = int(launches_all)
     total_regs = args.pairs * world * args.steps
     value = total_regs / dev_s
     e2e_value = total_regs / e2e_s

@@ -1,0 +1,124 @@
+// Drop-in shim: lo::CRegistration<PointT>::mm_lls_icp over the mulls_b200 C-ABI.
+//
+// A MULLS maintainer keeps include/common/cregistration.hpp as it is and replaces the BODY of
+// mm_lls_icp (cregistration.hpp:1125-1440) by
+//
+//     return lo::b200::mm_lls_icp<PointT>(registration_cons, max_iter_num, dis_thre_unit, ... );
+//
+// (all 23 arguments forwarded unchanged) or calls lo::b200::mm_lls_icp directly. The signature below
+// is the reference's (cregistration.hpp:1114-1123): same names, order, types and defaults, so
+// test/mulls_reg.cpp:194-195 and test/mulls_slam.cpp:477-482, :560-566, :642-648, :679-685 compile
+// unchanged. Needs PCL + Eigen (for the types only) and -lmulls_b200.
+//
+// Contract differences: block1->tree_* are not populated; options
+// normal_shooting_on / apply_motion_undistortion_while_registration / keep_less_source_points are
+// rejected (LOG + return 0 with the constraint untouched).
+#ifndef MULLS_B200_CREGISTRATION_SHIM_HPP
+#define MULLS_B200_CREGISTRATION_SHIM_HPP
+
+#include <cstring>
+#include <string>
+
+#include "mulls_b200/abi.h"
+#include "utility.hpp" // lo::constraint_t, lo::cloudblock_t, Matrix6d, Point_T
+
+namespace lo {
+namespace b200 {
+
+// One context per host thread (mm_lls_icp is called from the app's main thread, SURVEY 8b "Threading").
+inline mulls_ctx *thread_context(size_t need_src, size_t need_tgt) {
+    static thread_local mulls_ctx *ctx = nullptr;
+    static thread_local size_t cap_src = 0, cap_tgt = 0;
+    if (!ctx || need_src > cap_src || need_tgt > cap_tgt) {
+        if (ctx) mulls_destroy(ctx);
+        cap_src = need_src > cap_src ? need_src * 2 : cap_src;
+        cap_tgt = need_tgt > cap_tgt ? need_tgt * 2 : cap_tgt;
+        ctx = mulls_create(/*device*/ 0, /*max_pairs*/ 1, cap_src ? cap_src : 1, cap_tgt ? cap_tgt : 1);
+    }
+    return ctx;
+}
+
+template <typename PointT>
+inline mulls_cloud_view view_of(const typename pcl::PointCloud<PointT>::Ptr &cloud) {
+    static_assert(sizeof(PointT) == 48, "the C-ABI consumes pcl::PointXYZINormal rows (48 bytes)");
+    mulls_cloud_view v;
+    v.aos48 = cloud->points.empty() ? nullptr : reinterpret_cast<const float *>(cloud->points.data());
+    v.n = cloud->points.size();
+    return v;
+}
+
+template <typename PointT>
+int mm_lls_icp(constraint_t &registration_cons, // cblock_1 (target point cloud), cblock_2 (source point cloud)
+               int max_iter_num = 20, float dis_thre_unit = 1.5, float converge_translation = 0.002,
+               float converge_rotation_d = 0.01, float dis_thre_min = 0.4, float dis_thre_update_rate = 1.1,
+               std::string used_feature_type = "111110", std::string weight_strategy = "1101",
+               float z_xy_balanced_ratio = 1.0, float pt2pt_residual_window = 0.1, float pt2pl_residual_window = 0.1,
+               float pt2li_residual_window = 0.1, Eigen::Matrix4d initial_guess = Eigen::Matrix4d::Identity(),
+               bool apply_intersection_filter = true, bool apply_motion_undistortion_while_registration = false,
+               bool normal_shooting_on = false, float normal_bearing = 45.0, bool use_more_points = false,
+               bool keep_less_source_points = false, float sigma_thre = 0.5, float min_neccessary_corr_ratio = 0.03,
+               float max_bearable_rotation_d = 45.0) {
+    cloudblock_t &b1 = *registration_cons.block1; // target
+    cloudblock_t &b2 = *registration_cons.block2; // source
+    // clone_feature(..., false) for the target, clone_feature(..., !use_more_points) for the source
+    // (cregistration.hpp:1180-1181, utility.hpp:524-550): the library copies, the caller's clouds stay intact.
+    mulls_cloud_view tgt[MULLS_NUM_CLASSES] = {view_of<PointT>(b1.pc_ground), view_of<PointT>(b1.pc_pillar),
+                                               view_of<PointT>(b1.pc_facade), view_of<PointT>(b1.pc_beam),
+                                               view_of<PointT>(b1.pc_roof),   view_of<PointT>(b1.pc_vertex)};
+    const bool down = !use_more_points;
+    mulls_cloud_view src[MULLS_NUM_CLASSES] = {
+        view_of<PointT>(down ? b2.pc_ground_down : b2.pc_ground), view_of<PointT>(down ? b2.pc_pillar_down : b2.pc_pillar),
+        view_of<PointT>(down ? b2.pc_facade_down : b2.pc_facade), view_of<PointT>(down ? b2.pc_beam_down : b2.pc_beam),
+        view_of<PointT>(down ? b2.pc_roof_down : b2.pc_roof),     view_of<PointT>(b2.pc_vertex)};
+
+    mulls_icp_params p;
+    mulls_icp_default_params(&p);
+    p.max_iter_num = max_iter_num;
+    p.dis_thre_unit = dis_thre_unit;
+    p.converge_translation = converge_translation;
+    p.converge_rotation_d = converge_rotation_d;
+    p.dis_thre_min = dis_thre_min;
+    p.dis_thre_update_rate = dis_thre_update_rate;
+    std::strncpy(p.used_feature_type, used_feature_type.c_str(), 7);
+    std::strncpy(p.weight_strategy, weight_strategy.c_str(), 7);
+    p.z_xy_balanced_ratio = z_xy_balanced_ratio;
+    p.pt2pt_residual_window = pt2pt_residual_window;
+    p.pt2pl_residual_window = pt2pl_residual_window;
+    p.pt2li_residual_window = pt2li_residual_window;
+    p.apply_intersection_filter = apply_intersection_filter;
+    p.apply_motion_undistortion_while_registration = apply_motion_undistortion_while_registration;
+    p.normal_shooting_on = normal_shooting_on;
+    p.normal_bearing = normal_bearing;
+    p.use_more_points = use_more_points;
+    p.keep_less_source_points = keep_less_source_points;
+    p.sigma_thre = sigma_thre;
+    p.min_neccessary_corr_ratio = min_neccessary_corr_ratio;
+    p.max_bearable_rotation_d = max_bearable_rotation_d;
+    const bounds_t &lb = b1.local_bound; // read at cregistration.hpp:2916
+    p.target_bound[0] = lb.min_x, p.target_bound[1] = lb.min_y, p.target_bound[2] = lb.min_z;
+    p.target_bound[3] = lb.max_x, p.target_bound[4] = lb.max_y, p.target_bound[5] = lb.max_z;
+
+    double init[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) init[4 * r + c] = initial_guess(r, c);
+
+    size_t ns = 0, nt = 0;
+    for (int c = 0; c < MULLS_NUM_CLASSES; ++c) ns += src[c].n, nt += tgt[c].n;
+    mulls_ctx *ctx = thread_context(ns, nt);
+    mulls_icp_result out;
+    if (!ctx || mulls_icp_run(ctx, tgt, src, &p, init, &out, nullptr) != MULLS_OK) {
+        LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
+        return 0; // process_code 0: "registration did not run"; the constraint is left untouched
+    }
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) registration_cons.Trans1_2(r, c) = out.T[4 * r + c];     // :1405
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) registration_cons.information_matrix(r, c) = out.info[6 * r + c]; // :1418
+    registration_cons.sigma = out.sigma;           // :1419
+    registration_cons.confidence = out.confidence; // :1420
+    return out.code;                               // :1439
+}
+
+} // namespace b200
+} // namespace lo
+#endif

@@ -612,141 +612,138 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
     __shared__ double s_red[kWarps][kTerms];
     __shared__ uint32_t s_off[kWarps + 1];
     __shared__ uint32_t s_base;
-    __shared__ bool s_last;
 
-    // blocks entirely past the live part of the class only report an empty partial
-    const bool dead_block = (int)cd.first >= ns;
+    // blocks entirely past the live part of the class have nothing to contribute (k_solve skips them)
+    if ((int)cd.first >= ns) return;
     uint32_t dst_local = 0;
     uint8_t fl = 0;
     uint32_t gi = 0;
     bool kept = false, pass = false;
     double t[32];
-    if (!dead_block) {
-        // (1) destination of the kept sources: blocks before this one in the same (pair, class)
-        {
-            uint32_t acc = 0;
-            const uint32_t first_chunk = pc.class_chunk_begin[c];
-            for (uint32_t b = first_chunk + threadIdx.x; b < blockIdx.x; b += kIterBlock) acc += A.blk_kept[b];
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) s_off[warp] = acc;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t tt = 0;
-                for (int w = 0; w < kWarps; ++w) tt += s_off[w];
-                s_base = tt;
-            }
-            __syncthreads();
-        }
-        if (valid) {
-            gi = pc.src_base[c] + local;
-            fl = A.flags[gi];
-        }
-        kept = (fl & 1) != 0, pass = (fl & 2) != 0;
-        const unsigned kb = __ballot_sync(0xffffffffu, kept);
-        if (lane == 0) s_off[warp] = __popc(kb);
+    // (1) destination of the kept sources: blocks before this one in the same (pair, class)
+    {
+        uint32_t acc = 0;
+        const uint32_t first_chunk = pc.class_chunk_begin[c];
+        for (uint32_t b = first_chunk + threadIdx.x; b < blockIdx.x; b += kIterBlock) acc += A.blk_kept[b];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_off[warp] = acc;
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t run = 0;
-            for (int w = 0; w < kWarps; ++w) {
-                const uint32_t tt = s_off[w];
-                s_off[w] = run;
-                run += tt;
-            }
-            s_off[kWarps] = run;
+            uint32_t tt = 0;
+            for (int w = 0; w < kWarps; ++w) tt += s_off[w];
+            s_base = tt;
         }
         __syncthreads();
-        dst_local = s_base + s_off[warp] + __popc(kb & ((1u << lane) - 1u));
-
-        // (2) terms of the surviving correspondences
-#pragma unroll
-        for (int k = 0; k < 32; ++k) t[k] = 0.0;
-        float w_store = 0.0f;
-        int j = -1;
-        float4 p = make_float4(0, 0, 0, 0), n = make_float4(0, 0, 0, 0);
-        float d2 = 0.0f;
-        if (valid) {
-            p = A.src_pos[buf][gi];
-            n = A.src_nrm[buf][gi];
-            j = A.nn_idx[gi];
-            d2 = A.nn_d2[gi];
-            if (j >= 0) A.claim[pc.tgt_base[c] + j] = kClaimFree; // reset the table for the next iteration
-        }
-        float ratio_unused;
-        const bool few = too_few(pc, ps, ps.n_corr, ratio_unused);
-        if (pass && !few) {
-            const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
-            const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
-            const int it = ps.iter;
-            const bool resid_w = pc.w_residual && it > 2; // :1905-1907
-            const bool dist_w = pc.w_dist != 0, inten_w = pc.w_intensity != 0;
-            if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) {
-                const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, ps.n_corr);
-                terms_pt2pl(p, p.w, q, qn, wc, it, dist_w, resid_w, inten_w, pc.win_pt2pl, t, w_store);
-            } else if (c == MULLS_PILLAR || c == MULLS_BEAM) {
-                terms_pt2li(p, p.w, q, qn, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2li, t, w_store);
-            } else {
-                terms_pt2pt(p, p.w, q, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2pt, t);
-                w_store = d2; // pt2pt never stores a weight: the posterior reads the squared NN distance (Q2)
-            }
-        }
-        // (3) compaction into the other buffer (order preserved: :1776-1789)
-        if (kept) {
-            const uint32_t gd = pc.src_base[c] + dst_local;
-            A.src_pos[buf ^ 1][gd] = p;
-            A.src_nrm[buf ^ 1][gd] = n;
-            A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
-            A.corr_j[gd] = pass ? j : -1;
-            A.corr_w[gd] = w_store;
-        }
-        // (4) block reduction in a fixed order. Warp level: reduce-scatter butterfly — at every step a
-        // lane keeps half of the terms and receives the partner's sums of that half, so after 5 steps
-        // lane i holds the warp total of term i (31 shuffles instead of 27 x 5).
-#pragma unroll
-        for (int half = 16; half >= 1; half >>= 1) {
-            const bool upper = (lane & half) != 0;
-#pragma unroll
-            for (int k = 0; k < half; ++k) {
-                const double send = upper ? t[k] : t[k + half];
-                const double keep = upper ? t[k + half] : t[k];
-                t[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-            }
-        }
-        if (lane < kTerms) s_red[warp][lane] = t[0];
-        __syncthreads();
     }
-    if (threadIdx.x < 27) {
-        double v = 0.0;
-        if (!dead_block)
-            for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
-        A.partials[(size_t)blockIdx.x * kTerms + threadIdx.x] = v;
+    if (valid) {
+        gi = pc.src_base[c] + local;
+        fl = A.flags[gi];
     }
-    // (5) last block of the pair: reduce all partials, solve, advance
-    __threadfence();
+    kept = (fl & 1) != 0, pass = (fl & 2) != 0;
+    const unsigned kb = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) s_off[warp] = __popc(kb);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned nblk = pc.chunk_end - pc.chunk_begin;
-        const unsigned prev = atomicAdd(&ps.arrive_acc, 1u);
-        s_last = (prev == nblk - 1);
+        uint32_t run = 0;
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t tt = s_off[w];
+            s_off[w] = run;
+            run += tt;
+        }
+        s_off[kWarps] = run;
     }
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    dst_local = s_base + s_off[warp] + __popc(kb & ((1u << lane) - 1u));
+
+    // (2) terms of the surviving correspondences
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t[k] = 0.0;
+    float w_store = 0.0f;
+    int j = -1;
+    float4 p = make_float4(0, 0, 0, 0), n = make_float4(0, 0, 0, 0);
+    float d2 = 0.0f;
+    if (valid) {
+        p = A.src_pos[buf][gi];
+        n = A.src_nrm[buf][gi];
+        j = A.nn_idx[gi];
+        d2 = A.nn_d2[gi];
+        if (j >= 0) A.claim[pc.tgt_base[c] + j] = kClaimFree; // reset the table for the next iteration
+    }
+    float ratio_unused;
+    const bool few = too_few(pc, ps, ps.n_corr, ratio_unused);
+    if (pass && !few) {
+        const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
+        const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
+        const int it = ps.iter;
+        const bool resid_w = pc.w_residual && it > 2; // :1905-1907
+        const bool dist_w = pc.w_dist != 0, inten_w = pc.w_intensity != 0;
+        if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) {
+            const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, ps.n_corr);
+            terms_pt2pl(p, p.w, q, qn, wc, it, dist_w, resid_w, inten_w, pc.win_pt2pl, t, w_store);
+        } else if (c == MULLS_PILLAR || c == MULLS_BEAM) {
+            terms_pt2li(p, p.w, q, qn, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2li, t, w_store);
+        } else {
+            terms_pt2pt(p, p.w, q, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2pt, t);
+            w_store = d2; // pt2pt never stores a weight: the posterior reads the squared NN distance (Q2)
+        }
+    }
+    // (3) compaction into the other buffer (order preserved: :1776-1789)
+    if (kept) {
+        const uint32_t gd = pc.src_base[c] + dst_local;
+        A.src_pos[buf ^ 1][gd] = p;
+        A.src_nrm[buf ^ 1][gd] = n;
+        A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
+        A.corr_j[gd] = pass ? j : -1;
+        A.corr_w[gd] = w_store;
+    }
+    // (4) block reduction in a fixed order. Warp level: reduce-scatter butterfly — at every step a lane
+    // keeps half of the terms and receives the partner's sums of that half, so after 5 steps lane i holds
+    // the warp total of term i (31 shuffles instead of 27 x 5).
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double send = upper ? t[k] : t[k + half];
+            const double keep = upper ? t[k + half] : t[k];
+            t[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    if (lane < kTerms) s_red[warp][lane] = t[0];
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double v = 0.0;
+        for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
+        A.partials[(size_t)blockIdx.x * kTerms + threadIdx.x] = v;
+    }
+}
+
+// ---- k_solve: one block per pair, after k_accumulate. Sums the per-chunk partials of every class in chunk
+//      order (fixed order => bit-reproducible), then one thread solves and advances the pair state.
+__global__ void __launch_bounds__(kIterBlock) k_solve(DeviceArrays A, int buf) {
+    const uint32_t pair = blockIdx.x;
+    const PairConst &pc = A.pc[pair];
+    PairState &ps = A.ps[pair];
+    if (ps.status != kRunning) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kIterBlock / 32;
     __shared__ double s_S[kNumClasses][kTerms];
     __shared__ double s_scratch[160];
     __shared__ int s_newn[kNumClasses];
-    // per class: sum the partials of its chunks in chunk order (fixed order => deterministic)
+    __shared__ uint32_t s_off[kWarps];
     for (int cc = 0; cc < kNumClasses; ++cc) {
-        const uint32_t b0 = pc.class_chunk_begin[cc], b1 = pc.class_chunk_begin[cc + 1];
-        // 4 threads per term, strided, then combined in a fixed order
-        const int term = threadIdx.x >> 2, sub = threadIdx.x & 3;
+        const uint32_t b0 = pc.class_chunk_begin[cc];
+        // only the chunks that held live sources this iteration wrote a partial
+        const uint32_t live = (uint32_t)((ps.n_src[cc] + kIterBlock - 1) / kIterBlock);
+        const uint32_t b1 = min(pc.class_chunk_begin[cc + 1], b0 + live);
+        const int term = threadIdx.x >> 2, sub = threadIdx.x & 3; // 4 threads per term, strided
         double v = 0.0;
         if (term < 27)
             for (uint32_t b = b0 + sub; b < b1; b += 4) v += A.partials[(size_t)b * kTerms + term];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (term < 27 && sub == 0) s_S[cc][term] = v;
-        // kept sources of the class = its new size
-        uint32_t acc = 0;
+        uint32_t acc = 0; // kept sources of the class = its new size
         for (uint32_t b = b0 + threadIdx.x; b < b1; b += kIterBlock) acc += A.blk_kept[b];
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         __syncthreads();
@@ -764,19 +761,13 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
         for (int cc = 0; cc < kNumClasses; ++cc)
             if (pc.used[cc]) srcpts += (uint64_t)ps.n_src[cc];
         ps.alg_bytes += 28ull * srcpts;
-        mulls_icp_trace *tr = A.trace ? &A.trace[cd.pair] : nullptr;
-        const bool dedup_any = true;
-        (void)dedup_any;
+        mulls_icp_trace *tr = A.trace ? &A.trace[pair] : nullptr;
         for (int cc = 0; cc < kNumClasses; ++cc) {
-            const bool active = pc.used[cc] && ps.n_src[cc] >= 3 && ps.n_tgt[cc] >= 3;
-            // classes that did not run determine_corres keep their cloud untouched
-            if (active) ps.n_src[cc] = s_newn[cc];
+            ps.n_src[cc] = s_newn[cc]; // classes that skipped determine_corres keep everything (k_resolve)
             if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src[cc];
         }
-        solve_and_advance(A, cd.pair, &s_S[0][0], s_scratch, buf ^ 1);
+        solve_and_advance(A, pair, &s_S[0][0], s_scratch, buf ^ 1);
         for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
-        ps.arrive_acc = 0;
-        __threadfence();
     }
 }
 
@@ -790,6 +781,7 @@ __global__ void __launch_bounds__(kIterBlock) k_posterior(DeviceArrays A) {
     if (ps.status != kNeedPosterior) return;
     const int c = (int)cd.seg;
     const int buf = ps.final_buf;
+    if ((int)cd.first >= ps.n_src[c]) return; // k_finalize only sums the live chunks
     const uint32_t local = cd.first + threadIdx.x;
     const bool valid = (int)local < ps.n_src[c];
     double vtpv = 0.0;
@@ -851,7 +843,6 @@ __global__ void __launch_bounds__(kIterBlock) k_posterior(DeviceArrays A) {
     constexpr int kWarps = kIterBlock / 32;
     __shared__ double s_v[kWarps];
     __shared__ int s_n[kWarps];
-    __shared__ bool s_last;
     for (int o = 16; o > 0; o >>= 1) {
         vtpv += __shfl_xor_sync(0xffffffffu, vtpv, o);
         nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
@@ -870,32 +861,36 @@ __global__ void __launch_bounds__(kIterBlock) k_posterior(DeviceArrays A) {
         }
         A.post_partials[2 * (size_t)blockIdx.x] = v;
         A.post_partials[2 * (size_t)blockIdx.x + 1] = (double)n;
-        __threadfence();
-        const unsigned nblk = pc.chunk_end - pc.chunk_begin;
-        s_last = atomicAdd(&ps.arrive_post, 1u) == nblk - 1;
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) {
-        // class order of :2529-2534: ground, facade, roof, pillar, beam, vertex; chunk order inside
-        const int order[6] = {MULLS_GROUND, MULLS_FACADE, MULLS_ROOF, MULLS_PILLAR, MULLS_BEAM, MULLS_VERTEX};
-        double VTPV = 0.0;
-        long long nob = 0;
-        for (int o = 0; o < 6; ++o)
-            for (uint32_t b = pc.class_chunk_begin[order[o]]; b < pc.class_chunk_begin[order[o] + 1]; ++b) {
-                VTPV += A.post_partials[2 * (size_t)b];
-                nob += (long long)A.post_partials[2 * (size_t)b + 1];
-            }
-        const double sigma2 = VTPV / (double)((int)nob - 6);
-        ps.sigma2 = sigma2;
-        ps.code = (sqrt(sigma2) < pc.sigma_thre) ? 1 : -3;
-        __shared__ double s_inv[36], s_lu[36];
-        inverse6(ps.cofactor, s_inv, s_lu);
-        for (int k = 0; k < 36; ++k) ps.info[k] = (1.0 / sigma2) * s_inv[k];
-        ps.status = kDone;
-        ps.arrive_post = 0;
+}
+
+// ---- k_finalize: one thread per pair: sigma^2 = VTPV/(n-6) (:2536), code 1 / -3 (:2540-2543), information
+//      matrix = cofactor^-1 / sigma^2 (:1386). Partials are summed in the class order of :2529-2534.
+__global__ void k_finalize(DeviceArrays A, int n_pairs) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const PairConst &pc = A.pc[pair];
+    PairState &ps = A.ps[pair];
+    if (ps.status != kNeedPosterior) return;
+    const int order[6] = {MULLS_GROUND, MULLS_FACADE, MULLS_ROOF, MULLS_PILLAR, MULLS_BEAM, MULLS_VERTEX};
+    double VTPV = 0.0;
+    long long nob = 0;
+    for (int o = 0; o < 6; ++o) {
+        const uint32_t b0 = pc.class_chunk_begin[order[o]];
+        const uint32_t live = (uint32_t)((ps.n_src[order[o]] + kIterBlock - 1) / kIterBlock);
+        const uint32_t b1 = min(pc.class_chunk_begin[order[o] + 1], b0 + live);
+        for (uint32_t b = b0; b < b1; ++b) {
+            VTPV += A.post_partials[2 * (size_t)b];
+            nob += (long long)A.post_partials[2 * (size_t)b + 1];
+        }
     }
+    const double sigma2 = VTPV / (double)((int)nob - 6);
+    ps.sigma2 = sigma2;
+    ps.code = (sqrt(sigma2) < pc.sigma_thre) ? 1 : -3;
+    double inv[36], lu[36];
+    inverse6(ps.cofactor, inv, lu);
+    for (int k = 0; k < 36; ++k) ps.info[k] = (1.0 / sigma2) * inv[k];
+    ps.status = kDone;
 }
 
 // ---- k_state_init: reset the per-pair accumulators that the ingest kernels update atomically

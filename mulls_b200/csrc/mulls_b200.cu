@@ -460,12 +460,14 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
             k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
             k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            k_solve<<<(unsigned)np, kIterBlock, 0, st>>>(A, buf);
             CK(cudaEventRecord(ctx->ev_done[it], st));
-            launches += 3;
+            launches += 4;
             n_search_ev = it + 1;
         }
         k_posterior<<<n_itc, kIterBlock, 0, st>>>(A);
-        ++launches;
+        k_finalize<<<(unsigned)ceil_div(np, 64), 64, 0, st>>>(A, np);
+        launches += 2;
     }
     CK(cudaEventRecord(ctx->ev_iter, st));
     k_collect<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->d_results);

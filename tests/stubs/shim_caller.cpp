@@ -1,0 +1,22 @@
+// The reference's call (test/mulls_reg.cpp:194-195) against the drop-in shim, with stand-in PCL/Eigen types.
+#include <cstdio>
+#include <string>
+
+#include "utility.hpp"
+#include "common/cregistration_b200.hpp"
+
+using namespace lo;
+
+int main() {
+    constraint_t reg_con;
+    int reg_max_iter_num = 10;
+    float reg_corr_dis_thre = 3.0f, converge_tran = 0.001f, converge_rot_d = 0.01f;
+    Eigen::Matrix4d init_mat = Eigen::Matrix4d::Identity();
+    // argument list of test/mulls_reg.cpp:194-195
+    int code = lo::b200::mm_lls_icp<Point_T>(reg_con, reg_max_iter_num, reg_corr_dis_thre, converge_tran, converge_rot_d,
+                                             0.25 * reg_corr_dis_thre, 1.1, "111110", "1101", 1.0, 0.1, 0.1, 0.1, init_mat);
+    // defaults-only call
+    int code2 = lo::b200::mm_lls_icp<Point_T>(reg_con);
+    std::printf("shim compiled and linked; codes %d %d\n", code, code2);
+    return 0;
+}
