@@ -73,7 +73,9 @@ struct PairState {
     int n_levels;
     int status, code, iter, iters_entered, final_buf;
     int source_feature_points_count;
-    int n_src[kNumClasses];
+    int n_src[kNumClasses];   // live source points of each class on THIS rank
+    int n_src_g[kNumClasses]; // ... over all ranks (== n_src unless the source is sharded)
+    int n_src_g_next[kNumClasses];
     int n_tgt[kNumClasses];
     uint32_t n_corr[kNumClasses];      // |Corr_f| of the current iteration (atomics in k_resolve)
     uint32_t n_corr_last[kNumClasses]; // same, frozen for the result
@@ -103,6 +105,7 @@ struct DeviceArrays {
     float4 *tgt_pos, *tgt_nrm;       // target SoA, Morton-sorted inside each (pair,class) slice
     float4 *src_pos[2], *src_nrm[2]; // source SoA ping-pong
     float *src_hint[2];              // previous NN distance^2 (search start-level hint)
+    int *src_prevj[2];               // previous NN target (seeds the next search with a real candidate)
     int *nn_idx;                     // per source: matched target (index inside its class slice) or -1
     float *nn_d2;
     uint8_t *flags;                  // bit0 kept as source point, bit1 correspondence passes rejectors
@@ -120,6 +123,8 @@ struct DeviceArrays {
     ChunkDesc *in_chunks;
     ChunkDesc *it_chunks;
     mulls_icp_trace *trace; // may be null
+    int *xch_i32;           // exchange buffer of the sharded mode (counts / bbox), 32 ints
+    double *xch_f64;        // exchange buffer of the sharded mode (per-class sums), 6*kTerms + 2 doubles
     int *running;           // pairs still iterating (device counter)
     volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop
 };

@@ -217,6 +217,7 @@ __global__ void k_seg_offsets(DeviceArrays A, int n_pairs) {
         for (int c = 0; c < kNumClasses; ++c) {
             ps.n_tgt[c] = (int)ps.seg_count[c];
             ps.n_src[c] = (int)ps.seg_count[kNumClasses + c];
+            ps.n_src_g[c] = ps.n_src[c];
             ps.n_corr[c] = 0;
             ps.n_corr_last[c] = 0;
         }
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(256) k_gather(DeviceArrays A, const uint64_t *
         A.src_pos[0][d] = pos;
         A.src_nrm[0][d] = n2;
         A.src_hint[0][d] = -1.0f;
+        A.src_prevj[0][d] = -1;
     }
 }
 

@@ -67,8 +67,7 @@ constexpr int kStackDepth = 48; // DFS entries: at most 7 stay behind per descen
 // Morton code = parent code << 3 | child) — the octree analogue of the kd-tree descent it replaces.
 __device__ __forceinline__ void nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
                                           int start_level, float &best_d2, int &best_j) {
-    best_d2 = INFINITY;
-    best_j = -1;
+    // best_d2 / best_j come in seeded: (INFINITY, -1) or a real candidate (the previous iteration's match)
     const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
     const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
     const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
@@ -182,7 +181,7 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
     const PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning || A.hash_used[1]) return;
     const int c = (int)cd.seg;
-    const int ns = ps.n_src[c], nt = ps.n_tgt[c];
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
     const uint32_t local = cd.first + threadIdx.x;
     if ((int)local >= ns) return;
     const uint32_t gi = pc.src_base[c] + local;
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
     int best_j = -1;
     float best_d2 = INFINITY;
     // determine_corres needs >= 3 points on both sides (:1727-1728)
-    if (pc.used[c] && ns >= 3 && nt >= 3) {
+    if (pc.used[c] && nsg >= 3 && nt >= 3) {
         GridView g;
         g.table = A.hash + ps.hash_base[c];
         g.mask = ps.hash_mask[c];
@@ -219,10 +218,15 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
         const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
         const float r2_prune = (float)max_dist_sqr * 1.0001f;
         int sl = start_level0;
-        const float hint = A.src_hint[buf][gi];
-        if (hint >= 0.0f) {
-            // smallest level whose guaranteed coverage exceeds 1.3x the previous NN distance
-            const float need = 1.3f * sqrtf(hint) / (0.999f * 0.5f * g.h0); // cover_l = 0.999 * h0 * 2^(l-1)
+        // Seed with the previous iteration's match: a real candidate, so the box-distance pruning bites from
+        // the first cell on; the search then only has to prove that nothing is closer (still exact).
+        const int pj = A.src_prevj[buf][gi];
+        if (pj >= 0) {
+            const float4 q = __ldg(&g.pos[pj]);
+            best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
+            best_j = pj;
+            // smallest level whose guaranteed coverage 0.999 * h0 * 2^(l-1) reaches that distance
+            const float need = 1.001f * sqrtf(best_d2) / (0.999f * 0.5f * g.h0);
             sl = (need <= 1.0f) ? 0 : (ilogbf(need) + 1);
         }
         nn_search(g, p.x, p.y, p.z, r2_prune, sl, best_d2, best_j);
@@ -243,11 +247,11 @@ __global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf)
     PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning) return;
     const int c = (int)cd.seg;
-    const int ns = ps.n_src[c], nt = ps.n_tgt[c];
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
     const uint32_t local = cd.first + threadIdx.x;
     const bool valid = (int)local < ns;
-    const bool active = pc.used[c] && ns >= 3 && nt >= 3; // determine_corres ran for this class
-    const bool dedup = active && ns >= kDedupMinSrc;
+    const bool active = pc.used[c] && nsg >= 3 && nt >= 3; // determine_corres ran for this class
+    const bool dedup = active && nsg >= kDedupMinSrc;
     bool kept = false, pass = false;
     if (valid) {
         const uint32_t gi = pc.src_base[c] + local;
@@ -693,6 +697,7 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
         A.src_pos[buf ^ 1][gd] = p;
         A.src_nrm[buf ^ 1][gd] = n;
         A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
+        A.src_prevj[buf ^ 1][gd] = j;
         A.corr_j[gd] = pass ? j : -1;
         A.corr_w[gd] = w_store;
     }
@@ -759,15 +764,132 @@ __global__ void __launch_bounds__(kIterBlock) k_solve(DeviceArrays A, int buf) {
     if (threadIdx.x == 0) {
         uint64_t srcpts = 0;
         for (int cc = 0; cc < kNumClasses; ++cc)
-            if (pc.used[cc]) srcpts += (uint64_t)ps.n_src[cc];
+            if (pc.used[cc]) srcpts += (uint64_t)ps.n_src_g[cc];
         ps.alg_bytes += 28ull * srcpts;
+        if (pc.sharded) {
+            // source-sharded registration: publish this rank's per-class sums; the all-reduce and
+            // k_shard_solve (identical on every rank) finish the iteration
+            for (int cc = 0; cc < kNumClasses; ++cc) {
+                ps.n_src[cc] = s_newn[cc];
+                for (int k = 0; k < kTerms; ++k) A.xch_f64[cc * kTerms + k] = (k < 27) ? s_S[cc][k] : 0.0;
+            }
+            return;
+        }
         mulls_icp_trace *tr = A.trace ? &A.trace[pair] : nullptr;
         for (int cc = 0; cc < kNumClasses; ++cc) {
             ps.n_src[cc] = s_newn[cc]; // classes that skipped determine_corres keep everything (k_resolve)
+            ps.n_src_g[cc] = s_newn[cc];
             if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src[cc];
         }
         solve_and_advance(A, pair, &s_S[0][0], s_scratch, buf ^ 1);
         for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+    }
+}
+
+// ---- sharded mode (mulls_icp_run_sharded, BASELINE config 5): one pair, the target replicated, the source
+//      classes split over ranks in contiguous index ranges. Three tiny exchange steps per iteration, each an
+//      all-reduce supplied by the caller (NCCL): claim table (min), counts (sum), per-class sums (sum).
+// after ingest: global class sizes and the global bbox of source ground/pillar/facade
+__global__ void k_shard_pack_setup(DeviceArrays A, int phase) {
+    PairState &ps = A.ps[0];
+    if (phase == 0) { // bbox: min over [min_xyz, -max_xyz] in the ordered-int encoding
+        for (int d = 0; d < 3; ++d) {
+            A.xch_i32[d] = ps.bb_src[d];
+            A.xch_i32[3 + d] = ~ps.bb_src[3 + d]; // max(x) = ~min(~x), no overflow for INT_MIN
+        }
+    } else if (phase == 1) {
+        for (int d = 0; d < 3; ++d) {
+            ps.bb_src[d] = A.xch_i32[d];
+            ps.bb_src[3 + d] = ~A.xch_i32[3 + d];
+        }
+    } else if (phase == 2) {
+        for (int c = 0; c < kNumClasses; ++c) A.xch_i32[c] = ps.n_src[c];
+    } else {
+        const PairConst &pc = A.pc[0];
+        int cnt = 0;
+        for (int c = 0; c < kNumClasses; ++c) ps.n_src_g[c] = A.xch_i32[c];
+        if (pc.used[MULLS_PILLAR]) cnt += ps.n_src_g[MULLS_PILLAR];
+        if (pc.used[MULLS_FACADE]) cnt += ps.n_src_g[MULLS_FACADE];
+        if (pc.used[MULLS_BEAM]) cnt += ps.n_src_g[MULLS_BEAM];
+        ps.source_feature_points_count = cnt;
+    }
+}
+// after k_resolve: this rank's correspondence and kept-source counts -> exchange buffer; and back
+__global__ void __launch_bounds__(kIterBlock) k_shard_counts(DeviceArrays A, int phase) {
+    const PairConst &pc = A.pc[0];
+    PairState &ps = A.ps[0];
+    if (ps.status != kRunning) {
+        if (phase == 0 && threadIdx.x < 2 * kNumClasses) A.xch_i32[threadIdx.x] = 0;
+        return;
+    }
+    if (phase == 0) {
+        __shared__ uint32_t s_w[kIterBlock / 32];
+        for (int cc = 0; cc < kNumClasses; ++cc) {
+            const uint32_t b0 = pc.class_chunk_begin[cc];
+            const uint32_t live = (uint32_t)((ps.n_src[cc] + kIterBlock - 1) / kIterBlock);
+            const uint32_t b1 = min(pc.class_chunk_begin[cc + 1], b0 + live);
+            uint32_t acc = 0;
+            for (uint32_t b = b0 + threadIdx.x; b < b1; b += kIterBlock) acc += A.blk_kept[b];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t tot = 0;
+                for (int w = 0; w < kIterBlock / 32; ++w) tot += s_w[w];
+                A.xch_i32[kNumClasses + cc] = (int)tot;
+                A.xch_i32[cc] = (int)ps.n_corr[cc];
+            }
+        }
+    } else if (threadIdx.x == 0) {
+        for (int cc = 0; cc < kNumClasses; ++cc) {
+            ps.n_corr[cc] = (uint32_t)A.xch_i32[cc];
+            ps.n_src_g_next[cc] = A.xch_i32[kNumClasses + cc]; // the class size after this iteration's shrinking
+        }
+    }
+}
+// after the all-reduce of the per-class sums: every rank solves the same system and advances identically
+__global__ void k_shard_solve(DeviceArrays A, int buf) {
+    PairState &ps = A.ps[0];
+    if (ps.status != kRunning || threadIdx.x != 0) return;
+    __shared__ double s_scratch[160];
+    mulls_icp_trace *tr = A.trace ? &A.trace[0] : nullptr;
+    for (int cc = 0; cc < kNumClasses; ++cc) {
+        ps.n_src_g[cc] = ps.n_src_g_next[cc];
+        if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src_g[cc];
+    }
+    solve_and_advance(A, 0, A.xch_f64, s_scratch, buf ^ 1);
+    for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+}
+// posterior in sharded mode: VTPV / n_obs of this rank -> exchange buffer
+__global__ void k_shard_post(DeviceArrays A, int phase) {
+    const PairConst &pc = A.pc[0];
+    PairState &ps = A.ps[0];
+    if (threadIdx.x != 0) return;
+    if (phase == 0) {
+        double VTPV = 0.0, nob = 0.0;
+        if (ps.status == kNeedPosterior) {
+            const int order[6] = {MULLS_GROUND, MULLS_FACADE, MULLS_ROOF, MULLS_PILLAR, MULLS_BEAM, MULLS_VERTEX};
+            for (int o = 0; o < 6; ++o) {
+                const uint32_t b0 = pc.class_chunk_begin[order[o]];
+                const uint32_t live = (uint32_t)((ps.n_src[order[o]] + kIterBlock - 1) / kIterBlock);
+                const uint32_t b1 = min(pc.class_chunk_begin[order[o] + 1], b0 + live);
+                for (uint32_t b = b0; b < b1; ++b) {
+                    VTPV += A.post_partials[2 * (size_t)b];
+                    nob += A.post_partials[2 * (size_t)b + 1];
+                }
+            }
+        }
+        A.xch_f64[0] = VTPV;
+        A.xch_f64[1] = nob;
+    } else if (ps.status == kNeedPosterior) {
+        const double sigma2 = A.xch_f64[0] / (double)((int)A.xch_f64[1] - 6);
+        ps.sigma2 = sigma2;
+        ps.code = (sqrt(sigma2) < pc.sigma_thre) ? 1 : -3;
+        double inv[36], lu[36];
+        inverse6(ps.cofactor, inv, lu);
+        for (int k = 0; k < 36; ++k) ps.info[k] = (1.0 / sigma2) * inv[k];
+        ps.status = kDone;
     }
 }
 
@@ -926,7 +1048,7 @@ __global__ void k_collect(DeviceArrays A, int n_pairs, mulls_icp_result *out) {
     r.iters = ps.iters_entered;
     for (int c = 0; c < kNumClasses; ++c) {
         r.n_corr[c] = ps.n_corr_last[c];
-        r.n_src[c] = (uint32_t)ps.n_src[c];
+        r.n_src[c] = (uint32_t)ps.n_src_g[c];
     }
 }
 

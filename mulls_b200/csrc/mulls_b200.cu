@@ -180,6 +180,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
         ALLOC(A.src_pos[b], cs);
         ALLOC(A.src_nrm[b], cs);
         ALLOC(A.src_hint[b], cs);
+        ALLOC(A.src_prevj[b], cs);
     }
     ALLOC(A.nn_idx, cs);
     ALLOC(A.nn_d2, cs);
@@ -206,6 +207,8 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ALLOC(ctx->d_results, max_pairs);
     ALLOC(ctx->d_trace, max_pairs);
     ALLOC(A.running, 1);
+    ALLOC(A.xch_i32, 32);
+    ALLOC(A.xch_f64, kNumClasses * kTerms + 8);
 #undef ALLOC
     if ((e = cudaHostAlloc((void **)&ctx->h_running, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
         return fail("mapped flag", e);
@@ -391,30 +394,30 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     return MULLS_OK;
 }
 
-// Launch the whole path on the resident inputs. If `hook` is given (sharded mode) it is called between
-// the phases that need a cross-rank exchange.
-static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
-    if (!ctx || !ctx->uploaded) return MULLS_E_ARG;
-    if (hook) {
-        ctx->err = "sharded mode is not available in this build";
-        return MULLS_E_UNSUPPORTED;
-    }
-    CK(cudaSetDevice(ctx->device));
+// Ingest phase on the resident inputs: state reset, initial guess, intersection filter, Morton sort,
+// hashed multi-level grid. Shared by the registration path and mulls_pca_features.
+static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &launches, mulls_allreduce_fn hook = nullptr,
+                         void *user = nullptr) {
     cudaStream_t st = ctx->stream;
-    DeviceArrays A = ctx->A;
-    A.trace = trace ? ctx->d_trace : nullptr;
     const int np = (int)ctx->n_pairs;
     const uint32_t n_in = (uint32_t)ctx->n_in;
-    uint64_t launches = 0;
-    CK(cudaEventRecord(ctx->ev_begin, st));
     if (trace) CK(cudaMemsetAsync(ctx->d_trace, 0, np * sizeof(mulls_icp_trace), st));
     CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
     k_state_init<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np);
     ++launches;
-    const unsigned n_inc = (unsigned)ctx->h_in_chunks.size(), n_itc = (unsigned)ctx->h_it_chunks.size();
+    const unsigned n_inc = (unsigned)ctx->h_in_chunks.size();
     if (n_inc) {
         k_ingest_transform<<<n_inc, kIngestBlock, 0, st>>>(A);
         ++launches;
+    }
+    if (hook) { // sharded source: the intersection filter needs the bbox over all shards
+        k_shard_pack_setup<<<1, 1, 0, st>>>(A, 0);
+        if (hook(user, A.xch_i32, 6, 1, 1, (void *)st) != 0) {
+            ctx->err = "all-reduce callback failed";
+            return MULLS_E_COMM;
+        }
+        k_shard_pack_setup<<<1, 1, 0, st>>>(A, 1);
+        launches += 2;
     }
     k_pair_setup<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->h0_min);
     ++launches;
@@ -430,6 +433,15 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
     }
     k_seg_offsets<<<1, 256, 0, st>>>(A, np);
     ++launches;
+    if (hook) { // global class sizes (:1195-1201 counts, K_filter_distant_point test)
+        k_shard_pack_setup<<<1, 1, 0, st>>>(A, 2);
+        if (hook(user, A.xch_i32, kNumClasses, 1, 0, (void *)st) != 0) {
+            ctx->err = "all-reduce callback failed";
+            return MULLS_E_COMM;
+        }
+        k_shard_pack_setup<<<1, 1, 0, st>>>(A, 3);
+        launches += 2;
+    }
     if (n_in) {
         k_gather<<<(unsigned)ceil_div(n_in, 256), 256, 0, st>>>(A, A.keys_b, A.vals_b, n_in);
         const unsigned hb = (unsigned)ceil_div((size_t)n_in + 1, 256);
@@ -443,6 +455,25 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
         k_hash_layout<<<1, 32, 0, st>>>(A, np);
         ++launches;
     }
+    return MULLS_OK;
+}
+
+// Launch the whole path on the resident inputs. If `hook` is given (sharded mode) it is called between
+// the phases that need a cross-rank exchange.
+static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
+    if (!ctx || !ctx->uploaded) return MULLS_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DeviceArrays A = ctx->A;
+    A.trace = trace ? ctx->d_trace : nullptr;
+    const int np = (int)ctx->n_pairs;
+    uint64_t launches = 0;
+    CK(cudaEventRecord(ctx->ev_begin, st));
+    {
+        int rc = launch_ingest(ctx, A, trace != nullptr, launches, hook, user);
+        if (rc != MULLS_OK) return rc;
+    }
+    const unsigned n_itc = (unsigned)ctx->h_it_chunks.size();
     CK(cudaEventRecord(ctx->ev_ingest, st));
     int n_search_ev = 0;
     if (n_itc) {
@@ -455,19 +486,54 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
                 if (*(volatile int *)ctx->h_running <= 0) break;
             }
             const int buf = it & 1;
+            if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
+                CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
             k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
+            if (hook) { // exchange 1: the duplicate-check claims of all shards (min of source indices)
+                if (hook(user, A.claim, ctx->n_tgt_total, 1, 1, (void *)st) != 0) {
+                    ctx->err = "all-reduce callback failed";
+                    return MULLS_E_COMM;
+                }
+            }
             k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            if (hook) { // exchange 2: correspondence counts (w_ground, -2 test) and surviving source counts
+                k_shard_counts<<<1, kIterBlock, 0, st>>>(A, 0);
+                if (hook(user, A.xch_i32, 2 * kNumClasses, 1, 0, (void *)st) != 0) {
+                    ctx->err = "all-reduce callback failed";
+                    return MULLS_E_COMM;
+                }
+                k_shard_counts<<<1, kIterBlock, 0, st>>>(A, 1);
+                launches += 2;
+            }
             k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
             k_solve<<<(unsigned)np, kIterBlock, 0, st>>>(A, buf);
+            if (hook) { // exchange 3: per-class normal-equation sums; then every rank solves the same system
+                if (hook(user, A.xch_f64, kNumClasses * kTerms, 0, 0, (void *)st) != 0) {
+                    ctx->err = "all-reduce callback failed";
+                    return MULLS_E_COMM;
+                }
+                k_shard_solve<<<1, 32, 0, st>>>(A, buf);
+                ++launches;
+            }
             CK(cudaEventRecord(ctx->ev_done[it], st));
             launches += 4;
             n_search_ev = it + 1;
         }
         k_posterior<<<n_itc, kIterBlock, 0, st>>>(A);
-        k_finalize<<<(unsigned)ceil_div(np, 64), 64, 0, st>>>(A, np);
-        launches += 2;
+        if (hook) {
+            k_shard_post<<<1, 32, 0, st>>>(A, 0);
+            if (hook(user, A.xch_f64, 2, 0, 0, (void *)st) != 0) {
+                ctx->err = "all-reduce callback failed";
+                return MULLS_E_COMM;
+            }
+            k_shard_post<<<1, 32, 0, st>>>(A, 1);
+            launches += 3;
+        } else {
+            k_finalize<<<(unsigned)ceil_div(np, 64), 64, 0, st>>>(A, np);
+            launches += 2;
+        }
     }
     CK(cudaEventRecord(ctx->ev_iter, st));
     k_collect<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->d_results);
@@ -543,9 +609,65 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
 }
 
 int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
-    if (!ctx || !out) return MULLS_E_ARG;
-    ctx->err = "mulls_pca_features is not available in this build";
-    return MULLS_E_UNSUPPORTED;
+    if (!ctx || !out || !out->eigenvalues || !out->principal || !out->normal || !out->pt_num || stride < 1 ||
+        !(radius > 0.f))
+        return MULLS_E_ARG;
+    // the cloud becomes the only target class of a one-pair batch: same filter-less ingest, same grid
+    mulls_icp_params P;
+    mulls_icp_default_params(&P);
+    std::strcpy(P.used_feature_type, "100000");
+    P.apply_intersection_filter = 0;
+    P.dis_thre_unit = radius; // the grid's top level then covers 2.5 x radius
+    P.max_iter_num = 0;
+    mulls_cloud_view tgt[MULLS_NUM_CLASSES] = {cloud, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
+    mulls_cloud_view src[MULLS_NUM_CLASSES] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
+    const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    int rc = upload_impl(ctx, 1, tgt, src, &P, ident, nullptr, nullptr);
+    if (rc != MULLS_OK) return rc;
+    const size_t n = cloud.n;
+    const size_t bytes = n * (9 * sizeof(float) + sizeof(int));
+    if (bytes > ctx->pca_buf_bytes) {
+        if (ctx->pca_buf) cudaFree(ctx->pca_buf);
+        ctx->pca_buf = nullptr;
+        ctx->pca_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->pca_buf, std::max<size_t>(bytes, 16)));
+        ctx->pca_buf_bytes = bytes;
+    }
+    cudaStream_t st = ctx->stream;
+    DeviceArrays A = ctx->A;
+    A.trace = nullptr;
+    uint64_t launches = 0;
+    rc = launch_ingest(ctx, A, false, launches);
+    if (rc != MULLS_OK) return rc;
+    PcaArgs args;
+    args.radius = radius;
+    args.r2 = (float)((double)radius * (double)radius);
+    args.k = k;
+    args.stride = stride;
+    args.eigenvalues = (float *)ctx->pca_buf;
+    args.principal = args.eigenvalues + 3 * n;
+    args.normal = args.principal + 3 * n;
+    args.pt_num = (int *)(args.normal + 3 * n);
+    CK(cudaMemsetAsync(ctx->pca_buf, 0, std::max<size_t>(bytes, 16), st));
+    if (n) {
+        k_pca<<<(unsigned)ceil_div(n, kPcaWarps), kPcaWarps * 32, 0, st>>>(A, args);
+        ++launches;
+        CK(cudaMemcpyAsync(out->eigenvalues, args.eigenvalues, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->principal, args.principal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->normal, args.normal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->pt_num, args.pt_num, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (ctx->h_flags[1]) {
+        ctx->err = "hash pool exhausted";
+        return MULLS_E_CAPACITY;
+    }
+    ctx->stats = mulls_run_stats();
+    ctx->stats.kernel_launches = launches;
+    ctx->uploaded = false; // the resident batch was replaced by the PCA cloud
+    return MULLS_OK;
 }
 
 } // extern "C"

@@ -157,6 +157,43 @@ class Context:
         out = [abi.result_to_dict(r) for r in res]
         return (out, [abi.trace_to_dict(t) for t in tr]) if want_trace else (out, None)
 
+    def run_sharded(self, pair, src_index_base, src_global_n, allreduce, want_trace: bool = False):
+        """mulls_icp_run_sharded: `pair["src"]` holds this rank's contiguous slice of every source class
+        (global start index src_index_base[c] of src_global_n[c] points); `allreduce(ptr, count, dtype, op,
+        stream) -> int` performs the in-place all-reduce on a device buffer (dtype 0 = f64, 1 = i32; op 0 = sum,
+        1 = min), e.g. mulls_b200.dist.torch_allreduce()."""
+        tv, sv, pa, init, keep = self._pack([pair])
+        base = (C.c_uint32 * 6)(*[int(v) for v in src_index_base])
+        glob = (C.c_uint32 * 6)(*[int(v) for v in src_global_n])
+        res = abi.IcpResult()
+        tr = abi.IcpTrace() if want_trace else None
+
+        def _cb(user, ptr, count, dtype, op, stream):
+            try:
+                return int(allreduce(ptr, count, dtype, op, stream))
+            except Exception as exc:  # surface Python errors as a communication failure
+                print("all-reduce callback raised:", exc)
+                return 1
+
+        cb = abi.ALLREDUCE_FN(_cb)
+        self._check(self.lib.mulls_icp_run_sharded(self.handle, tv, sv, base, glob, pa, init.ctypes.data_as(
+            C.POINTER(C.c_double)), cb, None, C.byref(res), C.byref(tr) if tr is not None else None))
+        return abi.result_to_dict(res), (abi.trace_to_dict(tr) if tr is not None else None)
+
+    def pca_features(self, cloud: np.ndarray, radius: float, k: int, stride: int = 1) -> dict:
+        """PrincipleComponentAnalysis::get_pc_pca_feature (pca.hpp:294-354) on the GPU."""
+        c = abi.as_aos48(cloud)
+        n = c.shape[0]
+        ev = np.zeros((n, 3), np.float32)
+        pr = np.zeros((n, 3), np.float32)
+        nr = np.zeros((n, 3), np.float32)
+        cnt = np.zeros(n, np.int32)
+        out = abi.PcaOut(ev.ctypes.data_as(C.POINTER(C.c_float)), pr.ctypes.data_as(C.POINTER(C.c_float)),
+                         nr.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+        self._check(self.lib.mulls_pca_features(self.handle, abi.cloud_view(c), float(radius), int(k), int(stride),
+                                                C.byref(out)))
+        return {"eigenvalues": ev, "principal": pr, "normal": nr, "pt_num": cnt}
+
     def stats(self) -> dict:
         s = abi.RunStats()
         self._check(self.lib.mulls_get_stats(self.handle, C.byref(s)))

@@ -1024,7 +1024,7 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
 // ---------------------------------------------------------------------------------------------
 // pca.hpp:294-354 get_pc_pca_feature + :390-434 get_pca_feature, with
 // pcl::KdTreeFLANN::radiusSearch [3P] (all d2 <= r*r, ascending, truncated to max_nn, self included)
-// and pcl::PCA [3P] (centroid; cov = sum (p-mu)(p-mu)^T / (n-1) in float; eigen-pairs descending;
+// (strict: FLANN's KNNRadiusResultSet::addPoint tests dist < worst_dist_) and pcl::PCA [3P] (centroid; cov = sum (p-mu)(p-mu)^T / (n-1) in float; eigen-pairs descending;
 // third eigenvector replaced by col0 x col1). The eigen-decomposition here is a cyclic Jacobi in
 // double on the float covariance; Eigen's SelfAdjointEigenSolver<Matrix3f> (tridiagonal QL) agrees
 // to float rounding, which is the tolerance the PCA parity tests state.
@@ -1115,7 +1115,7 @@ int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stri
     Cloud C;
     load_cloud(cloud, C);
     const long n = (long)C.size();
-    const float r2 = radius * radius;
+    const float r2 = (float)((double)radius * (double)radius); // KdTreeFLANN::radiusSearch casts radius*radius to float
     // brute force through a uniform grid (oracle: clarity over speed)
     float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
     for (long i = 0; i < n; ++i) {
@@ -1158,7 +1158,7 @@ int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stri
                     const std::vector<int> &cell = cells[((size_t)cz * dims[1] + cy) * dims[0] + cx];
                     for (size_t t = 0; t < cell.size(); ++t) {
                         float d2 = KdTree::flann_l2(q, C[cell[t]]);
-                        if (d2 <= r2) nb.push_back(std::make_pair(d2, cell[t]));
+                        if (d2 < r2) nb.push_back(std::make_pair(d2, cell[t])); // FLANN result sets keep dist < radius
                     }
                 }
         std::sort(nb.begin(), nb.end());
