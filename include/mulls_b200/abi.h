@@ -183,7 +183,8 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
 
 /* PCA neighbourhood features (pca.hpp:294-354): for every `stride`-th point of `cloud` take the
  * at most `k` nearest neighbours within `radius` (the point itself included), and return
- * eigenvalues (descending), principal direction, normal direction, and the neighbour count. */
+ * eigenvalues (descending), principal direction, normal direction, and the neighbour count.
+ * k <= 0 or k > 1024 is treated as 1024 (the reference uses 25..50). */
 typedef struct mulls_pca_out {
     float *eigenvalues; /* [n][3] lambda1 >= lambda2 >= lambda3 (pcl::PCA convention) */
     float *principal;   /* [n][3] unit principal direction (eigenvector of lambda1) */
