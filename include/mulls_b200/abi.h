@@ -158,6 +158,7 @@ typedef struct mulls_run_stats {
     uint64_t kernel_launches;   /* kernels of this library launched by the last run */
     uint64_t algorithmic_bytes; /* sum over pairs and executed iterations of 28*(N_s,active + N_t) */
     uint64_t iterations;        /* sum over pairs of executed iterations */
+    uint64_t search_launches;   /* launches of the search kernel (one per ICP iteration of the batch) */
     float ms_ingest;            /* device time of the ingest phase (CUDA events) */
     float ms_iterate;           /* device time of the iteration kernels */
     float ms_search;            /* device time of the fused transform+NN+claim kernel only */

@@ -80,6 +80,7 @@ class RunStats(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("algorithmic_bytes", C.c_uint64),
         ("iterations", C.c_uint64),
+        ("search_launches", C.c_uint64),
         ("ms_ingest", C.c_float),
         ("ms_iterate", C.c_float),
         ("ms_search", C.c_float),

@@ -45,6 +45,8 @@ struct PairConst {
     double tbound[6];           // block1->local_bound
     // layout
     uint32_t in_off[kNumSegs];  // offset (points) of each input cloud in the AoS48 staging array
+    const float4 *in_ptr[kNumSegs]; // where the ingest kernel reads the cloud: the HBM copy, or (one-shot calls with
+                                    // pinned host buffers) the caller's buffer itself, streamed over PCIe (zero-copy)
     uint32_t in_n[kNumSegs];
     uint32_t tgt_base[kNumClasses]; // base of each class in the target SoA arrays (capacity = in_n)
     uint32_t src_base[kNumClasses]; // base of each class in the source SoA arrays

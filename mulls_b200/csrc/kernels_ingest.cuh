@@ -20,9 +20,10 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
     float x = 0, y = 0, z = 0;
     if (valid) {
         const size_t gi = (size_t)pc.in_off[seg] + local;
-        const float4 a = A.in_aos[3 * gi + 0]; // x y z _
-        const float4 b = A.in_aos[3 * gi + 1]; // nx ny nz _
-        const float4 c = A.in_aos[3 * gi + 2]; // intensity curvature _ _
+        const float4 *in = pc.in_ptr[seg] + 3 * (size_t)local;
+        const float4 a = in[0]; // x y z _
+        const float4 b = in[1]; // nx ny nz _
+        const float4 c = in[2]; // intensity curvature _ _
         x = a.x, y = a.y, z = a.z;
         float nx = b.x, ny = b.y, nz = b.z;
         if (is_src) {

@@ -65,9 +65,13 @@ constexpr int kStackDepth = 48; // DFS entries: at most 7 stay behind per descen
 // mask of existing children, the per-axis distances to the two child slabs are computed once, and only
 // children that exist and can still beat the best distance are pushed (nearest octant last = popped first;
 // Morton code = parent code << 3 | child) — the octree analogue of the kd-tree descent it replaces.
-__device__ __forceinline__ void nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
-                                          int start_level, float &best_d2, int &best_j) {
+// `budget` > 0 bounds the number of cell visits: when it runs out the function returns false with the best
+// candidate found so far (a valid seed for a second, unbounded call) — used to keep the 32 traversals of a
+// warp from waiting on a few expensive queries (they are regrouped and finished together, see k_search).
+__device__ __forceinline__ bool nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
+                                          int start_level, float &best_d2, int &best_j, int budget) {
     // best_d2 / best_j come in seeded: (INFINITY, -1) or a real candidate (the previous iteration's match)
+    int steps_left = (budget > 0) ? budget : 0x7fffffff;
     const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
     const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
     const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
@@ -100,10 +104,22 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
             sy[i] = spread12((uint32_t)ys[i]) << 1;
             sz[i] = spread12((uint32_t)zs[i]) << 2;
         }
+        // Live cells of the block as a bit mask, then one loop trip per LIVE cell: the 32 lanes of a warp run
+        // their i-th live cell together instead of idling through each other's pruned slots.
+        uint32_t live = 0;
+        {
+            const float bound0 = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
+                if (vx[i] && vy[j] && vz[m] && ex[i] + ey[j] + ez[m] <= bound0) live |= 1u << k;
+            }
+        }
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) { // k = 0: p's own cell first
+        while (live) { // lowest bit first: k = 0 is p's own cell
+            const int k = __ffs(live) - 1;
+            live &= live - 1;
             const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-            if (!(vx[i] && vy[j] && vz[m])) continue;
             int sp = 0;
             {
                 const uint64_t code = sx[i] | sy[j] | sz[m];
@@ -117,6 +133,7 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
                 --sp;
                 // a cell farther than the best so far (or than the radius) cannot change the result
                 if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                if (--steps_left < 0) return false;
                 const uint32_t meta = st_meta[sp];
                 const uint64_t code = (uint64_t)st_code[sp] | ((uint64_t)(meta & 0xf) << 32);
                 const int lv = (int)((meta >> 4) & 0xf);
@@ -172,22 +189,32 @@ __device__ __forceinline__ void nn_search(const GridView &g, float px, float py,
         if (cover2 >= r2_prune) break; // whole search radius examined
         if (l == L - 1) break;         // (n_levels is chosen so that the line above fires first)
     }
+    return true;
 }
 
 // ---- k_search ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count) {
+// start level for a search seeded with a candidate at squared distance d2: the smallest level whose
+// guaranteed coverage 0.999 * h0 * 2^(l-1) reaches that distance
+__device__ __forceinline__ int level_for_distance(const GridView &g, float d2) {
+    const float need = 1.001f * sqrtf(d2) / (0.999f * 0.5f * g.h0);
+    return (need <= 1.0f) ? 0 : (ilogbf(need) + 1);
+}
+
+__global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
+                                                      int budget) {
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning || A.hash_used[1]) return;
     const int c = (int)cd.seg;
     const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
+    if ((int)cd.first >= ns) return; // block-uniform
     const uint32_t local = cd.first + threadIdx.x;
-    if ((int)local >= ns) return;
-    const uint32_t gi = pc.src_base[c] + local;
+    const bool valid = (int)local < ns;
+    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
     float4 p = A.src_pos[buf][gi];
     float4 n = A.src_nrm[buf][gi];
-    if (ps.iter > 0) {
+    if (valid && ps.iter > 0) {
         // cregistration.hpp:1260 — incremental in-place update of the float source cloud
         const double *t = ps.T_inc;
         const double px = p.x, py = p.y, pz = p.z, qx = n.x, qy = n.y, qz = n.z;
@@ -200,23 +227,33 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
         A.src_pos[buf][gi] = p;
         A.src_nrm[buf][gi] = n;
     }
+    // determine_corres needs >= 3 points on both sides (:1727-1728)
+    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) { // block-uniform
+        if (valid) {
+            A.nn_idx[gi] = -1;
+            A.nn_d2[gi] = INFINITY;
+        }
+        return;
+    }
+    GridView g;
+    g.table = A.hash + ps.hash_base[c];
+    g.mask = ps.hash_mask[c];
+    g.pos = A.tgt_pos + pc.tgt_base[c];
+    g.nrm = A.tgt_nrm + pc.tgt_base[c];
+    g.ox = ps.origin[0], g.oy = ps.origin[1], g.oz = ps.origin[2];
+    g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
+    g.n_levels = ps.n_levels;
+    g.leaf_count = leaf_count;
+    // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
+    const float max_distance_f = 2.5f * ps.thre;
+    const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
+    const float r2_prune = (float)max_dist_sqr * 1.0001f;
+
+    // pass 1: every thread searches for its own source point, with a bounded number of cell visits
     int best_j = -1;
     float best_d2 = INFINITY;
-    // determine_corres needs >= 3 points on both sides (:1727-1728)
-    if (pc.used[c] && nsg >= 3 && nt >= 3) {
-        GridView g;
-        g.table = A.hash + ps.hash_base[c];
-        g.mask = ps.hash_mask[c];
-        g.pos = A.tgt_pos + pc.tgt_base[c];
-        g.nrm = A.tgt_nrm + pc.tgt_base[c];
-        g.ox = ps.origin[0], g.oy = ps.origin[1], g.oz = ps.origin[2];
-        g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
-        g.n_levels = ps.n_levels;
-        g.leaf_count = leaf_count;
-        // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
-        const float max_distance_f = 2.5f * ps.thre;
-        const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
-        const float r2_prune = (float)max_dist_sqr * 1.0001f;
+    bool finished = true;
+    if (valid) {
         int sl = start_level0;
         // Seed with the previous iteration's match: a real candidate, so the box-distance pruning bites from
         // the first cell on; the search then only has to prove that nothing is closer (still exact).
@@ -225,16 +262,50 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
             const float4 q = __ldg(&g.pos[pj]);
             best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
             best_j = pj;
-            // smallest level whose guaranteed coverage 0.999 * h0 * 2^(l-1) reaches that distance
-            const float need = 1.001f * sqrtf(best_d2) / (0.999f * 0.5f * g.h0);
-            sl = (need <= 1.0f) ? 0 : (ilogbf(need) + 1);
+            sl = level_for_distance(g, best_d2);
         }
-        nn_search(g, p.x, p.y, p.z, r2_prune, sl, best_d2, best_j);
-        if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
-        if (best_j >= 0) {
-            // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
-            atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
+        finished = nn_search(g, p.x, p.y, p.z, r2_prune, sl, best_d2, best_j, budget);
+    }
+    // pass 2: the unfinished (expensive) queries of the block are regrouped into the first threads and
+    // finished there, seeded with what pass 1 found — warps of similar cost instead of 31 idle lanes
+    __shared__ float4 s_q[kIterBlock];   // x y z best_d2
+    __shared__ int s_qj[kIterBlock];     // best_j
+    __shared__ int s_qi[kIterBlock];     // thread that owns the query
+    __shared__ int s_cnt;
+    if (budget > 0) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        if (!finished) {
+            const int slot = atomicAdd(&s_cnt, 1);
+            s_q[slot] = make_float4(p.x, p.y, p.z, best_d2);
+            s_qj[slot] = best_j;
+            s_qi[slot] = (int)threadIdx.x;
         }
+        __syncthreads();
+        const int m = s_cnt;
+        if ((int)threadIdx.x < m) {
+            const float4 q = s_q[threadIdx.x];
+            float d2 = q.w;
+            int j = s_qj[threadIdx.x];
+            const int sl = (j >= 0) ? level_for_distance(g, d2) : start_level0;
+            nn_search(g, q.x, q.y, q.z, r2_prune, sl, d2, j, 0);
+            s_q[threadIdx.x].w = d2;
+            s_qj[threadIdx.x] = j;
+        }
+        __syncthreads();
+        if (!finished) { // fetch the result back (slot order is arbitrary: find my slot)
+            for (int t = 0; t < m; ++t)
+                if (s_qi[t] == (int)threadIdx.x) {
+                    best_d2 = s_q[t].w;
+                    best_j = s_qj[t];
+                }
+        }
+    }
+    if (!valid) return;
+    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
+    if (best_j >= 0) {
+        // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
+        atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
     }
     A.nn_idx[gi] = best_j;
     A.nn_d2[gi] = best_d2;

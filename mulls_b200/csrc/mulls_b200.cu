@@ -42,6 +42,8 @@ struct mulls_ctx {
     // tunables
     int start_level0 = 5;
     int leaf_count = 32;
+    int search_budget = 0; // cell visits of the first search pass (0 = unbounded, single pass)
+    int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     float h0_min = 0.125f;
     int want_trace = 0;
     // timing
@@ -247,6 +249,8 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     std::string n(name);
     if (n == "start_level") ctx->start_level0 = value;
     else if (n == "leaf_count") ctx->leaf_count = value;
+    else if (n == "search_budget") ctx->search_budget = value;
+    else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
     else return MULLS_E_ARG;
     return MULLS_OK;
@@ -305,9 +309,12 @@ static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const dou
     return MULLS_OK;
 }
 
+// resident = true: the clouds are copied into HBM (mulls_batch_upload: they must survive the caller's buffers).
+// resident = false (one-shot calls): clouds in PINNED host memory are not copied at all — the ingest kernel
+// streams them over PCIe itself (zero-copy through the UVA alias), pageable ones are staged with cudaMemcpy.
 static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
                        const mulls_icp_params *params, const double *init_guess, const uint32_t *src_index_base,
-                       const uint32_t *src_global_n) {
+                       const uint32_t *src_global_n, bool resident = true) {
     if (!ctx || !tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
     if (n_pairs > ctx->max_pairs) {
         ctx->err = "more pairs than the context was created for";
@@ -366,12 +373,22 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
         ctx->err = "internal: chunk table capacity";
         return MULLS_E_CAPACITY;
     }
-    // H2D: the clouds (zero-copy views of the caller's buffers; pinned buffers copy asynchronously)
+    // the clouds: HBM copy, or zero-copy for pinned host buffers of one-shot calls
     for (size_t p = 0; p < n_pairs; ++p) {
-        const PairConst &pc = ctx->h_pc[p];
+        PairConst &pc = ctx->h_pc[p];
         for (int s = 0; s < kNumSegs; ++s) {
             const mulls_cloud_view &v = (s < kNumClasses) ? tgt[p * kNumClasses + s] : src[p * kNumClasses + (s - kNumClasses)];
+            pc.in_ptr[s] = ctx->A.in_aos + 3 * (size_t)pc.in_off[s];
             if (v.n == 0) continue;
+            if (!resident && ctx->zero_copy) {
+                cudaPointerAttributes attr;
+                if (cudaPointerGetAttributes(&attr, v.aos48) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                    attr.devicePointer != nullptr && ((uintptr_t)attr.devicePointer % 16) == 0) {
+                    pc.in_ptr[s] = (const float4 *)attr.devicePointer;
+                    continue;
+                }
+                cudaGetLastError(); // pageable memory: not an error, fall through to the copy
+            }
             CK(cudaMemcpyAsync((void *)(ctx->A.in_aos + 3 * (size_t)pc.in_off[s]), v.aos48, v.n * 48, cudaMemcpyHostToDevice,
                                ctx->stream));
         }
@@ -489,7 +506,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
+            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->search_budget);
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
             if (hook) { // exchange 1: the duplicate-check claims of all shards (min of source indices)
                 if (hook(user, A.claim, ctx->n_tgt_total, 1, 1, (void *)st) != 0) {
@@ -564,6 +581,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
         ms += t;
     }
     S.ms_search = ms;
+    S.search_launches = (uint64_t)n_search_ev;
     for (int p = 0; p < np; ++p) S.iterations += (uint64_t)ctx->h_results[p].iters;
     // algorithmic bytes are accumulated on the device per executed iteration
     {
@@ -586,9 +604,11 @@ int mulls_batch_run_resident(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_tr
 int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
                         const mulls_icp_params *params, const double *init_guess, mulls_icp_result *out,
                         mulls_icp_trace *trace) {
-    int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr);
+    int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
-    return run_impl(ctx, out, trace, nullptr, nullptr);
+    rc = run_impl(ctx, out, trace, nullptr, nullptr);
+    ctx->uploaded = false; // nothing stays resident after a one-shot call
+    return rc;
 }
 
 int mulls_icp_run(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES], const mulls_cloud_view src[MULLS_NUM_CLASSES],
@@ -603,9 +623,11 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
                           const mulls_icp_params *params, const double init_guess[16], mulls_allreduce_fn allreduce,
                           void *user, mulls_icp_result *out, mulls_icp_trace *trace) {
     if (!ctx || !allreduce) return MULLS_E_ARG;
-    int rc = upload_impl(ctx, 1, tgt, src_shard, params, init_guess, src_index_base, src_global_n);
+    int rc = upload_impl(ctx, 1, tgt, src_shard, params, init_guess, src_index_base, src_global_n, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
-    return run_impl(ctx, out, trace, allreduce, user);
+    rc = run_impl(ctx, out, trace, allreduce, user);
+    ctx->uploaded = false;
+    return rc;
 }
 
 int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
@@ -622,7 +644,7 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     mulls_cloud_view tgt[MULLS_NUM_CLASSES] = {cloud, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
     mulls_cloud_view src[MULLS_NUM_CLASSES] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
     const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    int rc = upload_impl(ctx, 1, tgt, src, &P, ident, nullptr, nullptr);
+    int rc = upload_impl(ctx, 1, tgt, src, &P, ident, nullptr, nullptr, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
     const size_t n = cloud.n;
     const size_t bytes = n * (9 * sizeof(float) + sizeof(int));

@@ -202,6 +202,54 @@ class Context:
         return d
 
 
+class PipelinedContext:
+    """N independent contexts (own CUDA stream each) on one device, driven from N host threads: while one
+    slice of a batch is being registered, the next slice's clouds are already crossing PCIe, and small
+    kernels of different slices fill each other's tails. Same results as one Context (pairs are independent)."""
+
+    def __init__(self, device: int, n_lanes: int, max_pairs_per_lane: int, max_src_pts: int, max_tgt_pts: int):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.lanes = [Context(device, max_pairs_per_lane, max_src_pts, max_tgt_pts) for _ in range(n_lanes)]
+        self.pool = ThreadPoolExecutor(n_lanes)
+        self._slices = None
+
+    def close(self):
+        for c in self.lanes:
+            c.close()
+        self.pool.shutdown()
+
+    def _split(self, pairs):
+        n, k = len(pairs), len(self.lanes)
+        bounds = [(n * i) // k for i in range(k + 1)]
+        return [pairs[bounds[i]:bounds[i + 1]] for i in range(k)]
+
+    def run_batch(self, pairs):
+        """Host buffers in, results out; slices are uploaded and registered concurrently."""
+        parts = self._split(pairs)
+        futs = [self.pool.submit(lambda c=c, p=p: c.run_batch(p)[0] if p else []) for c, p in zip(self.lanes, parts)]
+        out = []
+        for f in futs:
+            out += f.result()
+        return out
+
+    def upload(self, pairs):
+        self._slices = self._split(pairs)
+        for c, p in zip(self.lanes, self._slices):
+            if p:
+                c.upload(p)
+
+    def run_resident(self):
+        futs = [self.pool.submit(lambda c=c, p=p: c.run_resident()[0] if p else []) for c, p in zip(self.lanes, self._slices)]
+        out = []
+        for f in futs:
+            out += f.result()
+        return out
+
+    def stats(self):
+        return [c.stats() for c, p in zip(self.lanes, self._slices or [[]] * len(self.lanes)) if p]
+
+
 class CRegistration:
     """lo::CRegistration<PointT> — the part of its public surface on the hot path."""
 
