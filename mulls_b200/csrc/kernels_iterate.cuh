@@ -80,6 +80,47 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
     uint32_t st_code[kStackDepth], st_meta[kStackDepth], st_z[kStackDepth];
     float st_d2[kStackDepth];
     int l = min(max(start_level, 1), L - 1);
+    if (best_j < 0) {
+        // No candidate yet (first iteration): walk greedily from p's own level-l cell down through the nearest
+        // existing child to a leaf and take its best point as the seed. Costs a handful of probes, and gives the
+        // exact search below a tight bound from its first cell on, so that it does not stack every sibling
+        // within the (large) search radius.
+        // root of the walk: the first level, from l upwards, at which p's own cell exists
+        for (int lr = l; lr < L && best_j < 0; ++lr) {
+            const int ncell = (1 << kCoordBits) >> lr;
+            int cx = c0x >> lr, cy = c0y >> lr, cz = c0z >> lr;
+            if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell)) break;
+            uint64_t code = morton36((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+            for (int lv = lr;; --lv) {
+                uint32_t start, count, cmask;
+                if (!probe(g, cell_key(lv, code), start, count, cmask)) break; // only possible at lv == lr
+                if (count <= (uint32_t)g.leaf_count || lv == 0) {
+                    for (uint32_t jj = start; jj < start + count; ++jj) {
+                        const float4 q = __ldg(&g.pos[jj]);
+                        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
+                        if (d2 < best_d2) { // ties are settled by the exact search that follows
+                            best_d2 = d2;
+                            best_j = (int)jj;
+                        }
+                    }
+                    break;
+                }
+                const float hl = g.h0 * (float)(1 << lv);
+                const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
+                const int oy = (py >= g.oy + ((float)cy + 0.5f) * hl) ? 1 : 0;
+                const int oz = (pz >= g.oz + ((float)cz + 0.5f) * hl) ? 1 : 0;
+                int ch = ox | (oy << 1) | (oz << 2);
+                if (!((cmask >> ch) & 1u)) ch = __ffs((int)cmask) - 1; // any existing child still yields a valid seed
+                if (ch < 0) break;
+                code = (code << 3) | (uint64_t)ch;
+                cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
+            }
+        }
+        if (best_j >= 0) { // continue like a seeded search: the smallest level whose coverage reaches the seed
+            const float need = 1.001f * sqrtf(best_d2) / (0.999f * 0.5f * g.h0);
+            l = min(max((need <= 1.0f) ? 0 : (ilogbf(need) + 1), 1), L - 1);
+        }
+    }
     for (;; ++l) {
         const float H = g.h0 * (float)(1 << l);
         const int ncell = (1 << kCoordBits) >> l;

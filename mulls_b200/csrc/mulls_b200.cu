@@ -41,7 +41,7 @@ struct mulls_ctx {
     bool uploaded = false;
     // tunables
     int start_level0 = 5;
-    int leaf_count = 32;
+    int leaf_count = 64;
     int search_budget = 0; // cell visits of the first search pass (0 = unbounded, single pass)
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     float h0_min = 0.125f;
