@@ -11,13 +11,14 @@
 // unchanged. Needs PCL + Eigen (for the types only) and -lmulls_b200.
 //
 // Contract differences: block1->tree_* are not populated; options
-// normal_shooting_on / apply_motion_undistortion_while_registration / keep_less_source_points are
-// rejected (LOG + return 0 with the constraint untouched).
+// normal_shooting_on / keep_less_source_points are rejected (LOG + return 0 with the constraint untouched).
 #ifndef MULLS_B200_CREGISTRATION_SHIM_HPP
 #define MULLS_B200_CREGISTRATION_SHIM_HPP
 
+#include <cmath>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "mulls_b200/abi.h"
 #include "utility.hpp" // lo::constraint_t, lo::cloudblock_t, Matrix6d, Point_T
@@ -65,7 +66,8 @@ int mm_lls_icp(constraint_t &registration_cons, // cblock_1 (target point cloud)
     mulls_cloud_view tgt[MULLS_NUM_CLASSES] = {view_of<PointT>(b1.pc_ground), view_of<PointT>(b1.pc_pillar),
                                                view_of<PointT>(b1.pc_facade), view_of<PointT>(b1.pc_beam),
                                                view_of<PointT>(b1.pc_roof),   view_of<PointT>(b1.pc_vertex)};
-    const bool down = !use_more_points;
+    // the undistortion variant reads block2->pc_*_down whatever use_more_points says (cregistration.hpp:1251-1253)
+    const bool down = !use_more_points || apply_motion_undistortion_while_registration;
     mulls_cloud_view src[MULLS_NUM_CLASSES] = {
         view_of<PointT>(down ? b2.pc_ground_down : b2.pc_ground), view_of<PointT>(down ? b2.pc_pillar_down : b2.pc_pillar),
         view_of<PointT>(down ? b2.pc_facade_down : b2.pc_facade), view_of<PointT>(down ? b2.pc_beam_down : b2.pc_beam),
@@ -117,6 +119,80 @@ int mm_lls_icp(constraint_t &registration_cons, // cblock_1 (target point cloud)
     registration_cons.sigma = out.sigma;           // :1419
     registration_cons.confidence = out.confidence; // :1420
     return out.code;                               // :1439
+}
+
+// lo::CRegistration<PointT>::mm_lls_icp_4dof_global (cregistration.hpp:1584-1681), same signature. The reference
+// tries the headings one after the other; the trials are independent registrations of the same clouds, so here
+// they are ONE mulls_icp_run_batch call.
+template <typename PointT>
+bool mm_lls_icp_4dof_global(constraint_t &registration_con, float heading_step_d, int max_iter_num = 20,
+                            float dis_thre_unit = 1.5, float converge_translation = 0.005,
+                            float converge_rotation_d = 0.05, float dis_thre_min = 0.5,
+                            float dis_thre_update_rate = 1.05, float max_bearable_rotation_d = 15.0) {
+    (void)converge_rotation_d, (void)max_bearable_rotation_d; // not forwarded by the reference either (:1636-1638)
+    cloudblock_t &b1 = *registration_con.block1;
+    cloudblock_t &b2 = *registration_con.block2;
+    std::vector<double> guesses;
+    std::vector<float> headings;
+    for (float heading_d = 0.0f; heading_d < 360.0; heading_d += heading_step_d) { // float accumulation as :1604, :1654
+        const float heading_rad = heading_d * M_PI / 180.0;
+        const double c = cos(heading_rad), s = sin(heading_rad);
+        const double sx = b2.local_station.x, sy = b2.local_station.y, sz = b2.local_station.z;
+        // tran_mat_s2g * rot_z * tran_mat_g2s (:1621-1630), written out
+        const double R[16] = {c, s, 0, sx - c * sx - s * sy, -s, c, 0, sy + s * sx - c * sy, 0, 0, 1, sz - sz, 0, 0, 0, 1};
+        guesses.insert(guesses.end(), R, R + 16);
+        headings.push_back(heading_d);
+    }
+    const size_t n = headings.size();
+    mulls_cloud_view tgt1[MULLS_NUM_CLASSES] = {view_of<PointT>(b1.pc_ground), view_of<PointT>(b1.pc_pillar),
+                                                view_of<PointT>(b1.pc_facade), view_of<PointT>(b1.pc_beam),
+                                                view_of<PointT>(b1.pc_roof),   view_of<PointT>(b1.pc_vertex)};
+    mulls_cloud_view src1[MULLS_NUM_CLASSES] = {view_of<PointT>(b2.pc_ground_down), view_of<PointT>(b2.pc_pillar_down),
+                                                view_of<PointT>(b2.pc_facade_down), view_of<PointT>(b2.pc_beam_down),
+                                                view_of<PointT>(b2.pc_roof_down),   view_of<PointT>(b2.pc_vertex)};
+    mulls_icp_params p;
+    mulls_icp_default_params(&p);
+    p.max_iter_num = max_iter_num;
+    p.dis_thre_unit = dis_thre_unit;
+    p.converge_translation = converge_translation;
+    p.converge_rotation_d = converge_translation; // sic, :1636-1637
+    p.dis_thre_min = dis_thre_min;
+    p.dis_thre_update_rate = dis_thre_update_rate;
+    std::strncpy(p.used_feature_type, "111110", 7);
+    std::strncpy(p.weight_strategy, "1001", 7);
+    const bounds_t &lb = b1.local_bound;
+    p.target_bound[0] = lb.min_x, p.target_bound[1] = lb.min_y, p.target_bound[2] = lb.min_z;
+    p.target_bound[3] = lb.max_x, p.target_bound[4] = lb.max_y, p.target_bound[5] = lb.max_z;
+    std::vector<mulls_cloud_view> tgt(n * MULLS_NUM_CLASSES), src(n * MULLS_NUM_CLASSES);
+    std::vector<mulls_icp_params> params(n, p);
+    for (size_t i = 0; i < n; ++i)
+        for (int c = 0; c < MULLS_NUM_CLASSES; ++c) tgt[i * MULLS_NUM_CLASSES + c] = tgt1[c], src[i * MULLS_NUM_CLASSES + c] = src1[c];
+    size_t ns = 0, nt = 0;
+    for (int c = 0; c < MULLS_NUM_CLASSES; ++c) ns += src1[c].n, nt += tgt1[c].n;
+    mulls_ctx *ctx = mulls_create(0, n, ns ? ns : 1, nt ? nt : 1);
+    std::vector<mulls_icp_result> out(n);
+    const bool ran = ctx && mulls_icp_run_batch(ctx, n, tgt.data(), src.data(), params.data(), guesses.data(), out.data(), nullptr) == MULLS_OK;
+    if (!ran) LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
+    if (ctx) mulls_destroy(ctx);
+    if (!ran) return false;
+    float current_best_score = 0;
+    bool successful_reg = false;
+    for (size_t i = 0; i < n; ++i) {
+        if (out[i].code > 0) {
+            const float cur_score = out[i].confidence / out[i].sigma;
+            if (cur_score > current_best_score) {
+                for (int r = 0; r < 4; ++r)
+                    for (int c = 0; c < 4; ++c) registration_con.Trans1_2(r, c) = out[i].T[4 * r + c];
+                for (int r = 0; r < 6; ++r)
+                    for (int c = 0; c < 6; ++c) registration_con.information_matrix(r, c) = out[i].info[6 * r + c];
+                registration_con.sigma = out[i].sigma;
+                registration_con.confidence = out[i].confidence;
+                current_best_score = cur_score;
+            }
+            successful_reg = true;
+        }
+    }
+    return successful_reg;
 }
 
 } // namespace b200

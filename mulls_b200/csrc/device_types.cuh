@@ -39,6 +39,11 @@ struct PairConst {
     float max_t, max_r;         // max_bearable_translation / rotation (float as :1162,:1164)
     float min_ratio;            // min_neccessary_corr_ratio
     int apply_filter;
+    // motion undistortion at iteration 0 (cregistration.hpp:1248-1258, cfilter.hpp:496-516): slerp(I, q, s) * p + s * t
+    int undistort, ud_linear, ud_neg;
+    double ud_q[4];  // quaternion (x y z w) of the inverse initial guess
+    double ud_t[3];  // its translation
+    double ud_theta, ud_sin_theta;
     double cos_thre;            // cos(normal_bearing/180*pi), :1818
     double sigma_thre;          // :2524
     double init[16];            // initial guess, row-major

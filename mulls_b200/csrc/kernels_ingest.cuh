@@ -28,13 +28,46 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
         float nx = b.x, ny = b.y, nz = b.z;
         if (is_src) {
             const double *t = pc.init;
-            const double px = x, py = y, pz = z, qx = nx, qy = ny, qz = nz;
-            x = (float)(t[0] * px + t[1] * py + t[2] * pz + t[3]);
-            y = (float)(t[4] * px + t[5] * py + t[6] * pz + t[7]);
-            z = (float)(t[8] * px + t[9] * py + t[10] * pz + t[11]);
-            nx = (float)(t[0] * qx + t[1] * qy + t[2] * qz);
-            ny = (float)(t[4] * qx + t[5] * qy + t[6] * qz);
-            nz = (float)(t[8] * qx + t[9] * qy + t[10] * qz);
+            int n_apply = 1;
+            if (pc.undistort) {
+                if (cls == MULLS_VERTEX) {
+                    n_apply = 2; // not undistorted and not re-cloned: the initial guess lands twice (reference behaviour)
+                } else {
+                    const float curv = c.y; // timestamp ratio of the point inside its frame
+                    if (!(curv < 0.0f || (double)curv > 1.0)) {
+                        const double s = (double)curv;
+                        double scale0, scale1;
+                        if (pc.ud_linear) {
+                            scale0 = 1.0 - s;
+                            scale1 = s;
+                        } else {
+                            scale0 = sin((1.0 - s) * pc.ud_theta) / pc.ud_sin_theta;
+                            scale1 = sin(s * pc.ud_theta) / pc.ud_sin_theta;
+                        }
+                        if (pc.ud_neg) scale1 = -scale1;
+                        const double qx = scale1 * pc.ud_q[0], qy = scale1 * pc.ud_q[1], qz = scale1 * pc.ud_q[2],
+                                     qw = scale0 + scale1 * pc.ud_q[3];
+                        const double vx = x, vy = y, vz = z;
+                        double ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
+                        ux += ux, uy += uy, uz += uz;
+                        const double rx = vx + qw * ux + (qy * uz - qz * uy);
+                        const double ry = vy + qw * uy + (qz * ux - qx * uz);
+                        const double rz = vz + qw * uz + (qx * uy - qy * ux);
+                        x = (float)(rx + s * pc.ud_t[0]);
+                        y = (float)(ry + s * pc.ud_t[1]);
+                        z = (float)(rz + s * pc.ud_t[2]);
+                    }
+                }
+            }
+            for (int rep = 0; rep < n_apply; ++rep) {
+                const double px = x, py = y, pz = z, qx = nx, qy = ny, qz = nz;
+                x = (float)(t[0] * px + t[1] * py + t[2] * pz + t[3]);
+                y = (float)(t[4] * px + t[5] * py + t[6] * pz + t[7]);
+                z = (float)(t[8] * px + t[9] * py + t[10] * pz + t[11]);
+                nx = (float)(t[0] * qx + t[1] * qy + t[2] * qz);
+                ny = (float)(t[4] * qx + t[5] * qy + t[6] * qz);
+                nz = (float)(t[8] * qx + t[9] * qy + t[10] * qz);
+            }
         }
         A.stg_pos[gi] = make_float4(x, y, z, c.x);
         A.stg_nrm[gi] = make_float4(nx, ny, nz, __int_as_float((int)local));

@@ -262,14 +262,65 @@ int mulls_get_stats(const mulls_ctx *ctx, mulls_run_stats *out) {
     return MULLS_OK;
 }
 
+// Inverse of the initial guess (Eigen Matrix4d::inverse: cofactors / determinant), its quaternion
+// (Eigen::Quaterniond(Matrix3d)) and the per-pair constants of Eigen's slerp(Identity -> q)
+// (cregistration.hpp:1248, cfilter.hpp:499-502).
+static void setup_undistortion(const double *m, PairConst &pc) {
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    double T[16];
+    for (int i = 0; i < 16; ++i) T[i] = inv[i] * (1.0 / det);
+    double q[4]; // x y z w
+    double t = T[0] + T[5] + T[10];
+    if (t > 0.0) {
+        t = std::sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (T[9] - T[6]) * t;
+        q[1] = (T[2] - T[8]) * t;
+        q[2] = (T[4] - T[1]) * t;
+    } else {
+        int i = 0;
+        if (T[5] > T[0]) i = 1;
+        if (T[10] > T[5 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(T[5 * i] - T[5 * j] - T[5 * k] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (T[4 * k + j] - T[4 * j + k]) * t;
+        q[j] = (T[4 * j + i] + T[4 * i + j]) * t;
+        q[k] = (T[4 * k + i] + T[4 * i + k]) * t;
+    }
+    for (int i = 0; i < 4; ++i) pc.ud_q[i] = q[i];
+    pc.ud_t[0] = T[3], pc.ud_t[1] = T[7], pc.ud_t[2] = T[11];
+    const double one = 1.0 - 2.220446049250313e-16;
+    const double d = q[3], absD = std::fabs(d);
+    pc.ud_linear = (absD >= one) ? 1 : 0;
+    pc.ud_neg = (d < 0) ? 1 : 0;
+    pc.ud_theta = pc.ud_linear ? 0.0 : std::acos(absD);
+    pc.ud_sin_theta = pc.ud_linear ? 1.0 : std::sin(pc.ud_theta);
+}
+
 // ------------------------------------------------------------------------------------------------
 static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const double *init, PairConst &pc) {
     if (P.normal_shooting_on) {
         ctx->err = "normal_shooting_on is not implemented (SURVEY 8f rank 4)";
-        return MULLS_E_UNSUPPORTED;
-    }
-    if (P.apply_motion_undistortion_while_registration) {
-        ctx->err = "apply_motion_undistortion_while_registration is not implemented";
         return MULLS_E_UNSUPPORTED;
     }
     if (P.keep_less_source_points) {
@@ -301,7 +352,10 @@ static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const dou
     pc.max_t = (float)(2.0 * P.dis_thre_unit);
     pc.max_r = (float)(P.max_bearable_rotation_d / 180.0 * M_PI);
     pc.min_ratio = P.min_neccessary_corr_ratio;
-    pc.apply_filter = P.apply_intersection_filter ? 1 : 0;
+    // the intersection filter is skipped in the undistortion variant (cregistration.hpp:1186)
+    pc.undistort = P.apply_motion_undistortion_while_registration ? 1 : 0;
+    pc.apply_filter = (P.apply_intersection_filter && !pc.undistort) ? 1 : 0;
+    if (pc.undistort) setup_undistortion(init, pc);
     pc.cos_thre = std::cos(P.normal_bearing / 180.0 * M_PI);
     pc.sigma_thre = (double)P.sigma_thre;
     for (int i = 0; i < 16; ++i) pc.init[i] = init[i];

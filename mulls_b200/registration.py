@@ -41,6 +41,8 @@ class CloudBlock:
     pc_roof_down: np.ndarray = field(default_factory=_empty)
     # bounds_t local_bound: min_x min_y min_z max_x max_y max_z (utility.hpp:101-136)
     local_bound: tuple = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+    # centerpoint_t local_station (utility.hpp:92-99): the scanner position, pivot of the 4-DoF global search
+    local_station: tuple = (0.0, 0.0, 0.0)
 
     def clone_feature(self, get_feature_down: bool):
         """cloudblock_t::clone_feature (utility.hpp:524-550): the six clouds mm_lls_icp works on."""
@@ -250,12 +252,82 @@ class PipelinedContext:
         return [c.stats() for c, p in zip(self.lanes, self._slices or [[]] * len(self.lanes)) if p]
 
 
+def heading_trial_guesses(local_station, heading_step_d: float):
+    """The initial guesses mm_lls_icp_4dof_global tries (cregistration.hpp:1607-1641): a rotation about z by
+    heading_d = 0, step, 2*step, ... < 360 (accumulated in float as the reference does), about the source
+    block's station. Returns (list of heading_d, list of 4x4)."""
+    heads, mats = [], []
+    heading_d = np.float32(0.0)
+    step = np.float32(heading_step_d)
+    sx, sy, sz = (float(v) for v in local_station)
+    while float(heading_d) < 360.0:
+        heading_rad = np.float32(float(heading_d) * np.pi / 180.0)
+        rot = np.eye(4)
+        rot[0, 0] = np.cos(float(heading_rad))
+        rot[0, 1] = np.sin(float(heading_rad))
+        rot[1, 0] = -np.sin(float(heading_rad))
+        rot[1, 1] = np.cos(float(heading_rad))
+        g2s, s2g = np.eye(4), np.eye(4)
+        g2s[:3, 3] = (-sx, -sy, -sz)
+        s2g[:3, 3] = (sx, sy, sz)
+        mats.append(s2g @ rot @ g2s)
+        heads.append(float(heading_d))
+        heading_d = np.float32(heading_d + step)
+    return heads, mats
+
+
 class CRegistration:
     """lo::CRegistration<PointT> — the part of its public surface on the hot path."""
 
     def __init__(self, device: int = 0, max_src_pts: int = 700000, max_tgt_pts: int = 700000):
+        self._device, self._max_src, self._max_tgt = device, max_src_pts, max_tgt_pts
         self._ctx = Context(device, 1, max_src_pts, max_tgt_pts)
+        self._batch_ctx = None
         self.last_trace = None
+
+    def mm_lls_icp_4dof_global(self, registration_con: Constraint, heading_step_d: float, max_iter_num: int = 20,
+                               dis_thre_unit: float = 1.5, converge_translation: float = 0.005,
+                               converge_rotation_d: float = 0.05, dis_thre_min: float = 0.5,
+                               dis_thre_update_rate: float = 1.05, max_bearable_rotation_d: float = 15.0) -> bool:
+        """lo::CRegistration::mm_lls_icp_4dof_global (cregistration.hpp:1584-1681): try every heading and keep the
+        registration with the best confidence / sigma. The reference runs the trials one after the other; here
+        they are ONE batched call — the trials are independent registrations of the same clouds.
+        As in the reference, converge_translation is also passed as converge_rotation_d (:1636-1637) and
+        converge_rotation_d / max_bearable_rotation_d are not forwarded."""
+        heads, mats = heading_trial_guesses(registration_con.block2.local_station, heading_step_d)
+        p = abi.default_params()
+        p.max_iter_num = max_iter_num
+        p.dis_thre_unit = dis_thre_unit
+        p.converge_translation = converge_translation
+        p.converge_rotation_d = converge_translation
+        p.dis_thre_min = dis_thre_min
+        p.dis_thre_update_rate = dis_thre_update_rate
+        p.used_feature_type = b"111110"
+        p.weight_strategy = b"1001"
+        p.target_bound[:] = list(registration_con.block1.local_bound)
+        tgt = registration_con.block1.clone_feature(False)
+        src = registration_con.block2.clone_feature(True)
+        pairs = [{"tgt": tgt, "src": src, "params": p, "init_guess": m} for m in mats]
+        ns, nt = sum(len(s) for s in src), sum(len(t) for t in tgt)
+        if self._batch_ctx is None or self._batch_ctx.max_pairs < len(pairs) or self._batch_cap < (ns, nt):
+            if self._batch_ctx is not None:
+                self._batch_ctx.close()
+            self._batch_ctx = Context(self._device, len(pairs), max(ns, 1), max(nt, 1))
+            self._batch_cap = (ns, nt)
+        res, _ = self._batch_ctx.run_batch(pairs)
+        best_score, ok = 0.0, False
+        self.best_heading_d = None
+        for h, r in zip(heads, res):
+            if r["code"] > 0:
+                score = np.float32(r["confidence"]) / np.float32(r["sigma"])
+                if score > best_score:
+                    registration_con.Trans1_2 = r["T"]
+                    registration_con.sigma = r["sigma"]
+                    registration_con.information_matrix = r["info"]
+                    registration_con.confidence = r["confidence"]
+                    best_score, self.best_heading_d = float(score), h
+                ok = True
+        return ok
 
     def mm_lls_icp(self, registration_cons: Constraint, max_iter_num: int = 20, dis_thre_unit: float = 1.5,
                    converge_translation: float = 0.002, converge_rotation_d: float = 0.01, dis_thre_min: float = 0.4,

@@ -41,6 +41,7 @@ struct Pt {
     float x, y, z;
     float nx, ny, nz;
     float intensity;
+    float curvature; // timestamp ratio in the frame when motion undistortion is used (cfilter.hpp:412-467)
 };
 typedef std::vector<Pt> Cloud;
 
@@ -613,6 +614,96 @@ static void quat_euler_jacobi(const double e[3], double J[3][3]) {
     J[2][2] = 0.5 * (cr * cp * cy + sr * sp * sy);
 }
 
+// Eigen::Matrix4d::inverse() [3P]: general 4x4 inverse by cofactors (adjugate / determinant)
+static Mat4 inverse4(const Mat4 &M) {
+    const double *m = &M.a[0][0];
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    Mat4 R;
+    for (int i = 0; i < 16; ++i) (&R.a[0][0])[i] = inv[i] * (1.0 / det);
+    return R;
+}
+
+// Eigen::Quaterniond(Matrix3d) [3P] -> (x, y, z, w)
+static void quat_from_rotation(const Mat4 &T, double q[4]) {
+    const double(*m)[4] = T.a;
+    double t = m[0][0] + m[1][1] + m[2][2];
+    if (t > 0.0) {
+        t = std::sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (m[2][1] - m[1][2]) * t;
+        q[1] = (m[0][2] - m[2][0]) * t;
+        q[2] = (m[1][0] - m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (m[k][j] - m[j][k]) * t;
+        q[j] = (m[j][i] + m[i][j]) * t;
+        q[k] = (m[k][i] + m[i][k]) * t;
+    }
+}
+
+// cfilter.hpp:496-516 apply_motion_compensation(pc_in, pc_out, Tran): per point with timestamp ratio
+// s = curvature in [0,1]: p <- slerp(Identity, q(Tran), s) * p + s * t(Tran)   (Eigen slerp / quaternion
+// rotation [3P]); coordinates stored back as float; normals untouched.
+static void motion_compensate(Cloud &c, const Mat4 &Tran) {
+    double q[4];
+    quat_from_rotation(Tran, q);
+    const double tr[3] = {Tran.a[0][3], Tran.a[1][3], Tran.a[2][3]};
+    const float s_ambigous_thre = 0.0f;
+    const double one = 1.0 - 2.220446049250313e-16;
+    const double d = q[3]; // Identity.dot(other)
+    const double absD = std::fabs(d);
+    for (size_t i = 0; i < c.size(); ++i) {
+        Pt &p = c[i];
+        if (p.curvature < s_ambigous_thre || p.curvature > 1.0 - s_ambigous_thre) continue;
+        const double t = p.curvature;
+        double scale0, scale1;
+        if (absD >= one) {
+            scale0 = 1.0 - t;
+            scale1 = t;
+        } else {
+            const double theta = std::acos(absD);
+            const double sinTheta = std::sin(theta);
+            scale0 = std::sin((1.0 - t) * theta) / sinTheta;
+            scale1 = std::sin((t * theta)) / sinTheta;
+        }
+        if (d < 0) scale1 = -scale1;
+        const double qx = scale1 * q[0], qy = scale1 * q[1], qz = scale1 * q[2], qw = scale0 + scale1 * q[3];
+        const double vx = p.x, vy = p.y, vz = p.z;
+        double ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx; // uv = vec x v
+        ux += ux, uy += uy, uz += uz;
+        const double rx = vx + qw * ux + (qy * uz - qz * uy);
+        const double ry = vy + qw * uy + (qz * ux - qx * uz);
+        const double rz = vz + qw * uz + (qx * uy - qy * ux);
+        p.x = rx + t * tr[0];
+        p.y = ry + t * tr[1];
+        p.z = rz + t * tr[2];
+    }
+}
+
 struct Timers {
     double kd_build = 0, update = 0, search = 0, estimate = 0, total = 0;
 };
@@ -700,7 +791,7 @@ static void load_cloud(const mulls_cloud_view &v, Cloud &c) {
     c.resize(v.n);
     for (size_t i = 0; i < v.n; ++i) {
         const float *f = v.aos48 + 12 * i;
-        Pt p = {f[0], f[1], f[2], f[4], f[5], f[6], f[8]};
+        Pt p = {f[0], f[1], f[2], f[4], f[5], f[6], f[8], f[9]};
         c[i] = p;
     }
 }
@@ -748,6 +839,10 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
         load_cloud(tgtv[c], tc[c]);
         load_cloud(srcv[c], sc[c]);
     }
+    Cloud sc_orig[6]; // block2->pc_*_down as delivered (read again by the undistortion variant, :1251-1253)
+    const bool undistort = P.apply_motion_undistortion_while_registration != 0;
+    if (undistort)
+        for (int c = 0; c < 6; ++c) sc_orig[c] = sc[c];
     // :1183 apply initial guess
     for (int c = 0; c < 6; ++c) transform_cloud(sc[c], initial_guess);
 
@@ -822,8 +917,19 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
     for (int i = 0; i < P.max_iter_num; i++) {
         iters_entered = i + 1;
         double t1 = now_s();
-        // :1260 incremental in-place update of the float source clouds
-        for (int c = 0; c < 6; ++c) transform_cloud(sc[c], TempTran);
+        if (undistort && i == 0) {
+            // :1248-1258 undistort the delivered source clouds with the inverse initial guess, then apply the
+            // initial guess. The vertex cloud is not undistorted (undistort_keypoints_or_not = false) and is
+            // NOT re-cloned, so it receives the initial guess a second time — reproduced as the reference does.
+            const Mat4 inv_init_guess_mat = inverse4(initial_guess);
+            for (int c = 0; c < 5; ++c) {
+                sc[c] = sc_orig[c];
+                motion_compensate(sc[c], inv_init_guess_mat);
+            }
+            for (int c = 0; c < 6; ++c) transform_cloud(sc[c], initial_guess);
+        } else
+            // :1260 incremental in-place update of the float source clouds
+            for (int c = 0; c < 6; ++c) transform_cloud(sc[c], TempTran);
         double t2 = now_s();
         if (tm) tm->update += t2 - t1;
 

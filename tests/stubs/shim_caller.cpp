@@ -17,6 +17,7 @@ int main() {
                                              0.25 * reg_corr_dis_thre, 1.1, "111110", "1101", 1.0, 0.1, 0.1, 0.1, init_mat);
     // defaults-only call
     int code2 = lo::b200::mm_lls_icp<Point_T>(reg_con);
-    std::printf("shim compiled and linked; codes %d %d\n", code, code2);
+    bool ok4 = lo::b200::mm_lls_icp_4dof_global<Point_T>(reg_con, 45.0f); // the commented-out call of test/mulls_reg.cpp:197
+    std::printf("shim compiled and linked; codes %d %d %d\n", code, code2, (int)ok4);
     return 0;
 }

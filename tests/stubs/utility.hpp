@@ -59,9 +59,13 @@ namespace lo {
 struct bounds_t {
     double min_x = 0, min_y = 0, min_z = 0, max_x = 0, max_y = 0, max_z = 0;
 };
+struct centerpoint_t {
+    double x = 0, y = 0, z = 0;
+};
 struct cloudblock_t {
     typedef pcl::PointCloud<Point_T>::Ptr pcTPtr;
     bounds_t local_bound;
+    centerpoint_t local_station;
     pcTPtr pc_ground, pc_facade, pc_roof, pc_pillar, pc_beam, pc_vertex;
     pcTPtr pc_ground_down, pc_facade_down, pc_roof_down, pc_pillar_down, pc_beam_down;
     cloudblock_t() {

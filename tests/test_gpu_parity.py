@@ -219,3 +219,65 @@ def test_reference_interface_mirror(oracle_mod, small_pair):
     assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
     with pytest.raises(RuntimeError):  # options this build does not implement fail loudly
         creg.mm_lls_icp(con, normal_shooting_on=True)
+
+
+def test_motion_undistortion_variant(ctx, oracle_mod, small_pair):
+    """apply_motion_undistortion_while_registration (cregistration.hpp:1248-1258): per-point slerp by the
+    timestamp ratio in `curvature`, intersection filter off, vertex cloud gets the initial guess twice."""
+    rng = np.random.default_rng(7)
+    src = [s.copy() for s in small_pair["src"]]
+    for s in src:
+        s[:, 9] = rng.uniform(-0.05, 1.05, len(s)).astype(np.float32)  # a few ratios outside [0,1]: left untouched
+    tgt = list(small_pair["tgt"])
+    tgt[abi.VERTEX] = small_pair["tgt"][abi.PILLAR][::3].copy()
+    src[abi.VERTEX] = src[abi.PILLAR][::3].copy()
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.apply_motion_undistortion_while_registration = 1
+    p.used_feature_type = b"111111"
+    init = np.eye(4)
+    init[:3, :3] = synth.rpy_matrix(0.002, -0.001, 0.012)
+    init[:3, 3] = (0.9, 0.04, 0.01)
+    pair = dict(small_pair, tgt=tgt, src=src, params=p, init_guess=init)
+    assert_parity(*run_both(ctx, oracle_mod, pair))
+    # a rotation-free initial guess exercises the linear branch of the slerp
+    init2 = np.eye(4)
+    init2[:3, 3] = (0.7, 0.0, 0.0)
+    assert_parity(*run_both(ctx, oracle_mod, dict(pair, init_guess=init2)))
+
+
+def test_4dof_global_heading_search(oracle_mod, small_pair):
+    """mm_lls_icp_4dof_global (cregistration.hpp:1584-1681): the heading trials run as one batched call; the
+    winner and its outputs must equal the oracle run trial by trial in the reference's loop order."""
+    from mulls_b200.registration import CloudBlock, Constraint, CRegistration, heading_trial_guesses
+
+    # rotate the source by 90 degrees about its station so that only one heading trial can succeed
+    yaw = np.eye(4)
+    yaw[:3, :3] = synth.rpy_matrix(0.0, 0.0, np.pi / 2)
+    src = []
+    for s in small_pair["src"]:
+        a = s.copy()
+        a[:, 0:3] = (s[:, 0:3].astype(np.float64) @ yaw[:3, :3].T).astype(np.float32)
+        a[:, 4:7] = (s[:, 4:7].astype(np.float64) @ yaw[:3, :3].T).astype(np.float32)
+        src.append(a)
+    con = Constraint(block1=CloudBlock.from_class_list(small_pair["tgt"]), block2=CloudBlock.from_class_list(src))
+    con.block2.local_station = (0.0, 0.0, 0.0)
+    creg = CRegistration(0, 100000, 100000)
+    ok = creg.mm_lls_icp_4dof_global(con, 45.0, max_iter_num=12, dis_thre_unit=1.5)
+    # oracle, sequentially
+    heads, mats = heading_trial_guesses(con.block2.local_station, 45.0)
+    p = abi.default_params()
+    p.max_iter_num, p.dis_thre_unit, p.converge_translation, p.converge_rotation_d = 12, 1.5, 0.005, 0.005
+    p.dis_thre_min, p.dis_thre_update_rate, p.used_feature_type, p.weight_strategy = 0.5, 1.05, b"111110", b"1001"
+    p.target_bound[:] = list(con.block1.local_bound)
+    best, best_h, best_r = 0.0, None, None
+    for h, m in zip(heads, mats):
+        r, _ = oracle_mod.icp_run(con.block1.clone_feature(False), con.block2.clone_feature(True), p, m, want_trace=False)
+        if r["code"] > 0:
+            score = np.float32(r["confidence"]) / np.float32(r["sigma"])
+            if score > best:
+                best, best_h, best_r = float(score), h, r
+    assert ok == (best_r is not None) and ok
+    assert creg.best_heading_d == best_h
+    dt, dr = synth.pose_error(con.Trans1_2, best_r["T"])
+    assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
+    np.testing.assert_allclose(con.sigma, best_r["sigma"], rtol=1e-5)
