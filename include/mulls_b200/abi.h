@@ -91,11 +91,16 @@ typedef struct mulls_icp_params {
     int32_t normal_shooting_on;                           /* must be 0 (MULLS_E_UNSUPPORTED) */
     float normal_bearing;
     int32_t use_more_points; /* informational: the caller already chose pc_* vs pc_*_down */
-    int32_t keep_less_source_points; /* must be 0 (MULLS_E_UNSUPPORTED; time-seeded RNG upstream) */
+    int32_t keep_less_source_points; /* random down-sampling of :2866-2892, deterministic in random_seed */
     float sigma_thre;
     float min_neccessary_corr_ratio;
     float max_bearable_rotation_d;
     double target_bound[6]; /* block1->local_bound: min_x min_y min_z max_x max_y max_z */
+    /* Seed of the random down-sampling used by keep_less_source_points. The reference seeds pcl::RandomSample
+     * with time(NULL) (cfilter.hpp:620), i.e. its result is not reproducible; here the kept subset is
+     * a deterministic uniform sample: the k points with the smallest splitmix64(seed, cloud, index) keys. */
+    uint32_t random_seed;
+    uint32_t _pad;
 } mulls_icp_params;
 
 /* Outputs of mm_lls_icp: constraint_t::Trans1_2 / information_matrix / sigma / confidence

@@ -47,6 +47,8 @@ class IcpParams(C.Structure):
         ("min_neccessary_corr_ratio", C.c_float),
         ("max_bearable_rotation_d", C.c_float),
         ("target_bound", C.c_double * 6),
+        ("random_seed", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 
@@ -219,6 +221,7 @@ def default_params() -> IcpParams:
     p.max_bearable_rotation_d = 45.0
     big = 1.7976931348623157e308
     p.target_bound[:] = [-big, -big, -big, big, big, big]
+    p.random_seed = 0
     return p
 
 

@@ -44,6 +44,8 @@ struct PairConst {
     double ud_q[4];  // quaternion (x y z w) of the inverse initial guess
     double ud_t[3];  // its translation
     double ud_theta, ud_sin_theta;
+    int keep_less;          // keep_less_source_pts (cregistration.hpp:1191-1193, :2866-2892)
+    uint32_t random_seed;
     double cos_thre;            // cos(normal_bearing/180*pi), :1818
     double sigma_thre;          // :2524
     double init[16];            // initial guess, row-major
@@ -96,6 +98,11 @@ struct PairState {
     int bb_src[6];                     // ordered-int encoded bbox of source ground/pillar/facade
     int bb_tgt[6];                     // ordered-int encoded bbox of all target points
     uint64_t alg_bytes;                // 28*(N_s,active + N_t) summed over executed iterations
+    // random down-sampling (keep_less_source_points): radix select of the k-th smallest sampling key per cloud
+    int kl_keep[kNumSegs];             // -1: cloud untouched, else the number of points to keep
+    uint32_t kl_rank[kNumSegs];
+    uint64_t kl_prefix[kNumSegs];
+    uint32_t kl_hist[kNumSegs][256];
 };
 
 struct HashEntry { // 16 B, one LDG.128 per probe

@@ -210,6 +210,112 @@ __global__ void __launch_bounds__(kIngestBlock) k_make_keys(DeviceArrays A) {
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&ps.seg_count[seg], (unsigned)__popc(ballot));
 }
 
+// ---- keep_less_source_pts (cregistration.hpp:2866-2892) -> random_downsample_pcl (cfilter.hpp:606-628) --------
+// The reference samples with pcl::RandomSample seeded by time(NULL); here the kept subset of a cloud is the k
+// points with the smallest key splitmix64(seed, cloud, original index) (uniform, reproducible, order preserved).
+// k-th smallest key per cloud = 8-pass radix select (256-bin histogram per pass), then one marking pass.
+__device__ __forceinline__ uint64_t sample_key(uint32_t seed, uint32_t cloud_id, uint32_t index) {
+    uint64_t z = (((uint64_t)seed << 40) ^ ((uint64_t)cloud_id << 32) ^ (uint64_t)index) + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_keepless_plan(DeviceArrays A, int n_pairs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairConst &pc = A.pc[p];
+    PairState &ps = A.ps[p];
+    for (int s = 0; s < kNumSegs; ++s) {
+        ps.kl_keep[s] = -1;
+        ps.kl_prefix[s] = 0;
+        ps.kl_rank[s] = 0;
+        for (int b = 0; b < 256; ++b) ps.kl_hist[s][b] = 0;
+    }
+    if (!pc.keep_less) return;
+    const int S = kNumClasses; // source segments follow the six target segments
+    auto plan = [&](int seg, int keep) { // random_downsample_pcl: untouched if size <= keep_number
+        if ((int)ps.seg_count[seg] > keep) {
+            ps.kl_keep[seg] = keep;
+            ps.kl_rank[seg] = (uint32_t)keep;
+        }
+        return ((int)ps.seg_count[seg] > keep) ? keep : (int)ps.seg_count[seg];
+    };
+    // order and rates of :2882-2890 (target_down_rate 2, ground_down_rate 4, facade_down_rate 2)
+    const int tg = plan(MULLS_GROUND, (int)(ps.seg_count[MULLS_GROUND] / 2));
+    const int tf = plan(MULLS_FACADE, (int)(ps.seg_count[MULLS_FACADE] / 2));
+    plan(S + MULLS_GROUND, tg / 4);
+    plan(S + MULLS_FACADE, tf / 2);
+    plan(S + MULLS_PILLAR, (int)ps.seg_count[MULLS_PILLAR]);
+    plan(S + MULLS_BEAM, (int)ps.seg_count[MULLS_BEAM]);
+    plan(S + MULLS_ROOF, (int)ps.seg_count[MULLS_ROOF]);
+    plan(S + MULLS_VERTEX, (int)ps.seg_count[MULLS_VERTEX]);
+}
+
+// pass = 0..7: histogram of byte `pass` (from the top) of the keys whose higher bytes equal the prefix found so far
+__global__ void __launch_bounds__(kIngestBlock) k_keepless_hist(DeviceArrays A, int pass) {
+    const ChunkDesc cd = A.in_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    PairState &ps = A.ps[cd.pair];
+    const uint32_t seg = cd.seg;
+    if (ps.kl_keep[seg] <= 0) return; // untouched, or cleared entirely
+    __shared__ uint32_t s_hist[256];
+    s_hist[threadIdx.x] = 0; // kIngestBlock == 256
+    __syncthreads();
+    const uint32_t local = cd.first + threadIdx.x;
+    if (local < pc.in_n[seg]) {
+        const size_t gi = (size_t)pc.in_off[seg] + local;
+        if (A.keys_a[gi] != ~0ull) {
+            const uint64_t key = sample_key(pc.random_seed, seg, local);
+            const int shift = 56 - 8 * pass;
+            const bool match = (pass == 0) || ((key >> (shift + 8)) == (ps.kl_prefix[seg] >> (shift + 8)));
+            if (match) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
+        }
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&ps.kl_hist[seg][threadIdx.x], s_hist[threadIdx.x]);
+}
+
+__global__ void k_keepless_step(DeviceArrays A, int n_pairs, int pass) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    PairState &ps = A.ps[p];
+    for (int s = 0; s < kNumSegs; ++s) {
+        if (ps.kl_keep[s] <= 0) continue;
+        uint32_t cum = 0, rank = ps.kl_rank[s];
+        int d = 0;
+        for (; d < 256; ++d) {
+            const uint32_t h = ps.kl_hist[s][d];
+            if (cum + h >= rank) break;
+            cum += h;
+        }
+        ps.kl_prefix[s] |= (uint64_t)d << (56 - 8 * pass);
+        ps.kl_rank[s] = rank - cum;
+        for (int b = 0; b < 256; ++b) ps.kl_hist[s][b] = 0;
+    }
+}
+
+// drop the points whose key exceeds the k-th smallest one (keys are a bijection of the index: exactly k remain)
+__global__ void __launch_bounds__(kIngestBlock) k_keepless_mark(DeviceArrays A) {
+    const ChunkDesc cd = A.in_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    PairState &ps = A.ps[cd.pair];
+    const uint32_t seg = cd.seg;
+    const int keep = ps.kl_keep[seg];
+    if (keep < 0) return;
+    const uint32_t local = cd.first + threadIdx.x;
+    bool drop = false;
+    if (local < pc.in_n[seg]) {
+        const size_t gi = (size_t)pc.in_off[seg] + local;
+        if (A.keys_a[gi] != ~0ull) {
+            drop = (keep == 0) || sample_key(pc.random_seed, seg, local) > ps.kl_prefix[seg];
+            if (drop) A.keys_a[gi] = ~0ull;
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, drop);
+    if ((threadIdx.x & 31) == 0 && b) atomicSub(&ps.seg_count[seg], (unsigned)__popc(b));
+}
+
 // ---- k_seg_offsets: single block; exclusive scan of the valid counts in (pair, seg) order gives the
 //      start of every segment in the sorted array; also per-class sizes and :1195-1201.
 __global__ void k_seg_offsets(DeviceArrays A, int n_pairs) {

@@ -39,6 +39,7 @@ struct mulls_ctx {
     size_t n_pairs = 0, n_in = 0, n_src_total = 0, n_tgt_total = 0;
     int max_iter_max = 0;
     bool uploaded = false;
+    bool any_keep_less = false;
     // tunables
     int start_level0 = 5;
     int leaf_count = 64;
@@ -323,10 +324,6 @@ static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const dou
         ctx->err = "normal_shooting_on is not implemented (SURVEY 8f rank 4)";
         return MULLS_E_UNSUPPORTED;
     }
-    if (P.keep_less_source_points) {
-        ctx->err = "keep_less_source_points is not implemented (time-seeded pcl::RandomSample upstream)";
-        return MULLS_E_UNSUPPORTED;
-    }
     if (P.max_iter_num > MULLS_MAX_TRACE_ITERS) {
         ctx->err = "max_iter_num > 64";
         return MULLS_E_ARG;
@@ -356,6 +353,9 @@ static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const dou
     pc.undistort = P.apply_motion_undistortion_while_registration ? 1 : 0;
     pc.apply_filter = (P.apply_intersection_filter && !pc.undistort) ? 1 : 0;
     if (pc.undistort) setup_undistortion(init, pc);
+    // :1191 keep_less_source_pts is skipped in the undistortion variant
+    pc.keep_less = (P.keep_less_source_points && !pc.undistort) ? 1 : 0;
+    pc.random_seed = P.random_seed;
     pc.cos_thre = std::cos(P.normal_bearing / 180.0 * M_PI);
     pc.sigma_thre = (double)P.sigma_thre;
     for (int i = 0; i < 16; ++i) pc.init[i] = init[i];
@@ -381,11 +381,13 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->h_it_chunks.clear();
     size_t in_off = 0, s_off = 0, t_off = 0;
     int max_iter_max = 0;
+    bool any_keep_less = false;
     for (size_t p = 0; p < n_pairs; ++p) {
         PairConst &pc = ctx->h_pc[p];
         int rc = build_pair_const(ctx, params[p], init_guess + 16 * p, pc);
         if (rc != MULLS_OK) return rc;
         max_iter_max = std::max(max_iter_max, pc.max_iter);
+        any_keep_less = any_keep_less || pc.keep_less;
         size_t ns = 0, nt = 0;
         for (int c = 0; c < kNumClasses; ++c) {
             nt += tgt[p * kNumClasses + c].n;
@@ -461,6 +463,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->n_src_total = s_off;
     ctx->n_tgt_total = t_off;
     ctx->max_iter_max = max_iter_max;
+    ctx->any_keep_less = any_keep_less;
     ctx->uploaded = true;
     return MULLS_OK;
 }
@@ -495,6 +498,16 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
     if (n_inc) {
         k_make_keys<<<n_inc, kIngestBlock, 0, st>>>(A);
         ++launches;
+        if (ctx->any_keep_less) { // random down-sampling of :2866-2892: radix select of the k-th sampling key
+            const unsigned pb = (unsigned)ceil_div(np, 64);
+            k_keepless_plan<<<pb, 64, 0, st>>>(A, np);
+            for (int pass = 0; pass < 8; ++pass) {
+                k_keepless_hist<<<n_inc, kIngestBlock, 0, st>>>(A, pass);
+                k_keepless_step<<<pb, 64, 0, st>>>(A, np, pass);
+            }
+            k_keepless_mark<<<n_inc, kIngestBlock, 0, st>>>(A);
+            launches += 18;
+        }
         int seg_bits = 1;
         while ((1ull << seg_bits) <= (uint64_t)np * kNumSegs) ++seg_bits;
         size_t bytes = ctx->cub_temp_bytes;

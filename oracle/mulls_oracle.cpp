@@ -338,15 +338,19 @@ static Bounds cloud_bbx(const Cloud &c) {
     }
     return b;
 }
-// cfilter.hpp:950-981 bbx_filter (keep strictly-inside points, order preserved)
-static void bbx_filter(Cloud &c, const Bounds &b) {
+// cfilter.hpp:950-981 bbx_filter (keep strictly-inside points, order preserved); `orig` follows the points
+static void bbx_filter(Cloud &c, const Bounds &b, std::vector<uint32_t> *orig = nullptr) {
     Cloud out;
+    std::vector<uint32_t> oo;
     out.reserve(c.size());
     for (size_t i = 0; i < c.size(); ++i)
         if (c[i].x > b.min_x && c[i].x < b.max_x && c[i].y > b.min_y && c[i].y < b.max_y &&
-            c[i].z > b.min_z && c[i].z < b.max_z)
+            c[i].z > b.min_z && c[i].z < b.max_z) {
             out.push_back(c[i]);
+            if (orig) oo.push_back((*orig)[i]);
+        }
     c.swap(out);
+    if (orig) orig->swap(oo);
 }
 
 // cregistration.hpp:2686-2692
@@ -704,6 +708,39 @@ static void motion_compensate(Cloud &c, const Mat4 &Tran) {
     }
 }
 
+// cfilter.hpp:606-628 random_downsample_pcl. The reference draws the subset with pcl::RandomSample seeded by
+// time(NULL) (not reproducible). Oracle and CUDA path both define it as: keep the `keep_number` points with the
+// smallest key splitmix64(seed, cloud id, original index) — a uniform sample, order preserved.
+static inline uint64_t sample_key(uint32_t seed, uint32_t cloud_id, uint32_t index) {
+    uint64_t z = (((uint64_t)seed << 40) ^ ((uint64_t)cloud_id << 32) ^ (uint64_t)index) + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+static void random_downsample(Cloud &c, const std::vector<uint32_t> &orig, std::vector<uint32_t> &orig_out, int keep_number,
+                              uint32_t seed, uint32_t cloud_id) {
+    orig_out = orig;
+    if ((long long)c.size() <= (long long)keep_number) return;
+    if (keep_number == 0) {
+        c.clear();
+        orig_out.clear();
+        return;
+    }
+    std::vector<uint64_t> keys(c.size());
+    for (size_t i = 0; i < c.size(); ++i) keys[i] = sample_key(seed, cloud_id, orig[i]);
+    std::vector<uint64_t> sorted = keys;
+    std::nth_element(sorted.begin(), sorted.begin() + (keep_number - 1), sorted.end());
+    const uint64_t thr = sorted[keep_number - 1];
+    Cloud out;
+    orig_out.clear();
+    for (size_t i = 0; i < c.size(); ++i)
+        if (keys[i] <= thr) {
+            out.push_back(c[i]);
+            orig_out.push_back(orig[i]);
+        }
+    c.swap(out);
+}
+
 struct Timers {
     double kd_build = 0, update = 0, search = 0, estimate = 0, total = 0;
 };
@@ -839,6 +876,13 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
         load_cloud(tgtv[c], tc[c]);
         load_cloud(srcv[c], sc[c]);
     }
+    std::vector<uint32_t> t_orig[6], s_orig[6]; // original index of every surviving point (sampling keys)
+    for (int c = 0; c < 6; ++c) {
+        t_orig[c].resize(tc[c].size());
+        s_orig[c].resize(sc[c].size());
+        for (size_t i = 0; i < tc[c].size(); ++i) t_orig[c][i] = (uint32_t)i;
+        for (size_t i = 0; i < sc[c].size(); ++i) s_orig[c][i] = (uint32_t)i;
+    }
     Cloud sc_orig[6]; // block2->pc_*_down as delivered (read again by the undistortion variant, :1251-1253)
     const bool undistort = P.apply_motion_undistortion_while_registration != 0;
     if (undistort)
@@ -868,8 +912,22 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
         ib.max_x = std::min(tb[3], m.max_x) + pad;
         ib.max_y = std::min(tb[4], m.max_y) + pad;
         ib.max_z = std::min(tb[5], m.max_z) + pad;
-        for (int c = 0; c < 6; ++c) bbx_filter(tc[c], ib);
-        for (int c = 0; c < 6; ++c) bbx_filter(sc[c], ib);
+        for (int c = 0; c < 6; ++c) bbx_filter(tc[c], ib, &t_orig[c]);
+        for (int c = 0; c < 6; ++c) bbx_filter(sc[c], ib, &s_orig[c]);
+    }
+
+    // :1191-1193, :2866-2892 keep_less_source_pts (ground_down_rate 4, facade_down_rate 2, target_down_rate 2)
+    if (P.keep_less_source_points && !P.apply_motion_undistortion_while_registration) {
+        std::vector<uint32_t> tmp;
+        const uint32_t sd = P.random_seed;
+        random_downsample(tc[G], t_orig[G], tmp, (int)(tc[G].size() / 2), sd, 0 + G);
+        random_downsample(tc[F], t_orig[F], tmp, (int)(tc[F].size() / 2), sd, 0 + F);
+        random_downsample(sc[G], s_orig[G], tmp, (int)(tc[G].size() / 4), sd, 6 + G);
+        random_downsample(sc[F], s_orig[F], tmp, (int)(tc[F].size() / 2), sd, 6 + F);
+        random_downsample(sc[PL], s_orig[PL], tmp, (int)(tc[PL].size()), sd, 6 + PL);
+        random_downsample(sc[B], s_orig[B], tmp, (int)(tc[B].size()), sd, 6 + B);
+        random_downsample(sc[R], s_orig[R], tmp, (int)(tc[R].size()), sd, 6 + R);
+        random_downsample(sc[V], s_orig[V], tmp, (int)(tc[V].size()), sd, 6 + V);
     }
 
     // :1195-1201

@@ -281,3 +281,23 @@ def test_4dof_global_heading_search(oracle_mod, small_pair):
     dt, dr = synth.pose_error(con.Trans1_2, best_r["T"])
     assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
     np.testing.assert_allclose(con.sigma, best_r["sigma"], rtol=1e-5)
+
+
+def test_keep_less_source_points(ctx, oracle_mod, small_pair):
+    """keep_less_source_pts (cregistration.hpp:2866-2892) with the reproducible sampling rule; also the
+    map-to-map call-site shape of test/mulls_slam.cpp:477-482 (3 iterations, wider thresholds)."""
+    for seed, iters in ((7, 20), (123456, 3)):
+        p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+        p.keep_less_source_points, p.use_more_points, p.random_seed, p.max_iter_num = 1, 1, seed, iters
+        g, gt, o, ot = run_both(ctx, oracle_mod, dict(small_pair, params=p))
+        assert_parity(g, gt, o, ot)
+        nt = [len(t) for t in small_pair["tgt"]]
+        assert gt["n_src"][0][abi.GROUND] <= nt[abi.GROUND] // 2 // 4  # source ground <= |target ground / 2| / 4
+    # different seeds pick different subsets
+    p1 = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p1.keep_less_source_points, p1.random_seed = 1, 1
+    p2 = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p2.keep_less_source_points, p2.random_seed = 1, 2
+    r1, _ = ctx.run_batch([dict(small_pair, params=p1)])
+    r2, _ = ctx.run_batch([dict(small_pair, params=p2)])
+    assert not np.array_equal(r1[0]["T"], r2[0]["T"])
