@@ -837,42 +837,40 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
 
 // ---- k_solve: one block per pair, after k_accumulate. Sums the per-chunk partials of every class in chunk
 //      order (fixed order => bit-reproducible), then one thread solves and advances the pair state.
-__global__ void __launch_bounds__(kIterBlock) k_solve(DeviceArrays A, int buf) {
+constexpr int kSolveThreads = kNumClasses * 32; // one warp per feature class
+__global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf) {
     const uint32_t pair = blockIdx.x;
     const PairConst &pc = A.pc[pair];
     PairState &ps = A.ps[pair];
     if (ps.status != kRunning) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kWarps = kIterBlock / 32;
+    const int lane = threadIdx.x & 31, cc = threadIdx.x >> 5; // warp = class
     __shared__ double s_S[kNumClasses][kTerms];
     __shared__ double s_scratch[160];
     __shared__ int s_newn[kNumClasses];
-    __shared__ uint32_t s_off[kWarps];
-    for (int cc = 0; cc < kNumClasses; ++cc) {
+    {
         const uint32_t b0 = pc.class_chunk_begin[cc];
         // only the chunks that held live sources this iteration wrote a partial
         const uint32_t live = (uint32_t)((ps.n_src[cc] + kIterBlock - 1) / kIterBlock);
         const uint32_t b1 = min(pc.class_chunk_begin[cc + 1], b0 + live);
-        const int term = threadIdx.x >> 2, sub = threadIdx.x & 3; // 4 threads per term, strided
-        double v = 0.0;
-        if (term < 27)
-            for (uint32_t b = b0 + sub; b < b1; b += 4) v += A.partials[(size_t)b * kTerms + term];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (term < 27 && sub == 0) s_S[cc][term] = v;
-        uint32_t acc = 0; // kept sources of the class = its new size
-        for (uint32_t b = b0 + threadIdx.x; b < b1; b += kIterBlock) acc += A.blk_kept[b];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        __syncthreads();
-        if (lane == 0) s_off[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
-            for (int w = 0; w < kWarps; ++w) tot += s_off[w];
-            s_newn[cc] = (int)tot;
+        // lane = term; chunks in order, four independent accumulators combined in a fixed order
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (lane < 27) {
+            uint32_t b = b0;
+            for (; b + 4 <= b1; b += 4) {
+                a0 += A.partials[(size_t)(b + 0) * kTerms + lane];
+                a1 += A.partials[(size_t)(b + 1) * kTerms + lane];
+                a2 += A.partials[(size_t)(b + 2) * kTerms + lane];
+                a3 += A.partials[(size_t)(b + 3) * kTerms + lane];
+            }
+            for (; b < b1; ++b) a0 += A.partials[(size_t)b * kTerms + lane];
         }
-        __syncthreads();
+        if (lane < kTerms) s_S[cc][lane] = (lane < 27) ? ((a0 + a1) + (a2 + a3)) : 0.0;
+        uint32_t acc = 0; // kept sources of the class = its new size
+        for (uint32_t b = b0 + lane; b < b1; b += 32) acc += A.blk_kept[b];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_newn[cc] = (int)acc;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         uint64_t srcpts = 0;
         for (int cc = 0; cc < kNumClasses; ++cc)

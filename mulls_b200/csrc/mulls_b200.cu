@@ -592,7 +592,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
                 launches += 2;
             }
             k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
-            k_solve<<<(unsigned)np, kIterBlock, 0, st>>>(A, buf);
+            k_solve<<<(unsigned)np, kSolveThreads, 0, st>>>(A, buf);
             if (hook) { // exchange 3: per-class normal-equation sums; then every rank solves the same system
                 if (hook(user, A.xch_f64, kNumClasses * kTerms, 0, 0, (void *)st) != 0) {
                     ctx->err = "all-reduce callback failed";

@@ -5,6 +5,7 @@
 * synth_small.npz  — seeded synthetic pair (mulls_b200.synth, seed 1000, config "small") and the
                      ORACLE's outputs on it (oracle/mulls_oracle.cpp). Inputs are stored too, so the
                      fixture does not depend on numpy's RNG stream staying stable.
+* demo_pair_reg.npz — real data, scans 000000 / 000003 with the run_mulls_reg.sh parameter set (see below).
 * demo_pair.npz    — real data: /root/reference/demo_data/pcd/000000.pcd (target) and 000001.pcd
                      (source), every 4th point, split into feature classes by the SemanticKITTI label
                      the files carry in `curvature` (ground 40/44/48/49/72, facade 50/51/52,
@@ -109,5 +110,16 @@ if __name__ == "__main__":
         pair = {"tgt": [abi.as_aos48(t) for t in tgt], "src": [abi.as_aos48(s) for s in src], "params": p,
                 "init_guess": np.eye(4)}
         save(os.path.join(HERE, "demo_pair.npz"), pair)
+        # the run_mulls_reg.sh parameter set (script/run_mulls_reg.sh:12-46: corr_dis_thre 3.0, 10 iterations, weights
+        # "1101", bearing 45) on scans three frames apart, identity initial guess (no TEASER here)
+        src3 = demo_cloud(os.path.join(ref, "000003.pcd"))
+        q = abi.default_params()
+        q.max_iter_num, q.dis_thre_unit, q.dis_thre_min = 10, 3.0, 0.75
+        q.converge_translation, q.converge_rotation_d = 0.001, 0.01
+        q.used_feature_type = b"111000"
+        q.target_bound[:] = synth.cloud_bound(tgt)
+        pair = {"tgt": [abi.as_aos48(t) for t in tgt], "src": [abi.as_aos48(s) for s in src3], "params": q,
+                "init_guess": np.eye(4)}
+        save(os.path.join(HERE, "demo_pair_reg.npz"), pair)
     else:
         print("reference demo_data not present: demo_pair.npz left as committed")

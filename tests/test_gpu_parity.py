@@ -59,7 +59,7 @@ def test_small_pair(ctx, oracle_mod, small_pair):
     assert_parity(*run_both(ctx, oracle_mod, small_pair))
 
 
-@pytest.mark.parametrize("name", ["synth_small.npz", "demo_pair.npz"])
+@pytest.mark.parametrize("name", ["synth_small.npz", "demo_pair.npz", "demo_pair_reg.npz"])
 def test_golden_fixtures(ctx, golden_dir, name):
     """Against the committed golden outputs (no oracle call: the fixture is the expectation)."""
     pair, exp = load_golden_pair(os.path.join(golden_dir, name))

@@ -46,7 +46,7 @@ def test_invariants(oracle_mod, small_pair):
     assert res["sigma"] > 0 and 0 < res["confidence"] <= 1.0
 
 
-@pytest.mark.parametrize("name", ["synth_small.npz", "demo_pair.npz"])
+@pytest.mark.parametrize("name", ["synth_small.npz", "demo_pair.npz", "demo_pair_reg.npz"])
 def test_golden_regression(oracle_mod, golden_dir, name):
     """The oracle as committed reproduces the committed golden fixtures bit-for-bit in the integer
     outputs and to 1e-12 in the floating-point ones (same machine arithmetic, -ffp-contract=off)."""
