@@ -26,6 +26,7 @@ struct GridView {
     float ox, oy, oz, h0, inv_h0;
     int n_levels;
     int leaf_count; // cells with at most this many points are scanned, larger ones are descended
+    int defer_scan; // queue the leaves of a block and scan them together after its traversal
 };
 
 __device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t &start, uint32_t &count,
@@ -49,6 +50,25 @@ __device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t 
 __device__ __forceinline__ float axis_dist(float o, float H, int x, float p, float margin) {
     const float lo = o + (float)x * H - margin, hi = o + (float)(x + 1) * H + margin;
     return fmaxf(0.0f, fmaxf(lo - p, p - hi));
+}
+
+constexpr int kLeafQueue = 8;   // leaves of one block whose scan is deferred to the end of its traversal
+
+// examine the points [start, start+count) of a leaf: FLANN distance, total order (d2, original index)
+__device__ __forceinline__ void scan_leaf(const GridView &g, float px, float py, float pz, uint32_t start, uint32_t count,
+                                          float &best_d2, int &best_j) {
+    for (uint32_t jj = start; jj < start + count; ++jj) {
+        const float4 q = __ldg(&g.pos[jj]);
+        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
+        if (d2 < best_d2) {
+            best_d2 = d2;
+            best_j = (int)jj;
+        } else if (d2 == best_d2 && (int)jj != best_j) {
+            const int oj = __float_as_int(__ldg(&g.nrm[jj]).w);
+            const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
+            if (oj < ob) best_j = (int)jj;
+        }
+    }
 }
 
 constexpr int kStackDepth = 48; // DFS entries: at most 7 stay behind per descended level
@@ -79,6 +99,8 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
     const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
     uint32_t st_code[kStackDepth], st_meta[kStackDepth], st_z[kStackDepth];
     float st_d2[kStackDepth];
+    uint32_t q_start[kLeafQueue], q_count[kLeafQueue];
+    int nq = 0;
     int l = min(max(start_level, 1), L - 1);
     if (best_j < 0) {
         // No candidate yet (first iteration): walk greedily from p's own level-l cell down through the nearest
@@ -181,17 +203,12 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
                 uint32_t start, count, cmask;
                 if (!probe(g, cell_key(lv, code), start, count, cmask)) continue;
                 if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStackDepth) {
-                    for (uint32_t jj = start; jj < start + count; ++jj) {
-                        const float4 q = __ldg(&g.pos[jj]);
-                        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-                        if (d2 < best_d2) {
-                            best_d2 = d2;
-                            best_j = (int)jj;
-                        } else if (d2 == best_d2 && (int)jj != best_j) {
-                            const int oj = __float_as_int(__ldg(&g.nrm[jj]).w);
-                            const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
-                            if (oj < ob) best_j = (int)jj;
-                        }
+                    if (g.defer_scan && nq < kLeafQueue) { // scanned together with the block's other leaves
+                        q_start[nq] = start;
+                        q_count[nq] = count;
+                        ++nq;
+                    } else {
+                        scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
                     }
                 } else {
                     const int cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)st_z[sp];
@@ -207,23 +224,35 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
                     // octant of p relative to the cell centre: the child with zero (or least) distance
                     const int near_child = (ax[1] < ax[0] ? 1 : 0) | (ay[1] < ay[0] ? 2 : 0) | (az[1] < az[0] ? 4 : 0);
                     const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-#pragma unroll 1
-                    for (int c = 7; c >= 0; --c) {
-                        const int ch = c ^ near_child; // c = 0 -> nearest octant, pushed last (popped first)
-                        if (!((cmask >> ch) & 1u)) continue;
-                        const float d2c = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
-                        if (d2c > bound) continue;
+                    // children that exist and can still beat the bound, as a bit mask (no 8-trip loop) ...
+                    uint32_t pass = 0;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        if (ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2] <= bound) pass |= 1u << ch;
+                    pass &= cmask;
+                    // ... re-indexed by c = ch ^ near_child (bit permutation by conditional swaps), so that the
+                    // highest set bit is the farthest octant: pushed first, the nearest one last (popped first)
+                    if (near_child & 1) pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
+                    if (near_child & 2) pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
+                    if (near_child & 4) pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
+                    while (pass) {
+                        const int c = 31 - __clz((int)pass);
+                        pass ^= 1u << c;
+                        const int ch = c ^ near_child;
                         const uint64_t cc = (code << 3) | (uint64_t)ch;
                         st_code[sp] = (uint32_t)cc;
                         st_meta[sp] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) |
                                       ((uint32_t)(2 * cx + (ch & 1)) << 8) | ((uint32_t)(2 * cy + ((ch >> 1) & 1)) << 20);
                         st_z[sp] = (uint32_t)(2 * cz + (ch >> 2));
-                        st_d2[sp] = d2c;
+                        st_d2[sp] = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
                         ++sp;
                     }
                 }
             }
         }
+        // the queued leaves of this block: the lanes of a warp scan them at the same time
+        for (int qi = 0; qi < nq; ++qi) scan_leaf(g, px, py, pz, q_start[qi], q_count[qi], best_d2, best_j);
+        nq = 0;
         const float cover = 0.999f * 0.5f * H; // every target closer than this has been examined
         const float cover2 = cover * cover;
         if (best_d2 <= cover2) break;  // the best found is the global nearest
@@ -242,7 +271,7 @@ __device__ __forceinline__ int level_for_distance(const GridView &g, float d2) {
 }
 
 __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                      int budget) {
+                                                      int budget, int defer_scan) {
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
@@ -285,6 +314,8 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
     g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
     g.n_levels = ps.n_levels;
     g.leaf_count = leaf_count;
+    // deferring pays once the seeds are good (from the third iteration on: the big first corrections are applied)
+    g.defer_scan = (defer_scan == 2) ? (ps.iter >= 2) : defer_scan;
     // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
     const float max_distance_f = 2.5f * ps.thre;
     const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
