@@ -504,27 +504,35 @@ __global__ void __launch_bounds__(256) k_hash_build(DeviceArrays A, const uint64
 // of the pool in order; flags overflow instead of writing out of bounds.
 __global__ void k_hash_layout(DeviceArrays A, int n_pairs) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t used = 0;
-    bool overflow = false;
-    for (int p = 0; p < n_pairs; ++p) {
-        PairState &ps = A.ps[p];
-        for (int c = 0; c < kNumClasses; ++c) {
-            uint32_t cap = 16;
-            while (cap < 2u * ps.hash_entries[c]) cap <<= 1;
-            if (used + cap > A.hash_pool_entries) {
-                overflow = true;
-                cap = 16;
-                ps.hash_base[c] = 0;
-                ps.hash_mask[c] = 0; // degenerate, never searched: the run is reported as failed
-                continue;
+    // load factor <= 0.5 if the pool allows it, else <= 0.8 (longer probe chains, same results), else give up
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        uint64_t used = 0;
+        bool overflow = false;
+        for (int p = 0; p < n_pairs && !overflow; ++p) {
+            PairState &ps = A.ps[p];
+            for (int c = 0; c < kNumClasses; ++c) {
+                const uint64_t want = (attempt == 0) ? 2ull * ps.hash_entries[c] : (5ull * ps.hash_entries[c]) / 4 + 1;
+                uint32_t cap = 16;
+                while (cap < want) cap <<= 1;
+                if (used + cap > A.hash_pool_entries) {
+                    overflow = true;
+                    break;
+                }
+                ps.hash_base[c] = (uint32_t)used;
+                ps.hash_mask[c] = cap - 1;
+                used += cap;
             }
-            ps.hash_base[c] = (uint32_t)used;
-            ps.hash_mask[c] = cap - 1;
-            used += cap;
         }
+        A.hash_used[0] = overflow ? 0u : (uint32_t)used;
+        A.hash_used[1] = overflow ? 1u : 0u;
+        if (!overflow) return;
     }
-    A.hash_used[0] = (uint32_t)used;
-    A.hash_used[1] = overflow ? 1u : 0u;
+    // overflow: degenerate tables that are never searched (every kernel checks hash_used[1]); the run reports it
+    for (int p = 0; p < n_pairs; ++p)
+        for (int c = 0; c < kNumClasses; ++c) {
+            A.ps[p].hash_base[c] = 0;
+            A.ps[p].hash_mask[c] = 0;
+        }
 }
 
 __global__ void __launch_bounds__(256) k_hash_clear(DeviceArrays A) {

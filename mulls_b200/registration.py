@@ -94,6 +94,7 @@ class Context:
             raise RuntimeError(self.lib.mulls_last_error(None).decode())
         self.max_pairs = max_pairs
         self._keep = None
+        self._n = 0
 
     def close(self):
         if getattr(self, "handle", None):
@@ -142,9 +143,10 @@ class Context:
 
     def run_resident(self, want_trace: bool = False):
         n = self._n
-        res = (abi.IcpResult * n)()
-        tr = (abi.IcpTrace * n)() if want_trace else None
+        res = (abi.IcpResult * max(n, 1))()
+        tr = (abi.IcpTrace * max(n, 1))() if want_trace else None
         self._check(self.lib.mulls_batch_run_resident(self.handle, res, tr))
+        res, tr = res[:n], (tr[:n] if tr is not None else None)
         out = [abi.result_to_dict(r) for r in res]
         return (out, [abi.trace_to_dict(t) for t in tr]) if want_trace else (out, None)
 
