@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=16, help="scan pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=32, help="scan pairs per GPU per step")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--lanes", type=int, default=8, help="concurrent contexts (CUDA streams) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -236,13 +236,13 @@ def main():
     pipe = PipelinedContext(local_rank, lanes, (args.pairs + lanes - 1) // lanes, max_src, max_tgt)
 
     # ---- (A) device-resident, one stream: per-kernel attribution for the roofline ----------------
+    sampler = ClockSampler(local_rank)  # samples every 50 ms through all warm-up and timed regions below
+    sampler.start()
     ctx.upload(pairs)
     res = None
     for _ in range(args.warmup):
         res, _ = ctx.run_resident()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     dev_ms = 0.0
     search_ms = 0.0
     alg_bytes = 0
@@ -276,7 +276,6 @@ def main():
     barrier()
     wall_s = time.perf_counter() - t_wall
     lanes_s = ev0.elapsed_time(ev1) / 1e3
-    clocks = sampler.stop()
 
     # ---- (C) end to end through the C-ABI with host (pinned) buffers, same lanes ----------------------
     for _ in range(2):
@@ -287,6 +286,11 @@ def main():
         res_e2e = pipe.run_batch(pairs)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if len(sampler.lines) < 3:  # very short runs: keep the GPU under the same load until a few samples exist
+        t_fill = time.perf_counter()
+        while len(sampler.lines) < 3 and time.perf_counter() - t_fill < 2.0:
+            pipe.run_resident()
+    clocks = sampler.stop()
     h2d = sum(a.nbytes for p in pairs for side in ("tgt", "src") for a in p[side])
     from mulls_b200 import abi
     import ctypes
