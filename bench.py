@@ -269,21 +269,17 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
-        res_p = pipe.run_resident()
-        launches += sum(st["kernel_launches"] for st in pipe.stats())
+    res_p, launches = pipe.run_resident_steps(args.steps)  # every stream runs its K passes back to back
     ev1.record()
     barrier()
     wall_s = time.perf_counter() - t_wall
     lanes_s = ev0.elapsed_time(ev1) / 1e3
 
     # ---- (C) end to end through the C-ABI with host (pinned) buffers, same lanes ----------------------
-    for _ in range(2):
-        pipe.run_batch(pairs)
+    pipe.run_batch_steps(pairs, 2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res_e2e = pipe.run_batch(pairs)
+    res_e2e = pipe.run_batch_steps(pairs, args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if len(sampler.lines) < 3:  # very short runs: keep the GPU under the same load until a few samples exist

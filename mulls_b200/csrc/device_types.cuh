@@ -93,8 +93,6 @@ struct PairState {
     uint32_t hash_entries[kNumClasses]; // cells (all levels) of each target class
     uint32_t hash_base[kNumClasses];    // table of each class inside the hash pool
     uint32_t hash_mask[kNumClasses];    // capacity-1 (power of two, load factor <= 0.5)
-    uint32_t arrive_acc;               // block arrival counter of k_accumulate
-    uint32_t arrive_post;              // block arrival counter of k_posterior
     int bb_src[6];                     // ordered-int encoded bbox of source ground/pillar/facade
     int bb_tgt[6];                     // ordered-int encoded bbox of all target points
     uint64_t alg_bytes;                // 28*(N_s,active + N_t) summed over executed iterations
@@ -118,7 +116,6 @@ struct DeviceArrays {
     uint32_t *vals_a, *vals_b;
     float4 *tgt_pos, *tgt_nrm;       // target SoA, Morton-sorted inside each (pair,class) slice
     float4 *src_pos[2], *src_nrm[2]; // source SoA ping-pong
-    float *src_hint[2];              // previous NN distance^2 (search start-level hint)
     int *src_prevj[2];               // previous NN target (seeds the next search with a real candidate)
     int *nn_idx;                     // per source: matched target (index inside its class slice) or -1
     float *nn_d2;

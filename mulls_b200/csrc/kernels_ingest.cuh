@@ -392,7 +392,6 @@ __global__ void __launch_bounds__(256) k_gather(DeviceArrays A, const uint64_t *
         if (pc.sharded) n2.w = __int_as_float(__float_as_int(nrm.w) + (int)pc.src_index_base[seg - kNumClasses]);
         A.src_pos[0][d] = pos;
         A.src_nrm[0][d] = n2;
-        A.src_hint[0][d] = -1.0f;
         A.src_prevj[0][d] = -1;
     }
 }

@@ -640,7 +640,6 @@ __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *
     float ratio;
     const bool few = too_few(pc, ps, ps.n_corr, ratio);
     ps.confidence = ratio;
-    double *I4 = sm; // scratch
     if (few) {
         ps.code = -2;
         ps.status = kDone;
@@ -741,7 +740,6 @@ __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *
         return;
     }
     ps.iter = i + 1;
-    (void)I4;
 }
 
 // ---- k_accumulate ------------------------------------------------------------------------------
@@ -839,7 +837,6 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
         const uint32_t gd = pc.src_base[c] + dst_local;
         A.src_pos[buf ^ 1][gd] = p;
         A.src_nrm[buf ^ 1][gd] = n;
-        A.src_hint[buf ^ 1][gd] = (j >= 0) ? d2 : -1.0f;
         A.src_prevj[buf ^ 1][gd] = j;
         A.corr_j[gd] = pass ? j : -1;
         A.corr_w[gd] = w_store;
@@ -1167,7 +1164,6 @@ __global__ void k_state_init(DeviceArrays A, int n_pairs) {
     }
     for (int s = 0; s < kNumSegs; ++s) ps.seg_count[s] = ps.seg_start[s] = 0;
     for (int c = 0; c < kNumClasses; ++c) ps.hash_entries[c] = ps.n_corr[c] = 0;
-    ps.arrive_acc = ps.arrive_post = 0;
     ps.status = kRunning;
     if (p == 0) {
         *A.running = n_pairs;

@@ -47,7 +47,6 @@ struct mulls_ctx {
     int defer_scan = 2;    // queue the leaves of a block and scan them together: 0 off, 1 on, 2 from iteration 2 on
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     float h0_min = 0.125f;
-    int want_trace = 0;
     // timing
     cudaEvent_t ev_begin = nullptr, ev_ingest = nullptr, ev_iter = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_search; // 2 per iteration
@@ -183,7 +182,6 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     for (int b = 0; b < 2; ++b) {
         ALLOC(A.src_pos[b], cs);
         ALLOC(A.src_nrm[b], cs);
-        ALLOC(A.src_hint[b], cs);
         ALLOC(A.src_prevj[b], cs);
     }
     ALLOC(A.nn_idx, cs);

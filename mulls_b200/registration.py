@@ -250,6 +250,43 @@ class PipelinedContext:
             out += f.result()
         return out
 
+    def run_resident_steps(self, k: int):
+        """k passes over the resident batch; every lane runs its k passes back to back (no per-step barrier
+        between lanes). Returns (results of the last pass, per-lane summed kernel launches)."""
+
+        def work(c, p):
+            if not p:
+                return [], 0
+            launches, out = 0, []
+            for _ in range(k):
+                out = c.run_resident()[0]
+                launches += c.stats()["kernel_launches"]
+            return out, launches
+
+        futs = [self.pool.submit(work, c, p) for c, p in zip(self.lanes, self._slices)]
+        out, launches = [], 0
+        for f in futs:
+            o, n = f.result()
+            out += o
+            launches += n
+        return out, launches
+
+    def run_batch_steps(self, pairs, k: int):
+        """k end-to-end passes (host buffers -> results) over `pairs`, lanes free-running as above."""
+        parts = self._split(pairs)
+
+        def work(c, p):
+            out = []
+            for _ in range(k):
+                out = c.run_batch(p)[0] if p else []
+            return out
+
+        futs = [self.pool.submit(work, c, p) for c, p in zip(self.lanes, parts)]
+        out = []
+        for f in futs:
+            out += f.result()
+        return out
+
     def stats(self):
         return [c.stats() for c, p in zip(self.lanes, self._slices or [[]] * len(self.lanes)) if p]
 
