@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -53,6 +54,10 @@ struct mulls_ctx {
     mulls_run_stats stats{};
     std::vector<void *> allocs;
     std::string err;
+    // pipelined context (mulls_create_pipelined): the batch is split over independent lane contexts, each with
+    // its own stream and buffers, driven by one host thread each
+    std::vector<mulls_ctx *> lanes;
+    std::vector<size_t> lane_begin; // pair range of every lane for the resident batch
     // PCA scratch
     void *pca_buf = nullptr;
     size_t pca_buf_bytes = 0;
@@ -112,6 +117,8 @@ const char *mulls_last_error(const mulls_ctx *ctx) { return ctx ? ctx->err.c_str
 
 void mulls_destroy(mulls_ctx *ctx) {
     if (!ctx) return;
+    for (mulls_ctx *l : ctx->lanes) mulls_destroy(l);
+    ctx->lanes.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
@@ -244,8 +251,76 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     return ctx;
 }
 
+mulls_ctx *mulls_create_pipelined(int device, size_t max_pairs, size_t max_src_pts, size_t max_tgt_pts, int n_lanes) {
+    if (n_lanes <= 1) return mulls_create(device, max_pairs, max_src_pts, max_tgt_pts);
+    if ((size_t)n_lanes > max_pairs) n_lanes = (int)max_pairs;
+    mulls_ctx *ctx = new mulls_ctx();
+    ctx->device = device;
+    ctx->max_pairs = max_pairs;
+    ctx->max_src = max_src_pts;
+    ctx->max_tgt = max_tgt_pts;
+    const size_t per_lane = (max_pairs + n_lanes - 1) / n_lanes;
+    for (int l = 0; l < n_lanes; ++l) {
+        mulls_ctx *c = mulls_create(device, per_lane, max_src_pts, max_tgt_pts);
+        if (!c) { // g_create_error is set by the failed create
+            mulls_destroy(ctx);
+            return nullptr;
+        }
+        ctx->lanes.push_back(c);
+    }
+    return ctx;
+}
+
+} // extern "C"
+
+// Run fn(lane, first_pair, n_pairs_of_lane) on every lane of a pipelined context, one host thread per lane;
+// pairs are split into contiguous, near-equal ranges. Returns the first non-zero code.
+template <typename F>
+static int for_each_lane(mulls_ctx *ctx, size_t n_pairs, F fn) {
+    const size_t L = ctx->lanes.size();
+    std::vector<int> rc(L, MULLS_OK);
+    std::vector<std::thread> th;
+    ctx->lane_begin.assign(L + 1, 0);
+    for (size_t l = 0; l <= L; ++l) ctx->lane_begin[l] = (n_pairs * l) / L;
+    for (size_t l = 0; l < L; ++l) {
+        const size_t b = ctx->lane_begin[l], n = ctx->lane_begin[l + 1] - b;
+        if (n == 0) continue;
+        th.emplace_back([&, l, b, n]() { rc[l] = fn(ctx->lanes[l], b, n); });
+    }
+    for (auto &t : th) t.join();
+    for (size_t l = 0; l < L; ++l)
+        if (rc[l] != MULLS_OK) {
+            ctx->err = ctx->lanes[l]->err;
+            return rc[l];
+        }
+    return MULLS_OK;
+}
+
+static void merge_lane_stats(mulls_ctx *ctx) {
+    mulls_run_stats &S = ctx->stats;
+    S = mulls_run_stats();
+    for (size_t l = 0; l < ctx->lanes.size(); ++l) {
+        if (ctx->lane_begin.size() > l + 1 && ctx->lane_begin[l + 1] == ctx->lane_begin[l]) continue;
+        const mulls_run_stats &s = ctx->lanes[l]->stats;
+        S.kernel_launches += s.kernel_launches;
+        S.algorithmic_bytes += s.algorithmic_bytes;
+        S.iterations += s.iterations;
+        S.search_launches += s.search_launches;
+        S.ms_search += s.ms_search; // summed over concurrently running lanes: not a wall time
+        S.ms_ingest = std::max(S.ms_ingest, s.ms_ingest);
+        S.ms_iterate = std::max(S.ms_iterate, s.ms_iterate);
+        S.ms_total = std::max(S.ms_total, s.ms_total);
+    }
+}
+
+extern "C" {
+
 int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return MULLS_E_ARG;
+    for (mulls_ctx *l : ctx->lanes) {
+        const int rc = mulls_set_tunable(l, name, value);
+        if (rc != MULLS_OK) return rc;
+    }
     std::string n(name);
     if (n == "start_level") ctx->start_level0 = value;
     else if (n == "leaf_count") ctx->leaf_count = value;
@@ -661,16 +736,59 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
 
 int mulls_batch_upload(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
                        const mulls_icp_params *params, const double *init_guess) {
+    if (ctx && !ctx->lanes.empty()) {
+        if (!tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
+        if (n_pairs > ctx->max_pairs) {
+            ctx->err = "more pairs than the context was created for";
+            return MULLS_E_CAPACITY;
+        }
+        ctx->n_pairs = n_pairs;
+        const int rc = for_each_lane(ctx, n_pairs, [&](mulls_ctx *lane, size_t b, size_t n) {
+            return upload_impl(lane, n, tgt + b * kNumClasses, src + b * kNumClasses, params + b, init_guess + 16 * b, nullptr,
+                               nullptr);
+        });
+        ctx->uploaded = (rc == MULLS_OK);
+        return rc;
+    }
     return upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr);
 }
 
 int mulls_batch_run_resident(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace) {
+    if (ctx && !ctx->lanes.empty()) {
+        if (!ctx->uploaded) return MULLS_E_ARG;
+        const int rc = for_each_lane(ctx, ctx->n_pairs, [&](mulls_ctx *lane, size_t b, size_t) {
+            return run_impl(lane, out ? out + b : nullptr, trace ? trace + b : nullptr, nullptr, nullptr);
+        });
+        merge_lane_stats(ctx);
+        return rc;
+    }
     return run_impl(ctx, out, trace, nullptr, nullptr);
 }
 
 int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
                         const mulls_icp_params *params, const double *init_guess, mulls_icp_result *out,
                         mulls_icp_trace *trace) {
+    if (ctx && !ctx->lanes.empty()) {
+        // pipelined: every lane uploads and registers its slice on its own stream — while one slice is being
+        // registered the next one's clouds are already crossing PCIe
+        if (!tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
+        if (n_pairs > ctx->max_pairs) {
+            ctx->err = "more pairs than the context was created for";
+            return MULLS_E_CAPACITY;
+        }
+        ctx->n_pairs = n_pairs;
+        ctx->uploaded = false;
+        const int rc = for_each_lane(ctx, n_pairs, [&](mulls_ctx *lane, size_t b, size_t n) {
+            int r = upload_impl(lane, n, tgt + b * kNumClasses, src + b * kNumClasses, params + b, init_guess + 16 * b, nullptr,
+                                nullptr, /*resident=*/false);
+            if (r != MULLS_OK) return r;
+            r = run_impl(lane, out ? out + b : nullptr, trace ? trace + b : nullptr, nullptr, nullptr);
+            lane->uploaded = false;
+            return r;
+        });
+        merge_lane_stats(ctx);
+        return rc;
+    }
     int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
     rc = run_impl(ctx, out, trace, nullptr, nullptr);
@@ -690,6 +808,7 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
                           const mulls_icp_params *params, const double init_guess[16], mulls_allreduce_fn allreduce,
                           void *user, mulls_icp_result *out, mulls_icp_trace *trace) {
     if (!ctx || !allreduce) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
     int rc = upload_impl(ctx, 1, tgt, src_shard, params, init_guess, src_index_base, src_global_n, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
     rc = run_impl(ctx, out, trace, allreduce, user);
@@ -701,6 +820,7 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     if (!ctx || !out || !out->eigenvalues || !out->principal || !out->normal || !out->pt_num || stride < 1 ||
         !(radius > 0.f))
         return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
     // the cloud becomes the only target class of a one-pair batch: same filter-less ingest, same grid
     mulls_icp_params P;
     mulls_icp_default_params(&P);

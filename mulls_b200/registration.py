@@ -87,9 +87,15 @@ class Constraint:
 class Context:
     """Thin RAII wrapper of a mulls_ctx (one CUDA device, one stream)."""
 
-    def __init__(self, device: int = 0, max_pairs: int = 1, max_src_pts: int = 150000, max_tgt_pts: int = 150000):
+    def __init__(self, device: int = 0, max_pairs: int = 1, max_src_pts: int = 150000, max_tgt_pts: int = 150000,
+                 lanes: int = 1):
+        """lanes > 1: mulls_create_pipelined — batch calls are split over `lanes` native lanes (own stream, buffers
+        and host thread each) inside the library."""
         self.lib = abi.load_library()
-        self.handle = self.lib.mulls_create(device, max_pairs, max_src_pts, max_tgt_pts)
+        if lanes > 1:
+            self.handle = self.lib.mulls_create_pipelined(device, max_pairs, max_src_pts, max_tgt_pts, lanes)
+        else:
+            self.handle = self.lib.mulls_create(device, max_pairs, max_src_pts, max_tgt_pts)
         if not self.handle:
             raise RuntimeError(self.lib.mulls_last_error(None).decode())
         self.max_pairs = max_pairs

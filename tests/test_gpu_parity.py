@@ -301,3 +301,29 @@ def test_keep_less_source_points(ctx, oracle_mod, small_pair):
     r1, _ = ctx.run_batch([dict(small_pair, params=p1)])
     r2, _ = ctx.run_batch([dict(small_pair, params=p2)])
     assert not np.array_equal(r1[0]["T"], r2[0]["T"])
+
+
+def test_native_pipelined_context_equals_single_lane(small_pair):
+    """mulls_create_pipelined: the batch is split over native lanes (own stream + host thread each); results are
+    bit-identical to a one-lane context, for one-shot and resident runs, with fewer pairs than lanes too."""
+    from mulls_b200.registration import Context
+
+    pairs = [small_pair, synth.make_pair(1003, "small"), small_pair, synth.make_pair(1004, "small"), small_pair]
+    one = Context(0, 5, 100000, 100000)
+    ref, _ = one.run_batch(pairs)
+    pipe = Context(0, 5, 100000, 100000, lanes=3)
+    got, tr = pipe.run_batch(pairs, want_trace=True)
+    for a, b in zip(ref, got):
+        np.testing.assert_array_equal(a["T"], b["T"])
+        assert a["code"] == b["code"] and a["n_corr"] == b["n_corr"]
+    assert tr[4]["n_iter"] == got[4]["iters"]
+    pipe.upload(pairs)
+    again, _ = pipe.run_resident()
+    for a, b in zip(ref, again):
+        np.testing.assert_array_equal(a["T"], b["T"])
+    st = pipe.stats()
+    assert st["iterations"] == sum(r["iters"] for r in ref) and st["kernel_launches"] > 0
+    few, _ = pipe.run_batch(pairs[:2])  # fewer pairs than lanes
+    np.testing.assert_array_equal(few[1]["T"], ref[1]["T"])
+    one.close()
+    pipe.close()
