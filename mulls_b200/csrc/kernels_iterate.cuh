@@ -71,6 +71,146 @@ __device__ __forceinline__ void scan_leaf(const GridView &g, float px, float py,
     }
 }
 
+// No candidate yet (first iteration): walk greedily from p's own cell (first level, from `l` upwards, at which it
+// exists) down through the nearest existing child to a leaf and take its best point as the seed. A handful of
+// probes, and the exact search that follows has a tight bound from its first cell on instead of stacking every
+// sibling within the (large) search radius. Ties are settled by the exact search.
+__device__ __forceinline__ void greedy_seed(const GridView &g, float px, float py, float pz, int l, float &best_d2,
+                                            int &best_j) {
+    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
+    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
+    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
+    const int L = g.n_levels;
+    l = min(max(l, 1), L - 1);
+    for (int lr = l; lr < L && best_j < 0; ++lr) {
+        const int ncell = (1 << kCoordBits) >> lr;
+        int cx = c0x >> lr, cy = c0y >> lr, cz = c0z >> lr;
+        if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell)) break;
+        uint64_t code = morton36((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+        for (int lv = lr;; --lv) {
+            uint32_t start, count, cmask;
+            if (!probe(g, cell_key(lv, code), start, count, cmask)) break; // only possible at lv == lr
+            if (count <= (uint32_t)g.leaf_count || lv == 0) {
+                for (uint32_t jj = start; jj < start + count; ++jj) {
+                    const float4 q = __ldg(&g.pos[jj]);
+                    const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
+                    if (d2 < best_d2) {
+                        best_d2 = d2;
+                        best_j = (int)jj;
+                    }
+                }
+                break;
+            }
+            const float hl = g.h0 * (float)(1 << lv);
+            const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
+            const int oy = (py >= g.oy + ((float)cy + 0.5f) * hl) ? 1 : 0;
+            const int oz = (pz >= g.oz + ((float)cz + 0.5f) * hl) ? 1 : 0;
+            int ch = ox | (oy << 1) | (oz << 2);
+            if (!((cmask >> ch) & 1u)) ch = __ffs((int)cmask) - 1; // any existing child still yields a valid seed
+            if (ch < 0) break;
+            code = (code << 3) | (uint64_t)ch;
+            cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
+        }
+    }
+}
+
+// squared distance from p to the (slightly inflated) box of cell (x,y,z) at a level with cell size hl
+__device__ __forceinline__ float cell_dist2(const GridView &g, float px, float py, float pz, float hl, int x, int y,
+                                            int z, float margin) {
+    const float ax = axis_dist(g.ox, hl, x, px, margin), ay = axis_dist(g.oy, hl, y, py, margin),
+                az = axis_dist(g.oz, hl, z, pz, margin);
+    return ax * ax + ay * ay + az * az;
+}
+
+constexpr int kPacketStack = 96; // warp-shared DFS entries of the packet search (3 words each, in shared memory)
+
+// Packet search: the 32 queries of a warp (Morton-adjacent source points, each with a seed) are resolved by ONE
+// warp-uniform traversal. The warp walks the cells overlapping the union of the lanes' search balls; a cell is
+// visited if ANY lane can still improve inside it, its points are then tested by the lanes that need it. No lane
+// waits for another lane's traversal (the cause of the 11/32 thread efficiency of the per-thread search), at the
+// price of testing the union of the candidate sets. Exact for every lane: each lane sees a superset of the cells
+// its own ball overlaps. Returns false (nothing done) when the packet is too spread out for this to pay.
+__device__ __forceinline__ bool packet_search(const GridView &g, bool valid, float px, float py, float pz, float r2_prune,
+                                              float max_ext, float &best_d2, int &best_j, uint32_t *stk) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float margin = 1e-3f * g.h0;
+    const float bound0 = fminf(best_d2, r2_prune);
+    const float r = valid ? sqrtf(bound0) * 1.0001f + 2.0f * margin : 0.0f;
+    float lo[3] = {valid ? px - r : INFINITY, valid ? py - r : INFINITY, valid ? pz - r : INFINITY};
+    float hi[3] = {valid ? px + r : -INFINITY, valid ? py + r : -INFINITY, valid ? pz + r : -INFINITY};
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(full, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(full, hi[d], o));
+        }
+    if (!(hi[0] >= lo[0])) return true; // no valid lane
+    const float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+    if (!(ext <= max_ext)) return false; // spread-out packet (or an unseeded lane): per-thread search instead
+    // level whose cells are at least as wide as the union box: it overlaps at most 2 (3 with rounding) cells per axis
+    const int L = g.n_levels;
+    int l = 0;
+    while (l < L - 1 && g.h0 * (float)(1 << l) < ext) ++l;
+    const int ncell = (1 << kCoordBits) >> l;
+    int clo[3], chi[3];
+    {
+        const float o3[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            clo[d] = max(((int)floorf((lo[d] - o3[d]) * g.inv_h0)) >> l, 0);
+            chi[d] = min(((int)floorf((hi[d] - o3[d]) * g.inv_h0)) >> l, ncell - 1);
+        }
+    }
+    if ((chi[0] - clo[0] + 1) * (chi[1] - clo[1] + 1) * (chi[2] - clo[2] + 1) > 27) return false;
+    // warp-uniform DFS; the stack lives in shared memory, written by lane 0
+    int sp = 0;
+    for (int z = clo[2]; z <= chi[2]; ++z)
+        for (int y = clo[1]; y <= chi[1]; ++y)
+            for (int x = clo[0]; x <= chi[0]; ++x) {
+                if (lane == 0) {
+                    const uint64_t code = morton36((uint32_t)x, (uint32_t)y, (uint32_t)z);
+                    stk[3 * sp + 0] = (uint32_t)code;
+                    stk[3 * sp + 1] = (uint32_t)(code >> 32) | ((uint32_t)l << 4) | ((uint32_t)x << 8) | ((uint32_t)y << 20);
+                    stk[3 * sp + 2] = (uint32_t)z;
+                }
+                ++sp;
+            }
+    __syncwarp();
+    while (sp > 0) {
+        --sp;
+        const uint32_t w0 = stk[3 * sp + 0], meta = stk[3 * sp + 1], w2 = stk[3 * sp + 2];
+        __syncwarp(); // everyone has read the entry before lane 0 may overwrite the slot
+        const uint64_t code = (uint64_t)w0 | ((uint64_t)(meta & 0xf) << 32);
+        const int lv = (int)((meta >> 4) & 0xf), cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)w2;
+        const float hl = g.h0 * (float)(1 << lv);
+        const bool need = valid && cell_dist2(g, px, py, pz, hl, cx, cy, cz, margin) <= fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+        if (!__any_sync(full, need)) continue;
+        uint32_t start, count, cmask;
+        if (!probe(g, cell_key(lv, code), start, count, cmask)) continue; // uniform key: one broadcast load
+        if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kPacketStack) {
+            if (need) scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
+        } else {
+            if (lane == 0) {
+                int k = sp;
+                for (int ch = 0; ch < 8; ++ch)
+                    if ((cmask >> ch) & 1u) {
+                        const uint64_t cc = (code << 3) | (uint64_t)ch;
+                        stk[3 * k + 0] = (uint32_t)cc;
+                        stk[3 * k + 1] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) | ((uint32_t)(2 * cx + (ch & 1)) << 8) |
+                                         ((uint32_t)(2 * cy + ((ch >> 1) & 1)) << 20);
+                        stk[3 * k + 2] = (uint32_t)(2 * cz + (ch >> 2));
+                        ++k;
+                    }
+            }
+            sp += __popc(cmask & 0xffu);
+            __syncwarp();
+        }
+    }
+    return true;
+}
+
 constexpr int kStackDepth = 48; // DFS entries: at most 7 stay behind per descended level
 
 // Exact nearest target (index within the class slice) under the total order (d2, original index) among
@@ -102,46 +242,9 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
     uint32_t q_start[kLeafQueue], q_count[kLeafQueue];
     int nq = 0;
     int l = min(max(start_level, 1), L - 1);
-    if (best_j < 0) {
-        // No candidate yet (first iteration): walk greedily from p's own level-l cell down through the nearest
-        // existing child to a leaf and take its best point as the seed. Costs a handful of probes, and gives the
-        // exact search below a tight bound from its first cell on, so that it does not stack every sibling
-        // within the (large) search radius.
-        // root of the walk: the first level, from l upwards, at which p's own cell exists
-        for (int lr = l; lr < L && best_j < 0; ++lr) {
-            const int ncell = (1 << kCoordBits) >> lr;
-            int cx = c0x >> lr, cy = c0y >> lr, cz = c0z >> lr;
-            if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell)) break;
-            uint64_t code = morton36((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-            for (int lv = lr;; --lv) {
-                uint32_t start, count, cmask;
-                if (!probe(g, cell_key(lv, code), start, count, cmask)) break; // only possible at lv == lr
-                if (count <= (uint32_t)g.leaf_count || lv == 0) {
-                    for (uint32_t jj = start; jj < start + count; ++jj) {
-                        const float4 q = __ldg(&g.pos[jj]);
-                        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-                        if (d2 < best_d2) { // ties are settled by the exact search that follows
-                            best_d2 = d2;
-                            best_j = (int)jj;
-                        }
-                    }
-                    break;
-                }
-                const float hl = g.h0 * (float)(1 << lv);
-                const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
-                const int oy = (py >= g.oy + ((float)cy + 0.5f) * hl) ? 1 : 0;
-                const int oz = (pz >= g.oz + ((float)cz + 0.5f) * hl) ? 1 : 0;
-                int ch = ox | (oy << 1) | (oz << 2);
-                if (!((cmask >> ch) & 1u)) ch = __ffs((int)cmask) - 1; // any existing child still yields a valid seed
-                if (ch < 0) break;
-                code = (code << 3) | (uint64_t)ch;
-                cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
-            }
-        }
-        if (best_j >= 0) { // continue like a seeded search: the smallest level whose coverage reaches the seed
-            const float need = 1.001f * sqrtf(best_d2) / (0.999f * 0.5f * g.h0);
-            l = min(max((need <= 1.0f) ? 0 : (ilogbf(need) + 1), 1), L - 1);
-        }
+    if (best_j >= 0) { // seeded: the smallest level whose coverage 0.999 * h0 * 2^(l-1) reaches the seed
+        const float need = 1.001f * sqrtf(best_d2) / (0.999f * 0.5f * g.h0);
+        l = min(max((need <= 1.0f) ? 0 : (ilogbf(need) + 1), 1), L - 1);
     }
     for (;; ++l) {
         const float H = g.h0 * (float)(1 << l);
@@ -271,7 +374,7 @@ __device__ __forceinline__ int level_for_distance(const GridView &g, float d2) {
 }
 
 __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                      int budget, int defer_scan) {
+                                                      int budget, int defer_scan, float packet_max_ext) {
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
@@ -321,22 +424,29 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
     const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
     const float r2_prune = (float)max_dist_sqr * 1.0001f;
 
-    // pass 1: every thread searches for its own source point, with a bounded number of cell visits
+    // seeds: the previous iteration's match (a real candidate, so the box-distance pruning bites from the first
+    // cell on and the search only has to prove that nothing is closer), else a greedy descent
     int best_j = -1;
     float best_d2 = INFINITY;
-    bool finished = true;
     if (valid) {
-        int sl = start_level0;
-        // Seed with the previous iteration's match: a real candidate, so the box-distance pruning bites from
-        // the first cell on; the search then only has to prove that nothing is closer (still exact).
         const int pj = A.src_prevj[buf][gi];
         if (pj >= 0) {
             const float4 q = __ldg(&g.pos[pj]);
             best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
             best_j = pj;
-            sl = level_for_distance(g, best_d2);
+        } else {
+            greedy_seed(g, p.x, p.y, p.z, start_level0, best_d2, best_j);
         }
-        finished = nn_search(g, p.x, p.y, p.z, r2_prune, sl, best_d2, best_j, budget);
+    }
+    // packet search: one warp-uniform traversal for the 32 queries of the warp, when they are close together
+    __shared__ uint32_t s_pstack[kIterBlock / 32][3 * kPacketStack];
+    bool finished = false;
+    if (packet_max_ext > 0.0f)
+        finished = packet_search(g, valid, p.x, p.y, p.z, r2_prune, packet_max_ext, best_d2, best_j, s_pstack[threadIdx.x >> 5]);
+    // per-thread search (pass 1, optionally with a bounded number of cell visits)
+    if (!finished) {
+        finished = true;
+        if (valid) finished = nn_search(g, p.x, p.y, p.z, r2_prune, start_level0, best_d2, best_j, budget);
     }
     // pass 2: the unfinished (expensive) queries of the block are regrouped into the first threads and
     // finished there, seeded with what pass 1 found — warps of similar cost instead of 31 idle lanes

@@ -46,6 +46,7 @@ struct mulls_ctx {
     int leaf_count = 32;
     int search_budget = 0; // cell visits of the first search pass (0 = unbounded, single pass)
     int defer_scan = 2;    // queue the leaves of a block and scan them together: 0 off, 1 on, 2 from iteration 2 on
+    int packet_max_ext_mm = 0; // packet search for warps whose union search box is at most this wide (0 = off)
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     float h0_min = 0.125f;
     // timing
@@ -327,6 +328,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "search_budget") ctx->search_budget = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "defer_scan") ctx->defer_scan = value;
+    else if (n == "packet_max_ext_mm") ctx->packet_max_ext_mm = value;
     else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
     else return MULLS_E_ARG;
     return MULLS_OK;
@@ -648,7 +650,8 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->search_budget, ctx->defer_scan);
+            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->search_budget, ctx->defer_scan,
+                                                         (float)ctx->packet_max_ext_mm / 1000.0f);
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
             if (hook) { // exchange 1: the duplicate-check claims of all shards (min of source indices)
                 if (hook(user, A.claim, ctx->n_tgt_total, 1, 1, (void *)st) != 0) {

@@ -11,7 +11,7 @@ ms = max(sum(len(s) for s in p["src"]) for p in pairs); mt = max(sum(len(t) for 
 ctx = Context(0, P, ms, mt)
 ctx.upload(pairs)
 ref = None
-settings = [dict(defer_scan=d, leaf_count=l, start_level=5) for d in (0, 1) for l in (32, 64, 128)]
+settings = [dict(packet_max_ext_mm=e, leaf_count=l) for l in (32, 16) for e in (0, 500, 1000, 2000, 4000)]
 
 for st in settings:
     for k, v in st.items(): ctx.set_tunable(k, v)
