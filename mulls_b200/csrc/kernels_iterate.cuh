@@ -1,13 +1,15 @@
-// Iteration phase: one pass of the loop body of mm_lls_icp (cregistration.hpp:1239-1401) as three
-// kernels over (pair, class, 128-source chunk) work items:
-//   k_search      I1+I2a  apply the previous increment to the source (:1260), exact radius-bounded
-//                         1-NN on the hashed grid (replaces the kd-tree query of :1745), claim the target
-//   k_resolve     I2b     duplicate check (:1755-1792), distance rejector (:1794-1796), normal check
-//                         (:1798-1830), per-class correspondence counts
-//   k_accumulate  I3-I9   order-preserving source compaction (:1776-1789), 21+6 normal-equation terms
-//                         per correspondence (:1976-2275), deterministic block->pair reduction; the last
-//                         block of a pair solves the 6x6 system and advances the pair state (:1301-1400)
-//   k_posterior   I8      residuals of the converged iteration (:2518-2677), sigma, information matrix
+// Iteration phase: one pass of the loop body of mm_lls_icp (cregistration.hpp:1239-1401) as four kernels; the first
+// three run over (pair, class, 128-source chunk) work items, the fourth over pairs:
+//   k_search      I1+I2a  apply the previous increment to the source (:1260), exact radius-bounded 1-NN on the hashed
+//                         multi-level grid (replaces the kd-tree query of :1745), claim the target
+//   k_resolve     I2b     duplicate check (:1755-1792), distance rejector (:1794-1796), normal check (:1798-1830),
+//                         per-class correspondence counts
+//   k_accumulate  I3-I5   order-preserving source compaction (:1776-1789), 21+6 normal-equation terms per
+//                         correspondence (:1976-2275), fixed-order block reduction -> one partial per chunk
+//   k_solve       I5-I9   per pair: partials summed in chunk order, 6x6 solve, Euler/Jacobian, convergence and
+//                         status logic (:1301-1400) — the iteration driver lives on the device
+// After the loop: k_posterior + k_finalize (:2518-2677, :1386). Source-sharded registrations (k_shard_*) insert the
+// caller's all-reduce between these phases.
 #pragma once
 #include "device_math.cuh"
 #include "device_types.cuh"
