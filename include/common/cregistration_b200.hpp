@@ -11,8 +11,7 @@
 // unchanged. Needs PCL + Eigen (for the types only) and -lmulls_b200.
 //
 // Contract differences: block1->tree_* are not populated; options
-// normal_shooting_on is rejected (LOG + return 0 with the constraint untouched); keep_less_source_points uses a
-// reproducible uniform sample instead of the reference's time-seeded pcl::RandomSample.
+// keep_less_source_points uses a reproducible uniform sample instead of the reference's time-seeded pcl::RandomSample.
 #ifndef MULLS_B200_CREGISTRATION_SHIM_HPP
 #define MULLS_B200_CREGISTRATION_SHIM_HPP
 

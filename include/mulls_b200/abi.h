@@ -89,7 +89,7 @@ typedef struct mulls_icp_params {
     float pt2li_residual_window;
     int32_t apply_intersection_filter;
     int32_t apply_motion_undistortion_while_registration; /* sources carry the timestamp ratio in `curvature` */
-    int32_t normal_shooting_on;                           /* must be 0 (MULLS_E_UNSUPPORTED) */
+    int32_t normal_shooting_on;                           /* k = 10 normal-shooting candidates for ground/facade/roof */
     float normal_bearing;
     int32_t use_more_points; /* informational: the caller already chose pc_* vs pc_*_down */
     int32_t keep_less_source_points; /* random down-sampling of :2866-2892, deterministic in random_seed */

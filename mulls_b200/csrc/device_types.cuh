@@ -44,6 +44,7 @@ struct PairConst {
     double ud_q[4];  // quaternion (x y z w) of the inverse initial guess
     double ud_t[3];  // its translation
     double ud_theta, ud_sin_theta;
+    int normal_shooting;    // normal_shooting_on: k = 10 candidates for ground / facade / roof (:1730-1739)
     int keep_less;          // keep_less_source_pts (cregistration.hpp:1191-1193, :2866-2892)
     uint32_t random_seed;
     double cos_thre;            // cos(normal_bearing/180*pi), :1818

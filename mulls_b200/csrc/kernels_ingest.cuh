@@ -149,6 +149,9 @@ __global__ void k_pair_setup(DeviceArrays A, int n_pairs, float h0_min) {
     const float rmax = 2.5f * pc.thre_unit * 1.0001f;
     int L = 2; // level l's 2x2x2 block covers 0.999 * h0 * 2^(l-1) (see nn_search)
     while (L < kMaxLevels && 0.999f * 0.5f * h0 * (float)(1 << (L - 1)) < rmax) ++L;
+    // normal shooting needs the exact 10 nearest targets with no distance bound: full pyramid, whose top 2x2x2
+    // block (2 x 2048 level-0 cells per axis) spans the whole grid
+    if (pc.normal_shooting) L = kMaxLevels;
     ps.n_levels = L;
 
     for (int i = 0; i < 16; ++i) {

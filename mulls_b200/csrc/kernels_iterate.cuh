@@ -367,6 +367,109 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// exact k nearest targets (k = 10) for the normal-shooting correspondences of :1732-1737
+// (pcl::registration::CorrespondenceEstimationNormalShooting): same hierarchy as nn_search, the pruning bound is
+// the current k-th best distance and there is no search radius — the level pyramid of a pair that uses normal
+// shooting goes up to a block that spans the whole grid, so the result is exact however far the targets are.
+// Total order (d2, original index), as the oracle's kd-tree.
+// ------------------------------------------------------------------------------------------------
+constexpr int kShootK = 10;
+
+struct KnnList {
+    float d2[kShootK];
+    int j[kShootK];
+    int n;
+};
+__device__ __forceinline__ float knn_bound(const KnnList &kl) { return kl.n < kShootK ? INFINITY : kl.d2[kShootK - 1]; }
+
+__device__ __forceinline__ void knn_insert(const GridView &g, KnnList &kl, float d2, int j) {
+    if (kl.n == kShootK) {
+        const float w = kl.d2[kShootK - 1];
+        if (d2 > w) return;
+        if (d2 == w && __float_as_int(__ldg(&g.nrm[j]).w) >= __float_as_int(__ldg(&g.nrm[kl.j[kShootK - 1]]).w)) return;
+    }
+    for (int i = 0; i < kl.n; ++i)
+        if (kl.j[i] == j) return; // a point is met again when the search ascends a level
+    int pos = (kl.n < kShootK) ? kl.n : kShootK - 1;
+    while (pos > 0) {
+        const float dp = kl.d2[pos - 1];
+        bool before = d2 < dp;
+        if (d2 == dp) before = __float_as_int(__ldg(&g.nrm[j]).w) < __float_as_int(__ldg(&g.nrm[kl.j[pos - 1]]).w);
+        if (!before) break;
+        kl.d2[pos] = kl.d2[pos - 1];
+        kl.j[pos] = kl.j[pos - 1];
+        --pos;
+    }
+    kl.d2[pos] = d2;
+    kl.j[pos] = j;
+    if (kl.n < kShootK) ++kl.n;
+}
+
+__device__ __forceinline__ void knn_search(const GridView &g, float px, float py, float pz, int start_level, KnnList &kl) {
+    kl.n = 0;
+    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
+    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
+    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
+    const int L = g.n_levels;
+    const float margin = 1e-3f * g.h0;
+    uint32_t st_code[kStackDepth], st_meta[kStackDepth], st_z[kStackDepth];
+    float st_d2[kStackDepth];
+    for (int l = min(max(start_level, 1), L - 1);; ++l) {
+        const float H = g.h0 * (float)(1 << l);
+        const int ncell = (1 << kCoordBits) >> l;
+        for (int k = 0; k < 8; ++k) { // own cell first, then the half-side neighbours
+            int x = (c0x >> l) + ((k & 1) ? ((((c0x >> (l - 1)) & 1) ? 1 : -1)) : 0);
+            int y = (c0y >> l) + ((k & 2) ? ((((c0y >> (l - 1)) & 1) ? 1 : -1)) : 0);
+            int z = (c0z >> l) + ((k & 4) ? ((((c0z >> (l - 1)) & 1) ? 1 : -1)) : 0);
+            if (ncell == 2) x = k & 1, y = (k >> 1) & 1, z = k >> 2; // top of the full pyramid: the 8 cells ARE the grid
+            if (x < 0 || y < 0 || z < 0 || x >= ncell || y >= ncell || z >= ncell) continue;
+            int sp = 0;
+            {
+                const uint64_t code = morton36((uint32_t)x, (uint32_t)y, (uint32_t)z);
+                st_code[0] = (uint32_t)code;
+                st_meta[0] = (uint32_t)(code >> 32) | ((uint32_t)l << 4) | ((uint32_t)x << 8) | ((uint32_t)y << 20);
+                st_z[0] = (uint32_t)z;
+                st_d2[0] = cell_dist2(g, px, py, pz, H, x, y, z, margin);
+                sp = 1;
+            }
+            while (sp > 0) {
+                --sp;
+                if (st_d2[sp] > knn_bound(kl) * 1.0001f + 1e-12f) continue;
+                const uint32_t meta = st_meta[sp];
+                const uint64_t code = (uint64_t)st_code[sp] | ((uint64_t)(meta & 0xf) << 32);
+                const int lv = (int)((meta >> 4) & 0xf);
+                uint32_t start, count, cmask;
+                if (!probe(g, cell_key(lv, code), start, count, cmask)) continue;
+                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStackDepth) {
+                    for (uint32_t jj = start; jj < start + count; ++jj) {
+                        const float4 q = __ldg(&g.pos[jj]);
+                        knn_insert(g, kl, flann_l2(px, py, pz, q.x, q.y, q.z), (int)jj);
+                    }
+                } else {
+                    const int cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)st_z[sp];
+                    const float hc = 0.5f * g.h0 * (float)(1 << lv);
+                    for (int ch = 7; ch >= 0; --ch) {
+                        if (!((cmask >> ch) & 1u)) continue;
+                        const int x2 = 2 * cx + (ch & 1), y2 = 2 * cy + ((ch >> 1) & 1), z2 = 2 * cz + (ch >> 2);
+                        const float d2c = cell_dist2(g, px, py, pz, hc, x2, y2, z2, margin);
+                        if (d2c > knn_bound(kl) * 1.0001f + 1e-12f) continue;
+                        const uint64_t cc = (code << 3) | (uint64_t)ch;
+                        st_code[sp] = (uint32_t)cc;
+                        st_meta[sp] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) | ((uint32_t)x2 << 8) | ((uint32_t)y2 << 20);
+                        st_z[sp] = (uint32_t)z2;
+                        st_d2[sp] = d2c;
+                        ++sp;
+                    }
+                }
+            }
+        }
+        const float cover = 0.999f * 0.5f * H; // every target closer than this has been examined
+        if (kl.n == kShootK && kl.d2[kShootK - 1] <= cover * cover) break;
+        if (l == L - 1) break; // the top block spans the whole grid: everything has been examined
+    }
+}
+
 // ---- k_search ----------------------------------------------------------------------------------
 // start level for a search seeded with a candidate at squared distance d2: the smallest level whose
 // guaranteed coverage 0.999 * h0 * 2^(l-1) reaches that distance
@@ -426,6 +529,35 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
     const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
     const float r2_prune = (float)max_dist_sqr * 1.0001f;
 
+    if (pc.normal_shooting && (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF)) { // block-uniform
+        // :1732-1737 normal shooting [PCL CorrespondenceEstimationNormalShooting, k = 10]: among the 10 nearest targets
+        // the one with the smallest squared distance to the line through the source point along its normal; dropped
+        // if that value exceeds max_distance (NOT squared); correspondence distance = its squared NN distance.
+        int sj = -1;
+        float sd2 = INFINITY;
+        if (valid) {
+            KnnList kl;
+            knn_search(g, p.x, p.y, p.z, start_level0, kl);
+            double min_dist = 1.7976931348623157e308;
+            for (int t = 0; t < kl.n; ++t) {
+                const float4 q = __ldg(&g.pos[kl.j[t]]);
+                const float ptx = q.x - p.x, pty = q.y - p.y, ptz = q.z - p.z;
+                const double Nx = n.x, Ny = n.y, Nz = n.z, Vx = ptx, Vy = pty, Vz = ptz;
+                const double Cx = Ny * Vz - Nz * Vy, Cy = Nz * Vx - Nx * Vz, Cz = Nx * Vy - Ny * Vx;
+                const double dist = Cx * Cx + (Cy * Cy + Cz * Cz);
+                if (dist < min_dist) {
+                    min_dist = dist;
+                    sj = kl.j[t];
+                    sd2 = kl.d2[t];
+                }
+            }
+            if (sj >= 0 && min_dist > (double)max_distance_f) sj = -1;
+            if (sj >= 0) atomicMin(&A.claim[pc.tgt_base[c] + sj], (unsigned)__float_as_int(n.w));
+            A.nn_idx[gi] = sj;
+            A.nn_d2[gi] = sd2;
+        }
+        return;
+    }
     // seeds: the previous iteration's match (a real candidate, so the box-distance pruning bites from the first
     // cell on and the search only has to prove that nothing is closer), else a greedy descent
     int best_j = -1;

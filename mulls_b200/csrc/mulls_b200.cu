@@ -397,10 +397,6 @@ static void setup_undistortion(const double *m, PairConst &pc) {
 
 // ------------------------------------------------------------------------------------------------
 static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const double *init, PairConst &pc) {
-    if (P.normal_shooting_on) {
-        ctx->err = "normal_shooting_on is not implemented (SURVEY 8f rank 4)";
-        return MULLS_E_UNSUPPORTED;
-    }
     if (P.max_iter_num > MULLS_MAX_TRACE_ITERS) {
         ctx->err = "max_iter_num > 64";
         return MULLS_E_ARG;
@@ -433,6 +429,7 @@ static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const dou
     // :1191 keep_less_source_pts is skipped in the undistortion variant
     pc.keep_less = (P.keep_less_source_points && !pc.undistort) ? 1 : 0;
     pc.random_seed = P.random_seed;
+    pc.normal_shooting = P.normal_shooting_on ? 1 : 0;
     pc.cos_thre = std::cos(P.normal_bearing / 180.0 * M_PI);
     pc.sigma_thre = (double)P.sigma_thre;
     for (int i = 0; i < 16; ++i) pc.init[i] = init[i];

@@ -185,6 +185,71 @@ struct KdTree {
         dists[nd.dim] = saved;
     }
 
+    // exact k nearest neighbours under the total order (d2, index), ascending; FLANN's nearestKSearch [3P]
+    struct KBest {
+        int k, n;
+        float d2[16];
+        int idx[16];
+        float worst() const { return n < k ? std::numeric_limits<float>::infinity() : d2[n - 1]; }
+        void insert(float d, int i) {
+            if (n == k && !(d < d2[n - 1] || (d == d2[n - 1] && i < idx[n - 1]))) return;
+            int pos = (n < k) ? n : n - 1;
+            while (pos > 0 && (d < d2[pos - 1] || (d == d2[pos - 1] && i < idx[pos - 1]))) {
+                d2[pos] = d2[pos - 1];
+                idx[pos] = idx[pos - 1];
+                --pos;
+            }
+            d2[pos] = d;
+            idx[pos] = i;
+            if (n < k) ++n;
+        }
+    };
+    void search_k_rec(int node, const float q[3], float mindist, float dists[3], KBest &best) const {
+        const KdNode &nd = nodes[node];
+        if (nd.dim < 0) {
+            for (int k = nd.left; k < nd.right; ++k) best.insert(flann_l2(q, (*pts)[idx[k]]), idx[k]);
+            return;
+        }
+        float val = q[nd.dim];
+        float diff1 = val - nd.lo, diff2 = val - nd.hi;
+        int first, second;
+        float cut;
+        if (diff1 + diff2 < 0) {
+            first = nd.left;
+            second = nd.right;
+            cut = diff2 * diff2;
+        } else {
+            first = nd.right;
+            second = nd.left;
+            cut = diff1 * diff1;
+        }
+        search_k_rec(first, q, mindist, dists, best);
+        float saved = dists[nd.dim];
+        float md = mindist + cut - saved;
+        dists[nd.dim] = cut;
+        if (md * 0.99999f <= best.worst()) search_k_rec(second, q, md, dists, best);
+        dists[nd.dim] = saved;
+    }
+    int nearest_k(const float q[3], int k, int *index, float *d2) const {
+        if (idx.empty()) return 0;
+        float dists[3] = {0, 0, 0};
+        float mind = 0;
+        for (int d = 0; d < 3; ++d) {
+            if (q[d] < bmin[d]) dists[d] = (q[d] - bmin[d]) * (q[d] - bmin[d]);
+            if (q[d] > bmax[d]) dists[d] = (q[d] - bmax[d]) * (q[d] - bmax[d]);
+            mind += dists[d];
+        }
+        KBest best;
+        best.k = std::min(k, 16);
+        best.n = 0;
+        search_k_rec(0, q, mind, dists, best);
+        for (int i = 0; i < best.n; ++i) {
+            index[i] = best.idx[i];
+            d2[i] = best.d2[i];
+        }
+        return best.n;
+    }
+
     // exact nearest neighbour; returns false on an empty tree
     bool nearest(const float q[3], int &index, float &d2) const {
         if (idx.empty()) return false;
@@ -747,7 +812,7 @@ struct Timers {
 
 // cregistration.hpp:1701-1835 determine_corres (nearest-neighbour branch)
 static bool determine_corres(Cloud &S, const Cloud &T, const KdTree &tree, float dis_thre, Corrs &Corr_f,
-                             bool normal_check, float angle_thre_degree, int nn_threads) {
+                             bool normal_check, float angle_thre_degree, int nn_threads, bool normal_shooting = false) {
     const int K_min = 3;
     const float filter_dis_times = 2.5f;
     const int K_filter_distant_point = 500;
@@ -759,22 +824,61 @@ static bool determine_corres(Cloud &S, const Cloud &T, const KdTree &tree, float
     const int ns = (int)S.size();
     std::vector<int> nn_i(ns);
     std::vector<float> nn_d(ns);
-#pragma omp parallel for schedule(dynamic, 256) num_threads(nn_threads) if (nn_threads > 1)
-    for (int i = 0; i < ns; ++i) {
-        float q[3] = {S[i].x, S[i].y, S[i].z};
-        int j = -1;
-        float d2 = 0;
-        tree.nearest(q, j, d2);
-        nn_i[i] = j;
-        nn_d[i] = d2;
-    }
     Corrs Cc;
     Cc.reserve(ns);
-    for (int i = 0; i < ns; ++i) {
-        if (nn_i[i] < 0) continue;
-        if (nn_d[i] > max_dist_sqr) continue;
-        Corr c = {i, nn_i[i], nn_d[i]};
-        Cc.push_back(c);
+    if (!normal_shooting) {
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nn_threads) if (nn_threads > 1)
+        for (int i = 0; i < ns; ++i) {
+            float q[3] = {S[i].x, S[i].y, S[i].z};
+            int j = -1;
+            float d2 = 0;
+            tree.nearest(q, j, d2);
+            nn_i[i] = j;
+            nn_d[i] = d2;
+        }
+        for (int i = 0; i < ns; ++i) {
+            if (nn_i[i] < 0) continue;
+            if (nn_d[i] > max_dist_sqr) continue;
+            Corr c = {i, nn_i[i], nn_d[i]};
+            Cc.push_back(c);
+        }
+    } else {
+        // :1732-1737 CorrespondenceEstimationNormalShooting [3P], k = 10: among the k nearest targets the one with
+        // the smallest squared distance to the line through the source point along its normal; dropped if that
+        // value exceeds max_distance (NOT squared); corr.distance = squared NN distance of the chosen candidate.
+        const int K = 10;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nn_threads) if (nn_threads > 1)
+        for (int i = 0; i < ns; ++i) {
+            float q[3] = {S[i].x, S[i].y, S[i].z};
+            int ki[16];
+            float kd[16];
+            const int n = tree.nearest_k(q, K, ki, kd);
+            double min_dist = std::numeric_limits<double>::max();
+            int min_index = -1;
+            for (int j = 0; j < n; ++j) {
+                const Pt &t = T[ki[j]];
+                const float ptx = t.x - S[i].x, pty = t.y - S[i].y, ptz = t.z - S[i].z;
+                const double Nx = S[i].nx, Ny = S[i].ny, Nz = S[i].nz, Vx = ptx, Vy = pty, Vz = ptz;
+                const double Cx = Ny * Vz - Nz * Vy, Cy = Nz * Vx - Nx * Vz, Cz = Nx * Vy - Ny * Vx;
+                const double dist = Cx * Cx + (Cy * Cy + Cz * Cz); // [ORDER] Eigen 3-dot
+                if (dist < min_dist) {
+                    min_dist = dist;
+                    min_index = j;
+                }
+            }
+            if (min_index < 0 || min_dist > max_distance) {
+                nn_i[i] = -1;
+                nn_d[i] = 0;
+            } else {
+                nn_i[i] = ki[min_index];
+                nn_d[i] = kd[min_index];
+            }
+        }
+        for (int i = 0; i < ns; ++i) {
+            if (nn_i[i] < 0) continue;
+            Corr c = {i, nn_i[i], nn_d[i]};
+            Cc.push_back(c);
+        }
     }
 
     // :1755-1792 duplicate check + permanent source shrinking
@@ -968,6 +1072,7 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
     if (tm) tm->kd_build += now_s() - t0;
 
     const float nb = P.normal_bearing;
+    const bool nshoot = P.normal_shooting_on != 0; // ground, facade and roof only (:1273, :1283, :1290)
     const std::string ws(P.weight_strategy);
     int iters_entered = 0;
     if (trace) trace->n_iter = 0;
@@ -998,7 +1103,7 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
 #pragma omp section
                 {
                     if (used[G] && sc[G].size() > 0)
-                        if (!determine_corres(sc[G], tc[G], tree[G], dis_thre[G], corrs[G], true, nb, 1)) corrs[G].clear();
+                        if (!determine_corres(sc[G], tc[G], tree[G], dis_thre[G], corrs[G], true, nb, 1, nshoot)) corrs[G].clear();
                 }
 #pragma omp section
                 {
@@ -1008,7 +1113,7 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
 #pragma omp section
                 {
                     if (used[F] && sc[F].size() > 0)
-                        if (!determine_corres(sc[F], tc[F], tree[F], dis_thre[F], corrs[F], true, nb, 1)) corrs[F].clear();
+                        if (!determine_corres(sc[F], tc[F], tree[F], dis_thre[F], corrs[F], true, nb, 1, nshoot)) corrs[F].clear();
                     if (used[B] && sc[B].size() > 0)
                         if (!determine_corres(sc[B], tc[B], tree[B], dis_thre[B], corrs[B], true, nb, 1)) corrs[B].clear();
                 }
@@ -1016,10 +1121,12 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
         } else {
             for (int c = 0; c < 4; ++c)
                 if (used[c] && sc[c].size() > 0)
-                    if (!determine_corres(sc[c], tc[c], tree[c], dis_thre[c], corrs[c], true, nb, threads)) corrs[c].clear();
+                    if (!determine_corres(sc[c], tc[c], tree[c], dis_thre[c], corrs[c], true, nb, threads,
+                                          nshoot && (c == G || c == F)))
+                        corrs[c].clear();
         }
         if (used[R] && sc[R].size() > 0)
-            if (!determine_corres(sc[R], tc[R], tree[R], dis_thre[R], corrs[R], true, nb, threads ? threads : 1)) corrs[R].clear();
+            if (!determine_corres(sc[R], tc[R], tree[R], dis_thre[R], corrs[R], true, nb, threads ? threads : 1, nshoot)) corrs[R].clear();
         if (used[V] && sc[V].size() > 0)
             if (!determine_corres(sc[V], tc[V], tree[V], dis_thre[V], corrs[V], false, nb, threads ? threads : 1)) corrs[V].clear();
         // Q12: where the reference would re-use a stale list (class emptied, or

@@ -21,10 +21,6 @@ def test_capacity_unsupported_and_state_errors(small_pair):
     with pytest.raises(RuntimeError, match="-101"):       # MULLS_E_ARG: nothing uploaded
         ctx.run_resident()
     p = abi.IcpParams.from_buffer_copy(small_pair["params"])
-    p.normal_shooting_on = 1
-    with pytest.raises(RuntimeError, match="-103"):       # MULLS_E_UNSUPPORTED
-        ctx.run_batch([dict(small_pair, params=p)])
-    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
     p.max_iter_num = 1000
     with pytest.raises(RuntimeError, match="-101"):
         ctx.run_batch([dict(small_pair, params=p)])

@@ -217,8 +217,6 @@ def test_reference_interface_mirror(oracle_mod, small_pair):
     assert code == o["code"] == 1
     dt, dr = synth.pose_error(con.Trans1_2, o["T"])
     assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
-    with pytest.raises(RuntimeError):  # options this build does not implement fail loudly
-        creg.mm_lls_icp(con, normal_shooting_on=True)
 
 
 def test_motion_undistortion_variant(ctx, oracle_mod, small_pair):
@@ -327,3 +325,19 @@ def test_native_pipelined_context_equals_single_lane(small_pair):
     np.testing.assert_array_equal(few[1]["T"], ref[1]["T"])
     one.close()
     pipe.close()
+
+
+def test_normal_shooting_correspondences(ctx, oracle_mod, small_pair):
+    """normal_shooting_on (cregistration.hpp:1730-1739): exact 10-NN, minimum distance to the source normal line,
+    for ground / facade / roof; also with the intersection filter off (sources outside the target grid)."""
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.normal_shooting_on = 1
+    assert_parity(*run_both(ctx, oracle_mod, dict(small_pair, params=p)))
+    p2 = abi.IcpParams.from_buffer_copy(p)
+    p2.apply_intersection_filter = 0
+    init = np.eye(4)
+    init[:3, 3] = (0.4, -0.3, 0.02)
+    assert_parity(*run_both(ctx, oracle_mod, dict(small_pair, params=p2, init_guess=init)))
+    tiny = dict(small_pair, params=p, tgt=[t[:7] for t in small_pair["tgt"]])  # fewer than 10 targets per class
+    g, gt, o, ot = run_both(ctx, oracle_mod, tiny)
+    assert g["code"] == o["code"] and g["n_corr"] == o["n_corr"]
