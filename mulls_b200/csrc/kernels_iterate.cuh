@@ -372,7 +372,7 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
 // (pcl::registration::CorrespondenceEstimationNormalShooting): same hierarchy as nn_search, the pruning bound is
 // the current k-th best distance and there is no search radius — the level pyramid of a pair that uses normal
 // shooting goes up to a block that spans the whole grid, so the result is exact however far the targets are.
-// Total order (d2, original index), as the oracle's kd-tree.
+// Total order (d2, original index).
 // ------------------------------------------------------------------------------------------------
 constexpr int kShootK = 10;
 
