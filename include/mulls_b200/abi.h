@@ -20,6 +20,8 @@
  *                               caller-supplied all-reduce (NCCL in production)
  *   mulls_pca_features       <- lo::PrincipleComponentAnalysis<PointT>::get_pc_pca_feature
  *                               include/common/pca.hpp:294-354 (+ get_pca_feature :390-434)
+ *   mulls_map_update         <- lo::MapManager::update_local_map, src/map_manager.cpp:17-145
+ *   mulls_icp_run_to_map     <- mm_lls_icp with block1 = the device-resident local map
  *
  * Plain C, plain pointers and sizes. No torch / Eigen / PCL types cross this boundary; the C++ shim
  * in include/common/cregistration.hpp converts Eigen/PCL objects to these PODs.
@@ -204,6 +206,62 @@ typedef struct mulls_pca_out {
 } mulls_pca_out;
 int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride,
                        mulls_pca_out *out);
+
+/* ---- Device-resident local map -------------------------------------------------------
+ * lo::MapManager::update_local_map, src/map_manager.cpp:17-145 (+ map_based_dynamic_close_removal :149-217,
+ * map_scan_feature_pts_distance_removal :221-258; cloudblock_t::append_feature / transform_feature
+ * utility.hpp:438-470, :495-516; CFilter::dist_filter cfilter.hpp:838-873; random_downsample_pcl :606-628;
+ * get_cloud_bbx utility.hpp:817-847). The six target clouds of the scan-to-map registration stay in HBM between
+ * frames: per frame only the new scan's down-sampled feature clouds cross PCIe, and mulls_icp_run_to_map reads the
+ * target straight from the map. */
+typedef struct mulls_map mulls_map;
+
+/* Arguments of update_local_map (include/pgo/map_manager.h:22-32), same names and defaults. */
+typedef struct mulls_map_params {
+    float local_map_radius;              /* 80 */
+    int32_t max_num_pts;                 /* 20000 */
+    int32_t kept_vertex_num;             /* 800 */
+    float last_frame_reliable_radius;    /* 60; accepted and unused, as in the reference body */
+    int32_t map_based_dynamic_removal_on; /* 0; needs the preceding mulls_icp_run_to_map on the same context: the
+                                            reference queries the kd-trees that registration left in block1 */
+    char used_feature_type[8];           /* "111110" */
+    float dynamic_removal_center_radius; /* 30 */
+    float dynamic_dist_thre_min;         /* 0.3 */
+    float dynamic_dist_thre_max;         /* 3.0 */
+    float near_dist_thre;                /* 0.03 */
+    int32_t recalculate_feature_on;      /* 0; 1 (update_cloud_vectors, :95-115) is not implemented: MULLS_E_UNSUPPORTED */
+    uint32_t random_seed;                /* seed of the budgeted down-sampling (pcl::RandomSample in the reference) */
+} mulls_map_params;
+
+typedef struct mulls_map_info {
+    double pose_lo[16];     /* local_map->pose_lo after the update (= the scan's pose), row-major */
+    double local_bound[6];  /* local_map->local_bound: min_x min_y min_z max_x max_y max_z (map frame) */
+    double bound[6];        /* local_map->bound (world frame, points transformed by pose_lo) */
+    uint32_t n[MULLS_NUM_CLASSES];          /* points per class after the update */
+    uint32_t n_appended[MULLS_NUM_CLASSES]; /* scan points appended per class (after dynamic removal) */
+    int32_t feature_point_num;              /* ground + pillar + facade + beam + roof */
+    float ms_update;                        /* device time of the update (CUDA events) */
+} mulls_map_info;
+
+void mulls_map_default_params(mulls_map_params *p);
+/* A map whose six class clouds hold at most `max_pts_per_class` points each (map + appended scan). */
+mulls_map *mulls_map_create(mulls_ctx *ctx, size_t max_pts_per_class);
+void mulls_map_destroy(mulls_map *map);
+/* Replace the content of the map by host clouds (e.g. a map built elsewhere) and set its pose. */
+int mulls_map_set(mulls_map *map, const mulls_cloud_view cls[MULLS_NUM_CLASSES], const double pose_lo[16]);
+/* update_local_map(local_map, last_target_cblock, ...): `scan_down` are last_target_cblock->pc_*_down (index 5:
+ * pc_vertex), `scan_pose_lo` its pose_lo. The scan block itself is not modified (the reference leaves its down
+ * clouds transformed into the old map frame and thinned by the dynamic removal). */
+int mulls_map_update(mulls_map *map, const mulls_cloud_view scan_down[MULLS_NUM_CLASSES], const double scan_pose_lo[16],
+                     const mulls_map_params *params, mulls_map_info *info /* may be NULL */);
+int mulls_map_get_info(const mulls_map *map, mulls_map_info *info);
+/* Copy class `cls` of the map to the host (48-byte rows); *n receives the point count, `cap` is the room in rows. */
+int mulls_map_download(mulls_map *map, int cls, float *out_aos48, size_t cap, size_t *n);
+/* mm_lls_icp with block1 = the resident map: the target views and block1->local_bound come from the map
+ * (params->target_bound is ignored), only the source clouds are copied to the device. */
+int mulls_icp_run_to_map(mulls_ctx *ctx, mulls_map *map, const mulls_cloud_view src[MULLS_NUM_CLASSES],
+                         const mulls_icp_params *params, const double init_guess[16], mulls_icp_result *out,
+                         mulls_icp_trace *trace /* may be NULL */);
 
 /* Runtime tunables (integers), e.g. "start_level", "pairs_in_flight". Returns MULLS_E_ARG if unknown. */
 int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value);

@@ -100,6 +100,36 @@ class PcaOut(C.Structure):
     ]
 
 
+class MapParams(C.Structure):
+    """mulls_map_params: the arguments of MapManager::update_local_map (include/pgo/map_manager.h:22-32)."""
+    _fields_ = [
+        ("local_map_radius", C.c_float),
+        ("max_num_pts", C.c_int32),
+        ("kept_vertex_num", C.c_int32),
+        ("last_frame_reliable_radius", C.c_float),
+        ("map_based_dynamic_removal_on", C.c_int32),
+        ("used_feature_type", C.c_char * 8),
+        ("dynamic_removal_center_radius", C.c_float),
+        ("dynamic_dist_thre_min", C.c_float),
+        ("dynamic_dist_thre_max", C.c_float),
+        ("near_dist_thre", C.c_float),
+        ("recalculate_feature_on", C.c_int32),
+        ("random_seed", C.c_uint32),
+    ]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [
+        ("pose_lo", C.c_double * 16),
+        ("local_bound", C.c_double * 6),
+        ("bound", C.c_double * 6),
+        ("n", C.c_uint32 * NUM_CLASSES),
+        ("n_appended", C.c_uint32 * NUM_CLASSES),
+        ("feature_point_num", C.c_int32),
+        ("ms_update", C.c_float),
+    ]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
 
 # every symbol include/mulls_b200/abi.h declares
@@ -116,6 +146,14 @@ EXPORTED_SYMBOLS = (
     "mulls_get_stats",
     "mulls_icp_run_sharded",
     "mulls_pca_features",
+    "mulls_map_default_params",
+    "mulls_map_create",
+    "mulls_map_destroy",
+    "mulls_map_set",
+    "mulls_map_update",
+    "mulls_map_get_info",
+    "mulls_map_download",
+    "mulls_icp_run_to_map",
     "mulls_set_tunable",
 )
 
@@ -168,6 +206,24 @@ def load_library() -> C.CDLL:
     lib.mulls_pca_features.argtypes = [vp, CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(PcaOut)]
     lib.mulls_set_tunable.restype = C.c_int
     lib.mulls_set_tunable.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.mulls_map_default_params.restype = None
+    lib.mulls_map_default_params.argtypes = [C.POINTER(MapParams)]
+    lib.mulls_map_create.restype = vp
+    lib.mulls_map_create.argtypes = [vp, C.c_size_t]
+    lib.mulls_map_destroy.restype = None
+    lib.mulls_map_destroy.argtypes = [vp]
+    lib.mulls_map_set.restype = C.c_int
+    lib.mulls_map_set.argtypes = [vp, C.POINTER(CloudView), C.POINTER(C.c_double)]
+    lib.mulls_map_update.restype = C.c_int
+    lib.mulls_map_update.argtypes = [vp, C.POINTER(CloudView), C.POINTER(C.c_double), C.POINTER(MapParams),
+                                     C.POINTER(MapInfo)]
+    lib.mulls_map_get_info.restype = C.c_int
+    lib.mulls_map_get_info.argtypes = [vp, C.POINTER(MapInfo)]
+    lib.mulls_map_download.restype = C.c_int
+    lib.mulls_map_download.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.mulls_icp_run_to_map.restype = C.c_int
+    lib.mulls_icp_run_to_map.argtypes = [vp, vp, C.POINTER(CloudView), C.POINTER(IcpParams), C.POINTER(C.c_double),
+                                         C.POINTER(IcpResult), C.POINTER(IcpTrace)]
     _LIB = lib
     return lib
 
@@ -250,4 +306,34 @@ def trace_to_dict(t: IcpTrace) -> dict:
         "x": np.ctypeslib.as_array(t.x)[:n].copy(),
         "n_corr": np.ctypeslib.as_array(t.n_corr)[:n].copy(),
         "n_src": np.ctypeslib.as_array(t.n_src)[:n].copy(),
+    }
+
+
+def default_map_params() -> MapParams:
+    """The defaults of MapManager::update_local_map (include/pgo/map_manager.h:22-32) — pure Python."""
+    p = MapParams()
+    p.local_map_radius = 80.0
+    p.max_num_pts = 20000
+    p.kept_vertex_num = 800
+    p.last_frame_reliable_radius = 60.0
+    p.map_based_dynamic_removal_on = 0
+    p.used_feature_type = b"111110"
+    p.dynamic_removal_center_radius = 30.0
+    p.dynamic_dist_thre_min = 0.3
+    p.dynamic_dist_thre_max = 3.0
+    p.near_dist_thre = 0.03
+    p.recalculate_feature_on = 0
+    p.random_seed = 0
+    return p
+
+
+def map_info_to_dict(info: MapInfo) -> dict:
+    return {
+        "pose_lo": np.array(info.pose_lo[:], dtype=np.float64).reshape(4, 4),
+        "local_bound": np.array(info.local_bound[:], dtype=np.float64),
+        "bound": np.array(info.bound[:], dtype=np.float64),
+        "n": np.array(info.n[:], dtype=np.int64),
+        "n_appended": np.array(info.n_appended[:], dtype=np.int64),
+        "feature_point_num": int(info.feature_point_num),
+        "ms_update": float(info.ms_update),
     }

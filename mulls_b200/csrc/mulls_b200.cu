@@ -14,12 +14,15 @@
 #include "kernels_ingest.cuh"
 #include "kernels_iterate.cuh"
 #include "kernels_pca.cuh"
+#include "kernels_map.cuh"
 
 using namespace mulls;
 
 namespace {
 std::string g_create_error;
 }
+
+struct mulls_map;
 
 struct mulls_ctx {
     int device = 0;
@@ -62,6 +65,10 @@ struct mulls_ctx {
     // PCA scratch
     void *pca_buf = nullptr;
     size_t pca_buf_bytes = 0;
+    // the local map whose clouds the target slices of pair 0 currently index (set by mulls_icp_run_to_map, cleared
+    // by any other upload): what block1->tree_* are to MapManager::map_based_dynamic_close_removal
+    const mulls_map *tree_map = nullptr;
+    uint64_t tree_epoch = 0;
 };
 
 #define CK(call)                                                                                      \
@@ -442,8 +449,9 @@ static int build_pair_const(mulls_ctx *ctx, const mulls_icp_params &P, const dou
 // streams them over PCIe itself (zero-copy through the UVA alias), pageable ones are staged with cudaMemcpy.
 static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
                        const mulls_icp_params *params, const double *init_guess, const uint32_t *src_index_base,
-                       const uint32_t *src_global_n, bool resident = true) {
+                       const uint32_t *src_global_n, bool resident = true, bool tgt_on_device = false) {
     if (!ctx || !tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
+    ctx->tree_map = nullptr;
     if (n_pairs > ctx->max_pairs) {
         ctx->err = "more pairs than the context was created for";
         return MULLS_E_CAPACITY;
@@ -510,6 +518,10 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
             const mulls_cloud_view &v = (s < kNumClasses) ? tgt[p * kNumClasses + s] : src[p * kNumClasses + (s - kNumClasses)];
             pc.in_ptr[s] = ctx->A.in_aos + 3 * (size_t)pc.in_off[s];
             if (v.n == 0) continue;
+            if (tgt_on_device && s < kNumClasses) { // the view already points into HBM (device-resident local map)
+                pc.in_ptr[s] = (const float4 *)v.aos48;
+                continue;
+            }
             if (!resident && ctx->zero_copy) {
                 cudaPointerAttributes attr;
                 if (cudaPointerGetAttributes(&attr, v.aos48) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
@@ -877,6 +889,336 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     ctx->stats.kernel_launches = launches;
     ctx->uploaded = false; // the resident batch was replaced by the PCA cloud
     return MULLS_OK;
+}
+
+// ================================================================================================
+// Device-resident local map (MapManager::update_local_map, src/map_manager.cpp:17-145)
+// ================================================================================================
+} // extern "C"
+
+struct mulls_map {
+    mulls_ctx *ctx = nullptr;
+    size_t cap = 0;                      // rows per class buffer
+    float4 *buf[2][kNumClasses] = {};    // the map, ping-pong
+    float4 *mid[kNumClasses] = {};       // after append + transform + radius crop
+    float4 *scan[kNumClasses] = {};      // the scan's down clouds of the running update
+    uint8_t *drop[kNumClasses] = {};     // per scan point: removed by the dynamic filter
+    int cur = 0;
+    uint32_t n[kNumClasses] = {};
+    double pose[16];
+    double local_bound[6], bound[6];
+    MapState *d_state = nullptr, *h_state = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    mulls_map_info last{};
+    uint64_t epoch = 0; // bumped by every change of the content
+};
+
+namespace {
+// Eigen::Matrix4d::inverse(): adjugate / determinant
+void host_inverse4(const double *m, double *out) {
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * (1.0 / det);
+}
+void host_mul4(const double *a, const double *b, double *out) { // sequential over k
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += a[4 * i + k] * b[4 * k + j];
+            out[4 * i + j] = acc;
+        }
+}
+void map_fill_info(const mulls_map *m, mulls_map_info *info) {
+    *info = m->last;
+    for (int i = 0; i < 16; ++i) info->pose_lo[i] = m->pose[i];
+    for (int i = 0; i < 6; ++i) info->local_bound[i] = m->local_bound[i], info->bound[i] = m->bound[i];
+    for (int c = 0; c < kNumClasses; ++c) info->n[c] = m->n[c];
+    info->feature_point_num = (int)(m->n[0] + m->n[1] + m->n[2] + m->n[3] + m->n[4]);
+}
+} // namespace
+
+extern "C" {
+
+void mulls_map_default_params(mulls_map_params *p) { // include/pgo/map_manager.h:22-32
+    std::memset(p, 0, sizeof(*p));
+    p->local_map_radius = 80.f;
+    p->max_num_pts = 20000;
+    p->kept_vertex_num = 800;
+    p->last_frame_reliable_radius = 60.f;
+    p->map_based_dynamic_removal_on = 0;
+    std::strcpy(p->used_feature_type, "111110");
+    p->dynamic_removal_center_radius = 30.0f;
+    p->dynamic_dist_thre_min = 0.3f;
+    p->dynamic_dist_thre_max = 3.0f;
+    p->near_dist_thre = 0.03f;
+    p->recalculate_feature_on = 0;
+    p->random_seed = 0;
+}
+
+void mulls_map_destroy(mulls_map *m) {
+    if (!m) return;
+    mulls_ctx *ctx = m->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->tree_map == m) ctx->tree_map = nullptr;
+    for (int c = 0; c < kNumClasses; ++c) {
+        cudaFree(m->buf[0][c]);
+        cudaFree(m->buf[1][c]);
+        cudaFree(m->mid[c]);
+        cudaFree(m->scan[c]);
+        cudaFree(m->drop[c]);
+    }
+    cudaFree(m->d_state);
+    if (m->h_state) cudaFreeHost(m->h_state);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    delete m;
+}
+
+mulls_map *mulls_map_create(mulls_ctx *ctx, size_t max_pts_per_class) {
+    if (!ctx || max_pts_per_class == 0 || max_pts_per_class >= (1ull << 31)) return nullptr;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    mulls_map *m = new mulls_map();
+    m->ctx = ctx;
+    m->cap = max_pts_per_class;
+    bool ok = true;
+    const size_t bytes = max_pts_per_class * 48;
+    for (int c = 0; c < kNumClasses && ok; ++c) {
+        ok = ok && cudaMalloc((void **)&m->buf[0][c], bytes) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&m->buf[1][c], bytes) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&m->mid[c], bytes) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&m->scan[c], bytes) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&m->drop[c], max_pts_per_class) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc((void **)&m->d_state, sizeof(MapState)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&m->h_state, sizeof(MapState)) == cudaSuccess;
+    ok = ok && cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess;
+    if (!ok) {
+        ctx->err = std::string("mulls_map_create: ") + cudaGetErrorString(cudaGetLastError());
+        mulls_map_destroy(m);
+        return nullptr;
+    }
+    const double big = 1.7976931348623157e308;
+    for (int i = 0; i < 16; ++i) m->pose[i] = (i % 5 == 0) ? 1.0 : 0.0; // cloudblock_t starts at the identity pose
+    for (int d = 0; d < 3; ++d) {
+        m->local_bound[d] = m->bound[d] = big;
+        m->local_bound[3 + d] = m->bound[3 + d] = -big;
+    }
+    return m;
+}
+
+int mulls_map_set(mulls_map *m, const mulls_cloud_view cls[MULLS_NUM_CLASSES], const double pose_lo[16]) {
+    if (!m || !cls || !pose_lo) return MULLS_E_ARG;
+    mulls_ctx *ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    for (int c = 0; c < kNumClasses; ++c) {
+        if (cls[c].n > m->cap) {
+            ctx->err = "mulls_map_set: class cloud larger than the map's capacity";
+            return MULLS_E_CAPACITY;
+        }
+        if (cls[c].n > 0 && !cls[c].aos48) return MULLS_E_ARG;
+    }
+    const double big = 1.7976931348623157e308;
+    double lb[6] = {big, big, big, -big, -big, -big};
+    for (int c = 0; c < kNumClasses; ++c) {
+        if (cls[c].n)
+            CK(cudaMemcpyAsync(m->buf[m->cur][c], cls[c].aos48, cls[c].n * 48, cudaMemcpyHostToDevice, ctx->stream));
+        m->n[c] = (uint32_t)cls[c].n;
+        for (size_t i = 0; i < cls[c].n; ++i) // get_cloud_bbx, utility.hpp:817-847
+            for (int d = 0; d < 3; ++d) {
+                const double v = cls[c].aos48[12 * i + d];
+                if (lb[d] > v) lb[d] = v;
+                if (lb[3 + d] < v) lb[3 + d] = v;
+            }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 16; ++i) m->pose[i] = pose_lo[i];
+    for (int i = 0; i < 6; ++i) m->local_bound[i] = lb[i];
+    // the world-frame box is refreshed by the next update; until then report the local one moved by the pose's translation
+    for (int d = 0; d < 3; ++d) {
+        m->bound[d] = lb[d] + pose_lo[4 * d + 3];
+        m->bound[3 + d] = lb[3 + d] + pose_lo[4 * d + 3];
+    }
+    m->last = mulls_map_info();
+    ++m->epoch;
+    if (ctx->tree_map == m) ctx->tree_map = nullptr;
+    return MULLS_OK;
+}
+
+int mulls_map_get_info(const mulls_map *m, mulls_map_info *info) {
+    if (!m || !info) return MULLS_E_ARG;
+    map_fill_info(m, info);
+    return MULLS_OK;
+}
+
+int mulls_map_download(mulls_map *m, int cls, float *out_aos48, size_t cap, size_t *n) {
+    if (!m || cls < 0 || cls >= kNumClasses || !n) return MULLS_E_ARG;
+    mulls_ctx *ctx = m->ctx;
+    *n = m->n[cls];
+    if (!out_aos48) return MULLS_OK;
+    if (cap < m->n[cls]) {
+        ctx->err = "mulls_map_download: buffer too small";
+        return MULLS_E_CAPACITY;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (m->n[cls]) CK(cudaMemcpy(out_aos48, m->buf[m->cur][cls], (size_t)m->n[cls] * 48, cudaMemcpyDeviceToHost));
+    return MULLS_OK;
+}
+
+int mulls_map_update(mulls_map *m, const mulls_cloud_view scan_down[MULLS_NUM_CLASSES], const double scan_pose_lo[16],
+                     const mulls_map_params *params, mulls_map_info *info) {
+    if (!m || !scan_down || !scan_pose_lo || !params) return MULLS_E_ARG;
+    mulls_ctx *ctx = m->ctx;
+    const mulls_map_params &P = *params;
+    if (P.recalculate_feature_on) {
+        ctx->err = "mulls_map_update: recalculate_feature_on (update_cloud_vectors) is not implemented";
+        return MULLS_E_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    MapArgs M;
+    std::memset(&M, 0, sizeof(M));
+    const size_t nu = strnlen(P.used_feature_type, 8);
+    for (int c = 0; c < kNumClasses; ++c) {
+        M.used[c] = (c < (int)nu && P.used_feature_type[c] == '1') ? 1 : 0;
+        if (scan_down[c].n > 0 && !scan_down[c].aos48) return MULLS_E_ARG;
+        if (scan_down[c].n > m->cap || (size_t)m->n[c] + scan_down[c].n > m->cap) {
+            ctx->err = "mulls_map_update: map + scan exceed max_pts_per_class";
+            return MULLS_E_CAPACITY;
+        }
+    }
+    // :28, :32 tran_target_map = pose_scan^-1 * pose_map and its inverse
+    double inv_scan[16];
+    host_inverse4(scan_pose_lo, inv_scan);
+    host_mul4(inv_scan, m->pose, M.T);
+    host_inverse4(M.T, M.Tinv);
+    for (int i = 0; i < 16; ++i) M.pose[i] = scan_pose_lo[i];
+    M.radius = (double)P.local_map_radius;
+    M.max_num_pts = P.max_num_pts;
+    M.kept_vertex_num = P.kept_vertex_num;
+    M.seed = P.random_seed;
+    M.state = m->d_state;
+    const int nxt = m->cur ^ 1;
+    for (int c = 0; c < kNumClasses; ++c) {
+        M.old_pts[c] = m->buf[m->cur][c];
+        M.scan_pts[c] = m->scan[c];
+        M.scan_drop[c] = nullptr;
+        M.mid[c] = m->mid[c];
+        M.out[c] = m->buf[nxt][c];
+        M.n_old[c] = m->n[c];
+        M.n_scan[c] = (uint32_t)scan_down[c].n;
+    }
+    CK(cudaEventRecord(m->ev0, st));
+    for (int c = 0; c < kNumClasses; ++c)
+        if (scan_down[c].n)
+            CK(cudaMemcpyAsync(m->scan[c], scan_down[c].aos48, scan_down[c].n * 48, cudaMemcpyHostToDevice, st));
+    // :37-48 map-based dynamic object removal on the scan's pillar / beam / facade points
+    const int feature_point_num = (int)(m->n[0] + m->n[1] + m->n[2] + m->n[3] + m->n[4]);
+    if (P.map_based_dynamic_removal_on && feature_point_num > P.max_num_pts / 5) {
+        if (ctx->tree_map != m || ctx->tree_epoch != m->epoch) {
+            ctx->err = "mulls_map_update: map_based_dynamic_removal_on needs the target trees of the preceding "
+                       "mulls_icp_run_to_map on this map";
+            return MULLS_E_ARG;
+        }
+        MapDynArgs D;
+        std::memset(&D, 0, sizeof(D));
+        const int order[3] = {MULLS_PILLAR, MULLS_BEAM, MULLS_FACADE};
+        size_t nq = 0;
+        for (int k = 0; k < 3; ++k) {
+            const int c = order[k];
+            D.cls[k] = c;
+            D.scan_pts[k] = m->scan[c];
+            D.drop[k] = m->drop[c];
+            D.n_scan[k] = M.used[c] ? (uint32_t)scan_down[c].n : 0u;
+            if (D.n_scan[k]) {
+                CK(cudaMemsetAsync(m->drop[c], 0, D.n_scan[k], st));
+                M.scan_drop[c] = m->drop[c];
+            }
+            nq += D.n_scan[k];
+        }
+        for (int i = 0; i < 16; ++i) D.Tinv[i] = M.Tinv[i];
+        D.center_radius = P.dynamic_removal_center_radius;
+        D.dist_min = P.dynamic_dist_thre_min;
+        // :34 max_(dynamic_dist_thre_max, dynamic_dist_thre_min + 0.1)
+        D.dist_max = ((double)P.dynamic_dist_thre_max > (double)P.dynamic_dist_thre_min + 0.1)
+                         ? P.dynamic_dist_thre_max
+                         : (float)((double)P.dynamic_dist_thre_min + 0.1);
+        D.near_thre = P.near_dist_thre;
+        if (nq) k_map_dynamic<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(ctx->A, D);
+    }
+    k_map_merge<<<kNumClasses, kMapBlock, 0, st>>>(M);
+    k_map_sample<<<kNumClasses, kMapBlock, 0, st>>>(M);
+    CK(cudaMemcpyAsync(m->h_state, m->d_state, sizeof(MapState), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(m->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    // the map now lives in the other buffer, in the scan's frame
+    m->cur = nxt;
+    const MapState &S = *m->h_state;
+    const double big = 1.7976931348623157e308;
+    double lb[6] = {big, big, big, -big, -big, -big}, gb[6] = {big, big, big, -big, -big, -big};
+    for (int c = 0; c < kNumClasses; ++c) {
+        m->n[c] = S.n_out[c];
+        m->last.n_appended[c] = S.n_appended[c];
+        if (S.n_out[c] == 0) continue;
+        for (int d = 0; d < 3; ++d) {
+            lb[d] = std::min(lb[d], (double)S.lb[c][d]);
+            lb[3 + d] = std::max(lb[3 + d], (double)S.lb[c][3 + d]);
+            gb[d] = std::min(gb[d], (double)S.gb[c][d]);
+            gb[3 + d] = std::max(gb[3 + d], (double)S.gb[c][3 + d]);
+        }
+    }
+    for (int i = 0; i < 6; ++i) m->local_bound[i] = lb[i], m->bound[i] = gb[i];
+    for (int i = 0; i < 16; ++i) m->pose[i] = scan_pose_lo[i];
+    cudaEventElapsedTime(&m->last.ms_update, m->ev0, m->ev1);
+    ++m->epoch;
+    ctx->tree_map = nullptr; // :134 free_tree()
+    if (info) map_fill_info(m, info);
+    return MULLS_OK;
+}
+
+int mulls_icp_run_to_map(mulls_ctx *ctx, mulls_map *m, const mulls_cloud_view src[MULLS_NUM_CLASSES],
+                         const mulls_icp_params *params, const double init_guess[16], mulls_icp_result *out,
+                         mulls_icp_trace *trace) {
+    if (!ctx || !m || !src || !params || !init_guess) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    if (ctx != m->ctx) {
+        ctx->err = "mulls_icp_run_to_map: the map belongs to another context";
+        return MULLS_E_ARG;
+    }
+    mulls_cloud_view tgt[MULLS_NUM_CLASSES];
+    for (int c = 0; c < kNumClasses; ++c) {
+        tgt[c].aos48 = (const float *)m->buf[m->cur][c];
+        tgt[c].n = m->n[c];
+    }
+    mulls_icp_params P = *params;
+    for (int i = 0; i < 6; ++i) P.target_bound[i] = m->local_bound[i]; // block1->local_bound, cregistration.hpp:2916
+    int rc = upload_impl(ctx, 1, tgt, src, &P, init_guess, nullptr, nullptr, /*resident=*/false, /*tgt_on_device=*/true);
+    if (rc != MULLS_OK) return rc;
+    rc = run_impl(ctx, out, trace, nullptr, nullptr);
+    ctx->uploaded = false;
+    if (rc == MULLS_OK) { // the sorted target slices of this run stand in for block1->tree_*
+        ctx->tree_map = m;
+        ctx->tree_epoch = m->epoch;
+    }
+    return rc;
 }
 
 } // extern "C"

@@ -275,6 +275,30 @@ def make_pair(seed: int, config: str = "c2", n_points: int | None = None, max_it
     }
 
 
+def make_sequence(seed: int, n_frames: int, config: str = "small", n_points: int | None = None, max_iter: int = 20):
+    """A drive through one scene: `n_frames` sweeps at poses M^0 .. M^(n-1) (the odometry workload of
+    test/mulls_slam.cpp: every frame is registered to a local map built from the previous ones).
+    Returns dict(scans=[per frame six (n,12) arrays in the SENSOR frame], poses=[4x4 ground truth], params).
+    The vertex class — empty in `scan` — is filled with every 37th pillar/facade point so that the local map's
+    sixth cloud is exercised too."""
+    scene = make_scene(seed)
+    M = gt_motion()
+    kw = dict(n_points=120000, beams=64, elev_deg=(-24.8, 2.0), az_steps=2083)
+    if config == "small":
+        kw = dict(n_points=20000, beams=32, elev_deg=(-24.8, 2.0), az_steps=700)
+    if n_points is not None:
+        kw["n_points"] = n_points
+    poses = [np.eye(4)]
+    for _ in range(n_frames - 1):
+        poses.append(poses[-1] @ M)
+    scans = []
+    for k in range(n_frames):
+        sc = [abi.as_aos48(a) for a in scan(scene, _sensor_pose(poses[k]), seed * 7919 + k, **kw)]
+        sc[abi.VERTEX] = np.ascontiguousarray(np.concatenate([sc[abi.PILLAR], sc[abi.FACADE]], axis=0)[::37])
+        scans.append(sc)
+    return {"scans": scans, "poses": poses, "params": kitti_urban_params(max_iter)}
+
+
 def pose_error(T_a: np.ndarray, T_b: np.ndarray):
     """Translation (m) and rotation (rad) difference, the formulas of nav/odom_error_compute.h:65-82."""
     dt = float(np.linalg.norm(T_a[:3, 3] - T_b[:3, 3]))

@@ -785,6 +785,7 @@ static inline uint64_t sample_key(uint32_t seed, uint32_t cloud_id, uint32_t ind
 static void random_downsample(Cloud &c, const std::vector<uint32_t> &orig, std::vector<uint32_t> &orig_out, int keep_number,
                               uint32_t seed, uint32_t cloud_id) {
     orig_out = orig;
+    if (keep_number < 0) return; // size() <= keep_number compares as unsigned in the reference: always true
     if ((long long)c.size() <= (long long)keep_number) return;
     if (keep_number == 0) {
         c.clear();
@@ -948,7 +949,7 @@ static double now_s() {
 // ---------------------------------------------------------------------------------------------
 static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view srcv[6], const mulls_icp_params &P,
                       const double init_guess_rm[16], mulls_icp_result *out, mulls_icp_trace *trace, int threads,
-                      Timers *tm) {
+                      Timers *tm, Cloud *tree_clouds_out = nullptr) {
     const double t_begin = now_s();
     enum { G = 0, PL = 1, F = 2, B = 3, R = 4, V = 5 };
     int process_code = 0;
@@ -1070,6 +1071,12 @@ static int mm_lls_icp(const mulls_cloud_view tgtv[6], const mulls_cloud_view src
     }
     if (used[V] && tc[V].size() > 0) tree[V].build(tc[V]);
     if (tm) tm->kd_build += now_s() - t0;
+    // what block1->tree_* hold from here on (read later by MapManager::map_based_dynamic_close_removal)
+    if (tree_clouds_out)
+        for (int c = 0; c < 6; ++c) {
+            tree_clouds_out[c].clear();
+            if (used[c] && tc[c].size() > 0) tree_clouds_out[c] = tc[c];
+        }
 
     const float nb = P.normal_bearing;
     const bool nshoot = P.normal_shooting_on != 0; // ground, facade and roof only (:1273, :1283, :1290)
@@ -1334,6 +1341,138 @@ static void jacobi_eig3(const double Ain[3][3], double w[3], double V[3][3]) {
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// MapManager::update_local_map, src/map_manager.cpp:17-145 (recalculate_feature_on = false).
+// map[c] = local_map->pc_* (ground, pillar, facade, beam, roof, vertex), scan[c] = last_target_cblock->pc_*_down
+// (scan[5] = pc_vertex), trees[c] = the clouds block1's kd-trees were built on by the preceding registration.
+// ---------------------------------------------------------------------------------------------
+static void store_cloud(const Cloud &c, float *out) {
+    for (size_t i = 0; i < c.size(); ++i) {
+        float *f = out + 12 * i;
+        const Pt &p = c[i];
+        f[0] = p.x, f[1] = p.y, f[2] = p.z, f[3] = 1.0f;
+        f[4] = p.nx, f[5] = p.ny, f[6] = p.nz, f[7] = 0.0f;
+        f[8] = p.intensity, f[9] = p.curvature, f[10] = 0.0f, f[11] = 0.0f;
+    }
+}
+
+// map_manager.cpp:221-258 map_scan_feature_pts_distance_removal; the kd-tree query is an exact unbounded 1-NN, whose
+// squared distance is the minimum of FLANN's L2_Simple accumulation over the tree's points.
+static void scan_distance_removal(Cloud &pts, const Cloud &tree_pts, float center_radius, float dist_min, float dist_max,
+                                  float near_thre) {
+    if (pts.size() <= 10) return;
+    if (tree_pts.empty()) return; // no tree was built for this class (the reference would query a stale/unset tree)
+    Cloud keep;
+    for (size_t i = 0; i < pts.size(); ++i) {
+        const Pt &p = pts[i];
+        if (p.x * p.x + p.y * p.y > center_radius * center_radius) {
+            keep.push_back(p);
+            continue;
+        }
+        float best = std::numeric_limits<float>::infinity();
+        for (size_t j = 0; j < tree_pts.size(); ++j) {
+            const float d0 = p.x - tree_pts[j].x, d1 = p.y - tree_pts[j].y, d2 = p.z - tree_pts[j].z;
+            float r = 0.0f;
+            r += d0 * d0;
+            r += d1 * d1;
+            r += d2 * d2;
+            if (r < best) best = r;
+        }
+        if ((best > near_thre * near_thre && best < dist_min * dist_min) || best > dist_max * dist_max) keep.push_back(p);
+    }
+    pts.swap(keep);
+}
+
+// cfilter.hpp:838-873 dist_filter(cloud, xy_dis_thre, keep_inside = true, z_min = -DBL_MAX, z_max = DBL_MAX)
+static void dist_filter(Cloud &c, double xy_dis_thre) {
+    Cloud out;
+    const double zmax = 1.7976931348623157e308, zmin = -1.7976931348623157e308;
+    for (size_t i = 0; i < c.size(); ++i) {
+        const double dis_square = c[i].x * c[i].x + c[i].y * c[i].y; // float expression, widened
+        if (dis_square < xy_dis_thre * xy_dis_thre && c[i].z < zmax && c[i].z > zmin) out.push_back(c[i]);
+    }
+    c.swap(out);
+}
+
+static void map_update(Cloud map[6], Mat4 &map_pose, Cloud scan[6], const Mat4 &scan_pose, const Cloud *trees,
+                       const mulls_map_params &P, mulls_map_info *info) {
+    enum { G = 0, PL = 1, F = 2, B = 3, R = 4, V = 5 };
+    bool used[6];
+    for (int c = 0; c < 6; ++c) used[c] = (P.used_feature_type[c] == '1');
+    int feature_point_num = 0; // local_map->feature_point_num as the previous update left it (:131-133)
+    for (int c = 0; c < 5; ++c) feature_point_num += (int)map[c].size();
+    // :28 from the last local map to the target frame
+    const Mat4 tran_target_map = mul4(inverse4(scan_pose), map_pose);
+    // :32 the scan's down clouds go to the map frame (pc_vertex has no down cloud and stays where it is)
+    const Mat4 tran_inv = inverse4(tran_target_map);
+    for (int c = 0; c < 5; ++c) transform_cloud(scan[c], tran_inv);
+    // :34
+    float dist_max = P.dynamic_dist_thre_max;
+    if (!((double)dist_max > (double)P.dynamic_dist_thre_min + 0.1)) dist_max = (float)((double)P.dynamic_dist_thre_min + 0.1);
+    // :37-48, :190-206 (pillar, beam | facade)
+    if (P.map_based_dynamic_removal_on && feature_point_num > P.max_num_pts / 5 && trees) {
+        const int order[3] = {PL, B, F};
+        for (int k = 0; k < 3; ++k) {
+            const int c = order[k];
+            if (used[c])
+                scan_distance_removal(scan[c], trees[c], P.dynamic_removal_center_radius, P.dynamic_dist_thre_min, dist_max,
+                                      P.near_dist_thre);
+        }
+    }
+    // :54 append_feature(*last_target_cblock, true, used_feature_type), utility.hpp:438-470
+    for (int c = 0; c < 5; ++c)
+        if (used[c]) {
+            map[c].insert(map[c].end(), scan[c].begin(), scan[c].end());
+            if (info) info->n_appended[c] = (uint32_t)scan[c].size();
+        } else if (info)
+            info->n_appended[c] = 0;
+    map[V].insert(map[V].end(), scan[V].begin(), scan[V].end());
+    if (info) info->n_appended[V] = (uint32_t)scan[V].size();
+    // :57-59
+    for (int c = 0; c < 6; ++c) transform_cloud(map[c], tran_target_map);
+    map_pose = scan_pose;
+    // :62-67
+    for (int c = 0; c < 6; ++c) dist_filter(map[c], (double)P.local_map_radius);
+    // :69-85
+    feature_point_num = (int)(map[G].size() + map[F].size() + map[R].size() + map[PL].size() + map[B].size());
+    const int current_pts_count = feature_point_num;
+    int kept[6];
+    for (int c = 0; c < 5; ++c)
+        kept[c] = current_pts_count > 0 ? (int)(1.0 * P.max_num_pts / current_pts_count * map[c].size() + 1) : 0;
+    kept[V] = P.kept_vertex_num;
+    for (int c = 0; c < 6; ++c) {
+        if (c < 5 && current_pts_count == 0) continue; // every class is empty: nothing to sample
+        std::vector<uint32_t> orig(map[c].size()), tmp;
+        for (size_t i = 0; i < orig.size(); ++i) orig[i] = (uint32_t)i;
+        random_downsample(map[c], orig, tmp, kept[c], P.random_seed, 12 + c);
+    }
+    // :88-93 bounding boxes of the merged cloud, in the map frame and in the world frame
+    Bounds lb = {1.7976931348623157e308,  1.7976931348623157e308,  1.7976931348623157e308,
+                 -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+    Bounds gb = lb;
+    for (int c = 0; c < 6; ++c) {
+        const Bounds b = cloud_bbx(map[c]);
+        lb.min_x = std::min(lb.min_x, b.min_x), lb.min_y = std::min(lb.min_y, b.min_y), lb.min_z = std::min(lb.min_z, b.min_z);
+        lb.max_x = std::max(lb.max_x, b.max_x), lb.max_y = std::max(lb.max_y, b.max_y), lb.max_z = std::max(lb.max_z, b.max_z);
+        Cloud w = map[c];
+        transform_cloud(w, map_pose); // pcl::transformPointCloud: same arithmetic on x y z
+        const Bounds g = cloud_bbx(w);
+        gb.min_x = std::min(gb.min_x, g.min_x), gb.min_y = std::min(gb.min_y, g.min_y), gb.min_z = std::min(gb.min_z, g.min_z);
+        gb.max_x = std::max(gb.max_x, g.max_x), gb.max_y = std::max(gb.max_y, g.max_y), gb.max_z = std::max(gb.max_z, g.max_z);
+    }
+    if (info) {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) info->pose_lo[4 * i + j] = map_pose.a[i][j];
+        const double l[6] = {lb.min_x, lb.min_y, lb.min_z, lb.max_x, lb.max_y, lb.max_z};
+        const double g[6] = {gb.min_x, gb.min_y, gb.min_z, gb.max_x, gb.max_y, gb.max_z};
+        for (int i = 0; i < 6; ++i) info->local_bound[i] = l[i], info->bound[i] = g[i];
+        for (int c = 0; c < 6; ++c) info->n[c] = (uint32_t)map[c].size();
+        info->feature_point_num = (int)(map[G].size() + map[F].size() + map[R].size() + map[PL].size() + map[B].size());
+        info->ms_update = 0.f;
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -1472,6 +1611,42 @@ int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stri
     }
     return 0;
 }
+
+// One registration that also returns the clouds block1's kd-trees were built on (cregistration.hpp:1209-1232):
+// tree_out[c] has room for tgt[c].n rows of 12 floats, tree_n[c] receives the count (0 if no tree was built).
+int orc_icp_run_trees(const mulls_cloud_view tgt[6], const mulls_cloud_view src[6], const mulls_icp_params *params,
+                      const double init_guess[16], mulls_icp_result *out, float *const tree_out[6], size_t tree_n[6]) {
+    Cloud trees[6];
+    mm_lls_icp(tgt, src, *params, init_guess, out, nullptr, 0, nullptr, trees);
+    for (int c = 0; c < 6; ++c) {
+        tree_n[c] = trees[c].size();
+        if (tree_out[c]) store_cloud(trees[c], tree_out[c]);
+    }
+    return 0;
+}
+
+// update_local_map on host clouds. map_out[c] needs room for map_in[c].n + scan_down[c].n rows; `trees` may be NULL.
+int orc_map_update(const mulls_cloud_view map_in[6], const double map_pose[16], const mulls_cloud_view scan_down[6],
+                   const double scan_pose[16], const mulls_cloud_view *trees, const mulls_map_params *params,
+                   float *const map_out[6], mulls_map_info *info) {
+    Cloud map[6], scan[6], tr[6];
+    for (int c = 0; c < 6; ++c) {
+        load_cloud(map_in[c], map[c]);
+        load_cloud(scan_down[c], scan[c]);
+        if (trees) load_cloud(trees[c], tr[c]);
+    }
+    Mat4 mp, sp;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) mp.a[i][j] = map_pose[4 * i + j], sp.a[i][j] = scan_pose[4 * i + j];
+    mulls_map_info local;
+    std::memset(&local, 0, sizeof(local));
+    map_update(map, mp, scan, sp, trees ? tr : nullptr, *params, &local);
+    for (int c = 0; c < 6; ++c)
+        if (map_out[c]) store_cloud(map[c], map_out[c]);
+    if (info) *info = local;
+    return 0;
+}
+
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

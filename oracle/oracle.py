@@ -44,6 +44,15 @@ def load() -> C.CDLL:
         lib.orc_pca_features.restype = C.c_int
         lib.orc_pca_features.argtypes = [abi.CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(abi.PcaOut)]
         lib.orc_num_threads.restype = C.c_int
+        fpp = C.POINTER(C.c_float) * abi.NUM_CLASSES
+        lib.orc_icp_run_trees.restype = C.c_int
+        lib.orc_icp_run_trees.argtypes = [C.POINTER(abi.CloudView), C.POINTER(abi.CloudView), C.POINTER(abi.IcpParams),
+                                          C.POINTER(C.c_double), C.POINTER(abi.IcpResult), fpp,
+                                          C.POINTER(C.c_size_t)]
+        lib.orc_map_update.restype = C.c_int
+        lib.orc_map_update.argtypes = [C.POINTER(abi.CloudView), C.POINTER(C.c_double), C.POINTER(abi.CloudView),
+                                       C.POINTER(C.c_double), C.POINTER(abi.CloudView), C.POINTER(abi.MapParams), fpp,
+                                       C.POINTER(abi.MapInfo)]
         _LIB = lib
     return _LIB
 
@@ -93,3 +102,33 @@ def pca_features(cloud: np.ndarray, radius: float, k: int, stride: int = 1):
 
 def num_threads() -> int:
     return int(load().orc_num_threads())
+
+
+def icp_run_trees(tgt, src, params: abi.IcpParams, init_guess: np.ndarray):
+    """One registration (reference-shaped) that also returns the six clouds block1's kd-trees were built on
+    (cregistration.hpp:1209-1232): (result dict, [six (n,12) arrays])."""
+    lib = load()
+    res = abi.IcpResult()
+    init = np.ascontiguousarray(init_guess, dtype=np.float64).reshape(16)
+    bufs = [np.zeros((max(t.shape[0], 1), 12), np.float32) for t in tgt]
+    ptrs = (C.POINTER(C.c_float) * abi.NUM_CLASSES)(*[b.ctypes.data_as(C.POINTER(C.c_float)) for b in bufs])
+    n = (C.c_size_t * abi.NUM_CLASSES)()
+    lib.orc_icp_run_trees(views(tgt), views(src), C.byref(params), init.ctypes.data_as(C.POINTER(C.c_double)),
+                          C.byref(res), ptrs, n)
+    return abi.result_to_dict(res), [np.ascontiguousarray(bufs[c][: n[c]]) for c in range(abi.NUM_CLASSES)]
+
+
+def map_update(map_clouds, map_pose, scan_down, scan_pose, params: abi.MapParams, trees=None):
+    """MapManager::update_local_map on host clouds. Returns ([six (n,12) arrays], info dict)."""
+    lib = load()
+    mp = np.ascontiguousarray(map_pose, dtype=np.float64).reshape(16)
+    sp = np.ascontiguousarray(scan_pose, dtype=np.float64).reshape(16)
+    bufs = [np.zeros((max(map_clouds[c].shape[0] + scan_down[c].shape[0], 1), 12), np.float32)
+            for c in range(abi.NUM_CLASSES)]
+    ptrs = (C.POINTER(C.c_float) * abi.NUM_CLASSES)(*[b.ctypes.data_as(C.POINTER(C.c_float)) for b in bufs])
+    info = abi.MapInfo()
+    lib.orc_map_update(views(map_clouds), mp.ctypes.data_as(C.POINTER(C.c_double)), views(scan_down),
+                       sp.ctypes.data_as(C.POINTER(C.c_double)), views(trees) if trees is not None else None,
+                       C.byref(params), ptrs, C.byref(info))
+    d = abi.map_info_to_dict(info)
+    return [np.ascontiguousarray(bufs[c][: d["n"][c]]) for c in range(abi.NUM_CLASSES)], d
