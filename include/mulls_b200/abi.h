@@ -229,7 +229,7 @@ typedef struct mulls_map_params {
     float dynamic_dist_thre_min;         /* 0.3 */
     float dynamic_dist_thre_max;         /* 3.0 */
     float near_dist_thre;                /* 0.03 */
-    int32_t recalculate_feature_on;      /* 0; 1 (update_cloud_vectors, :95-115) is not implemented: MULLS_E_UNSUPPORTED */
+    int32_t recalculate_feature_on;      /* 0; 1: update_cloud_vectors (:95-115, :260-295) on the map's pillars and beams */
     uint32_t random_seed;                /* seed of the budgeted down-sampling (pcl::RandomSample in the reference) */
 } mulls_map_params;
 

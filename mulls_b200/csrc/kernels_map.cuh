@@ -8,6 +8,7 @@
 #include "device_math.cuh"
 #include "device_types.cuh"
 #include "kernels_ingest.cuh"
+#include "kernels_pca.cuh"
 
 namespace mulls {
 
@@ -275,6 +276,42 @@ __global__ void __launch_bounds__(kMapBlock) k_map_sample(MapArgs M) {
             M.state->gb[c][3 * side + comp - 3] = v;
     }
     if (threadIdx.x == 0) M.state->n_out[c] = s_total;
+}
+
+// ---- k_map_revector: MapManager::update_cloud_vectors (map_manager.cpp:260-295) after the PCA pass. One block;
+//      keeps, in order, the points with >= k_min neighbours and linearity (l1-l2)/l1 > min_linearity whose new
+//      principal direction is steep (pillar: |z| > sin_high) or flat (beam: |z| < sin_low); the direction goes to
+//      normal_*, the linearity to `curvature` (:283).
+__global__ void __launch_bounds__(kMapBlock) k_map_revector(const float4 *in, uint32_t n, PcaArgs F, int k_min, float sin_low,
+                                                            float sin_high, float min_linearity, float4 *out, uint32_t *n_out) {
+    __shared__ uint32_t s_warp[kMapBlock / 32];
+    __shared__ uint32_t s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    for (uint32_t tile = 0; tile < n; tile += kMapBlock) {
+        const uint32_t i = tile + threadIdx.x;
+        bool keep = false;
+        MapRow r;
+        if (i < n && F.pt_num[i] >= k_min) {
+            const float l1 = F.eigenvalues[3 * (size_t)i], l2 = F.eigenvalues[3 * (size_t)i + 1];
+            const float linear_2 = (l1 - l2) / l1;
+            const float pz = fabsf(F.principal[3 * (size_t)i + 2]);
+            if (linear_2 > min_linearity && (pz > sin_high || pz < sin_low)) {
+                keep = true;
+                const float4 *p = in + 3 * (size_t)i;
+                r.a = p[0], r.c = p[2];
+                r.b = make_float4(F.principal[3 * (size_t)i], F.principal[3 * (size_t)i + 1], F.principal[3 * (size_t)i + 2], 0.0f);
+                r.c.y = linear_2;
+            }
+        }
+        const uint32_t slot = map_tile_slot(keep, s_warp, &s_total);
+        if (keep) {
+            float4 *o = out + 3 * (size_t)slot;
+            o[0] = r.a, o[1] = r.b, o[2] = r.c;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *n_out = s_total;
 }
 
 } // namespace mulls

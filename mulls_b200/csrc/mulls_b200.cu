@@ -828,11 +828,12 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
     return rc;
 }
 
-int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
-    if (!ctx || !out || !out->eigenvalues || !out->principal || !out->normal || !out->pt_num || stride < 1 ||
-        !(radius > 0.f))
-        return MULLS_E_ARG;
-    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+} // extern "C"
+
+// PCA features of one cloud (host rows, or rows already in HBM) into ctx->pca_buf; `args` receives the device arrays.
+// Nothing is synchronised: the caller consumes the arrays on ctx->stream.
+static int pca_on_device(mulls_ctx *ctx, mulls_cloud_view cloud, bool cloud_on_device, float radius, int k, int stride,
+                         PcaArgs &args, uint64_t &launches) {
     // the cloud becomes the only target class of a one-pair batch: same filter-less ingest, same grid
     mulls_icp_params P;
     mulls_icp_default_params(&P);
@@ -843,7 +844,7 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     mulls_cloud_view tgt[MULLS_NUM_CLASSES] = {cloud, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
     mulls_cloud_view src[MULLS_NUM_CLASSES] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
     const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    int rc = upload_impl(ctx, 1, tgt, src, &P, ident, nullptr, nullptr, /*resident=*/false);
+    int rc = upload_impl(ctx, 1, tgt, src, &P, ident, nullptr, nullptr, /*resident=*/false, cloud_on_device);
     if (rc != MULLS_OK) return rc;
     const size_t n = cloud.n;
     const size_t bytes = n * (9 * sizeof(float) + sizeof(int));
@@ -857,10 +858,8 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     cudaStream_t st = ctx->stream;
     DeviceArrays A = ctx->A;
     A.trace = nullptr;
-    uint64_t launches = 0;
     rc = launch_ingest(ctx, A, false, launches);
     if (rc != MULLS_OK) return rc;
-    PcaArgs args;
     args.radius = radius;
     args.r2 = (float)((double)radius * (double)radius);
     args.k = k;
@@ -873,12 +872,31 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     if (n) {
         k_pca<<<(unsigned)ceil_div(n, kPcaWarps), kPcaWarps * 32, 0, st>>>(A, args);
         ++launches;
+    }
+    CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ctx->uploaded = false; // the resident batch was replaced by the PCA cloud
+    return MULLS_OK;
+}
+
+extern "C" {
+
+int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
+    if (!ctx || !out || !out->eigenvalues || !out->principal || !out->normal || !out->pt_num || stride < 1 ||
+        !(radius > 0.f))
+        return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    PcaArgs args;
+    uint64_t launches = 0;
+    int rc = pca_on_device(ctx, cloud, false, radius, k, stride, args, launches);
+    if (rc != MULLS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const size_t n = cloud.n;
+    if (n) {
         CK(cudaMemcpyAsync(out->eigenvalues, args.eigenvalues, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out->principal, args.principal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out->normal, args.normal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out->pt_num, args.pt_num, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (ctx->h_flags[1]) {
@@ -887,7 +905,6 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     }
     ctx->stats = mulls_run_stats();
     ctx->stats.kernel_launches = launches;
-    ctx->uploaded = false; // the resident batch was replaced by the PCA cloud
     return MULLS_OK;
 }
 
@@ -1087,10 +1104,6 @@ int mulls_map_update(mulls_map *m, const mulls_cloud_view scan_down[MULLS_NUM_CL
     if (!m || !scan_down || !scan_pose_lo || !params) return MULLS_E_ARG;
     mulls_ctx *ctx = m->ctx;
     const mulls_map_params &P = *params;
-    if (P.recalculate_feature_on) {
-        ctx->err = "mulls_map_update: recalculate_feature_on (update_cloud_vectors) is not implemented";
-        return MULLS_E_UNSUPPORTED;
-    }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     MapArgs M;
@@ -1190,6 +1203,41 @@ int mulls_map_update(mulls_map *m, const mulls_cloud_view scan_down[MULLS_NUM_CL
     cudaEventElapsedTime(&m->last.ms_update, m->ev0, m->ev1);
     ++m->epoch;
     ctx->tree_map = nullptr; // :134 free_tree()
+    // :95-115 update_cloud_vectors: re-estimate the direction of the map's pillar and beam points from the map itself
+    // (PCA over at most 20 neighbours within 1.8 m) and keep the ones that still look like a pillar / a beam. The
+    // bounding boxes above are not refreshed (the reference computes them before this step).
+    if (P.recalculate_feature_on) {
+        const float pca_radius = 1.8f, sin_high_pillar = 0.80f, sin_low_beam = 0.25f, min_linearity = 0.65f;
+        const int pca_max_k = 20, pca_min_k = 6;
+        const int cls[2] = {MULLS_PILLAR, MULLS_BEAM};
+        const float lo[2] = {0.0f, sin_low_beam}, hi[2] = {sin_high_pillar, 1.0f};
+        bool any = false;
+        for (int k = 0; k < 2; ++k) {
+            const int c = cls[k];
+            if (!M.used[c] || m->n[c] == 0) continue;
+            mulls_cloud_view v{(const float *)m->buf[m->cur][c], m->n[c]};
+            PcaArgs args;
+            uint64_t launches = 0;
+            const int rc = pca_on_device(ctx, v, true, pca_radius, pca_max_k, 1, args, launches);
+            if (rc != MULLS_OK) return rc;
+            k_map_revector<<<1, kMapBlock, 0, st>>>(m->buf[m->cur][c], m->n[c], args, pca_min_k, lo[k], hi[k], min_linearity,
+                                                   m->mid[c], &m->d_state->n_out[c]);
+            std::swap(m->buf[m->cur][c], m->mid[c]);
+            any = true;
+        }
+        if (any) {
+            CK(cudaMemcpyAsync(m->h_state, m->d_state, sizeof(MapState), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(m->ev1, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if (ctx->h_flags[1]) {
+                ctx->err = "hash pool exhausted";
+                return MULLS_E_CAPACITY;
+            }
+            for (int k = 0; k < 2; ++k) m->n[cls[k]] = m->h_state->n_out[cls[k]];
+            cudaEventElapsedTime(&m->last.ms_update, m->ev0, m->ev1);
+        }
+    }
     if (info) map_fill_info(m, info);
     return MULLS_OK;
 }

@@ -1342,8 +1342,12 @@ static void jacobi_eig3(const double Ain[3][3], double w[3], double V[3][3]) {
 }
 
 
+} // namespace
+extern "C" int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out);
+namespace {
+
 // ---------------------------------------------------------------------------------------------
-// MapManager::update_local_map, src/map_manager.cpp:17-145 (recalculate_feature_on = false).
+// MapManager::update_local_map, src/map_manager.cpp:17-145.
 // map[c] = local_map->pc_* (ground, pillar, facade, beam, roof, vertex), scan[c] = last_target_cblock->pc_*_down
 // (scan[5] = pc_vertex), trees[c] = the clouds block1's kd-trees were built on by the preceding registration.
 // ---------------------------------------------------------------------------------------------
@@ -1393,6 +1397,33 @@ static void dist_filter(Cloud &c, double xy_dis_thre) {
         if (dis_square < xy_dis_thre * xy_dis_thre && c[i].z < zmax && c[i].z > zmin) out.push_back(c[i]);
     }
     c.swap(out);
+}
+
+// map_manager.cpp:260-295 update_cloud_vectors (the kd-tree argument is unused there: get_pc_pca_feature builds its own)
+static void update_cloud_vectors(Cloud &pts, float pca_radius, int pca_k, int k_min, float sin_low, float sin_high,
+                                 float min_linearity) {
+    if (pts.empty()) return;
+    const size_t n = pts.size();
+    std::vector<float> rows(12 * n), ev(3 * n), pr(3 * n), nr(3 * n);
+    std::vector<int32_t> cnt(n);
+    store_cloud(pts, rows.data());
+    mulls_cloud_view v = {rows.data(), n};
+    mulls_pca_out out = {ev.data(), pr.data(), nr.data(), cnt.data()};
+    orc_pca_features(v, pca_radius, pca_k, 1, &out); // get_pc_pca_feature(feature_pts, features, radius, k, k_min)
+    Cloud keep;
+    for (size_t i = 0; i < n; ++i) {
+        if (cnt[i] < k_min) continue;
+        const float linear_2 = (ev[3 * i] - ev[3 * i + 1]) / ev[3 * i]; // pca.hpp:425
+        if (!(linear_2 > min_linearity)) continue;
+        const float pz = std::fabs(pr[3 * i + 2]);
+        if (pz > sin_high || pz < sin_low) {
+            Pt p = pts[i];
+            p.nx = pr[3 * i], p.ny = pr[3 * i + 1], p.nz = pr[3 * i + 2]; // assign_normal(pt, feature, false)
+            p.curvature = linear_2;                                      // :283
+            keep.push_back(p);
+        }
+    }
+    pts.swap(keep);
 }
 
 static void map_update(Cloud map[6], Mat4 &map_pose, Cloud scan[6], const Mat4 &scan_pose, const Cloud *trees,
@@ -1460,6 +1491,11 @@ static void map_update(Cloud map[6], Mat4 &map_pose, Cloud scan[6], const Mat4 &
         const Bounds g = cloud_bbx(w);
         gb.min_x = std::min(gb.min_x, g.min_x), gb.min_y = std::min(gb.min_y, g.min_y), gb.min_z = std::min(gb.min_z, g.min_z);
         gb.max_x = std::max(gb.max_x, g.max_x), gb.max_y = std::max(gb.max_y, g.max_y), gb.max_z = std::max(gb.max_z, g.max_z);
+    }
+    // :95-115 (the bounding boxes above are not refreshed)
+    if (P.recalculate_feature_on) {
+        if (used[PL]) update_cloud_vectors(map[PL], 1.8f, 20, 6, 0.0f, 0.80f, 0.65f);
+        if (used[B]) update_cloud_vectors(map[B], 1.8f, 20, 6, 0.25f, 1.0f, 0.65f);
     }
     if (info) {
         for (int i = 0; i < 4; ++i)

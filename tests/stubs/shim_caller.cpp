@@ -4,6 +4,7 @@
 
 #include "utility.hpp"
 #include "common/cregistration_b200.hpp"
+#include "pgo/map_manager_b200.hpp"
 
 using namespace lo;
 
@@ -18,6 +19,14 @@ int main() {
     // defaults-only call
     int code2 = lo::b200::mm_lls_icp<Point_T>(reg_con);
     bool ok4 = lo::b200::mm_lls_icp_4dof_global<Point_T>(reg_con, 45.0f); // the commented-out call of test/mulls_reg.cpp:197
-    std::printf("shim compiled and linked; codes %d %d %d\n", code, code2, (int)ok4);
+    // the local-map calls of test/mulls_slam.cpp:438-442 and :477-482 on the device-resident map
+    lo::b200::MapManagerB200 mmanager(1 << 12, 1 << 12);
+    cloudblock_Ptr cblock_local_map(new cloudblock_t), cblock_target(new cloudblock_t);
+    bool up1 = mmanager.update_local_map(cblock_local_map, cblock_target, 50.0f, 8000, 1000, 60.0f, false, "111110");
+    bool up2 = mmanager.update_local_map(cblock_local_map, cblock_target, 50.0f, 8000, 1000, 60.0f, true, "111110", 15.0f,
+                                         0.15f, 1.5f, 0.03f, true);
+    reg_con.block1 = cblock_local_map;
+    int code3 = mmanager.mm_lls_icp(reg_con, reg_max_iter_num, reg_corr_dis_thre, converge_tran, converge_rot_d);
+    std::printf("shim compiled and linked; codes %d %d %d | map %d %d %d\n", code, code2, (int)ok4, (int)up1, (int)up2, code3);
     return 0;
 }

@@ -64,8 +64,10 @@ struct centerpoint_t {
 };
 struct cloudblock_t {
     typedef pcl::PointCloud<Point_T>::Ptr pcTPtr;
-    bounds_t local_bound;
+    bounds_t local_bound, bound;
     centerpoint_t local_station;
+    Eigen::Matrix4d pose_lo = Eigen::Matrix4d::Identity(), pose_gt = Eigen::Matrix4d::Identity();
+    int feature_point_num = 0;
     pcTPtr pc_ground, pc_facade, pc_roof, pc_pillar, pc_beam, pc_vertex;
     pcTPtr pc_ground_down, pc_facade_down, pc_roof_down, pc_pillar_down, pc_beam_down;
     cloudblock_t() {

@@ -139,6 +139,29 @@ def test_oracle_dynamic_removal_drops_points_close_to_the_map():
     assert i1["n_appended"][abi.GROUND] == seq["scans"][0][abi.GROUND].shape[0]
 
 
+def test_oracle_recalculated_vectors_follow_the_geometry():
+    """update_cloud_vectors (map_manager.cpp:260-295): pillars keep steep directions, beams flat ones; the direction
+    comes from the map's own geometry, the linearity lands in `curvature`."""
+    seq = synth.make_sequence(6, 1, "c2")
+    sc = seq["scans"][0]
+    p = map_params(max_num_pts=40000, local_map_radius=60.0)
+    plain, i0 = oracle.map_update(EMPTY, np.eye(4), sc, np.eye(4), p)
+    pr = map_params(max_num_pts=40000, local_map_radius=60.0, recalculate_feature_on=1)
+    rec, i1 = oracle.map_update(EMPTY, np.eye(4), sc, np.eye(4), pr)
+    for c in (abi.GROUND, abi.FACADE, abi.ROOF, abi.VERTEX):
+        assert np.array_equal(plain[c], rec[c])
+    assert np.array_equal(i0["local_bound"], i1["local_bound"])  # boxes are computed before the recalculation
+    pil, beam = rec[abi.PILLAR], rec[abi.BEAM]
+    assert 0 < pil.shape[0] <= plain[abi.PILLAR].shape[0] and 0 < beam.shape[0] <= plain[abi.BEAM].shape[0]
+    assert (np.abs(pil[:, 6]) > 0.80).all() and (np.abs(beam[:, 6]) < 0.25).all()
+    assert (pil[:, 9] > 0.65).all() and (beam[:, 9] > 0.65).all() and (pil[:, 9] <= 1.0).all()
+    assert np.allclose(np.linalg.norm(pil[:, 4:7], axis=1), 1.0, atol=1e-5)
+    # survivors are a subsequence of the un-recalculated cloud
+    keys = {tuple(r) for r in plain[abi.PILLAR][:, :3].tolist()}
+    assert all(tuple(r) in keys for r in pil[:, :3].tolist())
+    assert i1["feature_point_num"] == int(i1["n"][:5].sum()) == sum(r.shape[0] for r in rec[:5])
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU: the device-resident map against the restatement
 # ------------------------------------------------------------------------------------------------
@@ -238,11 +261,38 @@ def test_gpu_map_errors():
     with pytest.raises(RuntimeError, match="-102"):  # capacity
         lm.update(seq["scans"][0], np.eye(4), map_params())
     lm2 = LocalMap(ctx, 1 << 16)
-    with pytest.raises(RuntimeError, match="-103"):  # update_cloud_vectors is not implemented
-        lm2.update(seq["scans"][0], np.eye(4), map_params(recalculate_feature_on=1))
     lm2.update(seq["scans"][0], np.eye(4), map_params(max_num_pts=2000))
     with pytest.raises(RuntimeError, match="-101"):  # dynamic removal without the preceding scan-to-map registration
         lm2.update(seq["scans"][0], np.eye(4), map_params(max_num_pts=2000, map_based_dynamic_removal_on=1))
     lm.close()
     lm2.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_map_recalculate_feature_matches_oracle():
+    """recalculate_feature_on: PCA is floating point — neighbour sets, survivors and xyz are exact; the new directions
+    and linearities agree to 1e-5 (both sides solve the 3x3 problem in fp64; the reference uses float Eigen)."""
+    from mulls_b200.map_manager import LocalMap
+    from mulls_b200.registration import Context
+
+    seq = synth.make_sequence(6, 2, "c2")
+    ctx = Context(0, 1, 200000, 400000)
+    lm = LocalMap(ctx, 1 << 18)
+    p0 = map_params(max_num_pts=40000, local_map_radius=60.0)
+    p1 = map_params(max_num_pts=40000, local_map_radius=60.0, recalculate_feature_on=1)
+    lm.update(seq["scans"][0], seq["poses"][0], p0)
+    omap, oinfo = oracle.map_update(EMPTY, np.eye(4), seq["scans"][0], seq["poses"][0], p0)
+    ginfo = lm.update(seq["scans"][1], seq["poses"][1], p1)
+    omap, oinfo = oracle.map_update(omap, oinfo["pose_lo"], seq["scans"][1], seq["poses"][1], p1)
+    _assert_info_equal(ginfo, oinfo, "recalc")
+    g = lm.download()
+    for c in (abi.GROUND, abi.FACADE, abi.ROOF, abi.VERTEX):
+        assert np.array_equal(g[c], omap[c])
+    for c in (abi.PILLAR, abi.BEAM):
+        assert g[c].shape == omap[c].shape and g[c].shape[0] > 50
+        assert np.array_equal(g[c][:, [0, 1, 2, 3, 8]], omap[c][:, [0, 1, 2, 3, 8]])
+        assert np.abs(g[c][:, 4:7] - omap[c][:, 4:7]).max() < 1e-5
+        assert np.abs(g[c][:, 9] - omap[c][:, 9]).max() < 1e-5
+    lm.close()
     ctx.close()
