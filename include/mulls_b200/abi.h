@@ -21,6 +21,7 @@
  *   mulls_pca_features       <- lo::PrincipleComponentAnalysis<PointT>::get_pc_pca_feature
  *                               include/common/pca.hpp:294-354 (+ get_pca_feature :390-434)
  *   mulls_map_update         <- lo::MapManager::update_local_map, src/map_manager.cpp:17-145
+ *   mulls_classify_nground   <- lo::CFilter<PointT>::classify_nground_pts, include/common/cfilter.hpp:2058-2290
  *   mulls_icp_run_to_map     <- mm_lls_icp with block1 = the device-resident local map
  *
  * Plain C, plain pointers and sizes. No torch / Eigen / PCL types cross this boundary; the C++ shim
@@ -262,6 +263,68 @@ int mulls_map_download(mulls_map *map, int cls, float *out_aos48, size_t cap, si
 int mulls_icp_run_to_map(mulls_ctx *ctx, mulls_map *map, const mulls_cloud_view src[MULLS_NUM_CLASSES],
                          const mulls_icp_params *params, const double init_guess[16], mulls_icp_result *out,
                          mulls_icp_trace *trace /* may be NULL */);
+
+/* ---- Non-ground feature classification -------------------------------------------------
+ * lo::CFilter<PointT>::classify_nground_pts, include/common/cfilter.hpp:2058-2290: PCA of every pca_down_rate-th point
+ * (pca.hpp:294-354, a16), linearity / planarity / direction thresholds -> pillar, beam, facade, roof (:2103-2166),
+ * vertex-neighbourhood promotion (:2169-2210), keypoints with the neighbourhood-category descriptor
+ * (encode_stable_points, :1071-1181), non-maximum suppression (non_max_suppress, :1243-1312) and the fixed-number
+ * down-sampling (random_downsample_pcl :606-628, xy_normal_balanced_downsample :551-602). */
+enum {
+    MULLS_OUT_PILLAR = 0,
+    MULLS_OUT_BEAM = 1,
+    MULLS_OUT_FACADE = 2,
+    MULLS_OUT_ROOF = 3,
+    MULLS_OUT_PILLAR_DOWN = 4,
+    MULLS_OUT_BEAM_DOWN = 5,
+    MULLS_OUT_FACADE_DOWN = 6,
+    MULLS_OUT_ROOF_DOWN = 7,
+    MULLS_OUT_VERTEX = 8,   /* the keypoints this call appends to cloud_vertex */
+    MULLS_OUT_UNGROUND = 9, /* cloud_in as the call leaves it (sampled, normals assigned) */
+    MULLS_OUT_COUNT = 10
+};
+
+/* Arguments of classify_nground_pts (cfilter.hpp:2070-2081), same names; defaults where the reference has them,
+ * otherwise the values extract_semantic_pts / test/mulls_slam.cpp pass by default. */
+typedef struct mulls_classify_params {
+    float neighbor_searching_radius;      /* 1.0 */
+    int32_t neighbor_k;                   /* 50; 1..64 */
+    int32_t neigh_k_min;                  /* 8 */
+    int32_t pca_down_rate;                /* 1 */
+    float edge_thre;                      /* 0.65 */
+    float planar_thre;                    /* 0.65 */
+    float edge_thre_down;                 /* 0.75 */
+    float planar_thre_down;               /* 0.75 */
+    int32_t extract_vertex_points_method; /* 2 */
+    float curvature_thre;                 /* 0.12 */
+    float vertex_curvature_non_max_radius; /* 1.5 * radius; unused by the reference body */
+    float linear_vertical_sin_high_thre;  /* 0.94 */
+    float linear_vertical_sin_low_thre;   /* 0.17 */
+    float planar_vertical_sin_high_thre;  /* 0.98 */
+    float planar_vertical_sin_low_thre;   /* 0.34 */
+    int32_t fixed_num_downsampling;       /* 0 */
+    int32_t pillar_down_fixed_num;        /* 200 */
+    int32_t facade_down_fixed_num;        /* 800 */
+    int32_t beam_down_fixed_num;          /* 200 */
+    int32_t roof_down_fixed_num;          /* 100 */
+    int32_t unground_down_fixed_num;      /* 20000 */
+    float beam_height_max;                /* FLT_MAX */
+    float roof_height_min;                /* -FLT_MAX */
+    float feature_pts_ratio_guess;        /* 0.3 */
+    int32_t sharpen_with_nms;             /* 1 */
+    int32_t use_distance_adaptive_pca;    /* 0; 1 is not implemented: MULLS_E_UNSUPPORTED */
+    uint32_t random_seed;                 /* seed of every random_downsample_pcl inside */
+} mulls_classify_params;
+
+typedef struct mulls_classify_out {
+    float *rows[MULLS_OUT_COUNT]; /* caller buffers of `cap` 48-byte rows each (NULL: not wanted) */
+    size_t cap;                   /* cloud_in.n rows are always enough */
+    size_t n[MULLS_OUT_COUNT];    /* rows written */
+} mulls_classify_out;
+
+void mulls_classify_default_params(mulls_classify_params *p);
+int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_classify_params *params,
+                           mulls_classify_out *out);
 
 /* Runtime tunables (integers), e.g. "start_level", "pairs_in_flight". Returns MULLS_E_ARG if unknown. */
 int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value);

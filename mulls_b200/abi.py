@@ -130,6 +130,52 @@ class MapInfo(C.Structure):
     ]
 
 
+OUT_NAMES = ("pillar", "beam", "facade", "roof", "pillar_down", "beam_down", "facade_down", "roof_down", "vertex",
+             "unground")
+OUT_COUNT = len(OUT_NAMES)
+
+
+class ClassifyParams(C.Structure):
+    """mulls_classify_params: the arguments of CFilter::classify_nground_pts (cfilter.hpp:2070-2081)."""
+    _fields_ = [
+        ("neighbor_searching_radius", C.c_float),
+        ("neighbor_k", C.c_int32),
+        ("neigh_k_min", C.c_int32),
+        ("pca_down_rate", C.c_int32),
+        ("edge_thre", C.c_float),
+        ("planar_thre", C.c_float),
+        ("edge_thre_down", C.c_float),
+        ("planar_thre_down", C.c_float),
+        ("extract_vertex_points_method", C.c_int32),
+        ("curvature_thre", C.c_float),
+        ("vertex_curvature_non_max_radius", C.c_float),
+        ("linear_vertical_sin_high_thre", C.c_float),
+        ("linear_vertical_sin_low_thre", C.c_float),
+        ("planar_vertical_sin_high_thre", C.c_float),
+        ("planar_vertical_sin_low_thre", C.c_float),
+        ("fixed_num_downsampling", C.c_int32),
+        ("pillar_down_fixed_num", C.c_int32),
+        ("facade_down_fixed_num", C.c_int32),
+        ("beam_down_fixed_num", C.c_int32),
+        ("roof_down_fixed_num", C.c_int32),
+        ("unground_down_fixed_num", C.c_int32),
+        ("beam_height_max", C.c_float),
+        ("roof_height_min", C.c_float),
+        ("feature_pts_ratio_guess", C.c_float),
+        ("sharpen_with_nms", C.c_int32),
+        ("use_distance_adaptive_pca", C.c_int32),
+        ("random_seed", C.c_uint32),
+    ]
+
+
+class ClassifyOut(C.Structure):
+    _fields_ = [
+        ("rows", C.POINTER(C.c_float) * OUT_COUNT),
+        ("cap", C.c_size_t),
+        ("n", C.c_size_t * OUT_COUNT),
+    ]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
 
 # every symbol include/mulls_b200/abi.h declares
@@ -154,6 +200,8 @@ EXPORTED_SYMBOLS = (
     "mulls_map_get_info",
     "mulls_map_download",
     "mulls_icp_run_to_map",
+    "mulls_classify_default_params",
+    "mulls_classify_nground",
     "mulls_set_tunable",
 )
 
@@ -224,6 +272,10 @@ def load_library() -> C.CDLL:
     lib.mulls_icp_run_to_map.restype = C.c_int
     lib.mulls_icp_run_to_map.argtypes = [vp, vp, C.POINTER(CloudView), C.POINTER(IcpParams), C.POINTER(C.c_double),
                                          C.POINTER(IcpResult), C.POINTER(IcpTrace)]
+    lib.mulls_classify_default_params.restype = None
+    lib.mulls_classify_default_params.argtypes = [C.POINTER(ClassifyParams)]
+    lib.mulls_classify_nground.restype = C.c_int
+    lib.mulls_classify_nground.argtypes = [vp, CloudView, C.POINTER(ClassifyParams), C.POINTER(ClassifyOut)]
     _LIB = lib
     return lib
 
@@ -337,3 +389,52 @@ def map_info_to_dict(info: MapInfo) -> dict:
         "feature_point_num": int(info.feature_point_num),
         "ms_update": float(info.ms_update),
     }
+
+
+def default_classify_params() -> ClassifyParams:
+    """Defaults of classify_nground_pts (cfilter.hpp:2070-2081) / extract_semantic_pts (:2295-2318) — pure Python."""
+    p = ClassifyParams()
+    p.neighbor_searching_radius = 1.0
+    p.neighbor_k = 50
+    p.neigh_k_min = 8
+    p.pca_down_rate = 1
+    p.edge_thre = 0.65
+    p.planar_thre = 0.65
+    p.edge_thre_down = 0.75
+    p.planar_thre_down = 0.75
+    p.extract_vertex_points_method = 2
+    p.curvature_thre = 0.12
+    p.vertex_curvature_non_max_radius = 1.5
+    p.linear_vertical_sin_high_thre = 0.94
+    p.linear_vertical_sin_low_thre = 0.17
+    p.planar_vertical_sin_high_thre = 0.98
+    p.planar_vertical_sin_low_thre = 0.34
+    p.fixed_num_downsampling = 0
+    p.pillar_down_fixed_num = 200
+    p.facade_down_fixed_num = 800
+    p.beam_down_fixed_num = 200
+    p.roof_down_fixed_num = 100
+    p.unground_down_fixed_num = 20000
+    p.beam_height_max = float(np.finfo(np.float32).max)
+    p.roof_height_min = -float(np.finfo(np.float32).max)
+    p.feature_pts_ratio_guess = 0.3
+    p.sharpen_with_nms = 1
+    p.use_distance_adaptive_pca = 0
+    p.random_seed = 0
+    return p
+
+
+def classify_call(fn, handle, cloud: np.ndarray, params: ClassifyParams) -> dict:
+    """Shared marshalling of mulls_classify_nground / its CPU restatement: returns {name: (n,12) float32}."""
+    cloud = as_aos48(cloud)
+    n = cloud.shape[0]
+    bufs = [np.zeros((max(n, 1), 12), np.float32) for _ in range(OUT_COUNT)]
+    out = ClassifyOut()
+    for k in range(OUT_COUNT):
+        out.rows[k] = bufs[k].ctypes.data_as(C.POINTER(C.c_float))
+    out.cap = max(n, 1)
+    args = ([handle] if handle is not None else []) + [cloud_view(cloud), C.byref(params), C.byref(out)]
+    rc = fn(*args)
+    if rc != 0:
+        return {"rc": rc}
+    return {OUT_NAMES[k]: np.ascontiguousarray(bufs[k][: out.n[k]]) for k in range(OUT_COUNT)}

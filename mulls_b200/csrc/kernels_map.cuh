@@ -293,15 +293,16 @@ __global__ void __launch_bounds__(kMapBlock) k_map_revector(const float4 *in, ui
         bool keep = false;
         MapRow r;
         if (i < n && F.pt_num[i] >= k_min) {
-            const float l1 = F.eigenvalues[3 * (size_t)i], l2 = F.eigenvalues[3 * (size_t)i + 1];
-            const float linear_2 = (l1 - l2) / l1;
+            // pca_feature_t keeps the eigenvalues and the ratios as double (pca.hpp:23-44, :425)
+            const double l1 = F.eigenvalues[3 * (size_t)i], l2 = F.eigenvalues[3 * (size_t)i + 1];
+            const double linear_2 = (l1 - l2) / l1;
             const float pz = fabsf(F.principal[3 * (size_t)i + 2]);
-            if (linear_2 > min_linearity && (pz > sin_high || pz < sin_low)) {
+            if (linear_2 > (double)min_linearity && (pz > sin_high || pz < sin_low)) {
                 keep = true;
                 const float4 *p = in + 3 * (size_t)i;
                 r.a = p[0], r.c = p[2];
                 r.b = make_float4(F.principal[3 * (size_t)i], F.principal[3 * (size_t)i + 1], F.principal[3 * (size_t)i + 2], 0.0f);
-                r.c.y = linear_2;
+                r.c.y = (float)linear_2;
             }
         }
         const uint32_t slot = map_tile_slot(keep, s_warp, &s_total);

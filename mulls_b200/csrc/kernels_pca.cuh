@@ -27,7 +27,12 @@ struct PcaArgs {
     int stride;     // pca_down_rate
     float *eigenvalues, *principal, *normal; // [n][3], indexed by ORIGINAL point index
     int *pt_num;                             // [n]
+    // optional (classification, needs 1 <= k <= kPcaListCap): the neighbour list of every query as radiusSearch returns
+    // it — ORIGINAL indices sorted by (distance, index), bit 31 = close_to_query_point (pca.hpp:337) — and, with it,
+    // pcl::PCA's float mean / covariance accumulated in exactly that order (bit-reproducible against the CPU path)
+    uint32_t *nbr; // [n][k]
 };
+constexpr int kPcaListCap = 64;
 
 __device__ inline void jacobi_eig3(double A[3][3], double w[3], double V[3][3]) {
     for (int i = 0; i < 3; ++i)
@@ -59,6 +64,26 @@ __device__ inline void jacobi_eig3(double A[3][3], double w[3], double V[3][3]) 
             }
     }
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+// eigen-pairs of the 3x3 covariance in descending order -> eigenvalues, principal direction, normal = col0 x col1
+__device__ inline void pca_finish(double Am[3][3], const PcaArgs &P, int orig) {
+    double w[3], V[3][3];
+    jacobi_eig3(Am, w, V);
+    int o0 = 0, o1 = 1, o2 = 2; // descending eigenvalues
+    if (w[o0] < w[o1]) { int t = o0; o0 = o1; o1 = t; }
+    if (w[o0] < w[o2]) { int t = o0; o0 = o2; o2 = t; }
+    if (w[o1] < w[o2]) { int t = o1; o1 = o2; o2 = t; }
+    const double e0[3] = {V[0][o0], V[1][o0], V[2][o0]}, e1[3] = {V[0][o1], V[1][o1], V[2][o1]};
+    const double e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    const double n0 = sqrt(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]);
+    const double n2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+    const double ww[3] = {w[o0], w[o1], w[o2]};
+    for (int d = 0; d < 3; ++d) {
+        P.eigenvalues[3 * orig + d] = (float)ww[d];
+        P.principal[3 * orig + d] = (float)(e0[d] / n0);
+        P.normal[3 * orig + d] = (float)(e2[d] / n2);
+    }
 }
 
 // warp-wide: number of list entries with key < v (keys are the uint bit patterns of non-negative floats)
@@ -231,8 +256,66 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca(DeviceArrays A, PcaArgs 
         return __float_as_int(__ldg(&nrm[idxs[i]]).w) <= tie_limit;
     };
     if (lane == 0) P.pt_num[orig] = n_sel;
+    __shared__ uint32_t s_lkey[kPcaWarps][kPcaListCap];
+    __shared__ int s_lorig[kPcaWarps][kPcaListCap];
+    __shared__ float s_lxyz[kPcaWarps][kPcaListCap][3];
+    __shared__ uint8_t s_lrank[kPcaWarps][kPcaListCap];
+    const bool lists = P.nbr != nullptr && n_sel <= kPcaListCap;
+    if (lists) {
+        // compact the selected entries, rank them by (distance, original index), store them in that order
+        int cnt = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            const bool sel = i < m && selected(i);
+            const unsigned b = __ballot_sync(0xffffffffu, sel);
+            const int off = cnt + __popc(b & ((1u << lane) - 1u));
+            if (sel && off < kPcaListCap) {
+                const float4 q = __ldg(&pos[idxs[i]]);
+                s_lkey[warp][off] = keys[i];
+                s_lorig[warp][off] = __float_as_int(__ldg(&nrm[idxs[i]]).w);
+                s_lxyz[warp][off][0] = q.x, s_lxyz[warp][off][1] = q.y, s_lxyz[warp][off][2] = q.z;
+            }
+            cnt += __popc(b);
+        }
+        __syncwarp();
+        for (int i = lane; i < n_sel; i += 32) {
+            const uint32_t ki = s_lkey[warp][i];
+            const int oi = s_lorig[warp][i];
+            int rank = 0;
+            for (int t = 0; t < n_sel; ++t) {
+                const uint32_t kt = s_lkey[warp][t];
+                rank += (kt < ki || (kt == ki && s_lorig[warp][t] < oi)) ? 1 : 0;
+            }
+            s_lrank[warp][rank] = (uint8_t)i;
+            const bool close = (double)__uint_as_float(ki) < 0.64 * (double)P.radius * (double)P.radius;
+            P.nbr[(size_t)orig * P.k + rank] = (uint32_t)oi | (close ? 0x80000000u : 0u);
+        }
+        __syncwarp();
+    }
     if (n_sel <= 3) { // pca.hpp:396-397: no feature for tiny neighbourhoods
         if (lane < 3) P.eigenvalues[3 * orig + lane] = P.principal[3 * orig + lane] = P.normal[3 * orig + lane] = 0.f;
+        return;
+    }
+    if (lists) {
+        if (lane == 0) { // pcl::PCA: float centroid, float covariance / (n-1), neighbours in radiusSearch order
+            float mu[3] = {0.f, 0.f, 0.f};
+            for (int t = 0; t < n_sel; ++t) {
+                const float *q = s_lxyz[warp][s_lrank[warp][t]];
+                mu[0] += q[0], mu[1] += q[1], mu[2] += q[2];
+            }
+            mu[0] /= (float)n_sel, mu[1] /= (float)n_sel, mu[2] /= (float)n_sel;
+            float c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+            for (int t = 0; t < n_sel; ++t) {
+                const float *q = s_lxyz[warp][s_lrank[warp][t]];
+                const float dx = q[0] - mu[0], dy = q[1] - mu[1], dz = q[2] - mu[2];
+                c00 += dx * dx, c01 += dx * dy, c02 += dx * dz, c11 += dy * dy, c12 += dy * dz, c22 += dz * dz;
+            }
+            const float dn = (float)(n_sel - 1);
+            double Am[3][3] = {{(double)(c00 / dn), (double)(c01 / dn), (double)(c02 / dn)},
+                               {(double)(c01 / dn), (double)(c11 / dn), (double)(c12 / dn)},
+                               {(double)(c02 / dn), (double)(c12 / dn), (double)(c22 / dn)}};
+            pca_finish(Am, P, orig);
+        }
         return;
     }
     // mean, then covariance / (n-1)
@@ -266,22 +349,7 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca(DeviceArrays A, PcaArgs 
     if (lane == 0) {
         const double inv = 1.0 / (double)(n_sel - 1);
         double Am[3][3] = {{c00 * inv, c01 * inv, c02 * inv}, {c01 * inv, c11 * inv, c12 * inv}, {c02 * inv, c12 * inv, c22 * inv}};
-        double w[3], V[3][3];
-        jacobi_eig3(Am, w, V);
-        int o0 = 0, o1 = 1, o2 = 2; // descending eigenvalues
-        if (w[o0] < w[o1]) { int t = o0; o0 = o1; o1 = t; }
-        if (w[o0] < w[o2]) { int t = o0; o0 = o2; o2 = t; }
-        if (w[o1] < w[o2]) { int t = o1; o1 = o2; o2 = t; }
-        const double e0[3] = {V[0][o0], V[1][o0], V[2][o0]}, e1[3] = {V[0][o1], V[1][o1], V[2][o1]};
-        const double e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
-        const double n0 = sqrt(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]);
-        const double n2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
-        const double ww[3] = {w[o0], w[o1], w[o2]};
-        for (int d = 0; d < 3; ++d) {
-            P.eigenvalues[3 * orig + d] = (float)ww[d];
-            P.principal[3 * orig + d] = (float)(e0[d] / n0);
-            P.normal[3 * orig + d] = (float)(e2[d] / n2);
-        }
+        pca_finish(Am, P, orig);
     }
 }
 

@@ -15,6 +15,7 @@
 #include "kernels_iterate.cuh"
 #include "kernels_pca.cuh"
 #include "kernels_map.cuh"
+#include "kernels_classify.cuh"
 
 using namespace mulls;
 
@@ -65,6 +66,9 @@ struct mulls_ctx {
     // PCA scratch
     void *pca_buf = nullptr;
     size_t pca_buf_bytes = 0;
+    // classification scratch (mulls_classify_nground)
+    void *cls_buf = nullptr;
+    size_t cls_buf_bytes = 0;
     // the local map whose clouds the target slices of pair 0 currently index (set by mulls_icp_run_to_map, cleared
     // by any other upload): what block1->tree_* are to MapManager::map_based_dynamic_close_removal
     const mulls_map *tree_map = nullptr;
@@ -132,6 +136,7 @@ void mulls_destroy(mulls_ctx *ctx) {
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->cub_temp) cudaFree(ctx->cub_temp);
     if (ctx->pca_buf) cudaFree(ctx->pca_buf);
+    if (ctx->cls_buf) cudaFree(ctx->cls_buf);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_running) cudaFreeHost(ctx->h_running);
@@ -833,7 +838,7 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
 // PCA features of one cloud (host rows, or rows already in HBM) into ctx->pca_buf; `args` receives the device arrays.
 // Nothing is synchronised: the caller consumes the arrays on ctx->stream.
 static int pca_on_device(mulls_ctx *ctx, mulls_cloud_view cloud, bool cloud_on_device, float radius, int k, int stride,
-                         PcaArgs &args, uint64_t &launches) {
+                         PcaArgs &args, uint64_t &launches, uint32_t *nbr = nullptr) {
     // the cloud becomes the only target class of a one-pair batch: same filter-less ingest, same grid
     mulls_icp_params P;
     mulls_icp_default_params(&P);
@@ -868,6 +873,7 @@ static int pca_on_device(mulls_ctx *ctx, mulls_cloud_view cloud, bool cloud_on_d
     args.principal = args.eigenvalues + 3 * n;
     args.normal = args.principal + 3 * n;
     args.pt_num = (int *)(args.normal + 3 * n);
+    args.nbr = nbr;
     CK(cudaMemsetAsync(ctx->pca_buf, 0, std::max<size_t>(bytes, 16), st));
     if (n) {
         k_pca<<<(unsigned)ceil_div(n, kPcaWarps), kPcaWarps * 32, 0, st>>>(A, args);
@@ -1267,6 +1273,189 @@ int mulls_icp_run_to_map(mulls_ctx *ctx, mulls_map *m, const mulls_cloud_view sr
         ctx->tree_epoch = m->epoch;
     }
     return rc;
+}
+
+// ================================================================================================
+// Non-ground feature classification (CFilter::classify_nground_pts, cfilter.hpp:2058-2290)
+// ================================================================================================
+void mulls_classify_default_params(mulls_classify_params *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->neighbor_searching_radius = 1.0f;
+    p->neighbor_k = 50;
+    p->neigh_k_min = 8;
+    p->pca_down_rate = 1;
+    p->edge_thre = 0.65f;
+    p->planar_thre = 0.65f;
+    p->edge_thre_down = 0.75f;
+    p->planar_thre_down = 0.75f;
+    p->extract_vertex_points_method = 2;
+    p->curvature_thre = 0.12f;
+    p->vertex_curvature_non_max_radius = 1.5f;
+    p->linear_vertical_sin_high_thre = 0.94f;
+    p->linear_vertical_sin_low_thre = 0.17f;
+    p->planar_vertical_sin_high_thre = 0.98f;
+    p->planar_vertical_sin_low_thre = 0.34f;
+    p->fixed_num_downsampling = 0;
+    p->pillar_down_fixed_num = 200;
+    p->facade_down_fixed_num = 800;
+    p->beam_down_fixed_num = 200;
+    p->roof_down_fixed_num = 100;
+    p->unground_down_fixed_num = 20000;
+    p->beam_height_max = FLT_MAX;
+    p->roof_height_min = -FLT_MAX;
+    p->feature_pts_ratio_guess = 0.3f;
+    p->sharpen_with_nms = 1;
+    p->use_distance_adaptive_pca = 0;
+    p->random_seed = 0;
+}
+
+int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_classify_params *params,
+                           mulls_classify_out *out) {
+    if (!ctx || !params || !out || (cloud_in.n > 0 && !cloud_in.aos48)) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    const mulls_classify_params &P = *params;
+    if (P.use_distance_adaptive_pca) {
+        ctx->err = "mulls_classify_nground: use_distance_adaptive_pca is not implemented";
+        return MULLS_E_UNSUPPORTED;
+    }
+    if (P.neighbor_k < 1 || P.neighbor_k > kPcaListCap || !(P.neighbor_searching_radius > 0.f)) {
+        ctx->err = "mulls_classify_nground: neighbor_k must be 1..64 and the radius positive";
+        return MULLS_E_ARG;
+    }
+    for (int k = 0; k < MULLS_OUT_COUNT; ++k) out->n[k] = 0;
+    const size_t n0 = cloud_in.n;
+    if (n0 == 0) return MULLS_OK;
+    if (n0 > ctx->max_tgt) {
+        ctx->err = "mulls_classify_nground: cloud exceeds max_tgt_pts of the context";
+        return MULLS_E_CAPACITY;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // :2086-2087 random_downsample_pcl(cloud_in, unground_down_fixed_num): the size it leaves is known up front
+    size_t n = n0;
+    const bool sample_in = P.fixed_num_downsampling && P.unground_down_fixed_num >= 0 && n0 > (size_t)P.unground_down_fixed_num;
+    if (sample_in) n = (size_t)P.unground_down_fixed_num;
+    const int stride = P.pca_down_rate > 0 ? P.pca_down_rate : 1;
+    // scratch layout
+    const size_t row_b = 48;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_in = take(n0 * row_b), o_rows = take(n0 * row_b);
+    size_t o_cls[4], o_srt[4], o_dn[4], o_dn2[4];
+    for (int c = 0; c < 4; ++c) o_cls[c] = take(n0 * row_b), o_srt[c] = take(n0 * row_b), o_dn[c] = take(n0 * row_b), o_dn2[c] = take(n0 * row_b);
+    const size_t o_sect = take(2 * n0 * row_b), o_vrows = take(n0 * row_b), o_vertex = take(n0 * row_b);
+    const size_t o_sel = take(4 * n0 * sizeof(float4)), o_nbr = take(n0 * (size_t)P.neighbor_k * sizeof(uint32_t));
+    const size_t o_l0 = take(n0), o_l = take(n0), o_df = take(n0), o_s4 = take(n0), o_vf = take(n0), o_st = take(sizeof(ClsState));
+    if (off > ctx->cls_buf_bytes) {
+        if (ctx->cls_buf) cudaFree(ctx->cls_buf);
+        ctx->cls_buf = nullptr;
+        ctx->cls_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->cls_buf, off));
+        ctx->cls_buf_bytes = off;
+    }
+    char *base = (char *)ctx->cls_buf;
+    ClsArgs C;
+    std::memset(&C, 0, sizeof(C));
+    C.P = P;
+    C.n = (uint32_t)n;
+    C.stride = stride;
+    C.rows = (float4 *)(base + o_rows);
+    for (int c = 0; c < 4; ++c) {
+        C.cls[c] = (float4 *)(base + o_cls[c]);
+        C.cls_sorted[c] = (float4 *)(base + o_srt[c]);
+        C.down[c] = (float4 *)(base + o_dn[c]);
+        C.down2[c] = (float4 *)(base + o_dn2[c]);
+    }
+    C.sect = (float4 *)(base + o_sect);
+    C.vrows = (float4 *)(base + o_vrows);
+    C.vertex = (float4 *)(base + o_vertex);
+    C.sel_pos = (float4 *)(base + o_sel);
+    C.label0 = (uint8_t *)(base + o_l0);
+    C.label = (uint8_t *)(base + o_l);
+    C.downflag = (uint8_t *)(base + o_df);
+    C.st4 = (uint8_t *)(base + o_s4);
+    C.vflag = (uint8_t *)(base + o_vf);
+    C.st = (ClsState *)(base + o_st);
+    uint32_t *nbr = (uint32_t *)(base + o_nbr);
+    CK(cudaEventRecord(ctx->ev_begin, st));
+    CK(cudaMemsetAsync(C.st, 0, sizeof(ClsState), st));
+    uint64_t launches = 0;
+    if (sample_in) {
+        CK(cudaMemcpyAsync(base + o_in, cloud_in.aos48, n0 * row_b, cudaMemcpyHostToDevice, st));
+        k_rows_sample<<<1, kClsBlock, 0, st>>>((const float4 *)(base + o_in), (uint32_t)n0, P.unground_down_fixed_num, P.random_seed,
+                                               18u, C.rows);
+        ++launches;
+    } else {
+        CK(cudaMemcpyAsync(C.rows, cloud_in.aos48, n0 * row_b, cudaMemcpyHostToDevice, st));
+    }
+    ClsState hs;
+    std::memset(&hs, 0, sizeof(hs));
+    if (n > 0) {
+        // :2089-2097 PCA of every pca_down_rate-th point, with the neighbour lists
+        mulls_cloud_view v{(const float *)C.rows, n};
+        const int rc = pca_on_device(ctx, v, true, P.neighbor_searching_radius, P.neighbor_k, stride, C.F, launches, nbr);
+        if (rc != MULLS_OK) return rc;
+        C.keys_a = ctx->A.keys_a;
+        C.keys_b = ctx->A.keys_b;
+        const unsigned gb = (unsigned)ceil_div(n, 256);
+        k_cls_label<<<gb, 256, 0, st>>>(C);
+        k_cls_compact<<<8, kClsBlock, 0, st>>>(C);
+        k_cls_promote<<<1, kClsBlock, 0, st>>>(C);
+        k_cls_compact2<<<4, kClsBlock, 0, st>>>(C);
+        k_cls_encode<<<gb, 256, 0, st>>>(C);
+        k_cls_compact_vertex<<<1, kClsBlock, 0, st>>>(C);
+        launches += 6;
+        if (P.sharpen_with_nms) {
+            CK(cudaMemsetAsync(C.keys_a, 0xff, n * sizeof(uint64_t), st));
+            k_nms_keys<<<dim3(gb, 4), 256, 0, st>>>(C);
+            size_t bytes = ctx->cub_temp_bytes;
+            CK(cub::DeviceRadixSort::SortKeys(ctx->cub_temp, bytes, C.keys_a, C.keys_b, (int)n, 0, 64, st));
+            k_nms_gather<<<gb, 256, 0, st>>>(C);
+            k_nms_select<<<4, kClsBlock, 0, st>>>(C);
+            launches += 3;
+        }
+        if (P.fixed_num_downsampling) {
+            k_cls_fixed<<<4, kClsBlock, 0, st>>>(C);
+            ++launches;
+        }
+        CK(cudaMemcpyAsync(&hs, C.st, sizeof(ClsState), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (n > 0 && ctx->h_flags[1]) {
+        ctx->err = "hash pool exhausted";
+        return MULLS_E_CAPACITY;
+    }
+    // results
+    const float4 *src[MULLS_OUT_COUNT];
+    size_t cnt[MULLS_OUT_COUNT];
+    for (int c = 0; c < 4; ++c) {
+        src[c] = hs.nms_ran[c] ? C.cls_sorted[c] : C.cls[c];
+        cnt[c] = hs.n_cls2[c];
+        src[4 + c] = P.fixed_num_downsampling ? C.down2[c] : C.down[c];
+        cnt[4 + c] = P.fixed_num_downsampling ? hs.n_down2[c] : hs.n_down[c];
+    }
+    src[MULLS_OUT_VERTEX] = C.vertex, cnt[MULLS_OUT_VERTEX] = hs.n_vertex;
+    src[MULLS_OUT_UNGROUND] = C.rows, cnt[MULLS_OUT_UNGROUND] = n;
+    for (int k = 0; k < MULLS_OUT_COUNT; ++k) {
+        out->n[k] = cnt[k];
+        if (!out->rows[k] || cnt[k] == 0) continue;
+        if (cnt[k] > out->cap) {
+            ctx->err = "mulls_classify_nground: output buffer too small";
+            return MULLS_E_CAPACITY;
+        }
+        CK(cudaMemcpyAsync(out->rows[k], src[k], cnt[k] * row_b, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev_end, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats = mulls_run_stats();
+    ctx->stats.kernel_launches = launches;
+    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev_begin, ctx->ev_end);
+    return MULLS_OK;
 }
 
 } // extern "C"

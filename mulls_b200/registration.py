@@ -204,6 +204,14 @@ class Context:
                                                 C.byref(out)))
         return {"eigenvalues": ev, "principal": pr, "normal": nr, "pt_num": cnt}
 
+    def classify_nground(self, cloud_in: np.ndarray, params: abi.ClassifyParams) -> dict:
+        """CFilter::classify_nground_pts (cfilter.hpp:2058-2290) on the GPU: {"pillar": (n,12) rows, "beam", "facade",
+        "roof", "pillar_down", ..., "vertex" (the new keypoints), "unground" (cloud_in as the call leaves it)}."""
+        res = abi.classify_call(self.lib.mulls_classify_nground, self.handle, cloud_in, params)
+        if "rc" in res:
+            self._check(res["rc"])
+        return res
+
     def stats(self) -> dict:
         s = abi.RunStats()
         self._check(self.lib.mulls_get_stats(self.handle, C.byref(s)))

@@ -1342,9 +1342,101 @@ static void jacobi_eig3(const double Ain[3][3], double w[3], double V[3][3]) {
 }
 
 
-} // namespace
-extern "C" int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out);
-namespace {
+// pca.hpp:294-354. Outputs as mulls_pca_out; points skipped by the stride get pt_num = 0. `lists` (optional) receives
+// the neighbour list of every query as radiusSearch returns it: (squared distance, index) sorted ascending.
+typedef std::vector<std::pair<float, int>> NbrList;
+static int pca_core(const Cloud &C, float radius, int k, int stride, mulls_pca_out *out, std::vector<NbrList> *lists) {
+    const long n = (long)C.size();
+    const float r2 = (float)((double)radius * (double)radius); // KdTreeFLANN::radiusSearch casts radius*radius to float
+    // brute force through a uniform grid (oracle: clarity over speed)
+    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+    for (long i = 0; i < n; ++i) {
+        mn[0] = std::min(mn[0], C[i].x);
+        mn[1] = std::min(mn[1], C[i].y);
+        mn[2] = std::min(mn[2], C[i].z);
+        mx[0] = std::max(mx[0], C[i].x);
+        mx[1] = std::max(mx[1], C[i].y);
+        mx[2] = std::max(mx[2], C[i].z);
+    }
+    const float h = radius * 1.0001f;
+    int dims[3];
+    for (int d = 0; d < 3; ++d) dims[d] = std::max(1, (int)std::floor((mx[d] - mn[d]) / h) + 1);
+    std::vector<std::vector<int>> cells((size_t)dims[0] * dims[1] * dims[2]);
+    auto cell_of = [&](const Pt &p, int c[3]) {
+        c[0] = std::min(dims[0] - 1, std::max(0, (int)std::floor((p.x - mn[0]) / h)));
+        c[1] = std::min(dims[1] - 1, std::max(0, (int)std::floor((p.y - mn[1]) / h)));
+        c[2] = std::min(dims[2] - 1, std::max(0, (int)std::floor((p.z - mn[2]) / h)));
+    };
+    for (long i = 0; i < n; ++i) {
+        int c[3];
+        cell_of(C[i], c);
+        cells[((size_t)c[2] * dims[1] + c[1]) * dims[0] + c[0]].push_back((int)i);
+    }
+    if (lists) lists->assign((size_t)n, NbrList());
+    for (long i = 0; i < n; ++i) {
+        out->pt_num[i] = 0;
+        for (int d = 0; d < 3; ++d) out->eigenvalues[3 * i + d] = out->principal[3 * i + d] = out->normal[3 * i + d] = 0.f;
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < n; i += stride) {
+        int c[3];
+        cell_of(C[i], c);
+        std::vector<std::pair<float, int>> nb;
+        float q[3] = {C[i].x, C[i].y, C[i].z};
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    int cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
+                    if (cx < 0 || cy < 0 || cz < 0 || cx >= dims[0] || cy >= dims[1] || cz >= dims[2]) continue;
+                    const std::vector<int> &cell = cells[((size_t)cz * dims[1] + cy) * dims[0] + cx];
+                    for (size_t t = 0; t < cell.size(); ++t) {
+                        float d2 = KdTree::flann_l2(q, C[cell[t]]);
+                        if (d2 < r2) nb.push_back(std::make_pair(d2, cell[t])); // FLANN result sets keep dist < radius
+                    }
+                }
+        std::sort(nb.begin(), nb.end());
+        if (k > 0 && (int)nb.size() > k) nb.resize(k);
+        const int m = (int)nb.size();
+        out->pt_num[i] = m;
+        if (lists) (*lists)[i] = nb;
+        if (m <= 3) continue; // pca.hpp:396-397
+        // pcl::PCA [3P]: float centroid, float covariance / (n-1)
+        float mu[3] = {0, 0, 0};
+        for (int t = 0; t < m; ++t) {
+            mu[0] += C[nb[t].second].x;
+            mu[1] += C[nb[t].second].y;
+            mu[2] += C[nb[t].second].z;
+        }
+        mu[0] /= (float)m;
+        mu[1] /= (float)m;
+        mu[2] /= (float)m;
+        float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int t = 0; t < m; ++t) {
+            float d[3] = {C[nb[t].second].x - mu[0], C[nb[t].second].y - mu[1], C[nb[t].second].z - mu[2]};
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) cov[a][b] += d[a] * d[b];
+        }
+        double A[3][3], w[3], V[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) A[a][b] = (double)(cov[a][b] / (float)(m - 1));
+        jacobi_eig3(A, w, V);
+        int ord[3] = {0, 1, 2};
+        std::sort(ord, ord + 3, [&](int a, int b) { return w[a] > w[b]; });
+        double e0[3] = {V[0][ord[0]], V[1][ord[0]], V[2][ord[0]]};
+        double e1[3] = {V[0][ord[1]], V[1][ord[1]], V[2][ord[1]]};
+        double e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+        double n0 = std::sqrt(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]);
+        double n2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+        for (int d = 0; d < 3; ++d) {
+            out->eigenvalues[3 * i + d] = (float)w[ord[d]];
+            out->principal[3 * i + d] = (float)(e0[d] / n0);
+            out->normal[3 * i + d] = (float)(e2[d] / n2);
+        }
+    }
+    return 0;
+}
+
+
 
 // ---------------------------------------------------------------------------------------------
 // MapManager::update_local_map, src/map_manager.cpp:17-145.
@@ -1404,22 +1496,22 @@ static void update_cloud_vectors(Cloud &pts, float pca_radius, int pca_k, int k_
                                  float min_linearity) {
     if (pts.empty()) return;
     const size_t n = pts.size();
-    std::vector<float> rows(12 * n), ev(3 * n), pr(3 * n), nr(3 * n);
+    std::vector<float> ev(3 * n), pr(3 * n), nr(3 * n);
     std::vector<int32_t> cnt(n);
-    store_cloud(pts, rows.data());
-    mulls_cloud_view v = {rows.data(), n};
     mulls_pca_out out = {ev.data(), pr.data(), nr.data(), cnt.data()};
-    orc_pca_features(v, pca_radius, pca_k, 1, &out); // get_pc_pca_feature(feature_pts, features, radius, k, k_min)
+    pca_core(pts, pca_radius, pca_k, 1, &out, nullptr); // get_pc_pca_feature(feature_pts, features, radius, k, k_min)
     Cloud keep;
     for (size_t i = 0; i < n; ++i) {
         if (cnt[i] < k_min) continue;
-        const float linear_2 = (ev[3 * i] - ev[3 * i + 1]) / ev[3 * i]; // pca.hpp:425
+        // pca.hpp:33-44, :425: the eigenvalues are stored as double, the ratio is a double
+        const double l1 = ev[3 * i], l2 = ev[3 * i + 1];
+        const double linear_2 = (l1 - l2) / l1;
         if (!(linear_2 > min_linearity)) continue;
         const float pz = std::fabs(pr[3 * i + 2]);
         if (pz > sin_high || pz < sin_low) {
             Pt p = pts[i];
             p.nx = pr[3 * i], p.ny = pr[3 * i + 1], p.nz = pr[3 * i + 2]; // assign_normal(pt, feature, false)
-            p.curvature = linear_2;                                      // :283
+            p.curvature = (float)linear_2;                               // :283
             keep.push_back(p);
         }
     }
@@ -1509,6 +1601,268 @@ static void map_update(Cloud map[6], Mat4 &map_pose, Cloud scan[6], const Mat4 &
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CFilter::classify_nground_pts, cfilter.hpp:2058-2290 (+ encode_stable_points :1071-1181, non_max_suppress
+// :1243-1312, xy_normal_balanced_downsample :551-602, random_downsample_pcl :606-628). Works on full 48-byte rows:
+// the stage keeps scores in PCL's padding float normal[3] (row[7]).
+// ---------------------------------------------------------------------------------------------
+struct Row {
+    float f[12];
+};
+typedef std::vector<Row> Rows;
+enum { RX = 0, RY = 1, RZ = 2, RNX = 4, RNY = 5, RNZ = 6, RN3 = 7, RINT = 8, RCURV = 9 };
+
+struct PcaFeat { // pca_feature_t (pca.hpp:23-54); value-initialised (all zero) until get_pca_feature fills it
+    int pt_num = 0;
+    double curvature = 0, linear_2 = 0, planar_2 = 0;
+    float pdir[3] = {0, 0, 0}, ndir[3] = {0, 0, 0};
+    std::vector<int> nbr;        // neighbor_indices (only when pt_num > 3, :431)
+    std::vector<char> close;     // close_to_query_point
+};
+
+static void rows_random_downsample(Rows &r, int keep_number, uint32_t seed, uint32_t cloud_id) {
+    if (keep_number < 0) return;
+    if ((long long)r.size() <= (long long)keep_number) return;
+    if (keep_number == 0) {
+        r.clear();
+        return;
+    }
+    std::vector<uint64_t> keys(r.size());
+    for (size_t i = 0; i < r.size(); ++i) keys[i] = sample_key(seed, cloud_id, (uint32_t)i);
+    std::vector<uint64_t> sorted = keys;
+    std::nth_element(sorted.begin(), sorted.begin() + (keep_number - 1), sorted.end());
+    const uint64_t thr = sorted[keep_number - 1];
+    Rows out;
+    for (size_t i = 0; i < r.size(); ++i)
+        if (keys[i] <= thr) out.push_back(r[i]);
+    r.swap(out);
+}
+
+// pca.hpp:437-454
+static void assign_normal(Row &pt, const PcaFeat &f, bool is_plane_feature) {
+    if (is_plane_feature) {
+        pt.f[RNX] = f.ndir[0], pt.f[RNY] = f.ndir[1], pt.f[RNZ] = f.ndir[2];
+        pt.f[RN3] = (float)f.planar_2;
+    } else {
+        pt.f[RNX] = f.pdir[0], pt.f[RNY] = f.pdir[1], pt.f[RNZ] = f.pdir[2];
+        pt.f[RN3] = (float)f.linear_2;
+    }
+}
+
+// cfilter.hpp:1243-1312 non_max_suppress(cloud_in, cloud_out, nms_radius). std::sort is not stable: ties on the score
+// are ordered by index here (oracle's convention, followed by the CUDA path). The kd-tree radius search keeps
+// d2 < (float)(r*r) with FLANN's L2_Simple distance.
+static bool non_max_suppress(Rows &cloud_in, Rows &cloud_out, float nms_radius) {
+    const int n = (int)cloud_in.size();
+    if (n < 10) return false;
+    std::stable_sort(cloud_in.begin(), cloud_in.end(), [](const Row &a, const Row &b) { return a.f[RN3] > b.f[RN3]; });
+    const float r2 = (float)((double)nms_radius * (double)nms_radius);
+    std::vector<char> visited(n, 0);
+    for (int id = 0; id < n; ++id) {
+        if (visited[id]) continue;
+        cloud_out.push_back(cloud_in[id]);
+        visited[id] = 1;
+        for (int j = 0; j < n; ++j) {
+            if (visited[j]) continue;
+            const float d0 = cloud_in[id].f[RX] - cloud_in[j].f[RX], d1 = cloud_in[id].f[RY] - cloud_in[j].f[RY],
+                        d2 = cloud_in[id].f[RZ] - cloud_in[j].f[RZ];
+            float r = 0.0f;
+            r += d0 * d0;
+            r += d1 * d1;
+            r += d2 * d2;
+            if (r < r2) visited[j] = 1;
+        }
+    }
+    return true;
+}
+
+// cfilter.hpp:551-602
+static void xy_normal_balanced_downsample(Rows &cloud, int keep_number_per_sector, int sector_num, uint32_t seed,
+                                          uint32_t cloud_id0) {
+    if ((long long)cloud.size() <= (long long)keep_number_per_sector) return;
+    std::vector<Rows> sectors(sector_num);
+    const double angle_per_sector = 360.0 / sector_num;
+    for (size_t i = 0; i < cloud.size(); ++i) {
+        double ang = std::atan2(cloud[i].f[RNY], cloud[i].f[RNX]);
+        if (ang < 0) ang += 2 * M_PI;
+        ang *= (180.0 / M_PI);
+        int sector_id = (int)(ang / angle_per_sector);
+        if (sector_id >= sector_num) sector_id = sector_num - 1; // ang == 360.0 indexes past the array in the reference
+        sectors[sector_id].push_back(cloud[i]);
+    }
+    Rows out;
+    for (int j = 0; j < sector_num; ++j) {
+        rows_random_downsample(sectors[j], keep_number_per_sector, seed, cloud_id0 + (uint32_t)j);
+        out.insert(out.end(), sectors[j].begin(), sectors[j].end());
+    }
+    cloud.swap(out);
+}
+
+static void classify_nground(Rows &cloud_in, const mulls_classify_params &P, Rows out[MULLS_OUT_COUNT]) {
+    Rows &pillar = out[MULLS_OUT_PILLAR], &beam = out[MULLS_OUT_BEAM], &facade = out[MULLS_OUT_FACADE], &roof = out[MULLS_OUT_ROOF];
+    Rows &pillar_down = out[MULLS_OUT_PILLAR_DOWN], &beam_down = out[MULLS_OUT_BEAM_DOWN],
+         &facade_down = out[MULLS_OUT_FACADE_DOWN], &roof_down = out[MULLS_OUT_ROOF_DOWN], &vertex = out[MULLS_OUT_VERTEX];
+    // :2086-2087
+    if (P.fixed_num_downsampling) rows_random_downsample(cloud_in, P.unground_down_fixed_num, P.random_seed, 18);
+    const int n = (int)cloud_in.size();
+    // :2089-2097 get_pc_pca_feature(cloud_in, features, tree, radius, k, 1, pca_down_rate, ...)
+    Cloud C(n);
+    for (int i = 0; i < n; ++i) {
+        Pt p = {cloud_in[i].f[RX], cloud_in[i].f[RY], cloud_in[i].f[RZ], 0, 0, 0, 0, 0};
+        C[i] = p;
+    }
+    std::vector<float> ev(3 * (size_t)n + 1), pr(3 * (size_t)n + 1), nr(3 * (size_t)n + 1);
+    std::vector<int32_t> cnt((size_t)n + 1);
+    mulls_pca_out po = {ev.data(), pr.data(), nr.data(), cnt.data()};
+    std::vector<NbrList> lists;
+    const int stride = P.pca_down_rate > 0 ? P.pca_down_rate : 1;
+    pca_core(C, P.neighbor_searching_radius, P.neighbor_k, stride, &po, &lists);
+    std::vector<PcaFeat> feat(n);
+    const float radius = P.neighbor_searching_radius;
+    for (int i = 0; i < n; i += stride) {
+        PcaFeat &f = feat[i];
+        f.pt_num = cnt[i];
+        if (f.pt_num > 3) { // get_pca_feature, pca.hpp:390-434
+            const double l1 = ev[3 * i], l2 = ev[3 * i + 1], l3 = ev[3 * i + 2];
+            f.curvature = ((l1 + l2 + l3) == 0) ? 0 : l3 / (l1 + l2 + l3);
+            f.linear_2 = (l1 - l2) / l1;
+            f.planar_2 = (l2 - l3) / l1;
+            for (int d = 0; d < 3; ++d) f.pdir[d] = pr[3 * i + d], f.ndir[d] = nr[3 * i + d];
+            f.nbr.resize(f.pt_num);
+            f.close.resize(f.pt_num);
+            for (int j = 0; j < f.pt_num; ++j) {
+                f.nbr[j] = lists[i][j].second;
+                f.close[j] = (lists[i][j].first < 0.64 * radius * radius) ? 1 : 0; // pca.hpp:337
+            }
+        }
+        if (f.pt_num > 1) assign_normal(cloud_in[i], f, true); // min_k = 1, pca.hpp:346-347
+    }
+    // :2100-2166
+    std::vector<int> index_with_feature(n, 0); // 0 none, 1 pillar, 2 beam, 3 facade, 4 roof
+    for (int i = 0; i < n; ++i) {
+        const PcaFeat &f = feat[i];
+        if (f.pt_num > P.neigh_k_min) {
+            if (f.linear_2 > P.edge_thre) {
+                if (std::abs(f.pdir[2]) > P.linear_vertical_sin_high_thre) {
+                    assign_normal(cloud_in[i], f, false);
+                    pillar.push_back(cloud_in[i]);
+                    index_with_feature[i] = 1;
+                } else if (std::abs(f.pdir[2]) < P.linear_vertical_sin_low_thre && cloud_in[i].f[RZ] < P.beam_height_max) {
+                    assign_normal(cloud_in[i], f, false);
+                    beam.push_back(cloud_in[i]);
+                    index_with_feature[i] = 2;
+                }
+                if (!P.sharpen_with_nms && f.linear_2 > P.edge_thre_down) {
+                    if (std::abs(f.pdir[2]) > P.linear_vertical_sin_high_thre)
+                        pillar_down.push_back(cloud_in[i]);
+                    else if (std::abs(f.pdir[2]) < P.linear_vertical_sin_low_thre && cloud_in[i].f[RZ] < P.beam_height_max)
+                        beam_down.push_back(cloud_in[i]);
+                }
+            } else if (f.planar_2 > P.planar_thre) {
+                if (std::abs(f.ndir[2]) > P.planar_vertical_sin_high_thre && cloud_in[i].f[RZ] > P.roof_height_min) {
+                    assign_normal(cloud_in[i], f, true);
+                    roof.push_back(cloud_in[i]);
+                    index_with_feature[i] = 4;
+                } else if (std::abs(f.ndir[2]) < P.planar_vertical_sin_low_thre) {
+                    assign_normal(cloud_in[i], f, true);
+                    facade.push_back(cloud_in[i]);
+                    index_with_feature[i] = 3;
+                }
+                if (!P.sharpen_with_nms && f.planar_2 > P.planar_thre_down) {
+                    if (std::abs(f.ndir[2]) > P.planar_vertical_sin_high_thre && cloud_in[i].f[RZ] > P.roof_height_min)
+                        roof_down.push_back(cloud_in[i]);
+                    else if (std::abs(f.ndir[2]) < P.planar_vertical_sin_low_thre)
+                        facade_down.push_back(cloud_in[i]);
+                }
+            }
+        }
+    }
+    // :2169-2210
+    int method = P.extract_vertex_points_method;
+    if (P.curvature_thre < 1e-8) method = 0;
+    if (method == 2) {
+        const float vertex_feature_ratio_thre = P.feature_pts_ratio_guess / stride;
+        for (int i = 0; i < n; ++i) {
+            const PcaFeat &f = feat[i];
+            if (index_with_feature[i] == 0 && f.pt_num > P.neigh_k_min && f.curvature > P.curvature_thre) {
+                int geo_feature_point_count = 0;
+                for (size_t j = 0; j < f.nbr.size(); ++j)
+                    if (index_with_feature[f.nbr[j]]) geo_feature_point_count++;
+                if (1.0 * geo_feature_point_count / f.pt_num > vertex_feature_ratio_thre) {
+                    assign_normal(cloud_in[i], f, false);
+                    cloud_in[i].f[RN3] = (float)(5.0 * f.curvature);
+                    if (std::abs(f.pdir[2]) > P.linear_vertical_sin_high_thre) {
+                        pillar.push_back(cloud_in[i]);
+                        index_with_feature[i] = 1;
+                    } else if (std::abs(f.pdir[2]) < P.linear_vertical_sin_low_thre && cloud_in[i].f[RZ] < P.beam_height_max) {
+                        beam.push_back(cloud_in[i]);
+                        index_with_feature[i] = 2;
+                    }
+                }
+            }
+        }
+    }
+    // :2219-2223 encode_stable_points (:1071-1181)
+    {
+        const int min_neighbor_feature_pts = (int)(P.feature_pts_ratio_guess / stride * P.neighbor_k) - 1;
+        const float min_curvature = 0.3 * P.curvature_thre;
+        for (int i = 0; i < n; ++i) {
+            const PcaFeat &f = feat[i];
+            if (f.pt_num > P.neigh_k_min && f.pt_num > 3 && f.curvature > min_curvature) {
+                float accu_intensity = 0.0;
+                Row pt = cloud_in[i];
+                pt.f[RN3] = (float)f.curvature;
+                int cnt_all[5] = {0, 0, 0, 0, 0}, cnt_close[5] = {0, 0, 0, 0, 0}, cnt_far[5] = {0, 0, 0, 0, 0};
+                const int neighbor_total_count = (int)f.nbr.size();
+                for (int j = 0; j < neighbor_total_count; ++j) {
+                    const int lab = index_with_feature[f.nbr[j]];
+                    if (lab >= 1 && lab <= 4) {
+                        cnt_all[lab]++;
+                        if (f.close[j])
+                            cnt_close[lab]++;
+                        else
+                            cnt_far[lab]++;
+                    }
+                    accu_intensity += cloud_in[f.nbr[j]].f[RINT];
+                }
+                if (cnt_all[1] + cnt_all[2] + cnt_all[3] + cnt_all[4] < min_neighbor_feature_pts) continue;
+                int a[5], c[5], r[5];
+                for (int l = 1; l <= 4; ++l) {
+                    a[l] = 100 * cnt_all[l] / neighbor_total_count;
+                    c[l] = 100 * cnt_close[l] / neighbor_total_count;
+                    r[l] = 100 * cnt_far[l] / neighbor_total_count;
+                }
+                const int descriptor = a[1] * 1000000 + a[2] * 10000 + a[3] * 100 + a[4];
+                const int descriptor_1 = c[1] * 1000000 + c[2] * 10000 + c[3] * 100 + c[4];
+                const int descriptor_2 = r[1] * 1000000 + r[2] * 10000 + r[3] * 100 + r[4];
+                pt.f[RCURV] = descriptor;
+                pt.f[RNX] = descriptor_1;
+                pt.f[RNY] = descriptor_2;
+                pt.f[RINT] = accu_intensity / neighbor_total_count;
+                vertex.push_back(pt);
+            }
+        }
+    }
+    // :2229-2253
+    if (P.sharpen_with_nms) {
+        const float nms_radius = 0.25 * P.neighbor_searching_radius;
+        if (P.pillar_down_fixed_num > 0) non_max_suppress(pillar, pillar_down, nms_radius);
+        if (P.facade_down_fixed_num > 0) non_max_suppress(facade, facade_down, nms_radius);
+        if (P.beam_down_fixed_num > 0) non_max_suppress(beam, beam_down, nms_radius);
+        if (P.roof_down_fixed_num > 0) non_max_suppress(roof, roof_down, nms_radius);
+    }
+    // :2257-2267
+    if (P.fixed_num_downsampling) {
+        rows_random_downsample(pillar_down, P.pillar_down_fixed_num, P.random_seed, 19);
+        const int sector_num = 4;
+        xy_normal_balanced_downsample(facade_down, (int)(P.facade_down_fixed_num / sector_num), sector_num, P.random_seed, 20);
+        xy_normal_balanced_downsample(beam_down, (int)(P.beam_down_fixed_num / sector_num), sector_num, P.random_seed, 24);
+        rows_random_downsample(roof_down, P.roof_down_fixed_num, P.random_seed, 28);
+    }
+    out[MULLS_OUT_UNGROUND] = cloud_in;
+}
+
 } // namespace
 
 extern "C" {
@@ -1560,92 +1914,7 @@ int orc_nn(const mulls_cloud_view tgt, const mulls_cloud_view src, double max_di
 int orc_pca_features(const mulls_cloud_view cloud, float radius, int k, int stride, mulls_pca_out *out) {
     Cloud C;
     load_cloud(cloud, C);
-    const long n = (long)C.size();
-    const float r2 = (float)((double)radius * (double)radius); // KdTreeFLANN::radiusSearch casts radius*radius to float
-    // brute force through a uniform grid (oracle: clarity over speed)
-    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
-    for (long i = 0; i < n; ++i) {
-        mn[0] = std::min(mn[0], C[i].x);
-        mn[1] = std::min(mn[1], C[i].y);
-        mn[2] = std::min(mn[2], C[i].z);
-        mx[0] = std::max(mx[0], C[i].x);
-        mx[1] = std::max(mx[1], C[i].y);
-        mx[2] = std::max(mx[2], C[i].z);
-    }
-    const float h = radius * 1.0001f;
-    int dims[3];
-    for (int d = 0; d < 3; ++d) dims[d] = std::max(1, (int)std::floor((mx[d] - mn[d]) / h) + 1);
-    std::vector<std::vector<int>> cells((size_t)dims[0] * dims[1] * dims[2]);
-    auto cell_of = [&](const Pt &p, int c[3]) {
-        c[0] = std::min(dims[0] - 1, std::max(0, (int)std::floor((p.x - mn[0]) / h)));
-        c[1] = std::min(dims[1] - 1, std::max(0, (int)std::floor((p.y - mn[1]) / h)));
-        c[2] = std::min(dims[2] - 1, std::max(0, (int)std::floor((p.z - mn[2]) / h)));
-    };
-    for (long i = 0; i < n; ++i) {
-        int c[3];
-        cell_of(C[i], c);
-        cells[((size_t)c[2] * dims[1] + c[1]) * dims[0] + c[0]].push_back((int)i);
-    }
-    for (long i = 0; i < n; ++i) {
-        out->pt_num[i] = 0;
-        for (int d = 0; d < 3; ++d) out->eigenvalues[3 * i + d] = out->principal[3 * i + d] = out->normal[3 * i + d] = 0.f;
-    }
-#pragma omp parallel for schedule(dynamic, 64)
-    for (long i = 0; i < n; i += stride) {
-        int c[3];
-        cell_of(C[i], c);
-        std::vector<std::pair<float, int>> nb;
-        float q[3] = {C[i].x, C[i].y, C[i].z};
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    int cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
-                    if (cx < 0 || cy < 0 || cz < 0 || cx >= dims[0] || cy >= dims[1] || cz >= dims[2]) continue;
-                    const std::vector<int> &cell = cells[((size_t)cz * dims[1] + cy) * dims[0] + cx];
-                    for (size_t t = 0; t < cell.size(); ++t) {
-                        float d2 = KdTree::flann_l2(q, C[cell[t]]);
-                        if (d2 < r2) nb.push_back(std::make_pair(d2, cell[t])); // FLANN result sets keep dist < radius
-                    }
-                }
-        std::sort(nb.begin(), nb.end());
-        if (k > 0 && (int)nb.size() > k) nb.resize(k);
-        const int m = (int)nb.size();
-        out->pt_num[i] = m;
-        if (m <= 3) continue; // pca.hpp:396-397
-        // pcl::PCA [3P]: float centroid, float covariance / (n-1)
-        float mu[3] = {0, 0, 0};
-        for (int t = 0; t < m; ++t) {
-            mu[0] += C[nb[t].second].x;
-            mu[1] += C[nb[t].second].y;
-            mu[2] += C[nb[t].second].z;
-        }
-        mu[0] /= (float)m;
-        mu[1] /= (float)m;
-        mu[2] /= (float)m;
-        float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int t = 0; t < m; ++t) {
-            float d[3] = {C[nb[t].second].x - mu[0], C[nb[t].second].y - mu[1], C[nb[t].second].z - mu[2]};
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b) cov[a][b] += d[a] * d[b];
-        }
-        double A[3][3], w[3], V[3][3];
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) A[a][b] = (double)(cov[a][b] / (float)(m - 1));
-        jacobi_eig3(A, w, V);
-        int ord[3] = {0, 1, 2};
-        std::sort(ord, ord + 3, [&](int a, int b) { return w[a] > w[b]; });
-        double e0[3] = {V[0][ord[0]], V[1][ord[0]], V[2][ord[0]]};
-        double e1[3] = {V[0][ord[1]], V[1][ord[1]], V[2][ord[1]]};
-        double e2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
-        double n0 = std::sqrt(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]);
-        double n2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
-        for (int d = 0; d < 3; ++d) {
-            out->eigenvalues[3 * i + d] = (float)w[ord[d]];
-            out->principal[3 * i + d] = (float)(e0[d] / n0);
-            out->normal[3 * i + d] = (float)(e2[d] / n2);
-        }
-    }
-    return 0;
+    return pca_core(C, radius, k, stride, out, nullptr);
 }
 
 // One registration that also returns the clouds block1's kd-trees were built on (cregistration.hpp:1209-1232):
@@ -1680,6 +1949,20 @@ int orc_map_update(const mulls_cloud_view map_in[6], const double map_pose[16], 
     for (int c = 0; c < 6; ++c)
         if (map_out[c]) store_cloud(map[c], map_out[c]);
     if (info) *info = local;
+    return 0;
+}
+
+
+// classify_nground_pts on host rows; out->rows[k] need cloud_in.n rows each (NULL: skipped), out->n receives the counts.
+int orc_classify_nground(const mulls_cloud_view cloud_in, const mulls_classify_params *params, mulls_classify_out *out) {
+    Rows in(cloud_in.n);
+    if (cloud_in.n) std::memcpy(in.data(), cloud_in.aos48, cloud_in.n * sizeof(Row));
+    Rows res[MULLS_OUT_COUNT];
+    classify_nground(in, *params, res);
+    for (int k = 0; k < MULLS_OUT_COUNT; ++k) {
+        out->n[k] = res[k].size();
+        if (out->rows[k] && !res[k].empty()) std::memcpy(out->rows[k], res[k].data(), res[k].size() * sizeof(Row));
+    }
     return 0;
 }
 

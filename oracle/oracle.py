@@ -53,6 +53,8 @@ def load() -> C.CDLL:
         lib.orc_map_update.argtypes = [C.POINTER(abi.CloudView), C.POINTER(C.c_double), C.POINTER(abi.CloudView),
                                        C.POINTER(C.c_double), C.POINTER(abi.CloudView), C.POINTER(abi.MapParams), fpp,
                                        C.POINTER(abi.MapInfo)]
+        lib.orc_classify_nground.restype = C.c_int
+        lib.orc_classify_nground.argtypes = [abi.CloudView, C.POINTER(abi.ClassifyParams), C.POINTER(abi.ClassifyOut)]
         _LIB = lib
     return _LIB
 
@@ -132,3 +134,8 @@ def map_update(map_clouds, map_pose, scan_down, scan_pose, params: abi.MapParams
                        C.byref(params), ptrs, C.byref(info))
     d = abi.map_info_to_dict(info)
     return [np.ascontiguousarray(bufs[c][: d["n"][c]]) for c in range(abi.NUM_CLASSES)], d
+
+
+def classify_nground(cloud: np.ndarray, params: abi.ClassifyParams) -> dict:
+    """CFilter::classify_nground_pts on host rows: {"pillar": (n,12), ..., "vertex": ..., "unground": ...}."""
+    return abi.classify_call(load().orc_classify_nground, None, cloud, params)
