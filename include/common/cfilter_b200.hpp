@@ -1,0 +1,92 @@
+// Drop-in shim: lo::CFilter<PointT>::classify_nground_pts (include/common/cfilter.hpp:2058-2290) over the mulls_b200
+// C-ABI. A MULLS maintainer replaces the BODY of classify_nground_pts by
+//
+//     return lo::b200::classify_nground_pts<PointT>(cloud_in, cloud_pillar, ... );      // all arguments forwarded
+//
+// and CFilter::extract_semantic_pts (:2295-2413) keeps calling it unchanged. Same names, order, types and defaults as
+// :2060-2081. The output clouds are expected empty at the call (as extract_semantic_pts passes them): results are
+// appended. Differences: every random_downsample_pcl inside is a reproducible uniform sample;
+// std::sort's unspecified order of equal NMS scores is fixed to "first pushed first".
+#ifndef MULLS_B200_CFILTER_SHIM_HPP
+#define MULLS_B200_CFILTER_SHIM_HPP
+
+#include <cfloat>
+#include <vector>
+
+#include "common/cregistration_b200.hpp" // thread_context, view_of
+#include "mulls_b200/abi.h"
+
+namespace lo {
+namespace b200 {
+
+template <typename PointT>
+bool classify_nground_pts(typename pcl::PointCloud<PointT>::Ptr &cloud_in, typename pcl::PointCloud<PointT>::Ptr &cloud_pillar,
+                          typename pcl::PointCloud<PointT>::Ptr &cloud_beam, typename pcl::PointCloud<PointT>::Ptr &cloud_facade,
+                          typename pcl::PointCloud<PointT>::Ptr &cloud_roof, typename pcl::PointCloud<PointT>::Ptr &cloud_pillar_down,
+                          typename pcl::PointCloud<PointT>::Ptr &cloud_beam_down, typename pcl::PointCloud<PointT>::Ptr &cloud_facade_down,
+                          typename pcl::PointCloud<PointT>::Ptr &cloud_roof_down, typename pcl::PointCloud<PointT>::Ptr &cloud_vertex,
+                          float neighbor_searching_radius, int neighbor_k, int neigh_k_min, int pca_down_rate, float edge_thre,
+                          float planar_thre, float edge_thre_down, float planar_thre_down, int extract_vertex_points_method,
+                          float curvature_thre, float vertex_curvature_non_max_radius, float linear_vertical_sin_high_thre,
+                          float linear_vertical_sin_low_thre, float planar_vertical_sin_high_thre,
+                          float planar_vertical_sin_low_thre, bool fixed_num_downsampling = false, int pillar_down_fixed_num = 200,
+                          int facade_down_fixed_num = 800, int beam_down_fixed_num = 200, int roof_down_fixed_num = 100,
+                          int unground_down_fixed_num = 20000, float beam_height_max = FLT_MAX, float roof_height_min = -FLT_MAX,
+                          float feature_pts_ratio_guess = 0.3, bool sharpen_with_nms = true,
+                          bool use_distance_adaptive_pca = false) {
+    static_assert(sizeof(PointT) == 48, "the C-ABI consumes pcl::PointXYZINormal rows (48 bytes)");
+    static thread_local uint32_t call_seed = 0;
+    mulls_classify_params p;
+    mulls_classify_default_params(&p);
+    p.neighbor_searching_radius = neighbor_searching_radius;
+    p.neighbor_k = neighbor_k;
+    p.neigh_k_min = neigh_k_min;
+    p.pca_down_rate = pca_down_rate;
+    p.edge_thre = edge_thre;
+    p.planar_thre = planar_thre;
+    p.edge_thre_down = edge_thre_down;
+    p.planar_thre_down = planar_thre_down;
+    p.extract_vertex_points_method = extract_vertex_points_method;
+    p.curvature_thre = curvature_thre;
+    p.vertex_curvature_non_max_radius = vertex_curvature_non_max_radius;
+    p.linear_vertical_sin_high_thre = linear_vertical_sin_high_thre;
+    p.linear_vertical_sin_low_thre = linear_vertical_sin_low_thre;
+    p.planar_vertical_sin_high_thre = planar_vertical_sin_high_thre;
+    p.planar_vertical_sin_low_thre = planar_vertical_sin_low_thre;
+    p.fixed_num_downsampling = fixed_num_downsampling;
+    p.pillar_down_fixed_num = pillar_down_fixed_num;
+    p.facade_down_fixed_num = facade_down_fixed_num;
+    p.beam_down_fixed_num = beam_down_fixed_num;
+    p.roof_down_fixed_num = roof_down_fixed_num;
+    p.unground_down_fixed_num = unground_down_fixed_num;
+    p.beam_height_max = beam_height_max;
+    p.roof_height_min = roof_height_min;
+    p.feature_pts_ratio_guess = feature_pts_ratio_guess;
+    p.sharpen_with_nms = sharpen_with_nms;
+    p.use_distance_adaptive_pca = use_distance_adaptive_pca;
+    p.random_seed = call_seed++;
+
+    const size_t n = cloud_in->points.size();
+    mulls_ctx *ctx = thread_context(1, n);
+    std::vector<std::vector<PointT>> rows(MULLS_OUT_COUNT, std::vector<PointT>(n ? n : 1));
+    mulls_classify_out out;
+    for (int k = 0; k < MULLS_OUT_COUNT; ++k) out.rows[k] = reinterpret_cast<float *>(rows[k].data()), out.n[k] = 0;
+    out.cap = n ? n : 1;
+    if (!ctx || mulls_classify_nground(ctx, view_of<PointT>(cloud_in), &p, &out) != MULLS_OK) {
+        LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
+        return false;
+    }
+    typename pcl::PointCloud<PointT>::Ptr *dst[MULLS_OUT_COUNT] = {&cloud_pillar,      &cloud_beam,        &cloud_facade,
+                                                                   &cloud_roof,        &cloud_pillar_down, &cloud_beam_down,
+                                                                   &cloud_facade_down, &cloud_roof_down,   &cloud_vertex,
+                                                                   &cloud_in};
+    for (int k = 0; k < MULLS_OUT_COUNT; ++k) {
+        if (k == MULLS_OUT_UNGROUND) (*dst[k])->points.clear(); // cloud_in is rewritten in place by the reference
+        (*dst[k])->points.insert((*dst[k])->points.end(), rows[k].begin(), rows[k].begin() + out.n[k]);
+    }
+    return true;
+}
+
+} // namespace b200
+} // namespace lo
+#endif

@@ -137,12 +137,42 @@ __global__ void __launch_bounds__(kClsBlock) k_cls_compact(ClsArgs C) {
     }
 }
 
-// ---- k_cls_promote: the promotion loop (:2169-2210). Sequential semantics: when point i is visited, the labels of
-//      the earlier promoted points are already in index_with_feature. st4: 0 no candidate, 1 undecided, 2 not promoted,
-//      3 promoted but neither pillar nor beam, 4 promoted pillar, 5 promoted beam. One block; rounds until settled.
+// ---- the promotion loop (:2169-2210). Sequential semantics: when point i is visited, the labels of the earlier
+//      promoted points are already in index_with_feature. st4: 0 no candidate, 1 undecided, 2 not promoted, 3 promoted
+//      but neither pillar nor beam, 4 promoted pillar, 5 promoted beam.
+__device__ __forceinline__ uint8_t promote_state(const ClsArgs &C, uint32_t i) {
+    const float az = fabsf(C.F.principal[3 * (size_t)i + 2]);
+    if (az > C.P.linear_vertical_sin_high_thre) return 4;
+    if (az < C.P.linear_vertical_sin_low_thre && C.rows[3 * (size_t)i].z < C.P.beam_height_max) return 5;
+    return 3;
+}
+
+// k_cls_promote_pre (all SMs): what can be settled without knowing the other candidates' fate. The count of labelled
+// neighbours only grows during the loop, so "enough threshold-loop neighbours" is final, and "not enough even if every
+// earlier candidate neighbour were promoted" is final too. (Other threads' decisions are invisible here: any non-zero
+// st4 of an earlier neighbour counts as "may still be promoted".)
+__global__ void __launch_bounds__(256) k_cls_promote_pre(ClsArgs C) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n || C.st4[i] != 1) return;
+    const float thre = C.P.feature_pts_ratio_guess / (float)C.stride;
+    const int pt_num = C.F.pt_num[i];
+    int sure = 0, maybe = 0;
+    for (int t = 0; t < pt_num; ++t) {
+        const uint32_t j = C.F.nbr[(size_t)i * C.F.k + t] & 0x7fffffffu;
+        if (C.label0[j])
+            ++sure;
+        else if (j < i && ((volatile uint8_t *)C.st4)[j] != 0)
+            ++maybe;
+    }
+    if (1.0 * sure / pt_num > (double)thre)
+        C.st4[i] = promote_state(C, i);
+    else if (!(1.0 * (sure + maybe) / pt_num > (double)thre))
+        C.st4[i] = 2;
+}
+
+// k_cls_promote (one block): the candidates that depend on each other, in monotone rounds, then the row updates
 __global__ void __launch_bounds__(kClsBlock) k_cls_promote(ClsArgs C) {
-    const mulls_classify_params &P = C.P;
-    const float thre = P.feature_pts_ratio_guess / (float)C.stride;
+    const float thre = C.P.feature_pts_ratio_guess / (float)C.stride;
     volatile uint8_t *st4 = C.st4;
     while (true) {
         int pending = 0;
@@ -162,31 +192,27 @@ __global__ void __launch_bounds__(kClsBlock) k_cls_promote(ClsArgs C) {
                         ++maybe;
                 }
             }
-            if (1.0 * sure / pt_num > (double)thre) {
-                const float az = fabsf(C.F.principal[3 * (size_t)i + 2]);
-                uint8_t s = 3;
-                if (az > P.linear_vertical_sin_high_thre)
-                    s = 4;
-                else if (az < P.linear_vertical_sin_low_thre && C.rows[3 * (size_t)i].z < P.beam_height_max)
-                    s = 5;
-                st4[i] = s;
-            } else if (1.0 * (sure + maybe) / pt_num > (double)thre) {
+            if (1.0 * sure / pt_num > (double)thre)
+                st4[i] = promote_state(C, i);
+            else if (1.0 * (sure + maybe) / pt_num > (double)thre)
                 pending = 1; // an earlier candidate is still open and could tip this one
-            } else {
+            else
                 st4[i] = 2;
-            }
         }
         if (!__syncthreads_or(pending)) break;
     }
-    // apply: assign_normal(pt, feature, false), normal[3] = 5 * curvature (:2194-2195), labels
-    for (uint32_t i = threadIdx.x; i < C.n; i += kClsBlock) {
-        const uint8_t s = st4[i];
-        if (s < 3) continue;
-        const ClsFeat f = cls_feat(C.F, i);
-        C.rows[3 * (size_t)i + 1] = make_float4(f.pdir[0], f.pdir[1], f.pdir[2], (float)(5.0 * f.curvature));
-        if (s == 4) C.label[i] = 1;
-        if (s == 5) C.label[i] = 2;
-    }
+}
+
+// k_cls_promote_apply: assign_normal(pt, feature, false), normal[3] = 5 * curvature (:2194-2195), labels
+__global__ void __launch_bounds__(256) k_cls_promote_apply(ClsArgs C) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n) return;
+    const uint8_t s = C.st4[i];
+    if (s < 3) return;
+    const ClsFeat f = cls_feat(C.F, i);
+    C.rows[3 * (size_t)i + 1] = make_float4(f.pdir[0], f.pdir[1], f.pdir[2], (float)(5.0 * f.curvature));
+    if (s == 4) C.label[i] = 1;
+    if (s == 5) C.label[i] = 2;
 }
 
 // ---- k_cls_compact2: blocks 0/1 append the promoted pillars / beams behind the threshold loop's
@@ -319,13 +345,15 @@ __global__ void __launch_bounds__(256) k_nms_gather(ClsArgs C) {
     o[0] = in[0], o[1] = in[1], o[2] = in[2];
 }
 
-// one block per class: greedy selection in score order, 1024 points at a time
+// one block per class: greedy selection in score order, 1024 points at a time. Inside a chunk every thread first
+// builds the bit mask of the EARLIER chunk points within the radius (32 words), then the rounds are pure bit tests
+// against two shared masks (selected / suppressed) that only ever gain bits.
 __global__ void __launch_bounds__(kClsBlock) k_nms_select(ClsArgs C) {
     const int c = blockIdx.x;
     __shared__ uint32_t s_warp[kClsBlock / 32];
     __shared__ uint32_t s_total;
     __shared__ float s_x[kClsBlock], s_y[kClsBlock], s_z[kClsBlock];
-    __shared__ uint8_t s_state[kClsBlock]; // 0 undecided, 1 selected, 2 suppressed
+    __shared__ uint32_t s_sel[kClsBlock / 32], s_sup[kClsBlock / 32];
     if (!nms_active(C, c)) {
         if (threadIdx.x == 0) C.st->nms_ran[c] = 0; // n_down stays what the threshold loop left (0 when sharpening)
         return;
@@ -335,55 +363,73 @@ __global__ void __launch_bounds__(kClsBlock) k_nms_select(ClsArgs C) {
     const float r2 = (float)((double)nms_radius * (double)nms_radius);
     const float4 *pts = C.cls_sorted[c];
     float4 *sel = C.sel_pos + (size_t)c * C.n;
-    if (threadIdx.x == 0) s_total = 0;
+    const uint32_t tid = threadIdx.x, myw = tid >> 5, mybit = 1u << (tid & 31);
+    if (tid == 0) s_total = 0;
     __syncthreads();
-    volatile uint8_t *state = s_state;
     for (uint32_t base = 0; base < n; base += kClsBlock) {
-        const uint32_t i = base + threadIdx.x;
+        const uint32_t i = base + tid;
         const bool valid = i < n;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) p = pts[3 * (size_t)i];
-        s_x[threadIdx.x] = p.x, s_y[threadIdx.x] = p.y, s_z[threadIdx.x] = p.z;
+        s_x[tid] = p.x, s_y[tid] = p.y, s_z[tid] = p.z;
+        if (tid < kClsBlock / 32) s_sel[tid] = 0, s_sup[tid] = 0;
         // (1) against the points selected in the earlier chunks
-        uint8_t st = valid ? 0 : 2;
+        bool open = valid;
         const uint32_t n_sel = s_total;
         if (valid)
             for (uint32_t t = 0; t < n_sel; ++t) {
                 const float4 q = sel[t];
                 if (flann_l2(q.x, q.y, q.z, p.x, p.y, p.z) < r2) {
-                    st = 2;
+                    open = false;
                     break;
                 }
             }
-        s_state[threadIdx.x] = st;
         __syncthreads();
-        // (2) inside the chunk: a point is selected once every earlier point within the radius is suppressed
+        if (!open) atomicOr(&s_sup[myw], mybit);
+        // (2) near mask over the earlier points of the chunk
+        uint32_t near[kClsBlock / 32];
+#pragma unroll
+        for (int w = 0; w < kClsBlock / 32; ++w) {
+            uint32_t mk = 0;
+            if (open && (uint32_t)(w * 32) < tid) {
+                const uint32_t lim = min(32u, tid - (uint32_t)(w * 32));
+                for (uint32_t b = 0; b < lim; ++b) {
+                    const uint32_t t = (uint32_t)(w * 32) + b;
+                    if (flann_l2(s_x[t], s_y[t], s_z[t], p.x, p.y, p.z) < r2) mk |= 1u << b;
+                }
+            }
+            near[w] = mk;
+        }
+        __syncthreads();
+        // (3) a point is selected once every earlier point within the radius is suppressed
         while (true) {
             int pending = 0;
-            if (state[threadIdx.x] == 0) {
-                bool suppressed = false, blocked = false;
-                for (uint32_t t = 0; t < threadIdx.x; ++t) {
-                    const uint8_t s = state[t];
-                    if (s == 2) continue;
-                    if (flann_l2(s_x[t], s_y[t], s_z[t], p.x, p.y, p.z) < r2) {
-                        if (s == 1) {
-                            suppressed = true;
-                            break;
-                        }
-                        blocked = true;
+            if (open) {
+                bool hit = false, blocked = false;
+#pragma unroll
+                for (int w = 0; w < kClsBlock / 32; ++w) {
+                    const uint32_t nm = near[w];
+                    if (nm) {
+                        const uint32_t se = ((volatile uint32_t *)s_sel)[w];
+                        const uint32_t su = ((volatile uint32_t *)s_sup)[w];
+                        if (nm & se) hit = true;
+                        if (nm & ~(se | su)) blocked = true;
                     }
                 }
-                if (suppressed)
-                    state[threadIdx.x] = 2;
-                else if (!blocked)
-                    state[threadIdx.x] = 1;
-                else
+                if (hit) {
+                    atomicOr(&s_sup[myw], mybit);
+                    open = false;
+                } else if (!blocked) {
+                    atomicOr(&s_sel[myw], mybit);
+                    open = false;
+                } else {
                     pending = 1;
+                }
             }
             if (!__syncthreads_or(pending)) break;
         }
-        // (3) append the chunk's selected points, in order
-        const bool keep = valid && s_state[threadIdx.x] == 1;
+        // (4) append the chunk's selected points, in order
+        const bool keep = valid && (s_sel[myw] & mybit);
         const uint32_t slot = map_tile_slot(keep, s_warp, &s_total);
         if (keep) {
             const float4 *r = pts + 3 * (size_t)i;
@@ -393,7 +439,7 @@ __global__ void __launch_bounds__(kClsBlock) k_nms_select(ClsArgs C) {
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         C.st->n_down[c] = s_total;
         C.st->nms_ran[c] = 1;
     }
@@ -406,6 +452,7 @@ struct SampleShared {
     uint32_t hist[256];
     uint64_t prefix;
     uint32_t rank;
+    uint32_t single;
 };
 
 // random_downsample_pcl (cfilter.hpp:606-628) of in[0..n) appended to out at *out_n: the points with the keep_number
@@ -416,7 +463,8 @@ __device__ void block_sample_append(const float4 *in, uint32_t n, long long keep
     if (threadIdx.x == 0) S.prefix = 0, S.rank = (uint32_t)(sample ? keep_num : 0);
     __syncthreads();
     if (sample && keep_num > 0) {
-        for (int pass = 0; pass < 8; ++pass) {
+        int pass = 0;
+        for (; pass < 8; ++pass) {
             if (threadIdx.x < 256) S.hist[threadIdx.x] = 0;
             __syncthreads();
             const int shift = 56 - 8 * pass;
@@ -436,6 +484,18 @@ __device__ void block_sample_append(const float4 *in, uint32_t n, long long keep
                 }
                 S.prefix = prefix | ((uint64_t)d << shift);
                 S.rank = rank - cum;
+                S.single = (S.hist[d] == 1u) ? 1u : 0u;
+            }
+            __syncthreads();
+            if (S.single) break; // one key carries this prefix: it is the k-th smallest, fetch its low bytes directly
+        }
+        if (pass < 7) {
+            const int shift = 56 - 8 * pass;
+            const uint64_t prefix = S.prefix;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += kClsBlock) {
+                const uint64_t key = sample_key(seed, cloud, i);
+                if ((key >> shift) == (prefix >> shift)) S.prefix = key;
             }
             __syncthreads();
         }

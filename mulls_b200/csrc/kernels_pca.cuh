@@ -114,52 +114,69 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca(DeviceArrays A, PcaArgs 
     // level whose cells are at least as wide as the radius: its 3x3x3 block around p covers the sphere
     int lq = 0;
     while (lq < ps.n_levels - 1 && 0.999f * ps.h0 * (float)(1 << lq) < P.radius) ++lq;
-    const int ncell = (1 << kCoordBits) >> lq;
-    const int cx = ((int)floorf((p.x - ps.origin[0]) * ps.inv_h0)) >> lq;
-    const int cy = ((int)floorf((p.y - ps.origin[1]) * ps.inv_h0)) >> lq;
-    const int cz = ((int)floorf((p.z - ps.origin[2]) * ps.inv_h0)) >> lq;
+    // Progressive radius: a 3x3x3 block of level-l cells contains every point within 0.999*h_l of p. Where the cloud is
+    // dense the k nearest neighbours lie well inside the radius, so start two levels finer and accept the first level
+    // whose guaranteed sphere already holds k points — same neighbours, a fraction of the candidates.
+    float rb2 = P.r2; // squared acceptance bound of the candidate stream
     uint32_t my_start = 0, my_count = 0;
-    if (lane < 27) {
-        const int x = cx + lane % 3 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane / 9 - 1;
-        if (x >= 0 && y >= 0 && z >= 0 && x < ncell && y < ncell && z < ncell) {
-            const HashEntry *table = A.hash + ps.hash_base[0];
-            const uint64_t key = cell_key(lq, morton36((uint32_t)x, (uint32_t)y, (uint32_t)z));
-            uint32_t slot = hash_key(key) & ps.hash_mask[0];
-            const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
-            while (true) {
-                const uint4 e = __ldg(reinterpret_cast<const uint4 *>(&table[slot]));
-                if (e.x == klo && (e.y & kKeyHiMask) == khi) {
-                    my_start = e.z;
-                    my_count = e.w;
-                    break;
+    int m = 0;       // entries in the list (capped)
+    int m_total = 0; // neighbours within the bound
+    for (int l = (P.k > 0) ? max(0, lq - 2) : lq;; ++l) {
+        const bool last = l >= lq;
+        if (!last) {
+            const float cover = 0.999f * ps.h0 * (float)(1 << l);
+            rb2 = fminf(cover * cover, P.r2);
+        } else {
+            rb2 = P.r2;
+        }
+        const int ncell = (1 << kCoordBits) >> l;
+        const int cx = ((int)floorf((p.x - ps.origin[0]) * ps.inv_h0)) >> l;
+        const int cy = ((int)floorf((p.y - ps.origin[1]) * ps.inv_h0)) >> l;
+        const int cz = ((int)floorf((p.z - ps.origin[2]) * ps.inv_h0)) >> l;
+        my_start = 0, my_count = 0;
+        if (lane < 27) {
+            const int x = cx + lane % 3 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane / 9 - 1;
+            if (x >= 0 && y >= 0 && z >= 0 && x < ncell && y < ncell && z < ncell) {
+                const HashEntry *table = A.hash + ps.hash_base[0];
+                const uint64_t key = cell_key(l, morton36((uint32_t)x, (uint32_t)y, (uint32_t)z));
+                uint32_t slot = hash_key(key) & ps.hash_mask[0];
+                const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+                while (true) {
+                    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(&table[slot]));
+                    if (e.x == klo && (e.y & kKeyHiMask) == khi) {
+                        my_start = e.z;
+                        my_count = e.w;
+                        break;
+                    }
+                    if (e.x == 0u && e.y == 0u) break;
+                    slot = (slot + 1) & ps.hash_mask[0];
                 }
-                if (e.x == 0u && e.y == 0u) break;
-                slot = (slot + 1) & ps.hash_mask[0];
             }
         }
-    }
-    // stream the candidates within the radius into the list (FLANN's radius result set keeps dist < r2)
-    int m = 0;          // entries in the list (capped)
-    int m_total = 0;    // neighbours within the radius
-    for (int c = 0; c < 27; ++c) {
-        const uint32_t start = __shfl_sync(0xffffffffu, my_start, c), count = __shfl_sync(0xffffffffu, my_count, c);
-        for (uint32_t base = 0; base < count; base += 32) {
-            const uint32_t j = start + base + lane;
-            bool in = false;
-            float d2 = 0.f;
-            if (base + lane < count) {
-                const float4 q = __ldg(&pos[j]);
-                d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
-                in = d2 < P.r2;
+        // stream the candidates within the bound into the list (FLANN's radius result set keeps dist < r2)
+        m_total = 0;
+        for (int c = 0; c < 27; ++c) {
+            const uint32_t start = __shfl_sync(0xffffffffu, my_start, c), count = __shfl_sync(0xffffffffu, my_count, c);
+            for (uint32_t base = 0; base < count; base += 32) {
+                const uint32_t j = start + base + lane;
+                bool in = false;
+                float d2 = 0.f;
+                if (base + lane < count) {
+                    const float4 q = __ldg(&pos[j]);
+                    d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
+                    in = d2 < rb2;
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, in);
+                const int off = m_total + __popc(b & ((1u << lane) - 1u));
+                if (in && off < kPcaCap) {
+                    keys[off] = __float_as_uint(d2);
+                    idxs[off] = (int)j;
+                }
+                m_total += __popc(b);
             }
-            const unsigned b = __ballot_sync(0xffffffffu, in);
-            const int off = m_total + __popc(b & ((1u << lane) - 1u));
-            if (in && off < kPcaCap) {
-                keys[off] = __float_as_uint(d2);
-                idxs[off] = (int)j;
-            }
-            m_total += __popc(b);
         }
+        if (last || m_total >= P.k) break; // the k nearest are all inside this level's sphere
+        __syncwarp();
     }
     __syncwarp();
     m = min(m_total, kPcaCap);
@@ -190,7 +207,7 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca(DeviceArrays A, PcaArgs 
                     for (uint32_t t = lane; t < count; t += 32) {
                         const float4 q = __ldg(&pos[start + t]);
                         const float d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
-                        cl += (d2 < P.r2 && __float_as_uint(d2) < trial) ? 1 : 0;
+                        cl += (d2 < rb2 && __float_as_uint(d2) < trial) ? 1 : 0;
                     }
                 }
                 for (int o = 16; o > 0; o >>= 1) cl += __shfl_xor_sync(0xffffffffu, cl, o);
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca(DeviceArrays A, PcaArgs 
                     if (base + lane < count) {
                         const float4 q = __ldg(&pos[j]);
                         d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
-                        in = d2 < P.r2 && __float_as_uint(d2) <= T;
+                        in = d2 < rb2 && __float_as_uint(d2) <= T;
                     }
                     const unsigned b = __ballot_sync(0xffffffffu, in);
                     const int off = mt + __popc(b & ((1u << lane) - 1u));

@@ -893,10 +893,24 @@ int mulls_pca_features(mulls_ctx *ctx, mulls_cloud_view cloud, float radius, int
     if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
     PcaArgs args;
     uint64_t launches = 0;
-    int rc = pca_on_device(ctx, cloud, false, radius, k, stride, args, launches);
+    const size_t n = cloud.n;
+    // k within the list capacity (the reference uses 20..50): pcl::PCA's float mean / covariance accumulated in
+    // radiusSearch order — bit-reproducible against the CPU path; larger or unlimited k: fp64 warp reduction
+    uint32_t *nbr = nullptr;
+    if (k >= 1 && k <= kPcaListCap && n > 0) {
+        const size_t bytes = n * (size_t)k * sizeof(uint32_t);
+        if (bytes > ctx->cls_buf_bytes) {
+            if (ctx->cls_buf) cudaFree(ctx->cls_buf);
+            ctx->cls_buf = nullptr;
+            ctx->cls_buf_bytes = 0;
+            CK(cudaMalloc(&ctx->cls_buf, bytes));
+            ctx->cls_buf_bytes = bytes;
+        }
+        nbr = (uint32_t *)ctx->cls_buf;
+    }
+    int rc = pca_on_device(ctx, cloud, false, radius, k, stride, args, launches, nbr);
     if (rc != MULLS_OK) return rc;
     cudaStream_t st = ctx->stream;
-    const size_t n = cloud.n;
     if (n) {
         CK(cudaMemcpyAsync(out->eigenvalues, args.eigenvalues, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out->principal, args.principal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1224,7 +1238,15 @@ int mulls_map_update(mulls_map *m, const mulls_cloud_view scan_down[MULLS_NUM_CL
             mulls_cloud_view v{(const float *)m->buf[m->cur][c], m->n[c]};
             PcaArgs args;
             uint64_t launches = 0;
-            const int rc = pca_on_device(ctx, v, true, pca_radius, pca_max_k, 1, args, launches);
+            const size_t nbr_bytes = (size_t)m->n[c] * pca_max_k * sizeof(uint32_t);
+            if (nbr_bytes > ctx->cls_buf_bytes) {
+                if (ctx->cls_buf) cudaFree(ctx->cls_buf);
+                ctx->cls_buf = nullptr;
+                ctx->cls_buf_bytes = 0;
+                CK(cudaMalloc(&ctx->cls_buf, nbr_bytes));
+                ctx->cls_buf_bytes = nbr_bytes;
+            }
+            const int rc = pca_on_device(ctx, v, true, pca_radius, pca_max_k, 1, args, launches, (uint32_t *)ctx->cls_buf);
             if (rc != MULLS_OK) return rc;
             k_map_revector<<<1, kMapBlock, 0, st>>>(m->buf[m->cur][c], m->n[c], args, pca_min_k, lo[k], hi[k], min_linearity,
                                                    m->mid[c], &m->d_state->n_out[c]);
@@ -1404,11 +1426,13 @@ int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mull
         const unsigned gb = (unsigned)ceil_div(n, 256);
         k_cls_label<<<gb, 256, 0, st>>>(C);
         k_cls_compact<<<8, kClsBlock, 0, st>>>(C);
+        k_cls_promote_pre<<<gb, 256, 0, st>>>(C);
         k_cls_promote<<<1, kClsBlock, 0, st>>>(C);
+        k_cls_promote_apply<<<gb, 256, 0, st>>>(C);
         k_cls_compact2<<<4, kClsBlock, 0, st>>>(C);
         k_cls_encode<<<gb, 256, 0, st>>>(C);
         k_cls_compact_vertex<<<1, kClsBlock, 0, st>>>(C);
-        launches += 6;
+        launches += 8;
         if (P.sharpen_with_nms) {
             CK(cudaMemsetAsync(C.keys_a, 0xff, n * sizeof(uint64_t), st));
             k_nms_keys<<<dim3(gb, 4), 256, 0, st>>>(C);

@@ -5,6 +5,7 @@
 #include "utility.hpp"
 #include "common/cregistration_b200.hpp"
 #include "pgo/map_manager_b200.hpp"
+#include "common/cfilter_b200.hpp"
 
 using namespace lo;
 
@@ -27,6 +28,14 @@ int main() {
                                          0.15f, 1.5f, 0.03f, true);
     reg_con.block1 = cblock_local_map;
     int code3 = mmanager.mm_lls_icp(reg_con, reg_max_iter_num, reg_corr_dis_thre, converge_tran, converge_rot_d);
+    // CFilter::classify_nground_pts with the argument list of cfilter.hpp:2367-2378 (extract_semantic_pts)
+    cloudblock_Ptr in_block(new cloudblock_t);
+    bool cls = lo::b200::classify_nground_pts<Point_T>(in_block->pc_unground, in_block->pc_pillar, in_block->pc_beam, in_block->pc_facade,
+                                                       in_block->pc_roof, in_block->pc_pillar_down, in_block->pc_beam_down,
+                                                       in_block->pc_facade_down, in_block->pc_roof_down, in_block->pc_vertex, 1.0f, 50, 8, 1,
+                                                       0.65f, 0.65f, 0.75f, 0.75f, 2, 0.12f, 1.5f, 0.94f, 0.17f, 0.98f, 0.34f, true, 200, 800,
+                                                       200, 100, 20000, FLT_MAX, 0.0f, 0.3f, true, false);
+    (void)cls;
     std::printf("shim compiled and linked; codes %d %d %d | map %d %d %d\n", code, code2, (int)ok4, (int)up1, (int)up2, code3);
     return 0;
 }

@@ -271,8 +271,8 @@ def test_gpu_map_errors():
 
 @pytest.mark.gpu
 def test_gpu_map_recalculate_feature_matches_oracle():
-    """recalculate_feature_on: PCA is floating point — neighbour sets, survivors and xyz are exact; the new directions
-    and linearities agree to 1e-5 (both sides solve the 3x3 problem in fp64; the reference uses float Eigen)."""
+    """recalculate_feature_on: the re-estimated directions and linearities are bit-identical to the restatement's (float
+    mean / covariance in radiusSearch order, fp64 Jacobi; the reference solves with float Eigen)."""
     from mulls_b200.map_manager import LocalMap
     from mulls_b200.registration import Context
 
@@ -287,12 +287,7 @@ def test_gpu_map_recalculate_feature_matches_oracle():
     omap, oinfo = oracle.map_update(omap, oinfo["pose_lo"], seq["scans"][1], seq["poses"][1], p1)
     _assert_info_equal(ginfo, oinfo, "recalc")
     g = lm.download()
-    for c in (abi.GROUND, abi.FACADE, abi.ROOF, abi.VERTEX):
-        assert np.array_equal(g[c], omap[c])
-    for c in (abi.PILLAR, abi.BEAM):
-        assert g[c].shape == omap[c].shape and g[c].shape[0] > 50
-        assert np.array_equal(g[c][:, [0, 1, 2, 3, 8]], omap[c][:, [0, 1, 2, 3, 8]])
-        assert np.abs(g[c][:, 4:7] - omap[c][:, 4:7]).max() < 1e-5
-        assert np.abs(g[c][:, 9] - omap[c][:, 9]).max() < 1e-5
+    assert g[abi.PILLAR].shape[0] > 50 and g[abi.BEAM].shape[0] > 50
+    _assert_maps_equal(g, omap, "recalc")  # the PCA accumulates in radiusSearch order on both sides: identical bits
     lm.close()
     ctx.close()

@@ -4,7 +4,9 @@ Floating-point parity bar (stated here as the task requires): neighbour COUNT ex
 1e-4 relative to the largest eigenvalue; eigenvector directions within 1e-3 rad up to sign, checked where
 the eigenvalue gap makes the direction well conditioned (gap > 5% of lambda1). The reference computes the
 covariance in float (pcl::PCA) and solves with Eigen's float SelfAdjointEigenSolver; both restatements use
-fp64 Jacobi on the same neighbour set, so they agree far tighter than that bar."""
+fp64 Jacobi on the same neighbour set, so they agree far tighter than that bar — for k <= 64 (the reference's
+range) the CUDA path accumulates the float covariance in radiusSearch order like the CPU path and the outputs are
+bit-identical; for larger / unlimited k it reduces in fp64 across the warp and the stated tolerance applies."""
 import numpy as np
 import pytest
 
@@ -58,4 +60,8 @@ def test_gpu_pca_matches_oracle(oracle_mod, radius, k, stride):
     assert dp[gap01].min() > np.cos(1e-3)
     assert dn[gap01 & gap12].min() > np.cos(1e-3)
     assert (g["pt_num"][~sel] <= 3).all()
+    if 1 <= k <= 64:
+        # list mode: pcl::PCA's float mean / covariance in radiusSearch order on both sides -> identical bits
+        for name in ("eigenvalues", "principal", "normal"):
+            assert np.array_equal(g[name].view(np.uint32), o[name].view(np.uint32)), name
     ctx.close()
