@@ -170,6 +170,10 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--lanes", type=int, default=8, help="concurrent contexts (CUDA streams) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-pack", default="auto", choices=["0", "1", "auto"],
+                    help="e2e leg: ship the clouds as 48-byte rows (0), repacked to the 28 B wire format on the host "
+                         "cores (1), or measure both and report the faster (auto)")
+    ap.add_argument("--pack-threads", type=int, default=0, help="host worker threads of the repacking (0: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -276,18 +280,33 @@ def main():
     lanes_s = ev0.elapsed_time(ev1) / 1e3
 
     # ---- (C) end to end through the C-ABI with host (pinned) buffers, same lanes ----------------------
-    pipe.run_batch_steps(pairs, 2)
-    barrier()
-    t0 = time.perf_counter()
-    res_e2e = pipe.run_batch_steps(pairs, args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    # The clouds cross PCIe either as the caller's 48-byte rows or repacked on the host cores to the 28 B/point wire
+    # format (the "host_pack" tunable, csrc/host_pack.h); both are the same public call and give identical results.
+    e2e_variants = {}
+    if args.pack_threads > 0:
+        pipe.set_tunable("pack_threads", args.pack_threads)
+    for hp in ([0, 1] if args.host_pack == "auto" else [int(args.host_pack)]):
+        pipe.set_tunable("host_pack", hp)
+        pipe.run_batch_steps(pairs, 2)
+        barrier()
+        t0 = time.perf_counter()
+        res_e2e = pipe.run_batch_steps(pairs, args.steps)
+        torch.cuda.synchronize()
+        e2e_variants[hp] = time.perf_counter() - t0
+        for a, b in zip(res, res_e2e):
+            assert np.array_equal(a["T"], b["T"])
+        barrier()
+    best_hp = min(e2e_variants, key=e2e_variants.get)
+    e2e_s = e2e_variants[best_hp]
+    pipe.set_tunable("host_pack", 0)
     if len(sampler.lines) < 3:  # very short runs: keep the GPU under the same load until a few samples exist
         t_fill = time.perf_counter()
         while len(sampler.lines) < 3 and time.perf_counter() - t_fill < 2.0:
             pipe.run_resident()
     clocks = sampler.stop()
     h2d = sum(a.nbytes for p in pairs for side in ("tgt", "src") for a in p[side])
+    if best_hp == 1:  # 28 of the 48 bytes of a row cross PCIe (16 B + 12 B per point, padded per cloud)
+        h2d = sum(16 * (len(a) + (3 * len(a) + 3) // 4) for p in pairs for side in ("tgt", "src") for a in p[side])
     from mulls_b200 import abi
     import ctypes
 
@@ -335,7 +354,10 @@ def main():
             "ms_per_step": 1e3 * lanes_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 accumulation", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "timing": "host clock around the synchronous C-ABI calls (pinned host buffers)"},
+                    "timing": "host clock around the synchronous C-ABI calls (pinned host buffers)",
+                    "host_pack": best_hp,
+                    "variants": {("rows48" if k == 0 else "host_packed28"): total_regs / world / v
+                                 for k, v in e2e_variants.items()} if world == 1 else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_search (transform + NN + claim)", "achieved": achieved, "peak": peak,

@@ -326,6 +326,13 @@ void mulls_classify_default_params(mulls_classify_params *p);
 int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_classify_params *params,
                            mulls_classify_out *out);
 
+/* The wire format the library ships host clouds in when the "host_pack" tunable is on (csrc/host_pack.h): the 28 of the
+ * 48 bytes of a pcl::PointXYZINormal row (utility.hpp:40) that the path reads, repacked on the host cores into pinned
+ * staging before the DMA. format 1: [n x (x y z intensity)] [n x (nx ny nz)]; format 2 (motion undistortion, which also
+ * reads `curvature`): [n x (x y z intensity)] [n x (nx ny nz curvature)]. `out` (16-byte aligned) receives
+ * 4n + 3n floats (format 1) or 8n floats (format 2). Exposed for callers that keep their clouds packed, and for tests. */
+int mulls_pack_rows(const float *aos48, size_t n, int format, float *out);
+
 /* Runtime tunables (integers), e.g. "start_level", "pairs_in_flight". Returns MULLS_E_ARG if unknown. */
 int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value);
 

@@ -203,6 +203,7 @@ EXPORTED_SYMBOLS = (
     "mulls_classify_default_params",
     "mulls_classify_nground",
     "mulls_set_tunable",
+    "mulls_pack_rows",
 )
 
 _LIB = None
@@ -252,6 +253,8 @@ def load_library() -> C.CDLL:
                                           C.POINTER(IcpTrace)]
     lib.mulls_pca_features.restype = C.c_int
     lib.mulls_pca_features.argtypes = [vp, CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(PcaOut)]
+    lib.mulls_pack_rows.restype = C.c_int
+    lib.mulls_pack_rows.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     lib.mulls_set_tunable.restype = C.c_int
     lib.mulls_set_tunable.argtypes = [vp, C.c_char_p, C.c_int]
     lib.mulls_map_default_params.restype = None

@@ -56,6 +56,7 @@ struct PairConst {
     const float4 *in_ptr[kNumSegs]; // where the ingest kernel reads the cloud: the HBM copy, or (one-shot calls with
                                     // pinned host buffers) the caller's buffer itself, streamed over PCIe (zero-copy)
     uint32_t in_n[kNumSegs];
+    uint32_t in_fmt[kNumSegs];  // layout behind in_ptr: 0 = 48-byte rows, 1 = packed 16+12 B, 2 = packed 16+16 B (host_pack.h)
     uint32_t tgt_base[kNumClasses]; // base of each class in the target SoA arrays (capacity = in_n)
     uint32_t src_base[kNumClasses]; // base of each class in the source SoA arrays
     uint32_t chunk_begin;            // iteration chunks of this pair: [chunk_begin, chunk_end)

@@ -20,12 +20,29 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
     float x = 0, y = 0, z = 0;
     if (valid) {
         const size_t gi = (size_t)pc.in_off[seg] + local;
-        const float4 *in = pc.in_ptr[seg] + 3 * (size_t)local;
-        const float4 a = in[0]; // x y z _
-        const float4 b = in[1]; // nx ny nz _
-        const float4 c = in[2]; // intensity curvature _ _
-        x = a.x, y = a.y, z = a.z;
-        float nx = b.x, ny = b.y, nz = b.z;
+        // three layouts behind in_ptr (block-uniform): the caller's 48-byte rows, or the host-packed wire formats
+        float nx, ny, nz, intensity, curvature = 0.0f;
+        const uint32_t fmt = pc.in_fmt[seg];
+        if (fmt == 0u) {
+            const float4 *in = pc.in_ptr[seg] + 3 * (size_t)local;
+            const float4 a = in[0]; // x y z _
+            const float4 b = in[1]; // nx ny nz _
+            const float4 c = in[2]; // intensity curvature _ _
+            x = a.x, y = a.y, z = a.z;
+            nx = b.x, ny = b.y, nz = b.z;
+            intensity = c.x, curvature = c.y;
+        } else {
+            const float4 *in = pc.in_ptr[seg];
+            const float4 a = in[local]; // x y z intensity
+            x = a.x, y = a.y, z = a.z, intensity = a.w;
+            if (fmt == 1u) {
+                const float *nr = reinterpret_cast<const float *>(in + pc.in_n[seg]) + 3 * (size_t)local;
+                nx = nr[0], ny = nr[1], nz = nr[2];
+            } else {
+                const float4 b = in[(size_t)pc.in_n[seg] + local]; // nx ny nz curvature
+                nx = b.x, ny = b.y, nz = b.z, curvature = b.w;
+            }
+        }
         if (is_src) {
             const double *t = pc.init;
             int n_apply = 1;
@@ -33,7 +50,7 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
                 if (cls == MULLS_VERTEX) {
                     n_apply = 2; // not undistorted and not re-cloned: the initial guess lands twice (reference behaviour)
                 } else {
-                    const float curv = c.y; // timestamp ratio of the point inside its frame
+                    const float curv = curvature; // timestamp ratio of the point inside its frame
                     if (!(curv < 0.0f || (double)curv > 1.0)) {
                         const double s = (double)curv;
                         double scale0, scale1;
@@ -69,7 +86,7 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
                 nz = (float)(t[8] * qx + t[9] * qy + t[10] * qz);
             }
         }
-        A.stg_pos[gi] = make_float4(x, y, z, c.x);
+        A.stg_pos[gi] = make_float4(x, y, z, intensity);
         A.stg_nrm[gi] = make_float4(nx, ny, nz, __int_as_float((int)local));
     }
     // bbox: source ground/pillar/facade (cregistration.hpp:2912-2915) and all target points (grid extent)

@@ -1,6 +1,8 @@
 // libmulls_b200.so — host side of the C-ABI (include/mulls_b200/abi.h) and kernel launch sequence.
 // CUDA runtime only: no torch, no PCL/Eigen. One context = one device, one stream.
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -11,6 +13,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "device_types.cuh"
+#include "host_pack.h"
 #include "kernels_ingest.cuh"
 #include "kernels_iterate.cuh"
 #include "kernels_pca.cuh"
@@ -52,6 +55,9 @@ struct mulls_ctx {
     int defer_scan = 2;    // queue the leaves of a block and scan them together: 0 off, 1 on, 2 from iteration 2 on
     int packet_max_ext_mm = 0; // packet search for warps whose union search box is at most this wide (0 = off)
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
+    int host_pack = 0;     // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h)
+    float4 *h_stage = nullptr; // pinned staging of the packed clouds (allocated on first use)
+    size_t h_stage_slots = 0;
     float h0_min = 0.125f;
     // timing
     cudaEvent_t ev_begin = nullptr, ev_ingest = nullptr, ev_iter = nullptr, ev_end = nullptr;
@@ -140,6 +146,7 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_running) cudaFreeHost(ctx->h_running);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_search) cudaEventDestroy(e);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -340,9 +347,19 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "search_budget") ctx->search_budget = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "defer_scan") ctx->defer_scan = value;
+    else if (n == "host_pack") ctx->host_pack = value;
+    else if (n == "pack_threads") PackPool::get().ensure_workers(value);
     else if (n == "packet_max_ext_mm") ctx->packet_max_ext_mm = value;
     else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
     else return MULLS_E_ARG;
+    return MULLS_OK;
+}
+
+int mulls_pack_rows(const float *aos48, size_t n, int format, float *out) {
+    if ((n > 0 && (!aos48 || !out)) || (format != kFmtPacked28 && format != kFmtPacked32) || ((uintptr_t)out % 16) != 0)
+        return MULLS_E_ARG;
+    pack_rows(aos48, 0, n, format, out, out + 4 * n);
+    _mm_sfence();
     return MULLS_OK;
 }
 
@@ -516,12 +533,69 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
         ctx->err = "internal: chunk table capacity";
         return MULLS_E_CAPACITY;
     }
-    // the clouds: HBM copy, or zero-copy for pinned host buffers of one-shot calls
+    // the clouds: repacked on the host cores and copied pair by pair (host_pack), or copied as they are, or read in
+    // place (zero-copy, pinned host buffers of one-shot calls)
+    const bool pack = ctx->host_pack != 0;
+    if (pack) {
+        if (!ctx->h_stage) {
+            const size_t slots = 2 * ctx->cap_in + 4 * kNumSegs * ctx->max_pairs;
+            CK(cudaMallocHost((void **)&ctx->h_stage, slots * sizeof(float4)));
+            ctx->h_stage_slots = slots;
+        }
+        PackPool &pool = PackPool::get();
+        pool.ensure_workers(0);
+        std::unique_ptr<std::atomic<int>[]> pending(new std::atomic<int>[n_pairs]);
+        std::vector<size_t> slot_begin(n_pairs + 1, 0);
+        std::vector<PackJob> jobs;
+        const size_t kJobPts = 16384; // multiple of 4 (pack_rows)
+        size_t slot = 0;
+        for (size_t p = 0; p < n_pairs; ++p) {
+            PairConst &pc = ctx->h_pc[p];
+            const int fmt = pc.undistort ? kFmtPacked32 : kFmtPacked28;
+            slot_begin[p] = slot;
+            int n_jobs = 0;
+            for (int s = 0; s < kNumSegs; ++s) {
+                const mulls_cloud_view &v = (s < kNumClasses) ? tgt[p * kNumClasses + s] : src[p * kNumClasses + (s - kNumClasses)];
+                pc.in_ptr[s] = ctx->A.in_aos + slot;
+                pc.in_fmt[s] = (uint32_t)fmt;
+                if (tgt_on_device && s < kNumClasses) { // the view already points into HBM (device-resident local map)
+                    pc.in_ptr[s] = (const float4 *)v.aos48;
+                    pc.in_fmt[s] = kFmtRows48;
+                    continue;
+                }
+                if (v.n == 0) continue;
+                float *pos = reinterpret_cast<float *>(ctx->h_stage + slot);
+                float *nrm = reinterpret_cast<float *>(ctx->h_stage + slot + v.n);
+                for (size_t f = 0; f < v.n; f += kJobPts) {
+                    jobs.push_back(PackJob{v.aos48, pos, nrm, f, std::min(kJobPts, v.n - f), fmt, &pending[p]});
+                    ++n_jobs;
+                }
+                slot += packed_slots(v.n, fmt);
+            }
+            pending[p].store(n_jobs, std::memory_order_relaxed);
+        }
+        slot_begin[n_pairs] = slot;
+        if (slot > ctx->h_stage_slots || slot > 3 * ctx->cap_in) {
+            ctx->err = "internal: packed staging capacity";
+            return MULLS_E_CAPACITY;
+        }
+        pool.submit(jobs); // FIFO: pair 0 is packed first, and its DMA runs while the next pairs are being packed
+        cudaError_t ce = cudaSuccess; // (every job is waited for even after an error: the jobs point at `pending`)
+        for (size_t p = 0; p < n_pairs; ++p) {
+            pool.help_until_done(pending[p]);
+            const size_t b = slot_begin[p], e = slot_begin[p + 1];
+            if (e > b && ce == cudaSuccess)
+                ce = cudaMemcpyAsync((void *)(ctx->A.in_aos + b), ctx->h_stage + b, (e - b) * sizeof(float4), cudaMemcpyHostToDevice,
+                                     ctx->stream);
+        }
+        CK(ce);
+    } else
     for (size_t p = 0; p < n_pairs; ++p) {
         PairConst &pc = ctx->h_pc[p];
         for (int s = 0; s < kNumSegs; ++s) {
             const mulls_cloud_view &v = (s < kNumClasses) ? tgt[p * kNumClasses + s] : src[p * kNumClasses + (s - kNumClasses)];
             pc.in_ptr[s] = ctx->A.in_aos + 3 * (size_t)pc.in_off[s];
+            pc.in_fmt[s] = kFmtRows48;
             if (v.n == 0) continue;
             if (tgt_on_device && s < kNumClasses) { // the view already points into HBM (device-resident local map)
                 pc.in_ptr[s] = (const float4 *)v.aos48;

@@ -237,6 +237,10 @@ class PipelinedContext:
             c.close()
         self.pool.shutdown()
 
+    def set_tunable(self, name: str, value: int):
+        for c in self.lanes:
+            c.set_tunable(name, value)
+
     def _split(self, pairs):
         n, k = len(pairs), len(self.lanes)
         bounds = [(n * i) // k for i in range(k + 1)]

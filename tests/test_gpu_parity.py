@@ -341,3 +341,69 @@ def test_normal_shooting_correspondences(ctx, oracle_mod, small_pair):
     tiny = dict(small_pair, params=p, tgt=[t[:7] for t in small_pair["tgt"]])  # fewer than 10 targets per class
     g, gt, o, ot = run_both(ctx, oracle_mod, tiny)
     assert g["code"] == o["code"] and g["n_corr"] == o["n_corr"]
+
+
+def test_host_packed_wire_format_is_bit_identical(oracle_mod, small_pair):
+    """The "host_pack" tunable repacks the 48-byte rows to the 28 B (32 B with motion undistortion) wire format on
+    the host cores before the DMA (csrc/host_pack.h). Every result bit must be the same as with the raw rows: one
+    context, a pipelined context (lanes share the worker pool), resident re-runs, the undistortion variant (format 2),
+    ragged / empty classes, and the resident-map path (device rows for the target, packed source)."""
+    from mulls_b200.map_manager import LocalMap
+    from mulls_b200.registration import Context
+
+    rng = np.random.default_rng(11)
+    src_u = [s.copy() for s in small_pair["src"]]
+    for s in src_u:
+        s[:, 9] = rng.uniform(-0.05, 1.05, len(s)).astype(np.float32)
+    pu = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    pu.apply_motion_undistortion_while_registration = 1
+    init = np.eye(4)
+    init[:3, :3] = synth.rpy_matrix(0.002, -0.001, 0.012)
+    init[:3, 3] = (0.9, 0.04, 0.01)
+    undist = dict(small_pair, src=src_u, params=pu, init_guess=init)
+    ragged = dict(small_pair, src=[small_pair["src"][0][:1001], small_pair["src"][1][:3], small_pair["src"][2][:2502],
+                                   small_pair["src"][3][:0], small_pair["src"][4][:7], small_pair["src"][5]])
+    pairs = [small_pair, undist, synth.make_pair(1003, "small"), ragged, small_pair]
+
+    raw = Context(0, 5, 100000, 100000)
+    ref, ref_tr = raw.run_batch(pairs, want_trace=True)
+    o, _ = oracle_mod.icp_run(undist["tgt"], undist["src"], undist["params"], undist["init_guess"])
+    assert ref[1]["code"] == o["code"] and ref[1]["n_corr"] == o["n_corr"]
+
+    def same(got, got_tr=None):
+        for i, (a, b) in enumerate(zip(ref, got)):
+            assert a["code"] == b["code"] and a["iters"] == b["iters"] and a["n_corr"] == b["n_corr"], i
+            np.testing.assert_array_equal(a["T"], b["T"])
+            np.testing.assert_array_equal(a["info"], b["info"])
+            if got_tr is not None:
+                np.testing.assert_array_equal(ref_tr[i]["atpa"], got_tr[i]["atpa"])
+
+    raw.set_tunable("host_pack", 1)
+    raw.set_tunable("pack_threads", 3)
+    same(*raw.run_batch(pairs, want_trace=True))
+    raw.upload(pairs)
+    same(raw.run_resident()[0])
+    same(raw.run_resident()[0])
+    one, _ = raw.run_batch([ragged])
+    np.testing.assert_array_equal(one[0]["T"], ref[3]["T"])
+    raw.close()
+
+    pipe = Context(0, 5, 100000, 100000, lanes=3)
+    pipe.set_tunable("host_pack", 1)
+    same(*pipe.run_batch(pairs, want_trace=True))
+    pipe.upload(pairs)
+    same(pipe.run_resident()[0])
+    pipe.close()
+
+    # resident map as the target (rows stay in HBM as 48-byte rows), packed source
+    pr = synth.make_pair(21, "small")
+    ctx = Context(0, 1, 60000, 60000)
+    lm = LocalMap(ctx, 1 << 16)
+    lm.set(pr["tgt"], np.eye(4))
+    r0, t0 = lm.icp_run(pr["src"], pr["params"], pr["init_guess"], want_trace=True)
+    ctx.set_tunable("host_pack", 1)
+    r1, t1 = lm.icp_run(pr["src"], pr["params"], pr["init_guess"], want_trace=True)
+    assert r0["code"] == r1["code"] == 1
+    assert np.array_equal(r0["T"], r1["T"]) and np.array_equal(t0["atpa"], t1["atpa"])
+    lm.close()
+    ctx.close()
