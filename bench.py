@@ -163,7 +163,7 @@ def cpu_reference_rate(pairs, budget_s, max_regs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=32, help="scan pairs per GPU per step")
@@ -298,7 +298,7 @@ def main():
         barrier()
     best_hp = min(e2e_variants, key=e2e_variants.get)
     e2e_s = e2e_variants[best_hp]
-    pipe.set_tunable("host_pack", 0)
+    pipe.set_tunable("host_pack", 2)  # the library default (pack when a call ships >= 2^18 points)
     if len(sampler.lines) < 3:  # very short runs: keep the GPU under the same load until a few samples exist
         t_fill = time.perf_counter()
         while len(sampler.lines) < 3 and time.perf_counter() - t_fill < 2.0:

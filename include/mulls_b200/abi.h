@@ -23,6 +23,7 @@
  *   mulls_map_update         <- lo::MapManager::update_local_map, src/map_manager.cpp:17-145
  *   mulls_classify_nground   <- lo::CFilter<PointT>::classify_nground_pts, include/common/cfilter.hpp:2058-2290
  *   mulls_icp_run_to_map     <- mm_lls_icp with block1 = the device-resident local map
+ *   mulls_fast_ground_filter <- lo::CFilter<PointT>::fast_ground_filter, include/common/cfilter.hpp:1658-2036
  *
  * Plain C, plain pointers and sizes. No torch / Eigen / PCL types cross this boundary; the C++ shim
  * in include/common/cregistration.hpp converts Eigen/PCL objects to these PODs.
@@ -325,6 +326,47 @@ typedef struct mulls_classify_out {
 void mulls_classify_default_params(mulls_classify_params *p);
 int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_classify_params *params,
                            mulls_classify_out *out);
+
+/* ---- Ground segmentation (first half) ---------------------------------------------------
+ * lo::CFilter<PointT>::fast_ground_filter, include/common/cfilter.hpp:1658-2036: 2-D grid over the cloud, lowest point
+ * per cell and per 3x3 neighbourhood, two height thresholds -> ground / non-ground, rate-based down-sampling by the
+ * position inside the cell, and (estimate_ground_normal_method 3, the default) a RANSAC plane per ground cell
+ * (estimate_ground_normal_by_ransac :2038-2054 -> CProceesing::plane_seg_ransac cprocessing.hpp:67-105 ->
+ * pcl::SACSegmentation, SACMODEL_PLANE / SAC_RANSAC, optimize coefficients; PCL 1.10 semantics restated). The first
+ * stage of extract_semantic_pts (:2355-2361); its `cloud_unground` is the input of mulls_classify_nground. */
+typedef struct mulls_ground_params { /* argument names of :1658-1672; defaults = extract_semantic_pts / mulls_slam gflags */
+    int32_t min_grid_pt_num;                     /* 10  (gf_grid_min_pt_num) */
+    float grid_resolution;                       /* 3.0 (gf_grid_size) */
+    float max_height_difference;                 /* 0.3 (gf_in_grid_h_thre) */
+    float neighbor_height_diff;                  /* 1.5 (gf_neigh_grid_h_thre) */
+    float max_ground_height;                     /* 5.0 (gf_max_h) */
+    int32_t ground_random_down_rate;             /* 15  (gf_ground_down_rate) */
+    int32_t ground_random_down_down_rate;        /* 2   (gf_down_down_rate) */
+    int32_t nonground_random_down_rate;          /* 3   (gf_nonground_down_rate) */
+    int32_t reliable_neighbor_grid_num_thre;     /* 0 */
+    int32_t estimate_ground_normal_method;       /* 3; 0 = (0,0,1), 3 = RANSAC per cell; 1 and 2: MULLS_E_UNSUPPORTED */
+    float normal_estimation_radius;              /* 2.0; only read by method 1 */
+    int32_t distance_weight_downsampling_method; /* 2 (dist_inverse_sampling_method): 0 off, 1 linear, 2 quadratic */
+    float standard_distance;                     /* 15.0 (unit_dist) */
+    int32_t fixed_num_downsampling;              /* 0 */
+    int32_t down_ground_fixed_num;               /* 300 (ground_down_fixed_num) */
+    float intensity_thre;                        /* FLT_MAX */
+    int32_t apply_grid_wise_outlier_filter;      /* 0 (extract_semantic_pts passes apply_scanner_filter here, :2361) */
+    float outlier_std_scale;                     /* 3.0 */
+    uint32_t random_seed; /* seed of random_downsample_pcl (fixed_num_downsampling); pcl::RandomSample is time-seeded */
+} mulls_ground_params;
+
+typedef struct mulls_ground_out {
+    float *ground;      /* cloud_ground: caller buffers of `cap` 48-byte rows each (NULL: not wanted) */
+    float *ground_down; /* cloud_ground_down */
+    float *unground;    /* cloud_unground; row[3] = approximate height above ground (:1752, :1880, :1894) */
+    size_t cap;         /* cloud_in.n rows are always enough */
+    size_t n_ground, n_ground_down, n_unground;
+} mulls_ground_out;
+
+void mulls_ground_default_params(mulls_ground_params *p);
+int mulls_fast_ground_filter(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_ground_params *params,
+                             mulls_ground_out *out);
 
 /* The wire format the library ships host clouds in when the "host_pack" tunable is on (csrc/host_pack.h): the 28 of the
  * 48 bytes of a pcl::PointXYZINormal row (utility.hpp:40) that the path reads, repacked on the host cores into pinned

@@ -176,6 +176,43 @@ class ClassifyOut(C.Structure):
     ]
 
 
+class GroundParams(C.Structure):
+    """mulls_ground_params: the arguments of CFilter::fast_ground_filter (cfilter.hpp:1658-1672)."""
+    _fields_ = [
+        ("min_grid_pt_num", C.c_int32),
+        ("grid_resolution", C.c_float),
+        ("max_height_difference", C.c_float),
+        ("neighbor_height_diff", C.c_float),
+        ("max_ground_height", C.c_float),
+        ("ground_random_down_rate", C.c_int32),
+        ("ground_random_down_down_rate", C.c_int32),
+        ("nonground_random_down_rate", C.c_int32),
+        ("reliable_neighbor_grid_num_thre", C.c_int32),
+        ("estimate_ground_normal_method", C.c_int32),
+        ("normal_estimation_radius", C.c_float),
+        ("distance_weight_downsampling_method", C.c_int32),
+        ("standard_distance", C.c_float),
+        ("fixed_num_downsampling", C.c_int32),
+        ("down_ground_fixed_num", C.c_int32),
+        ("intensity_thre", C.c_float),
+        ("apply_grid_wise_outlier_filter", C.c_int32),
+        ("outlier_std_scale", C.c_float),
+        ("random_seed", C.c_uint32),
+    ]
+
+
+class GroundOut(C.Structure):
+    _fields_ = [
+        ("ground", C.POINTER(C.c_float)),
+        ("ground_down", C.POINTER(C.c_float)),
+        ("unground", C.POINTER(C.c_float)),
+        ("cap", C.c_size_t),
+        ("n_ground", C.c_size_t),
+        ("n_ground_down", C.c_size_t),
+        ("n_unground", C.c_size_t),
+    ]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
 
 # every symbol include/mulls_b200/abi.h declares
@@ -204,6 +241,8 @@ EXPORTED_SYMBOLS = (
     "mulls_classify_nground",
     "mulls_set_tunable",
     "mulls_pack_rows",
+    "mulls_ground_default_params",
+    "mulls_fast_ground_filter",
 )
 
 _LIB = None
@@ -253,6 +292,10 @@ def load_library() -> C.CDLL:
                                           C.POINTER(IcpTrace)]
     lib.mulls_pca_features.restype = C.c_int
     lib.mulls_pca_features.argtypes = [vp, CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(PcaOut)]
+    lib.mulls_ground_default_params.restype = None
+    lib.mulls_ground_default_params.argtypes = [C.POINTER(GroundParams)]
+    lib.mulls_fast_ground_filter.restype = C.c_int
+    lib.mulls_fast_ground_filter.argtypes = [vp, CloudView, C.POINTER(GroundParams), C.POINTER(GroundOut)]
     lib.mulls_pack_rows.restype = C.c_int
     lib.mulls_pack_rows.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     lib.mulls_set_tunable.restype = C.c_int
@@ -441,3 +484,44 @@ def classify_call(fn, handle, cloud: np.ndarray, params: ClassifyParams) -> dict
     if rc != 0:
         return {"rc": rc}
     return {OUT_NAMES[k]: np.ascontiguousarray(bufs[k][: out.n[k]]) for k in range(OUT_COUNT)}
+
+
+def default_ground_params() -> GroundParams:
+    """Defaults of fast_ground_filter as extract_semantic_pts is called by test/mulls_slam.cpp (gflags :78-104) — pure Python."""
+    p = GroundParams()
+    p.min_grid_pt_num = 10
+    p.grid_resolution = 3.0
+    p.max_height_difference = 0.3
+    p.neighbor_height_diff = 1.5
+    p.max_ground_height = 5.0
+    p.ground_random_down_rate = 15
+    p.ground_random_down_down_rate = 2
+    p.nonground_random_down_rate = 3
+    p.reliable_neighbor_grid_num_thre = 0
+    p.estimate_ground_normal_method = 3
+    p.normal_estimation_radius = 2.0
+    p.distance_weight_downsampling_method = 2
+    p.standard_distance = 15.0
+    p.fixed_num_downsampling = 0
+    p.down_ground_fixed_num = 300
+    p.intensity_thre = 3.4028234663852886e38
+    p.apply_grid_wise_outlier_filter = 0
+    p.outlier_std_scale = 3.0
+    p.random_seed = 0
+    return p
+
+
+def ground_call(fn, handle, cloud: np.ndarray, params: GroundParams) -> dict:
+    """Shared marshalling of mulls_fast_ground_filter / its CPU restatement: {"ground", "ground_down", "unground"}."""
+    cloud = as_aos48(cloud)
+    n = max(cloud.shape[0], 1)
+    bufs = [np.zeros((n, 12), np.float32) for _ in range(3)]
+    fp = C.POINTER(C.c_float)
+    out = GroundOut(bufs[0].ctypes.data_as(fp), bufs[1].ctypes.data_as(fp), bufs[2].ctypes.data_as(fp), n, 0, 0, 0)
+    args = ([handle] if handle is not None else []) + [cloud_view(cloud), C.byref(params), C.byref(out)]
+    rc = fn(*args)
+    if rc != 0:
+        return {"rc": rc}
+    return {"ground": np.ascontiguousarray(bufs[0][: out.n_ground]),
+            "ground_down": np.ascontiguousarray(bufs[1][: out.n_ground_down]),
+            "unground": np.ascontiguousarray(bufs[2][: out.n_unground])}

@@ -93,16 +93,16 @@ class PackPool {
         static PackPool *pool = new PackPool(); // never destroyed: the workers are detached and outlive static teardown
         return *pool;
     }
-    // make sure at least `n` workers exist (n <= 0: the default, MULLS_PACK_THREADS or a quarter of the host cores)
+    // make sure at least `n` workers exist (n <= 0: the default, MULLS_PACK_THREADS or hw/16 clamped to 2..8)
     void ensure_workers(int n) {
         if (n <= 0) {
             const char *env = std::getenv("MULLS_PACK_THREADS");
             n = env ? std::atoi(env) : 0;
             if (n <= 0) {
                 const int hw = (int)std::thread::hardware_concurrency();
-                n = hw / 4;
+                n = hw / 16; // measured on a 128-core host: 4-8 workers feed PCIe, more only contend for memory
                 if (n < 2) n = 2;
-                if (n > 32) n = 32;
+                if (n > 8) n = 8;
             }
         }
         std::lock_guard<std::mutex> lk(m_);

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "device_types.cuh"
 #include "host_pack.h"
@@ -19,6 +20,7 @@
 #include "kernels_pca.cuh"
 #include "kernels_map.cuh"
 #include "kernels_classify.cuh"
+#include "kernels_ground.cuh"
 
 using namespace mulls;
 
@@ -55,7 +57,10 @@ struct mulls_ctx {
     int defer_scan = 2;    // queue the leaves of a block and scan them together: 0 off, 1 on, 2 from iteration 2 on
     int packet_max_ext_mm = 0; // packet search for warps whose union search box is at most this wide (0 = off)
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
-    int host_pack = 0;     // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h)
+    // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h):
+    // 0 never, 1 always, 2 when a call ships at least kPackMinPoints points (small calls are latency-bound: raw rows)
+    int host_pack = 2;
+    int stage_wc = 0;      // allocate the pinned staging write-combined (the host only streams into it)
     float4 *h_stage = nullptr; // pinned staging of the packed clouds (allocated on first use)
     size_t h_stage_slots = 0;
     float h0_min = 0.125f;
@@ -75,6 +80,9 @@ struct mulls_ctx {
     // classification scratch (mulls_classify_nground)
     void *cls_buf = nullptr;
     size_t cls_buf_bytes = 0;
+    // ground-filter scratch (mulls_fast_ground_filter): per-point part and per-cell part
+    void *gf_buf = nullptr, *gf_cell_buf = nullptr;
+    size_t gf_buf_bytes = 0, gf_cell_buf_bytes = 0;
     // the local map whose clouds the target slices of pair 0 currently index (set by mulls_icp_run_to_map, cleared
     // by any other upload): what block1->tree_* are to MapManager::map_based_dynamic_close_removal
     const mulls_map *tree_map = nullptr;
@@ -143,6 +151,8 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->cub_temp) cudaFree(ctx->cub_temp);
     if (ctx->pca_buf) cudaFree(ctx->pca_buf);
     if (ctx->cls_buf) cudaFree(ctx->cls_buf);
+    if (ctx->gf_buf) cudaFree(ctx->gf_buf);
+    if (ctx->gf_cell_buf) cudaFree(ctx->gf_cell_buf);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_running) cudaFreeHost(ctx->h_running);
@@ -348,6 +358,14 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "defer_scan") ctx->defer_scan = value;
     else if (n == "host_pack") ctx->host_pack = value;
+    else if (n == "stage_wc") {
+        if (ctx->stage_wc != value && ctx->h_stage) { // re-allocated with the new flag on the next packed upload
+            cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr;
+            ctx->h_stage_slots = 0;
+        }
+        ctx->stage_wc = value;
+    }
     else if (n == "pack_threads") PackPool::get().ensure_workers(value);
     else if (n == "packet_max_ext_mm") ctx->packet_max_ext_mm = value;
     else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
@@ -535,11 +553,17 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     }
     // the clouds: repacked on the host cores and copied pair by pair (host_pack), or copied as they are, or read in
     // place (zero-copy, pinned host buffers of one-shot calls)
-    const bool pack = ctx->host_pack != 0;
+    size_t host_points = 0;
+    for (size_t p = 0; p < n_pairs; ++p)
+        for (int s = 0; s < kNumSegs; ++s)
+            if (!(tgt_on_device && s < kNumClasses)) host_points += ctx->h_pc[p].in_n[s];
+    const size_t kPackMinPoints = 1u << 18;
+    const bool pack = ctx->host_pack == 1 || (ctx->host_pack == 2 && host_points >= kPackMinPoints);
     if (pack) {
         if (!ctx->h_stage) {
             const size_t slots = 2 * ctx->cap_in + 4 * kNumSegs * ctx->max_pairs;
-            CK(cudaMallocHost((void **)&ctx->h_stage, slots * sizeof(float4)));
+            CK(cudaHostAlloc((void **)&ctx->h_stage, slots * sizeof(float4),
+                             ctx->stage_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
             ctx->h_stage_slots = slots;
         }
         PackPool &pool = PackPool::get();
@@ -1547,6 +1571,237 @@ int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mull
             return MULLS_E_CAPACITY;
         }
         CK(cudaMemcpyAsync(out->rows[k], src[k], cnt[k] * row_b, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev_end, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats = mulls_run_stats();
+    ctx->stats.kernel_launches = launches;
+    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev_begin, ctx->ev_end);
+    return MULLS_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Ground segmentation (CFilter::fast_ground_filter, cfilter.hpp:1658-2036)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// first kSacDraws outputs of boost::mt19937 seeded with 12345u (every pcl::SampleConsensusModel object starts there)
+const uint32_t *sac_draw_table() {
+    static std::vector<uint32_t> tab;
+    if (tab.empty()) {
+        std::vector<uint32_t> t(kSacDraws);
+        uint32_t mt[624];
+        mt[0] = 12345u;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        int idx = 624;
+        for (int k = 0; k < kSacDraws; ++k) {
+            if (idx >= 624) {
+                for (int i = 0; i < 624; ++i) {
+                    const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                    mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                }
+                idx = 0;
+            }
+            uint32_t y = mt[idx++];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            t[k] = y;
+        }
+        tab.swap(t);
+    }
+    return tab.data();
+}
+int host_ord(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i >= 0 ? i : (i ^ 0x7fffffff);
+}
+} // namespace
+
+extern "C" {
+
+void mulls_ground_default_params(mulls_ground_params *p) { // extract_semantic_pts as test/mulls_slam.cpp calls it (gflags :78-104)
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->min_grid_pt_num = 10;
+    p->grid_resolution = 3.0f;
+    p->max_height_difference = 0.3f;
+    p->neighbor_height_diff = 1.5f;
+    p->max_ground_height = 5.0f;
+    p->ground_random_down_rate = 15;
+    p->ground_random_down_down_rate = 2;
+    p->nonground_random_down_rate = 3;
+    p->reliable_neighbor_grid_num_thre = 0;
+    p->estimate_ground_normal_method = 3;
+    p->normal_estimation_radius = 2.0f;
+    p->distance_weight_downsampling_method = 2;
+    p->standard_distance = 15.0f;
+    p->fixed_num_downsampling = 0;
+    p->down_ground_fixed_num = 300;
+    p->intensity_thre = FLT_MAX;
+    p->apply_grid_wise_outlier_filter = 0;
+    p->outlier_std_scale = 3.0f;
+    p->random_seed = 0;
+}
+
+int mulls_fast_ground_filter(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_ground_params *params,
+                             mulls_ground_out *out) {
+    if (!ctx || !params || !out || (cloud_in.n > 0 && !cloud_in.aos48)) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    const mulls_ground_params &P = *params;
+    if (P.estimate_ground_normal_method != 0 && P.estimate_ground_normal_method != 3) {
+        ctx->err = "mulls_fast_ground_filter: estimate_ground_normal_method 1 / 2 (pcl::NormalEstimation) are not implemented";
+        return MULLS_E_UNSUPPORTED;
+    }
+    if (P.ground_random_down_rate < 1 || P.nonground_random_down_rate < 1 || P.ground_random_down_down_rate < 1 ||
+        !(P.grid_resolution > 0.f)) {
+        ctx->err = "mulls_fast_ground_filter: the down-sampling rates must be >= 1 and grid_resolution positive";
+        return MULLS_E_ARG;
+    }
+    out->n_ground = out->n_ground_down = out->n_unground = 0;
+    const size_t n = cloud_in.n;
+    if (n == 0) return MULLS_OK;
+    if (n > ctx->max_tgt || n >= (1ull << 31)) {
+        ctx->err = "mulls_fast_ground_filter: cloud exceeds max_tgt_pts of the context";
+        return MULLS_E_CAPACITY;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // temporary storage of the library sort / scans
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)n, 0, 32, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, st);
+    // per-point scratch
+    const size_t row_b = 48;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_rows = take(n * row_b), o_g = take(n * row_b), o_gd = take(n * row_b), o_u = take(n * row_b);
+    const size_t o_key = take(4 * n), o_idx = take(4 * n), o_keys = take(4 * n), o_idxs = take(4 * n), o_call = take(4 * n);
+    const size_t o_hf = take(4 * n), o_hp = take(4 * n), o_dec = take(n), o_cand = take(16 * n), o_shuf = take(4 * n), o_inl = take(n);
+    const size_t o_st = take(sizeof(GfState)), o_draws = take(kSacDraws * sizeof(uint32_t));
+    const size_t o_tmp = take(std::max(sort_bytes, scan_bytes));
+    if (off > ctx->gf_buf_bytes) {
+        if (ctx->gf_buf) cudaFree(ctx->gf_buf);
+        ctx->gf_buf = nullptr;
+        ctx->gf_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->gf_buf, off));
+        ctx->gf_buf_bytes = off;
+    }
+    char *base = (char *)ctx->gf_buf;
+    GfArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.P = P;
+    A.n = (uint32_t)n;
+    A.rows = (const float4 *)(base + o_rows);
+    A.out_ground = (float4 *)(base + o_g);
+    A.out_ground_down = (float4 *)(base + o_gd);
+    A.out_unground = (float4 *)(base + o_u);
+    A.key = (uint32_t *)(base + o_key), A.idx = (uint32_t *)(base + o_idx);
+    A.key_s = (uint32_t *)(base + o_keys), A.idx_s = (uint32_t *)(base + o_idxs);
+    A.cell_all = (int *)(base + o_call);
+    A.high_flag = (uint32_t *)(base + o_hf), A.high_pos = (uint32_t *)(base + o_hp);
+    A.decision = (uint8_t *)(base + o_dec);
+    A.cand = (float4 *)(base + o_cand);
+    A.shuf = (int *)(base + o_shuf);
+    A.inl = (uint8_t *)(base + o_inl);
+    A.st = (GfState *)(base + o_st);
+    A.draws = (const uint32_t *)(base + o_draws);
+    void *tmp = base + o_tmp;
+    size_t tmp_bytes = std::max(sort_bytes, scan_bytes);
+    CK(cudaEventRecord(ctx->ev_begin, st));
+    CK(cudaMemcpyAsync((void *)A.rows, cloud_in.aos48, n * row_b, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void *)A.draws, sac_draw_table(), kSacDraws * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    GfState hs;
+    std::memset(&hs, 0, sizeof(hs));
+    hs.bb[0] = hs.bb[1] = host_ord(FLT_MAX);
+    hs.bb[2] = hs.bb[3] = host_ord(-FLT_MAX);
+    CK(cudaMemcpyAsync(A.st, &hs, sizeof(GfState), cudaMemcpyHostToDevice, st));
+    uint64_t launches = 0;
+    const unsigned pb = (unsigned)ceil_div(n, kGfBlock);
+    k_gf_bbox<<<pb, kGfBlock, 0, st>>>(A);
+    k_gf_setup<<<1, 32, 0, st>>>(A);
+    launches += 2;
+    CK(cudaMemcpyAsync(&hs, A.st, sizeof(GfState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hs.num_grid < 0 || hs.num_grid > (1 << 26)) {
+        ctx->err = "mulls_fast_ground_filter: the cloud spans more than 2^26 grid cells (outliers far from the scan?)";
+        return MULLS_E_CAPACITY;
+    }
+    const int num_grid = hs.num_grid;
+    if (num_grid > 0) { // (a degenerate cloud with zero extent along x or y has no cell: every point fails the id test)
+        const size_t g = (size_t)num_grid;
+        size_t coff = 0;
+        auto ctake = [&](size_t bytes) {
+            const size_t o = coff;
+            coff += (bytes + 255) / 256 * 256;
+            return o;
+        };
+        const size_t c_start = ctake(4 * g), c_end = ctake(4 * g), c_minz = ctake(4 * g), c_nb = ctake(4 * g), c_oth = ctake(4 * g);
+        const size_t c_rel = ctake(4 * g), c_nrm = ctake(16 * g), c_ng = ctake(4 * g), c_nu = ctake(4 * g), c_og = ctake(4 * g),
+                     c_ou = ctake(4 * g);
+        size_t cscan = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cscan, (uint32_t *)nullptr, (uint32_t *)nullptr, num_grid, st);
+        const size_t c_tmp = ctake(cscan);
+        if (coff > ctx->gf_cell_buf_bytes) {
+            if (ctx->gf_cell_buf) cudaFree(ctx->gf_cell_buf);
+            ctx->gf_cell_buf = nullptr;
+            ctx->gf_cell_buf_bytes = 0;
+            CK(cudaMalloc(&ctx->gf_cell_buf, coff));
+            ctx->gf_cell_buf_bytes = coff;
+        }
+        char *cb = (char *)ctx->gf_cell_buf;
+        A.cell_start = (uint32_t *)(cb + c_start), A.cell_end = (uint32_t *)(cb + c_end);
+        A.min_z = (float *)(cb + c_minz), A.neighbor_min_z = (float *)(cb + c_nb), A.outlier_thre = (float *)(cb + c_oth);
+        A.reliable = (int *)(cb + c_rel);
+        A.cell_normal = (float4 *)(cb + c_nrm);
+        A.cell_ng = (uint32_t *)(cb + c_ng), A.cell_nu = (uint32_t *)(cb + c_nu);
+        A.cell_og = (uint32_t *)(cb + c_og), A.cell_ou = (uint32_t *)(cb + c_ou);
+        void *ctmp = cb + c_tmp;
+        CK(cudaMemsetAsync(A.cell_start, 0, 4 * g, st));
+        CK(cudaMemsetAsync(A.cell_end, 0, 4 * g, st));
+        const unsigned wb = (unsigned)ceil_div(g * 32, kGfBlock), cbk = (unsigned)ceil_div(g, kGfBlock);
+        k_gf_assign<<<pb, kGfBlock, 0, st>>>(A);
+        size_t b1 = tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(tmp, b1, A.key, A.key_s, A.idx, A.idx_s, (int)n, 0, 32, st));
+        k_gf_bounds<<<pb, kGfBlock, 0, st>>>(A);
+        k_gf_cell_min<<<wb, kGfBlock, 0, st>>>(A, num_grid);
+        k_gf_neighbors<<<cbk, kGfBlock, 0, st>>>(A, num_grid);
+        k_gf_high<<<pb, kGfBlock, 0, st>>>(A);
+        size_t b2 = tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(tmp, b2, A.high_flag, A.high_pos, (int)n, st));
+        k_gf_high_emit<<<pb, kGfBlock, 0, st>>>(A);
+        k_gf_cell_decide<<<wb, kGfBlock, 0, st>>>(A, num_grid);
+        size_t b3 = cscan;
+        CK(cub::DeviceScan::ExclusiveSum(ctmp, b3, A.cell_ng, A.cell_og, num_grid, st));
+        b3 = cscan;
+        CK(cub::DeviceScan::ExclusiveSum(ctmp, b3, A.cell_nu, A.cell_ou, num_grid, st));
+        k_gf_totals<<<1, 1, 0, st>>>(A, num_grid);
+        k_gf_cell_emit<<<wb, kGfBlock, 0, st>>>(A, num_grid);
+        k_gf_down<<<1, kClsBlock, 0, st>>>(A);
+        launches += 11;
+        CK(cudaMemcpyAsync(&hs, A.st, sizeof(GfState), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        out->n_ground = hs.n_ground, out->n_ground_down = hs.n_ground_down, out->n_unground = hs.n_unground;
+        if (hs.n_ground > out->cap || hs.n_unground > out->cap) {
+            ctx->err = "mulls_fast_ground_filter: output buffer too small";
+            return MULLS_E_CAPACITY;
+        }
+        if (out->ground && hs.n_ground)
+            CK(cudaMemcpyAsync(out->ground, A.out_ground, hs.n_ground * row_b, cudaMemcpyDeviceToHost, st));
+        if (out->ground_down && hs.n_ground_down)
+            CK(cudaMemcpyAsync(out->ground_down, A.out_ground_down, hs.n_ground_down * row_b, cudaMemcpyDeviceToHost, st));
+        if (out->unground && hs.n_unground)
+            CK(cudaMemcpyAsync(out->unground, A.out_unground, hs.n_unground * row_b, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaEventRecord(ctx->ev_end, st));
     CK(cudaStreamSynchronize(st));

@@ -212,6 +212,13 @@ class Context:
             self._check(res["rc"])
         return res
 
+    def fast_ground_filter(self, cloud_in: np.ndarray, params: abi.GroundParams) -> dict:
+        """CFilter::fast_ground_filter (cfilter.hpp:1658-2036) on the GPU: {"ground", "ground_down", "unground"} rows."""
+        res = abi.ground_call(self.lib.mulls_fast_ground_filter, self.handle, cloud_in, params)
+        if "rc" in res:
+            self._check(res["rc"])
+        return res
+
     def stats(self) -> dict:
         s = abi.RunStats()
         self._check(self.lib.mulls_get_stats(self.handle, C.byref(s)))

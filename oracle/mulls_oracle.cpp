@@ -1865,6 +1865,400 @@ static void classify_nground(Rows &cloud_in, const mulls_classify_params &P, Row
 
 } // namespace
 
+// ---------------------------------------------------------------------------------------------
+// CFilter::fast_ground_filter, cfilter.hpp:1658-2036 (+ estimate_ground_normal_by_ransac :2038-2054,
+// CProceesing::plane_seg_ransac cprocessing.hpp:67-105). The per-cell plane is pcl::SACSegmentation<PointT> with
+// SACMODEL_PLANE / SAC_RANSAC / setOptimizeCoefficients(true) [3P]: PCL 1.10's RandomSampleConsensus::computeModel,
+// SampleConsensusModel::getSamples / drawIndexSample (boost::mt19937 seeded with 12345u per model object,
+// boost::uniform_int<>(0, INT_MAX) => rnd() = mt() >> 1), SampleConsensusModelPlane::{isSampleGood,
+// computeModelCoefficients, countWithinDistance, selectWithinDistance, optimizeModelCoefficients},
+// pcl::computeMeanAndCovarianceMatrix (float accumulators) and pcl::eigen33 / computeRoots, restated from the
+// published 1.10 sources. The float trigonometry of computeRoots (atan2f / cosf / sinf) is evaluated in double and
+// rounded to float (what a correctly rounded libm returns; the CUDA path does the same so that both sides agree bit
+// for bit). Eigen's 4-wide reductions are written in their SSE packet order and marked [ORDER].
+// ---------------------------------------------------------------------------------------------
+static const int kSacDraws = 16384; // mt19937 outputs available to one plane fit (5461 sample attempts)
+static const uint32_t *sac_draw_table() {
+    static std::vector<uint32_t> tab;
+    if (tab.empty()) {
+        // boost::mt19937 == std::mt19937 [3P]; written out to stay free of <random> implementation questions
+        uint32_t mt[624];
+        mt[0] = 12345u;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        int idx = 624;
+        tab.resize(kSacDraws);
+        for (int k = 0; k < kSacDraws; ++k) {
+            if (idx >= 624) {
+                for (int i = 0; i < 624; ++i) {
+                    const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                    mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                }
+                idx = 0;
+            }
+            uint32_t y = mt[idx++];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            tab[k] = y;
+        }
+    }
+    return tab.data();
+}
+
+// (int)(float) as the x86 cvttss2si the reference build executes: out of range -> INT_MIN
+static inline int to_int_x86(float f) {
+    if (!(f > -2147483904.0f && f < 2147483648.0f)) return std::numeric_limits<int>::min();
+    return (int)f;
+}
+
+// model_coefficients.dot(Vector4f(x, y, z, 1)) [ORDER]: Eigen packet reduction (a0+a2)+(a1+a3)
+static inline float plane_dot(const float c[4], float x, float y, float z) {
+    return (c[0] * x + c[2] * z) + (c[1] * y + c[3] * 1.0f);
+}
+
+// SampleConsensusModelPlane::computeModelCoefficients (sac_model_plane.hpp) [3P]
+static bool plane_from_sample(const Rows &pc, const int s[3], float c[4]) {
+    const float *p0 = pc[s[0]].f, *p1 = pc[s[1]].f, *p2 = pc[s[2]].f;
+    const float a0 = p1[0] - p0[0], a1 = p1[1] - p0[1], a2 = p1[2] - p0[2];
+    const float b0 = p2[0] - p0[0], b1 = p2[1] - p0[1], b2 = p2[2] - p0[2];
+    const float d0 = a0 / b0, d1 = a1 / b1, d2 = a2 / b2;
+    if ((d0 == d1) && (d2 == d1)) return false; // collinear
+    c[0] = a1 * b2 - a2 * b1;
+    c[1] = a2 * b0 - a0 * b2;
+    c[2] = a0 * b1 - a1 * b0;
+    c[3] = 0.0f;
+    const float z = (c[0] * c[0] + c[2] * c[2]) + (c[1] * c[1] + c[3] * c[3]); // squaredNorm [ORDER]
+    if (z > 0.0f) {
+        const float nrm = std::sqrt(z);
+        c[0] /= nrm, c[1] /= nrm, c[2] /= nrm, c[3] /= nrm;
+    }
+    c[3] = -1.0f * ((c[0] * p0[0] + c[2] * p0[2]) + (c[1] * p0[1] + c[3] * p0[3])); // head<4>().dot(p0) [ORDER], c[3] = 0
+    return true;
+}
+
+// pcl::computeRoots2 / computeRoots / eigen33 (common/impl/eigen.hpp), Scalar = float [3P]
+static void sac_roots2(float b, float c, float r[3]) {
+    r[0] = 0.0f;
+    float d = (float)((double)(b * b) - 4.0 * (double)c);
+    if (d < 0.0f) d = 0.0f;
+    const float sd = std::sqrt(d);
+    r[2] = 0.5f * (b + sd);
+    r[1] = 0.5f * (b - sd);
+}
+static void sac_roots(const float m[3][3], float r[3]) {
+    const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+                     m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+    const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+                     m[1][2] * m[1][2];
+    const float c2 = m[0][0] + m[1][1] + m[2][2];
+    if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+        sac_roots2(c2, c1, r);
+        return;
+    }
+    const float s_inv3 = (float)(1.0 / 3.0);
+    const float s_sqrt3 = std::sqrt(3.0f);
+    const float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    const float rho = std::sqrt(-a_over_3);
+    const float theta = (float)std::atan2((double)std::sqrt(-q), (double)half_b) * s_inv3;
+    const float cos_theta = (float)std::cos((double)theta);
+    const float sin_theta = (float)std::sin((double)theta);
+    r[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    if (r[0] >= r[1]) std::swap(r[0], r[1]);
+    if (r[1] >= r[2]) {
+        std::swap(r[1], r[2]);
+        if (r[0] >= r[1]) std::swap(r[0], r[1]);
+    }
+    if (r[0] <= 0.0f) sac_roots2(c2, c1, r);
+}
+static inline void cross3(const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void sac_eigen33_smallest(const float mat[3][3], float evec[3]) {
+    float scale = 0.0f;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(mat[i][j]));
+    if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+    float m[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) m[i][j] = mat[i][j] / scale;
+    float r[3];
+    sac_roots(m, r);
+    for (int i = 0; i < 3; ++i) m[i][i] -= r[0];
+    float v1[3], v2[3], v3[3];
+    cross3(m[0], m[1], v1);
+    cross3(m[0], m[2], v2);
+    cross3(m[1], m[2], v3);
+    const float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]; // fixed-size 3: sequential
+    const float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+    const float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+    const float *v;
+    float len;
+    if (l1 >= l2 && l1 >= l3) v = v1, len = l1;
+    else if (l2 >= l1 && l2 >= l3) v = v2, len = l2;
+    else v = v3, len = l3;
+    const float s = std::sqrt(len);
+    evec[0] = v[0] / s, evec[1] = v[1] / s, evec[2] = v[2] / s;
+}
+
+// pcl::SACSegmentation::segment for a plane, as plane_seg_ransac configures it [3P]. `pc` is the cell's candidate
+// cloud (indices_ = 0..n-1); on success `inliers` (ascending) and the refined coefficients are returned.
+static bool sac_plane_segment(const Rows &pc, double threshold, int max_iterations, std::vector<int> &inliers, float coeff[4]) {
+    const int n = (int)pc.size();
+    inliers.clear();
+    if (n < 3) return false; // getSamples: "Can not select 0 unique points out of n" -> no model
+    const uint32_t *draws = sac_draw_table();
+    int next = 0;
+    std::vector<int> shuffled(n);
+    for (int i = 0; i < n; ++i) shuffled[i] = i;
+    // RandomSampleConsensus::computeModel
+    int iterations = 0, n_best = -std::numeric_limits<int>::max();
+    double k = 1.0;
+    const double log_probability = std::log(1.0 - 0.99);
+    const double one_over_indices = 1.0 / (double)n;
+    unsigned skipped = 0;
+    const unsigned max_skip = (unsigned)max_iterations * 10u;
+    bool have_model = false;
+    float best[4] = {0, 0, 0, 0};
+    while ((double)iterations < k && skipped < max_skip) {
+        int sel[3];
+        bool got = false;
+        for (int iter = 0; iter < 1000 && !got; ++iter) { // getSamples: max_sample_checks_
+            if (next + 3 > kSacDraws) break;              // draw table exhausted (degenerate cell): treated as no sample
+            for (int i = 0; i < 3; ++i) {
+                const uint32_t r = draws[next++] >> 1;    // boost::uniform_int<>(0, INT_MAX) on a 32-bit engine
+                std::swap(shuffled[i], shuffled[i + (int)(r % (uint32_t)(n - i))]);
+            }
+            sel[0] = shuffled[0], sel[1] = shuffled[1], sel[2] = shuffled[2];
+            // isSampleGood
+            const float *p0 = pc[sel[0]].f, *p1 = pc[sel[1]].f, *p2 = pc[sel[2]].f;
+            const float d0 = (p1[0] - p0[0]) / (p2[0] - p0[0]), d1 = (p1[1] - p0[1]) / (p2[1] - p0[1]),
+                        d2 = (p1[2] - p0[2]) / (p2[2] - p0[2]);
+            got = (d0 != d1) || (d2 != d1);
+        }
+        if (!got) break; // "No samples could be selected!"
+        float c[4];
+        if (!plane_from_sample(pc, sel, c)) {
+            ++skipped;
+            continue;
+        }
+        int cnt = 0;
+        for (int i = 0; i < n; ++i)
+            if ((double)std::fabs(plane_dot(c, pc[i].f[0], pc[i].f[1], pc[i].f[2])) < threshold) ++cnt;
+        if (cnt > n_best) {
+            n_best = cnt;
+            have_model = true;
+            std::memcpy(best, c, sizeof(best));
+            const double w = (double)n_best * one_over_indices;
+            double p_no_outliers = 1.0 - std::pow(w, 3.0);
+            p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+            p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+            k = log_probability / std::log(p_no_outliers);
+        }
+        ++iterations;
+        if (iterations > max_iterations) break;
+    }
+    if (!have_model) return false;
+    for (int i = 0; i < n; ++i)
+        if ((double)std::fabs(plane_dot(best, pc[i].f[0], pc[i].f[1], pc[i].f[2])) < threshold) inliers.push_back(i);
+    if (inliers.empty()) return false; // segment(): "No inliers": coefficients stay empty (the reference then reads values[0]: UB)
+    // optimizeModelCoefficients
+    std::memcpy(coeff, best, sizeof(best));
+    if (inliers.size() >= 4) {
+        float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int id : inliers) {
+            const float x = pc[id].f[0], y = pc[id].f[1], z = pc[id].f[2];
+            accu[0] += x * x, accu[1] += x * y, accu[2] += x * z, accu[3] += y * y, accu[4] += y * z, accu[5] += z * z;
+            accu[6] += x, accu[7] += y, accu[8] += z;
+        }
+        const float cnt = (float)inliers.size();
+        for (int i = 0; i < 9; ++i) accu[i] /= cnt;
+        float cov[3][3];
+        cov[0][0] = accu[0] - accu[6] * accu[6];
+        cov[0][1] = accu[1] - accu[6] * accu[7];
+        cov[0][2] = accu[2] - accu[6] * accu[8];
+        cov[1][1] = accu[3] - accu[7] * accu[7];
+        cov[1][2] = accu[4] - accu[7] * accu[8];
+        cov[2][2] = accu[5] - accu[8] * accu[8];
+        cov[1][0] = cov[0][1], cov[2][0] = cov[0][2], cov[2][1] = cov[1][2];
+        float ev[3];
+        sac_eigen33_smallest(cov, ev);
+        coeff[0] = ev[0], coeff[1] = ev[1], coeff[2] = ev[2], coeff[3] = 0.0f;
+        // optimized_coefficients.dot(xyz_centroid), centroid = (mx, my, mz, 1) [ORDER]
+        coeff[3] = -1.0f * ((coeff[0] * accu[6] + coeff[2] * accu[8]) + (coeff[1] * accu[7] + coeff[3] * 1.0f));
+    }
+    inliers.clear();
+    for (int i = 0; i < n; ++i)
+        if ((double)std::fabs(plane_dot(coeff, pc[i].f[0], pc[i].f[1], pc[i].f[2])) < threshold) inliers.push_back(i);
+    return true;
+}
+
+static void fast_ground_filter(Rows &cloud_in, const mulls_ground_params &P, Rows &cloud_ground, Rows &cloud_ground_down,
+                               Rows &cloud_unground) {
+    const int n_in = (int)cloud_in.size();
+    const int min_grid_pt_num = P.min_grid_pt_num;
+    const float grid_resolution = P.grid_resolution, max_height_difference = P.max_height_difference,
+                neighbor_height_diff = P.neighbor_height_diff, max_ground_height = P.max_ground_height;
+    const int ground_random_down_rate = P.ground_random_down_rate, nonground_random_down_rate = P.nonground_random_down_rate;
+    const int method = P.estimate_ground_normal_method, dw_method = P.distance_weight_downsampling_method;
+    const float standard_distance = P.standard_distance, intensity_thre = P.intensity_thre;
+    if (n_in == 0) return;
+    const int reliable_grid_pts_count_thre = min_grid_pt_num - 1; // :1676
+    int count_checkpoint = 0;
+    float sum_height = 0.001;
+    const float underground_noise_thre = -std::numeric_limits<float>::max();
+    for (int j = 0; j < n_in; ++j) // :1688-1695
+        if (j % 100 == 0) {
+            sum_height += cloud_in[j].f[RZ];
+            count_checkpoint++;
+        }
+    const float appro_mean_height = sum_height / count_checkpoint;
+    const float non_ground_height_thre = appro_mean_height + max_ground_height;
+    // get_cloud_bbx (utility.hpp:817-847): doubles
+    double min_x = 1.7976931348623157e308, min_y = min_x, max_x = -min_x, max_y = -min_x;
+    for (int i = 0; i < n_in; ++i) {
+        const double x = cloud_in[i].f[RX], y = cloud_in[i].f[RY];
+        if (min_x > x) min_x = x;
+        if (min_y > y) min_y = y;
+        if (max_x < x) max_x = x;
+        if (max_y < y) max_y = y;
+    }
+    const int row = (int)std::ceil((max_y - min_y) / grid_resolution); // :1710-1713
+    const int col = (int)std::ceil((max_x - min_x) / grid_resolution);
+    const int num_grid = row * col;
+    struct Grid { // grid_t, cfilter.hpp:45-69
+        std::vector<int> point_id;
+        float min_z = 0.f, min_z_outlier_thre = -std::numeric_limits<float>::max(), neighbor_min_z = 0.f;
+        int pts_count = 0, reliable_neighbor_grid_num = 0;
+        float dist2station = 0.001f;
+    };
+    std::vector<Grid> grid(std::max(num_grid, 0));
+    for (int i = 0; i < num_grid; ++i) grid[i].min_z = grid[i].neighbor_min_z = std::numeric_limits<float>::max();
+    float distance_weight;
+    for (int j = 0; j < n_in; ++j) { // :1728-1766
+        Row &pt = cloud_in[j];
+        const int temp_col = (int)std::floor((pt.f[RX] - min_x) / grid_resolution);
+        const int temp_row = (int)std::floor((pt.f[RY] - min_y) / grid_resolution);
+        const int temp_id = temp_row * col + temp_col;
+        if (temp_id >= 0 && temp_id < num_grid) {
+            Grid &g = grid[temp_id];
+            if (dw_method > 0 && !g.pts_count)
+                g.dist2station = std::sqrt(pt.f[RX] * pt.f[RX] + pt.f[RY] * pt.f[RY] + pt.f[RZ] * pt.f[RZ]);
+            if (pt.f[RZ] > non_ground_height_thre) {
+                distance_weight = 1.0 * standard_distance / (g.dist2station + 0.0001);
+                int rate = nonground_random_down_rate;
+                if (dw_method == 1) rate = to_int_x86(distance_weight * nonground_random_down_rate + 1);
+                else if (dw_method == 2) rate = to_int_x86(distance_weight * distance_weight * nonground_random_down_rate + 1);
+                if (j % rate == 0 || pt.f[RINT] > intensity_thre) {
+                    pt.f[3] = pt.f[RZ] - (appro_mean_height - 3.0);
+                    cloud_unground.push_back(pt);
+                }
+            } else if (pt.f[RZ] > underground_noise_thre) {
+                g.pts_count++;
+                g.point_id.push_back(j);
+                if (pt.f[RZ] < g.min_z) g.min_z = g.neighbor_min_z = pt.f[RZ];
+            }
+        }
+    }
+    if (P.apply_grid_wise_outlier_filter) { // :1769-1788
+        for (int i = 0; i < num_grid; ++i) {
+            Grid &g = grid[i];
+            if (g.pts_count >= min_grid_pt_num) {
+                double sum_z = 0, sum_z2 = 0, std_z = 0, mean_z = 0;
+                for (int id : g.point_id) sum_z += cloud_in[id].f[RZ];
+                mean_z = sum_z / g.pts_count;
+                for (int id : g.point_id) sum_z2 += (cloud_in[id].f[RZ] - mean_z) * (cloud_in[id].f[RZ] - mean_z);
+                std_z = std::sqrt(sum_z2 / g.pts_count);
+                g.min_z_outlier_thre = mean_z - P.outlier_std_scale * std_z;
+                g.min_z = std::max(g.min_z, g.min_z_outlier_thre);
+                g.neighbor_min_z = g.min_z;
+            }
+        }
+    }
+    for (int m = 0; m < num_grid; ++m) { // :1793-1810
+        const int temp_row = m / col, temp_col = m % col;
+        if (temp_row >= 1 && temp_row <= row - 2 && temp_col >= 1 && temp_col <= col - 2)
+            for (int j = -1; j <= 1; ++j)
+                for (int k = -1; k <= 1; ++k) {
+                    grid[m].neighbor_min_z = std::min(grid[m].neighbor_min_z, grid[m + j * col + k].min_z);
+                    if (grid[m + j * col + k].pts_count > reliable_grid_pts_count_thre) grid[m].reliable_neighbor_grid_num++;
+                }
+    }
+    for (int i = 0; i < num_grid; ++i) { // :1830-1927 (per-cell outputs concatenated in cell order, :1930-1934)
+        Grid &g = grid[i];
+        if (!(g.pts_count >= min_grid_pt_num && g.reliable_neighbor_grid_num >= P.reliable_neighbor_grid_num_thre)) continue;
+        Rows grid_ground, cell_ground, cell_unground;
+        int ground_rate = ground_random_down_rate, nonground_rate = nonground_random_down_rate;
+        distance_weight = 1.0 * standard_distance / (g.dist2station + 0.0001);
+        if (dw_method == 1) {
+            ground_rate = to_int_x86(distance_weight * ground_random_down_rate + 1);
+            nonground_rate = to_int_x86(distance_weight * nonground_random_down_rate + 1);
+        } else if (dw_method == 2) {
+            ground_rate = to_int_x86(distance_weight * distance_weight * ground_random_down_rate + 1);
+            nonground_rate = to_int_x86(distance_weight * distance_weight * nonground_random_down_rate + 1);
+        }
+        if (g.min_z - g.neighbor_min_z < neighbor_height_diff) {
+            for (int j = 0; j < (int)g.point_id.size(); ++j) {
+                Row &pt = cloud_in[g.point_id[j]];
+                if (pt.f[RZ] > g.min_z_outlier_thre) {
+                    if (pt.f[RZ] - g.min_z < max_height_difference) {
+                        if (method == 3) grid_ground.push_back(pt);
+                        else if (j % ground_rate == 0) {
+                            if (method == 0) pt.f[RNX] = 0.0, pt.f[RNY] = 0.0, pt.f[RNZ] = 1.0;
+                            cell_ground.push_back(pt);
+                        }
+                    } else if (j % nonground_rate == 0 || pt.f[RINT] > intensity_thre) {
+                        pt.f[3] = pt.f[RZ] - g.min_z;
+                        cell_unground.push_back(pt);
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < (int)g.point_id.size(); ++j) {
+                Row &pt = cloud_in[g.point_id[j]];
+                if (pt.f[RZ] > g.min_z_outlier_thre && (j % nonground_rate == 0 || pt.f[RINT] > intensity_thre)) {
+                    pt.f[3] = pt.f[RZ] - g.neighbor_min_z;
+                    cell_unground.push_back(pt);
+                }
+            }
+        }
+        if (method == 3 && (int)grid_ground.size() >= min_grid_pt_num) { // :1903-1925
+            std::vector<int> inl;
+            float coeff[4];
+            const float dist_thre = 0.3 * max_height_difference; // float parameter of estimate_ground_normal_by_ransac
+            if (sac_plane_segment(grid_ground, (double)dist_thre, 20, inl, coeff)) {
+                const float normal_x = coeff[0], normal_y = coeff[1], normal_z = coeff[2];
+                for (int j = 0; j < (int)inl.size(); ++j) // grid_ground was swapped with the inlier cloud (:2047)
+                    if (j % ground_rate == 0 && std::abs(normal_z) > 0.8) {
+                        Row pt = grid_ground[inl[j]];
+                        pt.f[RNX] = normal_x, pt.f[RNY] = normal_y, pt.f[RNZ] = normal_z;
+                        cell_ground.push_back(pt);
+                    }
+            }
+        }
+        cloud_ground.insert(cloud_ground.end(), cell_ground.begin(), cell_ground.end());
+        cloud_unground.insert(cloud_unground.end(), cell_unground.begin(), cell_unground.end());
+    }
+    // :1942-1968 (methods 1 / 2 re-estimate the normals with pcl::NormalEstimation: not restated)
+    if (!P.fixed_num_downsampling) {
+        for (int i = 0; i < (int)cloud_ground.size(); ++i)
+            if (i % P.ground_random_down_down_rate == 0) cloud_ground_down.push_back(cloud_ground[i]);
+    } else {
+        cloud_ground_down = cloud_ground;
+        rows_random_downsample(cloud_ground_down, P.down_ground_fixed_num, P.random_seed, 30);
+    }
+}
+
+
 extern "C" {
 
 // Run one registration on the CPU. threads: 0 = reference-shaped (3 OpenMP sections), n>0 = n threads.
@@ -1964,6 +2358,32 @@ int orc_classify_nground(const mulls_cloud_view cloud_in, const mulls_classify_p
         if (out->rows[k] && !res[k].empty()) std::memcpy(out->rows[k], res[k].data(), res[k].size() * sizeof(Row));
     }
     return 0;
+}
+
+
+// fast_ground_filter on host rows; out->ground / ground_down / unground need cloud_in.n rows each (NULL: skipped).
+int orc_fast_ground_filter(const mulls_cloud_view cloud_in, const mulls_ground_params *params, mulls_ground_out *out) {
+    Rows in(cloud_in.n);
+    if (cloud_in.n) std::memcpy(in.data(), cloud_in.aos48, cloud_in.n * sizeof(Row));
+    Rows g, gd, u;
+    fast_ground_filter(in, *params, g, gd, u);
+    out->n_ground = g.size(), out->n_ground_down = gd.size(), out->n_unground = u.size();
+    if (out->ground && !g.empty()) std::memcpy(out->ground, g.data(), g.size() * sizeof(Row));
+    if (out->ground_down && !gd.empty()) std::memcpy(out->ground_down, gd.data(), gd.size() * sizeof(Row));
+    if (out->unground && !u.empty()) std::memcpy(out->unground, u.data(), u.size() * sizeof(Row));
+    return 0;
+}
+
+// the plane fit alone (tests): candidate rows in, refined inlier indices + coefficients out; returns 1 if a model was found
+int orc_sac_plane(const mulls_cloud_view cloud, double threshold, int max_iterations, int32_t *inliers, int32_t *n_inliers,
+                  float coeff[4]) {
+    Rows in(cloud.n);
+    if (cloud.n) std::memcpy(in.data(), cloud.aos48, cloud.n * sizeof(Row));
+    std::vector<int> inl;
+    const bool ok = sac_plane_segment(in, threshold, max_iterations, inl, coeff);
+    *n_inliers = (int32_t)inl.size();
+    for (size_t i = 0; i < inl.size(); ++i) inliers[i] = inl[i];
+    return ok ? 1 : 0;
 }
 
 

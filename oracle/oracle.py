@@ -55,6 +55,11 @@ def load() -> C.CDLL:
                                        C.POINTER(abi.MapInfo)]
         lib.orc_classify_nground.restype = C.c_int
         lib.orc_classify_nground.argtypes = [abi.CloudView, C.POINTER(abi.ClassifyParams), C.POINTER(abi.ClassifyOut)]
+        lib.orc_fast_ground_filter.restype = C.c_int
+        lib.orc_fast_ground_filter.argtypes = [abi.CloudView, C.POINTER(abi.GroundParams), C.POINTER(abi.GroundOut)]
+        lib.orc_sac_plane.restype = C.c_int
+        lib.orc_sac_plane.argtypes = [abi.CloudView, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_float)]
         _LIB = lib
     return _LIB
 
@@ -139,3 +144,19 @@ def map_update(map_clouds, map_pose, scan_down, scan_pose, params: abi.MapParams
 def classify_nground(cloud: np.ndarray, params: abi.ClassifyParams) -> dict:
     """CFilter::classify_nground_pts on host rows: {"pillar": (n,12), ..., "vertex": ..., "unground": ...}."""
     return abi.classify_call(load().orc_classify_nground, None, cloud, params)
+
+
+def fast_ground_filter(cloud: np.ndarray, params: abi.GroundParams) -> dict:
+    """CFilter::fast_ground_filter on host rows: {"ground", "ground_down", "unground"} as (n,12) rows."""
+    return abi.ground_call(load().orc_fast_ground_filter, None, cloud, params)
+
+
+def sac_plane(cloud: np.ndarray, threshold: float, max_iterations: int = 20):
+    """pcl::SACSegmentation plane fit as plane_seg_ransac configures it: (found, refined inlier indices, coefficients)."""
+    cloud = abi.as_aos48(cloud)
+    inl = np.zeros(max(len(cloud), 1), np.int32)
+    n = C.c_int32(0)
+    coeff = np.zeros(4, np.float32)
+    ok = load().orc_sac_plane(abi.cloud_view(cloud), float(threshold), int(max_iterations),
+                              inl.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), coeff.ctypes.data_as(C.POINTER(C.c_float)))
+    return bool(ok), inl[: n.value].copy(), coeff

@@ -1,0 +1,250 @@
+"""Ground segmentation (first half): lo::CFilter::fast_ground_filter,
+include/common/cfilter.hpp:1658-2036, with the per-cell RANSAC plane of estimate_ground_normal_by_ransac (:2038-2054)
+-> CProceesing::plane_seg_ransac (cprocessing.hpp:67-105) -> pcl::SACSegmentation (PCL 1.10 semantics restated).
+
+CPU part: (1) the restatement in oracle/ against what the reference code states; (2) the product's per-point / per-cell
+work functions (mulls_b200/csrc/ground_core.cuh, `__host__ __device__`) compiled for the host with a one-lane "warp"
+(tests/harness/ground_host.cu) against the restatement, bit for bit — the sequential semantics are checked before the
+code meets a GPU. GPU part: mulls_fast_ground_filter against the restatement, all three clouds compared as bit patterns.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from mulls_b200 import abi, synth
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def raw_scan(seed=5, config="c2", shuffle=True):
+    """A raw-looking sweep: every return of a synthetic scan (sensor frame, ground at z = -1.73), normals wiped."""
+    pr = synth.make_pair(seed, config)
+    raw = np.concatenate(pr["tgt"], axis=0).copy()
+    if shuffle:
+        np.random.default_rng(seed).shuffle(raw)
+    raw[:, 3:8] = 0
+    raw[:, 9:] = 0
+    return np.ascontiguousarray(raw), len(pr["tgt"][abi.GROUND])
+
+
+def params(**kw):
+    p = abi.default_ground_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+VARIANTS = {
+    "slam_defaults": {},
+    "no_distance_weight": dict(distance_weight_downsampling_method=0),
+    "linear_weight_low_ceiling": dict(distance_weight_downsampling_method=1, max_ground_height=0.8),
+    "fixed_normal": dict(estimate_ground_normal_method=0, max_ground_height=0.8),
+    "outlier_filter_small_cells": dict(apply_grid_wise_outlier_filter=1, grid_resolution=1.7, min_grid_pt_num=8,
+                                       reliable_neighbor_grid_num_thre=3),
+    "intensity_keeps_signs": dict(intensity_thre=200.0, nonground_random_down_rate=7, ground_random_down_rate=4),
+}
+
+
+def _same(a, b, tag):
+    for k in ("ground", "ground_down", "unground"):
+        assert a[k].shape == b[k].shape, f"{tag}: {k} {a[k].shape} vs {b[k].shape}"
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), f"{tag}: {k} differs"
+
+
+def test_ground_structs_match_header():
+    code = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "mulls_b200/abi.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu\n", sizeof(mulls_ground_params), sizeof(mulls_ground_out),
+             offsetof(mulls_ground_params, standard_distance), offsetof(mulls_ground_params, random_seed),
+             offsetof(mulls_ground_out, n_ground));
+      return 0; }"""
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.c")
+        open(src, "w").write(code)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = [int(v) for v in subprocess.check_output([exe]).decode().split()]
+    assert out == [C.sizeof(abi.GroundParams), C.sizeof(abi.GroundOut), abi.GroundParams.standard_distance.offset,
+                   abi.GroundParams.random_seed.offset, abi.GroundOut.n_ground.offset]
+    lib = abi.load_library()
+    p = abi.GroundParams()
+    lib.mulls_ground_default_params(C.byref(p))
+    q = abi.default_ground_params()
+    for name, _ in abi.GroundParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+
+
+def test_oracle_ground_filter_follows_the_scene():
+    raw, n_ground_true = raw_scan()
+    o = oracle.fast_ground_filter(raw, params(distance_weight_downsampling_method=0))
+    g, u = o["ground"], o["unground"]
+    assert 0.04 * n_ground_true < g.shape[0] < 0.12 * n_ground_true  # 1 in 15 of the cell's inliers (:1915)
+    assert abs(np.median(g[:, 2]) + synth.SENSOR_HEIGHT) < 0.1       # the ground plane of the scene
+    assert (np.abs(g[:, 6]) > 0.8).all() and np.mean(g[:, 6]) > 0.99  # plane normals, |nz| > 0.8 (:1915)
+    assert np.allclose(np.linalg.norm(g[:, 4:7], axis=1), 1.0, atol=1e-5)
+    assert o["ground_down"].shape[0] == (g.shape[0] + 1) // 2 and np.array_equal(o["ground_down"], g[::2])  # :1958
+    # non-ground: height above the local ground in data[3] (:1880, :1894), all at least max_height_difference up
+    assert u.shape[0] > 5000 and (u[:, 3] >= 0.3).all() and u[:, 3].max() < 6.0
+    # deterministic
+    o2 = oracle.fast_ground_filter(raw, params(distance_weight_downsampling_method=0))
+    _same(o, o2, "repeat")
+
+
+def test_oracle_high_points_go_first_and_keep_scan_order():
+    """Points above appro_mean_height + max_ground_height are pushed while the cloud is walked (:1742-1755), i.e. they
+    lead cloud_unground in index order with data[3] = z - (mean - 3); the per-cell points follow in cell order."""
+    raw, _ = raw_scan()
+    p = params(max_ground_height=0.8, distance_weight_downsampling_method=0, nonground_random_down_rate=3)
+    u = oracle.fast_ground_filter(raw, p)["unground"]
+    mean_h = np.float32(0.001)
+    for j in range(0, raw.shape[0], 100):
+        mean_h = np.float32(mean_h + raw[j, 2])
+    mean_h = np.float32(mean_h / np.float32(len(range(0, raw.shape[0], 100))))
+    thre = np.float32(mean_h + np.float32(0.8))
+    sel = [j for j in range(0, raw.shape[0], 3) if raw[j, 2] > thre]
+    assert len(sel) > 100
+    head = u[: len(sel)]
+    assert np.array_equal(head[:, :3], raw[sel, :3])
+    assert np.array_equal(head[:, 3], (raw[sel, 2].astype(np.float64) - (np.float64(mean_h) - 3.0)).astype(np.float32))
+    assert (u[len(sel):, 2] <= thre).all()
+
+
+def test_oracle_plane_fit_recovers_a_known_plane():
+    rng = np.random.default_rng(1)
+    pts = np.zeros((300, 12), np.float32)
+    pts[:, 0:2] = rng.uniform(-1.5, 1.5, (300, 2))
+    pts[:, 2] = 0.05 * pts[:, 0] - 0.02 * pts[:, 1] + 0.4 + rng.normal(0, 0.01, 300)
+    pts[:25, 2] += rng.uniform(0.15, 0.3, 25)  # outliers above the plane
+    ok, inl, c = oracle.sac_plane(pts, 0.09, 20)
+    assert ok and 270 <= len(inl) <= 285 and (inl >= 25).sum() == 275
+    n_true = np.array([-0.05, 0.02, 1.0]) / np.linalg.norm([-0.05, 0.02, 1.0])
+    c = c * np.sign(c[2])
+    assert np.allclose(c[:3], n_true, atol=3e-3) and abs(c[3] + 0.4 * n_true[2]) < 5e-3
+    assert np.array_equal(inl, np.sort(inl))
+    # every model object starts its mt19937 at 12345: the fit is a pure function of the cloud
+    ok2, inl2, c2 = oracle.sac_plane(pts, 0.09, 20)
+    assert np.array_equal(inl, inl2)
+    # collinear / too small clouds give no model
+    line = np.zeros((20, 12), np.float32)
+    line[:, 0] = line[:, 1] = line[:, 2] = np.arange(20)  # (isSampleGood's ratio test: a diagonal line is rejected)
+    assert oracle.sac_plane(line, 0.09, 20)[0] is False
+    assert oracle.sac_plane(pts[:2], 0.09, 20)[0] is False
+
+
+@pytest.fixture(scope="module")
+def host_harness():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available: the host instantiation of ground_core.cuh cannot be built")
+    src = os.path.join(ROOT, "tests", "harness", "ground_host.cu")
+    out_dir = os.path.join(ROOT, "tests", "harness", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libground_host.so")
+    core = os.path.join(ROOT, "mulls_b200", "csrc", "ground_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.gfh_run.restype = C.c_int
+    lib.gfh_run.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.POINTER(abi.GroundParams), C.POINTER(abi.GroundOut)]
+
+    def run(cloud, p):
+        return abi.ground_call(lambda v, pp, o: lib.gfh_run(v.aos48, v.n, pp, o), None, cloud, p)
+
+    return run
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_product_core_on_host_matches_oracle(host_harness, variant):
+    raw, _ = raw_scan()
+    p = params(**VARIANTS[variant])
+    _same(host_harness(raw, p), oracle.fast_ground_filter(raw, p), variant)
+
+
+def test_product_core_on_host_small_and_unshuffled(host_harness):
+    raw, _ = raw_scan(seed=9, config="small", shuffle=False)
+    for kw in ({}, dict(estimate_ground_normal_method=0), dict(min_grid_pt_num=3, grid_resolution=0.9)):
+        p = params(**kw)
+        _same(host_harness(raw, p), oracle.fast_ground_filter(raw, p), str(kw))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", sorted(VARIANTS) + ["fixed_number", "small"])
+def test_gpu_ground_filter_matches_oracle(variant):
+    from mulls_b200.registration import Context
+
+    raw, n_ground_true = raw_scan()
+    if variant == "fixed_number":
+        p = params(fixed_num_downsampling=1, down_ground_fixed_num=300, random_seed=7)
+    elif variant == "small":
+        raw, n_ground_true = raw_scan(seed=9, config="small", shuffle=False)
+        p = params(min_grid_pt_num=5)
+    else:
+        p = params(**VARIANTS[variant])
+    ctx = Context(0, 1, 16, 200000)
+    g = ctx.fast_ground_filter(raw, p)
+    o = oracle.fast_ground_filter(raw, p)
+    _same(g, o, variant)
+    assert g["ground"].shape[0] > 100 and g["unground"].shape[0] > 100
+    if variant == "fixed_number":
+        assert g["ground_down"].shape[0] == 300
+    again = ctx.fast_ground_filter(raw, p)
+    _same(g, again, variant + " (repeat)")
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_ground_filter_feeds_the_classification():
+    """extract_semantic_pts (:2355-2384): fast_ground_filter -> classify_nground_pts on its cloud_unground."""
+    from mulls_b200.registration import Context
+
+    raw, _ = raw_scan()
+    ctx = Context(0, 1, 16, 200000)
+    gp = params()
+    g = ctx.fast_ground_filter(raw, gp)
+    o = oracle.fast_ground_filter(raw, gp)
+    cp = abi.default_classify_params()
+    cp.neighbor_searching_radius, cp.neighbor_k, cp.neigh_k_min, cp.pca_down_rate = 1.0, 30, 8, 1
+    cg = ctx.classify_nground(g["unground"], cp)
+    co = oracle.classify_nground(o["unground"], cp)
+    for k in abi.OUT_NAMES:
+        assert cg[k].shape == co[k].shape and np.array_equal(cg[k].view(np.uint32), co[k].view(np.uint32)), k
+    assert cg["facade"].shape[0] > 50
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_ground_filter_errors_and_degenerate_inputs():
+    from mulls_b200.registration import Context
+
+    ctx = Context(0, 1, 16, 5000)
+    raw, _ = raw_scan(seed=9, config="small")
+    e = ctx.fast_ground_filter(np.zeros((0, 12), np.float32), params())
+    assert all(e[k].shape[0] == 0 for k in e)
+    with pytest.raises(RuntimeError, match="-102"):
+        ctx.fast_ground_filter(raw[:6000], params())
+    with pytest.raises(RuntimeError, match="-103"):
+        ctx.fast_ground_filter(raw[:500], params(estimate_ground_normal_method=1))
+    with pytest.raises(RuntimeError, match="-101"):
+        ctx.fast_ground_filter(raw[:500], params(ground_random_down_rate=0))
+    far = raw[:500].copy()
+    far[0, 0] = 1e7  # one outlier 10 000 km away: more grid cells than the library accepts
+    with pytest.raises(RuntimeError, match="-102"):
+        ctx.fast_ground_filter(far, params())
+    line = raw[:400].copy()
+    line[:, 1] = 2.0  # zero extent along y: the reference's grid has no row, nothing comes out
+    d = ctx.fast_ground_filter(line, params())
+    o = oracle.fast_ground_filter(line, params())
+    assert all(d[k].shape[0] == o[k].shape[0] == 0 for k in d)
+    tiny = ctx.fast_ground_filter(raw[:5], params())  # below min_grid_pt_num everywhere
+    assert tiny["ground"].shape[0] == 0
+    ctx.close()
