@@ -1,5 +1,5 @@
-// Drop-in shim: lo::CFilter<PointT>::classify_nground_pts (include/common/cfilter.hpp:2058-2290) over the mulls_b200
-// C-ABI. A MULLS maintainer replaces the BODY of classify_nground_pts by
+// Drop-in shims: lo::CFilter<PointT>::classify_nground_pts (include/common/cfilter.hpp:2058-2290), fast_ground_filter
+// (:1658-2036) and voxel_downsample (:83-165) over the mulls_b200 C-ABI. A MULLS maintainer replaces the BODY of classify_nground_pts by
 //
 //     return lo::b200::classify_nground_pts<PointT>(cloud_in, cloud_pillar, ... );      // all arguments forwarded
 //
@@ -84,6 +84,84 @@ bool classify_nground_pts(typename pcl::PointCloud<PointT>::Ptr &cloud_in, typen
         if (k == MULLS_OUT_UNGROUND) (*dst[k])->points.clear(); // cloud_in is rewritten in place by the reference
         (*dst[k])->points.insert((*dst[k])->points.end(), rows[k].begin(), rows[k].begin() + out.n[k]);
     }
+    return true;
+}
+
+// lo::CFilter<PointT>::fast_ground_filter (include/common/cfilter.hpp:1658-2036), same names, order, types and defaults
+// as :1658-1672. cloud_curb / detect_curb_or_not are accepted and unused (the reference's curb code is `#if 0`, :1987).
+// The output clouds are appended to, as the reference does. estimate_ground_normal_method 1 / 2 return false.
+template <typename PointT>
+bool fast_ground_filter(const typename pcl::PointCloud<PointT>::Ptr &cloud_in, typename pcl::PointCloud<PointT>::Ptr &cloud_ground,
+                        typename pcl::PointCloud<PointT>::Ptr &cloud_ground_down, typename pcl::PointCloud<PointT>::Ptr &cloud_unground,
+                        typename pcl::PointCloud<PointT>::Ptr &cloud_curb, int min_grid_pt_num, float grid_resolution,
+                        float max_height_difference, float neighbor_height_diff, float max_ground_height,
+                        int ground_random_down_rate, int ground_random_down_down_rate, int nonground_random_down_rate,
+                        int reliable_neighbor_grid_num_thre, int estimate_ground_normal_method, float normal_estimation_radius,
+                        int distance_weight_downsampling_method, float standard_distance, bool fixed_num_downsampling = false,
+                        int down_ground_fixed_num = 1000, bool detect_curb_or_not = false, float intensity_thre = FLT_MAX,
+                        bool apply_grid_wise_outlier_filter = false, float outlier_std_scale = 3.0) {
+    static_assert(sizeof(PointT) == 48, "the C-ABI consumes pcl::PointXYZINormal rows (48 bytes)");
+    static thread_local uint32_t call_seed = 0;
+    (void)cloud_curb;
+    (void)detect_curb_or_not;
+    mulls_ground_params p;
+    mulls_ground_default_params(&p);
+    p.min_grid_pt_num = min_grid_pt_num;
+    p.grid_resolution = grid_resolution;
+    p.max_height_difference = max_height_difference;
+    p.neighbor_height_diff = neighbor_height_diff;
+    p.max_ground_height = max_ground_height;
+    p.ground_random_down_rate = ground_random_down_rate;
+    p.ground_random_down_down_rate = ground_random_down_down_rate;
+    p.nonground_random_down_rate = nonground_random_down_rate;
+    p.reliable_neighbor_grid_num_thre = reliable_neighbor_grid_num_thre;
+    p.estimate_ground_normal_method = estimate_ground_normal_method;
+    p.normal_estimation_radius = normal_estimation_radius;
+    p.distance_weight_downsampling_method = distance_weight_downsampling_method;
+    p.standard_distance = standard_distance;
+    p.fixed_num_downsampling = fixed_num_downsampling;
+    p.down_ground_fixed_num = down_ground_fixed_num;
+    p.intensity_thre = intensity_thre;
+    p.apply_grid_wise_outlier_filter = apply_grid_wise_outlier_filter;
+    p.outlier_std_scale = outlier_std_scale;
+    p.random_seed = call_seed++;
+    const size_t n = cloud_in->points.size();
+    mulls_ctx *ctx = thread_context(1, n);
+    std::vector<PointT> g(n ? n : 1), gd(n ? n : 1), u(n ? n : 1);
+    mulls_ground_out out;
+    out.ground = reinterpret_cast<float *>(g.data()), out.ground_down = reinterpret_cast<float *>(gd.data());
+    out.unground = reinterpret_cast<float *>(u.data());
+    out.cap = n ? n : 1;
+    out.n_ground = out.n_ground_down = out.n_unground = 0;
+    if (!ctx || mulls_fast_ground_filter(ctx, view_of<PointT>(cloud_in), &p, &out) != MULLS_OK) {
+        LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
+        return false;
+    }
+    cloud_ground->points.insert(cloud_ground->points.end(), g.begin(), g.begin() + out.n_ground);
+    cloud_ground_down->points.insert(cloud_ground_down->points.end(), gd.begin(), gd.begin() + out.n_ground_down);
+    cloud_unground->points.insert(cloud_unground->points.end(), u.begin(), u.begin() + out.n_unground);
+    return true;
+}
+
+// lo::CFilter<PointT>::voxel_downsample (include/common/cfilter.hpp:83-165)
+template <typename PointT>
+bool voxel_downsample(const typename pcl::PointCloud<PointT>::Ptr &cloud_in, typename pcl::PointCloud<PointT>::Ptr &cloud_out,
+                      float voxel_size) {
+    static_assert(sizeof(PointT) == 48, "the C-ABI consumes pcl::PointXYZINormal rows (48 bytes)");
+    if (voxel_size < 0.001) { // :89-97: the reference shares the input cloud and reports "disabled"
+        cloud_out = cloud_in;
+        return false;
+    }
+    const size_t n = cloud_in->points.size();
+    mulls_ctx *ctx = thread_context(1, n);
+    std::vector<PointT> rows(n ? n : 1);
+    size_t n_out = 0;
+    if (!ctx || mulls_voxel_downsample(ctx, view_of<PointT>(cloud_in), voxel_size, reinterpret_cast<float *>(rows.data()),
+                                       rows.size(), &n_out) != MULLS_OK) {
+        LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
+        return false;
+    }
+    cloud_out->points.insert(cloud_out->points.end(), rows.begin(), rows.begin() + n_out);
     return true;
 }
 

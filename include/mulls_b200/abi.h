@@ -24,6 +24,10 @@
  *   mulls_classify_nground   <- lo::CFilter<PointT>::classify_nground_pts, include/common/cfilter.hpp:2058-2290
  *   mulls_icp_run_to_map     <- mm_lls_icp with block1 = the device-resident local map
  *   mulls_fast_ground_filter <- lo::CFilter<PointT>::fast_ground_filter, include/common/cfilter.hpp:1658-2036
+ *   mulls_voxel_downsample   <- lo::CFilter<PointT>::voxel_downsample, include/common/cfilter.hpp:83-165
+ *   mulls_extract_semantic_pts <- lo::CFilter<PointT>::extract_semantic_pts, include/common/cfilter.hpp:2295-2413
+ *                               (mulls_voxel_downsample, mulls_fast_ground_filter and mulls_classify_nground also accept
+ *                                device pointers for their input rows and output buffers)
  *
  * Plain C, plain pointers and sizes. No torch / Eigen / PCL types cross this boundary; the C++ shim
  * in include/common/cregistration.hpp converts Eigen/PCL objects to these PODs.
@@ -367,6 +371,33 @@ typedef struct mulls_ground_out {
 void mulls_ground_default_params(mulls_ground_params *p);
 int mulls_fast_ground_filter(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mulls_ground_params *params,
                              mulls_ground_out *out);
+
+/* lo::CFilter<PointT>::voxel_downsample, include/common/cfilter.hpp:83-165: one point per occupied voxel, in voxel-index
+ * order (voxel_size < 0.001 copies the cloud, :89-97). `out` receives at most cloud_in.n rows. The reference's
+ * std::sort leaves open WHICH point of a voxel survives; here it is the one with the lowest index. */
+int mulls_voxel_downsample(mulls_ctx *ctx, mulls_cloud_view cloud_in, float voxel_size, float *out, size_t cap, size_t *n_out);
+
+/* lo::CFilter<PointT>::extract_semantic_pts, include/common/cfilter.hpp:2295-2413, the per-frame feature extraction:
+ * voxel_downsample(pc_raw -> pc_down) (:2346), fast_ground_filter(pc_down) (:2355-2361), classify_nground_pts(pc_unground)
+ * (:2378-2391) — chained in HBM: only the raw scan goes up and the feature clouds come down. Not produced: pc_sketch
+ * (:2348), the scanner / semantic-mask pre-filters (:2328-2342) and update_parameters_self_adaptive (:2406-2410). */
+typedef struct mulls_extract_params {
+    float vf_downsample_resolution; /* cloud_down_res */
+    mulls_ground_params ground;     /* the gf_* arguments */
+    mulls_classify_params classify; /* the pca_* / *_thre / *_fixed_num arguments */
+} mulls_extract_params;
+
+typedef struct mulls_extract_out {
+    float *pc_down;        /* in_block->pc_down; caller buffers of `cap` 48-byte rows (NULL: not wanted) */
+    float *pc_ground;      /* in_block->pc_ground */
+    float *pc_ground_down; /* in_block->pc_ground_down */
+    size_t cap;            /* pc_raw.n rows are always enough */
+    size_t n_down, n_ground, n_ground_down;
+    mulls_classify_out cls; /* pc_pillar .. pc_roof_down, pc_vertex, pc_unground (MULLS_OUT_*) */
+} mulls_extract_out;
+
+int mulls_extract_semantic_pts(mulls_ctx *ctx, mulls_cloud_view pc_raw, const mulls_extract_params *params,
+                               mulls_extract_out *out);
 
 /* The wire format the library ships host clouds in when the "host_pack" tunable is on (csrc/host_pack.h): the 28 of the
  * 48 bytes of a pcl::PointXYZINormal row (utility.hpp:40) that the path reads, repacked on the host cores into pinned

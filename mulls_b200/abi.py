@@ -213,6 +213,24 @@ class GroundOut(C.Structure):
     ]
 
 
+class ExtractParams(C.Structure):
+    """mulls_extract_params: CFilter::extract_semantic_pts (cfilter.hpp:2295-2413) = voxel filter + ground filter + classification."""
+    _fields_ = [("vf_downsample_resolution", C.c_float), ("ground", GroundParams), ("classify", ClassifyParams)]
+
+
+class ExtractOut(C.Structure):
+    _fields_ = [
+        ("pc_down", C.POINTER(C.c_float)),
+        ("pc_ground", C.POINTER(C.c_float)),
+        ("pc_ground_down", C.POINTER(C.c_float)),
+        ("cap", C.c_size_t),
+        ("n_down", C.c_size_t),
+        ("n_ground", C.c_size_t),
+        ("n_ground_down", C.c_size_t),
+        ("cls", ClassifyOut),
+    ]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
 
 # every symbol include/mulls_b200/abi.h declares
@@ -243,6 +261,8 @@ EXPORTED_SYMBOLS = (
     "mulls_pack_rows",
     "mulls_ground_default_params",
     "mulls_fast_ground_filter",
+    "mulls_voxel_downsample",
+    "mulls_extract_semantic_pts",
 )
 
 _LIB = None
@@ -296,6 +316,10 @@ def load_library() -> C.CDLL:
     lib.mulls_ground_default_params.argtypes = [C.POINTER(GroundParams)]
     lib.mulls_fast_ground_filter.restype = C.c_int
     lib.mulls_fast_ground_filter.argtypes = [vp, CloudView, C.POINTER(GroundParams), C.POINTER(GroundOut)]
+    lib.mulls_voxel_downsample.restype = C.c_int
+    lib.mulls_voxel_downsample.argtypes = [vp, CloudView, C.c_float, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.mulls_extract_semantic_pts.restype = C.c_int
+    lib.mulls_extract_semantic_pts.argtypes = [vp, CloudView, C.POINTER(ExtractParams), C.POINTER(ExtractOut)]
     lib.mulls_pack_rows.restype = C.c_int
     lib.mulls_pack_rows.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     lib.mulls_set_tunable.restype = C.c_int

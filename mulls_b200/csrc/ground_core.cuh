@@ -602,4 +602,31 @@ GF_HD void gf_cell_emit(const GfArgs &A, int c) {
     }
 }
 
+// ---- CFilter::voxel_downsample, cfilter.hpp:83-165 ---------------------------------------------------------------------
+// one point per occupied voxel, output in voxel-index order. std::sort on idpair_t compares the voxel index only (:42)
+// and is unstable: which point of a voxel leads its run is unspecified in the reference — here the lowest index
+// (stable radix sort).
+struct VxState {
+    int bb[6];               // ordered-int encoded min xyz, max xyz (pcl::getMinMax3D)
+    float mn[3];
+    float inv;               // inverse_voxel_size (:99)
+    unsigned long long mul_vx, mul_vy; // :117-119
+    uint32_t n_out;
+};
+GF_HD void vx_setup(VxState &S, float voxel_size) {
+    float mx[3];
+    for (int d = 0; d < 3; ++d) S.mn[d] = gf_unord(S.bb[d]), mx[d] = gf_unord(S.bb[3 + d]);
+    S.inv = 1.0f / voxel_size;
+    const unsigned long long max_vy = (unsigned long long)(ceilf((mx[1] - S.mn[1]) * S.inv) + 1.0f);
+    const unsigned long long max_vz = (unsigned long long)(ceilf((mx[2] - S.mn[2]) * S.inv) + 1.0f);
+    S.mul_vx = max_vy * max_vz;
+    S.mul_vy = max_vz;
+}
+GF_HD unsigned long long vx_key(const VxState &S, const float4 a) { // :128-132
+    const unsigned long long vx = (unsigned long long)floorf((a.x - S.mn[0]) * S.inv);
+    const unsigned long long vy = (unsigned long long)floorf((a.y - S.mn[1]) * S.inv);
+    const unsigned long long vz = (unsigned long long)floorf((a.z - S.mn[2]) * S.inv);
+    return vx * S.mul_vx + vy * S.mul_vy + vz;
+}
+
 } // namespace mulls

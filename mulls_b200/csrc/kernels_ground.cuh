@@ -125,4 +125,58 @@ __global__ void __launch_bounds__(kClsBlock) k_gf_down(GfArgs A) {
     if (threadIdx.x == 0) A.st->n_ground_down = S.total;
 }
 
+// ---- voxel_downsample (cfilter.hpp:83-165) -----------------------------------------------------------------------------
+struct VxArgs {
+    uint32_t n;
+    float voxel_size;
+    const float4 *rows;
+    VxState *st;
+    unsigned long long *key, *key_s;
+    uint32_t *idx, *idx_s, *head, *pos;
+    float4 *out;
+};
+__global__ void __launch_bounds__(kGfBlock) k_vx_bbox(VxArgs V) {
+    const uint32_t j = blockIdx.x * kGfBlock + threadIdx.x;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (j < V.n) {
+        const float4 a = V.rows[3 * (size_t)j];
+        mn[0] = mx[0] = a.x, mn[1] = mx[1] = a.y, mn[2] = mx[2] = a.z;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&V.st->bb[d], gf_ord(mn[d]));
+            atomicMax(&V.st->bb[3 + d], gf_ord(mx[d]));
+        }
+}
+__global__ void k_vx_setup(VxArgs V) { vx_setup(*V.st, V.voxel_size); }
+__global__ void __launch_bounds__(kGfBlock) k_vx_keys(VxArgs V) {
+    const uint32_t j = blockIdx.x * kGfBlock + threadIdx.x;
+    if (j < V.n) {
+        V.key[j] = vx_key(*V.st, V.rows[3 * (size_t)j]);
+        V.idx[j] = j;
+    }
+}
+__global__ void __launch_bounds__(kGfBlock) k_vx_heads(VxArgs V) {
+    const uint32_t i = blockIdx.x * kGfBlock + threadIdx.x;
+    if (i < V.n) V.head[i] = (i == 0 || V.key_s[i] != V.key_s[i - 1]) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(kGfBlock) k_vx_gather(VxArgs V) {
+    const uint32_t i = blockIdx.x * kGfBlock + threadIdx.x;
+    if (i >= V.n) return;
+    if (V.head[i]) {
+        const float4 *r = V.rows + 3 * (size_t)V.idx_s[i];
+        float4 *o = V.out + 3 * (size_t)V.pos[i];
+        o[0] = r[0], o[1] = r[1], o[2] = r[2];
+    }
+    if (i + 1 == V.n) V.st->n_out = V.pos[i] + V.head[i];
+}
+
 } // namespace mulls

@@ -60,6 +60,7 @@ struct mulls_ctx {
     // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h):
     // 0 never, 1 always, 2 when a call ships at least kPackMinPoints points (small calls are latency-bound: raw rows)
     int host_pack = 2;
+    int poll_pause = 64;   // _mm_pause() count between two cudaEventQuery calls of the launch loop's flow control
     int stage_wc = 0;      // allocate the pinned staging write-combined (the host only streams into it)
     float4 *h_stage = nullptr; // pinned staging of the packed clouds (allocated on first use)
     size_t h_stage_slots = 0;
@@ -83,6 +84,8 @@ struct mulls_ctx {
     // ground-filter scratch (mulls_fast_ground_filter): per-point part and per-cell part
     void *gf_buf = nullptr, *gf_cell_buf = nullptr;
     size_t gf_buf_bytes = 0, gf_cell_buf_bytes = 0;
+    void *vx_buf = nullptr, *ext_buf = nullptr; // voxel filter scratch; clouds handed between the stages of extract_semantic_pts
+    size_t vx_buf_bytes = 0, ext_buf_bytes = 0;
     // the local map whose clouds the target slices of pair 0 currently index (set by mulls_icp_run_to_map, cleared
     // by any other upload): what block1->tree_* are to MapManager::map_based_dynamic_close_removal
     const mulls_map *tree_map = nullptr;
@@ -153,6 +156,8 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->cls_buf) cudaFree(ctx->cls_buf);
     if (ctx->gf_buf) cudaFree(ctx->gf_buf);
     if (ctx->gf_cell_buf) cudaFree(ctx->gf_cell_buf);
+    if (ctx->vx_buf) cudaFree(ctx->vx_buf);
+    if (ctx->ext_buf) cudaFree(ctx->ext_buf);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_running) cudaFreeHost(ctx->h_running);
@@ -358,6 +363,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "defer_scan") ctx->defer_scan = value;
     else if (n == "host_pack") ctx->host_pack = value;
+    else if (n == "poll_pause") ctx->poll_pause = value;
     else if (n == "stage_wc") {
         if (ctx->stage_wc != value && ctx->h_stage) { // re-allocated with the new flag on the next packed upload
             cudaFreeHost(ctx->h_stage);
@@ -566,6 +572,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
                              ctx->stage_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
             ctx->h_stage_slots = slots;
         }
+        CK(cudaStreamSynchronize(ctx->stream)); // the staging may still be read by a copy of a call that failed half-way
         PackPool &pool = PackPool::get();
         pool.ensure_workers(0);
         std::unique_ptr<std::atomic<int>[]> pending(new std::atomic<int>[n_pairs]);
@@ -645,8 +652,11 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     if (!ctx->h_it_chunks.empty())
         CK(cudaMemcpyAsync(ctx->A.it_chunks, ctx->h_it_chunks.data(), ctx->h_it_chunks.size() * sizeof(ChunkDesc),
                            cudaMemcpyHostToDevice, ctx->stream));
-    // the host vectors above are pageable: make sure the copies are done before they can change
-    CK(cudaStreamSynchronize(ctx->stream));
+    // The tables above live in pageable vectors: cudaMemcpyAsync has already staged them when it returns. The clouds,
+    // however, may be the caller's pinned buffers (truly asynchronous copies): a resident upload returns to the caller
+    // before anything else runs, so it waits here; a one-shot call goes straight on to run_impl, which synchronises
+    // before it returns — the kernels are queued while the clouds are still crossing PCIe.
+    if (resident) CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_pairs = n_pairs;
     ctx->n_in = in_off;
     ctx->n_src_total = s_off;
@@ -754,8 +764,9 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
             // flow control: stay at most two iterations ahead of the device and stop launching as soon
             // as every pair has converged or failed (the device mirrors its counter into mapped memory)
             if (it >= 2) {
-                while (cudaEventQuery(ctx->ev_done[it - 2]) == cudaErrorNotReady) {
-                }
+                // (poll with pauses: several lanes spinning inside the driver slow each other's launches down)
+                while (cudaEventQuery(ctx->ev_done[it - 2]) == cudaErrorNotReady)
+                    for (int k = 0; k < ctx->poll_pause; ++k) _mm_pause();
                 if (*(volatile int *)ctx->h_running <= 0) break;
             }
             const int buf = it & 1;
@@ -1505,12 +1516,12 @@ int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mull
     CK(cudaMemsetAsync(C.st, 0, sizeof(ClsState), st));
     uint64_t launches = 0;
     if (sample_in) {
-        CK(cudaMemcpyAsync(base + o_in, cloud_in.aos48, n0 * row_b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(base + o_in, cloud_in.aos48, n0 * row_b, cudaMemcpyDefault, st)); // host or device rows
         k_rows_sample<<<1, kClsBlock, 0, st>>>((const float4 *)(base + o_in), (uint32_t)n0, P.unground_down_fixed_num, P.random_seed,
                                                18u, C.rows);
         ++launches;
     } else {
-        CK(cudaMemcpyAsync(C.rows, cloud_in.aos48, n0 * row_b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(C.rows, cloud_in.aos48, n0 * row_b, cudaMemcpyDefault, st));
     }
     ClsState hs;
     std::memset(&hs, 0, sizeof(hs));
@@ -1717,7 +1728,7 @@ int mulls_fast_ground_filter(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mu
     void *tmp = base + o_tmp;
     size_t tmp_bytes = std::max(sort_bytes, scan_bytes);
     CK(cudaEventRecord(ctx->ev_begin, st));
-    CK(cudaMemcpyAsync((void *)A.rows, cloud_in.aos48, n * row_b, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void *)A.rows, cloud_in.aos48, n * row_b, cudaMemcpyDefault, st)); // host or device rows
     CK(cudaMemcpyAsync((void *)A.draws, sac_draw_table(), kSacDraws * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     GfState hs;
     std::memset(&hs, 0, sizeof(hs));
@@ -1797,17 +1808,165 @@ int mulls_fast_ground_filter(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mu
             return MULLS_E_CAPACITY;
         }
         if (out->ground && hs.n_ground)
-            CK(cudaMemcpyAsync(out->ground, A.out_ground, hs.n_ground * row_b, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->ground, A.out_ground, hs.n_ground * row_b, cudaMemcpyDefault, st));
         if (out->ground_down && hs.n_ground_down)
-            CK(cudaMemcpyAsync(out->ground_down, A.out_ground_down, hs.n_ground_down * row_b, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->ground_down, A.out_ground_down, hs.n_ground_down * row_b, cudaMemcpyDefault, st));
         if (out->unground && hs.n_unground)
-            CK(cudaMemcpyAsync(out->unground, A.out_unground, hs.n_unground * row_b, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->unground, A.out_unground, hs.n_unground * row_b, cudaMemcpyDefault, st));
     }
     CK(cudaEventRecord(ctx->ev_end, st));
     CK(cudaStreamSynchronize(st));
     ctx->stats = mulls_run_stats();
     ctx->stats.kernel_launches = launches;
     cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev_begin, ctx->ev_end);
+    return MULLS_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// CFilter::voxel_downsample (cfilter.hpp:83-165) and the chain of CFilter::extract_semantic_pts (:2295-2413)
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mulls_voxel_downsample(mulls_ctx *ctx, mulls_cloud_view cloud_in, float voxel_size, float *out, size_t cap, size_t *n_out) {
+    if (!ctx || !n_out || (cloud_in.n > 0 && (!cloud_in.aos48 || !out))) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    *n_out = 0;
+    const size_t n = cloud_in.n;
+    if (n == 0) return MULLS_OK;
+    if (n > ctx->max_tgt || n >= (1ull << 31)) {
+        ctx->err = "mulls_voxel_downsample: cloud exceeds max_tgt_pts of the context";
+        return MULLS_E_CAPACITY;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t row_b = 48;
+    if (voxel_size < 0.001) { // :89-97 disabled: cloud_out = cloud_in
+        if (n > cap) {
+            ctx->err = "mulls_voxel_downsample: output buffer too small";
+            return MULLS_E_CAPACITY;
+        }
+        CK(cudaMemcpyAsync(out, cloud_in.aos48, n * row_b, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+        *n_out = n;
+        return MULLS_OK;
+    }
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, st);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_rows = take(n * row_b), o_out = take(n * row_b), o_key = take(8 * n), o_keys = take(8 * n);
+    const size_t o_idx = take(4 * n), o_idxs = take(4 * n), o_head = take(4 * n), o_pos = take(4 * n), o_st = take(sizeof(VxState));
+    const size_t o_tmp = take(std::max(sort_bytes, scan_bytes));
+    if (off > ctx->vx_buf_bytes) {
+        if (ctx->vx_buf) cudaFree(ctx->vx_buf);
+        ctx->vx_buf = nullptr;
+        ctx->vx_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->vx_buf, off));
+        ctx->vx_buf_bytes = off;
+    }
+    char *base = (char *)ctx->vx_buf;
+    VxArgs V;
+    V.n = (uint32_t)n;
+    V.voxel_size = voxel_size;
+    V.rows = (const float4 *)(base + o_rows);
+    V.out = (float4 *)(base + o_out);
+    V.key = (unsigned long long *)(base + o_key), V.key_s = (unsigned long long *)(base + o_keys);
+    V.idx = (uint32_t *)(base + o_idx), V.idx_s = (uint32_t *)(base + o_idxs);
+    V.head = (uint32_t *)(base + o_head), V.pos = (uint32_t *)(base + o_pos);
+    V.st = (VxState *)(base + o_st);
+    void *tmp = base + o_tmp;
+    const size_t tmp_bytes = std::max(sort_bytes, scan_bytes);
+    VxState hs;
+    std::memset(&hs, 0, sizeof(hs));
+    for (int d = 0; d < 3; ++d) hs.bb[d] = host_ord(FLT_MAX), hs.bb[3 + d] = host_ord(-FLT_MAX);
+    CK(cudaEventRecord(ctx->ev_begin, st));
+    CK(cudaMemcpyAsync((void *)V.rows, cloud_in.aos48, n * row_b, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(V.st, &hs, sizeof(VxState), cudaMemcpyHostToDevice, st));
+    const unsigned pb = (unsigned)ceil_div(n, kGfBlock);
+    k_vx_bbox<<<pb, kGfBlock, 0, st>>>(V);
+    k_vx_setup<<<1, 1, 0, st>>>(V);
+    k_vx_keys<<<pb, kGfBlock, 0, st>>>(V);
+    size_t b1 = tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(tmp, b1, V.key, V.key_s, V.idx, V.idx_s, (int)n, 0, 64, st));
+    k_vx_heads<<<pb, kGfBlock, 0, st>>>(V);
+    size_t b2 = tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(tmp, b2, V.head, V.pos, (int)n, st));
+    k_vx_gather<<<pb, kGfBlock, 0, st>>>(V);
+    CK(cudaMemcpyAsync(&hs, V.st, sizeof(VxState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *n_out = hs.n_out;
+    if (hs.n_out > cap) {
+        ctx->err = "mulls_voxel_downsample: output buffer too small";
+        return MULLS_E_CAPACITY;
+    }
+    CK(cudaMemcpyAsync(out, V.out, (size_t)hs.n_out * row_b, cudaMemcpyDefault, st));
+    CK(cudaEventRecord(ctx->ev_end, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats = mulls_run_stats();
+    ctx->stats.kernel_launches = 5;
+    cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev_begin, ctx->ev_end);
+    return MULLS_OK;
+}
+
+int mulls_extract_semantic_pts(mulls_ctx *ctx, mulls_cloud_view pc_raw, const mulls_extract_params *params,
+                               mulls_extract_out *out) {
+    if (!ctx || !params || !out || (pc_raw.n > 0 && !pc_raw.aos48)) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    out->n_down = out->n_ground = out->n_ground_down = 0;
+    for (int k = 0; k < MULLS_OUT_COUNT; ++k) out->cls.n[k] = 0;
+    const size_t n = pc_raw.n;
+    if (n == 0) return MULLS_OK;
+    if ((out->pc_down || out->pc_ground || out->pc_ground_down) && out->cap < n) {
+        ctx->err = "mulls_extract_semantic_pts: the output buffers must hold pc_raw.n rows";
+        return MULLS_E_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    // the clouds handed from stage to stage stay in HBM: pc_down and the ground filter's cloud_unground
+    const size_t row_b = 48, need = 2 * n * row_b;
+    if (need > ctx->ext_buf_bytes) {
+        if (ctx->ext_buf) cudaFree(ctx->ext_buf);
+        ctx->ext_buf = nullptr;
+        ctx->ext_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->ext_buf, need));
+        ctx->ext_buf_bytes = need;
+    }
+    float *d_down = (float *)ctx->ext_buf, *d_ung = (float *)((char *)ctx->ext_buf + n * row_b);
+    float ms = 0.f;
+    uint64_t launches = 0;
+    // :2346 voxel_downsample(pc_raw, pc_down) (pc_sketch, :2348, is not a feature cloud and is not produced)
+    size_t n_down = 0;
+    int rc = mulls_voxel_downsample(ctx, pc_raw, params->vf_downsample_resolution, d_down, n, &n_down);
+    if (rc != MULLS_OK) return rc;
+    ms += ctx->stats.ms_total, launches += ctx->stats.kernel_launches;
+    out->n_down = n_down;
+    if (out->pc_down && n_down) {
+        CK(cudaMemcpyAsync(out->pc_down, d_down, n_down * row_b, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    // :2355-2361 fast_ground_filter(pc_down -> pc_ground, pc_ground_down, pc_unground)
+    mulls_ground_out g;
+    std::memset(&g, 0, sizeof(g));
+    g.ground = out->pc_ground, g.ground_down = out->pc_ground_down, g.unground = d_ung;
+    g.cap = n;
+    rc = mulls_fast_ground_filter(ctx, mulls_cloud_view{d_down, n_down}, &params->ground, &g);
+    if (rc != MULLS_OK) return rc;
+    ms += ctx->stats.ms_total, launches += ctx->stats.kernel_launches;
+    out->n_ground = g.n_ground, out->n_ground_down = g.n_ground_down;
+    // :2378-2391 classify_nground_pts(pc_unground -> pillar, beam, facade, roof, their down clouds, vertex)
+    rc = mulls_classify_nground(ctx, mulls_cloud_view{d_ung, g.n_unground}, &params->classify, &out->cls);
+    if (rc != MULLS_OK) return rc;
+    ms += ctx->stats.ms_total, launches += ctx->stats.kernel_launches;
+    ctx->stats.ms_total = ms;
+    ctx->stats.kernel_launches = launches;
     return MULLS_OK;
 }
 

@@ -219,6 +219,39 @@ class Context:
             self._check(res["rc"])
         return res
 
+    def voxel_downsample(self, cloud_in: np.ndarray, voxel_size: float) -> np.ndarray:
+        """CFilter::voxel_downsample (cfilter.hpp:83-165) on the GPU: one row per occupied voxel, voxel-index order."""
+        cloud = abi.as_aos48(cloud_in)
+        out = np.zeros((max(len(cloud), 1), 12), np.float32)
+        n = C.c_size_t(0)
+        self._check(self.lib.mulls_voxel_downsample(self.handle, abi.cloud_view(cloud), float(voxel_size),
+                                                    out.ctypes.data_as(C.POINTER(C.c_float)), len(out), C.byref(n)))
+        return np.ascontiguousarray(out[: n.value])
+
+    def extract_semantic_pts(self, pc_raw: np.ndarray, vf_downsample_resolution: float, ground: abi.GroundParams,
+                             classify: abi.ClassifyParams) -> dict:
+        """CFilter::extract_semantic_pts (cfilter.hpp:2295-2413) on the GPU, stages chained in HBM: {"down", "ground",
+        "ground_down", "pillar", ..., "vertex", "unground"} as (n,12) rows."""
+        raw = abi.as_aos48(pc_raw)
+        n = max(len(raw), 1)
+        fp = C.POINTER(C.c_float)
+        bufs = {k: np.zeros((n, 12), np.float32) for k in ("down", "ground", "ground_down")}
+        cbufs = [np.zeros((n, 12), np.float32) for _ in range(abi.OUT_COUNT)]
+        P = abi.ExtractParams(float(vf_downsample_resolution), ground, classify)
+        out = abi.ExtractOut()
+        out.pc_down, out.pc_ground = bufs["down"].ctypes.data_as(fp), bufs["ground"].ctypes.data_as(fp)
+        out.pc_ground_down = bufs["ground_down"].ctypes.data_as(fp)
+        out.cap = n
+        for k in range(abi.OUT_COUNT):
+            out.cls.rows[k] = cbufs[k].ctypes.data_as(fp)
+        out.cls.cap = n
+        self._check(self.lib.mulls_extract_semantic_pts(self.handle, abi.cloud_view(raw), C.byref(P), C.byref(out)))
+        res = {"down": bufs["down"][: out.n_down].copy(), "ground": bufs["ground"][: out.n_ground].copy(),
+               "ground_down": bufs["ground_down"][: out.n_ground_down].copy()}
+        for k in range(abi.OUT_COUNT):
+            res[abi.OUT_NAMES[k]] = np.ascontiguousarray(cbufs[k][: out.cls.n[k]])
+        return res
+
     def stats(self) -> dict:
         s = abi.RunStats()
         self._check(self.lib.mulls_get_stats(self.handle, C.byref(s)))

@@ -1866,6 +1866,50 @@ static void classify_nground(Rows &cloud_in, const mulls_classify_params &P, Row
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
+// CFilter::voxel_downsample, cfilter.hpp:83-165: one point per occupied voxel, output in voxel-index order.
+// pcl::getMinMax3D [3P] on a dense cloud = component-wise float min / max. std::sort on idpair_t compares the voxel
+// index only (:42) and is not stable, so WHICH point of a voxel leads its run is unspecified in the reference; the
+// oracle (and the CUDA path) take the one with the lowest index.
+// ---------------------------------------------------------------------------------------------
+static bool voxel_downsample(const Rows &cloud_in, Rows &cloud_out, float voxel_size) {
+    cloud_out.clear();
+    if (voxel_size < 0.001) { // :89-97 disabled: cloud_out = cloud_in
+        cloud_out = cloud_in;
+        return false;
+    }
+    const size_t n = cloud_in.size();
+    if (n == 0) return true;
+    const float inverse_voxel_size = 1.0f / voxel_size;
+    float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    float mx[3] = {-mn[0], -mn[0], -mn[0]};
+    for (size_t i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = std::min(mn[d], cloud_in[i].f[d]);
+            mx[d] = std::max(mx[d], cloud_in[i].f[d]);
+        }
+    const float gap[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+    const unsigned long long max_vy = std::ceil(gap[1] * inverse_voxel_size) + 1;
+    const unsigned long long max_vz = std::ceil(gap[2] * inverse_voxel_size) + 1;
+    const unsigned long long mul_vx = max_vy * max_vz, mul_vy = max_vz, mul_vz = 1;
+    std::vector<std::pair<unsigned long long, int>> id_pairs(n);
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned long long vx = std::floor((cloud_in[i].f[0] - mn[0]) * inverse_voxel_size);
+        const unsigned long long vy = std::floor((cloud_in[i].f[1] - mn[1]) * inverse_voxel_size);
+        const unsigned long long vz = std::floor((cloud_in[i].f[2] - mn[2]) * inverse_voxel_size);
+        id_pairs[i] = {vx * mul_vx + vy * mul_vy + vz * mul_vz, (int)i};
+    }
+    std::sort(id_pairs.begin(), id_pairs.end()); // (voxel, index): the lowest index leads each run
+    size_t begin_id = 0;
+    while (begin_id < n) {
+        cloud_out.push_back(cloud_in[id_pairs[begin_id].second]);
+        size_t compare_id = begin_id + 1;
+        while (compare_id < n && id_pairs[begin_id].first == id_pairs[compare_id].first) compare_id++;
+        begin_id = compare_id;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // CFilter::fast_ground_filter, cfilter.hpp:1658-2036 (+ estimate_ground_normal_by_ransac :2038-2054,
 // CProceesing::plane_seg_ransac cprocessing.hpp:67-105). The per-cell plane is pcl::SACSegmentation<PointT> with
 // SACMODEL_PLANE / SAC_RANSAC / setOptimizeCoefficients(true) [3P]: PCL 1.10's RandomSampleConsensus::computeModel,
@@ -2384,6 +2428,17 @@ int orc_sac_plane(const mulls_cloud_view cloud, double threshold, int max_iterat
     *n_inliers = (int32_t)inl.size();
     for (size_t i = 0; i < inl.size(); ++i) inliers[i] = inl[i];
     return ok ? 1 : 0;
+}
+
+
+// voxel_downsample on host rows; `out` needs cloud_in.n rows
+int orc_voxel_downsample(const mulls_cloud_view cloud_in, float voxel_size, float *out, size_t *n_out) {
+    Rows in(cloud_in.n), res;
+    if (cloud_in.n) std::memcpy(in.data(), cloud_in.aos48, cloud_in.n * sizeof(Row));
+    voxel_downsample(in, res, voxel_size);
+    *n_out = res.size();
+    if (out && !res.empty()) std::memcpy(out, res.data(), res.size() * sizeof(Row));
+    return 0;
 }
 
 

@@ -57,6 +57,8 @@ def load() -> C.CDLL:
         lib.orc_classify_nground.argtypes = [abi.CloudView, C.POINTER(abi.ClassifyParams), C.POINTER(abi.ClassifyOut)]
         lib.orc_fast_ground_filter.restype = C.c_int
         lib.orc_fast_ground_filter.argtypes = [abi.CloudView, C.POINTER(abi.GroundParams), C.POINTER(abi.GroundOut)]
+        lib.orc_voxel_downsample.restype = C.c_int
+        lib.orc_voxel_downsample.argtypes = [abi.CloudView, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
         lib.orc_sac_plane.restype = C.c_int
         lib.orc_sac_plane.argtypes = [abi.CloudView, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_float)]
@@ -160,3 +162,12 @@ def sac_plane(cloud: np.ndarray, threshold: float, max_iterations: int = 20):
     ok = load().orc_sac_plane(abi.cloud_view(cloud), float(threshold), int(max_iterations),
                               inl.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), coeff.ctypes.data_as(C.POINTER(C.c_float)))
     return bool(ok), inl[: n.value].copy(), coeff
+
+
+def voxel_downsample(cloud: np.ndarray, voxel_size: float) -> np.ndarray:
+    """CFilter::voxel_downsample on host rows: one point per occupied voxel, in voxel-index order."""
+    cloud = abi.as_aos48(cloud)
+    out = np.zeros((max(len(cloud), 1), 12), np.float32)
+    n = C.c_size_t(0)
+    load().orc_voxel_downsample(abi.cloud_view(cloud), float(voxel_size), out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n))
+    return np.ascontiguousarray(out[: n.value])

@@ -110,3 +110,31 @@ extern "C" int gfh_run(const float *rows48, size_t n, const mulls_ground_params 
     if (out->unground) std::memcpy(out->unground, ou.data(), 48 * (size_t)S.n_unground);
     return 0;
 }
+
+// CFilter::voxel_downsample through the product's vx_setup / vx_key (the sort / scan / gather of the device path are
+// plain loops here)
+extern "C" int gfh_voxel(const float *rows48, size_t n, float voxel_size, float *out, size_t *n_out) {
+    *n_out = 0;
+    if (n == 0) return 0;
+    const float4 *rows = reinterpret_cast<const float4 *>(rows48);
+    VxState S;
+    std::memset(&S, 0, sizeof(S));
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (size_t j = 0; j < n; ++j) {
+        const float4 a = rows[3 * j];
+        mn[0] = std::min(mn[0], a.x), mn[1] = std::min(mn[1], a.y), mn[2] = std::min(mn[2], a.z);
+        mx[0] = std::max(mx[0], a.x), mx[1] = std::max(mx[1], a.y), mx[2] = std::max(mx[2], a.z);
+    }
+    for (int d = 0; d < 3; ++d) S.bb[d] = gf_ord(mn[d]), S.bb[3 + d] = gf_ord(mx[d]);
+    vx_setup(S, voxel_size);
+    std::vector<unsigned long long> key(n);
+    std::vector<uint32_t> perm(n);
+    for (size_t j = 0; j < n; ++j) key[j] = vx_key(S, rows[3 * j]);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (i == 0 || key[perm[i]] != key[perm[i - 1]]) std::memcpy(out + 12 * (m++), rows48 + 12 * (size_t)perm[i], 48);
+    *n_out = m;
+    return 0;
+}

@@ -36,6 +36,16 @@ int main() {
                                                        0.65f, 0.65f, 0.75f, 0.75f, 2, 0.12f, 1.5f, 0.94f, 0.17f, 0.98f, 0.34f, true, 200, 800,
                                                        200, 100, 20000, FLT_MAX, 0.0f, 0.3f, true, false);
     (void)cls;
+    // the first two stages of extract_semantic_pts: voxel_downsample (cfilter.hpp:2346) and fast_ground_filter with the
+    // argument list of :2355-2361
+    in_block->pc_raw.reset(new pcl::PointCloud<Point_T>());
+    in_block->pc_down.reset(new pcl::PointCloud<Point_T>());
+    bool vox = lo::b200::voxel_downsample<Point_T>(in_block->pc_raw, in_block->pc_down, 0.05f);
+    bool gf = lo::b200::fast_ground_filter<Point_T>(in_block->pc_down, in_block->pc_ground, in_block->pc_ground_down,
+                                                    in_block->pc_unground, in_block->pc_vertex, 10, 3.0f, 0.3f, 1.5f, 5.0f, 15, 2, 3,
+                                                    0, 3, 2.0f, 2, 15.0f, false, 300, false, FLT_MAX, false);
+    (void)vox;
+    (void)gf;
     std::printf("shim compiled and linked; codes %d %d %d | map %d %d %d\n", code, code2, (int)ok4, (int)up1, (int)up2, code3);
     return 0;
 }

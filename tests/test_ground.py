@@ -157,9 +157,21 @@ def host_harness():
     lib.gfh_run.restype = C.c_int
     lib.gfh_run.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.POINTER(abi.GroundParams), C.POINTER(abi.GroundOut)]
 
+    lib.gfh_voxel.restype = C.c_int
+    lib.gfh_voxel.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
+
     def run(cloud, p):
         return abi.ground_call(lambda v, pp, o: lib.gfh_run(v.aos48, v.n, pp, o), None, cloud, p)
 
+    def voxel(cloud, size):
+        cloud = abi.as_aos48(cloud)
+        out = np.zeros((max(len(cloud), 1), 12), np.float32)
+        n = C.c_size_t(0)
+        lib.gfh_voxel(cloud.ctypes.data_as(C.POINTER(C.c_float)), len(cloud), size, out.ctypes.data_as(C.POINTER(C.c_float)),
+                      C.byref(n))
+        return out[: n.value]
+
+    run.voxel = voxel
     return run
 
 
@@ -175,6 +187,88 @@ def test_product_core_on_host_small_and_unshuffled(host_harness):
     for kw in ({}, dict(estimate_ground_normal_method=0), dict(min_grid_pt_num=3, grid_resolution=0.9)):
         p = params(**kw)
         _same(host_harness(raw, p), oracle.fast_ground_filter(raw, p), str(kw))
+
+
+def test_oracle_voxel_downsample_keeps_one_point_per_voxel():
+    raw, _ = raw_scan()
+    for size in (0.05, 0.2):
+        o = oracle.voxel_downsample(raw, size)
+        mn = raw[:, :3].min(0)
+        inv = np.float32(1.0) / np.float32(size)
+        vox = np.floor((raw[:, :3] - mn) * inv).astype(np.int64)
+        nvy = int(np.ceil((raw[:, 1].max() - mn[1]) * inv)) + 1
+        nvz = int(np.ceil((raw[:, 2].max() - mn[2]) * inv)) + 1
+        key = (vox[:, 0] * nvy + vox[:, 1]) * nvz + vox[:, 2]
+        uniq, first = np.unique(key, return_index=True)  # sorted voxel ids, lowest index of each
+        assert o.shape[0] == len(uniq) and np.array_equal(o, raw[first])
+    assert np.array_equal(oracle.voxel_downsample(raw, 0.0005), raw)  # :89-97 disabled
+    assert oracle.voxel_downsample(raw[:0], 0.1).shape[0] == 0
+
+
+def test_product_voxel_key_on_host_matches_oracle(host_harness):
+    raw, _ = raw_scan()
+    for size in (0.03, 0.1, 0.45):
+        h, o = host_harness.voxel(raw, size), oracle.voxel_downsample(raw, size)
+        assert h.shape == o.shape and np.array_equal(h.view(np.uint32), o.view(np.uint32)), size
+
+
+def test_extract_structs_match_header():
+    code = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "mulls_b200/abi.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu\n", sizeof(mulls_extract_params), sizeof(mulls_extract_out),
+             offsetof(mulls_extract_params, classify), offsetof(mulls_extract_out, n_ground_down),
+             offsetof(mulls_extract_out, cls));
+      return 0; }"""
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.c")
+        open(src, "w").write(code)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = [int(v) for v in subprocess.check_output([exe]).decode().split()]
+    assert out == [C.sizeof(abi.ExtractParams), C.sizeof(abi.ExtractOut), abi.ExtractParams.classify.offset,
+                   abi.ExtractOut.n_ground_down.offset, abi.ExtractOut.cls.offset]
+
+
+@pytest.mark.gpu
+def test_gpu_voxel_downsample_matches_oracle():
+    from mulls_b200.registration import Context
+
+    raw, _ = raw_scan()
+    ctx = Context(0, 1, 16, 200000)
+    for size in (0.03, 0.1, 0.45, 0.0005):
+        g, o = ctx.voxel_downsample(raw, size), oracle.voxel_downsample(raw, size)
+        assert g.shape == o.shape and np.array_equal(g.view(np.uint32), o.view(np.uint32)), size
+    assert ctx.voxel_downsample(raw[:0], 0.1).shape[0] == 0
+    one = ctx.voxel_downsample(raw[:1], 0.1)
+    assert np.array_equal(one, raw[:1])
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_extract_semantic_pts_equals_the_chain_of_restatements():
+    """CFilter::extract_semantic_pts (:2295-2413): raw scan in, feature clouds out, the three stages chained in HBM."""
+    from mulls_b200.registration import Context
+
+    raw, _ = raw_scan()
+    gp = params()
+    cp = abi.default_classify_params()
+    cp.neighbor_searching_radius, cp.neighbor_k, cp.neigh_k_min, cp.pca_down_rate = 1.0, 30, 8, 1
+    cp.fixed_num_downsampling, cp.random_seed = 1, 5
+    ctx = Context(0, 1, 16, 200000)
+    g = ctx.extract_semantic_pts(raw, 0.05, gp, cp)
+    down = oracle.voxel_downsample(raw, 0.05)
+    og = oracle.fast_ground_filter(down, gp)
+    oc = oracle.classify_nground(og["unground"], cp)
+    assert np.array_equal(g["down"].view(np.uint32), down.view(np.uint32))
+    for k in ("ground", "ground_down"):
+        assert g[k].shape == og[k].shape and np.array_equal(g[k].view(np.uint32), og[k].view(np.uint32)), k
+    for k in abi.OUT_NAMES:
+        assert g[k].shape == oc[k].shape and np.array_equal(g[k].view(np.uint32), oc[k].view(np.uint32)), k
+    assert g["ground"].shape[0] > 100 and g["facade"].shape[0] > 50 and g["pillar"].shape[0] > 5
+    ctx.close()
 
 
 @pytest.mark.gpu
