@@ -564,6 +564,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
         for (int s = 0; s < kNumSegs; ++s)
             if (!(tgt_on_device && s < kNumClasses)) host_points += ctx->h_pc[p].in_n[s];
     const size_t kPackMinPoints = 1u << 18;
+    bool tables_sent = false;
     const bool pack = ctx->host_pack == 1 || (ctx->host_pack == 2 && host_points >= kPackMinPoints);
     if (pack) {
         if (!ctx->h_stage) {
@@ -611,7 +612,15 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
             return MULLS_E_CAPACITY;
         }
         pool.submit(jobs); // FIFO: pair 0 is packed first, and its DMA runs while the next pairs are being packed
-        cudaError_t ce = cudaSuccess; // (every job is waited for even after an error: the jobs point at `pending`)
+        // the (pageable, hence synchronously staged) tables go first: queued behind the clouds they would wait for them
+        cudaError_t ce = cudaMemcpyAsync(ctx->A.pc, ctx->h_pc.data(), n_pairs * sizeof(PairConst), cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess && !ctx->h_in_chunks.empty())
+            ce = cudaMemcpyAsync(ctx->A.in_chunks, ctx->h_in_chunks.data(), ctx->h_in_chunks.size() * sizeof(ChunkDesc),
+                                 cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess && !ctx->h_it_chunks.empty())
+            ce = cudaMemcpyAsync(ctx->A.it_chunks, ctx->h_it_chunks.data(), ctx->h_it_chunks.size() * sizeof(ChunkDesc),
+                                 cudaMemcpyHostToDevice, ctx->stream);
+        tables_sent = true; // (every job is waited for even after an error: the jobs point at `pending`)
         for (size_t p = 0; p < n_pairs; ++p) {
             pool.help_until_done(pending[p]);
             const size_t b = slot_begin[p], e = slot_begin[p + 1];
@@ -645,13 +654,15 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
                                ctx->stream));
         }
     }
-    CK(cudaMemcpyAsync(ctx->A.pc, ctx->h_pc.data(), n_pairs * sizeof(PairConst), cudaMemcpyHostToDevice, ctx->stream));
-    if (!ctx->h_in_chunks.empty())
-        CK(cudaMemcpyAsync(ctx->A.in_chunks, ctx->h_in_chunks.data(), ctx->h_in_chunks.size() * sizeof(ChunkDesc),
-                           cudaMemcpyHostToDevice, ctx->stream));
-    if (!ctx->h_it_chunks.empty())
-        CK(cudaMemcpyAsync(ctx->A.it_chunks, ctx->h_it_chunks.data(), ctx->h_it_chunks.size() * sizeof(ChunkDesc),
-                           cudaMemcpyHostToDevice, ctx->stream));
+    if (!tables_sent) {
+        CK(cudaMemcpyAsync(ctx->A.pc, ctx->h_pc.data(), n_pairs * sizeof(PairConst), cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->h_in_chunks.empty())
+            CK(cudaMemcpyAsync(ctx->A.in_chunks, ctx->h_in_chunks.data(), ctx->h_in_chunks.size() * sizeof(ChunkDesc),
+                               cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->h_it_chunks.empty())
+            CK(cudaMemcpyAsync(ctx->A.it_chunks, ctx->h_it_chunks.data(), ctx->h_it_chunks.size() * sizeof(ChunkDesc),
+                               cudaMemcpyHostToDevice, ctx->stream));
+    }
     // The tables above live in pageable vectors: cudaMemcpyAsync has already staged them when it returns. The clouds,
     // however, may be the caller's pinned buffers (truly asynchronous copies): a resident upload returns to the caller
     // before anything else runs, so it waits here; a one-shot call goes straight on to run_impl, which synchronises
