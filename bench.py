@@ -166,7 +166,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="scan pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=64,
+                    help="scan pairs per GPU per step (64 = BASELINE config 4: 512 pairs over 8 GPUs)")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--lanes", type=int, default=8, help="concurrent contexts (CUDA streams) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")

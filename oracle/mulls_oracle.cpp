@@ -1920,6 +1920,9 @@ static bool voxel_downsample(const Rows &cloud_in, Rows &cloud_out, float voxel_
 // published 1.10 sources. The float trigonometry of computeRoots (atan2f / cosf / sinf) is evaluated in double and
 // rounded to float (what a correctly rounded libm returns; the CUDA path does the same so that both sides agree bit
 // for bit). Eigen's 4-wide reductions are written in their SSE packet order and marked [ORDER].
+// There is no copy of PCL in this image to diff against: the constants that matter (probability 0.99, the seed 12345,
+// max_sample_checks 1000, "iterations > max_iterations" -> 21 counted trials, max_skip = 10 x max_iterations, the
+// "fewer than 4 inliers: keep the RANSAC coefficients" rule) are as published for 1.10 and are UNPINNED like the rest.
 // ---------------------------------------------------------------------------------------------
 static const int kSacDraws = 16384; // mt19937 outputs available to one plane fit (5461 sample attempts)
 static const uint32_t *sac_draw_table() {

@@ -18,10 +18,11 @@ fp = C.POINTER(C.c_float)
 for _ in range(3):
     t0 = time.perf_counter(); lib.mulls_pack_rows(rows.ctypes.data_as(fp), n, 1, outb[off:].ctypes.data_as(fp)); dt = time.perf_counter() - t0
 print(f"host cores {os.cpu_count()}; mulls_pack_rows on one thread: {dt/n*1e9:.2f} ns/point ({48*n/dt/1e9:.1f} GB/s read)", flush=True)
-allpairs = bench.make_pairs(bench.rank_seeds(0, 64), "c2")
+allpairs = bench.make_pairs(bench.rank_seeds(0, int(os.environ.get("SWEEP_MAX_PAIRS", "64"))), "c2")
 keep = bench.pin_pairs(allpairs)
 ms = max(sum(len(s) for s in p["src"]) for p in allpairs); mt = max(sum(len(t) for t in p["tgt"]) for p in allpairs)
-for P, lanes in ((32, 8), (48, 12), (64, 16), (64, 8), (32, 8)):
+CONFIGS = [tuple(int(v) for v in c.split("x")) for c in os.environ.get("SWEEP_CONFIGS", "32x8,48x12,64x16,64x8,32x8").split(",")]
+for P, lanes in CONFIGS:
     pairs = allpairs[:P]
     pc = PipelinedContext(0, lanes, (P + lanes - 1) // lanes, ms, mt)
     pc.upload(pairs)
