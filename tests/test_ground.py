@@ -189,6 +189,33 @@ def test_product_core_on_host_small_and_unshuffled(host_harness):
         _same(host_harness(raw, p), oracle.fast_ground_filter(raw, p), str(kw))
 
 
+def test_product_core_on_host_edge_cases(host_harness):
+    """Tiny and degenerate clouds, points exactly on cell borders, half the cloud above the height ceiling, NaN heights,
+    very dense cells, collinear cells (no plane): the product's core and the restatement must agree on all of them."""
+    raw, _ = raw_scan(seed=9, config="small")
+    cases = {"tiny": raw[:5], "one": raw[:1], "duplicates": np.repeat(raw[:1], 50, axis=0)}
+    g = raw[:4000].copy()
+    g[:, 0], g[:, 1] = np.round(g[:, 0] / 3.0) * 3.0, np.round(g[:, 1] / 3.0) * 3.0
+    cases["borders"] = g
+    h = raw[:3000].copy()
+    h[:, 2] += 10.0 * (np.arange(3000) % 2)
+    cases["half_high"] = h
+    z = raw[:3000].copy()
+    z[::7, 2] = np.nan
+    cases["nan_z"] = z
+    d = raw[:3000].copy()
+    d[:, 0:2] *= 0.01
+    cases["dense_cell"] = d
+    c = raw[:3000].copy()
+    c[:, 1] = c[:, 2] = c[:, 0]
+    cases["collinear"] = c
+    for name, cloud in cases.items():
+        for kw in ({}, dict(estimate_ground_normal_method=0),
+                   dict(distance_weight_downsampling_method=0, min_grid_pt_num=3, max_ground_height=0.5)):
+            p = params(**kw)
+            _same(host_harness(cloud, p), oracle.fast_ground_filter(cloud, p), f"{name} {kw}")
+
+
 def test_oracle_voxel_downsample_keeps_one_point_per_voxel():
     raw, _ = raw_scan()
     for size in (0.05, 0.2):
