@@ -46,6 +46,14 @@ int main() {
                                                     0, 3, 2.0f, 2, 15.0f, false, 300, false, FLT_MAX, false);
     (void)vox;
     (void)gf;
+    // CFilter::extract_semantic_pts with the argument list of test/mulls_slam.cpp:363-377 (all 50 arguments)
+    cloudblock_Ptr blk(new cloudblock_t);
+    int ground_down_rate = 15, nonground_down_rate = 3;
+    bool ext = lo::b200::extract_semantic_pts<Point_T>(blk, 0.05f, 3.0f, 0.3f, 1.5f, 5.0f, ground_down_rate, nonground_down_rate, 1.0f, 50,
+                                                       0.65f, 0.65f, 0.12f, 0.75f, 0.75f, false, 2, 15.0f, 3, 2.0f, false, false, false, 2, 10,
+                                                       0, 2, 8, 1, FLT_MAX, 0.94f, 0.17f, 0.98f, 0.34f, true, false, 300, 200, 800, 200, 100,
+                                                       10000, FLT_MAX, 0.0f, 2.0f, -7.0f, 0.3f, false, false, 0.0f, 0.0f);
+    (void)ext;
     std::printf("shim compiled and linked; codes %d %d %d | map %d %d %d\n", code, code2, (int)ok4, (int)up1, (int)up2, code3);
     return 0;
 }

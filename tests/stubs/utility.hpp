@@ -69,9 +69,10 @@ struct cloudblock_t {
     Eigen::Matrix4d pose_lo = Eigen::Matrix4d::Identity(), pose_gt = Eigen::Matrix4d::Identity();
     int feature_point_num = 0;
     pcTPtr pc_ground, pc_facade, pc_roof, pc_pillar, pc_beam, pc_vertex;
-    pcTPtr pc_ground_down, pc_facade_down, pc_roof_down, pc_pillar_down, pc_beam_down, pc_unground, pc_raw, pc_down;
+    pcTPtr pc_ground_down, pc_facade_down, pc_roof_down, pc_pillar_down, pc_beam_down, pc_unground, pc_raw, pc_down, pc_sketch;
+    int down_feature_point_num = 0;
     cloudblock_t() {
-        pcTPtr *all[] = {&pc_ground, &pc_facade, &pc_roof, &pc_pillar, &pc_beam, &pc_vertex, &pc_unground, &pc_raw, &pc_down,
+        pcTPtr *all[] = {&pc_ground, &pc_facade, &pc_roof, &pc_pillar, &pc_beam, &pc_vertex, &pc_unground, &pc_raw, &pc_down, &pc_sketch,
                          &pc_ground_down, &pc_facade_down, &pc_roof_down, &pc_pillar_down, &pc_beam_down};
         for (auto p : all) *p = pcTPtr(new pcl::PointCloud<Point_T>());
     }
