@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -241,7 +241,7 @@ def main():
     pipe = PipelinedContext(local_rank, lanes, (args.pairs + lanes - 1) // lanes, max_src, max_tgt)
 
     # ---- (A) device-resident, one stream: per-kernel attribution for the roofline ----------------
-    sampler = ClockSampler(local_rank)  # samples every 50 ms through all warm-up and timed regions below
+    sampler = ClockSampler(local_rank)  # samples every 200 ms (the recipe's interval; a 50 ms poll measurably slowed the host-API-heavy e2e leg) through all warm-up and timed regions below
     sampler.start()
     ctx.upload(pairs)
     res = None
