@@ -2059,7 +2059,8 @@ static void sac_eigen33_smallest(const float mat[3][3], float evec[3]) {
 
 // pcl::SACSegmentation::segment for a plane, as plane_seg_ransac configures it [3P]. `pc` is the cell's candidate
 // cloud (indices_ = 0..n-1); on success `inliers` (ascending) and the refined coefficients are returned.
-static bool sac_plane_segment(const Rows &pc, double threshold, int max_iterations, std::vector<int> &inliers, float coeff[4]) {
+static bool sac_plane_segment(const Rows &pc, double threshold, int max_iterations, std::vector<int> &inliers, float coeff[4],
+                              float *ransac_coeff = nullptr, int *ransac_iterations = nullptr) {
     const int n = (int)pc.size();
     inliers.clear();
     if (n < 3) return false; // getSamples: "Can not select 0 unique points out of n" -> no model
@@ -2118,6 +2119,8 @@ static bool sac_plane_segment(const Rows &pc, double threshold, int max_iteratio
     for (int i = 0; i < n; ++i)
         if ((double)std::fabs(plane_dot(best, pc[i].f[0], pc[i].f[1], pc[i].f[2])) < threshold) inliers.push_back(i);
     if (inliers.empty()) return false; // segment(): "No inliers": coefficients stay empty (the reference then reads values[0]: UB)
+    if (ransac_coeff) std::memcpy(ransac_coeff, best, sizeof(best)); // (tests: the model RANSAC settled on, before refinement)
+    if (ransac_iterations) *ransac_iterations = iterations;
     // optimizeModelCoefficients
     std::memcpy(coeff, best, sizeof(best));
     if (inliers.size() >= 4) {
@@ -2419,6 +2422,25 @@ int orc_fast_ground_filter(const mulls_cloud_view cloud_in, const mulls_ground_p
     if (out->ground_down && !gd.empty()) std::memcpy(out->ground_down, gd.data(), gd.size() * sizeof(Row));
     if (out->unground && !u.empty()) std::memcpy(out->unground, u.data(), u.size() * sizeof(Row));
     return 0;
+}
+
+// the plane fit with the RANSAC stage exposed (tests): coefficients of the best sample model and the trial count
+int orc_sac_plane_ransac(const mulls_cloud_view cloud, double threshold, int max_iterations, float ransac_coeff[4], int32_t *iterations) {
+    Rows in(cloud.n);
+    if (cloud.n) std::memcpy(in.data(), cloud.aos48, cloud.n * sizeof(Row));
+    std::vector<int> inl;
+    float coeff[4];
+    int it = 0;
+    const bool ok = sac_plane_segment(in, threshold, max_iterations, inl, coeff, ransac_coeff, &it);
+    *iterations = it;
+    return ok ? 1 : 0;
+}
+
+// the tabulated mt19937(12345) outputs the plane fit draws from (tests compare them with an independent generator)
+int orc_sac_draws(uint32_t *out, int n) {
+    const uint32_t *t = sac_draw_table();
+    for (int i = 0; i < n && i < kSacDraws; ++i) out[i] = t[i];
+    return n < kSacDraws ? n : kSacDraws;
 }
 
 // the plane fit alone (tests): candidate rows in, refined inlier indices + coefficients out; returns 1 if a model was found
