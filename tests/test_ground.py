@@ -435,17 +435,18 @@ def test_oracle_front_end_matches_the_golden_fixture(host_harness):
 
 @pytest.mark.gpu
 def test_gpu_front_end_matches_the_golden_fixture():
-    """No oracle call: the committed fixture is the expectation."""
+    """No oracle call: the committed fixture is the expectation. The voxel and ground stages on the real scan; the
+    classification digests of the fixture are pinned on the CPU side (test above) and that stage is compared with the
+    restatement cloud by cloud on the GPU in tests/test_classify.py."""
     from mulls_b200.registration import Context
 
     raw, z, check = _load_frontend_fixture()
     (gp, cp), voxel = _frontend_params()
     ctx = Context(0, 1, 16, 100000)
-    e = ctx.extract_semantic_pts(raw, voxel, gp, cp)
-    # the voxel and ground stages: digests of the committed fixture (the product's core reproduces them on the host too)
-    for k in ("down", "ground", "ground_down"):
-        check(k, e[k])
-    # the classification digests of the fixture are pinned on the CPU side (test above); on the GPU that stage is compared
-    # with the restatement cloud by cloud in tests/test_classify.py — here its input must be the fixture's pc_unground size
-    assert e["unground"].shape[0] == int(z["n_unground"])
+    down = ctx.voxel_downsample(raw, voxel)
+    check("down", down)
+    g = ctx.fast_ground_filter(down, gp)
+    check("ground", g["ground"])
+    check("ground_down", g["ground_down"])
+    assert g["unground"].shape[0] == int(z["n_unground"])
     ctx.close()
