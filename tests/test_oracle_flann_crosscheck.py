@@ -48,3 +48,33 @@ def test_oracle_nn_equals_flann_on_the_real_data_fixture():
     for c in range(6):
         if len(pair["tgt"][c]) >= 10 and len(pair["src"][c]):
             _check(pair["tgt"][c], pair["src"][c], f"class {c}")
+
+
+def test_oracle_pca_neighbourhoods_equal_flann_radius_search():
+    """PrincipleComponentAnalysis::get_pc_pca_feature (pca.hpp:294-354) takes the K nearest neighbours within R from
+    KdTreeFLANN::radiusSearch. The oracle's neighbourhoods (size, eigenvalues, normal) against cv2.flann's radius search
+    followed by a float64 numpy eigen-decomposition of the same covariance."""
+    from test_classify import unground_cloud
+
+    ung = unground_cloud(n_keep=20000)
+    R, K = 0.7, 25
+    o = oracle.pca_features(ung, R, K, 1)
+    xyz = np.ascontiguousarray(ung[:, :3])
+    index = cv2.flann_Index(xyz, dict(algorithm=4, leaf_max_size=15))
+    r2 = float(np.float32(np.float64(np.float32(R)) ** 2))  # KdTreeFLANN::radiusSearch: (float)(radius * radius)
+    checked = 0
+    for q in np.random.default_rng(0).choice(len(ung), 400, replace=False):
+        n, ind, _ = index.radiusSearch(xyz[q:q + 1], r2, K, params=dict(checks=-1, eps=0.0, sorted=True))
+        m = min(int(n), K)
+        assert m == o["pt_num"][q], q
+        if m <= 3:
+            continue
+        nb = xyz[ind[0, :m]].astype(np.float64)
+        w, v = np.linalg.eigh(np.cov(nb.T))  # ascending; cov / (n - 1) like pcl::PCA
+        ev = o["eigenvalues"][q].astype(np.float64)  # descending
+        assert np.allclose(ev, w[::-1], rtol=2e-3, atol=1e-6), (q, ev, w[::-1])
+        if w[1] - w[0] > 1e-3 * w[2]:  # the normal is well defined
+            nrm = o["normal"][q].astype(np.float64)
+            assert abs(nrm @ v[:, 0]) > np.cos(np.radians(1.0)), q
+        checked += 1
+    assert checked > 300
