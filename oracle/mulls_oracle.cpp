@@ -13,7 +13,10 @@
 // function cites the lines it restates. Third-party semantics (PCL 1.10 / FLANN 1.9.1 /
 // Eigen 3.3.7 — not vendored in the reference) are restated from their published behaviour and
 // marked [3P]. It is cross-checked by an independent numpy/scipy restatement in
-// tests/test_oracle_crosscheck.py and by ground-truth recovery tests, not by the reference binary.
+// tests/test_oracle_crosscheck.py and by ground-truth recovery tests, not by the reference binary. The one piece of
+// third-party code available here, OpenCV's FLANN descendant (cv2.flann), pins the kd-tree NN stage bit for bit and
+// the PCA neighbourhoods (tests/test_oracle_flann_crosscheck.py); tests/test_ground_crosscheck.py pins the ground
+// filter's restatement against independent numpy / pure-Python restatements (incl. the mt19937 sample stream).
 //
 // Arithmetic fidelity: the reference mixes float and double exactly as written in its source; the
 // expressions below keep the same operand types so that the compiler applies the same conversions.
