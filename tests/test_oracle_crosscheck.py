@@ -122,3 +122,25 @@ def test_first_iteration_normal_equations(oracle_mod, small_pair):
     np.testing.assert_allclose(bvec, tr["atpb"][0], rtol=0, atol=2e-5 * np.abs(tr["atpb"][0]).max())
     x = np.linalg.solve(tr["atpa"][0], tr["atpb"][0])
     np.testing.assert_allclose(x, tr["x"][0], rtol=1e-8, atol=1e-12)
+
+
+def test_increment_matrix_is_the_roll_pitch_yaw_rotation_of_scipy(small_pair):
+    """construct_trans_a (cregistration.hpp:2740-2764) builds Rz(gamma) Ry(beta) Rx(alpha) from the solved 6-vector
+    (tx ty tz alpha beta gamma): with max_iter_num = 1 the registration result IS that matrix (:1357-1405), so it must
+    equal scipy's extrinsic 'xyz' Euler rotation of the solution the trace reports."""
+    from scipy.spatial.transform import Rotation
+
+    from mulls_b200 import abi
+    from oracle import oracle
+
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.max_iter_num = 1
+    res, tr = oracle.icp_run(small_pair["tgt"], small_pair["src"], p, np.eye(4))
+    assert res["code"] == 1 and res["iters"] == 1
+    x = np.asarray(tr["x"][0], dtype=np.float64)
+    T = np.asarray(res["T"], dtype=np.float64).reshape(4, 4)
+    assert np.linalg.norm(x[3:]) > 1e-4  # a real rotation, not the identity
+    R = Rotation.from_euler("xyz", x[3:6]).as_matrix()
+    np.testing.assert_allclose(T[:3, :3], R, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(T[:3, 3], x[:3], rtol=0, atol=1e-15)
+    assert np.array_equal(T[3], [0.0, 0.0, 0.0, 1.0])
