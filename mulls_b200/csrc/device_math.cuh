@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdint>
 
+#include "grid_key.cuh"
+
 namespace mulls {
 
 __device__ __forceinline__ int float_to_ordered(float f) {
@@ -13,33 +15,6 @@ __device__ __forceinline__ int float_to_ordered(float f) {
     return i >= 0 ? i : (i ^ 0x7fffffff);
 }
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : (i ^ 0x7fffffff)); }
-
-// FLANN L2_Simple<float> accumulation (result += diff*diff per axis, float) — the distance the
-// reference's kd-tree returns to CorrespondenceEstimation (cregistration.hpp:1745).
-__device__ __forceinline__ float flann_l2(float px, float py, float pz, float qx, float qy, float qz) {
-    float dx = px - qx, dy = py - qy, dz = pz - qz;
-    return (dx * dx + dy * dy) + dz * dz;
-}
-
-// 12-bit -> every third bit
-__device__ __forceinline__ uint64_t spread12(uint32_t v) {
-    uint64_t x = v & 0xfffu;
-    x = (x | (x << 16)) & 0x0000ff0000ffull;       // not needed for 12 bits but keeps the pattern generic
-    x = (x | (x << 8)) & 0x00f00f00f00full;
-    x = (x | (x << 4)) & 0x0c30c30c30c3ull;
-    x = (x | (x << 2)) & 0x249249249249ull;
-    return x;
-}
-__device__ __forceinline__ uint64_t morton36(uint32_t x, uint32_t y, uint32_t z) {
-    return spread12(x) | (spread12(y) << 1) | (spread12(z) << 2);
-}
-
-__device__ __forceinline__ uint32_t hash_key(uint64_t key) {
-    key ^= key >> 33;
-    key *= 0xff51afd7ed558ccdull;
-    key ^= key >> 29;
-    return (uint32_t)key;
-}
 
 // cregistration.hpp:2686-2692 get_weight_by_dist_adaptive
 __device__ __forceinline__ float weight_by_dist_adaptive(float dist, int iter_num) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/mulls_b200/abi.h"
+#include "search_core.cuh" // HashEntry, GridView
 
 namespace mulls {
 
@@ -16,6 +17,7 @@ constexpr int kMaxLevels = 12;
 constexpr int kCoordBits = 12;            // Morton bits per axis
 constexpr int kDedupMinSrc = 500;         // K_filter_distant_point (cregistration.hpp:1704)
 constexpr unsigned kClaimFree = 0x7f7f7f7fu;
+constexpr int kIterFlags = 256;           // per-iteration stop flags kept for the launch loop of sharded runs
 
 enum PairStatus : int { kRunning = 0, kNeedPosterior = 1, kDone = 2 };
 
@@ -105,10 +107,6 @@ struct PairState {
     uint32_t kl_hist[kNumSegs][256];
 };
 
-struct HashEntry { // 16 B, one LDG.128 per probe
-    uint32_t key_lo, key_hi, start, count;
-};
-
 // All device pointers of a context, passed by value to the kernels.
 struct DeviceArrays {
     const float4 *in_aos;   // input clouds, 3 float4 per point (pcl::PointXYZINormal)
@@ -140,6 +138,7 @@ struct DeviceArrays {
     double *xch_f64;        // exchange buffer of the sharded mode (per-class sums), 6*kTerms + 2 doubles
     int *running;           // pairs still iterating (device counter)
     volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop
+    volatile int *h_running_iter; // [it]: pairs still iterating at the END of iteration it (sharded runs: rank-deterministic stop)
 };
 
 } // namespace mulls

@@ -417,14 +417,10 @@ __global__ void __launch_bounds__(256) k_gather(DeviceArrays A, const uint64_t *
 }
 
 // ---- hashed multi-level grid over a target class --------------------------------------------
-// key of the level-l cell containing Morton code m:  ((l+1) << 40) | (m >> 3l); 0 marks an empty slot.
-__device__ __forceinline__ uint64_t cell_key(int level, uint64_t code_at_level) {
-    return ((uint64_t)(level + 1) << 40) | code_at_level;
-}
-
-__device__ __forceinline__ void hash_insert(HashEntry *table, uint32_t mask, uint64_t key, uint32_t start) {
-    uint32_t slot = hash_key(key) & mask;
-    const unsigned long long packed = key;
+// Entry = {key_lo, key_hi | child mask << 16, start, count} (grid_key.cuh); (0, 0) marks an empty slot.
+__device__ __forceinline__ void hash_insert(HashEntry *table, uint32_t mask, uint32_t klo, uint32_t khi, uint32_t start) {
+    uint32_t slot = cell_hash(klo, khi) & mask;
+    const unsigned long long packed = (unsigned long long)klo | ((unsigned long long)khi << 32);
     while (true) {
         unsigned long long *kp = reinterpret_cast<unsigned long long *>(&table[slot]);
         unsigned long long old = atomicCAS(kp, 0ull, packed);
@@ -436,10 +432,8 @@ __device__ __forceinline__ void hash_insert(HashEntry *table, uint32_t mask, uin
     }
 }
 // key_hi carries, above the 16 key bits, the 8-bit mask of existing children (set while closing cells)
-constexpr uint32_t kKeyHiMask = 0xffffu;
-__device__ __forceinline__ HashEntry *hash_find(HashEntry *table, uint32_t mask, uint64_t key) {
-    uint32_t slot = hash_key(key) & mask;
-    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+__device__ __forceinline__ HashEntry *hash_find(HashEntry *table, uint32_t mask, uint32_t klo, uint32_t khi) {
+    uint32_t slot = cell_hash(klo, khi) & mask;
     while (true) {
         const uint32_t lo = *reinterpret_cast<volatile uint32_t *>(&table[slot].key_lo);
         const uint32_t hi = *reinterpret_cast<volatile uint32_t *>(&table[slot].key_hi);
@@ -497,7 +491,9 @@ __global__ void __launch_bounds__(256) k_hash_build(DeviceArrays A, const uint64
         const uint32_t local = i - ps.seg_start[cls];
         HashEntry *table = A.hash + ps.hash_base[cls];
         const uint64_t m = kcur & mmask;
-        for (int l = 0; l <= top && l < L; ++l) hash_insert(table, ps.hash_mask[cls], cell_key(l, m >> (3 * l)), local);
+        const uint32_t x0 = compact12(m), y0 = compact12(m >> 1), z0 = compact12(m >> 2);
+        for (int l = 0; l <= top && l < L; ++l)
+            hash_insert(table, ps.hash_mask[cls], cell_key_lo(x0 >> l, y0 >> l, z0 >> l), cell_key_hi(z0 >> l, l), local);
     } else {
         if (!prev_t) return;
         const uint32_t sg = (uint32_t)(kprev >> 36);
@@ -507,13 +503,14 @@ __global__ void __launch_bounds__(256) k_hash_build(DeviceArrays A, const uint64
         const uint32_t local_end = i - ps.seg_start[cls];
         HashEntry *table = A.hash + ps.hash_base[cls];
         const uint64_t m = kprev & mmask;
+        const uint32_t x0 = compact12(m), y0 = compact12(m >> 1), z0 = compact12(m >> 2);
         for (int l = 0; l <= top && l < L; ++l) {
-            const uint64_t code = m >> (3 * l);
-            HashEntry *e = hash_find(table, ps.hash_mask[cls], cell_key(l, code));
+            const uint32_t x = x0 >> l, y = y0 >> l, z = z0 >> l;
+            HashEntry *e = hash_find(table, ps.hash_mask[cls], cell_key_lo(x, y, z), cell_key_hi(z, l));
             if (e) e->count = local_end - e->start;
-            if (l + 1 < L) { // tell the parent which of its 8 children exists
-                HashEntry *par = hash_find(table, ps.hash_mask[cls], cell_key(l + 1, code >> 3));
-                if (par) atomicOr(&par->key_hi, 1u << (16 + (uint32_t)(code & 7)));
+            if (l + 1 < L) { // tell the parent which of its 8 children exists (child = x bit | y bit << 1 | z bit << 2)
+                HashEntry *par = hash_find(table, ps.hash_mask[cls], cell_key_lo(x >> 1, y >> 1, z >> 1), cell_key_hi(z >> 1, l + 1));
+                if (par) atomicOr(&par->key_hi, 1u << (16 + ((x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2))));
             }
         }
     }

@@ -18,353 +18,39 @@
 namespace mulls {
 
 // ------------------------------------------------------------------------------------------------
-// exact 1-NN within radius on the multi-level hashed grid of one target class
+// exact 1-NN within radius on the multi-level hashed grid of one target class: search_core.cuh
+// (__host__ __device__; the CPU suite runs the same functions against a brute-force scan)
 // ------------------------------------------------------------------------------------------------
-struct GridView {
-    const HashEntry *table;
-    uint32_t mask;
-    const float4 *pos; // class slice
-    const float4 *nrm; // class slice (w = original index, for tie-breaks)
-    float ox, oy, oz, h0, inv_h0;
-    int n_levels;
-    int leaf_count; // cells with at most this many points are scanned, larger ones are descended
-    int defer_scan; // queue the leaves of a block and scan them together after its traversal
+constexpr int kSearchRanges = 8;  // candidate ranges queued per thread before the flat scan (one block / one split)
+constexpr int kSearchStack = 12;  // dense cells waiting to be split (overflow: the cell is scanned whole)
+
+// per-thread scratch of the search in shared memory, interleaved by thread (conflict-free 8-byte accesses)
+struct SmemScratch {
+    uint2 *base; // &s_scratch[0][threadIdx.x]
+    __device__ __forceinline__ uint2 &range(int i) { return base[i * kIterBlock]; }
+    __device__ __forceinline__ uint2 &stack(int i) { return base[(kSearchRanges + i) * kIterBlock]; }
 };
 
-__device__ __forceinline__ bool probe(const GridView &g, uint64_t key, uint32_t &start, uint32_t &count,
-                                      uint32_t &child_mask) {
-    uint32_t slot = hash_key(key) & g.mask;
-    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
-    while (true) {
-        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(&g.table[slot]));
-        if (e.x == klo && (e.y & kKeyHiMask) == khi) {
-            start = e.z;
-            count = e.w;
-            child_mask = e.y >> 16;
-            return true;
-        }
-        if (e.x == 0u && e.y == 0u) return false;
-        slot = (slot + 1) & g.mask;
-    }
-}
-
-// distance along one axis from p to the (slightly inflated) extent of cell x at a level with cell size H
-__device__ __forceinline__ float axis_dist(float o, float H, int x, float p, float margin) {
-    const float lo = o + (float)x * H - margin, hi = o + (float)(x + 1) * H + margin;
-    return fmaxf(0.0f, fmaxf(lo - p, p - hi));
-}
-
-constexpr int kLeafQueue = 8;   // leaves of one block whose scan is deferred to the end of its traversal
-
-// examine the points [start, start+count) of a leaf: FLANN distance, total order (d2, original index)
-__device__ __forceinline__ void scan_leaf(const GridView &g, float px, float py, float pz, uint32_t start, uint32_t count,
-                                          float &best_d2, int &best_j) {
-    for (uint32_t jj = start; jj < start + count; ++jj) {
-        const float4 q = __ldg(&g.pos[jj]);
-        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-        if (d2 < best_d2) {
-            best_d2 = d2;
-            best_j = (int)jj;
-        } else if (d2 == best_d2 && (int)jj != best_j) {
-            const int oj = __float_as_int(__ldg(&g.nrm[jj]).w);
-            const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
-            if (oj < ob) best_j = (int)jj;
-        }
-    }
-}
-
-// No candidate yet (first iteration): walk greedily from p's own cell (first level, from `l` upwards, at which it
-// exists) down through the nearest existing child to a leaf and take its best point as the seed. A handful of
-// probes, and the exact search that follows has a tight bound from its first cell on instead of stacking every
-// sibling within the (large) search radius. Ties are settled by the exact search.
-__device__ __forceinline__ void greedy_seed(const GridView &g, float px, float py, float pz, int l, float &best_d2,
-                                            int &best_j) {
-    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
-    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
-    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
-    const int L = g.n_levels;
-    l = min(max(l, 1), L - 1);
-    for (int lr = l; lr < L && best_j < 0; ++lr) {
-        const int ncell = (1 << kCoordBits) >> lr;
-        int cx = c0x >> lr, cy = c0y >> lr, cz = c0z >> lr;
-        if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell)) break;
-        uint64_t code = morton36((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-        for (int lv = lr;; --lv) {
-            uint32_t start, count, cmask;
-            if (!probe(g, cell_key(lv, code), start, count, cmask)) break; // only possible at lv == lr
-            if (count <= (uint32_t)g.leaf_count || lv == 0) {
-                for (uint32_t jj = start; jj < start + count; ++jj) {
-                    const float4 q = __ldg(&g.pos[jj]);
-                    const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-                    if (d2 < best_d2) {
-                        best_d2 = d2;
-                        best_j = (int)jj;
-                    }
-                }
-                break;
-            }
-            const float hl = g.h0 * (float)(1 << lv);
-            const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
-            const int oy = (py >= g.oy + ((float)cy + 0.5f) * hl) ? 1 : 0;
-            const int oz = (pz >= g.oz + ((float)cz + 0.5f) * hl) ? 1 : 0;
-            int ch = ox | (oy << 1) | (oz << 2);
-            if (!((cmask >> ch) & 1u)) ch = __ffs((int)cmask) - 1; // any existing child still yields a valid seed
-            if (ch < 0) break;
-            code = (code << 3) | (uint64_t)ch;
-            cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
-        }
-    }
+__device__ __forceinline__ GridView grid_of(const DeviceArrays &A, const PairConst &pc, const PairState &ps, int c, int leaf_count) {
+    GridView g;
+    g.table = A.hash + ps.hash_base[c];
+    g.mask = ps.hash_mask[c];
+    g.pos = A.tgt_pos + pc.tgt_base[c];
+    g.nrm = A.tgt_nrm + pc.tgt_base[c];
+    g.ox = ps.origin[0], g.oy = ps.origin[1], g.oz = ps.origin[2];
+    g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
+    g.n_levels = ps.n_levels;
+    g.leaf_count = leaf_count;
+    return g;
 }
 
 // squared distance from p to the (slightly inflated) box of cell (x,y,z) at a level with cell size hl
 __device__ __forceinline__ float cell_dist2(const GridView &g, float px, float py, float pz, float hl, int x, int y,
                                             int z, float margin) {
-    const float ax = axis_dist(g.ox, hl, x, px, margin), ay = axis_dist(g.oy, hl, y, py, margin),
-                az = axis_dist(g.oz, hl, z, pz, margin);
+    const float ax = slab_dist(g.ox + (float)x * hl, g.ox + (float)(x + 1) * hl, px, margin);
+    const float ay = slab_dist(g.oy + (float)y * hl, g.oy + (float)(y + 1) * hl, py, margin);
+    const float az = slab_dist(g.oz + (float)z * hl, g.oz + (float)(z + 1) * hl, pz, margin);
     return ax * ax + ay * ay + az * az;
-}
-
-constexpr int kPacketStack = 96; // warp-shared DFS entries of the packet search (3 words each, in shared memory)
-
-// Packet search: the 32 queries of a warp (Morton-adjacent source points, each with a seed) are resolved by ONE
-// warp-uniform traversal. The warp walks the cells overlapping the union of the lanes' search balls; a cell is
-// visited if ANY lane can still improve inside it, its points are then tested by the lanes that need it. No lane
-// waits for another lane's traversal (the cause of the 11/32 thread efficiency of the per-thread search), at the
-// price of testing the union of the candidate sets. Exact for every lane: each lane sees a superset of the cells
-// its own ball overlaps. Returns false (nothing done) when the packet is too spread out for this to pay.
-__device__ __forceinline__ bool packet_search(const GridView &g, bool valid, float px, float py, float pz, float r2_prune,
-                                              float max_ext, float &best_d2, int &best_j, uint32_t *stk) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const float margin = 1e-3f * g.h0;
-    const float bound0 = fminf(best_d2, r2_prune);
-    const float r = valid ? sqrtf(bound0) * 1.0001f + 2.0f * margin : 0.0f;
-    float lo[3] = {valid ? px - r : INFINITY, valid ? py - r : INFINITY, valid ? pz - r : INFINITY};
-    float hi[3] = {valid ? px + r : -INFINITY, valid ? py + r : -INFINITY, valid ? pz + r : -INFINITY};
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[d] = fminf(lo[d], __shfl_xor_sync(full, lo[d], o));
-            hi[d] = fmaxf(hi[d], __shfl_xor_sync(full, hi[d], o));
-        }
-    if (!(hi[0] >= lo[0])) return true; // no valid lane
-    const float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
-    if (!(ext <= max_ext)) return false; // spread-out packet (or an unseeded lane): per-thread search instead
-    // level whose cells are at least as wide as the union box: it overlaps at most 2 (3 with rounding) cells per axis
-    const int L = g.n_levels;
-    int l = 0;
-    while (l < L - 1 && g.h0 * (float)(1 << l) < ext) ++l;
-    const int ncell = (1 << kCoordBits) >> l;
-    int clo[3], chi[3];
-    {
-        const float o3[3] = {g.ox, g.oy, g.oz};
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            clo[d] = max(((int)floorf((lo[d] - o3[d]) * g.inv_h0)) >> l, 0);
-            chi[d] = min(((int)floorf((hi[d] - o3[d]) * g.inv_h0)) >> l, ncell - 1);
-        }
-    }
-    if ((chi[0] - clo[0] + 1) * (chi[1] - clo[1] + 1) * (chi[2] - clo[2] + 1) > 27) return false;
-    // warp-uniform DFS; the stack lives in shared memory, written by lane 0
-    int sp = 0;
-    for (int z = clo[2]; z <= chi[2]; ++z)
-        for (int y = clo[1]; y <= chi[1]; ++y)
-            for (int x = clo[0]; x <= chi[0]; ++x) {
-                if (lane == 0) {
-                    const uint64_t code = morton36((uint32_t)x, (uint32_t)y, (uint32_t)z);
-                    stk[3 * sp + 0] = (uint32_t)code;
-                    stk[3 * sp + 1] = (uint32_t)(code >> 32) | ((uint32_t)l << 4) | ((uint32_t)x << 8) | ((uint32_t)y << 20);
-                    stk[3 * sp + 2] = (uint32_t)z;
-                }
-                ++sp;
-            }
-    __syncwarp();
-    while (sp > 0) {
-        --sp;
-        const uint32_t w0 = stk[3 * sp + 0], meta = stk[3 * sp + 1], w2 = stk[3 * sp + 2];
-        __syncwarp(); // everyone has read the entry before lane 0 may overwrite the slot
-        const uint64_t code = (uint64_t)w0 | ((uint64_t)(meta & 0xf) << 32);
-        const int lv = (int)((meta >> 4) & 0xf), cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)w2;
-        const float hl = g.h0 * (float)(1 << lv);
-        const bool need = valid && cell_dist2(g, px, py, pz, hl, cx, cy, cz, margin) <= fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-        if (!__any_sync(full, need)) continue;
-        uint32_t start, count, cmask;
-        if (!probe(g, cell_key(lv, code), start, count, cmask)) continue; // uniform key: one broadcast load
-        if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kPacketStack) {
-            if (need) scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
-        } else {
-            if (lane == 0) {
-                int k = sp;
-                for (int ch = 0; ch < 8; ++ch)
-                    if ((cmask >> ch) & 1u) {
-                        const uint64_t cc = (code << 3) | (uint64_t)ch;
-                        stk[3 * k + 0] = (uint32_t)cc;
-                        stk[3 * k + 1] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) | ((uint32_t)(2 * cx + (ch & 1)) << 8) |
-                                         ((uint32_t)(2 * cy + ((ch >> 1) & 1)) << 20);
-                        stk[3 * k + 2] = (uint32_t)(2 * cz + (ch >> 2));
-                        ++k;
-                    }
-            }
-            sp += __popc(cmask & 0xffu);
-            __syncwarp();
-        }
-    }
-    return true;
-}
-
-constexpr int kStackDepth = 48; // DFS entries: at most 7 stay behind per descended level
-
-// Exact nearest target (index within the class slice) under the total order (d2, original index) among
-// all targets with d2 <= r2_prune.
-//
-// Ascend: at level l >= 1 the 2x2x2 block of cells that contains p's own cell and, along every axis, the
-// neighbour on the side of the half of the cell p lies in, covers the 3x3x3 block of level l-1 around p.
-// Every target closer than cover_l = 0.999 * h_(l-1) is therefore inside the block (the 0.1% absorbs the
-// float rounding of the cell assignment), and the search stops at the first level whose block has been
-// examined with best <= cover_l or cover_l >= radius. 8 probes per level instead of 27.
-// Descend: a cell holding more than leaf_count points is not scanned but split: its entry carries the
-// mask of existing children, the per-axis distances to the two child slabs are computed once, and only
-// children that exist and can still beat the best distance are pushed (nearest octant last = popped first;
-// Morton code = parent code << 3 | child) — the octree analogue of the kd-tree descent it replaces.
-// `budget` > 0 bounds the number of cell visits: when it runs out the function returns false with the best
-// candidate found so far (a valid seed for a second, unbounded call) — used to keep the 32 traversals of a
-// warp from waiting on a few expensive queries (they are regrouped and finished together, see k_search).
-__device__ __forceinline__ bool nn_search(const GridView &g, float px, float py, float pz, float r2_prune,
-                                          int start_level, float &best_d2, int &best_j, int budget) {
-    // best_d2 / best_j come in seeded: (INFINITY, -1) or a real candidate (the previous iteration's match)
-    int steps_left = (budget > 0) ? budget : 0x7fffffff;
-    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
-    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
-    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
-    const int L = g.n_levels;
-    const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
-    uint32_t st_code[kStackDepth], st_meta[kStackDepth], st_z[kStackDepth];
-    float st_d2[kStackDepth];
-    uint32_t q_start[kLeafQueue], q_count[kLeafQueue];
-    int nq = 0;
-    int l = min(max(start_level, 1), L - 1);
-    if (best_j >= 0) { // seeded: the smallest level whose coverage 0.999 * h0 * 2^(l-1) reaches the seed
-        const float need = 1.001f * sqrtf(best_d2) / (0.999f * 0.5f * g.h0);
-        l = min(max((need <= 1.0f) ? 0 : (ilogbf(need) + 1), 1), L - 1);
-    }
-    for (;; ++l) {
-        const float H = g.h0 * (float)(1 << l);
-        const int ncell = (1 << kCoordBits) >> l;
-        int xs[2], ys[2], zs[2];
-        xs[0] = c0x >> l, ys[0] = c0y >> l, zs[0] = c0z >> l;
-        xs[1] = xs[0] + (((c0x >> (l - 1)) & 1) ? 1 : -1);
-        ys[1] = ys[0] + (((c0y >> (l - 1)) & 1) ? 1 : -1);
-        zs[1] = zs[0] + (((c0z >> (l - 1)) & 1) ? 1 : -1);
-        float ex[2], ey[2], ez[2];
-        uint64_t sx[2], sy[2], sz[2];
-        bool vx[2], vy[2], vz[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            vx[i] = xs[i] >= 0 && xs[i] < ncell;
-            vy[i] = ys[i] >= 0 && ys[i] < ncell;
-            vz[i] = zs[i] >= 0 && zs[i] < ncell;
-            ex[i] = axis_dist(g.ox, H, xs[i], px, margin);
-            ey[i] = axis_dist(g.oy, H, ys[i], py, margin);
-            ez[i] = axis_dist(g.oz, H, zs[i], pz, margin);
-            ex[i] *= ex[i], ey[i] *= ey[i], ez[i] *= ez[i];
-            sx[i] = spread12((uint32_t)xs[i]);
-            sy[i] = spread12((uint32_t)ys[i]) << 1;
-            sz[i] = spread12((uint32_t)zs[i]) << 2;
-        }
-        // Live cells of the block as a bit mask, then one loop trip per LIVE cell: the 32 lanes of a warp run
-        // their i-th live cell together instead of idling through each other's pruned slots.
-        uint32_t live = 0;
-        {
-            const float bound0 = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-                if (vx[i] && vy[j] && vz[m] && ex[i] + ey[j] + ez[m] <= bound0) live |= 1u << k;
-            }
-        }
-#pragma unroll 1
-        while (live) { // lowest bit first: k = 0 is p's own cell
-            const int k = __ffs(live) - 1;
-            live &= live - 1;
-            const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-            int sp = 0;
-            {
-                const uint64_t code = sx[i] | sy[j] | sz[m];
-                st_code[0] = (uint32_t)code;
-                st_meta[0] = (uint32_t)(code >> 32) | ((uint32_t)l << 4) | ((uint32_t)xs[i] << 8) | ((uint32_t)ys[j] << 20);
-                st_z[0] = (uint32_t)zs[m];
-                st_d2[0] = ex[i] + ey[j] + ez[m];
-                sp = 1;
-            }
-            while (sp > 0) {
-                --sp;
-                // a cell farther than the best so far (or than the radius) cannot change the result
-                if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
-                if (--steps_left < 0) return false;
-                const uint32_t meta = st_meta[sp];
-                const uint64_t code = (uint64_t)st_code[sp] | ((uint64_t)(meta & 0xf) << 32);
-                const int lv = (int)((meta >> 4) & 0xf);
-                uint32_t start, count, cmask;
-                if (!probe(g, cell_key(lv, code), start, count, cmask)) continue;
-                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStackDepth) {
-                    if (g.defer_scan && nq < kLeafQueue) { // scanned together with the block's other leaves
-                        q_start[nq] = start;
-                        q_count[nq] = count;
-                        ++nq;
-                    } else {
-                        scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
-                    }
-                } else {
-                    const int cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)st_z[sp];
-                    const float hc = 0.5f * g.h0 * (float)(1 << lv);
-                    float ax[2], ay[2], az[2];
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        ax[b] = axis_dist(g.ox, hc, 2 * cx + b, px, margin);
-                        ay[b] = axis_dist(g.oy, hc, 2 * cy + b, py, margin);
-                        az[b] = axis_dist(g.oz, hc, 2 * cz + b, pz, margin);
-                        ax[b] *= ax[b], ay[b] *= ay[b], az[b] *= az[b];
-                    }
-                    // octant of p relative to the cell centre: the child with zero (or least) distance
-                    const int near_child = (ax[1] < ax[0] ? 1 : 0) | (ay[1] < ay[0] ? 2 : 0) | (az[1] < az[0] ? 4 : 0);
-                    const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-                    // children that exist and can still beat the bound, as a bit mask (no 8-trip loop) ...
-                    uint32_t pass = 0;
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                        if (ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2] <= bound) pass |= 1u << ch;
-                    pass &= cmask;
-                    // ... re-indexed by c = ch ^ near_child (bit permutation by conditional swaps), so that the
-                    // highest set bit is the farthest octant: pushed first, the nearest one last (popped first)
-                    if (near_child & 1) pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
-                    if (near_child & 2) pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
-                    if (near_child & 4) pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
-                    while (pass) {
-                        const int c = 31 - __clz((int)pass);
-                        pass ^= 1u << c;
-                        const int ch = c ^ near_child;
-                        const uint64_t cc = (code << 3) | (uint64_t)ch;
-                        st_code[sp] = (uint32_t)cc;
-                        st_meta[sp] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) |
-                                      ((uint32_t)(2 * cx + (ch & 1)) << 8) | ((uint32_t)(2 * cy + ((ch >> 1) & 1)) << 20);
-                        st_z[sp] = (uint32_t)(2 * cz + (ch >> 2));
-                        st_d2[sp] = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
-                        ++sp;
-                    }
-                }
-            }
-        }
-        // the queued leaves of this block: the lanes of a warp scan them at the same time
-        for (int qi = 0; qi < nq; ++qi) scan_leaf(g, px, py, pz, q_start[qi], q_count[qi], best_d2, best_j);
-        nq = 0;
-        const float cover = 0.999f * 0.5f * H; // every target closer than this has been examined
-        const float cover2 = cover * cover;
-        if (best_d2 <= cover2) break;  // the best found is the global nearest
-        if (cover2 >= r2_prune) break; // whole search radius examined
-        if (l == L - 1) break;         // (n_levels is chosen so that the line above fires first)
-    }
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,9 +58,11 @@ __device__ __forceinline__ bool nn_search(const GridView &g, float px, float py,
 // (pcl::registration::CorrespondenceEstimationNormalShooting): same hierarchy as nn_search, the pruning bound is
 // the current k-th best distance and there is no search radius — the level pyramid of a pair that uses normal
 // shooting goes up to a block that spans the whole grid, so the result is exact however far the targets are.
-// Total order (d2, original index).
+// Total order (d2, original index). A rarely used option: plain per-thread DFS with its stack in local memory,
+// kept out of k_search (own kernel, k_search_shoot).
 // ------------------------------------------------------------------------------------------------
 constexpr int kShootK = 10;
+constexpr int kShootStack = 48; // DFS entries: at most 7 stay behind per descended level
 
 struct KnnList {
     float d2[kShootK];
@@ -413,8 +101,8 @@ __device__ __forceinline__ void knn_search(const GridView &g, float px, float py
     const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
     const int L = g.n_levels;
     const float margin = 1e-3f * g.h0;
-    uint32_t st_code[kStackDepth], st_meta[kStackDepth], st_z[kStackDepth];
-    float st_d2[kStackDepth];
+    uint2 st_cell[kShootStack]; // pack_cell(x, y, z, level, 0)
+    float st_d2[kShootStack];
     for (int l = min(max(start_level, 1), L - 1);; ++l) {
         const float H = g.h0 * (float)(1 << l);
         const int ncell = (1 << kCoordBits) >> l;
@@ -425,39 +113,30 @@ __device__ __forceinline__ void knn_search(const GridView &g, float px, float py
             if (ncell == 2) x = k & 1, y = (k >> 1) & 1, z = k >> 2; // top of the full pyramid: the 8 cells ARE the grid
             if (x < 0 || y < 0 || z < 0 || x >= ncell || y >= ncell || z >= ncell) continue;
             int sp = 0;
-            {
-                const uint64_t code = morton36((uint32_t)x, (uint32_t)y, (uint32_t)z);
-                st_code[0] = (uint32_t)code;
-                st_meta[0] = (uint32_t)(code >> 32) | ((uint32_t)l << 4) | ((uint32_t)x << 8) | ((uint32_t)y << 20);
-                st_z[0] = (uint32_t)z;
-                st_d2[0] = cell_dist2(g, px, py, pz, H, x, y, z, margin);
-                sp = 1;
-            }
+            st_cell[0] = pack_cell((uint32_t)x, (uint32_t)y, (uint32_t)z, l, 0u);
+            st_d2[0] = cell_dist2(g, px, py, pz, H, x, y, z, margin);
+            sp = 1;
             while (sp > 0) {
                 --sp;
                 if (st_d2[sp] > knn_bound(kl) * 1.0001f + 1e-12f) continue;
-                const uint32_t meta = st_meta[sp];
-                const uint64_t code = (uint64_t)st_code[sp] | ((uint64_t)(meta & 0xf) << 32);
-                const int lv = (int)((meta >> 4) & 0xf);
+                const uint2 ce = st_cell[sp];
+                const int lv = (int)((ce.y >> 4) & 0xfu);
+                const int cx = (int)(ce.x & 0xfffu), cy = (int)((ce.x >> 12) & 0xfffu), cz = (int)((ce.x >> 24) | ((ce.y & 0xfu) << 8));
                 uint32_t start, count, cmask;
-                if (!probe(g, cell_key(lv, code), start, count, cmask)) continue;
-                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStackDepth) {
+                if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) continue;
+                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kShootStack) {
                     for (uint32_t jj = start; jj < start + count; ++jj) {
                         const float4 q = __ldg(&g.pos[jj]);
                         knn_insert(g, kl, flann_l2(px, py, pz, q.x, q.y, q.z), (int)jj);
                     }
                 } else {
-                    const int cx = (int)((meta >> 8) & 0xfff), cy = (int)(meta >> 20), cz = (int)st_z[sp];
                     const float hc = 0.5f * g.h0 * (float)(1 << lv);
                     for (int ch = 7; ch >= 0; --ch) {
                         if (!((cmask >> ch) & 1u)) continue;
                         const int x2 = 2 * cx + (ch & 1), y2 = 2 * cy + ((ch >> 1) & 1), z2 = 2 * cz + (ch >> 2);
                         const float d2c = cell_dist2(g, px, py, pz, hc, x2, y2, z2, margin);
                         if (d2c > knn_bound(kl) * 1.0001f + 1e-12f) continue;
-                        const uint64_t cc = (code << 3) | (uint64_t)ch;
-                        st_code[sp] = (uint32_t)cc;
-                        st_meta[sp] = (uint32_t)(cc >> 32) | ((uint32_t)(lv - 1) << 4) | ((uint32_t)x2 << 8) | ((uint32_t)y2 << 20);
-                        st_z[sp] = (uint32_t)z2;
+                        st_cell[sp] = pack_cell((uint32_t)x2, (uint32_t)y2, (uint32_t)z2, lv - 1, 0u);
                         st_d2[sp] = d2c;
                         ++sp;
                     }
@@ -471,29 +150,13 @@ __device__ __forceinline__ void knn_search(const GridView &g, float px, float py
 }
 
 // ---- k_search ----------------------------------------------------------------------------------
-// start level for a search seeded with a candidate at squared distance d2: the smallest level whose
-// guaranteed coverage 0.999 * h0 * 2^(l-1) reaches that distance
-__device__ __forceinline__ int level_for_distance(const GridView &g, float d2) {
-    const float need = 1.001f * sqrtf(d2) / (0.999f * 0.5f * g.h0);
-    return (need <= 1.0f) ? 0 : (ilogbf(need) + 1);
-}
-
-__global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                      int budget, int defer_scan, float packet_max_ext) {
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
-    const PairConst &pc = A.pc[cd.pair];
-    const PairState &ps = A.ps[cd.pair];
-    if (ps.status != kRunning || A.hash_used[1]) return;
-    const int c = (int)cd.seg;
-    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
-    if ((int)cd.first >= ns) return; // block-uniform
-    const uint32_t local = cd.first + threadIdx.x;
-    const bool valid = (int)local < ns;
-    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
-    float4 p = A.src_pos[buf][gi];
-    float4 n = A.src_nrm[buf][gi];
+// what every search kernel does first: cregistration.hpp:1260 — incremental in-place update of the float source
+// cloud by the previous iteration's TempTran (double math, float store, as pcl::transformPointCloudWithNormals)
+__device__ __forceinline__ void load_and_advance(DeviceArrays &A, const PairState &ps, int buf, uint32_t gi, bool valid,
+                                                 float4 &p, float4 &n) {
+    p = A.src_pos[buf][gi];
+    n = A.src_nrm[buf][gi];
     if (valid && ps.iter > 0) {
-        // cregistration.hpp:1260 — incremental in-place update of the float source cloud
         const double *t = ps.T_inc;
         const double px = p.x, py = p.y, pz = p.z, qx = n.x, qy = n.y, qz = n.z;
         p.x = (float)(t[0] * px + t[1] * py + t[2] * pz + t[3]);
@@ -505,6 +168,28 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
         A.src_pos[buf][gi] = p;
         A.src_nrm[buf][gi] = n;
     }
+}
+
+// shoot = 0: every class except the normal-shooting ones; shoot = 1 (k_search_shoot): only those
+__device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
+    return pc.normal_shooting && (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF);
+}
+
+__global__ void __launch_bounds__(kIterBlock, 6) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
+                                                          float reseed_cells) {
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    const PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning || A.hash_used[1]) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
+    if ((int)cd.first >= ns) return; // block-uniform
+    if (shoots(pc, c)) return;       // block-uniform: k_search_shoot's work
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ns;
+    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
+    float4 p, n;
+    load_and_advance(A, ps, buf, gi, valid, p, n);
     // determine_corres needs >= 3 points on both sides (:1727-1728)
     if (!(pc.used[c] && nsg >= 3 && nt >= 3)) { // block-uniform
         if (valid) {
@@ -513,111 +198,36 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
         }
         return;
     }
-    GridView g;
-    g.table = A.hash + ps.hash_base[c];
-    g.mask = ps.hash_mask[c];
-    g.pos = A.tgt_pos + pc.tgt_base[c];
-    g.nrm = A.tgt_nrm + pc.tgt_base[c];
-    g.ox = ps.origin[0], g.oy = ps.origin[1], g.oz = ps.origin[2];
-    g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
-    g.n_levels = ps.n_levels;
-    g.leaf_count = leaf_count;
-    // deferring pays once the seeds are good (from the third iteration on: the big first corrections are applied)
-    g.defer_scan = (defer_scan == 2) ? (ps.iter >= 2) : defer_scan;
+    if (!valid) return;
+    const GridView g = grid_of(A, pc, ps, c, leaf_count);
     // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
     const float max_distance_f = 2.5f * ps.thre;
     const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
     const float r2_prune = (float)max_dist_sqr * 1.0001f;
-
-    if (pc.normal_shooting && (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF)) { // block-uniform
-        // :1732-1737 normal shooting [PCL CorrespondenceEstimationNormalShooting, k = 10]: among the 10 nearest targets
-        // the one with the smallest squared distance to the line through the source point along its normal; dropped
-        // if that value exceeds max_distance (NOT squared); correspondence distance = its squared NN distance.
-        int sj = -1;
-        float sd2 = INFINITY;
-        if (valid) {
-            KnnList kl;
-            knn_search(g, p.x, p.y, p.z, start_level0, kl);
-            double min_dist = 1.7976931348623157e308;
-            for (int t = 0; t < kl.n; ++t) {
-                const float4 q = __ldg(&g.pos[kl.j[t]]);
-                const float ptx = q.x - p.x, pty = q.y - p.y, ptz = q.z - p.z;
-                const double Nx = n.x, Ny = n.y, Nz = n.z, Vx = ptx, Vy = pty, Vz = ptz;
-                const double Cx = Ny * Vz - Nz * Vy, Cy = Nz * Vx - Nx * Vz, Cz = Nx * Vy - Ny * Vx;
-                const double dist = Cx * Cx + (Cy * Cy + Cz * Cz);
-                if (dist < min_dist) {
-                    min_dist = dist;
-                    sj = kl.j[t];
-                    sd2 = kl.d2[t];
-                }
-            }
-            if (sj >= 0 && min_dist > (double)max_distance_f) sj = -1;
-            if (sj >= 0) atomicMin(&A.claim[pc.tgt_base[c] + sj], (unsigned)__float_as_int(n.w));
-            A.nn_idx[gi] = sj;
-            A.nn_d2[gi] = sd2;
-        }
-        return;
-    }
     // seeds: the previous iteration's match (a real candidate, so the box-distance pruning bites from the first
-    // cell on and the search only has to prove that nothing is closer), else a greedy descent
+    // cell on and the search only has to prove that nothing is closer); a stale or missing one is replaced by a
+    // short walk through p's own cells when that is closer
     int best_j = -1;
     float best_d2 = INFINITY;
-    if (valid) {
+    NoStats st;
+    {
         const int pj = A.src_prevj[buf][gi];
         if (pj >= 0) {
             const float4 q = __ldg(&g.pos[pj]);
             best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
             best_j = pj;
-        } else {
-            greedy_seed(g, p.x, p.y, p.z, start_level0, best_d2, best_j);
+        }
+        const float rs = reseed_cells * g.h0;
+        if (best_j < 0 || best_d2 > rs * rs) {
+            float d2 = INFINITY;
+            int j = -1;
+            quick_seed(g, p.x, p.y, p.z, start_level0, d2, j, st);
+            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
         }
     }
-    // packet search: one warp-uniform traversal for the 32 queries of the warp, when they are close together
-    __shared__ uint32_t s_pstack[kIterBlock / 32][3 * kPacketStack];
-    bool finished = false;
-    if (packet_max_ext > 0.0f)
-        finished = packet_search(g, valid, p.x, p.y, p.z, r2_prune, packet_max_ext, best_d2, best_j, s_pstack[threadIdx.x >> 5]);
-    // per-thread search (pass 1, optionally with a bounded number of cell visits)
-    if (!finished) {
-        finished = true;
-        if (valid) finished = nn_search(g, p.x, p.y, p.z, r2_prune, start_level0, best_d2, best_j, budget);
-    }
-    // pass 2: the unfinished (expensive) queries of the block are regrouped into the first threads and
-    // finished there, seeded with what pass 1 found — warps of similar cost instead of 31 idle lanes
-    __shared__ float4 s_q[kIterBlock];   // x y z best_d2
-    __shared__ int s_qj[kIterBlock];     // best_j
-    __shared__ int s_qi[kIterBlock];     // thread that owns the query
-    __shared__ int s_cnt;
-    if (budget > 0) {
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
-        if (!finished) {
-            const int slot = atomicAdd(&s_cnt, 1);
-            s_q[slot] = make_float4(p.x, p.y, p.z, best_d2);
-            s_qj[slot] = best_j;
-            s_qi[slot] = (int)threadIdx.x;
-        }
-        __syncthreads();
-        const int m = s_cnt;
-        if ((int)threadIdx.x < m) {
-            const float4 q = s_q[threadIdx.x];
-            float d2 = q.w;
-            int j = s_qj[threadIdx.x];
-            const int sl = (j >= 0) ? level_for_distance(g, d2) : start_level0;
-            nn_search(g, q.x, q.y, q.z, r2_prune, sl, d2, j, 0);
-            s_q[threadIdx.x].w = d2;
-            s_qj[threadIdx.x] = j;
-        }
-        __syncthreads();
-        if (!finished) { // fetch the result back (slot order is arbitrary: find my slot)
-            for (int t = 0; t < m; ++t)
-                if (s_qi[t] == (int)threadIdx.x) {
-                    best_d2 = s_q[t].w;
-                    best_j = s_qj[t];
-                }
-        }
-    }
-    if (!valid) return;
+    __shared__ uint2 s_scratch[kSearchRanges + kSearchStack][kIterBlock];
+    SmemScratch S{&s_scratch[0][threadIdx.x]};
+    nn_search<kSearchRanges, kSearchStack>(g, p.x, p.y, p.z, r2_prune, start_level0, best_d2, best_j, S, st);
     if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
     if (best_j >= 0) {
         // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
@@ -625,6 +235,54 @@ __global__ void __launch_bounds__(kIterBlock) k_search(DeviceArrays A, int buf, 
     }
     A.nn_idx[gi] = best_j;
     A.nn_d2[gi] = best_d2;
+}
+
+// :1732-1737 normal shooting [PCL CorrespondenceEstimationNormalShooting, k = 10]: among the 10 nearest targets
+// the one with the smallest squared distance to the line through the source point along its normal; dropped
+// if that value exceeds max_distance (NOT squared); correspondence distance = its squared NN distance.
+// Launched only when a pair of the batch asked for normal shooting.
+__global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int buf, int start_level0, int leaf_count) {
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    const PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning || A.hash_used[1]) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
+    if ((int)cd.first >= ns || !shoots(pc, c)) return; // block-uniform
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ns;
+    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
+    float4 p, n;
+    load_and_advance(A, ps, buf, gi, valid, p, n);
+    if (!valid) return;
+    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) {
+        A.nn_idx[gi] = -1;
+        A.nn_d2[gi] = INFINITY;
+        return;
+    }
+    const GridView g = grid_of(A, pc, ps, c, leaf_count);
+    const float max_distance_f = 2.5f * ps.thre;
+    int sj = -1;
+    float sd2 = INFINITY;
+    KnnList kl;
+    knn_search(g, p.x, p.y, p.z, start_level0, kl);
+    double min_dist = 1.7976931348623157e308;
+    for (int t = 0; t < kl.n; ++t) {
+        const float4 q = __ldg(&g.pos[kl.j[t]]);
+        const float ptx = q.x - p.x, pty = q.y - p.y, ptz = q.z - p.z;
+        const double Nx = n.x, Ny = n.y, Nz = n.z, Vx = ptx, Vy = pty, Vz = ptz;
+        const double Cx = Ny * Vz - Nz * Vy, Cy = Nz * Vx - Nx * Vz, Cz = Nx * Vy - Ny * Vx;
+        const double dist = Cx * Cx + (Cy * Cy + Cz * Cz);
+        if (dist < min_dist) {
+            min_dist = dist;
+            sj = kl.j[t];
+            sd2 = kl.d2[t];
+        }
+    }
+    if (sj >= 0 && min_dist > (double)max_distance_f) sj = -1;
+    if (sj >= 0) atomicMin(&A.claim[pc.tgt_base[c] + sj], (unsigned)__float_as_int(n.w));
+    A.nn_idx[gi] = sj;
+    A.nn_d2[gi] = sd2;
 }
 
 // ---- k_resolve ---------------------------------------------------------------------------------
@@ -1231,9 +889,14 @@ __global__ void __launch_bounds__(kIterBlock) k_shard_counts(DeviceArrays A, int
     }
 }
 // after the all-reduce of the per-class sums: every rank solves the same system and advances identically
-__global__ void k_shard_solve(DeviceArrays A, int buf) {
+__global__ void k_shard_solve(DeviceArrays A, int buf, int it_flag) {
     PairState &ps = A.ps[0];
-    if (ps.status != kRunning || threadIdx.x != 0) return;
+    if (threadIdx.x != 0) return;
+    if (ps.status != kRunning) {
+        A.h_running_iter[it_flag] = *A.running;
+        __threadfence_system();
+        return;
+    }
     __shared__ double s_scratch[160];
     mulls_icp_trace *tr = A.trace ? &A.trace[0] : nullptr;
     for (int cc = 0; cc < kNumClasses; ++cc) {
@@ -1242,6 +905,8 @@ __global__ void k_shard_solve(DeviceArrays A, int buf) {
     }
     solve_and_advance(A, 0, A.xch_f64, s_scratch, buf ^ 1);
     for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+    A.h_running_iter[it_flag] = *A.running; // what the launch loop of every rank reads two iterations later
+    __threadfence_system();
 }
 // posterior in sharded mode: VTPV / n_obs of this rank -> exchange buffer
 __global__ void k_shard_post(DeviceArrays A, int phase) {

@@ -138,9 +138,8 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca(DeviceArrays A, PcaArgs 
             const int x = cx + lane % 3 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane / 9 - 1;
             if (x >= 0 && y >= 0 && z >= 0 && x < ncell && y < ncell && z < ncell) {
                 const HashEntry *table = A.hash + ps.hash_base[0];
-                const uint64_t key = cell_key(l, morton36((uint32_t)x, (uint32_t)y, (uint32_t)z));
-                uint32_t slot = hash_key(key) & ps.hash_mask[0];
-                const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+                const uint32_t klo = cell_key_lo((uint32_t)x, (uint32_t)y, (uint32_t)z), khi = cell_key_hi((uint32_t)z, l);
+                uint32_t slot = cell_hash(klo, khi) & ps.hash_mask[0];
                 while (true) {
                     const uint4 e = __ldg(reinterpret_cast<const uint4 *>(&table[slot]));
                     if (e.x == klo && (e.y & kKeyHiMask) == khi) {

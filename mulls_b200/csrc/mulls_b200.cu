@@ -53,9 +53,8 @@ struct mulls_ctx {
     // tunables
     int start_level0 = 5;
     int leaf_count = 32;
-    int search_budget = 0; // cell visits of the first search pass (0 = unbounded, single pass)
-    int defer_scan = 2;    // queue the leaves of a block and scan them together: 0 off, 1 on, 2 from iteration 2 on
-    int packet_max_ext_mm = 0; // packet search for warps whose union search box is at most this wide (0 = off)
+    int reseed_cells_x4 = 8; // a seed farther than this many quarter level-0 cells is challenged by a quick descent
+    bool any_normal_shooting = false;
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h):
     // 0 never, 1 always, 2 when a call ships at least kPackMinPoints points (small calls are latency-bound: raw rows)
@@ -254,12 +253,13 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ALLOC(A.xch_i32, 32);
     ALLOC(A.xch_f64, kNumClasses * kTerms + 8);
 #undef ALLOC
-    if ((e = cudaHostAlloc((void **)&ctx->h_running, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
+    if ((e = cudaHostAlloc((void **)&ctx->h_running, (1 + kIterFlags) * sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
         return fail("mapped flag", e);
     {
         int *dptr = nullptr;
         if ((e = cudaHostGetDevicePointer((void **)&dptr, ctx->h_running, 0)) != cudaSuccess) return fail("mapped flag", e);
         A.h_running = dptr;
+        A.h_running_iter = dptr + 1;
     }
     ctx->ev_done.resize(MULLS_MAX_TRACE_ITERS);
     for (auto &ev : ctx->ev_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -359,9 +359,8 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     std::string n(name);
     if (n == "start_level") ctx->start_level0 = value;
     else if (n == "leaf_count") ctx->leaf_count = value;
-    else if (n == "search_budget") ctx->search_budget = value;
+    else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
-    else if (n == "defer_scan") ctx->defer_scan = value;
     else if (n == "host_pack") ctx->host_pack = value;
     else if (n == "poll_pause") ctx->poll_pause = value;
     else if (n == "stage_wc") {
@@ -373,7 +372,6 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
         ctx->stage_wc = value;
     }
     else if (n == "pack_threads") PackPool::get().ensure_workers(value);
-    else if (n == "packet_max_ext_mm") ctx->packet_max_ext_mm = value;
     else if (n == "h0_min_mm") ctx->h0_min = (float)value / 1000.0f;
     else return MULLS_E_ARG;
     return MULLS_OK;
@@ -509,13 +507,14 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->h_it_chunks.clear();
     size_t in_off = 0, s_off = 0, t_off = 0;
     int max_iter_max = 0;
-    bool any_keep_less = false;
+    bool any_keep_less = false, any_shoot = false;
     for (size_t p = 0; p < n_pairs; ++p) {
         PairConst &pc = ctx->h_pc[p];
         int rc = build_pair_const(ctx, params[p], init_guess + 16 * p, pc);
         if (rc != MULLS_OK) return rc;
         max_iter_max = std::max(max_iter_max, pc.max_iter);
         any_keep_less = any_keep_less || pc.keep_less;
+        any_shoot = any_shoot || pc.normal_shooting;
         size_t ns = 0, nt = 0;
         for (int c = 0; c < kNumClasses; ++c) {
             nt += tgt[p * kNumClasses + c].n;
@@ -674,6 +673,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->n_tgt_total = t_off;
     ctx->max_iter_max = max_iter_max;
     ctx->any_keep_less = any_keep_less;
+    ctx->any_normal_shooting = any_shoot;
     ctx->uploaded = true;
     return MULLS_OK;
 }
@@ -754,7 +754,15 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
 
 // Launch the whole path on the resident inputs. If `hook` is given (sharded mode) it is called between
 // the phases that need a cross-rank exchange.
+static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user);
 static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
+    const int rc = run_impl_inner(ctx, out, trace, hook, user);
+    // an error exit may leave async copies from / into the caller's buffers (clouds, trace, results) in flight:
+    // nothing is handed back before the stream has drained
+    if (rc != MULLS_OK && ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
     if (!ctx || !ctx->uploaded) return MULLS_E_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -778,14 +786,22 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
                 // (poll with pauses: several lanes spinning inside the driver slow each other's launches down)
                 while (cudaEventQuery(ctx->ev_done[it - 2]) == cudaErrorNotReady)
                     for (int k = 0; k < ctx->poll_pause; ++k) _mm_pause();
-                if (*(volatile int *)ctx->h_running <= 0) break;
+                // Sharded runs must take this decision identically on every rank (the ranks issue matching collectives):
+                // they read the count the device recorded at the END of iteration it-2 — written once, before
+                // ev_done[it-2] — never the live flag, whose value at this instant depends on each rank's timing.
+                if (hook ? ((volatile int *)ctx->h_running)[1 + std::min(it - 2, kIterFlags - 1)] <= 0
+                         : *(volatile int *)ctx->h_running <= 0)
+                    break;
             }
             const int buf = it & 1;
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->search_budget, ctx->defer_scan,
-                                                         (float)ctx->packet_max_ext_mm / 1000.0f);
+            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4);
+            if (ctx->any_normal_shooting) {
+                k_search_shoot<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
+                ++launches;
+            }
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
             if (hook) { // exchange 1: the duplicate-check claims of all shards (min of source indices)
                 if (hook(user, A.claim, ctx->n_tgt_total, 1, 1, (void *)st) != 0) {
@@ -810,7 +826,7 @@ static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trac
                     ctx->err = "all-reduce callback failed";
                     return MULLS_E_COMM;
                 }
-                k_shard_solve<<<1, 32, 0, st>>>(A, buf);
+                k_shard_solve<<<1, 32, 0, st>>>(A, buf, std::min(it, kIterFlags - 1));
                 ++launches;
             }
             CK(cudaEventRecord(ctx->ev_done[it], st));
@@ -944,8 +960,14 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
                           const uint32_t src_index_base[MULLS_NUM_CLASSES], const uint32_t src_global_n[MULLS_NUM_CLASSES],
                           const mulls_icp_params *params, const double init_guess[16], mulls_allreduce_fn allreduce,
                           void *user, mulls_icp_result *out, mulls_icp_trace *trace) {
-    if (!ctx || !allreduce) return MULLS_E_ARG;
+    if (!ctx || !allreduce || !params) return MULLS_E_ARG;
     if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    if (params->keep_less_source_points && !params->apply_motion_undistortion_while_registration) {
+        // the down-sampling quota and its sampling keys are defined over the WHOLE source cloud (:2866-2892); a
+        // shard-local plan would keep ~world times too many points and a different subset than the unsharded run
+        ctx->err = "keep_less_source_points is not supported for a source-sharded registration";
+        return MULLS_E_UNSUPPORTED;
+    }
     int rc = upload_impl(ctx, 1, tgt, src_shard, params, init_guess, src_index_base, src_global_n, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
     rc = run_impl(ctx, out, trace, allreduce, user);
@@ -1592,7 +1614,7 @@ int mulls_classify_nground(mulls_ctx *ctx, mulls_cloud_view cloud_in, const mull
             ctx->err = "mulls_classify_nground: output buffer too small";
             return MULLS_E_CAPACITY;
         }
-        CK(cudaMemcpyAsync(out->rows[k], src[k], cnt[k] * row_b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->rows[k], src[k], cnt[k] * row_b, cudaMemcpyDefault, st));
     }
     CK(cudaEventRecord(ctx->ev_end, st));
     CK(cudaStreamSynchronize(st));
@@ -1960,7 +1982,7 @@ int mulls_extract_semantic_pts(mulls_ctx *ctx, mulls_cloud_view pc_raw, const mu
     ms += ctx->stats.ms_total, launches += ctx->stats.kernel_launches;
     out->n_down = n_down;
     if (out->pc_down && n_down) {
-        CK(cudaMemcpyAsync(out->pc_down, d_down, n_down * row_b, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out->pc_down, d_down, n_down * row_b, cudaMemcpyDefault, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     // :2355-2361 fast_ground_filter(pc_down -> pc_ground, pc_ground_down, pc_unground)

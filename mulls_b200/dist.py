@@ -52,3 +52,61 @@ def shard_sources(src_clouds, rank: int, world: int):
         base.append(lo)
         glob.append(n)
     return shards, base, glob
+
+
+def run_sharded_local(pair, world: int, device: int, max_src: int, max_tgt: int, want_trace: bool = False):
+    """BASELINE config 5's partitioning on ONE device (tests, single-GPU boxes): `world` contexts each hold the
+    full target and one contiguous slice of every source class, are driven from `world` host threads, and meet in
+    an all-reduce that combines the ranks' device buffers (sum / min) exactly where ncclAllReduce sits in a
+    multi-GPU run. Returns ([result dict per rank], [trace dict per rank] or None)."""
+    import threading
+
+    import torch
+
+    from .registration import Context
+
+    ctxs = [Context(device, 1, max_src, max_tgt) for _ in range(world)]
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    dev = torch.device("cuda", device)
+
+    def make_hook(rank):
+        def hook(ptr, count, dtype, op, stream):
+            torch.cuda.ExternalStream(stream, device=dev).synchronize()
+            slots[rank] = tensor_from_ptr(ptr, count, dtype, dev)
+            barrier.wait(timeout=120)
+            if rank == 0:
+                stack = torch.stack([s.clone() for s in slots])
+                red = stack.sum(0) if op == 0 else stack.min(0).values
+                for s in slots:
+                    s.copy_(red)
+                torch.cuda.synchronize()
+            barrier.wait(timeout=120)
+            return 0
+
+        return hook
+
+    out = [None] * world
+    err = [None] * world
+
+    def worker(rank):
+        try:
+            shards, base, glob = shard_sources(pair["src"], rank, world)
+            out[rank] = ctxs[rank].run_sharded(dict(pair, src=shards), base, glob, make_hook(rank), want_trace=want_trace)
+        except Exception as exc:  # noqa: BLE001
+            err[rank] = exc
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    for c in ctxs:
+        c.close()
+    for e in err:
+        if e is not None:
+            raise e
+    if any(t.is_alive() for t in threads):
+        raise RuntimeError("sharded run did not finish")
+    return [o[0] for o in out], ([o[1] for o in out] if want_trace else None)
