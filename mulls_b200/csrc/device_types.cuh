@@ -107,6 +107,8 @@ struct PairState {
     uint32_t kl_hist[kNumSegs][256];
 };
 
+struct FinishSync;
+
 // All device pointers of a context, passed by value to the kernels.
 struct DeviceArrays {
     const float4 *in_aos;   // input clouds, 3 float4 per point (pcl::PointXYZINormal)
@@ -136,6 +138,8 @@ struct DeviceArrays {
     mulls_icp_trace *trace; // may be null
     int *xch_i32;           // exchange buffer of the sharded mode (counts / bbox), 32 ints
     double *xch_f64;        // exchange buffer of the sharded mode (per-class sums), 6*kTerms + 2 doubles
+    unsigned *pair_sync;    // k_finish: per pair [resolved chunks, accumulated chunks] of the current iteration
+    struct FinishSync *fsync; // k_finish: ticket / done counters
     int *running;           // pairs still iterating (device counter)
     volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop
     volatile int *h_running_iter; // [it]: pairs still iterating at the END of iteration it (sharded runs: rank-deterministic stop)

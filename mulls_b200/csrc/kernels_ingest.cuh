@@ -518,16 +518,17 @@ __global__ void __launch_bounds__(256) k_hash_build(DeviceArrays A, const uint64
 
 // k_hash_layout: single block. Power-of-two table per (pair, class) with load factor <= 0.5, carved out
 // of the pool in order; flags overflow instead of writing out of bounds.
-__global__ void k_hash_layout(DeviceArrays A, int n_pairs) {
+__global__ void k_hash_layout(DeviceArrays A, int n_pairs, int slack) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    // load factor <= 0.5 if the pool allows it, else <= 0.8 (longer probe chains, same results), else give up
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // load factor <= 1/slack if the pool allows it (slack 4: a miss costs ~1.4 probes instead of 2.5 at 1/2), else
+    // <= 0.5, else <= 0.8 (longer probe chains, same results), else give up
+    for (int attempt = 0; attempt < 3; ++attempt) {
         uint64_t used = 0;
         bool overflow = false;
         for (int p = 0; p < n_pairs && !overflow; ++p) {
             PairState &ps = A.ps[p];
             for (int c = 0; c < kNumClasses; ++c) {
-                const uint64_t want = (attempt == 0) ? 2ull * ps.hash_entries[c] : (5ull * ps.hash_entries[c]) / 4 + 1;
+                const uint64_t want = (attempt == 0) ? (uint64_t)slack * ps.hash_entries[c] : (attempt == 1) ? 2ull * ps.hash_entries[c] : (5ull * ps.hash_entries[c]) / 4 + 1;
                 uint32_t cap = 16;
                 while (cap < want) cap <<= 1;
                 if (used + cap > A.hash_pool_entries) {

@@ -21,14 +21,141 @@ namespace mulls {
 // exact 1-NN within radius on the multi-level hashed grid of one target class: search_core.cuh
 // (__host__ __device__; the CPU suite runs the same functions against a brute-force scan)
 // ------------------------------------------------------------------------------------------------
-constexpr int kSearchRanges = 8;  // candidate ranges queued per thread before the flat scan (one block / one split)
-constexpr int kSearchStack = 12;  // dense cells waiting to be split (overflow: the cell is scanned whole)
+constexpr int kSearchRanges = 8;  // candidate ranges queued per thread between two scans (one block / one split)
+constexpr int kSearchStack = 8;   // dense cells waiting to be split (overflow: the cell is scanned whole)
 
-// per-thread scratch of the search in shared memory, interleaved by thread (conflict-free 8-byte accesses)
+// ---- the warp-cooperative form of the search (see SoloCoop in search_core.cuh for the per-thread semantics) -----
+// Traversal stays per lane (a few probes per query); the candidates it queues are examined by the whole warp as ONE
+// flat list: per-query candidate counts are broad (median 16, p99 > 100), so a per-lane scan loop keeps ~8 of 32
+// lanes busy, while equal shares of the flat list keep all of them busy whatever the split between the queries.
+//   ranges    lane l queues its ranges straight into ent[0..nr)[l]; obase[l] = items queued by the lanes before l
+//   shares    lane i examines items [i*C, (i+1)*C), C = ceil(T / 32): a 5-step search for the owner of its first
+//             item, then the same lean loop a single thread would run, walking from range to range
+//   result    per owner a 64-bit key (distance bits << 32 | target) in shared memory. A lane keeps the best of the
+//             owner it is working for in registers (starting from the owner's current key, so that most candidates
+//             fail one compare) and publishes an improvement when it moves on to another owner: compare-and-swap
+//             loop; equal distances are settled by the ORIGINAL index, exactly like consider()
+struct WarpShared {
+    uint2 ent[kSearchRanges][32]; // [r][lane] = {start, count}
+    uint32_t obase[33];
+    uint32_t nr[32];
+    float4 qp[32];
+    unsigned long long best[32];
+};
+
+// per-thread scratch of the search in shared memory: the range queue lives in the warp's table, the stack of dense
+// cells is interleaved by thread (conflict-free 8-byte accesses)
 struct SmemScratch {
-    uint2 *base; // &s_scratch[0][threadIdx.x]
-    __device__ __forceinline__ uint2 &range(int i) { return base[i * kIterBlock]; }
-    __device__ __forceinline__ uint2 &stack(int i) { return base[(kSearchRanges + i) * kIterBlock]; }
+    uint2 *ranges; // &warp.ent[0][lane]
+    uint2 *stk;    // &s_stack[0][threadIdx.x]
+    __device__ __forceinline__ uint2 &range(int i) { return ranges[i * 32]; }
+    __device__ __forceinline__ uint2 &stack(int i) { return stk[i * kIterBlock]; }
+};
+
+struct WarpCoop {
+    WarpShared *w;
+    __device__ __forceinline__ bool any(bool b) { return __any_sync(0xffffffffu, b); }
+
+    __device__ __forceinline__ void offer(const GridView &g, int owner, uint32_t d2bits, int j) {
+        unsigned long long old = *(volatile unsigned long long *)&w->best[owner];
+        const unsigned long long mine = ((unsigned long long)d2bits << 32) | (unsigned long long)(uint32_t)j;
+        while (true) {
+            const uint32_t od2 = (uint32_t)(old >> 32);
+            const int oj = (int)(uint32_t)old;
+            bool win = d2bits < od2;
+            if (!win && d2bits == od2 && oj != j)
+                win = oj < 0 || __float_as_int(__ldg(&g.nrm[j]).w) < __float_as_int(__ldg(&g.nrm[oj]).w);
+            if (!win) return;
+            const unsigned long long prev = atomicCAS(&w->best[owner], old, mine);
+            if (prev == old) return;
+            old = prev;
+        }
+    }
+
+    template <class Scratch, class Stats>
+    __device__ __forceinline__ void scan(const GridView &g, float px, float py, float pz, Scratch &S, int &nr, float &best_d2,
+                                         int &best_j, Stats &st) {
+        const unsigned full = 0xffffffffu;
+        if (!__any_sync(full, nr > 0)) return;
+        const int lane = threadIdx.x & 31;
+        uint32_t cnt = 0;
+        for (int r = 0; r < nr; ++r) cnt += S.range(r).y;
+        uint32_t incl = cnt; // inclusive prefix sum of the item counts over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t T = __shfl_sync(full, incl, 31);
+        w->obase[lane] = incl - cnt;
+        w->nr[lane] = (uint32_t)nr;
+        w->qp[lane] = make_float4(px, py, pz, 0.0f);
+        w->best[lane] = ((unsigned long long)__float_as_uint(best_d2) << 32) | (unsigned long long)(uint32_t)best_j;
+        __syncwarp();
+        const unsigned queued = __ballot_sync(full, nr > 0); // lanes that queued anything (the owners to walk through)
+        const uint32_t C = (T + 31u) >> 5;
+        const uint32_t s0 = (uint32_t)lane * C;
+        if (s0 < T) {
+            uint32_t n = min(C, T - s0);
+            // owner of item s0: the last lane whose base is <= s0 (lanes with nothing queued share their successor's base)
+            int owner = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (w->obase[owner + step] <= s0) owner += step;
+            uint32_t r = 0, off = w->obase[owner];
+            uint2 en = w->ent[0][owner];
+            while (off + en.y <= s0) {
+                off += en.y;
+                en = w->ent[++r][owner];
+            }
+            const float4 *cur = g.pos + en.x + (s0 - off);
+            uint32_t seg_left = en.y - (s0 - off);
+            float4 o = w->qp[owner];
+            unsigned long long key = *(volatile unsigned long long *)&w->best[owner];
+            uint32_t lbd = (uint32_t)(key >> 32);
+            int lbj = (int)(uint32_t)key;
+            bool improved = false;
+            while (true) {
+                // the part of the current range that belongs to this lane's share: one tight loop
+                const uint32_t m = min(n, seg_left);
+                n -= m, seg_left -= m;
+#pragma unroll 2
+                for (uint32_t i = 0; i < m; ++i) {
+                    const float4 q = __ldg(cur);
+                    const uint32_t bits = __float_as_uint(flann_l2(o.x, o.y, o.z, q.x, q.y, q.z));
+                    if (bits <= lbd) {
+                        const int jj = (int)(cur - g.pos);
+                        if (bits < lbd) {
+                            lbd = bits, lbj = jj, improved = true;
+                        } else if (jj != lbj &&
+                                   (lbj < 0 || __float_as_int(__ldg(&g.nrm[jj]).w) < __float_as_int(__ldg(&g.nrm[lbj]).w))) {
+                            lbj = jj, improved = true;
+                        }
+                    }
+                    ++cur;
+                }
+                if (n == 0) break;
+                // next range: of the same owner, or of the next lane that queued any
+                if (++r == w->nr[owner]) {
+                    if (improved) offer(g, owner, lbd, lbj);
+                    owner = __ffs((int)(queued & (0xfffffffeu << owner))) - 1;
+                    r = 0;
+                    o = w->qp[owner];
+                    key = *(volatile unsigned long long *)&w->best[owner];
+                    lbd = (uint32_t)(key >> 32), lbj = (int)(uint32_t)key, improved = false;
+                }
+                en = w->ent[r][owner];
+                cur = g.pos + en.x, seg_left = en.y;
+            }
+            if (improved) offer(g, owner, lbd, lbj);
+        }
+        __syncwarp();
+        const unsigned long long b = w->best[lane];
+        best_d2 = __uint_as_float((uint32_t)(b >> 32));
+        best_j = (int)(uint32_t)b;
+        nr = 0;
+        __syncwarp(); // the next round's writes to ent / qp / best must not overtake these reads
+    }
 };
 
 __device__ __forceinline__ GridView grid_of(const DeviceArrays &A, const PairConst &pc, const PairState &ps, int c, int leaf_count) {
@@ -175,7 +302,7 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
     return pc.normal_shooting && (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF);
 }
 
-__global__ void __launch_bounds__(kIterBlock, 6) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
+__global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
                                                           float reseed_cells) {
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
@@ -198,7 +325,6 @@ __global__ void __launch_bounds__(kIterBlock, 6) k_search(DeviceArrays A, int bu
         }
         return;
     }
-    if (!valid) return;
     const GridView g = grid_of(A, pc, ps, c, leaf_count);
     // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
     const float max_distance_f = 2.5f * ps.thre;
@@ -210,24 +336,21 @@ __global__ void __launch_bounds__(kIterBlock, 6) k_search(DeviceArrays A, int bu
     int best_j = -1;
     float best_d2 = INFINITY;
     NoStats st;
-    {
+    if (valid) {
         const int pj = A.src_prevj[buf][gi];
         if (pj >= 0) {
             const float4 q = __ldg(&g.pos[pj]);
             best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
             best_j = pj;
         }
-        const float rs = reseed_cells * g.h0;
-        if (best_j < 0 || best_d2 > rs * rs) {
-            float d2 = INFINITY;
-            int j = -1;
-            quick_seed(g, p.x, p.y, p.z, start_level0, d2, j, st);
-            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
-        }
     }
-    __shared__ uint2 s_scratch[kSearchRanges + kSearchStack][kIterBlock];
-    SmemScratch S{&s_scratch[0][threadIdx.x]};
-    nn_search<kSearchRanges, kSearchStack>(g, p.x, p.y, p.z, r2_prune, start_level0, best_d2, best_j, S, st);
+    const float rs = reseed_cells * g.h0;
+    __shared__ uint2 s_stack[kSearchStack][kIterBlock];
+    __shared__ WarpShared s_warp[kIterBlock / 32];
+    SmemScratch S{&s_warp[threadIdx.x >> 5].ent[0][threadIdx.x & 31], &s_stack[0][threadIdx.x]};
+    WarpCoop co{&s_warp[threadIdx.x >> 5]};
+    nn_search<kSearchRanges, kSearchStack>(g, valid, p.x, p.y, p.z, r2_prune, start_level0, rs * rs, best_d2, best_j, S, co, st);
+    if (!valid) return;
     if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
     if (best_j >= 0) {
         // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
@@ -286,8 +409,17 @@ __global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int
 }
 
 // ---- k_resolve ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) {
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+// kFused: the body runs inside k_finish, where data produced by OTHER blocks of the SAME launch is read — such loads
+// bypass L1 (ld.global.cg): a line cached by an earlier block of this SM may predate the producer's store.
+template <bool kFused, typename T>
+__device__ __forceinline__ T ld_x(const T *p) {
+    if (kFused) return __ldcg(p);
+    return *p;
+}
+
+template <bool kFused>
+__device__ __forceinline__ void resolve_body(DeviceArrays &A, int buf, uint32_t chunk) {
+    const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
     PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning) return;
@@ -338,10 +470,11 @@ __global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf)
             k += s_kept[w];
             p += s_pass[w];
         }
-        A.blk_kept[blockIdx.x] = k;
+        A.blk_kept[chunk] = k;
         if (p) atomicAdd(&ps.n_corr[c], p);
     }
 }
+__global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) { resolve_body<false>(A, buf, blockIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // per-correspondence normal-equation terms. Layout of the kTerms doubles of a partial:
@@ -518,7 +651,7 @@ __device__ __forceinline__ void pair_left_running(DeviceArrays &A) {
 
 // Solve + state update of one pair; executed by thread 0 of the last block of k_accumulate
 // (cregistration.hpp:1301-1400 after the summations). S = per-class sums [6][kTerms] in shared memory.
-__device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *S, double *sm /*>= 150 doubles*/,
+__device__ __noinline__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *S, double *sm /*>= 150 doubles*/,
                                   int buf_written) {
     const PairConst &pc = A.pc[pair];
     PairState &ps = A.ps[pair];
@@ -645,8 +778,9 @@ __device__ void solve_and_advance(DeviceArrays &A, uint32_t pair, const double *
 }
 
 // ---- k_accumulate ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) {
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+template <bool kFused>
+__device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32_t chunk) {
+    const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
     PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning) return;
@@ -671,7 +805,7 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
     {
         uint32_t acc = 0;
         const uint32_t first_chunk = pc.class_chunk_begin[c];
-        for (uint32_t b = first_chunk + threadIdx.x; b < blockIdx.x; b += kIterBlock) acc += A.blk_kept[b];
+        for (uint32_t b = first_chunk + threadIdx.x; b < chunk; b += kIterBlock) acc += ld_x<kFused>(&A.blk_kept[b]);
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) s_off[warp] = acc;
         __syncthreads();
@@ -684,7 +818,7 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
     }
     if (valid) {
         gi = pc.src_base[c] + local;
-        fl = A.flags[gi];
+        fl = ld_x<kFused>(&A.flags[gi]);
     }
     kept = (fl & 1) != 0, pass = (fl & 2) != 0;
     const unsigned kb = __ballot_sync(0xffffffffu, kept);
@@ -716,8 +850,11 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
         d2 = A.nn_d2[gi];
         if (j >= 0) A.claim[pc.tgt_base[c] + j] = kClaimFree; // reset the table for the next iteration
     }
+    uint32_t n_corr[kNumClasses]; // complete since every k_resolve block of the pair has finished
+#pragma unroll
+    for (int k = 0; k < kNumClasses; ++k) n_corr[k] = ld_x<kFused>(&ps.n_corr[k]);
     float ratio_unused;
-    const bool few = too_few(pc, ps, ps.n_corr, ratio_unused);
+    const bool few = too_few(pc, ps, n_corr, ratio_unused);
     if (pass && !few) {
         const float4 q = A.tgt_pos[pc.tgt_base[c] + j];
         const float4 qn = A.tgt_nrm[pc.tgt_base[c] + j];
@@ -725,7 +862,7 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
         const bool resid_w = pc.w_residual && it > 2; // :1905-1907
         const bool dist_w = pc.w_dist != 0, inten_w = pc.w_intensity != 0;
         if (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF) {
-            const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, ps.n_corr);
+            const float wc = (c == MULLS_FACADE) ? 1.0f : balanced_ground_weight(pc, n_corr);
             terms_pt2pl(p, p.w, q, qn, wc, it, dist_w, resid_w, inten_w, pc.win_pt2pl, t, w_store);
         } else if (c == MULLS_PILLAR || c == MULLS_BEAM) {
             terms_pt2li(p, p.w, q, qn, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2li, t, w_store);
@@ -761,23 +898,25 @@ __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int b
     if (threadIdx.x < 27) {
         double v = 0.0;
         for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
-        A.partials[(size_t)blockIdx.x * kTerms + threadIdx.x] = v;
+        A.partials[(size_t)chunk * kTerms + threadIdx.x] = v;
     }
 }
+__global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) { accumulate_body<false>(A, buf, blockIdx.x); }
 
-// ---- k_solve: one block per pair, after k_accumulate. Sums the per-chunk partials of every class in chunk
-//      order (fixed order => bit-reproducible), then one thread solves and advances the pair state.
-constexpr int kSolveThreads = kNumClasses * 32; // one warp per feature class
-__global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf) {
-    const uint32_t pair = blockIdx.x;
+// ---- solve: one block per pair, after every k_accumulate block of the pair. Sums the per-chunk partials of every
+//      class in chunk order (fixed order => bit-reproducible), then one thread solves and advances the pair state.
+//      Any block size that is a multiple of 32: the warps take the classes in turn.
+template <bool kFused>
+__device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pair) {
     const PairConst &pc = A.pc[pair];
     PairState &ps = A.ps[pair];
     if (ps.status != kRunning) return;
-    const int lane = threadIdx.x & 31, cc = threadIdx.x >> 5; // warp = class
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     __shared__ double s_S[kNumClasses][kTerms];
     __shared__ double s_scratch[160];
     __shared__ int s_newn[kNumClasses];
-    {
+    __shared__ uint32_t s_ncorr[kNumClasses];
+    for (int cc = warp; cc < kNumClasses; cc += n_warps) {
         const uint32_t b0 = pc.class_chunk_begin[cc];
         // only the chunks that held live sources this iteration wrote a partial
         const uint32_t live = (uint32_t)((ps.n_src[cc] + kIterBlock - 1) / kIterBlock);
@@ -787,18 +926,21 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf
         if (lane < 27) {
             uint32_t b = b0;
             for (; b + 4 <= b1; b += 4) {
-                a0 += A.partials[(size_t)(b + 0) * kTerms + lane];
-                a1 += A.partials[(size_t)(b + 1) * kTerms + lane];
-                a2 += A.partials[(size_t)(b + 2) * kTerms + lane];
-                a3 += A.partials[(size_t)(b + 3) * kTerms + lane];
+                a0 += ld_x<kFused>(&A.partials[(size_t)(b + 0) * kTerms + lane]);
+                a1 += ld_x<kFused>(&A.partials[(size_t)(b + 1) * kTerms + lane]);
+                a2 += ld_x<kFused>(&A.partials[(size_t)(b + 2) * kTerms + lane]);
+                a3 += ld_x<kFused>(&A.partials[(size_t)(b + 3) * kTerms + lane]);
             }
-            for (; b < b1; ++b) a0 += A.partials[(size_t)b * kTerms + lane];
+            for (; b < b1; ++b) a0 += ld_x<kFused>(&A.partials[(size_t)b * kTerms + lane]);
         }
         if (lane < kTerms) s_S[cc][lane] = (lane < 27) ? ((a0 + a1) + (a2 + a3)) : 0.0;
         uint32_t acc = 0; // kept sources of the class = its new size
-        for (uint32_t b = b0 + lane; b < b1; b += 32) acc += A.blk_kept[b];
+        for (uint32_t b = b0 + lane; b < b1; b += 32) acc += ld_x<kFused>(&A.blk_kept[b]);
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_newn[cc] = (int)acc;
+        if (lane == 0) {
+            s_newn[cc] = (int)acc;
+            s_ncorr[cc] = ld_x<kFused>(&ps.n_corr[cc]);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -819,10 +961,74 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf
         for (int cc = 0; cc < kNumClasses; ++cc) {
             ps.n_src[cc] = s_newn[cc]; // classes that skipped determine_corres keep everything (k_resolve)
             ps.n_src_g[cc] = s_newn[cc];
+            ps.n_corr[cc] = s_ncorr[cc];
             if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src[cc];
         }
         solve_and_advance(A, pair, &s_S[0][0], s_scratch, buf ^ 1);
         for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+    }
+}
+constexpr int kSolveThreads = kNumClasses * 32; // one warp per feature class
+__global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf) { solve_body<false>(A, buf, blockIdx.x); }
+
+// ---- k_finish: everything of one ICP iteration after the search, in ONE launch (2 x chunks blocks). Blocks take
+//      tickets: the first `n_chunks` tickets resolve a chunk (duplicate check, rejectors, counts), the next `n_chunks`
+//      accumulate a chunk — after waiting for every resolve block of THEIR PAIR (the class weights and the
+//      compaction offsets need the pair's complete counts) — and the block that finishes a pair's last chunk solves
+//      its 6x6 system and advances its state. A waiting block only ever waits for tickets handed out BEFORE its own,
+//      i.e. for blocks that are already running and never wait themselves: no deadlock, whatever the residency.
+//      Pairs progress independently: one pair's accumulation overlaps another's resolution.
+struct FinishSync {
+    unsigned ticket, done, stuck, _pad;
+};
+__global__ void __launch_bounds__(kIterBlock) k_finish(DeviceArrays A, int buf, uint32_t n_chunks) {
+    __shared__ uint32_t s_ticket;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&A.fsync->ticket, 1u);
+    __syncthreads();
+    const uint32_t t = s_ticket;
+    const bool second = t >= n_chunks;
+    const uint32_t chunk = second ? t - n_chunks : t;
+    const uint32_t pair = A.it_chunks[chunk].pair;
+    const uint32_t pair_chunks = A.pc[pair].chunk_end - A.pc[pair].chunk_begin;
+    unsigned *resolved = &A.pair_sync[2 * pair], *accumulated = &A.pair_sync[2 * pair + 1];
+    if (!second) {
+        resolve_body<true>(A, buf, chunk);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(resolved, 1u);
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            unsigned spins = 0;
+            while (*(volatile unsigned *)resolved < pair_chunks) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) { // (cannot happen; never hang the device on a logic error)
+                    atomicExch(&A.fsync->stuck, 1u);
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        accumulate_body<true>(A, buf, chunk);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(accumulated, 1u) == pair_chunks - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            solve_body<true>(A, buf, pair);
+            if (threadIdx.x == 0) *resolved = 0, *accumulated = 0; // every block of the pair is past its wait
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&A.fsync->done, 1u) == 2 * n_chunks - 1) A.fsync->ticket = 0, A.fsync->done = 0;
     }
 }
 

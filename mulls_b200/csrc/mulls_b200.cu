@@ -53,6 +53,9 @@ struct mulls_ctx {
     // tunables
     int start_level0 = 5;
     int leaf_count = 32;
+    int fused_finish = 0;    // 1: k_finish (one launch after the search) instead of k_resolve + k_accumulate + k_solve —
+                             // measured slower at batch scale (per-block ticket / fence latency), see DESIGN.md
+    int hash_slack = 4;      // table capacity >= hash_slack x cells (power of two): load factor <= 1/hash_slack
     int reseed_cells_x4 = 8; // a seed farther than this many quarter level-0 cells is challenged by a quick descent
     bool any_normal_shooting = false;
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
@@ -240,6 +243,8 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
         ALLOC(A.hash, pool);
     }
     ALLOC(A.hash_used, 2);
+    ALLOC(A.pair_sync, 2 * max_pairs);
+    ALLOC(A.fsync, 1);
     ALLOC(A.blk_kept, ctx->cap_it_chunks);
     ALLOC(A.partials, ctx->cap_it_chunks * kTerms);
     ALLOC(A.post_partials, ctx->cap_it_chunks * 2);
@@ -360,6 +365,8 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     if (n == "start_level") ctx->start_level0 = value;
     else if (n == "leaf_count") ctx->leaf_count = value;
     else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
+    else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
+    else if (n == "fused_finish") ctx->fused_finish = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "host_pack") ctx->host_pack = value;
     else if (n == "poll_pause") ctx->poll_pause = value;
@@ -740,13 +747,13 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
         k_gather<<<(unsigned)ceil_div(n_in, 256), 256, 0, st>>>(A, A.keys_b, A.vals_b, n_in);
         const unsigned hb = (unsigned)ceil_div((size_t)n_in + 1, 256);
         k_hash_build<<<hb, 256, 0, st>>>(A, A.keys_b, n_in, 0);
-        k_hash_layout<<<1, 32, 0, st>>>(A, np);
+        k_hash_layout<<<1, 32, 0, st>>>(A, np, ctx->hash_slack);
         k_hash_clear<<<1184, 256, 0, st>>>(A);
         k_hash_build<<<hb, 256, 0, st>>>(A, A.keys_b, n_in, 1);
         k_hash_build<<<hb, 256, 0, st>>>(A, A.keys_b, n_in, 2);
         launches += 6;
     } else {
-        k_hash_layout<<<1, 32, 0, st>>>(A, np);
+        k_hash_layout<<<1, 32, 0, st>>>(A, np, ctx->hash_slack);
         ++launches;
     }
     return MULLS_OK;
@@ -776,6 +783,8 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         if (rc != MULLS_OK) return rc;
     }
     const unsigned n_itc = (unsigned)ctx->h_it_chunks.size();
+    CK(cudaMemsetAsync(A.pair_sync, 0, 2 * ctx->max_pairs * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(A.fsync, 0, sizeof(FinishSync), st));
     CK(cudaEventRecord(ctx->ev_ingest, st));
     int n_search_ev = 0;
     if (n_itc) {
@@ -808,6 +817,13 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
                     ctx->err = "all-reduce callback failed";
                     return MULLS_E_COMM;
                 }
+            }
+            if (!hook && ctx->fused_finish) { // resolve + accumulate + solve of every pair in one launch (tickets, see k_finish)
+                k_finish<<<2 * n_itc, kIterBlock, 0, st>>>(A, buf, n_itc);
+                CK(cudaEventRecord(ctx->ev_done[it], st));
+                launches += 2;
+                n_search_ev = it + 1;
+                continue;
             }
             k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
             if (hook) { // exchange 2: correspondence counts (w_ground, -2 test) and surviving source counts

@@ -88,6 +88,15 @@ MULLS_HD int f2i_bits(float f) {
 #endif
 }
 
+// index of the lowest set bit (v != 0)
+MULLS_HD int lowest_bit(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
 // finish a probe whose first slot was loaded by the caller: follow the chain (rare at load factor <= 0.5)
 MULLS_HD bool probe_finish(const GridView &g, uint32_t slot, uint4 e, uint32_t klo, uint32_t khi, uint32_t &start,
                            uint32_t &count, uint32_t &cmask) {
@@ -146,12 +155,11 @@ MULLS_HD void scan_ranges(const GridView &g, float px, float py, float pz, Scrat
     nr = 0;
 }
 
-// No candidate yet: climb from p's own level-1 cell to the first level at which it exists, walk down through the
-// nearest existing child to a small cell and take its best point. A handful of probes; ties are settled by the
-// exact search that follows.
+// No (good) candidate yet: climb from p's own level-1 cell to the first level at which it exists and walk down
+// through the nearest existing child to a small cell. That cell is queued as a candidate range — its best point seeds
+// the exact search (a handful of probes; ties are settled by the search). Returns false if p's cells are all empty.
 template <class Stats>
-MULLS_HD void quick_seed(const GridView &g, float px, float py, float pz, int max_level, float &best_d2, int &best_j,
-                         Stats &st) {
+MULLS_HD bool quick_locate(const GridView &g, float px, float py, float pz, int max_level, uint2 &leaf, Stats &st) {
     const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
     const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
     const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
@@ -167,15 +175,8 @@ MULLS_HD void quick_seed(const GridView &g, float px, float py, float pz, int ma
         for (int lv = lr;;) {
             if (count <= (uint32_t)g.leaf_count || lv == 0) {
                 st.seed_eval((int)count);
-                for (uint32_t jj = start; jj < start + count; ++jj) {
-                    const float4 q = ld_point(&g.pos[jj]);
-                    const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-                    if (d2 < best_d2) {
-                        best_d2 = d2;
-                        best_j = (int)jj;
-                    }
-                }
-                return;
+                leaf = make_uint2(start, count);
+                return true;
             }
             const float hl = g.h0 * (float)(1 << lv);
             const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
@@ -191,13 +192,14 @@ MULLS_HD void quick_seed(const GridView &g, float px, float py, float pz, int ma
                     }
                 ch = bestc;
             }
-            if (ch < 0) return;
+            if (ch < 0) return false;
             cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
             --lv;
             st.seed_probe();
-            if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) return; // (cannot happen)
+            if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) return false; // (cannot happen)
         }
     }
+    return false;
 }
 
 // distance along one axis from p to the slab [lo - margin, hi + margin]
@@ -210,15 +212,143 @@ MULLS_HD uint2 pack_cell(uint32_t x, uint32_t y, uint32_t z, int lv, uint32_t cm
     return make_uint2(cell_key_lo(x, y, z), (z >> 8) | ((uint32_t)lv << 4) | (cmask << 8));
 }
 
-template <int kRanges, int kStack, class Scratch, class Stats>
-MULLS_HD void nn_search(const GridView &g, float px, float py, float pz, float r2_prune, int start_level, float &best_d2,
-                        int &best_j, Scratch &S, Stats &st) {
-    // best_d2 / best_j come in seeded: (INFINITY, -1) or a real candidate
-    const float fx = (px - g.ox) * g.inv_h0, fy = (py - g.oy) * g.inv_h0, fz = (pz - g.oz) * g.inv_h0;
-    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-    const int c0x = (int)flx, c0y = (int)fly, c0z = (int)flz;
+// How the lanes of a warp cooperate. The per-thread form (host instantiation, and the reference semantics of the
+// device form): nothing is shared. The device form (WarpCoop, kernels_iterate.cuh) keeps the 32 lanes of a warp in
+// step through the phases of the search and examines the queued candidates of ALL lanes as one flat list.
+struct SoloCoop {
+    MULLS_HD bool any(bool b) { return b; }
+    template <class Scratch, class Stats>
+    MULLS_HD void scan(const GridView &g, float px, float py, float pz, Scratch &S, int &nr, float &best_d2, int &best_j,
+                       Stats &st) {
+        scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
+    }
+};
+
+// geometry of one query, fixed for the whole search
+struct QueryFrame {
+    float fx, fy, fz, flx, fly, flz; // position in level-0 cell units and its floor
+    int c0x, c0y, c0z;
+    float margin;
+};
+
+// the 2x2x2 block of level l around p: cells that can still beat the bound are probed (eight independent loads);
+// small cells are queued as candidate ranges, dense ones go to the stack
+template <int kStack, class Scratch, class Stats>
+MULLS_HD void block_phase(const GridView &g, const QueryFrame &f, float px, float py, float pz, int l, float bound0,
+                          Scratch &S, int &nr, int &sp, Stats &st) {
+    const float H = g.h0 * (float)(1 << l);
+    const int ncell = 4096 >> l;
+    const int cx = f.c0x >> l, cy = f.c0y >> l, cz = f.c0z >> l;
+    int sx, sy, sz; // side of the half-cell p lies in
+    if (l == 0) {
+        sx = (f.fx - f.flx) >= 0.5f, sy = (f.fy - f.fly) >= 0.5f, sz = (f.fz - f.flz) >= 0.5f;
+    } else {
+        sx = (f.c0x >> (l - 1)) & 1, sy = (f.c0y >> (l - 1)) & 1, sz = (f.c0z >> (l - 1)) & 1;
+    }
+    const int nx = cx + (sx ? 1 : -1), ny = cy + (sy ? 1 : -1), nz = cz + (sz ? 1 : -1);
+    // squared distance from p to the neighbour slab along each axis (p is inside its own slab: 0)
+    float ex = sx ? ((g.ox + (float)(cx + 1) * H) - f.margin) - px : px - ((g.ox + (float)cx * H) + f.margin);
+    float ey = sy ? ((g.oy + (float)(cy + 1) * H) - f.margin) - py : py - ((g.oy + (float)cy * H) + f.margin);
+    float ez = sz ? ((g.oz + (float)(cz + 1) * H) - f.margin) - pz : pz - ((g.oz + (float)cz * H) + f.margin);
+    ex = fmaxf(ex, 0.0f), ey = fmaxf(ey, 0.0f), ez = fmaxf(ez, 0.0f);
+    ex *= ex, ey *= ey, ez *= ez;
+    const bool vx0 = cx >= 0 && cx < ncell, vx1 = nx >= 0 && nx < ncell;
+    const bool vy0 = cy >= 0 && cy < ncell, vy1 = ny >= 0 && ny < ncell;
+    const bool vz0 = cz >= 0 && cz < ncell, vz1 = nz >= 0 && nz < ncell;
+    // cells that can still beat the bound, as a mask; then one probe per live cell (k = 0 is p's own cell)
+    uint32_t live = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool i = k & 1, j = (k >> 1) & 1, m = k >> 2;
+        const float d2c = (i ? ex : 0.0f) + (j ? ey : 0.0f) + (m ? ez : 0.0f);
+        if ((i ? vx1 : vx0) && (j ? vy1 : vy0) && (m ? vz1 : vz0) && d2c <= bound0) live |= 1u << k;
+    }
+    while (live) {
+        const int k = lowest_bit(live);
+        live &= live - 1;
+        const uint32_t x = (uint32_t)((k & 1) ? nx : cx), y = (uint32_t)((k & 2) ? ny : cy), z = (uint32_t)((k & 4) ? nz : cz);
+        uint32_t start, count, cmask;
+        st.probe(0);
+        if (!probe_cell(g, x, y, z, l, start, count, cmask)) continue;
+        if (count <= (uint32_t)g.leaf_count || l == 0 || sp == kStack) S.range(nr++) = make_uint2(start, count);
+        else S.stack(sp++) = pack_cell(x, y, z, l, cmask);
+    }
+}
+
+// split the next dense cell of the stack that can still beat the bound: its existing children within the bound are
+// probed (independent loads); small ones are queued as ranges, dense ones pushed (nearest octant last = next to pop)
+template <int kStack, class Scratch, class Stats>
+MULLS_HD void expand_one(const GridView &g, const QueryFrame &f, float px, float py, float pz, float bound, Scratch &S,
+                         int &nr, int &sp, Stats &st) {
+    while (sp > 0) {
+        const uint2 ce = S.stack(--sp);
+        const int lv = (int)((ce.y >> 4) & 0xfu);
+        const uint32_t cmask = (ce.y >> 8) & 0xffu;
+        const int x = (int)(ce.x & 0xfffu), y = (int)((ce.x >> 12) & 0xfffu), z = (int)((ce.x >> 24) | ((ce.y & 0xfu) << 8));
+        const float hc = 0.5f * g.h0 * (float)(1 << lv); // child size
+        // per-axis squared distances to the two child slabs
+        float ax0, ax1, ay0, ay1, az0, az1;
+        {
+            const float lox = g.ox + (float)(2 * x) * hc, mdx = g.ox + (float)(2 * x + 1) * hc, hix = g.ox + (float)(2 * x + 2) * hc;
+            const float loy = g.oy + (float)(2 * y) * hc, mdy = g.oy + (float)(2 * y + 1) * hc, hiy = g.oy + (float)(2 * y + 2) * hc;
+            const float loz = g.oz + (float)(2 * z) * hc, mdz = g.oz + (float)(2 * z + 1) * hc, hiz = g.oz + (float)(2 * z + 2) * hc;
+            ax0 = slab_dist(lox, mdx, px, f.margin), ax1 = slab_dist(mdx, hix, px, f.margin);
+            ay0 = slab_dist(loy, mdy, py, f.margin), ay1 = slab_dist(mdy, hiy, py, f.margin);
+            az0 = slab_dist(loz, mdz, pz, f.margin), az1 = slab_dist(mdz, hiz, pz, f.margin);
+            ax0 *= ax0, ax1 *= ax1, ay0 *= ay0, ay1 *= ay1, az0 *= az0, az1 *= az1;
+        }
+        // the cell itself may have fallen behind the bound since it was pushed
+        if (fminf(ax0, ax1) + fminf(ay0, ay1) + fminf(az0, az1) > bound) continue;
+        st.expand();
+        const int near_child = (ax1 < ax0 ? 1 : 0) | (ay1 < ay0 ? 2 : 0) | (az1 < az0 ? 4 : 0);
+        // existing children within the bound, re-indexed by c = ch ^ near_child so that the lowest bit is the
+        // farthest octant: pushed first, the nearest one last (popped first)
+        uint32_t pass = 0;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+            if (((ch & 1) ? ax1 : ax0) + ((ch & 2) ? ay1 : ay0) + ((ch & 4) ? az1 : az0) <= bound) pass |= 1u << ch;
+        pass &= cmask;
+        if (near_child & 1) pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
+        if (near_child & 2) pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
+        if (near_child & 4) pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
+        pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1); // reverse the 8 bits: farthest (c = 7) becomes bit 0
+        pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
+        pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
+        while (pass) {
+            const int b = lowest_bit(pass);
+            pass &= pass - 1;
+            const int ch = (7 - b) ^ near_child;
+            const uint32_t x2 = (uint32_t)(2 * x + (ch & 1)), y2 = (uint32_t)(2 * y + ((ch >> 1) & 1)), z2 = (uint32_t)(2 * z + (ch >> 2));
+            uint32_t start, count, cm2;
+            st.probe(1);
+            if (!probe_cell(g, x2, y2, z2, lv - 1, start, count, cm2)) continue;
+            if (count <= (uint32_t)g.leaf_count || lv - 1 == 0 || sp == kStack) S.range(nr++) = make_uint2(start, count);
+            else S.stack(sp++) = pack_cell(x2, y2, z2, lv - 1, cm2);
+        }
+        return; // one split per round: what it queued is examined before the next dense cell is opened
+    }
+}
+
+// `active`: this lane holds a query (all lanes of a warp call the function; see Coop). kRanges >= 8: one block or one
+// split queues at most eight ranges between two scans.
+// reseed_d2: a candidate farther than this (or none at all) is challenged by the small cell quick_locate finds.
+template <int kRanges, int kStack, class Scratch, class Coop, class Stats>
+MULLS_HD void nn_search(const GridView &g, bool active, float px, float py, float pz, float r2_prune, int start_level,
+                        float reseed_d2, float &best_d2, int &best_j, Scratch &S, Coop &co, Stats &st) {
+    static_assert(kRanges >= 8, "a block or a split queues up to eight ranges");
+    // best_d2 / best_j come in seeded: (INFINITY, -1) or a real candidate (the previous iteration's match)
+    int nr = 0, sp = 0;
+    if (active && (best_j < 0 || best_d2 > reseed_d2)) {
+        uint2 leaf;
+        if (quick_locate(g, px, py, pz, start_level, leaf, st)) S.range(nr++) = leaf;
+    }
+    co.scan(g, px, py, pz, S, nr, best_d2, best_j, st); // the seed cells of all lanes, examined together
+    QueryFrame f;
+    f.fx = (px - g.ox) * g.inv_h0, f.fy = (py - g.oy) * g.inv_h0, f.fz = (pz - g.oz) * g.inv_h0;
+    f.flx = floorf(f.fx), f.fly = floorf(f.fy), f.flz = floorf(f.fz);
+    f.c0x = (int)f.flx, f.c0y = (int)f.fly, f.c0z = (int)f.flz;
+    f.margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
     const int L = g.n_levels;
-    const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
     int l;
     if (best_j >= 0) { // seeded: the smallest level whose coverage reaches the seed
         const float need = 1.001f * sqrtf(best_d2);
@@ -229,120 +359,26 @@ MULLS_HD void nn_search(const GridView &g, float px, float py, float pz, float r
     } else {
         l = (start_level < 1) ? 1 : ((start_level < L - 1) ? start_level : L - 1);
     }
-    int nr = 0, sp = 0;
-    for (;; ++l) {
-        st.level();
-        const float H = g.h0 * (float)(1 << l);
-        const int ncell = 4096 >> l;
-        const int cx = c0x >> l, cy = c0y >> l, cz = c0z >> l;
-        int sx, sy, sz; // side of the half-cell p lies in
-        if (l == 0) {
-            sx = (fx - flx) >= 0.5f, sy = (fy - fly) >= 0.5f, sz = (fz - flz) >= 0.5f;
-        } else {
-            sx = (c0x >> (l - 1)) & 1, sy = (c0y >> (l - 1)) & 1, sz = (c0z >> (l - 1)) & 1;
+    while (co.any(active)) {
+        if (active) {
+            st.level();
+            block_phase<kStack>(g, f, px, py, pz, l, fminf(best_d2, r2_prune) * 1.0001f + 1e-12f, S, nr, sp, st);
         }
-        const int nx = cx + (sx ? 1 : -1), ny = cy + (sy ? 1 : -1), nz = cz + (sz ? 1 : -1);
-        // squared distance from p to the neighbour slab along each axis (p is inside its own slab: 0)
-        float ex = sx ? ((g.ox + (float)(cx + 1) * H) - margin) - px : px - ((g.ox + (float)cx * H) + margin);
-        float ey = sy ? ((g.oy + (float)(cy + 1) * H) - margin) - py : py - ((g.oy + (float)cy * H) + margin);
-        float ez = sz ? ((g.oz + (float)(cz + 1) * H) - margin) - pz : pz - ((g.oz + (float)cz * H) + margin);
-        ex = fmaxf(ex, 0.0f), ey = fmaxf(ey, 0.0f), ez = fmaxf(ez, 0.0f);
-        ex *= ex, ey *= ey, ez *= ez;
-        const bool vx0 = cx >= 0 && cx < ncell, vx1 = nx >= 0 && nx < ncell;
-        const bool vy0 = cy >= 0 && cy < ncell, vy1 = ny >= 0 && ny < ncell;
-        const bool vz0 = cz >= 0 && cz < ncell, vz1 = nz >= 0 && nz < ncell;
-        const float bound0 = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-        // eight independent probes (dead cells predicated off), then their resolution
-        uint4 e[8];
-        uint32_t slot[8];
-        uint32_t live = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const bool i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-            const float d2c = (i ? ex : 0.0f) + (j ? ey : 0.0f) + (m ? ez : 0.0f);
-            const bool ok = (i ? vx1 : vx0) && (j ? vy1 : vy0) && (m ? vz1 : vz0) && d2c <= bound0;
-            e[k] = make_uint4(0u, 0u, 0u, 0u);
-            slot[k] = 0;
-            if (ok) {
-                const uint32_t x = (uint32_t)(i ? nx : cx), y = (uint32_t)(j ? ny : cy), z = (uint32_t)(m ? nz : cz);
-                const uint32_t klo = cell_key_lo(x, y, z), khi = cell_key_hi(z, l);
-                slot[k] = cell_hash(klo, khi) & g.mask;
-                e[k] = ld_entry(&g.table[slot[k]]);
-                live |= 1u << k;
-                st.probe(0);
-            }
+        co.scan(g, px, py, pz, S, nr, best_d2, best_j, st);
+        // descent through the dense cells of the block, one split per round
+        while (co.any(active && sp > 0)) {
+            if (active && sp > 0) expand_one<kStack>(g, f, px, py, pz, fminf(best_d2, r2_prune) * 1.0001f + 1e-12f, S, nr, sp, st);
+            co.scan(g, px, py, pz, S, nr, best_d2, best_j, st);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (!((live >> k) & 1u)) continue;
-            const bool i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-            const uint32_t x = (uint32_t)(i ? nx : cx), y = (uint32_t)(j ? ny : cy), z = (uint32_t)(m ? nz : cz);
-            uint32_t start, count, cmask;
-            if (!probe_finish(g, slot[k], e[k], cell_key_lo(x, y, z), cell_key_hi(z, l), start, count, cmask)) continue;
-            if (count <= (uint32_t)g.leaf_count || l == 0 || sp == kStack) S.range(nr++) = make_uint2(start, count);
-            else S.stack(sp++) = pack_cell(x, y, z, l, cmask);
+        if (active) {
+            const float H = g.h0 * (float)(1 << l);
+            const float cover = (l == 0) ? 0.998f * 0.5f * g.h0 : 0.999f * 0.5f * H; // every closer target has been examined
+            const float cover2 = cover * cover;
+            if (best_d2 <= cover2) active = false;       // the best found is the global nearest
+            else if (cover2 >= r2_prune) active = false; // whole search radius examined
+            else if (l == L - 1) active = false;         // (n_levels is chosen so that the line above fires first)
+            else ++l;
         }
-        scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
-        // descent through the dense cells of the block
-        while (sp > 0) {
-            const uint2 ce = S.stack(--sp);
-            const int lv = (int)((ce.y >> 4) & 0xfu);
-            const uint32_t cmask = (ce.y >> 8) & 0xffu;
-            const int x = (int)(ce.x & 0xfffu), y = (int)((ce.x >> 12) & 0xfffu), z = (int)((ce.x >> 24) | ((ce.y & 0xfu) << 8));
-            const float hc = 0.5f * g.h0 * (float)(1 << lv); // child size
-            // per-axis squared distances to the two child slabs
-            float ax[2], ay[2], az[2];
-            {
-                const float lox = g.ox + (float)(2 * x) * hc, mdx = g.ox + (float)(2 * x + 1) * hc, hix = g.ox + (float)(2 * x + 2) * hc;
-                const float loy = g.oy + (float)(2 * y) * hc, mdy = g.oy + (float)(2 * y + 1) * hc, hiy = g.oy + (float)(2 * y + 2) * hc;
-                const float loz = g.oz + (float)(2 * z) * hc, mdz = g.oz + (float)(2 * z + 1) * hc, hiz = g.oz + (float)(2 * z + 2) * hc;
-                ax[0] = slab_dist(lox, mdx, px, margin), ax[1] = slab_dist(mdx, hix, px, margin);
-                ay[0] = slab_dist(loy, mdy, py, margin), ay[1] = slab_dist(mdy, hiy, py, margin);
-                az[0] = slab_dist(loz, mdz, pz, margin), az[1] = slab_dist(mdz, hiz, pz, margin);
-                ax[0] *= ax[0], ax[1] *= ax[1], ay[0] *= ay[0], ay[1] *= ay[1], az[0] *= az[0], az[1] *= az[1];
-            }
-            const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-            // the cell itself may have fallen behind the bound since it was pushed
-            if (fminf(ax[0], ax[1]) + fminf(ay[0], ay[1]) + fminf(az[0], az[1]) > bound) continue;
-            st.expand();
-            if (nr + 8 > kRanges) scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
-            const int near_child = (ax[1] < ax[0] ? 1 : 0) | (ay[1] < ay[0] ? 2 : 0) | (az[1] < az[0] ? 4 : 0);
-            uint32_t pass = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ch = (7 - k) ^ near_child; // the nearest octant comes last: pushed last, popped first
-                const bool ok = ((cmask >> ch) & 1u) && (((ch & 1) ? ax[1] : ax[0]) + ((ch & 2) ? ay[1] : ay[0]) + ((ch & 4) ? az[1] : az[0]) <= bound);
-                e[k] = make_uint4(0u, 0u, 0u, 0u);
-                slot[k] = 0;
-                if (ok) {
-                    const uint32_t x2 = (uint32_t)(2 * x + (ch & 1)), y2 = (uint32_t)(2 * y + ((ch >> 1) & 1)),
-                                   z2 = (uint32_t)(2 * z + (ch >> 2));
-                    const uint32_t klo = cell_key_lo(x2, y2, z2), khi = cell_key_hi(z2, lv - 1);
-                    slot[k] = cell_hash(klo, khi) & g.mask;
-                    e[k] = ld_entry(&g.table[slot[k]]);
-                    pass |= 1u << k;
-                    st.probe(1);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (!((pass >> k) & 1u)) continue;
-                const int ch = (7 - k) ^ near_child;
-                const uint32_t x2 = (uint32_t)(2 * x + (ch & 1)), y2 = (uint32_t)(2 * y + ((ch >> 1) & 1)),
-                               z2 = (uint32_t)(2 * z + (ch >> 2));
-                uint32_t start, count, cm2;
-                if (!probe_finish(g, slot[k], e[k], cell_key_lo(x2, y2, z2), cell_key_hi(z2, lv - 1), start, count, cm2)) continue;
-                if (count <= (uint32_t)g.leaf_count || lv - 1 == 0 || sp == kStack) S.range(nr++) = make_uint2(start, count);
-                else S.stack(sp++) = pack_cell(x2, y2, z2, lv - 1, cm2);
-            }
-            // small cells found so far tighten the bound before the next dense cell is opened
-            scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
-        }
-        const float cover = (l == 0) ? 0.998f * 0.5f * g.h0 : 0.999f * 0.5f * H; // every closer target has been examined
-        const float cover2 = cover * cover;
-        if (best_d2 <= cover2) break;  // the best found is the global nearest
-        if (cover2 >= r2_prune) break; // whole search radius examined
-        if (l == L - 1) break;         // (n_levels is chosen so that the line above fires first)
     }
 }
 

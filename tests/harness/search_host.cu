@@ -138,15 +138,10 @@ int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_pru
             const float4 t = g.pos[best_j];
             best_d2 = flann_l2(px, py, pz, t.x, t.y, t.z);
         }
-        if (best_j < 0 || (reseed_d2 >= 0.0f && best_d2 > reseed_d2)) {
-            float d2 = INFINITY;
-            int j = -1;
-            quick_seed(g, px, py, pz, start_level, d2, j, C);
-            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
-        }
         HostScratch<8, 12> S;
         C.cur_evals = 0;
-        nn_search<8, 12>(g, px, py, pz, r2_prune, start_level, best_d2, best_j, S, C);
+        SoloCoop co;
+        nn_search<8, 12>(g, true, px, py, pz, r2_prune, start_level, (reseed_d2 >= 0.0f) ? reseed_d2 : INFINITY, best_d2, best_j, S, co, C);
         C.max_evals_query = std::max(C.max_evals_query, C.cur_evals);
         if (evals_per_query) evals_per_query[i] = (uint32_t)C.cur_evals;
         out_d2[i] = best_d2;
