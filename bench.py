@@ -132,21 +132,49 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_rate(pairs, budget_s, max_regs):
-    """The oracle (CPU restatement of the reference's algorithm, reference-shaped: kd-tree per class and
-    3 OpenMP sections per registration) on the host cores: cores//3 registrations in flight."""
+def host_cores():
+    """Cores this process may run on (cgroup / affinity aware — os.cpu_count() is the machine's, not ours)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def gpu_numa_cpus(device_index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None."""
+    try:
+        out = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                                      text=True).strip()
+        bus = out[-12:].lower()  # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus & set(os.sched_getaffinity(0)) or None
+    except Exception:
+        return None
+
+
+def cpu_reference_rate(pairs, budget_s, max_regs, all_cores=False):
+    """The oracle (CPU restatement of the reference's algorithm) on the host cores.
+    reference-shaped (default): kd-tree per class and 3 OpenMP sections per registration as cregistration.hpp:1268-1292,
+    cores//3 registrations in flight so that every core the process may use is busy;
+    all_cores: one registration at a time, `parallel for` over the queries on all cores (BASELINE.md section 3 ii)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle
 
     oracle.load()
-    cores = os.cpu_count() or 1
-    workers = max(1, cores // 3)
-    n = min(max_regs, max(workers, 1) * 4)
+    cores = host_cores()
+    workers = 1 if all_cores else max(1, cores // 3)
+    n = min(max_regs, max(workers, 1) * 4) if not all_cores else max_regs
     jobs = [pairs[i % len(pairs)] for i in range(n)]
 
     def one(p):
-        oracle.icp_run(p["tgt"], p["src"], p["params"], p["init_guess"], threads=0, want_trace=False)
+        oracle.icp_run(p["tgt"], p["src"], p["params"], p["init_guess"], threads=(cores if all_cores else 0), want_trace=False)
         return 1
 
     t0 = time.perf_counter()
@@ -157,7 +185,7 @@ def cpu_reference_rate(pairs, budget_s, max_regs):
             if time.perf_counter() - t0 > budget_s and done >= workers:
                 break
     dt = time.perf_counter() - t0
-    return done / dt, min(cores, workers * 3), done, dt
+    return done / dt, (cores if all_cores else min(cores, workers * 3)), done, dt
 
 
 def main():
@@ -189,25 +217,31 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        pairs = make_pairs([1000 + i for i in range(min(args.pairs, 8))], args.config)
+        pairs = make_pairs([1000 + i for i in range(args.pairs)], args.config)  # the GPU arm's pairs of rank 0
         per_step_budget = 8.0
         for _ in range(args.warmup):
             cpu_reference_rate(pairs, 1.0, 8)
         t0 = time.perf_counter()
-        regs = 0
-        cores = 1
-        for _ in range(args.steps):
-            rate, cores, done, dt = cpu_reference_rate(pairs, per_step_budget, 10 ** 9)
+        regs, cores, rates = 0, 1, []
+        for k in range(args.steps):
+            shift = (k * 8) % len(pairs)  # every step starts at a different pair: all of them are visited
+            rate, cores, done, dt = cpu_reference_rate(pairs[shift:] + pairs[:shift], per_step_budget, 10 ** 9)
             regs += done
+            rates.append(rate)
         total = time.perf_counter() - t0
         value = regs / total
+        ac_rate, ac_cores, ac_done, ac_dt = cpu_reference_rate(pairs, 6.0, 64, all_cores=True)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 accumulation",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{regs} registrations of the workload's pairs, reference-shaped "
-                                           f"(3 OpenMP sections each), {cores // 3} in flight"},
+                                 "sample": f"{regs} registrations over the workload's {len(pairs)} pairs, reference-shaped "
+                                           f"(3 OpenMP sections each), {max(1, cores // 3)} in flight on {host_cores()} usable cores",
+                                 "per_step": {"min": min(rates), "median": float(np.median(rates)), "max": max(rates)},
+                                 "all_cores_variant": {"value": ac_rate, "cores": ac_cores,
+                                                       "sample": f"{ac_done} registrations one at a time, parallel-for over "
+                                                                 f"the queries, in {ac_dt:.1f} s"}},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -218,6 +252,18 @@ def main():
     from mulls_b200.registration import Context
 
     torch.cuda.set_device(local_rank)
+    # several ranks share the host: keep each rank (and the library's pack workers / lane threads it spawns) on the
+    # cores of its GPU's NUMA node, so that the pinned staging and the repacking stay local to the PCIe root
+    affinity = "all usable cores"
+    if world > 1:
+        cpus = gpu_numa_cpus(local_rank)
+        if cpus:
+            share = sorted(cpus)
+            per_node = max(1, len([r for r in range(world) if gpu_numa_cpus(r) == cpus]))
+            k = [r for r in range(world) if gpu_numa_cpus(r) == cpus].index(local_rank)
+            share = share[k::per_node] if len(share) >= 4 * per_node else share
+            os.sched_setaffinity(0, share)
+            affinity = f"{len(share)} cores of the GPU's NUMA node"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -238,6 +284,7 @@ def main():
 
     lanes = max(1, min(args.lanes, args.pairs))
     ctx = Context(local_rank, args.pairs, max_src, max_tgt)
+    ctx.set_tunable("use_graph", 0)  # per-kernel CUDA events for the roofline: the host launch loop (the lanes run the graph)
     pipe = PipelinedContext(local_rank, lanes, (args.pairs + lanes - 1) // lanes, max_src, max_tgt)
 
     # ---- (A) device-resident, one stream: per-kernel attribution for the roofline ----------------
@@ -279,6 +326,28 @@ def main():
     barrier()
     wall_s = time.perf_counter() - t_wall
     lanes_s = ev0.elapsed_time(ev1) / 1e3
+
+    # ---- (B2) the same with convergence switched off: every pair runs all 20 iterations (BASELINE configs[1] "20 iters")
+    fixed20 = None
+    if args.config == "c2":
+        from mulls_b200 import abi as _abi
+
+        pairs20 = []
+        for p in pairs:
+            q = _abi.IcpParams.from_buffer_copy(p["params"])
+            q.converge_translation, q.converge_rotation_d = 0.0, 0.0
+            pairs20.append(dict(p, params=q))
+        pipe.upload(pairs20)
+        pipe.run_resident()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k20 = max(2, min(args.steps, 5))
+        f0.record()
+        r20, _ = pipe.run_resident_steps(k20)
+        f1.record()
+        barrier()
+        assert all(r["iters"] == 20 for r in r20), [r["iters"] for r in r20]
+        fixed20 = (k20, f0.elapsed_time(f1) / 1e3)
 
     # ---- (C) end to end through the C-ABI with host (pinned) buffers, same lanes ----------------------
     # The clouds cross PCIe either as the caller's 48-byte rows or repacked on the host cores to the 28 B/point wire
@@ -322,8 +391,8 @@ def main():
 
     # ---- reduce over ranks -------------------------------------------------------------------
     dev_s = dev_ms / 1e3
-    (dev_s, e2e_s, wall_s, lanes_s), (launches_all, _, _) = reduce_over_ranks(
-        dist, "cuda", [dev_s, e2e_s, wall_s, lanes_s], [float(launches), float(alg_bytes), float(search_ms)])
+    (dev_s, e2e_s, wall_s, lanes_s, f20_s), (launches_all, _, _) = reduce_over_ranks(
+        dist, "cuda", [dev_s, e2e_s, wall_s, lanes_s, fixed20[1] if fixed20 else 0.0], [float(launches), float(alg_bytes), float(search_ms)])
     launches = int(launches_all)
     total_regs = args.pairs * world * args.steps
     value = total_regs / lanes_s
@@ -372,6 +441,10 @@ def main():
             "timing": f"value: CUDA events around {args.steps} steps with {lanes} concurrent contexts; value_single_stream "
                       "and roofline: the library's CUDA events on its one stream",
             "mean_iterations": iters / max(args.pairs * args.steps, 1),
+            "fixed_20_iterations": ({"value": args.pairs * world * fixed20[0] / f20_s, "unit": UNIT, "steps": fixed20[0],
+                                     "note": "convergence test disabled: every pair runs max_iter_num = 20 iterations"}
+                                    if fixed20 else None),
+            "host_affinity": affinity,
             "max_pose_err_vs_gt_m": max(e[0] for e in errs),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -15,6 +15,7 @@
 #ifndef MULLS_B200_CREGISTRATION_SHIM_HPP
 #define MULLS_B200_CREGISTRATION_SHIM_HPP
 
+#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -26,17 +27,32 @@
 namespace lo {
 namespace b200 {
 
-// One context per host thread (mm_lls_icp is called from the app's main thread, SURVEY 8b "Threading").
-inline mulls_ctx *thread_context(size_t need_src, size_t need_tgt) {
-    static thread_local mulls_ctx *ctx = nullptr;
-    static thread_local size_t cap_src = 0, cap_tgt = 0;
-    if (!ctx || need_src > cap_src || need_tgt > cap_tgt) {
+// Contexts are kept per host thread (mm_lls_icp is called from the app's main thread, SURVEY 8b "Threading"), grown
+// when a call needs more room, and destroyed when the thread ends.
+struct ThreadContext {
+    mulls_ctx *ctx = nullptr;
+    size_t cap_pairs = 0, cap_src = 0, cap_tgt = 0;
+    ~ThreadContext() {
         if (ctx) mulls_destroy(ctx);
-        cap_src = need_src > cap_src ? need_src * 2 : cap_src;
-        cap_tgt = need_tgt > cap_tgt ? need_tgt * 2 : cap_tgt;
-        ctx = mulls_create(/*device*/ 0, /*max_pairs*/ 1, cap_src ? cap_src : 1, cap_tgt ? cap_tgt : 1);
     }
-    return ctx;
+    mulls_ctx *get(size_t pairs, size_t need_src, size_t need_tgt) {
+        if (!ctx || pairs > cap_pairs || need_src > cap_src || need_tgt > cap_tgt) {
+            if (ctx) mulls_destroy(ctx);
+            cap_pairs = pairs > cap_pairs ? pairs : cap_pairs;
+            cap_src = need_src > cap_src ? need_src * 2 : cap_src;
+            cap_tgt = need_tgt > cap_tgt ? need_tgt * 2 : cap_tgt;
+            ctx = mulls_create(/*device*/ 0, cap_pairs ? cap_pairs : 1, cap_src ? cap_src : 1, cap_tgt ? cap_tgt : 1);
+        }
+        return ctx;
+    }
+};
+inline mulls_ctx *thread_context(size_t need_src, size_t need_tgt) {
+    static thread_local ThreadContext tc;
+    return tc.get(1, need_src, need_tgt);
+}
+inline mulls_ctx *thread_batch_context(size_t pairs, size_t need_src, size_t need_tgt) {
+    static thread_local ThreadContext tc;
+    return tc.get(pairs, need_src, need_tgt);
 }
 
 template <typename PointT>
@@ -109,8 +125,16 @@ int mm_lls_icp(constraint_t &registration_cons, // cblock_1 (target point cloud)
     mulls_ctx *ctx = thread_context(ns, nt);
     mulls_icp_result out;
     if (!ctx || mulls_icp_run(ctx, tgt, src, &p, init, &out, nullptr) != MULLS_OK) {
+        // An infrastructure failure (no device, capacity, CUDA error) must look like a FAILED registration to the
+        // callers, which only test `< 0` and then read Trans1_2 (test/mulls_slam.cpp:650, :686): leave what the
+        // reference leaves when no iteration ran — the initial guess, an identity information matrix — with a
+        // sigma no acceptance test passes, and return a negative code of our own (-4: device path failed).
         LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
-        return 0; // process_code 0: "registration did not run"; the constraint is left untouched
+        registration_cons.Trans1_2 = initial_guess;
+        registration_cons.information_matrix.setIdentity();
+        registration_cons.sigma = FLT_MAX;
+        registration_cons.confidence = 0.0f;
+        return -4;
     }
     for (int r = 0; r < 4; ++r)
         for (int c = 0; c < 4; ++c) registration_cons.Trans1_2(r, c) = out.T[4 * r + c];     // :1405
@@ -169,11 +193,10 @@ bool mm_lls_icp_4dof_global(constraint_t &registration_con, float heading_step_d
         for (int c = 0; c < MULLS_NUM_CLASSES; ++c) tgt[i * MULLS_NUM_CLASSES + c] = tgt1[c], src[i * MULLS_NUM_CLASSES + c] = src1[c];
     size_t ns = 0, nt = 0;
     for (int c = 0; c < MULLS_NUM_CLASSES; ++c) ns += src1[c].n, nt += tgt1[c].n;
-    mulls_ctx *ctx = mulls_create(0, n, ns ? ns : 1, nt ? nt : 1);
+    mulls_ctx *ctx = thread_batch_context(n, ns, nt); // kept per thread: a heading search per frame re-uses it
     std::vector<mulls_icp_result> out(n);
     const bool ran = ctx && mulls_icp_run_batch(ctx, n, tgt.data(), src.data(), params.data(), guesses.data(), out.data(), nullptr) == MULLS_OK;
     if (!ran) LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx);
-    if (ctx) mulls_destroy(ctx);
     if (!ran) return false;
     float current_best_score = 0;
     bool successful_reg = false;

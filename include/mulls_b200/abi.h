@@ -200,6 +200,19 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
                           mulls_allreduce_fn allreduce, void *user, mulls_icp_result *out,
                           mulls_icp_trace *trace);
 
+/* Stand-in for block1->tree_* (cregistration.hpp:1213-1232): mm_lls_icp leaves a kd-tree per target class in
+ * registration_cons.block1, and MapManager::map_scan_feature_pts_distance_removal (src/map_manager.cpp:221-258, called
+ * from :197-205) runs nearestKSearch(point, 1, ...) on them. Here the last mulls_icp_run / mulls_icp_run_batch (pair 0)
+ * on `ctx` leaves its sorted target slices and their grid in HBM, and this call answers the same query on them:
+ * for every query point the exact nearest target of class `cls` (FLANN float distance, ties to the lower index)
+ * within the radius the registration searched (2.5 * dis_thre_unit, which covers dynamic_dist_thre_max of
+ * map_manager.h:28). idx[i] = index of that target in the caller's ORIGINAL class cloud (the reference's index is
+ * into its bbox-filtered private clone), d2[i] = squared distance; nothing within the radius: idx -1, d2 +inf.
+ * Targets removed by the intersection filter are not candidates (as in the reference: the trees are built after
+ * the filter, :1186-1232). Returns MULLS_E_ARG if no registration has run on the context since its last upload. */
+int mulls_nn_query(mulls_ctx *ctx, int cls, const float *xyz /* [n][3], host */, size_t n, int32_t *idx /* [n] */,
+                   float *d2 /* [n] */);
+
 /* PCA neighbourhood features (pca.hpp:294-354): for every `stride`-th point of `cloud` take the
  * at most `k` nearest neighbours within `radius` (the point itself included), and return
  * eigenvalues (descending), principal direction, normal direction, and the neighbour count.

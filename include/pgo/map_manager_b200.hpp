@@ -13,8 +13,11 @@
 #ifndef MULLS_B200_MAP_MANAGER_SHIM_HPP
 #define MULLS_B200_MAP_MANAGER_SHIM_HPP
 
+#include <cfloat>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "common/cregistration_b200.hpp"
 #include "mulls_b200/abi.h"
@@ -87,6 +90,8 @@ class MapManagerB200 {
         m.local_bound.max_x = info.local_bound[3], m.local_bound.max_y = info.local_bound[4], m.local_bound.max_z = info.local_bound[5];
         m.bound.min_x = info.bound[0], m.bound.min_y = info.bound[1], m.bound.min_z = info.bound[2];
         m.bound.max_x = info.bound[3], m.bound.max_y = info.bound[4], m.bound.max_z = info.bound[5];
+        for (int c = 0; c < MULLS_NUM_CLASSES; ++c) n_[c] = info.n[c];
+        synced_ = true;
         return true;
     }
 
@@ -101,7 +106,7 @@ class MapManagerB200 {
                    bool apply_motion_undistortion_while_registration = false, bool normal_shooting_on = false,
                    float normal_bearing = 45.0, bool use_more_points = false, bool keep_less_source_points = false,
                    float sigma_thre = 0.5, float min_neccessary_corr_ratio = 0.03, float max_bearable_rotation_d = 45.0) {
-        if (!map_) return 0;
+        if (!map_) return -4;
         typedef Point_T P;
         cloudblock_t &b2 = *registration_cons.block2;
         const bool down = !use_more_points || apply_motion_undistortion_while_registration;
@@ -138,8 +143,12 @@ class MapManagerB200 {
             for (int c = 0; c < 4; ++c) init[4 * r + c] = initial_guess(r, c);
         mulls_icp_result out;
         if (mulls_icp_run_to_map(ctx_, map_, src, &p, init, &out, nullptr) != MULLS_OK) {
-            LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx_);
-            return 0;
+            LOG(ERROR) << "mulls_b200: " << mulls_last_error(ctx_); // same failure convention as b200::mm_lls_icp
+            registration_cons.Trans1_2 = initial_guess;
+            registration_cons.information_matrix.setIdentity();
+            registration_cons.sigma = FLT_MAX;
+            registration_cons.confidence = 0.0f;
+            return -4;
         }
         for (int r = 0; r < 4; ++r)
             for (int c = 0; c < 4; ++c) registration_cons.Trans1_2(r, c) = out.T[4 * r + c];
@@ -150,11 +159,44 @@ class MapManagerB200 {
         return out.code;
     }
 
+    // does `block` still hold exactly the clouds this object downloaded after its last update? (a caller that edits the
+    // map's host clouds itself falls back to the host path of mm_lls_icp)
+    bool mirrors(const cloudblock_t &block) const {
+        if (!map_ || !synced_) return false;
+        const cloudblock_t::pcTPtr *cls[MULLS_NUM_CLASSES] = {&block.pc_ground, &block.pc_pillar, &block.pc_facade,
+                                                              &block.pc_beam,   &block.pc_roof,   &block.pc_vertex};
+        for (int c = 0; c < MULLS_NUM_CLASSES; ++c)
+            if ((*cls[c])->points.size() != n_[c]) return false;
+        return true;
+    }
+
   private:
     mulls_ctx *ctx_ = nullptr;
     mulls_map *map_ = nullptr;
     uint32_t seed_ = 0;
+    bool synced_ = false;
+    size_t n_[MULLS_NUM_CLASSES] = {0, 0, 0, 0, 0, 0};
 };
+
+// The cloudblocks whose clouds live in HBM (lo::MapManager::update_local_map of dropin/map_manager.h registers its
+// local_map argument here; lo::CRegistration::mm_lls_icp of dropin/cregistration.hpp looks registration_cons.block1 up).
+// One entry per cloudblock address and host thread.
+inline MapManagerB200 *&resident_slot(const cloudblock_t *block) {
+    static thread_local std::vector<std::pair<const cloudblock_t *, MapManagerB200 *>> table;
+    for (auto &e : table)
+        if (e.first == block) return e.second;
+    table.push_back(std::make_pair(block, (MapManagerB200 *)nullptr));
+    return table.back().second;
+}
+inline MapManagerB200 &resident_map_for(const cloudblock_t *block) {
+    MapManagerB200 *&slot = resident_slot(block);
+    if (!slot) slot = new MapManagerB200(); // lives as long as the thread's map (the SLAM loop's only local map)
+    return *slot;
+}
+inline MapManagerB200 *resident_map_if_current(const cloudblock_t *block) {
+    MapManagerB200 *m = resident_slot(block);
+    return (m && m->mirrors(*block)) ? m : nullptr;
+}
 
 } // namespace b200
 } // namespace lo

@@ -258,6 +258,7 @@ EXPORTED_SYMBOLS = (
     "mulls_classify_default_params",
     "mulls_classify_nground",
     "mulls_set_tunable",
+    "mulls_nn_query",
     "mulls_pack_rows",
     "mulls_ground_default_params",
     "mulls_fast_ground_filter",
@@ -322,6 +323,8 @@ def load_library() -> C.CDLL:
     lib.mulls_extract_semantic_pts.argtypes = [vp, CloudView, C.POINTER(ExtractParams), C.POINTER(ExtractOut)]
     lib.mulls_pack_rows.restype = C.c_int
     lib.mulls_pack_rows.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+    lib.mulls_nn_query.restype = C.c_int
+    lib.mulls_nn_query.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     lib.mulls_set_tunable.restype = C.c_int
     lib.mulls_set_tunable.argtypes = [vp, C.c_char_p, C.c_int]
     lib.mulls_map_default_params.restype = None

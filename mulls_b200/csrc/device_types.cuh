@@ -109,6 +109,18 @@ struct PairState {
 
 struct FinishSync;
 
+// Per-run control block in device memory: what a kernel that was recorded into a CUDA graph (fixed arguments, grids
+// sized for the context's capacity) needs to know about THIS run, and the iteration counter of the device-side loop.
+struct LoopCtl {
+    int it;          // iteration index of the graph's WHILE loop (the host loop passes its own)
+    int n_it_chunks; // iteration chunks of this upload (blocks beyond it return at once)
+    int n_pairs;
+    int trace_on;    // write the per-iteration trace
+    int max_iter;    // max over the pairs of max_iter_num
+    unsigned solved; // pairs whose k_solve block has finished this iteration
+    int _pad[2];
+};
+
 // All device pointers of a context, passed by value to the kernels.
 struct DeviceArrays {
     const float4 *in_aos;   // input clouds, 3 float4 per point (pcl::PointXYZINormal)
@@ -140,6 +152,7 @@ struct DeviceArrays {
     double *xch_f64;        // exchange buffer of the sharded mode (per-class sums), 6*kTerms + 2 doubles
     unsigned *pair_sync;    // k_finish: per pair [resolved chunks, accumulated chunks] of the current iteration
     struct FinishSync *fsync; // k_finish: ticket / done counters
+    LoopCtl *ctl;
     int *running;           // pairs still iterating (device counter)
     volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop
     volatile int *h_running_iter; // [it]: pairs still iterating at the END of iteration it (sharded runs: rank-deterministic stop)

@@ -17,6 +17,14 @@
 
 namespace mulls {
 
+// kernels recorded into the iteration graph are launched over the context's CAPACITY and take the double-buffer index
+// from the device-side loop counter (buf < 0); the host loop passes exact grids and buf = it & 1
+__device__ __forceinline__ bool chunk_in_run(const DeviceArrays &A) { return blockIdx.x < (unsigned)A.ctl->n_it_chunks; }
+__device__ __forceinline__ int loop_buf(const DeviceArrays &A, int buf) { return buf >= 0 ? buf : (A.ctl->it & 1); }
+__device__ __forceinline__ mulls_icp_trace *trace_of(const DeviceArrays &A, uint32_t pair) {
+    return (A.trace && A.ctl->trace_on) ? &A.trace[pair] : nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------
 // exact 1-NN within radius on the multi-level hashed grid of one target class: search_core.cuh
 // (__host__ __device__; the CPU suite runs the same functions against a brute-force scan)
@@ -35,6 +43,8 @@ constexpr int kSearchStack = 8;   // dense cells waiting to be split (overflow: 
 //             owner it is working for in registers (starting from the owner's current key, so that most candidates
 //             fail one compare) and publishes an improvement when it moves on to another owner: compare-and-swap
 //             loop; equal distances are settled by the ORIGINAL index, exactly like consider()
+constexpr int kSoloScanLanes = 3; // at most this many lanes with queued ranges: they scan on their own
+
 struct WarpShared {
     uint2 ent[kSearchRanges][32]; // [r][lane] = {start, count}
     uint32_t obase[33];
@@ -76,7 +86,12 @@ struct WarpCoop {
     __device__ __forceinline__ void scan(const GridView &g, float px, float py, float pz, Scratch &S, int &nr, float &best_d2,
                                          int &best_j, Stats &st) {
         const unsigned full = 0xffffffffu;
-        if (!__any_sync(full, nr > 0)) return;
+        const unsigned queued = __ballot_sync(full, nr > 0); // lanes that queued anything (the owners to walk through)
+        if (queued == 0u) return;
+        if (__popc(queued) <= kSoloScanLanes) { // a handful of stragglers: sharing their work costs more than it saves
+            scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
+            return;
+        }
         const int lane = threadIdx.x & 31;
         uint32_t cnt = 0;
         for (int r = 0; r < nr; ++r) cnt += S.range(r).y;
@@ -92,7 +107,6 @@ struct WarpCoop {
         w->qp[lane] = make_float4(px, py, pz, 0.0f);
         w->best[lane] = ((unsigned long long)__float_as_uint(best_d2) << 32) | (unsigned long long)(uint32_t)best_j;
         __syncwarp();
-        const unsigned queued = __ballot_sync(full, nr > 0); // lanes that queued anything (the owners to walk through)
         const uint32_t C = (T + 31u) >> 5;
         const uint32_t s0 = (uint32_t)lane * C;
         if (s0 < T) {
@@ -303,7 +317,10 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
 }
 
 __global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                          float reseed_cells) {
+                                                          float reseed_cells, int dfs_until) {
+    if (!chunk_in_run(A)) return;
+    if (buf < 0 && A.ctl->it < dfs_until) return; // (iteration graph) this iteration is k_search_dfs's
+    buf = loop_buf(A, buf);
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
@@ -360,11 +377,341 @@ __global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int b
     A.nn_d2[gi] = best_d2;
 }
 
+// ---- k_search_dfs: the same search, one independent depth-first walk per thread (nn_search_dfs): no cooperation,
+//      no synchronisation, the tightest pruning; the warp-cooperative k_search keeps more lanes busy per instruction.
+//      Which one serves an iteration is a tunable (see DESIGN.md for the measurements behind the default).
+constexpr int kDfsRanges = 8, kDfsStack = 16;
+struct DfsScratch {
+    uint2 *base; // &s_scratch[0][threadIdx.x]
+    __device__ __forceinline__ uint2 &range(int i) { return base[i * kIterBlock]; }
+    __device__ __forceinline__ uint2 &stack(int i) { return base[(kDfsRanges + i) * kIterBlock]; }
+};
+
+__global__ void __launch_bounds__(kIterBlock, 9) k_search_dfs(DeviceArrays A, int buf, int start_level0, int leaf_count,
+                                                             float reseed_cells, int defer_from_iter, int dfs_until) {
+    if (!chunk_in_run(A)) return;
+    if (buf < 0 && A.ctl->it >= dfs_until) return; // (iteration graph) this iteration is k_search's
+    buf = loop_buf(A, buf);
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    const PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning || A.hash_used[1]) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
+    if ((int)cd.first >= ns) return; // block-uniform
+    if (shoots(pc, c)) return;       // block-uniform: k_search_shoot's work
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ns;
+    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
+    float4 p, n;
+    load_and_advance(A, ps, buf, gi, valid, p, n);
+    if (!valid) return;
+    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) {
+        A.nn_idx[gi] = -1;
+        A.nn_d2[gi] = INFINITY;
+        return;
+    }
+    const GridView g = grid_of(A, pc, ps, c, leaf_count);
+    const float max_distance_f = 2.5f * ps.thre;
+    const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
+    const float r2_prune = (float)max_dist_sqr * 1.0001f;
+    __shared__ uint2 s_scratch[kDfsRanges + kDfsStack][kIterBlock];
+    DfsScratch S{&s_scratch[0][threadIdx.x]};
+    NoStats st;
+    int best_j = -1;
+    float best_d2 = INFINITY;
+    {
+        const int pj = A.src_prevj[buf][gi];
+        if (pj >= 0) {
+            const float4 q = __ldg(&g.pos[pj]);
+            best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
+            best_j = pj;
+        }
+        const float rs = reseed_cells * g.h0;
+        if (best_j < 0 || best_d2 > rs * rs) {
+            uint2 leaf;
+            if (quick_locate(g, p.x, p.y, p.z, start_level0, leaf, st)) {
+                int nr = 0;
+                S.range(nr++) = leaf;
+                scan_ranges(g, p.x, p.y, p.z, S, nr, best_d2, best_j, st);
+            }
+        }
+    }
+    nn_search_dfs<kDfsRanges, kDfsStack>(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, S, st);
+    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
+    if (best_j >= 0) atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
+    A.nn_idx[gi] = best_j;
+    A.nn_d2[gi] = best_d2;
+}
+
+// ---- k_search_walk: round 1's per-thread walk (depth-first stack of (cell, box distance) in local memory, small
+//      cells examined where they are met or queued per block), on the coordinate keys of grid_key.cuh and with
+//      level-0 blocks. Kept selectable: the yardstick the other two forms are measured against on the same box.
+constexpr int kWalkStack = 48; // DFS entries: at most 7 stay behind per descended level
+constexpr int kWalkQueue = 8;  // leaves of one block whose scan is deferred to the end of its traversal
+
+__device__ __forceinline__ void walk_scan_leaf(const GridView &g, float px, float py, float pz, uint32_t start, uint32_t count,
+                                               float &best_d2, int &best_j) {
+    for (uint32_t jj = start; jj < start + count; ++jj) {
+        const float4 q = __ldg(&g.pos[jj]);
+        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
+        if (d2 < best_d2) {
+            best_d2 = d2;
+            best_j = (int)jj;
+        } else if (d2 == best_d2 && best_j >= 0 && (int)jj != best_j) {
+            const int oj = __float_as_int(__ldg(&g.nrm[jj]).w);
+            const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
+            if (oj < ob) best_j = (int)jj;
+        }
+    }
+}
+
+// walk greedily from p's own cell (first level, from `l` upwards, at which it exists) down through the nearest
+// existing child to a leaf and take its best point as the seed
+__device__ __forceinline__ void walk_greedy_seed(const GridView &g, float px, float py, float pz, int l, float &best_d2, int &best_j) {
+    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
+    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
+    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
+    const int L = g.n_levels;
+    l = min(max(l, 1), L - 1);
+    for (int lr = l; lr < L && best_j < 0; ++lr) {
+        const int ncell = (1 << kCoordBits) >> lr;
+        int cx = c0x >> lr, cy = c0y >> lr, cz = c0z >> lr;
+        if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell)) break;
+        for (int lv = lr;; --lv) {
+            uint32_t start, count, cmask;
+            if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) break; // only possible at lv == lr
+            if (count <= (uint32_t)g.leaf_count || lv == 0) {
+                for (uint32_t jj = start; jj < start + count; ++jj) {
+                    const float4 q = __ldg(&g.pos[jj]);
+                    const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
+                    if (d2 < best_d2) best_d2 = d2, best_j = (int)jj;
+                }
+                break;
+            }
+            const float hl = g.h0 * (float)(1 << lv);
+            const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
+            const int oy = (py >= g.oy + ((float)cy + 0.5f) * hl) ? 1 : 0;
+            const int oz = (pz >= g.oz + ((float)cz + 0.5f) * hl) ? 1 : 0;
+            int ch = ox | (oy << 1) | (oz << 2);
+            if (!((cmask >> ch) & 1u)) ch = __ffs((int)cmask) - 1; // any existing child still yields a valid seed
+            if (ch < 0) break;
+            cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
+        }
+    }
+}
+
+__device__ __forceinline__ float walk_axis_dist(float o, float H, int x, float p, float margin) {
+    const float lo = o + (float)x * H - margin, hi = o + (float)(x + 1) * H + margin;
+    return fmaxf(0.0f, fmaxf(lo - p, p - hi));
+}
+
+// stack storage of the walk: thread-local arrays (local memory, L1-cached) or shared memory interleaved by thread
+struct WalkStackLocal {
+    uint32_t cell[kWalkStack], meta[kWalkStack];
+    float d2[kWalkStack];
+    __device__ __forceinline__ void put(int i, uint32_t c, uint32_t m, float d) { cell[i] = c, meta[i] = m, d2[i] = d; }
+    __device__ __forceinline__ float dist(int i) const { return d2[i]; }
+    __device__ __forceinline__ void get(int i, uint32_t &c, uint32_t &m) const { c = cell[i], m = meta[i]; }
+};
+constexpr int kWalkSmemStack = 16;
+struct WalkStackSmem { // uint4-free: three word arrays, [entry][thread]
+    uint32_t *base;    // &s_walk[0][threadIdx.x]; entry i: words (3*i .. 3*i+2) * kIterBlock
+    __device__ __forceinline__ void put(int i, uint32_t c, uint32_t m, float d) {
+        base[(3 * i) * kIterBlock] = c, base[(3 * i + 1) * kIterBlock] = m, base[(3 * i + 2) * kIterBlock] = __float_as_uint(d);
+    }
+    __device__ __forceinline__ float dist(int i) const { return __uint_as_float(base[(3 * i + 2) * kIterBlock]); }
+    __device__ __forceinline__ void get(int i, uint32_t &c, uint32_t &m) const { c = base[(3 * i) * kIterBlock], m = base[(3 * i + 1) * kIterBlock]; }
+};
+
+template <class Stack, int kDepth>
+__device__ __forceinline__ void nn_search_walk(const GridView &g, float px, float py, float pz, float r2_prune, int start_level,
+                                               bool defer_scan, float &best_d2, int &best_j, Stack &stk) {
+    const float fx = (px - g.ox) * g.inv_h0, fy = (py - g.oy) * g.inv_h0, fz = (pz - g.oz) * g.inv_h0;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int c0x = (int)flx, c0y = (int)fly, c0z = (int)flz;
+    const int L = g.n_levels;
+    const float margin = 1e-3f * g.h0;
+    // stack entry: cell = x | y << 12 | (z & 0xff) << 24, meta = z >> 8 | level << 4, and the cell's box distance
+    uint32_t q_start[kWalkQueue], q_count[kWalkQueue];
+    int nq = 0;
+    int l = min(max(start_level, 1), L - 1);
+    if (best_j >= 0) { // seeded: the smallest level whose coverage reaches the seed (level 0: 0.998 * h0 / 2)
+        const float need = 1.001f * sqrtf(best_d2);
+        const float t = need / (0.999f * 0.5f * g.h0);
+        if (t <= 1.0f) l = (need <= 0.998f * 0.5f * g.h0) ? 0 : 1;
+        else l = ilogbf(t) + 1;
+        l = min(l, L - 1);
+    }
+    for (;; ++l) {
+        const float H = g.h0 * (float)(1 << l);
+        const int ncell = (1 << kCoordBits) >> l;
+        int xs[2], ys[2], zs[2];
+        xs[0] = c0x >> l, ys[0] = c0y >> l, zs[0] = c0z >> l;
+        if (l == 0) {
+            xs[1] = xs[0] + (((fx - flx) >= 0.5f) ? 1 : -1);
+            ys[1] = ys[0] + (((fy - fly) >= 0.5f) ? 1 : -1);
+            zs[1] = zs[0] + (((fz - flz) >= 0.5f) ? 1 : -1);
+        } else {
+            xs[1] = xs[0] + (((c0x >> (l - 1)) & 1) ? 1 : -1);
+            ys[1] = ys[0] + (((c0y >> (l - 1)) & 1) ? 1 : -1);
+            zs[1] = zs[0] + (((c0z >> (l - 1)) & 1) ? 1 : -1);
+        }
+        float ex[2], ey[2], ez[2];
+        bool vx[2], vy[2], vz[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            vx[i] = xs[i] >= 0 && xs[i] < ncell;
+            vy[i] = ys[i] >= 0 && ys[i] < ncell;
+            vz[i] = zs[i] >= 0 && zs[i] < ncell;
+            ex[i] = walk_axis_dist(g.ox, H, xs[i], px, margin);
+            ey[i] = walk_axis_dist(g.oy, H, ys[i], py, margin);
+            ez[i] = walk_axis_dist(g.oz, H, zs[i], pz, margin);
+            ex[i] *= ex[i], ey[i] *= ey[i], ez[i] *= ez[i];
+        }
+        uint32_t live = 0;
+        {
+            const float bound0 = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
+                if (vx[i] && vy[j] && vz[m] && ex[i] + ey[j] + ez[m] <= bound0) live |= 1u << k;
+            }
+        }
+#pragma unroll 1
+        while (live) { // lowest bit first: k = 0 is p's own cell
+            const int k = __ffs(live) - 1;
+            live &= live - 1;
+            const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
+            int sp = 0;
+            stk.put(0, cell_key_lo((uint32_t)xs[i], (uint32_t)ys[j], (uint32_t)zs[m]), ((uint32_t)zs[m] >> 8) | ((uint32_t)l << 4),
+                    ex[i] + ey[j] + ez[m]);
+            sp = 1;
+            while (sp > 0) {
+                --sp;
+                // a cell farther than the best so far (or than the radius) cannot change the result
+                if (stk.dist(sp) > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                uint32_t cell, meta;
+                stk.get(sp, cell, meta);
+                const int lv = (int)((meta >> 4) & 0xfu);
+                const int cx = (int)(cell & 0xfffu), cy = (int)((cell >> 12) & 0xfffu), cz = (int)((cell >> 24) | ((meta & 0xfu) << 8));
+                uint32_t start, count, cmask;
+                if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) continue;
+                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kDepth) {
+                    if (defer_scan && nq < kWalkQueue) { // scanned together with the block's other leaves
+                        q_start[nq] = start;
+                        q_count[nq] = count;
+                        ++nq;
+                    } else {
+                        walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
+                    }
+                } else {
+                    const float hc = 0.5f * g.h0 * (float)(1 << lv);
+                    float ax[2], ay[2], az[2];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        ax[b] = walk_axis_dist(g.ox, hc, 2 * cx + b, px, margin);
+                        ay[b] = walk_axis_dist(g.oy, hc, 2 * cy + b, py, margin);
+                        az[b] = walk_axis_dist(g.oz, hc, 2 * cz + b, pz, margin);
+                        ax[b] *= ax[b], ay[b] *= ay[b], az[b] *= az[b];
+                    }
+                    const int near_child = (ax[1] < ax[0] ? 1 : 0) | (ay[1] < ay[0] ? 2 : 0) | (az[1] < az[0] ? 4 : 0);
+                    const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+                    uint32_t pass = 0;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        if (ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2] <= bound) pass |= 1u << ch;
+                    pass &= cmask;
+                    if (near_child & 1) pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
+                    if (near_child & 2) pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
+                    if (near_child & 4) pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
+                    while (pass) {
+                        const int c = 31 - __clz((int)pass);
+                        pass ^= 1u << c;
+                        const int ch = c ^ near_child;
+                        const uint32_t x2 = (uint32_t)(2 * cx + (ch & 1)), y2 = (uint32_t)(2 * cy + ((ch >> 1) & 1)), z2 = (uint32_t)(2 * cz + (ch >> 2));
+                        stk.put(sp, cell_key_lo(x2, y2, z2), (z2 >> 8) | ((uint32_t)(lv - 1) << 4), ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2]);
+                        ++sp;
+                    }
+                }
+            }
+        }
+        for (int qi = 0; qi < nq; ++qi) walk_scan_leaf(g, px, py, pz, q_start[qi], q_count[qi], best_d2, best_j);
+        nq = 0;
+        const float cover = (l == 0) ? 0.998f * 0.5f * g.h0 : 0.999f * 0.5f * H;
+        const float cover2 = cover * cover;
+        if (best_d2 <= cover2) break;
+        if (cover2 >= r2_prune) break;
+        if (l == L - 1) break;
+    }
+}
+
+template <int kMinBlocks, bool kSmem>
+__global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search_walk(DeviceArrays A, int buf, int start_level0, int leaf_count,
+                                                                       int defer_from_iter, float reseed_cells) {
+    if (!chunk_in_run(A)) return;
+    buf = loop_buf(A, buf);
+    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+    const PairConst &pc = A.pc[cd.pair];
+    const PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning || A.hash_used[1]) return;
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
+    if ((int)cd.first >= ns) return;
+    if (shoots(pc, c)) return;
+    const uint32_t local = cd.first + threadIdx.x;
+    const bool valid = (int)local < ns;
+    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
+    float4 p, n;
+    load_and_advance(A, ps, buf, gi, valid, p, n);
+    if (!valid) return;
+    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) {
+        A.nn_idx[gi] = -1;
+        A.nn_d2[gi] = INFINITY;
+        return;
+    }
+    const GridView g = grid_of(A, pc, ps, c, leaf_count);
+    const float max_distance_f = 2.5f * ps.thre;
+    const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
+    const float r2_prune = (float)max_dist_sqr * 1.0001f;
+    int best_j = -1;
+    float best_d2 = INFINITY;
+    const int pj = A.src_prevj[buf][gi];
+    if (pj >= 0) {
+        const float4 q = __ldg(&g.pos[pj]);
+        best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
+        best_j = pj;
+    }
+    {
+        const float rs = reseed_cells * g.h0; // a match that the last increment left far away is challenged by a fresh seed
+        if (best_j < 0 || best_d2 > rs * rs) {
+            float d2 = INFINITY;
+            int j = -1;
+            walk_greedy_seed(g, p.x, p.y, p.z, start_level0, d2, j);
+            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
+        }
+    }
+    if (kSmem) {
+        __shared__ uint32_t s_walk[3 * kWalkSmemStack][kIterBlock];
+        WalkStackSmem stk{&s_walk[0][threadIdx.x]};
+        nn_search_walk<WalkStackSmem, kWalkSmemStack>(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, stk);
+    } else {
+        WalkStackLocal stk;
+        nn_search_walk<WalkStackLocal, kWalkStack>(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, stk);
+    }
+    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
+    if (best_j >= 0) atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
+    A.nn_idx[gi] = best_j;
+    A.nn_d2[gi] = best_d2;
+}
+
 // :1732-1737 normal shooting [PCL CorrespondenceEstimationNormalShooting, k = 10]: among the 10 nearest targets
 // the one with the smallest squared distance to the line through the source point along its normal; dropped
 // if that value exceeds max_distance (NOT squared); correspondence distance = its squared NN distance.
 // Launched only when a pair of the batch asked for normal shooting.
 __global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int buf, int start_level0, int leaf_count) {
+    if (!chunk_in_run(A)) return;
+    buf = loop_buf(A, buf);
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
@@ -474,7 +821,9 @@ __device__ __forceinline__ void resolve_body(DeviceArrays &A, int buf, uint32_t 
         if (p) atomicAdd(&ps.n_corr[c], p);
     }
 }
-__global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) { resolve_body<false>(A, buf, blockIdx.x); }
+__global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) {
+    if (chunk_in_run(A)) resolve_body<false>(A, loop_buf(A, buf), blockIdx.x);
+}
 
 // ------------------------------------------------------------------------------------------------
 // per-correspondence normal-equation terms. Layout of the kTerms doubles of a partial:
@@ -665,7 +1014,7 @@ __device__ __noinline__ void solve_and_advance(DeviceArrays &A, uint32_t pair, c
             if (pc.used[c]) pts += (uint64_t)ps.n_tgt[c];
         ps.alg_bytes += 28ull * pts; // sources added by the caller of this function (pre-compaction counts)
     }
-    mulls_icp_trace *tr = A.trace ? &A.trace[pair] : nullptr;
+    mulls_icp_trace *tr = trace_of(A, pair);
     if (tr && i < MULLS_MAX_TRACE_ITERS) {
         tr->n_iter = i + 1;
         for (int c = 0; c < kNumClasses; ++c) tr->n_corr[i][c] = ps.n_corr[c];
@@ -901,7 +1250,9 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
         A.partials[(size_t)chunk * kTerms + threadIdx.x] = v;
     }
 }
-__global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) { accumulate_body<false>(A, buf, blockIdx.x); }
+__global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) {
+    if (chunk_in_run(A)) accumulate_body<false>(A, loop_buf(A, buf), blockIdx.x);
+}
 
 // ---- solve: one block per pair, after every k_accumulate block of the pair. Sums the per-chunk partials of every
 //      class in chunk order (fixed order => bit-reproducible), then one thread solves and advances the pair state.
@@ -957,7 +1308,7 @@ __device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pa
             }
             return;
         }
-        mulls_icp_trace *tr = A.trace ? &A.trace[pair] : nullptr;
+        mulls_icp_trace *tr = trace_of(A, pair);
         for (int cc = 0; cc < kNumClasses; ++cc) {
             ps.n_src[cc] = s_newn[cc]; // classes that skipped determine_corres keep everything (k_resolve)
             ps.n_src_g[cc] = s_newn[cc];
@@ -969,7 +1320,26 @@ __device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pa
     }
 }
 constexpr int kSolveThreads = kNumClasses * 32; // one warp per feature class
-__global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf) { solve_body<false>(A, buf, blockIdx.x); }
+// loop_handle != 0: the launch is the last kernel of the iteration graph's WHILE body — the block that finishes last
+// advances the loop counter and tells the graph whether another iteration is needed (pairs still running)
+__global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf, unsigned long long loop_handle) {
+    LoopCtl &ctl = *A.ctl;
+    if (blockIdx.x >= (unsigned)ctl.n_pairs) return;
+    solve_body<false>(A, loop_buf(A, buf), blockIdx.x);
+    if (loop_handle == 0ull) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl.solved, 1u) == (unsigned)ctl.n_pairs - 1u) {
+            ctl.solved = 0;
+            const int it = ctl.it + 1;
+            ctl.it = it;
+            __threadfence();
+            const bool again = *(volatile int *)A.running > 0 && it < ctl.max_iter;
+            cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, again ? 1u : 0u);
+        }
+    }
+}
 
 // ---- k_finish: everything of one ICP iteration after the search, in ONE launch (2 x chunks blocks). Blocks take
 //      tickets: the first `n_chunks` tickets resolve a chunk (duplicate check, rejectors, counts), the next `n_chunks`
@@ -1104,7 +1474,7 @@ __global__ void k_shard_solve(DeviceArrays A, int buf, int it_flag) {
         return;
     }
     __shared__ double s_scratch[160];
-    mulls_icp_trace *tr = A.trace ? &A.trace[0] : nullptr;
+    mulls_icp_trace *tr = trace_of(A, 0);
     for (int cc = 0; cc < kNumClasses; ++cc) {
         ps.n_src_g[cc] = ps.n_src_g_next[cc];
         if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src_g[cc];
@@ -1150,6 +1520,7 @@ __global__ void k_shard_post(DeviceArrays A, int phase) {
 // cregistration.hpp:2518-2544: VTPV and observation count over the correspondences of the converged
 // iteration with its estimate x; sigma^2, code 1 / -3, information matrix (:1386).
 __global__ void __launch_bounds__(kIterBlock) k_posterior(DeviceArrays A) {
+    if (!chunk_in_run(A)) return;
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     PairState &ps = A.ps[cd.pair];
@@ -1242,6 +1613,7 @@ __global__ void __launch_bounds__(kIterBlock) k_posterior(DeviceArrays A) {
 // ---- k_finalize: one thread per pair: sigma^2 = VTPV/(n-6) (:2536), code 1 / -3 (:2540-2543), information
 //      matrix = cofactor^-1 / sigma^2 (:1386). Partials are summed in the class order of :2529-2534.
 __global__ void k_finalize(DeviceArrays A, int n_pairs) {
+    if (n_pairs < 0) n_pairs = A.ctl->n_pairs; // recorded into the iteration graph: launched over the capacity
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= n_pairs) return;
     const PairConst &pc = A.pc[pair];
@@ -1268,6 +1640,31 @@ __global__ void k_finalize(DeviceArrays A, int n_pairs) {
     ps.status = kDone;
 }
 
+// ---- k_nn_query: mulls_nn_query — exact 1-NN of arbitrary query points in one target class of pair 0, on the grid
+//      the last registration built (what block1->tree_*->nearestKSearch(p, 1) answers in the reference)
+__global__ void __launch_bounds__(kIterBlock) k_nn_query(DeviceArrays A, int cls, const float *xyz, uint32_t n, int start_level0,
+                                                        int leaf_count, int *out_idx, float *out_d2) {
+    const uint32_t i = blockIdx.x * kIterBlock + threadIdx.x;
+    if (i >= n) return;
+    const PairConst &pc = A.pc[0];
+    const PairState &ps = A.ps[0];
+    int best_j = -1;
+    float best_d2 = INFINITY;
+    if (ps.n_tgt[cls] > 0 && !A.hash_used[1]) {
+        const GridView g = grid_of(A, pc, ps, cls, leaf_count);
+        const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+        const float rmax = 2.5f * pc.thre_unit;
+        const float r2 = rmax * rmax * 1.0001f;
+        walk_greedy_seed(g, px, py, pz, start_level0, best_d2, best_j);
+        WalkStackLocal stk;
+        nn_search_walk<WalkStackLocal, kWalkStack>(g, px, py, pz, r2, start_level0, false, best_d2, best_j, stk);
+        if (best_j >= 0 && !((double)best_d2 <= (double)rmax * (double)rmax)) best_j = -1;
+        if (best_j >= 0) best_j = __float_as_int(__ldg(&g.nrm[best_j]).w);
+    }
+    out_idx[i] = best_j;
+    out_d2[i] = best_j >= 0 ? best_d2 : INFINITY;
+}
+
 // ---- k_state_init: reset the per-pair accumulators that the ingest kernels update atomically
 __global__ void k_state_init(DeviceArrays A, int n_pairs) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1288,6 +1685,7 @@ __global__ void k_state_init(DeviceArrays A, int n_pairs) {
 
 // ---- k_collect: pair state -> mulls_icp_result (device copy, then one D2H)
 __global__ void k_collect(DeviceArrays A, int n_pairs, mulls_icp_result *out) {
+    if (n_pairs < 0) n_pairs = A.ctl->n_pairs;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     const PairState &ps = A.ps[p];

@@ -50,9 +50,24 @@ struct mulls_ctx {
     int max_iter_max = 0;
     bool uploaded = false;
     bool any_keep_less = false;
+    bool grid_valid = false; // pair 0's sorted target slices and grid are those of the last registration (mulls_nn_query)
     // tunables
     int start_level0 = 5;
     int leaf_count = 32;
+    // iteration loop as a CUDA graph: WHILE(pairs running) { search, resolve, accumulate, solve } + posterior, finalize,
+    // collect — one launch, the loop condition is set on the device (no host polling). Built on first use, rebuilt when a
+    // tunable baked into its kernel nodes changes. 0: the host launch loop (per-kernel events for the bench's roofline).
+    int use_graph = 1;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_key[6] = {-1, -1, -1, -1, -1, -1}; // the tunables baked into the kernel nodes
+    LoopCtl *h_ctl = nullptr;            // pinned staging of the control block
+    // which search kernel serves an iteration: iterations < dfs_until run k_search_dfs (per-thread depth first), the rest the
+    // warp-cooperative k_search; dfs_defer_from: k_search_dfs queues a block's small cells from this iteration on
+    int walk_reseed_x4 = 1 << 20; // (quarter level-0 cells) a previous match farther than this is challenged by a fresh greedy seed
+    int search_walk = 0;     // 1: every iteration runs k_search_walk (round 1's per-thread walk; host launch loop only)
+    int dfs_until = 2;
+    int dfs_defer_from = 2;
     int fused_finish = 0;    // 1: k_finish (one launch after the search) instead of k_resolve + k_accumulate + k_solve —
                              // measured slower at batch scale (per-block ticket / fence latency), see DESIGN.md
     int hash_slack = 4;      // table capacity >= hash_slack x cells (power of two): load factor <= 1/hash_slack
@@ -163,6 +178,9 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_running) cudaFreeHost(ctx->h_running);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_search) cudaEventDestroy(e);
@@ -245,6 +263,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ALLOC(A.hash_used, 2);
     ALLOC(A.pair_sync, 2 * max_pairs);
     ALLOC(A.fsync, 1);
+    ALLOC(A.ctl, 1);
     ALLOC(A.blk_kept, ctx->cap_it_chunks);
     ALLOC(A.partials, ctx->cap_it_chunks * kTerms);
     ALLOC(A.post_partials, ctx->cap_it_chunks * 2);
@@ -268,10 +287,11 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     }
     ctx->ev_done.resize(MULLS_MAX_TRACE_ITERS);
     for (auto &ev : ctx->ev_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    A.trace = nullptr;
+    A.trace = ctx->d_trace; // written only when LoopCtl::trace_on is set for the run
     if ((e = cudaMallocHost((void **)&ctx->h_results, max_pairs * sizeof(mulls_icp_result))) != cudaSuccess)
         return fail("pinned results", e);
     if ((e = cudaMallocHost((void **)&ctx->h_flags, 2 * sizeof(uint32_t))) != cudaSuccess) return fail("pinned flags", e);
+    if ((e = cudaMallocHost((void **)&ctx->h_ctl, sizeof(LoopCtl))) != cudaSuccess) return fail("pinned control block", e);
     // radix-sort temp storage for the largest possible sort
     {
         size_t bytes = 0;
@@ -367,6 +387,11 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
     else if (n == "fused_finish") ctx->fused_finish = value;
+    else if (n == "use_graph") ctx->use_graph = value;
+    else if (n == "dfs_until") ctx->dfs_until = value;
+    else if (n == "search_walk") ctx->search_walk = value;
+    else if (n == "walk_reseed_x4") ctx->walk_reseed_x4 = value;
+    else if (n == "dfs_defer_from") ctx->dfs_defer_from = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "host_pack") ctx->host_pack = value;
     else if (n == "poll_pause") ctx->poll_pause = value;
@@ -503,6 +528,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
                        const uint32_t *src_global_n, bool resident = true, bool tgt_on_device = false) {
     if (!ctx || !tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
     ctx->tree_map = nullptr;
+    ctx->grid_valid = false;
     if (n_pairs > ctx->max_pairs) {
         ctx->err = "more pairs than the context was created for";
         return MULLS_E_CAPACITY;
@@ -759,6 +785,49 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
     return MULLS_OK;
 }
 
+// The iteration loop as a CUDA graph (CUDA 12.4+ conditional nodes): WHILE(handle) { k_search [, k_search_shoot],
+// k_resolve, k_accumulate, k_solve } followed by k_posterior, k_finalize, k_collect. Kernel nodes are recorded once per
+// context with grids sized for its capacity; what a run needs to know (chunk / pair counts, trace switch, loop counter)
+// is read from LoopCtl in device memory. k_solve's last block sets the loop condition: no host polling, one launch.
+static int build_iteration_graph(mulls_ctx *ctx) {
+    const int key[6] = {ctx->start_level0, ctx->leaf_count, ctx->reseed_cells_x4, ctx->any_normal_shooting ? 1 : 0, ctx->dfs_until, ctx->dfs_defer_from};
+    if (ctx->graph_exec && std::memcmp(key, ctx->graph_key, sizeof(key)) == 0) return MULLS_OK;
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
+    if (ctx->graph) cudaGraphDestroy(ctx->graph), ctx->graph = nullptr;
+    cudaStream_t st = ctx->stream;
+    DeviceArrays A = ctx->A;
+    const unsigned cap_chunks = (unsigned)std::max<size_t>(ctx->cap_it_chunks, 1), cap_pairs = (unsigned)std::max<size_t>(ctx->max_pairs, 1);
+    CK(cudaGraphCreate(&ctx->graph, 0));
+    cudaGraphConditionalHandle handle;
+    CK(cudaGraphConditionalHandleCreate(&handle, ctx->graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams wp = {cudaGraphNodeTypeConditional};
+    wp.conditional.handle = handle;
+    wp.conditional.type = cudaGraphCondTypeWhile;
+    wp.conditional.size = 1;
+    cudaGraphNode_t while_node;
+    CK(cudaGraphAddNode(&while_node, ctx->graph, nullptr, 0, &wp));
+    cudaGraph_t body = wp.conditional.phGraph_out[0];
+    CK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    if (ctx->dfs_until > 0)
+        k_search_dfs<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
+                                                         ctx->dfs_defer_from, ctx->dfs_until);
+    k_search<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
+                                                 ctx->dfs_until);
+    if (ctx->any_normal_shooting) k_search_shoot<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count);
+    k_resolve<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
+    k_accumulate<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
+    k_solve<<<cap_pairs, kSolveThreads, 0, st>>>(A, -1, (unsigned long long)handle);
+    CK(cudaStreamEndCapture(st, nullptr));
+    CK(cudaStreamBeginCaptureToGraph(st, ctx->graph, &while_node, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+    k_posterior<<<cap_chunks, kIterBlock, 0, st>>>(A);
+    k_finalize<<<(unsigned)ceil_div(cap_pairs, 64), 64, 0, st>>>(A, -1);
+    k_collect<<<(unsigned)ceil_div(cap_pairs, 128), 128, 0, st>>>(A, -1, ctx->d_results);
+    CK(cudaStreamEndCapture(st, nullptr));
+    CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+    std::memcpy(ctx->graph_key, key, sizeof(key));
+    return MULLS_OK;
+}
+
 // Launch the whole path on the resident inputs. If `hook` is given (sharded mode) it is called between
 // the phases that need a cross-rank exchange.
 static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user);
@@ -774,7 +843,6 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DeviceArrays A = ctx->A;
-    A.trace = trace ? ctx->d_trace : nullptr;
     const int np = (int)ctx->n_pairs;
     uint64_t launches = 0;
     CK(cudaEventRecord(ctx->ev_begin, st));
@@ -783,11 +851,25 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         if (rc != MULLS_OK) return rc;
     }
     const unsigned n_itc = (unsigned)ctx->h_it_chunks.size();
+    {
+        LoopCtl &c = *ctx->h_ctl; // (the previous run has been synchronised: the staging copy is free)
+        c = LoopCtl();
+        c.n_it_chunks = (int)n_itc, c.n_pairs = np, c.trace_on = trace ? 1 : 0, c.max_iter = ctx->max_iter_max;
+        CK(cudaMemcpyAsync(A.ctl, ctx->h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
+    }
+    const bool graphed = !hook && ctx->use_graph && !ctx->fused_finish;
+    if (graphed) {
+        const int rc = build_iteration_graph(ctx);
+        if (rc != MULLS_OK) return rc;
+    }
     CK(cudaMemsetAsync(A.pair_sync, 0, 2 * ctx->max_pairs * sizeof(unsigned), st));
     CK(cudaMemsetAsync(A.fsync, 0, sizeof(FinishSync), st));
     CK(cudaEventRecord(ctx->ev_ingest, st));
     int n_search_ev = 0;
-    if (n_itc) {
+    if (graphed) {
+        CK(cudaGraphLaunch(ctx->graph_exec, st));
+        CK(cudaMemcpyAsync(ctx->h_ctl, A.ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, st)); // iterations executed
+    } else if (n_itc) {
         for (int it = 0; it < ctx->max_iter_max; ++it) {
             // flow control: stay at most two iterations ahead of the device and stop launching as soon
             // as every pair has converged or failed (the device mirrors its counter into mapped memory)
@@ -806,7 +888,19 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4);
+            if (ctx->search_walk) {
+                const float rs = 0.25f * (float)ctx->walk_reseed_x4;
+                if (ctx->search_walk == 1) k_search_walk<10, false><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
+                else if (ctx->search_walk == 2) k_search_walk<12, false><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
+                else if (ctx->search_walk == 3) k_search_walk<10, true><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
+                else k_search_walk<8, false><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
+            }
+            else if (it < ctx->dfs_until)
+                k_search_dfs<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
+                                                            ctx->dfs_defer_from, ctx->dfs_until);
+            else
+                k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
+                                                        ctx->dfs_until);
             if (ctx->any_normal_shooting) {
                 k_search_shoot<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
                 ++launches;
@@ -836,7 +930,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
                 launches += 2;
             }
             k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
-            k_solve<<<(unsigned)np, kSolveThreads, 0, st>>>(A, buf);
+            k_solve<<<(unsigned)np, kSolveThreads, 0, st>>>(A, buf, 0ull);
             if (hook) { // exchange 3: per-class normal-equation sums; then every rank solves the same system
                 if (hook(user, A.xch_f64, kNumClasses * kTerms, 0, 0, (void *)st) != 0) {
                     ctx->err = "all-reduce callback failed";
@@ -864,14 +958,17 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         }
     }
     CK(cudaEventRecord(ctx->ev_iter, st));
-    k_collect<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->d_results);
-    ++launches;
+    if (!graphed) {
+        k_collect<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->d_results);
+        ++launches;
+    }
     CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, np * sizeof(mulls_icp_result), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (trace) CK(cudaMemcpyAsync(trace, ctx->d_trace, np * sizeof(mulls_icp_trace), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev_end, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (graphed) launches += (uint64_t)ctx->h_ctl->it * (4u + (ctx->any_normal_shooting ? 1u : 0u) + (ctx->dfs_until > 0 ? 1u : 0u)) + 3u;
     if (ctx->h_flags[1]) {
         ctx->err = "hash pool exhausted (target clouds produce more grid cells than the context reserves)";
         return MULLS_E_CAPACITY;
@@ -900,6 +997,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         CK(cudaMemcpy(hs.data(), A.ps, np * sizeof(PairState), cudaMemcpyDeviceToHost));
         for (int p = 0; p < np; ++p) S.algorithmic_bytes += hs[p].alg_bytes;
     }
+    ctx->grid_valid = !hook;
     return MULLS_OK;
 }
 
@@ -969,6 +1067,35 @@ int mulls_icp_run(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
                   const mulls_icp_params *params, const double init_guess[16], mulls_icp_result *out,
                   mulls_icp_trace *trace) {
     return mulls_icp_run_batch(ctx, 1, tgt, src, params, init_guess, out, trace);
+}
+
+int mulls_nn_query(mulls_ctx *ctx, int cls, const float *xyz, size_t n, int32_t *idx, float *d2) {
+    if (!ctx || cls < 0 || cls >= kNumClasses || (n > 0 && (!xyz || !idx || !d2))) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0]; // (a pipelined context answers for the first pair of its first lane)
+    if (!ctx->grid_valid) {
+        ctx->err = "mulls_nn_query: no registration has run on this context since its last upload";
+        return MULLS_E_ARG;
+    }
+    if (n == 0) return MULLS_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    float *d_q = nullptr;
+    int *d_i = nullptr;
+    float *d_d = nullptr;
+    CK(cudaMallocAsync((void **)&d_q, 3 * n * sizeof(float), st));
+    CK(cudaMallocAsync((void **)&d_i, n * sizeof(int), st));
+    CK(cudaMallocAsync((void **)&d_d, n * sizeof(float), st));
+    CK(cudaMemcpyAsync(d_q, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_nn_query<<<(unsigned)ceil_div(n, kIterBlock), kIterBlock, 0, st>>>(ctx->A, cls, d_q, (uint32_t)n, ctx->start_level0,
+                                                                           ctx->leaf_count, d_i, d_d);
+    CK(cudaMemcpyAsync(idx, d_i, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(d2, d_d, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    cudaFreeAsync(d_q, st);
+    cudaFreeAsync(d_i, st);
+    cudaFreeAsync(d_d, st);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return MULLS_OK;
 }
 
 int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],

@@ -382,4 +382,133 @@ MULLS_HD void nn_search(const GridView &g, bool active, float px, float py, floa
     }
 }
 
+// ---- the per-thread depth-first form -------------------------------------------------------------------------
+// One query per thread, no cooperation: the block's live cells are walked depth first, nearest octant first, and a
+// small cell is examined the moment it is met, so that every later cell is pruned against the tightest bound. Costs
+// SIMT efficiency (the 32 walks of a warp diverge) but no synchronisation and the fewest candidates. `defer`: the
+// small cells of one block are queued (kRanges) and examined together in one flat loop — pays once the seeds are
+// good (late iterations), costs candidates while they are not.
+template <int kRanges, int kStack, class Scratch, class Stats>
+MULLS_HD void nn_search_dfs(const GridView &g, float px, float py, float pz, float r2_prune, int start_level, bool defer,
+                            float &best_d2, int &best_j, Scratch &S, Stats &st) {
+    QueryFrame f;
+    f.fx = (px - g.ox) * g.inv_h0, f.fy = (py - g.oy) * g.inv_h0, f.fz = (pz - g.oz) * g.inv_h0;
+    f.flx = floorf(f.fx), f.fly = floorf(f.fy), f.flz = floorf(f.fz);
+    f.c0x = (int)f.flx, f.c0y = (int)f.fly, f.c0z = (int)f.flz;
+    f.margin = 1e-3f * g.h0;
+    const int L = g.n_levels;
+    int l;
+    if (best_j >= 0) {
+        const float need = 1.001f * sqrtf(best_d2);
+        const float t = need / (0.999f * 0.5f * g.h0);
+        if (t <= 1.0f) l = (need <= 0.998f * 0.5f * g.h0) ? 0 : 1;
+        else l = ilogbf(t) + 1;
+        l = (l < L - 1) ? l : L - 1;
+    } else {
+        l = (start_level < 1) ? 1 : ((start_level < L - 1) ? start_level : L - 1);
+    }
+    int nr = 0;
+    for (;; ++l) {
+        st.level();
+        const float H = g.h0 * (float)(1 << l);
+        const int ncell = 4096 >> l;
+        const int cx = f.c0x >> l, cy = f.c0y >> l, cz = f.c0z >> l;
+        int sx, sy, sz;
+        if (l == 0) {
+            sx = (f.fx - f.flx) >= 0.5f, sy = (f.fy - f.fly) >= 0.5f, sz = (f.fz - f.flz) >= 0.5f;
+        } else {
+            sx = (f.c0x >> (l - 1)) & 1, sy = (f.c0y >> (l - 1)) & 1, sz = (f.c0z >> (l - 1)) & 1;
+        }
+        const int nx = cx + (sx ? 1 : -1), ny = cy + (sy ? 1 : -1), nz = cz + (sz ? 1 : -1);
+        float ex = sx ? ((g.ox + (float)(cx + 1) * H) - f.margin) - px : px - ((g.ox + (float)cx * H) + f.margin);
+        float ey = sy ? ((g.oy + (float)(cy + 1) * H) - f.margin) - py : py - ((g.oy + (float)cy * H) + f.margin);
+        float ez = sz ? ((g.oz + (float)(cz + 1) * H) - f.margin) - pz : pz - ((g.oz + (float)cz * H) + f.margin);
+        ex = fmaxf(ex, 0.0f), ey = fmaxf(ey, 0.0f), ez = fmaxf(ez, 0.0f);
+        ex *= ex, ey *= ey, ez *= ez;
+        const bool vx0 = cx >= 0 && cx < ncell, vx1 = nx >= 0 && nx < ncell;
+        const bool vy0 = cy >= 0 && cy < ncell, vy1 = ny >= 0 && ny < ncell;
+        const bool vz0 = cz >= 0 && cz < ncell, vz1 = nz >= 0 && nz < ncell;
+        uint32_t live = 0;
+        {
+            const float bound0 = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool i = k & 1, j = (k >> 1) & 1, m = k >> 2;
+                const float d2c = (i ? ex : 0.0f) + (j ? ey : 0.0f) + (m ? ez : 0.0f);
+                if ((i ? vx1 : vx0) && (j ? vy1 : vy0) && (m ? vz1 : vz0) && d2c <= bound0) live |= 1u << k;
+            }
+        }
+        while (live) { // lowest bit first: k = 0 is p's own cell
+            const int k = lowest_bit(live);
+            live &= live - 1;
+            {
+                const float d2c = ((k & 1) ? ex : 0.0f) + ((k & 2) ? ey : 0.0f) + ((k & 4) ? ez : 0.0f);
+                if (d2c > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue; // the bound has moved since the mask was built
+            }
+            int sp = 0;
+            S.stack(sp++) = pack_cell((uint32_t)((k & 1) ? nx : cx), (uint32_t)((k & 2) ? ny : cy), (uint32_t)((k & 4) ? nz : cz), l, 0u);
+            bool root = true;
+            while (sp > 0) {
+                const uint2 ce = S.stack(--sp);
+                const int lv = (int)((ce.y >> 4) & 0xfu);
+                const int x = (int)(ce.x & 0xfffu), y = (int)((ce.x >> 12) & 0xfffu), z = (int)((ce.x >> 24) | ((ce.y & 0xfu) << 8));
+                const float hl = g.h0 * (float)(1 << lv);
+                if (!root) { // a pushed child may have fallen behind the bound since
+                    const float ax = slab_dist(g.ox + (float)x * hl, g.ox + (float)(x + 1) * hl, px, f.margin);
+                    const float ay = slab_dist(g.oy + (float)y * hl, g.oy + (float)(y + 1) * hl, py, f.margin);
+                    const float az = slab_dist(g.oz + (float)z * hl, g.oz + (float)(z + 1) * hl, pz, f.margin);
+                    if (ax * ax + ay * ay + az * az > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                }
+                root = false;
+                uint32_t start, count, cmask;
+                st.probe(lv == l ? 0 : 1);
+                if (!probe_cell(g, (uint32_t)x, (uint32_t)y, (uint32_t)z, lv, start, count, cmask)) continue;
+                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kStack) {
+                    S.range(nr++) = make_uint2(start, count);
+                    if (!defer || nr == kRanges) scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
+                    continue;
+                }
+                st.expand();
+                const float hc = 0.5f * hl;
+                float ax0, ax1, ay0, ay1, az0, az1;
+                {
+                    const float lox = g.ox + (float)(2 * x) * hc, mdx = g.ox + (float)(2 * x + 1) * hc, hix = g.ox + (float)(2 * x + 2) * hc;
+                    const float loy = g.oy + (float)(2 * y) * hc, mdy = g.oy + (float)(2 * y + 1) * hc, hiy = g.oy + (float)(2 * y + 2) * hc;
+                    const float loz = g.oz + (float)(2 * z) * hc, mdz = g.oz + (float)(2 * z + 1) * hc, hiz = g.oz + (float)(2 * z + 2) * hc;
+                    ax0 = slab_dist(lox, mdx, px, f.margin), ax1 = slab_dist(mdx, hix, px, f.margin);
+                    ay0 = slab_dist(loy, mdy, py, f.margin), ay1 = slab_dist(mdy, hiy, py, f.margin);
+                    az0 = slab_dist(loz, mdz, pz, f.margin), az1 = slab_dist(mdz, hiz, pz, f.margin);
+                    ax0 *= ax0, ax1 *= ax1, ay0 *= ay0, ay1 *= ay1, az0 *= az0, az1 *= az1;
+                }
+                const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
+                const int near_child = (ax1 < ax0 ? 1 : 0) | (ay1 < ay0 ? 2 : 0) | (az1 < az0 ? 4 : 0);
+                uint32_t pass = 0;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    if (((ch & 1) ? ax1 : ax0) + ((ch & 2) ? ay1 : ay0) + ((ch & 4) ? az1 : az0) <= bound) pass |= 1u << ch;
+                pass &= cmask;
+                // re-index by c = ch ^ near_child and reverse: the lowest bit is the farthest octant (pushed first)
+                if (near_child & 1) pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
+                if (near_child & 2) pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
+                if (near_child & 4) pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
+                pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
+                pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
+                pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
+                while (pass) {
+                    const int b = lowest_bit(pass);
+                    pass &= pass - 1;
+                    const int ch = (7 - b) ^ near_child;
+                    S.stack(sp++) = pack_cell((uint32_t)(2 * x + (ch & 1)), (uint32_t)(2 * y + ((ch >> 1) & 1)), (uint32_t)(2 * z + (ch >> 2)), lv - 1, 0u);
+                }
+            }
+        }
+        scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st); // what the block deferred
+        const float cover = (l == 0) ? 0.998f * 0.5f * g.h0 : 0.999f * 0.5f * H;
+        const float cover2 = cover * cover;
+        if (best_d2 <= cover2) break;
+        if (cover2 >= r2_prune) break;
+        if (l == L - 1) break;
+    }
+}
+
 } // namespace mulls

@@ -190,6 +190,16 @@ class Context:
             C.POINTER(C.c_double)), cb, None, C.byref(res), C.byref(tr) if tr is not None else None))
         return abi.result_to_dict(res), (abi.trace_to_dict(tr) if tr is not None else None)
 
+    def nn_query(self, cls: int, xyz: np.ndarray):
+        """mulls_nn_query: what block1->tree_*->nearestKSearch(point, 1) answers in the reference, on the sorted target
+        slices the last registration left in HBM. Returns (index into the caller's class cloud or -1, squared distance)."""
+        q = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        idx = np.empty(len(q), np.int32)
+        d2 = np.empty(len(q), np.float32)
+        self._check(self.lib.mulls_nn_query(self.handle, int(cls), q.ctypes.data_as(C.POINTER(C.c_float)), len(q),
+                                            idx.ctypes.data_as(C.POINTER(C.c_int32)), d2.ctypes.data_as(C.POINTER(C.c_float))))
+        return idx, d2
+
     def pca_features(self, cloud: np.ndarray, radius: float, k: int, stride: int = 1) -> dict:
         """PrincipleComponentAnalysis::get_pc_pca_feature (pca.hpp:294-354) on the GPU."""
         c = abi.as_aos48(cloud)

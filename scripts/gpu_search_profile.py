@@ -15,6 +15,15 @@ tun = dict(kv.split("=") for kv in sys.argv[4:])
 pairs = [synth.make_pair(1000 + i, cfg) for i in range(n_pairs)]
 ns = max(sum(len(s) for s in p["src"]) for p in pairs)
 nt = max(sum(len(t) for t in p["tgt"]) for p in pairs)
+import torch
+a = torch.empty(1 << 28, dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)
+for _ in range(3): b.copy_(a)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): b.copy_(a)
+e1.record(); torch.cuda.synchronize()
+print(f"box calibration: device copy {2 * a.numel() * 10 / e0.elapsed_time(e1) / 1e6:.0f} GB/s", flush=True)
+del a, b
 ctx = Context(0, n_pairs, ns + 16, nt + 16)
 for k, v in tun.items():
     ctx.set_tunable(k, int(v))

@@ -46,10 +46,17 @@ def trans_a(x):
     return T
 
 
+SHARE = 0
+MODE = 0
+
+
 def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     config = sys.argv[2] if len(sys.argv) > 2 else "c2"
     leaf = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+    global SHARE, MODE
+    MODE = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    SHARE = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     lib = load_harness()
     pair = synth.make_pair(seed, config)
     res, tr = oracle.icp_run(pair["tgt"], pair["src"], pair["params"], pair["init_guess"], threads=8)
@@ -93,6 +100,8 @@ def main():
             out_idx = np.empty(m, np.int32)
             out_d2 = np.empty(m, np.float32)
             stats = np.zeros(12, np.uint64)
+            stats[11] = SHARE
+            stats[10] = MODE
             epq = np.zeros(m, np.uint32)
             qc = np.ascontiguousarray(q)
             t0 = time.time()

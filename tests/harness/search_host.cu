@@ -129,28 +129,80 @@ int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_pru
     HostGrid *G = (HostGrid *)h;
     const GridView &g = G->g;
     Counters C;
-    for (uint32_t i = 0; i < m; ++i) {
-        const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
-        float best_d2 = INFINITY;
-        int best_j = -1;
-        if (seed && seed[i] >= 0) {
-            best_j = (int)G->inv[seed[i]];
-            const float4 t = g.pos[best_j];
-            best_d2 = flann_l2(px, py, pz, t.x, t.y, t.z);
+    const bool share = stats[11] != 0; // study switch: warps of 32 consecutive queries exchange their seeds first
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t nw = std::min<uint32_t>(32, m - base);
+        float sd2[32];
+        int sj[32];
+        for (uint32_t k = 0; k < nw; ++k) {
+            const uint32_t i = base + k;
+            const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+            sd2[k] = INFINITY, sj[k] = -1;
+            if (seed && seed[i] >= 0) {
+                sj[k] = (int)G->inv[seed[i]];
+                const float4 t = g.pos[sj[k]];
+                sd2[k] = flann_l2(px, py, pz, t.x, t.y, t.z);
+            }
+            if (share && (sj[k] < 0 || (reseed_d2 >= 0.0f && sd2[k] > reseed_d2))) { // seed phase of nn_search, done here
+                uint2 leaf;
+                if (quick_locate(g, px, py, pz, start_level, leaf, C)) {
+                    C.eval((int)leaf.y);
+                    for (uint32_t jj = leaf.x; jj < leaf.x + leaf.y; ++jj) {
+                        const float4 t = g.pos[jj];
+                        consider(g, flann_l2(px, py, pz, t.x, t.y, t.z), jj, sd2[k], sj[k]);
+                    }
+                }
+            }
         }
-        HostScratch<8, 12> S;
-        C.cur_evals = 0;
-        SoloCoop co;
-        nn_search<8, 12>(g, true, px, py, pz, r2_prune, start_level, (reseed_d2 >= 0.0f) ? reseed_d2 : INFINITY, best_d2, best_j, S, co, C);
-        C.max_evals_query = std::max(C.max_evals_query, C.cur_evals);
-        if (evals_per_query) evals_per_query[i] = (uint32_t)C.cur_evals;
-        out_d2[i] = best_d2;
-        if (best_j >= 0) {
-            int oi;
-            std::memcpy(&oi, &g.nrm[best_j].w, 4);
-            out_idx[i] = oi;
-        } else {
-            out_idx[i] = -1;
+        if (share) {
+            float nd2[32];
+            int nj[32];
+            for (uint32_t k = 0; k < nw; ++k) nd2[k] = sd2[k], nj[k] = sj[k];
+            for (uint32_t k = 0; k < nw; ++k) {
+                const uint32_t i = base + k;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t k2 = k ^ (uint32_t)o;
+                    if (k2 >= nw || sj[k2] < 0) continue;
+                    const float4 t = g.pos[sj[k2]];
+                    C.eval(1);
+                    consider(g, flann_l2(q[3 * i], q[3 * i + 1], q[3 * i + 2], t.x, t.y, t.z), (uint32_t)sj[k2], nd2[k], nj[k]);
+                }
+            }
+            for (uint32_t k = 0; k < nw; ++k) sd2[k] = nd2[k], sj[k] = nj[k];
+        }
+        for (uint32_t k = 0; k < nw; ++k) {
+            const uint32_t i = base + k;
+            const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+            float best_d2 = sd2[k];
+            int best_j = sj[k];
+            HostScratch<8, 48> S;
+            C.cur_evals = 0;
+            SoloCoop co;
+            const int mode = (int)stats[10]; // 0: rounds (nn_search), 1: depth first, 2: depth first with deferred scans
+            if (mode == 0) {
+                nn_search<8, 12>(g, true, px, py, pz, r2_prune, start_level,
+                                 share ? INFINITY : ((reseed_d2 >= 0.0f) ? reseed_d2 : INFINITY), best_d2, best_j, S, co, C);
+            } else {
+                if (!share && (best_j < 0 || (reseed_d2 >= 0.0f && best_d2 > reseed_d2))) {
+                    uint2 leaf;
+                    int nr1 = 0;
+                    if (quick_locate(g, px, py, pz, start_level, leaf, C)) {
+                        S.range(nr1++) = leaf;
+                        scan_ranges(g, px, py, pz, S, nr1, best_d2, best_j, C);
+                    }
+                }
+                nn_search_dfs<8, 48>(g, px, py, pz, r2_prune, start_level, mode == 2, best_d2, best_j, S, C);
+            }
+            C.max_evals_query = std::max(C.max_evals_query, C.cur_evals);
+            if (evals_per_query) evals_per_query[i] = (uint32_t)C.cur_evals;
+            out_d2[i] = best_d2;
+            if (best_j >= 0) {
+                int oi;
+                std::memcpy(&oi, &g.nrm[best_j].w, 4);
+                out_idx[i] = oi;
+            } else {
+                out_idx[i] = -1;
+            }
         }
     }
     stats[0] = C.probes_block, stats[1] = C.probes_child, stats[2] = C.evals, stats[3] = C.expands, stats[4] = C.levels;

@@ -407,3 +407,69 @@ def test_host_packed_wire_format_is_bit_identical(oracle_mod, small_pair):
     assert np.array_equal(r0["T"], r1["T"]) and np.array_equal(t0["atpa"], t1["atpa"])
     lm.close()
     ctx.close()
+
+
+def test_graph_loop_equals_host_loop(oracle_mod, small_pair):
+    """The iteration loop as ONE CUDA-graph launch (device-side WHILE, the default) and as the host launch loop
+    (use_graph = 0, the path the bench times per kernel) give bit-identical results and traces — also when the pairs
+    of a batch stop at different iterations, when one fails early (-1 / -2), and for max_iter = 1."""
+    from mulls_b200.registration import Context
+
+    pairs = [small_pair]
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.max_iter_num = 1
+    pairs.append(dict(small_pair, params=p))
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.max_iter_num = 3
+    pairs.append(dict(small_pair, params=p))
+    far = np.eye(4)
+    far[0, 3] = 40.0  # nothing within the correspondence threshold: code -2 in the first iteration
+    pairs.append(dict(small_pair, init_guess=far))
+    out = {}
+    for mode in (1, 0):
+        ctx = Context(0, len(pairs), 30000, 30000)
+        ctx.set_tunable("use_graph", mode)
+        out[mode] = ctx.run_batch(pairs, want_trace=True)
+        again = ctx.run_batch(pairs, want_trace=True)  # the recorded graph is re-launched, not rebuilt
+        for a, b in zip(out[mode][0], again[0]):
+            assert np.array_equal(a["T"], b["T"]) and a["iters"] == b["iters"]
+        ctx.close()
+    for (a, ta), (b, tb) in zip(zip(*out[1]), zip(*out[0])):
+        assert a["code"] == b["code"] and a["iters"] == b["iters"] and a["n_corr"] == b["n_corr"]
+        assert np.array_equal(a["T"], b["T"]) and np.array_equal(a["info"], b["info"])
+        assert ta["n_iter"] == tb["n_iter"]
+        np.testing.assert_array_equal(ta["atpa"], tb["atpa"])
+        np.testing.assert_array_equal(ta["n_src"], tb["n_src"])
+    assert [r["code"] for r in out[1][0]] == [1, 1, 1, -2] and [r["iters"] for r in out[1][0]][1:3] == [1, 3]
+    o, ot = oracle_mod.icp_run(small_pair["tgt"], small_pair["src"], small_pair["params"], small_pair["init_guess"])
+    assert_parity(out[1][0][0], out[1][1][0], o, ot)
+
+
+def test_nn_query_stands_in_for_the_target_kdtrees(ctx, oracle_mod, small_pair):
+    """mulls_nn_query = block1->tree_*->nearestKSearch(p, 1) (src/map_manager.cpp:221-258 on the trees of
+    cregistration.hpp:1213-1232): on the clouds the oracle's mm_lls_icp built its trees on, the same neighbour and the
+    same float distance for scan points and for arbitrary points, 'nothing' beyond the registration's search radius."""
+    g, _ = ctx.run_batch([small_pair])
+    res, trees = oracle_mod.icp_run_trees(small_pair["tgt"], small_pair["src"], small_pair["params"], small_pair["init_guess"])
+    rng = np.random.default_rng(5)
+    rmax = 2.5 * small_pair["params"].dis_thre_unit
+    for c in (abi.PILLAR, abi.FACADE, abi.BEAM, abi.GROUND):
+        tree_cloud = trees[c]
+        if len(tree_cloud) < 3:
+            continue
+        q = np.concatenate([small_pair["src"][c][:400, :3] + rng.normal(0, 0.2, (len(small_pair["src"][c][:400]), 3)),
+                            rng.uniform(-30, 30, (200, 3))]).astype(np.float32)
+        rows = np.zeros((len(q), 12), np.float32)
+        rows[:, :3] = q
+        oi, od = oracle_mod.nn(tree_cloud, rows, 1e9)
+        idx, d2 = ctx.nn_query(c, q)
+        inside = od.astype(np.float64) <= np.float64(np.float32(rmax)) ** 2
+        assert inside.sum() > 100
+        np.testing.assert_array_equal(d2[inside], od[inside])
+        # indices: the oracle's are into its filtered clone, ours into the caller's cloud — the POINTS must coincide
+        np.testing.assert_array_equal(small_pair["tgt"][c][idx[inside], :3], tree_cloud[oi[inside], :3])
+        assert np.all(idx[~inside] == -1) and np.all(np.isinf(d2[~inside]))
+    fresh = type(ctx)(0, 1, 1000, 1000)
+    with pytest.raises(RuntimeError):
+        fresh.nn_query(0, np.zeros((1, 3), np.float32))
+    fresh.close()

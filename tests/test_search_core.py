@@ -42,7 +42,7 @@ def n_levels(h0, radius):
     return L
 
 
-def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0):
+def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0, mode=0):
     tgt_xyz = np.ascontiguousarray(tgt_xyz, np.float32)
     q_xyz = np.ascontiguousarray(q_xyz, np.float32)
     origin = (tgt_xyz.min(0) - 2 * h0).astype(np.float32)
@@ -53,6 +53,7 @@ def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0)
     idx = np.empty(m, np.int32)
     d2 = np.empty(m, np.float32)
     stats = np.zeros(12, np.uint64)
+    stats[10] = mode  # 0: rounds (the warp-cooperative kernel's per-thread semantics), 1 / 2: depth first
     r = np.float32(radius)
     r2 = np.float32(np.float32(np.float64(r) * np.float64(r)) * np.float32(1.0001))
     sd = np.ascontiguousarray(seeds, np.int32) if seeds is not None else None
@@ -103,15 +104,17 @@ def test_random_clouds_equal_brute_force(lib, seed):
     bi, bd = brute(tgt, q)
     for radius in (3.5, 1.25, 0.3):
         for leaf in (32, 4):
-            idx, d2 = run(lib, tgt, q, radius, leaf=leaf)
-            check(idx, d2, bi, bd, radius)
+            for mode in (0, 1, 2):
+                idx, d2 = run(lib, tgt, q, radius, leaf=leaf, mode=mode)
+                check(idx, d2, bi, bd, radius)
     # seeded: good seeds (the answer), stale seeds (random target), mixed with none
     seeds = bi.copy()
     seeds[::3] = rng.integers(0, len(tgt), len(seeds[::3]))
     seeds[1::7] = -1
     for reseed in (-1.0, 0.0625):
-        idx, d2 = run(lib, tgt, q, 3.5, seeds=seeds, reseed=reseed)
-        check(idx, d2, bi, bd, 3.5)
+        for mode in (0, 1, 2):
+            idx, d2 = run(lib, tgt, q, 3.5, seeds=seeds, reseed=reseed, mode=mode)
+            check(idx, d2, bi, bd, 3.5)
 
 
 def test_tiny_and_degenerate_grids(lib):
@@ -136,8 +139,9 @@ def test_synthetic_pair_equals_oracle_kdtree(lib):
         if len(tgt) < 3 or len(src) < 3:
             continue
         oi, od = oracle.nn(tgt, src, 1e9)
-        idx, d2 = run(lib, tgt[:, :3], src[:, :3], 3.5)
-        check(idx, d2, oi, od, 3.5)
+        for mode in (0, 1, 2):
+            idx, d2 = run(lib, tgt[:, :3], src[:, :3], 3.5, mode=mode)
+            check(idx, d2, oi, od, 3.5)
         moved = src.copy()
         moved[:, 0] += 0.07
         moved[:, 1] -= 0.03

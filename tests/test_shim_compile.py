@@ -19,3 +19,21 @@ def test_shim_builds_links_and_runs():
         out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "shim compiled and linked" in out.stdout
+
+
+def test_dropin_headers_replace_the_reference_classes_without_edits():
+    """include/dropin/{cregistration.hpp, cfilter.hpp, map_manager.h}: the reference's own header and class names
+    (lo::CRegistration<PointT>, lo::CFilter<PointT>, lo::MapManager), its call sequences (test/mulls_reg.cpp:134-195,
+    test/mulls_slam.cpp:270, :360-377, :438-446, :633-685) verbatim, the drop-in directory merely first on the include
+    path. The reference's headers are played by stand-ins (tests/stubs/ref) whose replaced bodies flag if they ever run;
+    members the drop-in does not replace must stay reachable (inherited)."""
+    libdir = os.path.join(ROOT, "mulls_b200", "csrc")
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "dropin_caller")
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-I", os.path.join(ROOT, "include", "dropin"),
+                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "stubs", "ref"),
+                               "-I", os.path.join(ROOT, "tests", "stubs"), os.path.join(ROOT, "tests", "stubs", "dropin_caller.cpp"),
+                               "-o", exe, "-L", libdir, "-lmulls_b200", f"-Wl,-rpath,{libdir}"])
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "drop-in compiled and linked" in out.stdout and "failures 0" in out.stdout
