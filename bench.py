@@ -349,6 +349,56 @@ def main():
         assert all(r["iters"] == 20 for r in r20), [r["iters"] for r in r20]
         fixed20 = (k20, f0.elapsed_time(f1) / 1e3)
 
+    # ---- (B3) BASELINE config 5 at N >= 2: ONE 128-beam registration with its source sharded over the ranks, the
+    # per-iteration exchanges (claim table: min; counts and per-class sums: sum) as ncclAllReduce calls inside the
+    # library (mulls_icp_run_sharded_nccl), next to the same registration unsharded on rank 0's GPU
+    c5 = None
+    if world > 1 and args.config == "c2":
+        from mulls_b200.dist import nccl_init_from_torch, shard_sources
+
+        pair5 = synth.make_pair(1000, "c5")
+        shards, base5, glob5 = shard_sources(pair5["src"], rank, world)
+        ctx5 = Context(local_rank, 1, max(1, sum(len(x) for x in shards)), sum(len(t) for t in pair5["tgt"]))
+        nccl_init_from_torch(ctx5)
+        for _ in range(3):
+            r5, _ = ctx5.run_sharded_nccl(dict(pair5, src=shards), base5, glob5)
+        barrier()
+        ms5 = []
+        for _ in range(5):
+            r5, _ = ctx5.run_sharded_nccl(dict(pair5, src=shards), base5, glob5)
+            ms5.append(ctx5.stats()["ms_total"])
+        barrier()
+        ctx5.close()
+        # the exchanges alone: the three all-reduces of one iteration, timed back to back on this rank's stream
+        tmin = torch.zeros(sum(len(t) for t in pair5["tgt"]), dtype=torch.int32, device="cuda")
+        tcnt = torch.zeros(12, dtype=torch.int32, device="cuda")
+        tsum = torch.zeros(6 * 28, dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN), dist.all_reduce(tcnt), dist.all_reduce(tsum)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN), dist.all_reduce(tcnt), dist.all_reduce(tsum)
+        c1.record()
+        torch.cuda.synchronize()
+        coll_ms = c0.elapsed_time(c1) / 10
+        un_ms = None
+        if rank == 0:
+            one = Context(local_rank, 1, sum(len(x) for x in pair5["src"]), sum(len(t) for t in pair5["tgt"]))
+            one.upload([pair5])
+            for _ in range(3):
+                ru, _ = one.run_resident()
+            un = []
+            for _ in range(5):
+                ru, _ = one.run_resident()
+                un.append(one.stats()["ms_total"])
+            un_ms = float(np.median(un))
+            dtp, drp = synth.pose_error(r5["T"], ru[0]["T"])
+            same = r5["code"] == ru[0]["code"] and r5["iters"] == ru[0]["iters"] and dtp <= 1e-4 and drp <= 1e-4
+            one.close()
+        c5 = {"sharded_ms": float(np.median(ms5)), "collectives_ms_per_iteration": coll_ms, "unsharded_ms": un_ms,
+              "iters": r5["iters"], "equal_to_unsharded": bool(same) if rank == 0 else None}
+
     # ---- (C) end to end through the C-ABI with host (pinned) buffers, same lanes ----------------------
     # The clouds cross PCIe either as the caller's 48-byte rows or repacked on the host cores to the 28 B/point wire
     # format (the "host_pack" tunable, csrc/host_pack.h); both are the same public call and give identical results.
@@ -391,8 +441,9 @@ def main():
 
     # ---- reduce over ranks -------------------------------------------------------------------
     dev_s = dev_ms / 1e3
-    (dev_s, e2e_s, wall_s, lanes_s, f20_s), (launches_all, _, _) = reduce_over_ranks(
-        dist, "cuda", [dev_s, e2e_s, wall_s, lanes_s, fixed20[1] if fixed20 else 0.0], [float(launches), float(alg_bytes), float(search_ms)])
+    (dev_s, e2e_s, wall_s, lanes_s, f20_s, c5_ms, c5_coll), (launches_all, _, _) = reduce_over_ranks(
+        dist, "cuda", [dev_s, e2e_s, wall_s, lanes_s, fixed20[1] if fixed20 else 0.0, c5["sharded_ms"] if c5 else 0.0,
+                       c5["collectives_ms_per_iteration"] if c5 else 0.0], [float(launches), float(alg_bytes), float(search_ms)])
     launches = int(launches_all)
     total_regs = args.pairs * world * args.steps
     value = total_regs / lanes_s
@@ -445,6 +496,13 @@ def main():
                                      "note": "convergence test disabled: every pair runs max_iter_num = 20 iterations"}
                                     if fixed20 else None),
             "host_affinity": affinity,
+            "c5_sharded": ({"workload": "one 128-beam scan pair (BASELINE configs[4]: 263k / 265k returns of 300k rays), source classes "
+                                        f"sharded over {world} ranks, target replicated",
+                            "ms_per_registration_sharded": c5_ms, "ms_per_registration_unsharded_1gpu": c5["unsharded_ms"],
+                            "collectives_per_iteration": 3, "collectives_ms_per_iteration": c5_coll, "iterations": c5["iters"],
+                            "equal_to_unsharded": c5["equal_to_unsharded"],
+                            "timing": "device time of the whole call (ingest + iterations + posterior), max over ranks, median of 5"}
+                           if c5 else None),
             "max_pose_err_vs_gt_m": max(e[0] for e in errs),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -17,7 +17,8 @@
  *   mulls_batch_run_resident <- same, split so that inputs can stay resident in HBM between runs
  *   mulls_icp_run_sharded    <- the same call with the source clouds sharded over ranks
  *                               (BASELINE config 5); the per-iteration exchange is delegated to a
- *                               caller-supplied all-reduce (NCCL in production)
+ *                               caller-supplied all-reduce; mulls_icp_run_sharded_nccl: the same over NCCL inside the
+ *                               library (mulls_nccl_unique_id, mulls_nccl_init)
  *   mulls_pca_features       <- lo::PrincipleComponentAnalysis<PointT>::get_pc_pca_feature
  *                               include/common/pca.hpp:294-354 (+ get_pca_feature :390-434)
  *   mulls_map_update         <- lo::MapManager::update_local_map, src/map_manager.cpp:17-145
@@ -199,6 +200,26 @@ int mulls_icp_run_sharded(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_C
                           const mulls_icp_params *params, const double init_guess[16],
                           mulls_allreduce_fn allreduce, void *user, mulls_icp_result *out,
                           mulls_icp_trace *trace);
+
+/* The same over NCCL, entirely inside the library (no callback, nothing interpreted in the loop): the three
+ * exchanges of an iteration are ncclAllReduce calls enqueued on the context's stream between its kernels.
+ * libnccl.so.2 is resolved at run time with dlopen (inside a PyTorch process: the NCCL PyTorch has loaded), so the
+ * library has no link-time dependency on NCCL.
+ *   mulls_nccl_unique_id   rank 0 creates an id (ncclGetUniqueId) and ships the 128 bytes to the other ranks by any
+ *                          means (MPI, a file, torch.distributed.broadcast)
+ *   mulls_nccl_init        collective: ncclCommInitRank on the context's device; the communicator belongs to the
+ *                          context and is destroyed with it
+ *   mulls_icp_run_sharded_nccl   `comm` = an ncclComm_t of the SAME libnccl (e.g. one the application already has
+ *                          for these ranks), or NULL for the context's own (mulls_nccl_init) */
+#define MULLS_NCCL_ID_BYTES 128
+int mulls_nccl_unique_id(char id[MULLS_NCCL_ID_BYTES]);
+int mulls_nccl_init(mulls_ctx *ctx, int rank, int world, const char id[MULLS_NCCL_ID_BYTES]);
+int mulls_icp_run_sharded_nccl(mulls_ctx *ctx, void *comm /* ncclComm_t or NULL */,
+                               const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
+                               const mulls_cloud_view src_shard[MULLS_NUM_CLASSES],
+                               const uint32_t src_index_base[MULLS_NUM_CLASSES],
+                               const uint32_t src_global_n[MULLS_NUM_CLASSES], const mulls_icp_params *params,
+                               const double init_guess[16], mulls_icp_result *out, mulls_icp_trace *trace);
 
 /* Stand-in for block1->tree_* (cregistration.hpp:1213-1232): mm_lls_icp leaves a kd-tree per target class in
  * registration_cons.block1, and MapManager::map_scan_feature_pts_distance_removal (src/map_manager.cpp:221-258, called

@@ -259,6 +259,9 @@ EXPORTED_SYMBOLS = (
     "mulls_classify_nground",
     "mulls_set_tunable",
     "mulls_nn_query",
+    "mulls_nccl_unique_id",
+    "mulls_nccl_init",
+    "mulls_icp_run_sharded_nccl",
     "mulls_pack_rows",
     "mulls_ground_default_params",
     "mulls_fast_ground_filter",
@@ -311,6 +314,10 @@ def load_library() -> C.CDLL:
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(IcpParams),
                                           C.POINTER(C.c_double), ALLREDUCE_FN, vp, C.POINTER(IcpResult),
                                           C.POINTER(IcpTrace)]
+    lib.mulls_icp_run_sharded_nccl.restype = C.c_int
+    lib.mulls_icp_run_sharded_nccl.argtypes = [vp, vp, C.POINTER(CloudView), C.POINTER(CloudView), C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_uint32), C.POINTER(IcpParams), C.POINTER(C.c_double),
+                                               C.POINTER(IcpResult), C.POINTER(IcpTrace)]
     lib.mulls_pca_features.restype = C.c_int
     lib.mulls_pca_features.argtypes = [vp, CloudView, C.c_float, C.c_int, C.c_int, C.POINTER(PcaOut)]
     lib.mulls_ground_default_params.restype = None
@@ -323,6 +330,10 @@ def load_library() -> C.CDLL:
     lib.mulls_extract_semantic_pts.argtypes = [vp, CloudView, C.POINTER(ExtractParams), C.POINTER(ExtractOut)]
     lib.mulls_pack_rows.restype = C.c_int
     lib.mulls_pack_rows.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+    lib.mulls_nccl_unique_id.restype = C.c_int
+    lib.mulls_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.mulls_nccl_init.restype = C.c_int
+    lib.mulls_nccl_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     lib.mulls_nn_query.restype = C.c_int
     lib.mulls_nn_query.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     lib.mulls_set_tunable.restype = C.c_int

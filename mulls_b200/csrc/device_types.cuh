@@ -107,8 +107,6 @@ struct PairState {
     uint32_t kl_hist[kNumSegs][256];
 };
 
-struct FinishSync;
-
 // Per-run control block in device memory: what a kernel that was recorded into a CUDA graph (fixed arguments, grids
 // sized for the context's capacity) needs to know about THIS run, and the iteration counter of the device-side loop.
 struct LoopCtl {
@@ -150,8 +148,6 @@ struct DeviceArrays {
     mulls_icp_trace *trace; // may be null
     int *xch_i32;           // exchange buffer of the sharded mode (counts / bbox), 32 ints
     double *xch_f64;        // exchange buffer of the sharded mode (per-class sums), 6*kTerms + 2 doubles
-    unsigned *pair_sync;    // k_finish: per pair [resolved chunks, accumulated chunks] of the current iteration
-    struct FinishSync *fsync; // k_finish: ticket / done counters
     LoopCtl *ctl;
     int *running;           // pairs still iterating (device counter)
     volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop

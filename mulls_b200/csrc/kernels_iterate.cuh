@@ -29,149 +29,6 @@ __device__ __forceinline__ mulls_icp_trace *trace_of(const DeviceArrays &A, uint
 // exact 1-NN within radius on the multi-level hashed grid of one target class: search_core.cuh
 // (__host__ __device__; the CPU suite runs the same functions against a brute-force scan)
 // ------------------------------------------------------------------------------------------------
-constexpr int kSearchRanges = 8;  // candidate ranges queued per thread between two scans (one block / one split)
-constexpr int kSearchStack = 8;   // dense cells waiting to be split (overflow: the cell is scanned whole)
-
-// ---- the warp-cooperative form of the search (see SoloCoop in search_core.cuh for the per-thread semantics) -----
-// Traversal stays per lane (a few probes per query); the candidates it queues are examined by the whole warp as ONE
-// flat list: per-query candidate counts are broad (median 16, p99 > 100), so a per-lane scan loop keeps ~8 of 32
-// lanes busy, while equal shares of the flat list keep all of them busy whatever the split between the queries.
-//   ranges    lane l queues its ranges straight into ent[0..nr)[l]; obase[l] = items queued by the lanes before l
-//   shares    lane i examines items [i*C, (i+1)*C), C = ceil(T / 32): a 5-step search for the owner of its first
-//             item, then the same lean loop a single thread would run, walking from range to range
-//   result    per owner a 64-bit key (distance bits << 32 | target) in shared memory. A lane keeps the best of the
-//             owner it is working for in registers (starting from the owner's current key, so that most candidates
-//             fail one compare) and publishes an improvement when it moves on to another owner: compare-and-swap
-//             loop; equal distances are settled by the ORIGINAL index, exactly like consider()
-constexpr int kSoloScanLanes = 3; // at most this many lanes with queued ranges: they scan on their own
-
-struct WarpShared {
-    uint2 ent[kSearchRanges][32]; // [r][lane] = {start, count}
-    uint32_t obase[33];
-    uint32_t nr[32];
-    float4 qp[32];
-    unsigned long long best[32];
-};
-
-// per-thread scratch of the search in shared memory: the range queue lives in the warp's table, the stack of dense
-// cells is interleaved by thread (conflict-free 8-byte accesses)
-struct SmemScratch {
-    uint2 *ranges; // &warp.ent[0][lane]
-    uint2 *stk;    // &s_stack[0][threadIdx.x]
-    __device__ __forceinline__ uint2 &range(int i) { return ranges[i * 32]; }
-    __device__ __forceinline__ uint2 &stack(int i) { return stk[i * kIterBlock]; }
-};
-
-struct WarpCoop {
-    WarpShared *w;
-    __device__ __forceinline__ bool any(bool b) { return __any_sync(0xffffffffu, b); }
-
-    __device__ __forceinline__ void offer(const GridView &g, int owner, uint32_t d2bits, int j) {
-        unsigned long long old = *(volatile unsigned long long *)&w->best[owner];
-        const unsigned long long mine = ((unsigned long long)d2bits << 32) | (unsigned long long)(uint32_t)j;
-        while (true) {
-            const uint32_t od2 = (uint32_t)(old >> 32);
-            const int oj = (int)(uint32_t)old;
-            bool win = d2bits < od2;
-            if (!win && d2bits == od2 && oj != j)
-                win = oj < 0 || __float_as_int(__ldg(&g.nrm[j]).w) < __float_as_int(__ldg(&g.nrm[oj]).w);
-            if (!win) return;
-            const unsigned long long prev = atomicCAS(&w->best[owner], old, mine);
-            if (prev == old) return;
-            old = prev;
-        }
-    }
-
-    template <class Scratch, class Stats>
-    __device__ __forceinline__ void scan(const GridView &g, float px, float py, float pz, Scratch &S, int &nr, float &best_d2,
-                                         int &best_j, Stats &st) {
-        const unsigned full = 0xffffffffu;
-        const unsigned queued = __ballot_sync(full, nr > 0); // lanes that queued anything (the owners to walk through)
-        if (queued == 0u) return;
-        if (__popc(queued) <= kSoloScanLanes) { // a handful of stragglers: sharing their work costs more than it saves
-            scan_ranges(g, px, py, pz, S, nr, best_d2, best_j, st);
-            return;
-        }
-        const int lane = threadIdx.x & 31;
-        uint32_t cnt = 0;
-        for (int r = 0; r < nr; ++r) cnt += S.range(r).y;
-        uint32_t incl = cnt; // inclusive prefix sum of the item counts over the lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(full, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t T = __shfl_sync(full, incl, 31);
-        w->obase[lane] = incl - cnt;
-        w->nr[lane] = (uint32_t)nr;
-        w->qp[lane] = make_float4(px, py, pz, 0.0f);
-        w->best[lane] = ((unsigned long long)__float_as_uint(best_d2) << 32) | (unsigned long long)(uint32_t)best_j;
-        __syncwarp();
-        const uint32_t C = (T + 31u) >> 5;
-        const uint32_t s0 = (uint32_t)lane * C;
-        if (s0 < T) {
-            uint32_t n = min(C, T - s0);
-            // owner of item s0: the last lane whose base is <= s0 (lanes with nothing queued share their successor's base)
-            int owner = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (w->obase[owner + step] <= s0) owner += step;
-            uint32_t r = 0, off = w->obase[owner];
-            uint2 en = w->ent[0][owner];
-            while (off + en.y <= s0) {
-                off += en.y;
-                en = w->ent[++r][owner];
-            }
-            const float4 *cur = g.pos + en.x + (s0 - off);
-            uint32_t seg_left = en.y - (s0 - off);
-            float4 o = w->qp[owner];
-            unsigned long long key = *(volatile unsigned long long *)&w->best[owner];
-            uint32_t lbd = (uint32_t)(key >> 32);
-            int lbj = (int)(uint32_t)key;
-            bool improved = false;
-            while (true) {
-                // the part of the current range that belongs to this lane's share: one tight loop
-                const uint32_t m = min(n, seg_left);
-                n -= m, seg_left -= m;
-#pragma unroll 2
-                for (uint32_t i = 0; i < m; ++i) {
-                    const float4 q = __ldg(cur);
-                    const uint32_t bits = __float_as_uint(flann_l2(o.x, o.y, o.z, q.x, q.y, q.z));
-                    if (bits <= lbd) {
-                        const int jj = (int)(cur - g.pos);
-                        if (bits < lbd) {
-                            lbd = bits, lbj = jj, improved = true;
-                        } else if (jj != lbj &&
-                                   (lbj < 0 || __float_as_int(__ldg(&g.nrm[jj]).w) < __float_as_int(__ldg(&g.nrm[lbj]).w))) {
-                            lbj = jj, improved = true;
-                        }
-                    }
-                    ++cur;
-                }
-                if (n == 0) break;
-                // next range: of the same owner, or of the next lane that queued any
-                if (++r == w->nr[owner]) {
-                    if (improved) offer(g, owner, lbd, lbj);
-                    owner = __ffs((int)(queued & (0xfffffffeu << owner))) - 1;
-                    r = 0;
-                    o = w->qp[owner];
-                    key = *(volatile unsigned long long *)&w->best[owner];
-                    lbd = (uint32_t)(key >> 32), lbj = (int)(uint32_t)key, improved = false;
-                }
-                en = w->ent[r][owner];
-                cur = g.pos + en.x, seg_left = en.y;
-            }
-            if (improved) offer(g, owner, lbd, lbj);
-        }
-        __syncwarp();
-        const unsigned long long b = w->best[lane];
-        best_d2 = __uint_as_float((uint32_t)(b >> 32));
-        best_j = (int)(uint32_t)b;
-        nr = 0;
-        __syncwarp(); // the next round's writes to ent / qp / best must not overtake these reads
-    }
-};
-
 __device__ __forceinline__ GridView grid_of(const DeviceArrays &A, const PairConst &pc, const PairState &ps, int c, int leaf_count) {
     GridView g;
     g.table = A.hash + ps.hash_base[c];
@@ -316,10 +173,12 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
     return pc.normal_shooting && (c == MULLS_GROUND || c == MULLS_FACADE || c == MULLS_ROOF);
 }
 
+// ---- k_search: I1 + I2a of the iteration — apply the previous increment to the source (:1260), exact
+//      radius-bounded 1-NN on the hashed multi-level grid (nn_search_walk, search_core.cuh — replaces the kd-tree query
+//      of :1745), claim the target for the duplicate check. One query per thread; 48 registers, 10 blocks per SM.
 __global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                          float reseed_cells, int dfs_until) {
+                                                          int defer_from_iter, float reseed_cells) {
     if (!chunk_in_run(A)) return;
-    if (buf < 0 && A.ctl->it < dfs_until) return; // (iteration graph) this iteration is k_search_dfs's
     buf = loop_buf(A, buf);
     const ChunkDesc cd = A.it_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
@@ -334,12 +193,11 @@ __global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int b
     const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
     float4 p, n;
     load_and_advance(A, ps, buf, gi, valid, p, n);
+    if (!valid) return;
     // determine_corres needs >= 3 points on both sides (:1727-1728)
-    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) { // block-uniform
-        if (valid) {
-            A.nn_idx[gi] = -1;
-            A.nn_d2[gi] = INFINITY;
-        }
+    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) {
+        A.nn_idx[gi] = -1;
+        A.nn_d2[gi] = INFINITY;
         return;
     }
     const GridView g = grid_of(A, pc, ps, c, leaf_count);
@@ -348,332 +206,9 @@ __global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int b
     const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
     const float r2_prune = (float)max_dist_sqr * 1.0001f;
     // seeds: the previous iteration's match (a real candidate, so the box-distance pruning bites from the first
-    // cell on and the search only has to prove that nothing is closer); a stale or missing one is replaced by a
-    // short walk through p's own cells when that is closer
-    int best_j = -1;
-    float best_d2 = INFINITY;
+    // cell on and the search only has to prove that nothing is closer); a match that the last increment left far
+    // away (the big first corrections) is challenged by a fresh greedy descent
     NoStats st;
-    if (valid) {
-        const int pj = A.src_prevj[buf][gi];
-        if (pj >= 0) {
-            const float4 q = __ldg(&g.pos[pj]);
-            best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
-            best_j = pj;
-        }
-    }
-    const float rs = reseed_cells * g.h0;
-    __shared__ uint2 s_stack[kSearchStack][kIterBlock];
-    __shared__ WarpShared s_warp[kIterBlock / 32];
-    SmemScratch S{&s_warp[threadIdx.x >> 5].ent[0][threadIdx.x & 31], &s_stack[0][threadIdx.x]};
-    WarpCoop co{&s_warp[threadIdx.x >> 5]};
-    nn_search<kSearchRanges, kSearchStack>(g, valid, p.x, p.y, p.z, r2_prune, start_level0, rs * rs, best_d2, best_j, S, co, st);
-    if (!valid) return;
-    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
-    if (best_j >= 0) {
-        // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
-        atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
-    }
-    A.nn_idx[gi] = best_j;
-    A.nn_d2[gi] = best_d2;
-}
-
-// ---- k_search_dfs: the same search, one independent depth-first walk per thread (nn_search_dfs): no cooperation,
-//      no synchronisation, the tightest pruning; the warp-cooperative k_search keeps more lanes busy per instruction.
-//      Which one serves an iteration is a tunable (see DESIGN.md for the measurements behind the default).
-constexpr int kDfsRanges = 8, kDfsStack = 16;
-struct DfsScratch {
-    uint2 *base; // &s_scratch[0][threadIdx.x]
-    __device__ __forceinline__ uint2 &range(int i) { return base[i * kIterBlock]; }
-    __device__ __forceinline__ uint2 &stack(int i) { return base[(kDfsRanges + i) * kIterBlock]; }
-};
-
-__global__ void __launch_bounds__(kIterBlock, 9) k_search_dfs(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                             float reseed_cells, int defer_from_iter, int dfs_until) {
-    if (!chunk_in_run(A)) return;
-    if (buf < 0 && A.ctl->it >= dfs_until) return; // (iteration graph) this iteration is k_search's
-    buf = loop_buf(A, buf);
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
-    const PairConst &pc = A.pc[cd.pair];
-    const PairState &ps = A.ps[cd.pair];
-    if (ps.status != kRunning || A.hash_used[1]) return;
-    const int c = (int)cd.seg;
-    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
-    if ((int)cd.first >= ns) return; // block-uniform
-    if (shoots(pc, c)) return;       // block-uniform: k_search_shoot's work
-    const uint32_t local = cd.first + threadIdx.x;
-    const bool valid = (int)local < ns;
-    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
-    float4 p, n;
-    load_and_advance(A, ps, buf, gi, valid, p, n);
-    if (!valid) return;
-    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) {
-        A.nn_idx[gi] = -1;
-        A.nn_d2[gi] = INFINITY;
-        return;
-    }
-    const GridView g = grid_of(A, pc, ps, c, leaf_count);
-    const float max_distance_f = 2.5f * ps.thre;
-    const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
-    const float r2_prune = (float)max_dist_sqr * 1.0001f;
-    __shared__ uint2 s_scratch[kDfsRanges + kDfsStack][kIterBlock];
-    DfsScratch S{&s_scratch[0][threadIdx.x]};
-    NoStats st;
-    int best_j = -1;
-    float best_d2 = INFINITY;
-    {
-        const int pj = A.src_prevj[buf][gi];
-        if (pj >= 0) {
-            const float4 q = __ldg(&g.pos[pj]);
-            best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
-            best_j = pj;
-        }
-        const float rs = reseed_cells * g.h0;
-        if (best_j < 0 || best_d2 > rs * rs) {
-            uint2 leaf;
-            if (quick_locate(g, p.x, p.y, p.z, start_level0, leaf, st)) {
-                int nr = 0;
-                S.range(nr++) = leaf;
-                scan_ranges(g, p.x, p.y, p.z, S, nr, best_d2, best_j, st);
-            }
-        }
-    }
-    nn_search_dfs<kDfsRanges, kDfsStack>(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, S, st);
-    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
-    if (best_j >= 0) atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
-    A.nn_idx[gi] = best_j;
-    A.nn_d2[gi] = best_d2;
-}
-
-// ---- k_search_walk: round 1's per-thread walk (depth-first stack of (cell, box distance) in local memory, small
-//      cells examined where they are met or queued per block), on the coordinate keys of grid_key.cuh and with
-//      level-0 blocks. Kept selectable: the yardstick the other two forms are measured against on the same box.
-constexpr int kWalkStack = 48; // DFS entries: at most 7 stay behind per descended level
-constexpr int kWalkQueue = 8;  // leaves of one block whose scan is deferred to the end of its traversal
-
-__device__ __forceinline__ void walk_scan_leaf(const GridView &g, float px, float py, float pz, uint32_t start, uint32_t count,
-                                               float &best_d2, int &best_j) {
-    for (uint32_t jj = start; jj < start + count; ++jj) {
-        const float4 q = __ldg(&g.pos[jj]);
-        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-        if (d2 < best_d2) {
-            best_d2 = d2;
-            best_j = (int)jj;
-        } else if (d2 == best_d2 && best_j >= 0 && (int)jj != best_j) {
-            const int oj = __float_as_int(__ldg(&g.nrm[jj]).w);
-            const int ob = __float_as_int(__ldg(&g.nrm[best_j]).w);
-            if (oj < ob) best_j = (int)jj;
-        }
-    }
-}
-
-// walk greedily from p's own cell (first level, from `l` upwards, at which it exists) down through the nearest
-// existing child to a leaf and take its best point as the seed
-__device__ __forceinline__ void walk_greedy_seed(const GridView &g, float px, float py, float pz, int l, float &best_d2, int &best_j) {
-    const int c0x = (int)floorf((px - g.ox) * g.inv_h0);
-    const int c0y = (int)floorf((py - g.oy) * g.inv_h0);
-    const int c0z = (int)floorf((pz - g.oz) * g.inv_h0);
-    const int L = g.n_levels;
-    l = min(max(l, 1), L - 1);
-    for (int lr = l; lr < L && best_j < 0; ++lr) {
-        const int ncell = (1 << kCoordBits) >> lr;
-        int cx = c0x >> lr, cy = c0y >> lr, cz = c0z >> lr;
-        if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell)) break;
-        for (int lv = lr;; --lv) {
-            uint32_t start, count, cmask;
-            if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) break; // only possible at lv == lr
-            if (count <= (uint32_t)g.leaf_count || lv == 0) {
-                for (uint32_t jj = start; jj < start + count; ++jj) {
-                    const float4 q = __ldg(&g.pos[jj]);
-                    const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-                    if (d2 < best_d2) best_d2 = d2, best_j = (int)jj;
-                }
-                break;
-            }
-            const float hl = g.h0 * (float)(1 << lv);
-            const int ox = (px >= g.ox + ((float)cx + 0.5f) * hl) ? 1 : 0;
-            const int oy = (py >= g.oy + ((float)cy + 0.5f) * hl) ? 1 : 0;
-            const int oz = (pz >= g.oz + ((float)cz + 0.5f) * hl) ? 1 : 0;
-            int ch = ox | (oy << 1) | (oz << 2);
-            if (!((cmask >> ch) & 1u)) ch = __ffs((int)cmask) - 1; // any existing child still yields a valid seed
-            if (ch < 0) break;
-            cx = 2 * cx + (ch & 1), cy = 2 * cy + ((ch >> 1) & 1), cz = 2 * cz + (ch >> 2);
-        }
-    }
-}
-
-__device__ __forceinline__ float walk_axis_dist(float o, float H, int x, float p, float margin) {
-    const float lo = o + (float)x * H - margin, hi = o + (float)(x + 1) * H + margin;
-    return fmaxf(0.0f, fmaxf(lo - p, p - hi));
-}
-
-// stack storage of the walk: thread-local arrays (local memory, L1-cached) or shared memory interleaved by thread
-struct WalkStackLocal {
-    uint32_t cell[kWalkStack], meta[kWalkStack];
-    float d2[kWalkStack];
-    __device__ __forceinline__ void put(int i, uint32_t c, uint32_t m, float d) { cell[i] = c, meta[i] = m, d2[i] = d; }
-    __device__ __forceinline__ float dist(int i) const { return d2[i]; }
-    __device__ __forceinline__ void get(int i, uint32_t &c, uint32_t &m) const { c = cell[i], m = meta[i]; }
-};
-constexpr int kWalkSmemStack = 16;
-struct WalkStackSmem { // uint4-free: three word arrays, [entry][thread]
-    uint32_t *base;    // &s_walk[0][threadIdx.x]; entry i: words (3*i .. 3*i+2) * kIterBlock
-    __device__ __forceinline__ void put(int i, uint32_t c, uint32_t m, float d) {
-        base[(3 * i) * kIterBlock] = c, base[(3 * i + 1) * kIterBlock] = m, base[(3 * i + 2) * kIterBlock] = __float_as_uint(d);
-    }
-    __device__ __forceinline__ float dist(int i) const { return __uint_as_float(base[(3 * i + 2) * kIterBlock]); }
-    __device__ __forceinline__ void get(int i, uint32_t &c, uint32_t &m) const { c = base[(3 * i) * kIterBlock], m = base[(3 * i + 1) * kIterBlock]; }
-};
-
-template <class Stack, int kDepth>
-__device__ __forceinline__ void nn_search_walk(const GridView &g, float px, float py, float pz, float r2_prune, int start_level,
-                                               bool defer_scan, float &best_d2, int &best_j, Stack &stk) {
-    const float fx = (px - g.ox) * g.inv_h0, fy = (py - g.oy) * g.inv_h0, fz = (pz - g.oz) * g.inv_h0;
-    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-    const int c0x = (int)flx, c0y = (int)fly, c0z = (int)flz;
-    const int L = g.n_levels;
-    const float margin = 1e-3f * g.h0;
-    // stack entry: cell = x | y << 12 | (z & 0xff) << 24, meta = z >> 8 | level << 4, and the cell's box distance
-    uint32_t q_start[kWalkQueue], q_count[kWalkQueue];
-    int nq = 0;
-    int l = min(max(start_level, 1), L - 1);
-    if (best_j >= 0) { // seeded: the smallest level whose coverage reaches the seed (level 0: 0.998 * h0 / 2)
-        const float need = 1.001f * sqrtf(best_d2);
-        const float t = need / (0.999f * 0.5f * g.h0);
-        if (t <= 1.0f) l = (need <= 0.998f * 0.5f * g.h0) ? 0 : 1;
-        else l = ilogbf(t) + 1;
-        l = min(l, L - 1);
-    }
-    for (;; ++l) {
-        const float H = g.h0 * (float)(1 << l);
-        const int ncell = (1 << kCoordBits) >> l;
-        int xs[2], ys[2], zs[2];
-        xs[0] = c0x >> l, ys[0] = c0y >> l, zs[0] = c0z >> l;
-        if (l == 0) {
-            xs[1] = xs[0] + (((fx - flx) >= 0.5f) ? 1 : -1);
-            ys[1] = ys[0] + (((fy - fly) >= 0.5f) ? 1 : -1);
-            zs[1] = zs[0] + (((fz - flz) >= 0.5f) ? 1 : -1);
-        } else {
-            xs[1] = xs[0] + (((c0x >> (l - 1)) & 1) ? 1 : -1);
-            ys[1] = ys[0] + (((c0y >> (l - 1)) & 1) ? 1 : -1);
-            zs[1] = zs[0] + (((c0z >> (l - 1)) & 1) ? 1 : -1);
-        }
-        float ex[2], ey[2], ez[2];
-        bool vx[2], vy[2], vz[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            vx[i] = xs[i] >= 0 && xs[i] < ncell;
-            vy[i] = ys[i] >= 0 && ys[i] < ncell;
-            vz[i] = zs[i] >= 0 && zs[i] < ncell;
-            ex[i] = walk_axis_dist(g.ox, H, xs[i], px, margin);
-            ey[i] = walk_axis_dist(g.oy, H, ys[i], py, margin);
-            ez[i] = walk_axis_dist(g.oz, H, zs[i], pz, margin);
-            ex[i] *= ex[i], ey[i] *= ey[i], ez[i] *= ez[i];
-        }
-        uint32_t live = 0;
-        {
-            const float bound0 = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-                if (vx[i] && vy[j] && vz[m] && ex[i] + ey[j] + ez[m] <= bound0) live |= 1u << k;
-            }
-        }
-#pragma unroll 1
-        while (live) { // lowest bit first: k = 0 is p's own cell
-            const int k = __ffs(live) - 1;
-            live &= live - 1;
-            const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-            int sp = 0;
-            stk.put(0, cell_key_lo((uint32_t)xs[i], (uint32_t)ys[j], (uint32_t)zs[m]), ((uint32_t)zs[m] >> 8) | ((uint32_t)l << 4),
-                    ex[i] + ey[j] + ez[m]);
-            sp = 1;
-            while (sp > 0) {
-                --sp;
-                // a cell farther than the best so far (or than the radius) cannot change the result
-                if (stk.dist(sp) > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
-                uint32_t cell, meta;
-                stk.get(sp, cell, meta);
-                const int lv = (int)((meta >> 4) & 0xfu);
-                const int cx = (int)(cell & 0xfffu), cy = (int)((cell >> 12) & 0xfffu), cz = (int)((cell >> 24) | ((meta & 0xfu) << 8));
-                uint32_t start, count, cmask;
-                if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) continue;
-                if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kDepth) {
-                    if (defer_scan && nq < kWalkQueue) { // scanned together with the block's other leaves
-                        q_start[nq] = start;
-                        q_count[nq] = count;
-                        ++nq;
-                    } else {
-                        walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
-                    }
-                } else {
-                    const float hc = 0.5f * g.h0 * (float)(1 << lv);
-                    float ax[2], ay[2], az[2];
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        ax[b] = walk_axis_dist(g.ox, hc, 2 * cx + b, px, margin);
-                        ay[b] = walk_axis_dist(g.oy, hc, 2 * cy + b, py, margin);
-                        az[b] = walk_axis_dist(g.oz, hc, 2 * cz + b, pz, margin);
-                        ax[b] *= ax[b], ay[b] *= ay[b], az[b] *= az[b];
-                    }
-                    const int near_child = (ax[1] < ax[0] ? 1 : 0) | (ay[1] < ay[0] ? 2 : 0) | (az[1] < az[0] ? 4 : 0);
-                    const float bound = fminf(best_d2, r2_prune) * 1.0001f + 1e-12f;
-                    uint32_t pass = 0;
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                        if (ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2] <= bound) pass |= 1u << ch;
-                    pass &= cmask;
-                    if (near_child & 1) pass = ((pass & 0x55u) << 1) | ((pass & 0xaau) >> 1);
-                    if (near_child & 2) pass = ((pass & 0x33u) << 2) | ((pass & 0xccu) >> 2);
-                    if (near_child & 4) pass = ((pass & 0x0fu) << 4) | ((pass & 0xf0u) >> 4);
-                    while (pass) {
-                        const int c = 31 - __clz((int)pass);
-                        pass ^= 1u << c;
-                        const int ch = c ^ near_child;
-                        const uint32_t x2 = (uint32_t)(2 * cx + (ch & 1)), y2 = (uint32_t)(2 * cy + ((ch >> 1) & 1)), z2 = (uint32_t)(2 * cz + (ch >> 2));
-                        stk.put(sp, cell_key_lo(x2, y2, z2), (z2 >> 8) | ((uint32_t)(lv - 1) << 4), ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2]);
-                        ++sp;
-                    }
-                }
-            }
-        }
-        for (int qi = 0; qi < nq; ++qi) walk_scan_leaf(g, px, py, pz, q_start[qi], q_count[qi], best_d2, best_j);
-        nq = 0;
-        const float cover = (l == 0) ? 0.998f * 0.5f * g.h0 : 0.999f * 0.5f * H;
-        const float cover2 = cover * cover;
-        if (best_d2 <= cover2) break;
-        if (cover2 >= r2_prune) break;
-        if (l == L - 1) break;
-    }
-}
-
-template <int kMinBlocks, bool kSmem>
-__global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search_walk(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                                       int defer_from_iter, float reseed_cells) {
-    if (!chunk_in_run(A)) return;
-    buf = loop_buf(A, buf);
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
-    const PairConst &pc = A.pc[cd.pair];
-    const PairState &ps = A.ps[cd.pair];
-    if (ps.status != kRunning || A.hash_used[1]) return;
-    const int c = (int)cd.seg;
-    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
-    if ((int)cd.first >= ns) return;
-    if (shoots(pc, c)) return;
-    const uint32_t local = cd.first + threadIdx.x;
-    const bool valid = (int)local < ns;
-    const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
-    float4 p, n;
-    load_and_advance(A, ps, buf, gi, valid, p, n);
-    if (!valid) return;
-    if (!(pc.used[c] && nsg >= 3 && nt >= 3)) {
-        A.nn_idx[gi] = -1;
-        A.nn_d2[gi] = INFINITY;
-        return;
-    }
-    const GridView g = grid_of(A, pc, ps, c, leaf_count);
-    const float max_distance_f = 2.5f * ps.thre;
-    const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
-    const float r2_prune = (float)max_dist_sqr * 1.0001f;
     int best_j = -1;
     float best_d2 = INFINITY;
     const int pj = A.src_prevj[buf][gi];
@@ -683,24 +218,21 @@ __global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search_walk(DeviceAr
         best_j = pj;
     }
     {
-        const float rs = reseed_cells * g.h0; // a match that the last increment left far away is challenged by a fresh seed
+        const float rs = reseed_cells * g.h0;
         if (best_j < 0 || best_d2 > rs * rs) {
             float d2 = INFINITY;
             int j = -1;
-            walk_greedy_seed(g, p.x, p.y, p.z, start_level0, d2, j);
+            walk_greedy_seed(g, p.x, p.y, p.z, start_level0, d2, j, st);
             if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
         }
     }
-    if (kSmem) {
-        __shared__ uint32_t s_walk[3 * kWalkSmemStack][kIterBlock];
-        WalkStackSmem stk{&s_walk[0][threadIdx.x]};
-        nn_search_walk<WalkStackSmem, kWalkSmemStack>(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, stk);
-    } else {
-        WalkStackLocal stk;
-        nn_search_walk<WalkStackLocal, kWalkStack>(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, stk);
-    }
+    // queueing a block's small cells pays once the seeds are good (the big first corrections have been applied)
+    nn_search_walk(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, st);
     if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
-    if (best_j >= 0) atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
+    if (best_j >= 0) {
+        // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
+        atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
+    }
     A.nn_idx[gi] = best_j;
     A.nn_d2[gi] = best_d2;
 }
@@ -756,15 +288,6 @@ __global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int
 }
 
 // ---- k_resolve ---------------------------------------------------------------------------------
-// kFused: the body runs inside k_finish, where data produced by OTHER blocks of the SAME launch is read — such loads
-// bypass L1 (ld.global.cg): a line cached by an earlier block of this SM may predate the producer's store.
-template <bool kFused, typename T>
-__device__ __forceinline__ T ld_x(const T *p) {
-    if (kFused) return __ldcg(p);
-    return *p;
-}
-
-template <bool kFused>
 __device__ __forceinline__ void resolve_body(DeviceArrays &A, int buf, uint32_t chunk) {
     const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
@@ -822,7 +345,7 @@ __device__ __forceinline__ void resolve_body(DeviceArrays &A, int buf, uint32_t 
     }
 }
 __global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) {
-    if (chunk_in_run(A)) resolve_body<false>(A, loop_buf(A, buf), blockIdx.x);
+    if (chunk_in_run(A)) resolve_body(A, loop_buf(A, buf), blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1127,7 +650,6 @@ __device__ __noinline__ void solve_and_advance(DeviceArrays &A, uint32_t pair, c
 }
 
 // ---- k_accumulate ------------------------------------------------------------------------------
-template <bool kFused>
 __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32_t chunk) {
     const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
@@ -1154,7 +676,7 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     {
         uint32_t acc = 0;
         const uint32_t first_chunk = pc.class_chunk_begin[c];
-        for (uint32_t b = first_chunk + threadIdx.x; b < chunk; b += kIterBlock) acc += ld_x<kFused>(&A.blk_kept[b]);
+        for (uint32_t b = first_chunk + threadIdx.x; b < chunk; b += kIterBlock) acc += A.blk_kept[b];
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) s_off[warp] = acc;
         __syncthreads();
@@ -1167,7 +689,7 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     }
     if (valid) {
         gi = pc.src_base[c] + local;
-        fl = ld_x<kFused>(&A.flags[gi]);
+        fl = A.flags[gi];
     }
     kept = (fl & 1) != 0, pass = (fl & 2) != 0;
     const unsigned kb = __ballot_sync(0xffffffffu, kept);
@@ -1201,7 +723,7 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     }
     uint32_t n_corr[kNumClasses]; // complete since every k_resolve block of the pair has finished
 #pragma unroll
-    for (int k = 0; k < kNumClasses; ++k) n_corr[k] = ld_x<kFused>(&ps.n_corr[k]);
+    for (int k = 0; k < kNumClasses; ++k) n_corr[k] = ps.n_corr[k];
     float ratio_unused;
     const bool few = too_few(pc, ps, n_corr, ratio_unused);
     if (pass && !few) {
@@ -1251,13 +773,12 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     }
 }
 __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) {
-    if (chunk_in_run(A)) accumulate_body<false>(A, loop_buf(A, buf), blockIdx.x);
+    if (chunk_in_run(A)) accumulate_body(A, loop_buf(A, buf), blockIdx.x);
 }
 
 // ---- solve: one block per pair, after every k_accumulate block of the pair. Sums the per-chunk partials of every
 //      class in chunk order (fixed order => bit-reproducible), then one thread solves and advances the pair state.
 //      Any block size that is a multiple of 32: the warps take the classes in turn.
-template <bool kFused>
 __device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pair) {
     const PairConst &pc = A.pc[pair];
     PairState &ps = A.ps[pair];
@@ -1277,20 +798,20 @@ __device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pa
         if (lane < 27) {
             uint32_t b = b0;
             for (; b + 4 <= b1; b += 4) {
-                a0 += ld_x<kFused>(&A.partials[(size_t)(b + 0) * kTerms + lane]);
-                a1 += ld_x<kFused>(&A.partials[(size_t)(b + 1) * kTerms + lane]);
-                a2 += ld_x<kFused>(&A.partials[(size_t)(b + 2) * kTerms + lane]);
-                a3 += ld_x<kFused>(&A.partials[(size_t)(b + 3) * kTerms + lane]);
+                a0 += A.partials[(size_t)(b + 0) * kTerms + lane];
+                a1 += A.partials[(size_t)(b + 1) * kTerms + lane];
+                a2 += A.partials[(size_t)(b + 2) * kTerms + lane];
+                a3 += A.partials[(size_t)(b + 3) * kTerms + lane];
             }
-            for (; b < b1; ++b) a0 += ld_x<kFused>(&A.partials[(size_t)b * kTerms + lane]);
+            for (; b < b1; ++b) a0 += A.partials[(size_t)b * kTerms + lane];
         }
         if (lane < kTerms) s_S[cc][lane] = (lane < 27) ? ((a0 + a1) + (a2 + a3)) : 0.0;
         uint32_t acc = 0; // kept sources of the class = its new size
-        for (uint32_t b = b0 + lane; b < b1; b += 32) acc += ld_x<kFused>(&A.blk_kept[b]);
+        for (uint32_t b = b0 + lane; b < b1; b += 32) acc += A.blk_kept[b];
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) {
             s_newn[cc] = (int)acc;
-            s_ncorr[cc] = ld_x<kFused>(&ps.n_corr[cc]);
+            s_ncorr[cc] = ps.n_corr[cc];
         }
     }
     __syncthreads();
@@ -1325,7 +846,7 @@ constexpr int kSolveThreads = kNumClasses * 32; // one warp per feature class
 __global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf, unsigned long long loop_handle) {
     LoopCtl &ctl = *A.ctl;
     if (blockIdx.x >= (unsigned)ctl.n_pairs) return;
-    solve_body<false>(A, loop_buf(A, buf), blockIdx.x);
+    solve_body(A, loop_buf(A, buf), blockIdx.x);
     if (loop_handle == 0ull) return;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1338,67 +859,6 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf
             const bool again = *(volatile int *)A.running > 0 && it < ctl.max_iter;
             cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, again ? 1u : 0u);
         }
-    }
-}
-
-// ---- k_finish: everything of one ICP iteration after the search, in ONE launch (2 x chunks blocks). Blocks take
-//      tickets: the first `n_chunks` tickets resolve a chunk (duplicate check, rejectors, counts), the next `n_chunks`
-//      accumulate a chunk — after waiting for every resolve block of THEIR PAIR (the class weights and the
-//      compaction offsets need the pair's complete counts) — and the block that finishes a pair's last chunk solves
-//      its 6x6 system and advances its state. A waiting block only ever waits for tickets handed out BEFORE its own,
-//      i.e. for blocks that are already running and never wait themselves: no deadlock, whatever the residency.
-//      Pairs progress independently: one pair's accumulation overlaps another's resolution.
-struct FinishSync {
-    unsigned ticket, done, stuck, _pad;
-};
-__global__ void __launch_bounds__(kIterBlock) k_finish(DeviceArrays A, int buf, uint32_t n_chunks) {
-    __shared__ uint32_t s_ticket;
-    __shared__ int s_last;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&A.fsync->ticket, 1u);
-    __syncthreads();
-    const uint32_t t = s_ticket;
-    const bool second = t >= n_chunks;
-    const uint32_t chunk = second ? t - n_chunks : t;
-    const uint32_t pair = A.it_chunks[chunk].pair;
-    const uint32_t pair_chunks = A.pc[pair].chunk_end - A.pc[pair].chunk_begin;
-    unsigned *resolved = &A.pair_sync[2 * pair], *accumulated = &A.pair_sync[2 * pair + 1];
-    if (!second) {
-        resolve_body<true>(A, buf, chunk);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(resolved, 1u);
-        }
-    } else {
-        if (threadIdx.x == 0) {
-            unsigned spins = 0;
-            while (*(volatile unsigned *)resolved < pair_chunks) {
-                __nanosleep(64);
-                if (++spins > (1u << 24)) { // (cannot happen; never hang the device on a logic error)
-                    atomicExch(&A.fsync->stuck, 1u);
-                    break;
-                }
-            }
-            __threadfence();
-        }
-        __syncthreads();
-        accumulate_body<true>(A, buf, chunk);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            s_last = atomicAdd(accumulated, 1u) == pair_chunks - 1;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            solve_body<true>(A, buf, pair);
-            if (threadIdx.x == 0) *resolved = 0, *accumulated = 0; // every block of the pair is past its wait
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&A.fsync->done, 1u) == 2 * n_chunks - 1) A.fsync->ticket = 0, A.fsync->done = 0;
     }
 }
 
@@ -1655,9 +1115,9 @@ __global__ void __launch_bounds__(kIterBlock) k_nn_query(DeviceArrays A, int cls
         const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
         const float rmax = 2.5f * pc.thre_unit;
         const float r2 = rmax * rmax * 1.0001f;
-        walk_greedy_seed(g, px, py, pz, start_level0, best_d2, best_j);
-        WalkStackLocal stk;
-        nn_search_walk<WalkStackLocal, kWalkStack>(g, px, py, pz, r2, start_level0, false, best_d2, best_j, stk);
+        NoStats st;
+        walk_greedy_seed(g, px, py, pz, start_level0, best_d2, best_j, st);
+        nn_search_walk(g, px, py, pz, r2, start_level0, false, best_d2, best_j, st);
         if (best_j >= 0 && !((double)best_d2 <= (double)rmax * (double)rmax)) best_j = -1;
         if (best_j >= 0) best_j = __float_as_int(__ldg(&g.nrm[best_j]).w);
     }

@@ -13,6 +13,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <dlfcn.h>
+#include <mutex>
+
 #include "device_types.cuh"
 #include "host_pack.h"
 #include "kernels_ingest.cuh"
@@ -27,6 +30,48 @@ using namespace mulls;
 namespace {
 std::string g_create_error;
 }
+
+// ---- NCCL without a link-time dependency: the five entry points used, resolved from libnccl.so.2 on first use ----
+namespace {
+struct ncclUniqueIdBytes {
+    char internal[128]; // nccl.h: ncclUniqueId
+};
+struct NcclApi {
+    typedef int (*get_id_t)(void *);
+    typedef int (*init_rank_t)(void **, int, ncclUniqueIdBytes, int);
+    typedef int (*all_reduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*destroy_t)(void *);
+    typedef const char *(*err_t)(int);
+    get_id_t get_id = nullptr;
+    init_rank_t init_rank = nullptr;
+    all_reduce_t all_reduce = nullptr;
+    destroy_t destroy = nullptr;
+    err_t err = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.get_id = (NcclApi::get_id_t)dlsym(h, "ncclGetUniqueId");
+        api.init_rank = (NcclApi::init_rank_t)dlsym(h, "ncclCommInitRank");
+        api.all_reduce = (NcclApi::all_reduce_t)dlsym(h, "ncclAllReduce");
+        api.destroy = (NcclApi::destroy_t)dlsym(h, "ncclCommDestroy");
+        api.err = (NcclApi::err_t)dlsym(h, "ncclGetErrorString");
+        api.ok = api.get_id && api.init_rank && api.all_reduce && api.destroy;
+    });
+    return api;
+}
+// the all-reduce hook of run_impl over NCCL: user = the communicator (nccl.h: ncclInt32 = 2, ncclFloat64 = 8; ncclSum = 0, ncclMin = 3)
+int nccl_allreduce_hook(void *user, void *buf, size_t count, int dtype, int op, void *stream) {
+    if (count == 0) return 0;
+    return nccl_api().all_reduce(buf, buf, count, dtype == 0 ? 8 : 2, op == 0 ? 0 : 3, user, (cudaStream_t)stream);
+}
+} // namespace
+
 
 struct mulls_map;
 
@@ -49,6 +94,7 @@ struct mulls_ctx {
     size_t n_pairs = 0, n_in = 0, n_src_total = 0, n_tgt_total = 0;
     int max_iter_max = 0;
     bool uploaded = false;
+    void *nccl_comm = nullptr; // ncclComm_t created by mulls_nccl_init (destroyed with the context)
     bool any_keep_less = false;
     bool grid_valid = false; // pair 0's sorted target slices and grid are those of the last registration (mulls_nn_query)
     // tunables
@@ -62,16 +108,9 @@ struct mulls_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     int graph_key[6] = {-1, -1, -1, -1, -1, -1}; // the tunables baked into the kernel nodes
     LoopCtl *h_ctl = nullptr;            // pinned staging of the control block
-    // which search kernel serves an iteration: iterations < dfs_until run k_search_dfs (per-thread depth first), the rest the
-    // warp-cooperative k_search; dfs_defer_from: k_search_dfs queues a block's small cells from this iteration on
-    int walk_reseed_x4 = 1 << 20; // (quarter level-0 cells) a previous match farther than this is challenged by a fresh greedy seed
-    int search_walk = 0;     // 1: every iteration runs k_search_walk (round 1's per-thread walk; host launch loop only)
-    int dfs_until = 2;
-    int dfs_defer_from = 2;
-    int fused_finish = 0;    // 1: k_finish (one launch after the search) instead of k_resolve + k_accumulate + k_solve —
-                             // measured slower at batch scale (per-block ticket / fence latency), see DESIGN.md
+    int defer_from_iter = 3; // k_search queues the small cells of a block (one scan loop per block) from this iteration on
     int hash_slack = 4;      // table capacity >= hash_slack x cells (power of two): load factor <= 1/hash_slack
-    int reseed_cells_x4 = 8; // a seed farther than this many quarter level-0 cells is challenged by a quick descent
+    int reseed_cells_x4 = 16; // a previous match farther than this many quarter level-0 cells is challenged by a greedy descent
     bool any_normal_shooting = false;
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h):
@@ -178,6 +217,7 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_running) cudaFreeHost(ctx->h_running);
+    if (ctx->nccl_comm && nccl_api().ok) nccl_api().destroy(ctx->nccl_comm);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->graph) cudaGraphDestroy(ctx->graph);
@@ -261,8 +301,6 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
         ALLOC(A.hash, pool);
     }
     ALLOC(A.hash_used, 2);
-    ALLOC(A.pair_sync, 2 * max_pairs);
-    ALLOC(A.fsync, 1);
     ALLOC(A.ctl, 1);
     ALLOC(A.blk_kept, ctx->cap_it_chunks);
     ALLOC(A.partials, ctx->cap_it_chunks * kTerms);
@@ -385,13 +423,9 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     if (n == "start_level") ctx->start_level0 = value;
     else if (n == "leaf_count") ctx->leaf_count = value;
     else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
+    else if (n == "defer_from_iter") ctx->defer_from_iter = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
-    else if (n == "fused_finish") ctx->fused_finish = value;
     else if (n == "use_graph") ctx->use_graph = value;
-    else if (n == "dfs_until") ctx->dfs_until = value;
-    else if (n == "search_walk") ctx->search_walk = value;
-    else if (n == "walk_reseed_x4") ctx->walk_reseed_x4 = value;
-    else if (n == "dfs_defer_from") ctx->dfs_defer_from = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
     else if (n == "host_pack") ctx->host_pack = value;
     else if (n == "poll_pause") ctx->poll_pause = value;
@@ -790,7 +824,7 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
 // context with grids sized for its capacity; what a run needs to know (chunk / pair counts, trace switch, loop counter)
 // is read from LoopCtl in device memory. k_solve's last block sets the loop condition: no host polling, one launch.
 static int build_iteration_graph(mulls_ctx *ctx) {
-    const int key[6] = {ctx->start_level0, ctx->leaf_count, ctx->reseed_cells_x4, ctx->any_normal_shooting ? 1 : 0, ctx->dfs_until, ctx->dfs_defer_from};
+    const int key[6] = {ctx->start_level0, ctx->leaf_count, ctx->reseed_cells_x4, ctx->any_normal_shooting ? 1 : 0, ctx->defer_from_iter, 0};
     if (ctx->graph_exec && std::memcmp(key, ctx->graph_key, sizeof(key)) == 0) return MULLS_OK;
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
     if (ctx->graph) cudaGraphDestroy(ctx->graph), ctx->graph = nullptr;
@@ -808,11 +842,8 @@ static int build_iteration_graph(mulls_ctx *ctx) {
     CK(cudaGraphAddNode(&while_node, ctx->graph, nullptr, 0, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    if (ctx->dfs_until > 0)
-        k_search_dfs<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
-                                                         ctx->dfs_defer_from, ctx->dfs_until);
-    k_search<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
-                                                 ctx->dfs_until);
+    k_search<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter,
+                                                 0.25f * (float)ctx->reseed_cells_x4);
     if (ctx->any_normal_shooting) k_search_shoot<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count);
     k_resolve<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
     k_accumulate<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
@@ -857,13 +888,11 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         c.n_it_chunks = (int)n_itc, c.n_pairs = np, c.trace_on = trace ? 1 : 0, c.max_iter = ctx->max_iter_max;
         CK(cudaMemcpyAsync(A.ctl, ctx->h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
     }
-    const bool graphed = !hook && ctx->use_graph && !ctx->fused_finish;
+    const bool graphed = !hook && ctx->use_graph;
     if (graphed) {
         const int rc = build_iteration_graph(ctx);
         if (rc != MULLS_OK) return rc;
     }
-    CK(cudaMemsetAsync(A.pair_sync, 0, 2 * ctx->max_pairs * sizeof(unsigned), st));
-    CK(cudaMemsetAsync(A.fsync, 0, sizeof(FinishSync), st));
     CK(cudaEventRecord(ctx->ev_ingest, st));
     int n_search_ev = 0;
     if (graphed) {
@@ -888,19 +917,8 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            if (ctx->search_walk) {
-                const float rs = 0.25f * (float)ctx->walk_reseed_x4;
-                if (ctx->search_walk == 1) k_search_walk<10, false><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
-                else if (ctx->search_walk == 2) k_search_walk<12, false><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
-                else if (ctx->search_walk == 3) k_search_walk<10, true><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
-                else k_search_walk<8, false><<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->dfs_defer_from, rs);
-            }
-            else if (it < ctx->dfs_until)
-                k_search_dfs<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
-                                                            ctx->dfs_defer_from, ctx->dfs_until);
-            else
-                k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, 0.25f * (float)ctx->reseed_cells_x4,
-                                                        ctx->dfs_until);
+            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter,
+                                                    0.25f * (float)ctx->reseed_cells_x4);
             if (ctx->any_normal_shooting) {
                 k_search_shoot<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
                 ++launches;
@@ -911,13 +929,6 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
                     ctx->err = "all-reduce callback failed";
                     return MULLS_E_COMM;
                 }
-            }
-            if (!hook && ctx->fused_finish) { // resolve + accumulate + solve of every pair in one launch (tickets, see k_finish)
-                k_finish<<<2 * n_itc, kIterBlock, 0, st>>>(A, buf, n_itc);
-                CK(cudaEventRecord(ctx->ev_done[it], st));
-                launches += 2;
-                n_search_ev = it + 1;
-                continue;
             }
             k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
             if (hook) { // exchange 2: correspondence counts (w_ground, -2 test) and surviving source counts
@@ -968,7 +979,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
     CK(cudaEventRecord(ctx->ev_end, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    if (graphed) launches += (uint64_t)ctx->h_ctl->it * (4u + (ctx->any_normal_shooting ? 1u : 0u) + (ctx->dfs_until > 0 ? 1u : 0u)) + 3u;
+    if (graphed) launches += (uint64_t)ctx->h_ctl->it * (4u + (ctx->any_normal_shooting ? 1u : 0u)) + 3u;
     if (ctx->h_flags[1]) {
         ctx->err = "hash pool exhausted (target clouds produce more grid cells than the context reserves)";
         return MULLS_E_CAPACITY;
@@ -1067,6 +1078,56 @@ int mulls_icp_run(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
                   const mulls_icp_params *params, const double init_guess[16], mulls_icp_result *out,
                   mulls_icp_trace *trace) {
     return mulls_icp_run_batch(ctx, 1, tgt, src, params, init_guess, out, trace);
+}
+
+} // extern "C"
+
+extern "C" {
+
+int mulls_nccl_unique_id(char id[MULLS_NCCL_ID_BYTES]) {
+    if (!id) return MULLS_E_ARG;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return MULLS_E_COMM;
+    ncclUniqueIdBytes u;
+    if (api.get_id(&u) != 0) return MULLS_E_COMM;
+    std::memcpy(id, u.internal, MULLS_NCCL_ID_BYTES);
+    return MULLS_OK;
+}
+
+int mulls_nccl_init(mulls_ctx *ctx, int rank, int world, const char id[MULLS_NCCL_ID_BYTES]) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return MULLS_E_ARG;
+    if (!ctx->lanes.empty()) ctx = ctx->lanes[0];
+    NcclApi &api = nccl_api();
+    if (!api.ok) {
+        ctx->err = "libnccl.so.2 not found (or too old)";
+        return MULLS_E_COMM;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) api.destroy(ctx->nccl_comm), ctx->nccl_comm = nullptr;
+    ncclUniqueIdBytes u;
+    std::memcpy(u.internal, id, MULLS_NCCL_ID_BYTES);
+    const int rc = api.init_rank(&ctx->nccl_comm, world, u, rank);
+    if (rc != 0) {
+        ctx->err = std::string("ncclCommInitRank: ") + (api.err ? api.err(rc) : "failed");
+        ctx->nccl_comm = nullptr;
+        return MULLS_E_COMM;
+    }
+    return MULLS_OK;
+}
+
+int mulls_icp_run_sharded_nccl(mulls_ctx *ctx, void *comm, const mulls_cloud_view tgt[MULLS_NUM_CLASSES],
+                               const mulls_cloud_view src_shard[MULLS_NUM_CLASSES], const uint32_t src_index_base[MULLS_NUM_CLASSES],
+                               const uint32_t src_global_n[MULLS_NUM_CLASSES], const mulls_icp_params *params,
+                               const double init_guess[16], mulls_icp_result *out, mulls_icp_trace *trace) {
+    if (!ctx) return MULLS_E_ARG;
+    mulls_ctx *owner = ctx->lanes.empty() ? ctx : ctx->lanes[0];
+    if (!comm) comm = owner->nccl_comm;
+    if (!comm || !nccl_api().ok) {
+        owner->err = "no NCCL communicator: call mulls_nccl_init first (or pass an ncclComm_t)";
+        return MULLS_E_COMM;
+    }
+    return mulls_icp_run_sharded(ctx, tgt, src_shard, src_index_base, src_global_n, params, init_guess, nccl_allreduce_hook, comm, out,
+                                 trace);
 }
 
 int mulls_nn_query(mulls_ctx *ctx, int cls, const float *xyz, size_t n, int32_t *idx, float *d2) {

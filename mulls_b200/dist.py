@@ -40,6 +40,31 @@ def torch_allreduce(group=None):
     return allreduce
 
 
+def nccl_unique_id() -> bytes:
+    """mulls_nccl_unique_id: 128 bytes to be shipped from rank 0 to every rank (see nccl_init_from_torch)."""
+    import ctypes as C
+
+    from . import abi
+
+    buf = C.create_string_buffer(128)
+    rc = abi.load_library().mulls_nccl_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"mulls_nccl_unique_id failed ({rc}): libnccl.so.2 not available")
+    return buf.raw
+
+
+def nccl_init_from_torch(ctx, group=None):
+    """Give `ctx` its own NCCL communicator over the ranks of a torch.distributed group: rank 0 creates the id, the
+    group's broadcast ships it (any backend), every rank calls mulls_nccl_init."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0, group=group)
+    ctx.nccl_init(rank, world, uid[0])
+
+
 def shard_sources(src_clouds, rank: int, world: int):
     """Contiguous index ranges per class (keeps "first in source order" meaningful).
     Returns (shards, index_base, global_n)."""

@@ -190,6 +190,23 @@ class Context:
             C.POINTER(C.c_double)), cb, None, C.byref(res), C.byref(tr) if tr is not None else None))
         return abi.result_to_dict(res), (abi.trace_to_dict(tr) if tr is not None else None)
 
+    def nccl_init(self, rank: int, world: int, unique_id: bytes):
+        """mulls_nccl_init: collective; `unique_id` = the 128 bytes rank 0 got from mulls_b200.dist.nccl_unique_id()."""
+        self._check(self.lib.mulls_nccl_init(self.handle, int(rank), int(world), C.c_char_p(bytes(unique_id))))
+
+    def run_sharded_nccl(self, pair, src_index_base, src_global_n, want_trace: bool = False):
+        """mulls_icp_run_sharded_nccl on the context's own communicator (nccl_init): the per-iteration exchanges are
+        ncclAllReduce calls inside the library — nothing interpreted in the loop."""
+        tv, sv, pa, init, keep = self._pack([pair])
+        base = (C.c_uint32 * 6)(*[int(v) for v in src_index_base])
+        glob = (C.c_uint32 * 6)(*[int(v) for v in src_global_n])
+        res = abi.IcpResult()
+        tr = abi.IcpTrace() if want_trace else None
+        self._check(self.lib.mulls_icp_run_sharded_nccl(self.handle, None, tv, sv, base, glob, pa,
+                                                        init.ctypes.data_as(C.POINTER(C.c_double)), C.byref(res),
+                                                        C.byref(tr) if tr is not None else None))
+        return abi.result_to_dict(res), (abi.trace_to_dict(tr) if tr is not None else None)
+
     def nn_query(self, cls: int, xyz: np.ndarray):
         """mulls_nn_query: what block1->tree_*->nearestKSearch(point, 1) answers in the reference, on the sorted target
         slices the last registration left in HBM. Returns (index into the caller's class cloud or -1, squared distance)."""

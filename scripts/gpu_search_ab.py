@@ -1,4 +1,4 @@
-"""A/B of the search kernels in ONE process on ONE box: the same resident batch, per-iteration device time of the
+"""A/B of search tunables in ONE process on ONE box: the same resident batch, per-iteration device time of the
 search launch (host launch loop, CUDA events), for a list of tunable settings.
     python scripts/gpu_search_ab.py <pairs> <config> "dfs_until=0" "dfs_until=20" "dfs_until=2" ..."""
 import os, sys

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from mulls_b200 import synth
-from mulls_b200.dist import shard_sources, torch_allreduce
+from mulls_b200.dist import nccl_init_from_torch, shard_sources
 from mulls_b200.registration import Context
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c5"
@@ -22,16 +22,16 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pair = synth.make_pair(1000, cfg)
 shards, base, glob = shard_sources(pair["src"], rank, world)
 ctx = Context(local, 1, max(1, sum(len(s) for s in shards)), sum(len(t) for t in pair["tgt"]))
-hook = torch_allreduce()
+nccl_init_from_torch(ctx)  # the library's own communicator: the exchanges are ncclAllReduce calls inside the C++ loop
 for _ in range(2):
-    res, tr = ctx.run_sharded(dict(pair, src=shards), base, glob, hook, want_trace=True)
+    res, tr = ctx.run_sharded_nccl(dict(pair, src=shards), base, glob, want_trace=True)
 dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 n = 5
 ms = 0.0
 for _ in range(n):
-    res, tr = ctx.run_sharded(dict(pair, src=shards), base, glob, hook, want_trace=True)
+    res, tr = ctx.run_sharded_nccl(dict(pair, src=shards), base, glob, want_trace=True)
     ms += ctx.stats()["ms_total"]
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / n

@@ -1,4 +1,4 @@
-"""Study (CPU): work per query of the product's search (search_core.cuh, host instantiation) on the synthetic C2
+"""Study (CPU): work per query of the product's search (search_core.cuh: walk_greedy_seed + nn_search_walk, host instantiation) on the synthetic C2
 pair, iteration by iteration, with exactness checked against the oracle's kd-tree NN. The query sets of the
 iterations are emulated: sources moved by the oracle's per-iteration increments, shrunk by the duplicate check.
     python scripts/studies/search_stats.py [seed] [config]
@@ -46,17 +46,15 @@ def trans_a(x):
     return T
 
 
-SHARE = 0
-MODE = 0
+DEFER_FROM = 3
 
 
 def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     config = sys.argv[2] if len(sys.argv) > 2 else "c2"
     leaf = int(sys.argv[3]) if len(sys.argv) > 3 else 32
-    global SHARE, MODE
-    MODE = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-    SHARE = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    global DEFER_FROM
+    DEFER_FROM = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     lib = load_harness()
     pair = synth.make_pair(seed, config)
     res, tr = oracle.icp_run(pair["tgt"], pair["src"], pair["params"], pair["init_guess"], threads=8)
@@ -100,12 +98,11 @@ def main():
             out_idx = np.empty(m, np.int32)
             out_d2 = np.empty(m, np.float32)
             stats = np.zeros(12, np.uint64)
-            stats[11] = SHARE
-            stats[10] = MODE
+            stats[10] = 1 if it >= DEFER_FROM else 0
             epq = np.zeros(m, np.uint32)
             qc = np.ascontiguousarray(q)
             t0 = time.time()
-            lib.sh_search(G, qc.ctypes.data, seeds.ctypes.data if seeds is not None else None, m, float(r2), 5, 0.0625,
+            lib.sh_search(G, qc.ctypes.data, seeds.ctypes.data if seeds is not None else None, m, float(r2), 5, 0.25,
                           out_idx.ctypes.data, out_d2.ctypes.data, stats.ctypes.data, epq.ctypes.data)
             dt = time.time() - t0
             # exactness vs the oracle's kd-tree
@@ -121,8 +118,8 @@ def main():
             a[9] += m
             a[10] = max(a[10], float(stats[8]))
             a[11] += bad + badd
-            print(f"  it{it}: m={m} probes/q={(stats[0] + stats[1]) / m:.2f} (child {stats[1] / m:.2f}) evals/q={stats[2] / m:.1f} "
-                  f"expands/q={stats[3] / m:.2f} levels/q={stats[4] / m:.2f} flushes/q={stats[5] / m:.2f} "
+            print(f"  it{it}: m={m} probes/q={stats[0] / m:.2f} evals/q={stats[2] / m:.1f} "
+                  f"expands/q={stats[3] / m:.2f} levels/q={stats[4] / m:.2f} "
                   f"seed probes/q={stats[6] / m:.2f} seed evals/q={stats[7] / m:.1f} max evals={stats[8]} "
                   f"p50/p90/p99 evals={np.percentile(epq, 50):.0f}/{np.percentile(epq, 90):.0f}/{np.percentile(epq, 99):.0f} "
                   f"mismatch idx={bad} d2={badd} [{dt * 1e6 / m:.2f} us/q host]")
@@ -145,7 +142,7 @@ def main():
     print("== totals per iteration (all classes) ==")
     for (it,), a in sorted(tot.items()):
         m = a[9]
-        print(f"it{it}: queries={int(m)} probes/q={(a[0] + a[1]) / m:.2f} evals/q={a[2] / m:.1f} expands/q={a[3] / m:.2f} "
+        print(f"it{it}: queries={int(m)} probes/q={a[0] / m:.2f} evals/q={a[2] / m:.1f} expands/q={a[3] / m:.2f} "
               f"levels/q={a[4] / m:.2f} seed probes/q={a[6] / m:.2f} seed evals/q={a[7] / m:.1f} mismatches={int(a[11])}")
 
 

@@ -24,22 +24,13 @@ struct HostGrid {
 };
 
 struct Counters {
-    uint64_t probes_block = 0, probes_child = 0, evals = 0, expands = 0, levels = 0, flushes = 0, seed_probes = 0,
-             seed_evals = 0, max_evals_query = 0, cur_evals = 0;
-    void probe(int kind) { (kind ? probes_child : probes_block)++; }
+    uint64_t probes = 0, evals = 0, expands = 0, levels = 0, seed_probes = 0, seed_evals = 0, max_evals_query = 0, cur_evals = 0;
+    void probe() { probes++; }
     void eval(int n) { evals += n, cur_evals += n; }
     void expand() { expands++; }
     void level() { levels++; }
-    void flush() { flushes++; }
     void seed_probe() { seed_probes++; }
     void seed_eval(int n) { seed_evals += n; }
-};
-
-template <int kRanges, int kStack>
-struct HostScratch {
-    uint2 r[kRanges], s[kStack];
-    uint2 &range(int i) { return r[i]; }
-    uint2 &stack(int i) { return s[i]; }
 };
 
 void insert(HostGrid &G, uint32_t x, uint32_t y, uint32_t z, int level, uint32_t start, uint32_t count, uint32_t cmask) {
@@ -123,90 +114,44 @@ void sh_grid_info(void *h, uint64_t *out /*[3]: cells, table capacity, sum of in
 }
 
 // q: m x 3 floats. seed: original target index of a candidate or -1 (may be null). Results as ORIGINAL target indices.
-// reseed_d2: a seeded query whose seed is farther than this also tries the quick seed (negative: never).
+// reseed_d2: a seeded query whose seed is farther than this also tries the greedy seed (negative: never) — the seeding
+// rule of k_search. stats[10] on entry: 1 = queue the small cells of a block (k_search from iteration defer_from_iter on).
 int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_prune, int start_level, float reseed_d2,
               int *out_idx, float *out_d2, uint64_t *stats /*[12]*/, uint32_t *evals_per_query /*[m] or null*/) {
     HostGrid *G = (HostGrid *)h;
     const GridView &g = G->g;
     Counters C;
-    const bool share = stats[11] != 0; // study switch: warps of 32 consecutive queries exchange their seeds first
-    for (uint32_t base = 0; base < m; base += 32) {
-        const uint32_t nw = std::min<uint32_t>(32, m - base);
-        float sd2[32];
-        int sj[32];
-        for (uint32_t k = 0; k < nw; ++k) {
-            const uint32_t i = base + k;
-            const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
-            sd2[k] = INFINITY, sj[k] = -1;
-            if (seed && seed[i] >= 0) {
-                sj[k] = (int)G->inv[seed[i]];
-                const float4 t = g.pos[sj[k]];
-                sd2[k] = flann_l2(px, py, pz, t.x, t.y, t.z);
-            }
-            if (share && (sj[k] < 0 || (reseed_d2 >= 0.0f && sd2[k] > reseed_d2))) { // seed phase of nn_search, done here
-                uint2 leaf;
-                if (quick_locate(g, px, py, pz, start_level, leaf, C)) {
-                    C.eval((int)leaf.y);
-                    for (uint32_t jj = leaf.x; jj < leaf.x + leaf.y; ++jj) {
-                        const float4 t = g.pos[jj];
-                        consider(g, flann_l2(px, py, pz, t.x, t.y, t.z), jj, sd2[k], sj[k]);
-                    }
-                }
-            }
+    const bool defer = stats[10] != 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+        float best_d2 = INFINITY;
+        int best_j = -1;
+        if (seed && seed[i] >= 0) {
+            best_j = (int)G->inv[seed[i]];
+            const float4 t = g.pos[best_j];
+            best_d2 = flann_l2(px, py, pz, t.x, t.y, t.z);
         }
-        if (share) {
-            float nd2[32];
-            int nj[32];
-            for (uint32_t k = 0; k < nw; ++k) nd2[k] = sd2[k], nj[k] = sj[k];
-            for (uint32_t k = 0; k < nw; ++k) {
-                const uint32_t i = base + k;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t k2 = k ^ (uint32_t)o;
-                    if (k2 >= nw || sj[k2] < 0) continue;
-                    const float4 t = g.pos[sj[k2]];
-                    C.eval(1);
-                    consider(g, flann_l2(q[3 * i], q[3 * i + 1], q[3 * i + 2], t.x, t.y, t.z), (uint32_t)sj[k2], nd2[k], nj[k]);
-                }
-            }
-            for (uint32_t k = 0; k < nw; ++k) sd2[k] = nd2[k], sj[k] = nj[k];
+        if (best_j < 0 || (reseed_d2 >= 0.0f && best_d2 > reseed_d2)) {
+            float d2 = INFINITY;
+            int j = -1;
+            walk_greedy_seed(g, px, py, pz, start_level, d2, j, C);
+            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
         }
-        for (uint32_t k = 0; k < nw; ++k) {
-            const uint32_t i = base + k;
-            const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
-            float best_d2 = sd2[k];
-            int best_j = sj[k];
-            HostScratch<8, 48> S;
-            C.cur_evals = 0;
-            SoloCoop co;
-            const int mode = (int)stats[10]; // 0: rounds (nn_search), 1: depth first, 2: depth first with deferred scans
-            if (mode == 0) {
-                nn_search<8, 12>(g, true, px, py, pz, r2_prune, start_level,
-                                 share ? INFINITY : ((reseed_d2 >= 0.0f) ? reseed_d2 : INFINITY), best_d2, best_j, S, co, C);
-            } else {
-                if (!share && (best_j < 0 || (reseed_d2 >= 0.0f && best_d2 > reseed_d2))) {
-                    uint2 leaf;
-                    int nr1 = 0;
-                    if (quick_locate(g, px, py, pz, start_level, leaf, C)) {
-                        S.range(nr1++) = leaf;
-                        scan_ranges(g, px, py, pz, S, nr1, best_d2, best_j, C);
-                    }
-                }
-                nn_search_dfs<8, 48>(g, px, py, pz, r2_prune, start_level, mode == 2, best_d2, best_j, S, C);
-            }
-            C.max_evals_query = std::max(C.max_evals_query, C.cur_evals);
-            if (evals_per_query) evals_per_query[i] = (uint32_t)C.cur_evals;
-            out_d2[i] = best_d2;
-            if (best_j >= 0) {
-                int oi;
-                std::memcpy(&oi, &g.nrm[best_j].w, 4);
-                out_idx[i] = oi;
-            } else {
-                out_idx[i] = -1;
-            }
+        C.cur_evals = 0;
+        nn_search_walk(g, px, py, pz, r2_prune, start_level, defer, best_d2, best_j, C);
+        C.max_evals_query = std::max(C.max_evals_query, C.cur_evals);
+        if (evals_per_query) evals_per_query[i] = (uint32_t)C.cur_evals;
+        out_d2[i] = best_d2;
+        if (best_j >= 0) {
+            int oi;
+            std::memcpy(&oi, &g.nrm[best_j].w, 4);
+            out_idx[i] = oi;
+        } else {
+            out_idx[i] = -1;
         }
     }
-    stats[0] = C.probes_block, stats[1] = C.probes_child, stats[2] = C.evals, stats[3] = C.expands, stats[4] = C.levels;
-    stats[5] = C.flushes, stats[6] = C.seed_probes, stats[7] = C.seed_evals, stats[8] = C.max_evals_query;
+    stats[0] = C.probes, stats[2] = C.evals, stats[3] = C.expands, stats[4] = C.levels;
+    stats[6] = C.seed_probes, stats[7] = C.seed_evals, stats[8] = C.max_evals_query;
     return 0;
 }
 

@@ -1,7 +1,8 @@
 """CPU checks of the product's search logic (mulls_b200/csrc/search_core.cuh, __host__ __device__): the very functions
-k_search runs on the device are instantiated on the host by tests/harness/search_host.cu (grid built there with the
-same keys / hash / entry layout as k_hash_build) and compared with a brute-force scan under the reference's total
-order (FLANN float distance, then original index) and with the oracle's kd-tree NN (cregistration.hpp:1742-1745)."""
+k_search runs on the device (walk_greedy_seed, nn_search_walk) are instantiated on the host by
+tests/harness/search_host.cu (grid built there with the same keys / hash / entry layout as k_hash_build) and compared
+with a brute-force scan under the reference's total order (FLANN float distance, then original index) and with the
+oracle's kd-tree NN (cregistration.hpp:1742-1745)."""
 import ctypes as C
 import os
 import subprocess
@@ -53,7 +54,7 @@ def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0,
     idx = np.empty(m, np.int32)
     d2 = np.empty(m, np.float32)
     stats = np.zeros(12, np.uint64)
-    stats[10] = mode  # 0: rounds (the warp-cooperative kernel's per-thread semantics), 1 / 2: depth first
+    stats[10] = mode  # 1: the small cells of a block are queued and examined together (k_search's late iterations)
     r = np.float32(radius)
     r2 = np.float32(np.float32(np.float64(r) * np.float64(r)) * np.float32(1.0001))
     sd = np.ascontiguousarray(seeds, np.int32) if seeds is not None else None
@@ -104,7 +105,7 @@ def test_random_clouds_equal_brute_force(lib, seed):
     bi, bd = brute(tgt, q)
     for radius in (3.5, 1.25, 0.3):
         for leaf in (32, 4):
-            for mode in (0, 1, 2):
+            for mode in (0, 1):
                 idx, d2 = run(lib, tgt, q, radius, leaf=leaf, mode=mode)
                 check(idx, d2, bi, bd, radius)
     # seeded: good seeds (the answer), stale seeds (random target), mixed with none
@@ -112,7 +113,7 @@ def test_random_clouds_equal_brute_force(lib, seed):
     seeds[::3] = rng.integers(0, len(tgt), len(seeds[::3]))
     seeds[1::7] = -1
     for reseed in (-1.0, 0.0625):
-        for mode in (0, 1, 2):
+        for mode in (0, 1):
             idx, d2 = run(lib, tgt, q, 3.5, seeds=seeds, reseed=reseed, mode=mode)
             check(idx, d2, bi, bd, 3.5)
 
@@ -139,7 +140,7 @@ def test_synthetic_pair_equals_oracle_kdtree(lib):
         if len(tgt) < 3 or len(src) < 3:
             continue
         oi, od = oracle.nn(tgt, src, 1e9)
-        for mode in (0, 1, 2):
+        for mode in (0, 1):
             idx, d2 = run(lib, tgt[:, :3], src[:, :3], 3.5, mode=mode)
             check(idx, d2, oi, od, 3.5)
         moved = src.copy()
