@@ -25,6 +25,7 @@ e1.record(); torch.cuda.synchronize()
 print(f"box calibration: device copy {2 * a.numel() * 10 / e0.elapsed_time(e1) / 1e6:.0f} GB/s", flush=True)
 del a, b
 ctx = Context(0, n_pairs, ns + 16, nt + 16)
+ctx.set_tunable("use_graph", 0)  # host launch loop: per-kernel CUDA events
 for k, v in tun.items():
     ctx.set_tunable(k, int(v))
 ctx.upload(pairs)
