@@ -255,15 +255,16 @@ def main():
     # several ranks share the host: keep each rank (and the library's pack workers / lane threads it spawns) on the
     # cores of its GPU's NUMA node, so that the pinned staging and the repacking stay local to the PCIe root
     affinity = "all usable cores"
-    if world > 1:
-        cpus = gpu_numa_cpus(local_rank)
-        if cpus:
-            share = sorted(cpus)
-            per_node = max(1, len([r for r in range(world) if gpu_numa_cpus(r) == cpus]))
-            k = [r for r in range(world) if gpu_numa_cpus(r) == cpus].index(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    cpus = gpu_numa_cpus(local_rank)
+    if cpus:
+        share = sorted(cpus)
+        if world > 1:
+            same = [r for r in range(world) if gpu_numa_cpus(r) == cpus]
+            per_node, k = max(1, len(same)), same.index(local_rank)
             share = share[k::per_node] if len(share) >= 4 * per_node else share
-            os.sched_setaffinity(0, share)
-            affinity = f"{len(share)} cores of the GPU's NUMA node"
+        os.sched_setaffinity(0, share)
+        affinity = f"{len(share)} cores of the GPU's NUMA node"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -506,6 +507,7 @@ def main():
             "max_pose_err_vs_gt_m": max(e[0] for e in errs),
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)  # the CPU leg uses every core the process may run on
             rate, cores, done, dt = cpu_reference_rate(pairs, 12.0, 10 ** 9)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{done} registrations of the same pairs in {dt:.1f} s, oracle "

@@ -183,6 +183,11 @@ typedef struct mulls_run_stats {
     float ms_search;            /* device time of the fused transform+NN+claim kernel only */
     float ms_total;
     float ms_search_iter[MULLS_MAX_TRACE_ITERS]; /* per-iteration device time of the search kernel */
+    /* one-shot calls with host buffers (mulls_icp_run_batch): where the call's wall time went */
+    float ms_host_pack; /* host: repacking the clouds into the pinned staging (0 when they are shipped as rows) */
+    float ms_h2d;       /* device: first cloud copy enqueued -> last cloud copy done */
+    float ms_host_call; /* host: wall time of the whole call */
+    float ms_host_upload; /* host: wall time of the upload part (tables, packing, enqueueing the copies) */
 } mulls_run_stats;
 int mulls_get_stats(const mulls_ctx *ctx, mulls_run_stats *out);
 

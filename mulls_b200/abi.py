@@ -88,6 +88,10 @@ class RunStats(C.Structure):
         ("ms_search", C.c_float),
         ("ms_total", C.c_float),
         ("ms_search_iter", C.c_float * MAX_TRACE_ITERS),
+        ("ms_host_pack", C.c_float),
+        ("ms_h2d", C.c_float),
+        ("ms_host_call", C.c_float),
+        ("ms_host_upload", C.c_float),
     ]
 
 

@@ -176,8 +176,11 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
 // ---- k_search: I1 + I2a of the iteration — apply the previous increment to the source (:1260), exact
 //      radius-bounded 1-NN on the hashed multi-level grid (nn_search_walk, search_core.cuh — replaces the kd-tree query
 //      of :1745), claim the target for the duplicate check. One query per thread; 48 registers, 10 blocks per SM.
-__global__ void __launch_bounds__(kIterBlock, 10) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                          int defer_from_iter, float reseed_cells) {
+// kMinBlocks: resident blocks per SM the register allocation is held to (10: 48 registers, 12: 40, 16: 32 + spills) —
+// the `search_blocks` tunable picks the instantiation
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
+                                                                  int defer_from_iter, float reseed_cells) {
     if (!chunk_in_run(A)) return;
     buf = loop_buf(A, buf);
     const ChunkDesc cd = A.it_chunks[blockIdx.x];

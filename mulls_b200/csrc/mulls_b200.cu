@@ -5,6 +5,7 @@
 #include <memory>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -108,6 +109,7 @@ struct mulls_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     int graph_key[6] = {-1, -1, -1, -1, -1, -1}; // the tunables baked into the kernel nodes
     LoopCtl *h_ctl = nullptr;            // pinned staging of the control block
+    int search_blocks = 16;  // resident k_search blocks per SM (10 / 12 / 16: register budget 48 / 40 / 32; measured 4.46 / 4.27 / 4.13 ms of search per 64-pair step)
     int defer_from_iter = 3; // k_search queues the small cells of a block (one scan loop per block) from this iteration on
     int hash_slack = 4;      // table capacity >= hash_slack x cells (power of two): load factor <= 1/hash_slack
     int reseed_cells_x4 = 16; // a previous match farther than this many quarter level-0 cells is challenged by a greedy descent
@@ -122,7 +124,9 @@ struct mulls_ctx {
     size_t h_stage_slots = 0;
     float h0_min = 0.125f;
     // timing
-    cudaEvent_t ev_begin = nullptr, ev_ingest = nullptr, ev_iter = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_ingest = nullptr, ev_iter = nullptr, ev_end = nullptr, ev_h2d0 = nullptr;
+    bool h2d_timed = false;                 // ev_h2d0 was recorded by the upload of the current one-shot call
+    float up_ms_pack = 0.f, up_ms_host = 0.f; // host-side times of that upload
     std::vector<cudaEvent_t> ev_search; // 2 per iteration
     mulls_run_stats stats{};
     std::vector<void *> allocs;
@@ -169,6 +173,9 @@ static cudaError_t dev_alloc(mulls_ctx *ctx, T **p, size_t n) {
 }
 
 static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+static inline double wall_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 extern "C" {
 
@@ -228,6 +235,7 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (ctx->ev_ingest) cudaEventDestroy(ctx->ev_ingest);
     if (ctx->ev_iter) cudaEventDestroy(ctx->ev_iter);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_h2d0) cudaEventDestroy(ctx->ev_h2d0);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -279,7 +287,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ALLOC(A.keys_b, cin);
     ALLOC(A.vals_a, cin);
     ALLOC(A.vals_b, cin);
-    ALLOC(A.tgt_pos, ct);
+    ALLOC(A.tgt_pos, ct + kScanOverrun); // (walk_scan_leaf's last group reads past a cell)
     ALLOC(A.tgt_nrm, ct);
     for (int b = 0; b < 2; ++b) {
         ALLOC(A.src_pos[b], cs);
@@ -342,6 +350,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     cudaEventCreate(&ctx->ev_ingest);
     cudaEventCreate(&ctx->ev_iter);
     cudaEventCreate(&ctx->ev_end);
+    cudaEventCreate(&ctx->ev_h2d0);
     ctx->ev_search.resize(2 * MULLS_MAX_TRACE_ITERS);
     for (auto &ev : ctx->ev_search) cudaEventCreate(&ev);
     if ((e = cudaMemsetAsync(A.ps, 0, max_pairs * sizeof(PairState), ctx->stream)) != cudaSuccess) return fail("memset", e);
@@ -424,6 +433,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "leaf_count") ctx->leaf_count = value;
     else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
     else if (n == "defer_from_iter") ctx->defer_from_iter = value;
+    else if (n == "search_blocks") ctx->search_blocks = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
     else if (n == "use_graph") ctx->use_graph = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
@@ -569,6 +579,9 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     }
     CK(cudaSetDevice(ctx->device));
     ctx->uploaded = false;
+    const double t_up0 = wall_ms();
+    ctx->h2d_timed = false;
+    ctx->up_ms_pack = 0.f;
     ctx->h_pc.assign(n_pairs, PairConst());
     ctx->h_in_chunks.clear();
     ctx->h_it_chunks.clear();
@@ -687,15 +700,19 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
             ce = cudaMemcpyAsync(ctx->A.it_chunks, ctx->h_it_chunks.data(), ctx->h_it_chunks.size() * sizeof(ChunkDesc),
                                  cudaMemcpyHostToDevice, ctx->stream);
         tables_sent = true; // (every job is waited for even after an error: the jobs point at `pending`)
+        if (ce == cudaSuccess && cudaEventRecord(ctx->ev_h2d0, ctx->stream) == cudaSuccess) ctx->h2d_timed = true;
+        const double t_pack0 = wall_ms();
         for (size_t p = 0; p < n_pairs; ++p) {
             pool.help_until_done(pending[p]);
+            if (p + 1 == n_pairs) ctx->up_ms_pack = (float)(wall_ms() - t_pack0);
             const size_t b = slot_begin[p], e = slot_begin[p + 1];
             if (e > b && ce == cudaSuccess)
                 ce = cudaMemcpyAsync((void *)(ctx->A.in_aos + b), ctx->h_stage + b, (e - b) * sizeof(float4), cudaMemcpyHostToDevice,
                                      ctx->stream);
         }
         CK(ce);
-    } else
+    } else {
+    if (cudaEventRecord(ctx->ev_h2d0, ctx->stream) == cudaSuccess) ctx->h2d_timed = true;
     for (size_t p = 0; p < n_pairs; ++p) {
         PairConst &pc = ctx->h_pc[p];
         for (int s = 0; s < kNumSegs; ++s) {
@@ -720,6 +737,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
                                ctx->stream));
         }
     }
+    }
     if (!tables_sent) {
         CK(cudaMemcpyAsync(ctx->A.pc, ctx->h_pc.data(), n_pairs * sizeof(PairConst), cudaMemcpyHostToDevice, ctx->stream));
         if (!ctx->h_in_chunks.empty())
@@ -742,6 +760,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->any_keep_less = any_keep_less;
     ctx->any_normal_shooting = any_shoot;
     ctx->uploaded = true;
+    ctx->up_ms_host = (float)(wall_ms() - t_up0);
     return MULLS_OK;
 }
 
@@ -819,12 +838,23 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
     return MULLS_OK;
 }
 
+static void launch_search(mulls_ctx *ctx, unsigned grid, cudaStream_t st, const DeviceArrays &A, int buf) {
+    const float reseed = 0.25f * (float)ctx->reseed_cells_x4;
+    if (ctx->search_blocks >= 16)
+        k_search<16><<<grid, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+    else if (ctx->search_blocks >= 12)
+        k_search<12><<<grid, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+    else
+        k_search<10><<<grid, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+}
+
 // The iteration loop as a CUDA graph (CUDA 12.4+ conditional nodes): WHILE(handle) { k_search [, k_search_shoot],
 // k_resolve, k_accumulate, k_solve } followed by k_posterior, k_finalize, k_collect. Kernel nodes are recorded once per
 // context with grids sized for its capacity; what a run needs to know (chunk / pair counts, trace switch, loop counter)
 // is read from LoopCtl in device memory. k_solve's last block sets the loop condition: no host polling, one launch.
 static int build_iteration_graph(mulls_ctx *ctx) {
-    const int key[6] = {ctx->start_level0, ctx->leaf_count, ctx->reseed_cells_x4, ctx->any_normal_shooting ? 1 : 0, ctx->defer_from_iter, 0};
+    const int key[6] = {ctx->start_level0, ctx->leaf_count, ctx->reseed_cells_x4, ctx->any_normal_shooting ? 1 : 0, ctx->defer_from_iter,
+                        ctx->search_blocks};
     if (ctx->graph_exec && std::memcmp(key, ctx->graph_key, sizeof(key)) == 0) return MULLS_OK;
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
     if (ctx->graph) cudaGraphDestroy(ctx->graph), ctx->graph = nullptr;
@@ -842,8 +872,7 @@ static int build_iteration_graph(mulls_ctx *ctx) {
     CK(cudaGraphAddNode(&while_node, ctx->graph, nullptr, 0, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    k_search<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter,
-                                                 0.25f * (float)ctx->reseed_cells_x4);
+    launch_search(ctx, cap_chunks, st, A, -1);
     if (ctx->any_normal_shooting) k_search_shoot<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count);
     k_resolve<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
     k_accumulate<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
@@ -917,8 +946,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            k_search<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter,
-                                                    0.25f * (float)ctx->reseed_cells_x4);
+            launch_search(ctx, n_itc, st, A, buf);
             if (ctx->any_normal_shooting) {
                 k_search_shoot<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
                 ++launches;
@@ -992,6 +1020,9 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
     cudaEventElapsedTime(&S.ms_ingest, ctx->ev_begin, ctx->ev_ingest);
     cudaEventElapsedTime(&S.ms_iterate, ctx->ev_ingest, ctx->ev_iter);
     cudaEventElapsedTime(&S.ms_total, ctx->ev_begin, ctx->ev_end);
+    if (ctx->h2d_timed) cudaEventElapsedTime(&S.ms_h2d, ctx->ev_h2d0, ctx->ev_begin);
+    S.ms_host_pack = ctx->up_ms_pack, S.ms_host_upload = ctx->up_ms_host;
+    ctx->h2d_timed = false;
     float ms = 0.f;
     for (int it = 0; it < n_search_ev; ++it) {
         float t = 0.f;
@@ -1057,20 +1088,24 @@ int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *
         ctx->n_pairs = n_pairs;
         ctx->uploaded = false;
         const int rc = for_each_lane(ctx, n_pairs, [&](mulls_ctx *lane, size_t b, size_t n) {
+            const double t0 = wall_ms();
             int r = upload_impl(lane, n, tgt + b * kNumClasses, src + b * kNumClasses, params + b, init_guess + 16 * b, nullptr,
                                 nullptr, /*resident=*/false);
             if (r != MULLS_OK) return r;
             r = run_impl(lane, out ? out + b : nullptr, trace ? trace + b : nullptr, nullptr, nullptr);
             lane->uploaded = false;
+            lane->stats.ms_host_call = (float)(wall_ms() - t0);
             return r;
         });
         merge_lane_stats(ctx);
         return rc;
     }
+    const double t0 = wall_ms();
     int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr, /*resident=*/false);
     if (rc != MULLS_OK) return rc;
     rc = run_impl(ctx, out, trace, nullptr, nullptr);
     ctx->uploaded = false; // nothing stays resident after a one-shot call
+    ctx->stats.ms_host_call = (float)(wall_ms() - t0);
     return rc;
 }
 

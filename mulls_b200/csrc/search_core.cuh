@@ -113,11 +113,13 @@ MULLS_HD bool probe_finish(const GridView &g, uint32_t slot, uint4 e, uint32_t k
     }
 }
 
-MULLS_HD bool probe_cell(const GridView &g, uint32_t x, uint32_t y, uint32_t z, int level, uint32_t &start, uint32_t &count,
-                         uint32_t &cmask) {
-    const uint32_t klo = cell_key_lo(x, y, z), khi = cell_key_hi(z, level);
+MULLS_HD bool probe_key(const GridView &g, uint32_t klo, uint32_t khi, uint32_t &start, uint32_t &count, uint32_t &cmask) {
     const uint32_t slot = cell_hash(klo, khi) & g.mask;
     return probe_finish(g, slot, ld_entry(&g.table[slot]), klo, khi, start, count, cmask);
+}
+MULLS_HD bool probe_cell(const GridView &g, uint32_t x, uint32_t y, uint32_t z, int level, uint32_t &start, uint32_t &count,
+                         uint32_t &cmask) {
+    return probe_key(g, cell_key_lo(x, y, z), cell_key_hi(z, level), start, count, cmask);
 }
 
 // distance along one axis from p to the slab [lo - margin, hi + margin]
@@ -142,19 +144,64 @@ MULLS_HD int highest_bit(uint32_t v) {
 constexpr int kWalkStack = 48; // DFS entries: at most 7 stay behind per descended level
 constexpr int kWalkQueue = 8;  // small cells of one block whose scan is deferred to the end of its traversal
 
-// examine the points [start, start+count) of a small cell: FLANN distance, total order (d2, original index)
+// one candidate under the total order (FLANN float distance, original index)
+MULLS_HD void walk_consider(const GridView &g, float d2, uint32_t jj, float &best_d2, int &best_j) {
+    if (d2 < best_d2) {
+        best_d2 = d2;
+        best_j = (int)jj;
+    } else if (d2 == best_d2 && best_j >= 0 && (int)jj != best_j) {
+        const int oj = f2i_bits(ld_point(&g.nrm[jj]).w);
+        const int ob = f2i_bits(ld_point(&g.nrm[best_j]).w);
+        if (oj < ob) best_j = (int)jj;
+    }
+}
+
+// fused estimate of the squared distance: within 6e-7 relative of flann_l2 (both are a few roundings away from the real
+// value) — only ever used to decide whether the exact distance has to be looked at
+MULLS_HD float approx_l2(float px, float py, float pz, float qx, float qy, float qz) {
+    const float dx = px - qx, dy = py - qy, dz = pz - qz;
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+#else
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+#endif
+}
+
+// examine the points [start, start+count) of a small cell (count >= 1): FLANN distance, total order (d2, original index).
+// Four candidates per trip (independent loads at fixed offsets from one address): the fused estimates are reduced to
+// their minimum, and only a group whose minimum could reach the best so far is looked at exactly, point by point — with
+// a real candidate as the seed that is the exception. The last group of a cell may read up to two points past the
+// cell (their estimates are replaced by +inf): the position array carries kScanOverrun spare elements at its end.
+constexpr int kScanOverrun = 4;
 MULLS_HD void walk_scan_leaf(const GridView &g, float px, float py, float pz, uint32_t start, uint32_t count, float &best_d2,
                              int &best_j) {
-    for (uint32_t jj = start; jj < start + count; ++jj) {
-        const float4 q = ld_point(&g.pos[jj]);
-        const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-        if (d2 < best_d2) {
-            best_d2 = d2;
-            best_j = (int)jj;
-        } else if (d2 == best_d2 && best_j >= 0 && (int)jj != best_j) {
-            const int oj = f2i_bits(ld_point(&g.nrm[jj]).w);
-            const int ob = f2i_bits(ld_point(&g.nrm[best_j]).w);
-            if (oj < ob) best_j = (int)jj;
+    const uint32_t end = start + count;
+    uint32_t jj = start;
+    for (; jj + 4 <= end; jj += 4) {
+        const float4 *b = &g.pos[jj];
+        const float4 q0 = ld_point(b), q1 = ld_point(b + 1), q2 = ld_point(b + 2), q3 = ld_point(b + 3);
+        const float a0 = approx_l2(px, py, pz, q0.x, q0.y, q0.z), a1 = approx_l2(px, py, pz, q1.x, q1.y, q1.z);
+        const float a2 = approx_l2(px, py, pz, q2.x, q2.y, q2.z), a3 = approx_l2(px, py, pz, q3.x, q3.y, q3.z);
+        const float m = fminf(fminf(a0, a1), fminf(a2, a3));
+        if (m * 0.999999f <= best_d2) {
+            walk_consider(g, flann_l2(px, py, pz, q0.x, q0.y, q0.z), jj, best_d2, best_j);
+            walk_consider(g, flann_l2(px, py, pz, q1.x, q1.y, q1.z), jj + 1, best_d2, best_j);
+            walk_consider(g, flann_l2(px, py, pz, q2.x, q2.y, q2.z), jj + 2, best_d2, best_j);
+            walk_consider(g, flann_l2(px, py, pz, q3.x, q3.y, q3.z), jj + 3, best_d2, best_j);
+        }
+    }
+    if (jj < end) { // 1..3 points left
+        const float4 *b = &g.pos[jj];
+        const float4 q0 = ld_point(b), q1 = ld_point(b + 1), q2 = ld_point(b + 2);
+        const bool v1 = jj + 1 < end, v2 = jj + 2 < end;
+        const float a0 = approx_l2(px, py, pz, q0.x, q0.y, q0.z);
+        const float a1 = v1 ? approx_l2(px, py, pz, q1.x, q1.y, q1.z) : INFINITY;
+        const float a2 = v2 ? approx_l2(px, py, pz, q2.x, q2.y, q2.z) : INFINITY;
+        const float m = fminf(a0, fminf(a1, a2));
+        if (m * 0.999999f <= best_d2) {
+            walk_consider(g, flann_l2(px, py, pz, q0.x, q0.y, q0.z), jj, best_d2, best_j);
+            if (v1) walk_consider(g, flann_l2(px, py, pz, q1.x, q1.y, q1.z), jj + 1, best_d2, best_j);
+            if (v2) walk_consider(g, flann_l2(px, py, pz, q2.x, q2.y, q2.z), jj + 2, best_d2, best_j);
         }
     }
 }
@@ -179,11 +226,7 @@ MULLS_HD void walk_greedy_seed(const GridView &g, float px, float py, float pz, 
             if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) break; // only possible at lv == lr
             if (count <= (uint32_t)g.leaf_count || lv == 0) {
                 st.seed_eval((int)count);
-                for (uint32_t jj = start; jj < start + count; ++jj) {
-                    const float4 q = ld_point(&g.pos[jj]);
-                    const float d2 = flann_l2(px, py, pz, q.x, q.y, q.z);
-                    if (d2 < best_d2) best_d2 = d2, best_j = (int)jj;
-                }
+                walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
                 break;
             }
             const float hl = g.h0 * (float)(1 << lv);
@@ -214,17 +257,19 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
     const int c0x = (int)flx, c0y = (int)fly, c0z = (int)flz;
     const int L = g.n_levels;
     const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
-    // stack entry: cell = x | y << 12 | (z & 0xff) << 24, meta = z >> 8 | level << 4, and the cell's box distance
+    // stack entry: the two key words of the cell (grid_key.cuh) and its box distance
     uint32_t st_cell[kWalkStack], st_meta[kWalkStack];
     float st_d2[kWalkStack];
     uint32_t q_start[kWalkQueue], q_count[kWalkQueue];
     int nq = 0;
     int l = (start_level < 1) ? 1 : ((start_level < L - 1) ? start_level : L - 1);
-    if (best_j >= 0) { // seeded: the smallest level whose coverage reaches the seed (level 0: 0.998 * h0 / 2)
-        const float need = 1.001f * sqrtf(best_d2);
-        const float t = need / (0.999f * 0.5f * g.h0);
-        if (t <= 1.0f) l = (need <= 0.998f * 0.5f * g.h0) ? 0 : 1;
-        else l = ilogbf(t) + 1;
+    if (best_j >= 0) { // seeded: the smallest level whose coverage reaches the seed (level 0: 0.998 * h0 / 2).
+        // Only a starting point — the stop test below is what makes the result exact — so the level comes from the
+        // exponent of (need / cover_1)^2 instead of a square root and a division: floor(log2 t) = floor(log2 t^2) >> 1
+        const float c1 = 0.999f * 0.5f * g.h0, c0 = 0.998f * 0.5f * g.h0;
+        const float t2 = (1.002001f * best_d2) * (1.0f / (c1 * c1));
+        if (t2 <= 1.0f) l = (1.002001f * best_d2 <= c0 * c0) ? 0 : 1;
+        else l = ((int)((f2i_bits(t2) >> 23) & 0xff) - 127 >> 1) + 1;
         l = (l < L - 1) ? l : L - 1;
     }
     for (;; ++l) {
@@ -249,11 +294,14 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
             vx[i] = xs[i] >= 0 && xs[i] < ncell;
             vy[i] = ys[i] >= 0 && ys[i] < ncell;
             vz[i] = zs[i] >= 0 && zs[i] < ncell;
-            ex[i] = walk_axis_dist(g.ox, H, xs[i], px, margin);
-            ey[i] = walk_axis_dist(g.oy, H, ys[i], py, margin);
-            ez[i] = walk_axis_dist(g.oz, H, zs[i], pz, margin);
-            ex[i] *= ex[i], ey[i] *= ey[i], ez[i] *= ez[i];
         }
+        // p lies inside its own cell (the margin covers the rounding of the cell assignment): only the three
+        // neighbour slabs are at a distance
+        ex[0] = ey[0] = ez[0] = 0.0f;
+        ex[1] = walk_axis_dist(g.ox, H, xs[1], px, margin);
+        ey[1] = walk_axis_dist(g.oy, H, ys[1], py, margin);
+        ez[1] = walk_axis_dist(g.oz, H, zs[1], pz, margin);
+        ex[1] *= ex[1], ey[1] *= ey[1], ez[1] *= ez[1];
         // live cells of the block as a bit mask, then one loop trip per LIVE cell
         uint32_t live = 0;
         {
@@ -271,7 +319,7 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
             const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
             int sp = 0;
             st_cell[0] = cell_key_lo((uint32_t)xs[i], (uint32_t)ys[j], (uint32_t)zs[m]);
-            st_meta[0] = ((uint32_t)zs[m] >> 8) | ((uint32_t)l << 4);
+            st_meta[0] = cell_key_hi((uint32_t)zs[m], l);
             st_d2[0] = ex[i] + ey[j] + ez[m];
             sp = 1;
             while (sp > 0) {
@@ -279,11 +327,10 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
                 // a cell farther than the best so far (or than the radius) cannot change the result
                 if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
                 const uint32_t cell = st_cell[sp], meta = st_meta[sp];
-                const int lv = (int)((meta >> 4) & 0xfu);
-                const int cx = (int)(cell & 0xfffu), cy = (int)((cell >> 12) & 0xfffu), cz = (int)((cell >> 24) | ((meta & 0xfu) << 8));
                 uint32_t start, count, cmask;
                 st.probe();
-                if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) continue;
+                if (!probe_key(g, cell, meta, start, count, cmask)) continue;
+                const int lv = (int)((meta >> 4) & 0xfu) - 1;
                 if (count <= (uint32_t)g.leaf_count || lv == 0 || sp + 8 > kWalkStack) {
                     if (defer_scan && nq < kWalkQueue) { // examined together with the block's other small cells
                         q_start[nq] = start;
@@ -295,6 +342,7 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
                     }
                 } else {
                     st.expand();
+                    const int cx = (int)(cell & 0xfffu), cy = (int)((cell >> 12) & 0xfffu), cz = (int)((cell >> 24) | ((meta & 0xfu) << 8));
                     const float hc = 0.5f * g.h0 * (float)(1 << lv);
                     float ax[2], ay[2], az[2];
 #pragma unroll
@@ -324,7 +372,7 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
                         const int ch = c ^ near_child;
                         const uint32_t x2 = (uint32_t)(2 * cx + (ch & 1)), y2 = (uint32_t)(2 * cy + ((ch >> 1) & 1)), z2 = (uint32_t)(2 * cz + (ch >> 2));
                         st_cell[sp] = cell_key_lo(x2, y2, z2);
-                        st_meta[sp] = (z2 >> 8) | ((uint32_t)(lv - 1) << 4);
+                        st_meta[sp] = cell_key_hi(z2, lv - 1);
                         st_d2[sp] = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
                         ++sp;
                     }

@@ -12,7 +12,15 @@ n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 runs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfg = sys.argv[3] if len(sys.argv) > 3 else "c2"
 tun = dict(kv.split("=") for kv in sys.argv[4:])
-pairs = [synth.make_pair(1000 + i, cfg) for i in range(n_pairs)]
+from concurrent.futures import ProcessPoolExecutor
+from mulls_b200 import abi
+def _gen(a):
+    p = synth.make_pair(a[0], a[1])
+    return {"tgt": p["tgt"], "src": p["src"], "params": bytes(p["params"]), "init_guess": p["init_guess"]}
+with ProcessPoolExecutor(min(32, n_pairs)) as ex:
+    pairs = list(ex.map(_gen, [(1000 + i, cfg) for i in range(n_pairs)]))
+for p in pairs:
+    p["params"] = abi.IcpParams.from_buffer_copy(p["params"])
 ns = max(sum(len(s) for s in p["src"]) for p in pairs)
 nt = max(sum(len(t) for t in p["tgt"]) for p in pairs)
 import torch

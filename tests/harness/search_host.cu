@@ -61,7 +61,7 @@ void *sh_build(const float *pts, uint32_t n, float ox, float oy, float oz, float
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-    G->pos.resize(n), G->nrm.resize(n), G->inv.resize(n);
+    G->pos.resize(n + kScanOverrun), G->nrm.resize(n), G->inv.resize(n);
     std::vector<uint64_t> sk(n);
     for (uint32_t s = 0; s < n; ++s) {
         const uint32_t i = order[s];
