@@ -116,7 +116,11 @@ struct LoopCtl {
     int trace_on;    // write the per-iteration trace
     int max_iter;    // max over the pairs of max_iter_num
     unsigned solved; // pairs whose k_solve block has finished this iteration
-    int _pad[2];
+    // Work lists of the iteration kernels. live_chunks[it & 1] holds the ids of the chunks that still own live sources
+    // (built after the ingest for iteration 0, by k_solve for the next iteration); the kernels run a fixed number of
+    // resident blocks that fetch list positions from work[] — no block is launched for a chunk that has nothing to do.
+    unsigned n_live[2];
+    unsigned work[4]; // fetch counters: 0 k_search, 1 k_resolve, 2 k_accumulate, 3 k_search_shoot
 };
 
 // All device pointers of a context, passed by value to the kernels.
@@ -149,6 +153,8 @@ struct DeviceArrays {
     int *xch_i32;           // exchange buffer of the sharded mode (counts / bbox), 32 ints
     double *xch_f64;        // exchange buffer of the sharded mode (per-class sums), 6*kTerms + 2 doubles
     LoopCtl *ctl;
+    uint32_t *live_chunks;  // 2 x live_stride chunk ids (see LoopCtl)
+    uint32_t live_stride;
     int *running;           // pairs still iterating (device counter)
     volatile int *h_running; // the same, mirrored into mapped pinned host memory for the launch loop
     volatile int *h_running_iter; // [it]: pairs still iterating at the END of iteration it (sharded runs: rank-deterministic stop)

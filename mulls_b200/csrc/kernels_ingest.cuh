@@ -9,7 +9,10 @@ namespace mulls {
 
 // ---- k_ingest_transform: AoS48 -> staging SoA; source gets the initial guess (double math, float store,
 //      pcl::transformPointCloudWithNormals semantics); bbox reductions for the intersection filter.
-__global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays A) {
+// kUndistort = false: the instantiation for batches in which no pair asks for motion undistortion (no slerp code, 32
+// registers, 8 blocks per SM — the kernel is a latency-bound stream: 28 B read + 32 B written per point)
+template <bool kUndistort>
+__global__ void __launch_bounds__(kIngestBlock, kUndistort ? 4 : 6) k_ingest_transform(DeviceArrays A) {
     const ChunkDesc cd = A.in_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     const uint32_t seg = cd.seg;
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
         if (is_src) {
             const double *t = pc.init;
             int n_apply = 1;
-            if (pc.undistort) {
+            if (kUndistort && pc.undistort) {
                 if (cls == MULLS_VERTEX) {
                     n_apply = 2; // not undistorted and not re-cloned: the initial guess lands twice (reference behaviour)
                 } else {
@@ -101,13 +104,20 @@ __global__ void __launch_bounds__(kIngestBlock) k_ingest_transform(DeviceArrays 
             mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
             mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
         }
+    __shared__ float s_mn[kIngestBlock / 32][3], s_mx[kIngestBlock / 32][3];
     if ((threadIdx.x & 31) == 0) {
-        int *bb = is_src ? A.ps[cd.pair].bb_src : A.ps[cd.pair].bb_tgt;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            atomicMin(&bb[d], float_to_ordered(mn[d]));
-            atomicMax(&bb[3 + d], float_to_ordered(mx[d]));
-        }
+        for (int d = 0; d < 3; ++d) s_mn[threadIdx.x >> 5][d] = mn[d], s_mx[threadIdx.x >> 5][d] = mx[d];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) { // one atomic per block and bound
+        const int d = threadIdx.x % 3;
+        const bool is_max = threadIdx.x >= 3;
+        float v = is_max ? s_mx[0][d] : s_mn[0][d];
+        for (int w = 1; w < kIngestBlock / 32; ++w) v = is_max ? fmaxf(v, s_mx[w][d]) : fminf(v, s_mn[w][d]);
+        int *bb = is_src ? A.ps[cd.pair].bb_src : A.ps[cd.pair].bb_tgt;
+        if (is_max) atomicMax(&bb[3 + d], float_to_ordered(v));
+        else atomicMin(&bb[d], float_to_ordered(v));
     }
 }
 
@@ -196,7 +206,7 @@ __global__ void k_pair_setup(DeviceArrays A, int n_pairs, float h0_min) {
 
 // ---- k_make_keys: intersection filter (cfilter.hpp:950-981: strictly inside) + 64-bit sort key
 //      [pair*12+seg | morton36(cell)]; filtered-out points sort to the very end.
-__global__ void __launch_bounds__(kIngestBlock) k_make_keys(DeviceArrays A) {
+__global__ void __launch_bounds__(kIngestBlock) k_make_keys(DeviceArrays A, int sort_sources) {
     const ChunkDesc cd = A.in_chunks[blockIdx.x];
     const PairConst &pc = A.pc[cd.pair];
     PairState &ps = A.ps[cd.pair];
@@ -222,6 +232,8 @@ __global__ void __launch_bounds__(kIngestBlock) k_make_keys(DeviceArrays A) {
             cy = min(max(cy, 0), hi);
             cz = min(max(cz, 0), hi);
             key = ((uint64_t)(cd.pair * kNumSegs + seg) << 36) | morton36((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+            // (study switch: sources left in the caller's order — nothing but the search's locality depends on it)
+            if (!sort_sources && seg >= kNumClasses) key = ((uint64_t)(cd.pair * kNumSegs + seg) << 36) | (uint64_t)local;
         }
         A.keys_a[gi] = key;
         A.vals_a[gi] = (uint32_t)gi;

@@ -25,6 +25,49 @@ __device__ __forceinline__ mulls_icp_trace *trace_of(const DeviceArrays &A, uint
     return (A.trace && A.ctl->trace_on) ? &A.trace[pair] : nullptr;
 }
 
+// The iteration kernels run a fixed number of resident blocks; each block fetches positions of the live-chunk list of
+// this iteration (LoopCtl::n_live / work, device_types.cuh) until the list is exhausted. `body(chunk)` is executed by
+// the whole block; a body may leave early per thread, but only before any barrier it contains.
+template <class Body>
+__device__ __forceinline__ void for_each_live_chunk(const DeviceArrays &A, int parity, int which, Body body) {
+    __shared__ uint32_t s_fetch;
+    LoopCtl &ctl = *A.ctl;
+    const uint32_t n = ctl.n_live[parity];
+    const uint32_t *list = A.live_chunks + (size_t)parity * A.live_stride;
+    for (;;) {
+        __syncthreads(); // the previous chunk is finished with and s_fetch has been read by everyone
+        if (threadIdx.x == 0) s_fetch = atomicAdd(&ctl.work[which], 1u);
+        __syncthreads();
+        const uint32_t w = s_fetch;
+        if (w >= n) break;
+        body(list[w]);
+    }
+}
+
+// warp-aggregated append of the chunks [first, first + count) of one (pair, class) to a live list
+__device__ __forceinline__ void append_live_chunks(const DeviceArrays &A, int parity, uint32_t first, uint32_t count, uint32_t base) {
+    uint32_t *list = A.live_chunks + (size_t)parity * A.live_stride;
+    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) list[base + k] = first + k;
+}
+
+// after the ingest: the chunks that own at least one source point form the list of iteration 0
+__global__ void __launch_bounds__(256) k_live_init(DeviceArrays A) {
+    LoopCtl &ctl = *A.ctl;
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = false;
+    if (chunk < (uint32_t)ctl.n_it_chunks) {
+        const ChunkDesc cd = A.it_chunks[chunk];
+        live = (int)cd.first < A.ps[cd.pair].n_src[cd.seg];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl.n_live[0], (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) A.live_chunks[base + __popc(m & ((1u << lane) - 1u))] = chunk;
+}
+
 // ------------------------------------------------------------------------------------------------
 // exact 1-NN within radius on the multi-level hashed grid of one target class: search_core.cuh
 // (__host__ __device__; the CPU suite runs the same functions against a brute-force scan)
@@ -178,12 +221,11 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
 //      of :1745), claim the target for the duplicate check. One query per thread; 48 registers, 10 blocks per SM.
 // kMinBlocks: resident blocks per SM the register allocation is held to (10: 48 registers, 12: 40, 16: 32 + spills) —
 // the `search_blocks` tunable picks the instantiation
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                                  int defer_from_iter, float reseed_cells) {
-    if (!chunk_in_run(A)) return;
-    buf = loop_buf(A, buf);
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+// `sub`: which warp-sized quarter of the chunk this warp examines (the search needs no cooperation inside a block, so
+// the warps of k_search fetch their work one by one)
+__device__ __forceinline__ void search_chunk(DeviceArrays &A, int buf, uint32_t chunk, uint32_t sub, int start_level0, int leaf_count,
+                                             int defer_from_iter, float reseed_cells) {
+    const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning || A.hash_used[1]) return;
@@ -191,7 +233,7 @@ __global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search(DeviceArrays 
     const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
     if ((int)cd.first >= ns) return; // block-uniform
     if (shoots(pc, c)) return;       // block-uniform: k_search_shoot's work
-    const uint32_t local = cd.first + threadIdx.x;
+    const uint32_t local = cd.first + 32u * sub + (threadIdx.x & 31u);
     const bool valid = (int)local < ns;
     const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
     float4 p, n;
@@ -239,15 +281,34 @@ __global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search(DeviceArrays 
     A.nn_idx[gi] = best_j;
     A.nn_d2[gi] = best_d2;
 }
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
+                                                                  int defer_from_iter, float reseed_cells) {
+    buf = loop_buf(A, buf);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // first kernel of the iteration: counters and list the later ones use
+        LoopCtl &ctl = *A.ctl;
+        ctl.work[1] = ctl.work[2] = ctl.work[3] = 0u;
+        ctl.n_live[buf ^ 1] = 0u;
+    }
+    // work unit = a quarter chunk (32 sources), fetched per warp: no barrier, a warp that finishes early moves on
+    const uint32_t n_units = (kIterBlock / 32) * A.ctl->n_live[buf];
+    const uint32_t *list = A.live_chunks + (size_t)buf * A.live_stride;
+    for (;;) {
+        uint32_t u = 0;
+        if ((threadIdx.x & 31) == 0) u = atomicAdd(&A.ctl->work[0], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        search_chunk(A, buf, list[u / (kIterBlock / 32)], u % (kIterBlock / 32), start_level0, leaf_count, defer_from_iter, reseed_cells);
+        __syncwarp();
+    }
+}
 
 // :1732-1737 normal shooting [PCL CorrespondenceEstimationNormalShooting, k = 10]: among the 10 nearest targets
 // the one with the smallest squared distance to the line through the source point along its normal; dropped
 // if that value exceeds max_distance (NOT squared); correspondence distance = its squared NN distance.
 // Launched only when a pair of the batch asked for normal shooting.
-__global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int buf, int start_level0, int leaf_count) {
-    if (!chunk_in_run(A)) return;
-    buf = loop_buf(A, buf);
-    const ChunkDesc cd = A.it_chunks[blockIdx.x];
+__device__ __forceinline__ void search_shoot_chunk(DeviceArrays &A, int buf, uint32_t chunk, int start_level0, int leaf_count) {
+    const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning || A.hash_used[1]) return;
@@ -288,6 +349,10 @@ __global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int
     if (sj >= 0) atomicMin(&A.claim[pc.tgt_base[c] + sj], (unsigned)__float_as_int(n.w));
     A.nn_idx[gi] = sj;
     A.nn_d2[gi] = sd2;
+}
+__global__ void __launch_bounds__(kIterBlock) k_search_shoot(DeviceArrays A, int buf, int start_level0, int leaf_count) {
+    buf = loop_buf(A, buf);
+    for_each_live_chunk(A, buf, 3, [&](uint32_t chunk) { search_shoot_chunk(A, buf, chunk, start_level0, leaf_count); });
 }
 
 // ---- k_resolve ---------------------------------------------------------------------------------
@@ -348,7 +413,8 @@ __device__ __forceinline__ void resolve_body(DeviceArrays &A, int buf, uint32_t 
     }
 }
 __global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf) {
-    if (chunk_in_run(A)) resolve_body(A, loop_buf(A, buf), blockIdx.x);
+    buf = loop_buf(A, buf);
+    for_each_live_chunk(A, buf, 1, [&](uint32_t chunk) { resolve_body(A, buf, chunk); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -776,7 +842,33 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     }
 }
 __global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) {
-    if (chunk_in_run(A)) accumulate_body(A, loop_buf(A, buf), blockIdx.x);
+    buf = loop_buf(A, buf);
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->work[0] = 0u; // the next iteration's k_search starts its list at 0
+    for_each_live_chunk(A, buf, 2, [&](uint32_t chunk) { accumulate_body(A, buf, chunk); });
+}
+
+// the chunks of this pair that still own live sources go onto the next iteration's list (whole block; the pair's state
+// has just been advanced by thread 0)
+__device__ __forceinline__ void publish_live_chunks(const DeviceArrays &A, uint32_t pair, int next_parity) {
+    __shared__ uint32_t s_base;
+    __syncthreads();
+    const PairConst &pc = A.pc[pair];
+    const PairState &ps = A.ps[pair];
+    if (ps.status != kRunning) return; // block-uniform
+    uint32_t count[kNumClasses], total = 0;
+#pragma unroll
+    for (int c = 0; c < kNumClasses; ++c) {
+        count[c] = (uint32_t)((ps.n_src[c] + kIterBlock - 1) / kIterBlock);
+        total += count[c];
+    }
+    if (threadIdx.x == 0) s_base = atomicAdd(&A.ctl->n_live[next_parity], total);
+    __syncthreads();
+    uint32_t base = s_base;
+#pragma unroll
+    for (int c = 0; c < kNumClasses; ++c) {
+        append_live_chunks(A, next_parity, pc.class_chunk_begin[c], count[c], base);
+        base += count[c];
+    }
 }
 
 // ---- solve: one block per pair, after every k_accumulate block of the pair. Sums the per-chunk partials of every
@@ -830,8 +922,7 @@ __device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pa
                 ps.n_src[cc] = s_newn[cc];
                 for (int k = 0; k < kTerms; ++k) A.xch_f64[cc * kTerms + k] = (k < 27) ? s_S[cc][k] : 0.0;
             }
-            return;
-        }
+        } else {
         mulls_icp_trace *tr = trace_of(A, pair);
         for (int cc = 0; cc < kNumClasses; ++cc) {
             ps.n_src[cc] = s_newn[cc]; // classes that skipped determine_corres keep everything (k_resolve)
@@ -841,7 +932,10 @@ __device__ __forceinline__ void solve_body(DeviceArrays &A, int buf, uint32_t pa
         }
         solve_and_advance(A, pair, &s_S[0][0], s_scratch, buf ^ 1);
         for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+        }
     }
+    // (a sharded pair is advanced by k_shard_solve, after the exchange of the sums: it publishes the list)
+    if (!pc.sharded) publish_live_chunks(A, pair, buf ^ 1);
 }
 constexpr int kSolveThreads = kNumClasses * 32; // one warp per feature class
 // loop_handle != 0: the launch is the last kernel of the iteration graph's WHILE body — the block that finishes last
@@ -930,22 +1024,24 @@ __global__ void __launch_bounds__(kIterBlock) k_shard_counts(DeviceArrays A, int
 // after the all-reduce of the per-class sums: every rank solves the same system and advances identically
 __global__ void k_shard_solve(DeviceArrays A, int buf, int it_flag) {
     PairState &ps = A.ps[0];
-    if (threadIdx.x != 0) return;
-    if (ps.status != kRunning) {
-        A.h_running_iter[it_flag] = *A.running;
-        __threadfence_system();
-        return;
-    }
     __shared__ double s_scratch[160];
-    mulls_icp_trace *tr = trace_of(A, 0);
-    for (int cc = 0; cc < kNumClasses; ++cc) {
-        ps.n_src_g[cc] = ps.n_src_g_next[cc];
-        if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src_g[cc];
+    if (threadIdx.x == 0) {
+        if (ps.status != kRunning) {
+            A.h_running_iter[it_flag] = *A.running;
+            __threadfence_system();
+        } else {
+            mulls_icp_trace *tr = trace_of(A, 0);
+            for (int cc = 0; cc < kNumClasses; ++cc) {
+                ps.n_src_g[cc] = ps.n_src_g_next[cc];
+                if (tr && ps.iter < MULLS_MAX_TRACE_ITERS) tr->n_src[ps.iter][cc] = (uint32_t)ps.n_src_g[cc];
+            }
+            solve_and_advance(A, 0, A.xch_f64, s_scratch, buf ^ 1);
+            for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
+            A.h_running_iter[it_flag] = *A.running; // what the launch loop of every rank reads two iterations later
+            __threadfence_system();
+        }
     }
-    solve_and_advance(A, 0, A.xch_f64, s_scratch, buf ^ 1);
-    for (int cc = 0; cc < kNumClasses; ++cc) ps.n_corr[cc] = 0;
-    A.h_running_iter[it_flag] = *A.running; // what the launch loop of every rank reads two iterations later
-    __threadfence_system();
+    publish_live_chunks(A, 0, buf ^ 1); // this rank's shard: its own live chunks
 }
 // posterior in sharded mode: VTPV / n_obs of this rank -> exchange buffer
 __global__ void k_shard_post(DeviceArrays A, int phase) {
@@ -1163,6 +1259,8 @@ __global__ void k_collect(DeviceArrays A, int n_pairs, mulls_icp_result *out) {
         r.n_corr[c] = ps.n_corr_last[c];
         r.n_src[c] = (uint32_t)ps.n_src_g[c];
     }
+    // (the per-pair algorithmic-byte counters ride behind the results: one D2H fetches both)
+    reinterpret_cast<uint64_t *>(out + A.ctl->n_pairs)[p] = ps.alg_bytes;
 }
 
 } // namespace mulls

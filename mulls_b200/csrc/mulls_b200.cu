@@ -109,11 +109,14 @@ struct mulls_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     int graph_key[6] = {-1, -1, -1, -1, -1, -1}; // the tunables baked into the kernel nodes
     LoopCtl *h_ctl = nullptr;            // pinned staging of the control block
-    int search_blocks = 16;  // resident k_search blocks per SM (10 / 12 / 16: register budget 48 / 40 / 32; measured 4.46 / 4.27 / 4.13 ms of search per 64-pair step)
+    int num_sms = 148;
+    int sort_sources = 1;    // 0: sources stay in the caller's order (study switch)
+    int search_blocks = 12;  // resident k_search blocks per SM (10 / 12 / 16: register budget 48 / 40 / 32; measured 4.36 / 4.31 / 4.61 ms of search per 64-pair step)
     int defer_from_iter = 3; // k_search queues the small cells of a block (one scan loop per block) from this iteration on
     int hash_slack = 4;      // table capacity >= hash_slack x cells (power of two): load factor <= 1/hash_slack
     int reseed_cells_x4 = 16; // a previous match farther than this many quarter level-0 cells is challenged by a greedy descent
     bool any_normal_shooting = false;
+    bool any_undistort = false;
     int zero_copy = 0;     // opt-in: one-shot calls read pinned host clouds in place (measured slower than DMA: 20 vs 32 GB/s)
     // repack host clouds to the 28 B/point wire format on the host cores before the DMA (host_pack.h):
     // 0 never, 1 always, 2 when a call ships at least kPackMinPoints points (small calls are latency-bound: raw rows)
@@ -317,7 +320,14 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ALLOC(A.ps, max_pairs);
     ALLOC(A.in_chunks, ctx->cap_in_chunks);
     ALLOC(A.it_chunks, ctx->cap_it_chunks);
-    ALLOC(ctx->d_results, max_pairs);
+    ALLOC(A.live_chunks, 2 * ctx->cap_it_chunks);
+    A.live_stride = (uint32_t)ctx->cap_it_chunks;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+        ctx->num_sms = sms;
+    }
+    ALLOC(ctx->d_results, max_pairs + ceil_div(max_pairs * sizeof(uint64_t), sizeof(mulls_icp_result)) + 1);
     ALLOC(ctx->d_trace, max_pairs);
     ALLOC(A.running, 1);
     ALLOC(A.xch_i32, 32);
@@ -334,7 +344,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
     ctx->ev_done.resize(MULLS_MAX_TRACE_ITERS);
     for (auto &ev : ctx->ev_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     A.trace = ctx->d_trace; // written only when LoopCtl::trace_on is set for the run
-    if ((e = cudaMallocHost((void **)&ctx->h_results, max_pairs * sizeof(mulls_icp_result))) != cudaSuccess)
+    if ((e = cudaMallocHost((void **)&ctx->h_results, max_pairs * (sizeof(mulls_icp_result) + sizeof(uint64_t)))) != cudaSuccess)
         return fail("pinned results", e);
     if ((e = cudaMallocHost((void **)&ctx->h_flags, 2 * sizeof(uint32_t))) != cudaSuccess) return fail("pinned flags", e);
     if ((e = cudaMallocHost((void **)&ctx->h_ctl, sizeof(LoopCtl))) != cudaSuccess) return fail("pinned control block", e);
@@ -434,6 +444,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
     else if (n == "defer_from_iter") ctx->defer_from_iter = value;
     else if (n == "search_blocks") ctx->search_blocks = value;
+    else if (n == "sort_sources") ctx->sort_sources = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
     else if (n == "use_graph") ctx->use_graph = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
@@ -587,7 +598,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->h_it_chunks.clear();
     size_t in_off = 0, s_off = 0, t_off = 0;
     int max_iter_max = 0;
-    bool any_keep_less = false, any_shoot = false;
+    bool any_keep_less = false, any_shoot = false, any_undistort = false;
     for (size_t p = 0; p < n_pairs; ++p) {
         PairConst &pc = ctx->h_pc[p];
         int rc = build_pair_const(ctx, params[p], init_guess + 16 * p, pc);
@@ -595,6 +606,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
         max_iter_max = std::max(max_iter_max, pc.max_iter);
         any_keep_less = any_keep_less || pc.keep_less;
         any_shoot = any_shoot || pc.normal_shooting;
+        any_undistort = any_undistort || pc.undistort;
         size_t ns = 0, nt = 0;
         for (int c = 0; c < kNumClasses; ++c) {
             nt += tgt[p * kNumClasses + c].n;
@@ -759,6 +771,7 @@ static int upload_impl(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *t
     ctx->max_iter_max = max_iter_max;
     ctx->any_keep_less = any_keep_less;
     ctx->any_normal_shooting = any_shoot;
+    ctx->any_undistort = any_undistort;
     ctx->uploaded = true;
     ctx->up_ms_host = (float)(wall_ms() - t_up0);
     return MULLS_OK;
@@ -777,7 +790,8 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
     ++launches;
     const unsigned n_inc = (unsigned)ctx->h_in_chunks.size();
     if (n_inc) {
-        k_ingest_transform<<<n_inc, kIngestBlock, 0, st>>>(A);
+        if (ctx->any_undistort) k_ingest_transform<true><<<n_inc, kIngestBlock, 0, st>>>(A);
+        else k_ingest_transform<false><<<n_inc, kIngestBlock, 0, st>>>(A);
         ++launches;
     }
     if (hook) { // sharded source: the intersection filter needs the bbox over all shards
@@ -792,7 +806,7 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
     k_pair_setup<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->h0_min);
     ++launches;
     if (n_inc) {
-        k_make_keys<<<n_inc, kIngestBlock, 0, st>>>(A);
+        k_make_keys<<<n_inc, kIngestBlock, 0, st>>>(A, ctx->sort_sources);
         ++launches;
         if (ctx->any_keep_less) { // random down-sampling of :2866-2892: radix select of the k-th sampling key
             const unsigned pb = (unsigned)ceil_div(np, 64);
@@ -838,23 +852,35 @@ static int launch_ingest(mulls_ctx *ctx, DeviceArrays &A, bool trace, uint64_t &
     return MULLS_OK;
 }
 
-static void launch_search(mulls_ctx *ctx, unsigned grid, cudaStream_t st, const DeviceArrays &A, int buf) {
+// The iteration kernels run a fixed number of resident blocks that fetch live chunks (for_each_live_chunk): grids are
+// sized by the SM count and the blocks an SM holds, never by the batch.
+// ... and, for small batches, by the chunks there are (rounded up to a power of two: the grids are part of the graph)
+static unsigned chunk_bucket(const mulls_ctx *ctx) {
+    unsigned b = 1;
+    while (b < (unsigned)ctx->h_it_chunks.size()) b <<= 1;
+    return b;
+}
+static unsigned resident_grid(const mulls_ctx *ctx, int blocks_per_sm) {
+    return std::min((unsigned)(ctx->num_sms * blocks_per_sm), chunk_bucket(ctx));
+}
+static void launch_search(mulls_ctx *ctx, cudaStream_t st, const DeviceArrays &A, int buf) {
     const float reseed = 0.25f * (float)ctx->reseed_cells_x4;
     if (ctx->search_blocks >= 16)
-        k_search<16><<<grid, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+        k_search<16><<<resident_grid(ctx, 16), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
     else if (ctx->search_blocks >= 12)
-        k_search<12><<<grid, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+        k_search<12><<<resident_grid(ctx, 12), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
     else
-        k_search<10><<<grid, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+        k_search<10><<<resident_grid(ctx, 10), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
 }
+constexpr int kShootBlocksPerSm = 8, kResolveBlocksPerSm = 16, kAccumulateBlocksPerSm = 5;
 
 // The iteration loop as a CUDA graph (CUDA 12.4+ conditional nodes): WHILE(handle) { k_search [, k_search_shoot],
 // k_resolve, k_accumulate, k_solve } followed by k_posterior, k_finalize, k_collect. Kernel nodes are recorded once per
 // context with grids sized for its capacity; what a run needs to know (chunk / pair counts, trace switch, loop counter)
 // is read from LoopCtl in device memory. k_solve's last block sets the loop condition: no host polling, one launch.
 static int build_iteration_graph(mulls_ctx *ctx) {
-    const int key[6] = {ctx->start_level0, ctx->leaf_count, ctx->reseed_cells_x4, ctx->any_normal_shooting ? 1 : 0, ctx->defer_from_iter,
-                        ctx->search_blocks};
+    const int key[6] = {ctx->start_level0, ctx->leaf_count + (ctx->reseed_cells_x4 << 12), (int)chunk_bucket(ctx),
+                        ctx->any_normal_shooting ? 1 : 0, ctx->defer_from_iter, ctx->search_blocks};
     if (ctx->graph_exec && std::memcmp(key, ctx->graph_key, sizeof(key)) == 0) return MULLS_OK;
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
     if (ctx->graph) cudaGraphDestroy(ctx->graph), ctx->graph = nullptr;
@@ -872,14 +898,15 @@ static int build_iteration_graph(mulls_ctx *ctx) {
     CK(cudaGraphAddNode(&while_node, ctx->graph, nullptr, 0, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    launch_search(ctx, cap_chunks, st, A, -1);
-    if (ctx->any_normal_shooting) k_search_shoot<<<cap_chunks, kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count);
-    k_resolve<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
-    k_accumulate<<<cap_chunks, kIterBlock, 0, st>>>(A, -1);
+    launch_search(ctx, st, A, -1);
+    if (ctx->any_normal_shooting)
+        k_search_shoot<<<resident_grid(ctx, kShootBlocksPerSm), kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count);
+    k_resolve<<<resident_grid(ctx, kResolveBlocksPerSm), kIterBlock, 0, st>>>(A, -1);
+    k_accumulate<<<resident_grid(ctx, kAccumulateBlocksPerSm), kIterBlock, 0, st>>>(A, -1);
     k_solve<<<cap_pairs, kSolveThreads, 0, st>>>(A, -1, (unsigned long long)handle);
     CK(cudaStreamEndCapture(st, nullptr));
     CK(cudaStreamBeginCaptureToGraph(st, ctx->graph, &while_node, nullptr, 1, cudaStreamCaptureModeThreadLocal));
-    k_posterior<<<cap_chunks, kIterBlock, 0, st>>>(A);
+    k_posterior<<<std::min(cap_chunks, chunk_bucket(ctx)), kIterBlock, 0, st>>>(A);
     k_finalize<<<(unsigned)ceil_div(cap_pairs, 64), 64, 0, st>>>(A, -1);
     k_collect<<<(unsigned)ceil_div(cap_pairs, 128), 128, 0, st>>>(A, -1, ctx->d_results);
     CK(cudaStreamEndCapture(st, nullptr));
@@ -916,6 +943,10 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         c = LoopCtl();
         c.n_it_chunks = (int)n_itc, c.n_pairs = np, c.trace_on = trace ? 1 : 0, c.max_iter = ctx->max_iter_max;
         CK(cudaMemcpyAsync(A.ctl, ctx->h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
+        if (n_itc) { // the chunks that own source points after the intersection filter: work list of iteration 0
+            k_live_init<<<(unsigned)ceil_div(n_itc, 256), 256, 0, st>>>(A);
+            ++launches;
+        }
     }
     const bool graphed = !hook && ctx->use_graph;
     if (graphed) {
@@ -946,9 +977,9 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            launch_search(ctx, n_itc, st, A, buf);
+            launch_search(ctx, st, A, buf);
             if (ctx->any_normal_shooting) {
-                k_search_shoot<<<n_itc, kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
+                k_search_shoot<<<resident_grid(ctx, kShootBlocksPerSm), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
                 ++launches;
             }
             CK(cudaEventRecord(ctx->ev_search[2 * it + 1], st));
@@ -958,7 +989,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
                     return MULLS_E_COMM;
                 }
             }
-            k_resolve<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            k_resolve<<<resident_grid(ctx, kResolveBlocksPerSm), kIterBlock, 0, st>>>(A, buf);
             if (hook) { // exchange 2: correspondence counts (w_ground, -2 test) and surviving source counts
                 k_shard_counts<<<1, kIterBlock, 0, st>>>(A, 0);
                 if (hook(user, A.xch_i32, 2 * kNumClasses, 1, 0, (void *)st) != 0) {
@@ -968,7 +999,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
                 k_shard_counts<<<1, kIterBlock, 0, st>>>(A, 1);
                 launches += 2;
             }
-            k_accumulate<<<n_itc, kIterBlock, 0, st>>>(A, buf);
+            k_accumulate<<<resident_grid(ctx, kAccumulateBlocksPerSm), kIterBlock, 0, st>>>(A, buf);
             k_solve<<<(unsigned)np, kSolveThreads, 0, st>>>(A, buf, 0ull);
             if (hook) { // exchange 3: per-class normal-equation sums; then every rank solves the same system
                 if (hook(user, A.xch_f64, kNumClasses * kTerms, 0, 0, (void *)st) != 0) {
@@ -1001,7 +1032,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         k_collect<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(A, np, ctx->d_results);
         ++launches;
     }
-    CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, np * sizeof(mulls_icp_result), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, np * (sizeof(mulls_icp_result) + sizeof(uint64_t)), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (trace) CK(cudaMemcpyAsync(trace, ctx->d_trace, np * sizeof(mulls_icp_trace), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev_end, st));
@@ -1033,11 +1064,10 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
     S.ms_search = ms;
     S.search_launches = (uint64_t)n_search_ev;
     for (int p = 0; p < np; ++p) S.iterations += (uint64_t)ctx->h_results[p].iters;
-    // algorithmic bytes are accumulated on the device per executed iteration
+    // algorithmic bytes are accumulated on the device per executed iteration (k_collect puts them behind the results)
     {
-        std::vector<PairState> hs(np);
-        CK(cudaMemcpy(hs.data(), A.ps, np * sizeof(PairState), cudaMemcpyDeviceToHost));
-        for (int p = 0; p < np; ++p) S.algorithmic_bytes += hs[p].alg_bytes;
+        const uint64_t *ab = reinterpret_cast<const uint64_t *>(ctx->h_results + np);
+        for (int p = 0; p < np; ++p) S.algorithmic_bytes += ab[p];
     }
     ctx->grid_valid = !hook;
     return MULLS_OK;
