@@ -133,6 +133,8 @@ struct DeviceArrays {
     float4 *tgt_pos, *tgt_nrm;       // target SoA, Morton-sorted inside each (pair,class) slice
     float4 *src_pos[2], *src_nrm[2]; // source SoA ping-pong
     int *src_prevj[2];               // previous NN target (seeds the next search with a real candidate)
+    float4 *src_cert[2];             // where the source stood at its last full search (xyz) and the radius inside which
+                                     // its match is the only target (w; 0: no certificate) — k_search keeps matches with it
     int *nn_idx;                     // per source: matched target (index inside its class slice) or -1
     float *nn_d2;
     uint8_t *flags;                  // bit0 kept as source point, bit1 correspondence passes rejectors

@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(256) k_gather(DeviceArrays A, const uint64_t *
         A.src_pos[0][d] = pos;
         A.src_nrm[0][d] = n2;
         A.src_prevj[0][d] = -1;
+        A.src_cert[0][d] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

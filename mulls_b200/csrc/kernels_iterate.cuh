@@ -218,21 +218,93 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
 
 // ---- k_search: I1 + I2a of the iteration — apply the previous increment to the source (:1260), exact
 //      radius-bounded 1-NN on the hashed multi-level grid (nn_search_walk, search_core.cuh — replaces the kd-tree query
-//      of :1745), claim the target for the duplicate check. One query per thread; 48 registers, 10 blocks per SM.
-// kMinBlocks: resident blocks per SM the register allocation is held to (10: 48 registers, 12: 40, 16: 32 + spills) —
-// the `search_blocks` tunable picks the instantiation
-// `sub`: which warp-sized quarter of the chunk this warp examines (the search needs no cooperation inside a block, so
-// the warps of k_search fetch their work one by one)
-__device__ __forceinline__ void search_chunk(DeviceArrays &A, int buf, uint32_t chunk, uint32_t sub, int start_level0, int leaf_count,
-                                             int defer_from_iter, float reseed_cells) {
+//      of :1745), claim the target for the duplicate check. Resident blocks fetch their work from the live list.
+// Iterations 0 .. kKeepFromIter-1 ("direct"): work unit = a quarter chunk (32 sources) per WARP, one query per lane,
+//   no cooperation and no barrier; the last of them also leaves a certificate per query (src_cert: where the query
+//   stood, and a radius inside which its match is the only target).
+// From iteration kKeepFromIter on ("keep"): work unit = a chunk per BLOCK, two passes:
+//   A  every source: transform, then try to KEEP the previous match without a search: if |p - q| + |p - p_ref| stays
+//      below the certificate radius, q is still the unique nearest target and its distance is computed directly (the
+//      result a search would return, bit for bit). Queries that cannot be kept are listed in shared memory;
+//   B  the listed queries, densely packed into the first threads of the block: seeded exact search, new certificate.
+//   Late iterations keep most matches (measured on the C2 pair: 41 / 54 / 86 % in iterations 3 / 4 / 5; ~100 % once
+//   converged), and what is kept costs the streaming pass A only.
+constexpr int kKeepFromIter = 3;
+
+struct SearchArgs {
+    int start_level0, leaf_count, defer_from_iter;
+    float reseed_cells;
+};
+
+// what is fixed for all queries of one (pair, class): grid, radius
+struct SearchFrame {
+    GridView g;
+    double max_dist_sqr; // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
+    float r2_prune;
+    bool defer;
+};
+__device__ __forceinline__ SearchFrame search_frame(const DeviceArrays &A, const PairConst &pc, const PairState &ps, int c, const SearchArgs &sa) {
+    SearchFrame f;
+    f.g = grid_of(A, pc, ps, c, sa.leaf_count);
+    const float max_distance_f = 2.5f * ps.thre;
+    f.max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
+    f.r2_prune = (float)f.max_dist_sqr * 1.0001f;
+    f.defer = ps.iter >= sa.defer_from_iter; // queueing a block's small cells pays once the seeds are good
+    return f;
+}
+
+// keep test of CorrespondenceEstimation + claim + result of one query
+__device__ __forceinline__ void search_finish(DeviceArrays &A, const PairConst &pc, int c, uint32_t gi, int best_j, float best_d2,
+                                              double max_dist_sqr, float orig_index_bits) {
+    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
+    if (best_j >= 0) {
+        // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
+        atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(orig_index_bits));
+    }
+    A.nn_idx[gi] = best_j;
+    A.nn_d2[gi] = best_d2;
+}
+
+// seeded exact search of one query (p already advanced). Seeds: the previous iteration's match (a real candidate, so
+// the box-distance pruning bites from the first cell on and the search only has to prove that nothing is closer); a
+// match that the last increment left far away (the big first corrections) is challenged by a fresh greedy descent.
+template <class Bounds>
+__device__ __forceinline__ void search_one(DeviceArrays &A, const PairConst &pc, int c, int buf, uint32_t gi, const float4 p,
+                                           float orig_bits, const SearchFrame &f, const SearchArgs &sa, bool write_cert) {
+    NoStats st;
+    int best_j = -1;
+    float best_d2 = INFINITY;
+    const int pj = A.src_prevj[buf][gi];
+    if (pj >= 0) {
+        const float4 q = __ldg(&f.g.pos[pj]);
+        best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
+        best_j = pj;
+    }
+    {
+        const float rs = sa.reseed_cells * f.g.h0;
+        if (best_j < 0 || best_d2 > rs * rs) {
+            float d2 = INFINITY;
+            int j = -1;
+            walk_greedy_seed(f.g, p.x, p.y, p.z, sa.start_level0, d2, j, st);
+            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
+        }
+    }
+    const float cert2 = nn_search_walk_b<Bounds>(f.g, p.x, p.y, p.z, f.r2_prune, sa.start_level0, f.defer, best_d2, best_j, st);
+    if (write_cert) A.src_cert[buf][gi] = make_float4(p.x, p.y, p.z, sqrtf(cert2));
+    search_finish(A, pc, c, gi, best_j, best_d2, f.max_dist_sqr, orig_bits);
+}
+
+// direct mode: one warp, 32 consecutive sources of a chunk
+template <class Bounds>
+__device__ __forceinline__ void search_quarter(DeviceArrays &A, int buf, uint32_t chunk, uint32_t sub, const SearchArgs &sa, bool write_cert) {
     const ChunkDesc cd = A.it_chunks[chunk];
     const PairConst &pc = A.pc[cd.pair];
     const PairState &ps = A.ps[cd.pair];
     if (ps.status != kRunning || A.hash_used[1]) return;
     const int c = (int)cd.seg;
     const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
-    if ((int)cd.first >= ns) return; // block-uniform
-    if (shoots(pc, c)) return;       // block-uniform: k_search_shoot's work
+    if ((int)cd.first >= ns) return; // warp-uniform
+    if (shoots(pc, c)) return;       // warp-uniform: k_search_shoot's work
     const uint32_t local = cd.first + 32u * sub + (threadIdx.x & 31u);
     const bool valid = (int)local < ns;
     const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
@@ -245,61 +317,103 @@ __device__ __forceinline__ void search_chunk(DeviceArrays &A, int buf, uint32_t 
         A.nn_d2[gi] = INFINITY;
         return;
     }
-    const GridView g = grid_of(A, pc, ps, c, leaf_count);
-    // CorrespondenceEstimation keeps d2 <= (2.5*thre)^2, evaluated in double (:1745, PCL)
-    const float max_distance_f = 2.5f * ps.thre;
-    const double max_dist_sqr = (double)max_distance_f * (double)max_distance_f;
-    const float r2_prune = (float)max_dist_sqr * 1.0001f;
-    // seeds: the previous iteration's match (a real candidate, so the box-distance pruning bites from the first
-    // cell on and the search only has to prove that nothing is closer); a match that the last increment left far
-    // away (the big first corrections) is challenged by a fresh greedy descent
-    NoStats st;
-    int best_j = -1;
-    float best_d2 = INFINITY;
-    const int pj = A.src_prevj[buf][gi];
-    if (pj >= 0) {
-        const float4 q = __ldg(&g.pos[pj]);
-        best_d2 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
-        best_j = pj;
-    }
-    {
-        const float rs = reseed_cells * g.h0;
-        if (best_j < 0 || best_d2 > rs * rs) {
-            float d2 = INFINITY;
-            int j = -1;
-            walk_greedy_seed(g, p.x, p.y, p.z, start_level0, d2, j, st);
-            if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
-        }
-    }
-    // queueing a block's small cells pays once the seeds are good (the big first corrections have been applied)
-    nn_search_walk(g, p.x, p.y, p.z, r2_prune, start_level0, ps.iter >= defer_from_iter, best_d2, best_j, st);
-    if (best_j >= 0 && !((double)best_d2 <= max_dist_sqr)) best_j = -1;
-    if (best_j >= 0) {
-        // duplicate_check_table as a claim: the lowest source index wins (:1762-1786, Q5)
-        atomicMin(&A.claim[pc.tgt_base[c] + best_j], (unsigned)__float_as_int(n.w));
-    }
-    A.nn_idx[gi] = best_j;
-    A.nn_d2[gi] = best_d2;
+    const SearchFrame f = search_frame(A, pc, ps, c, sa);
+    search_one<Bounds>(A, pc, c, buf, gi, p, n.w, f, sa, write_cert);
 }
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kIterBlock, kMinBlocks) k_search(DeviceArrays A, int buf, int start_level0, int leaf_count,
-                                                                  int defer_from_iter, float reseed_cells) {
+
+// keep mode: one block, one chunk. need_list / n_need live in shared memory.
+__device__ __forceinline__ void search_keep_chunk(DeviceArrays &A, int buf, uint32_t chunk, const SearchArgs &sa, uint8_t *need_list,
+                                                  uint32_t *n_need) {
+    const ChunkDesc cd = A.it_chunks[chunk];
+    const PairConst &pc = A.pc[cd.pair];
+    const PairState &ps = A.ps[cd.pair];
+    if (ps.status != kRunning || A.hash_used[1]) return; // block-uniform, like the two below
+    const int c = (int)cd.seg;
+    const int ns = ps.n_src[c], nt = ps.n_tgt[c], nsg = ps.n_src_g[c];
+    if ((int)cd.first >= ns) return;
+    if (shoots(pc, c)) return;
+    const int lane = threadIdx.x & 31;
+    const bool active = pc.used[c] && nsg >= 3 && nt >= 3;
+    const SearchFrame f = search_frame(A, pc, ps, c, sa);
+    if (threadIdx.x == 0) *n_need = 0u;
+    __syncthreads();
+    // ---- pass A
+    {
+        const uint32_t local = cd.first + threadIdx.x;
+        const bool valid = (int)local < ns;
+        const uint32_t gi = pc.src_base[c] + (valid ? local : 0);
+        float4 p, n;
+        load_and_advance(A, ps, buf, gi, valid, p, n);
+        bool need = false;
+        if (valid) {
+            if (!active) {
+                A.nn_idx[gi] = -1;
+                A.nn_d2[gi] = INFINITY;
+            } else {
+                need = true;
+                const int pj = A.src_prevj[buf][gi];
+                const float4 ce = A.src_cert[buf][gi]; // p_ref, certificate radius (0: none)
+                if (pj >= 0 && ce.w > 0.0f) {
+                    const float4 q = __ldg(&f.g.pos[pj]);
+                    const float d1 = flann_l2(p.x, p.y, p.z, q.x, q.y, q.z);
+                    const float mv = flann_l2(p.x, p.y, p.z, ce.x, ce.y, ce.z);
+                    // every other target t: |p - t| >= |p_ref - t| - |p - p_ref| >= radius - moved. The factors and the
+                    // 3e-5 m absorb the float evaluation of all the distances involved (coordinates < 1 km)
+                    if ((sqrtf(d1) + sqrtf(mv)) * 1.0001f + 3e-5f < ce.w * 0.9999f) {
+                        search_finish(A, pc, c, gi, pj, d1, f.max_dist_sqr, n.w);
+                        need = false;
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(n_need, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) need_list[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)threadIdx.x;
+    }
+    __syncthreads();
+    // ---- pass B: the listed queries fill the first threads (whole warps stay out when few are left)
+    if (threadIdx.x < *n_need) {
+        const uint32_t gi = pc.src_base[c] + cd.first + need_list[threadIdx.x];
+        const float4 p = A.src_pos[buf][gi]; // (advanced by pass A)
+        search_one<WalkBounds>(A, pc, c, buf, gi, p, A.src_nrm[buf][gi].w, f, sa, true);
+    }
+}
+
+// One kernel per mode (own register allocation each): 0 = direct, 1 = direct + certificate, 2 = keep. The iteration
+// graph holds all three; the two that are not this iteration's return at once.
+constexpr int kSearchBlocksPerSm = 12; // 40 registers (measured against 10 / 16 blocks: 4.36 / 4.31 / 4.61 ms per 64-pair step)
+__device__ __forceinline__ int search_mode_of(int it) { return it >= kKeepFromIter ? 2 : (it == kKeepFromIter - 1 ? 1 : 0); }
+
+template <int kMode>
+__global__ void __launch_bounds__(kIterBlock, kSearchBlocksPerSm) k_search(DeviceArrays A, int buf, int it, int start_level0, int leaf_count,
+                                                                          int defer_from_iter, float reseed_cells) {
     buf = loop_buf(A, buf);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { // first kernel of the iteration: counters and list the later ones use
+    if (it < 0) it = A.ctl->it; // (graph: the device-side loop counter; every running pair is in this iteration)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // first kernel(s) of the iteration: counters and list the later ones use
         LoopCtl &ctl = *A.ctl;
         ctl.work[1] = ctl.work[2] = ctl.work[3] = 0u;
         ctl.n_live[buf ^ 1] = 0u;
     }
-    // work unit = a quarter chunk (32 sources), fetched per warp: no barrier, a warp that finishes early moves on
-    const uint32_t n_units = (kIterBlock / 32) * A.ctl->n_live[buf];
-    const uint32_t *list = A.live_chunks + (size_t)buf * A.live_stride;
-    for (;;) {
-        uint32_t u = 0;
-        if ((threadIdx.x & 31) == 0) u = atomicAdd(&A.ctl->work[0], 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= n_units) break;
-        search_chunk(A, buf, list[u / (kIterBlock / 32)], u % (kIterBlock / 32), start_level0, leaf_count, defer_from_iter, reseed_cells);
-        __syncwarp();
+    if (search_mode_of(it) != kMode) return;
+    const SearchArgs sa = {start_level0, leaf_count, defer_from_iter, reseed_cells};
+    if (kMode == 2) {
+        __shared__ uint8_t s_need[kIterBlock];
+        __shared__ uint32_t s_n_need;
+        for_each_live_chunk(A, buf, 0, [&](uint32_t chunk) { search_keep_chunk(A, buf, chunk, sa, s_need, &s_n_need); });
+    } else {
+        const uint32_t n_units = (kIterBlock / 32) * A.ctl->n_live[buf];
+        const uint32_t *list = A.live_chunks + (size_t)buf * A.live_stride;
+        for (;;) { // fetched per warp: no barrier, a warp that finishes early moves on
+            uint32_t u = 0;
+            if ((threadIdx.x & 31) == 0) u = atomicAdd(&A.ctl->work[0], 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= n_units) break;
+            if (kMode == 1) search_quarter<WalkBounds>(A, buf, list[u / (kIterBlock / 32)], u % (kIterBlock / 32), sa, true);
+            else search_quarter<NoBounds>(A, buf, list[u / (kIterBlock / 32)], u % (kIterBlock / 32), sa, false);
+            __syncwarp();
+        }
     }
 }
 
@@ -817,6 +931,7 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
         A.src_pos[buf ^ 1][gd] = p;
         A.src_nrm[buf ^ 1][gd] = n;
         A.src_prevj[buf ^ 1][gd] = j;
+        A.src_cert[buf ^ 1][gd] = A.src_cert[buf][gi];
         A.corr_j[gd] = pass ? j : -1;
         A.corr_w[gd] = w_store;
     }

@@ -296,6 +296,7 @@ mulls_ctx *mulls_create(int device, size_t max_pairs, size_t max_src_pts, size_t
         ALLOC(A.src_pos[b], cs);
         ALLOC(A.src_nrm[b], cs);
         ALLOC(A.src_prevj[b], cs);
+        ALLOC(A.src_cert[b], cs);
     }
     ALLOC(A.nn_idx, cs);
     ALLOC(A.nn_d2, cs);
@@ -443,7 +444,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "leaf_count") ctx->leaf_count = value;
     else if (n == "reseed_cells_x4") ctx->reseed_cells_x4 = value;
     else if (n == "defer_from_iter") ctx->defer_from_iter = value;
-    else if (n == "search_blocks") ctx->search_blocks = value;
+    else if (n == "search_blocks") ctx->search_blocks = value; // (kept for old scripts: the instantiations are fixed now)
     else if (n == "sort_sources") ctx->sort_sources = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
     else if (n == "use_graph") ctx->use_graph = value;
@@ -863,14 +864,15 @@ static unsigned chunk_bucket(const mulls_ctx *ctx) {
 static unsigned resident_grid(const mulls_ctx *ctx, int blocks_per_sm) {
     return std::min((unsigned)(ctx->num_sms * blocks_per_sm), chunk_bucket(ctx));
 }
-static void launch_search(mulls_ctx *ctx, cudaStream_t st, const DeviceArrays &A, int buf) {
+// it < 0 (recording the iteration graph): all three modes, each checks the device-side iteration counter; the host
+// launch loop knows the iteration and launches the one that runs
+static void launch_search(mulls_ctx *ctx, cudaStream_t st, const DeviceArrays &A, int buf, int it) {
     const float reseed = 0.25f * (float)ctx->reseed_cells_x4;
-    if (ctx->search_blocks >= 16)
-        k_search<16><<<resident_grid(ctx, 16), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
-    else if (ctx->search_blocks >= 12)
-        k_search<12><<<resident_grid(ctx, 12), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
-    else
-        k_search<10><<<resident_grid(ctx, 10), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+    const unsigned grid = resident_grid(ctx, kSearchBlocksPerSm);
+    const int mode = it < 0 ? -1 : (it >= kKeepFromIter ? 2 : (it == kKeepFromIter - 1 ? 1 : 0));
+    if (mode < 0 || mode == 0) k_search<0><<<grid, kIterBlock, 0, st>>>(A, buf, it, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+    if (mode < 0 || mode == 1) k_search<1><<<grid, kIterBlock, 0, st>>>(A, buf, it, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
+    if (mode < 0 || mode == 2) k_search<2><<<grid, kIterBlock, 0, st>>>(A, buf, it, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
 }
 constexpr int kShootBlocksPerSm = 8, kResolveBlocksPerSm = 16, kAccumulateBlocksPerSm = 5;
 
@@ -898,7 +900,7 @@ static int build_iteration_graph(mulls_ctx *ctx) {
     CK(cudaGraphAddNode(&while_node, ctx->graph, nullptr, 0, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    launch_search(ctx, st, A, -1);
+    launch_search(ctx, st, A, -1, -1);
     if (ctx->any_normal_shooting)
         k_search_shoot<<<resident_grid(ctx, kShootBlocksPerSm), kIterBlock, 0, st>>>(A, -1, ctx->start_level0, ctx->leaf_count);
     k_resolve<<<resident_grid(ctx, kResolveBlocksPerSm), kIterBlock, 0, st>>>(A, -1);
@@ -977,7 +979,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             if (hook) // other ranks' claims of the previous iteration must not survive in this rank's table
                 CK(cudaMemsetAsync(A.claim, 0x7f, std::max<size_t>(ctx->n_tgt_total, 1) * sizeof(unsigned), st));
             CK(cudaEventRecord(ctx->ev_search[2 * it], st));
-            launch_search(ctx, st, A, buf);
+            launch_search(ctx, st, A, buf, it);
             if (ctx->any_normal_shooting) {
                 k_search_shoot<<<resident_grid(ctx, kShootBlocksPerSm), kIterBlock, 0, st>>>(A, buf, ctx->start_level0, ctx->leaf_count);
                 ++launches;

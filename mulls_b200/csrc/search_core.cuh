@@ -144,15 +144,38 @@ MULLS_HD int highest_bit(uint32_t v) {
 constexpr int kWalkStack = 48; // DFS entries: at most 7 stay behind per descended level
 constexpr int kWalkQueue = 8;  // small cells of one block whose scan is deferred to the end of its traversal
 
+// What a finished search knows beyond its answer (all squared distances from the query): `second` — the closest
+// examined candidate other than the answer; `pruned` — the closest cell (box distance) that was left out because it
+// could not beat the bound. With the coverage radius of the last block they bound from below the distance of EVERY
+// target other than the answer: the certificate that lets a later iteration keep the match without searching
+// (k_search: a query that has moved by delta keeps its match q if |p - q| + delta < that bound).
+struct WalkBounds {
+    float second = INFINITY, pruned = INFINITY;
+    MULLS_HD void see(float d2) { second = fminf(second, d2); }
+    MULLS_HD void prune(float d2) { pruned = fminf(pruned, d2); }
+    MULLS_HD float radius2(float cover2) const { return fminf(fminf(second, pruned), cover2); }
+};
+// the same interface doing nothing: searches whose certificate nobody will read (the first iterations)
+struct NoBounds {
+    MULLS_HD void see(float) {}
+    MULLS_HD void prune(float) {}
+    MULLS_HD float radius2(float) const { return 0.0f; }
+};
+
 // one candidate under the total order (FLANN float distance, original index)
-MULLS_HD void walk_consider(const GridView &g, float d2, uint32_t jj, float &best_d2, int &best_j) {
+template <class Bounds>
+MULLS_HD void walk_consider(const GridView &g, float d2, uint32_t jj, float &best_d2, int &best_j, Bounds &wb) {
     if (d2 < best_d2) {
+        wb.see(best_d2); // (the displaced candidate; +inf while there was none)
         best_d2 = d2;
         best_j = (int)jj;
-    } else if (d2 == best_d2 && best_j >= 0 && (int)jj != best_j) {
-        const int oj = f2i_bits(ld_point(&g.nrm[jj]).w);
-        const int ob = f2i_bits(ld_point(&g.nrm[best_j]).w);
-        if (oj < ob) best_j = (int)jj;
+    } else if ((int)jj != best_j) {
+        wb.see(d2);
+        if (d2 == best_d2 && best_j >= 0) {
+            const int oj = f2i_bits(ld_point(&g.nrm[jj]).w);
+            const int ob = f2i_bits(ld_point(&g.nrm[best_j]).w);
+            if (oj < ob) best_j = (int)jj;
+        }
     }
 }
 
@@ -173,8 +196,9 @@ MULLS_HD float approx_l2(float px, float py, float pz, float qx, float qy, float
 // a real candidate as the seed that is the exception. The last group of a cell may read up to two points past the
 // cell (their estimates are replaced by +inf): the position array carries kScanOverrun spare elements at its end.
 constexpr int kScanOverrun = 4;
+template <class Bounds>
 MULLS_HD void walk_scan_leaf(const GridView &g, float px, float py, float pz, uint32_t start, uint32_t count, float &best_d2,
-                             int &best_j) {
+                             int &best_j, Bounds &wb) {
     const uint32_t end = start + count;
     uint32_t jj = start;
     for (; jj + 4 <= end; jj += 4) {
@@ -183,11 +207,14 @@ MULLS_HD void walk_scan_leaf(const GridView &g, float px, float py, float pz, ui
         const float a0 = approx_l2(px, py, pz, q0.x, q0.y, q0.z), a1 = approx_l2(px, py, pz, q1.x, q1.y, q1.z);
         const float a2 = approx_l2(px, py, pz, q2.x, q2.y, q2.z), a3 = approx_l2(px, py, pz, q3.x, q3.y, q3.z);
         const float m = fminf(fminf(a0, a1), fminf(a2, a3));
-        if (m * 0.999999f <= best_d2) {
-            walk_consider(g, flann_l2(px, py, pz, q0.x, q0.y, q0.z), jj, best_d2, best_j);
-            walk_consider(g, flann_l2(px, py, pz, q1.x, q1.y, q1.z), jj + 1, best_d2, best_j);
-            walk_consider(g, flann_l2(px, py, pz, q2.x, q2.y, q2.z), jj + 2, best_d2, best_j);
-            walk_consider(g, flann_l2(px, py, pz, q3.x, q3.y, q3.z), jj + 3, best_d2, best_j);
+        const float ml = m * 0.999999f; // below the exact float distance of every point of the group
+        if (ml <= best_d2) {
+            walk_consider(g, flann_l2(px, py, pz, q0.x, q0.y, q0.z), jj, best_d2, best_j, wb);
+            walk_consider(g, flann_l2(px, py, pz, q1.x, q1.y, q1.z), jj + 1, best_d2, best_j, wb);
+            walk_consider(g, flann_l2(px, py, pz, q2.x, q2.y, q2.z), jj + 2, best_d2, best_j, wb);
+            walk_consider(g, flann_l2(px, py, pz, q3.x, q3.y, q3.z), jj + 3, best_d2, best_j, wb);
+        } else {
+            wb.see(ml);
         }
     }
     if (jj < end) { // 1..3 points left
@@ -198,10 +225,13 @@ MULLS_HD void walk_scan_leaf(const GridView &g, float px, float py, float pz, ui
         const float a1 = v1 ? approx_l2(px, py, pz, q1.x, q1.y, q1.z) : INFINITY;
         const float a2 = v2 ? approx_l2(px, py, pz, q2.x, q2.y, q2.z) : INFINITY;
         const float m = fminf(a0, fminf(a1, a2));
-        if (m * 0.999999f <= best_d2) {
-            walk_consider(g, flann_l2(px, py, pz, q0.x, q0.y, q0.z), jj, best_d2, best_j);
-            if (v1) walk_consider(g, flann_l2(px, py, pz, q1.x, q1.y, q1.z), jj + 1, best_d2, best_j);
-            if (v2) walk_consider(g, flann_l2(px, py, pz, q2.x, q2.y, q2.z), jj + 2, best_d2, best_j);
+        const float ml = m * 0.999999f;
+        if (ml <= best_d2) {
+            walk_consider(g, flann_l2(px, py, pz, q0.x, q0.y, q0.z), jj, best_d2, best_j, wb);
+            if (v1) walk_consider(g, flann_l2(px, py, pz, q1.x, q1.y, q1.z), jj + 1, best_d2, best_j, wb);
+            if (v2) walk_consider(g, flann_l2(px, py, pz, q2.x, q2.y, q2.z), jj + 2, best_d2, best_j, wb);
+        } else {
+            wb.see(ml);
         }
     }
 }
@@ -226,7 +256,8 @@ MULLS_HD void walk_greedy_seed(const GridView &g, float px, float py, float pz, 
             if (!probe_cell(g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, lv, start, count, cmask)) break; // only possible at lv == lr
             if (count <= (uint32_t)g.leaf_count || lv == 0) {
                 st.seed_eval((int)count);
-                walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
+                NoBounds unused; // (the exact search that follows examines this cell again)
+                walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j, unused);
                 break;
             }
             const float hl = g.h0 * (float)(1 << lv);
@@ -249,9 +280,12 @@ MULLS_HD float walk_axis_dist(float o, float H, int x, float p, float margin) {
 
 // best_d2 / best_j come in seeded: (INFINITY, -1) or a real candidate. defer_scan: queue the small cells of a block
 // and examine them together after its traversal (pays once the seeds are good).
-template <class Stats>
-MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, float r2_prune, int start_level, bool defer_scan,
-                             float &best_d2, int &best_j, Stats &st) {
+// Returns the squared certificate radius: every target other than the answer is at least that far (squared) from p
+// (Bounds = WalkBounds; with NoBounds nothing is tracked and 0 — no certificate — is returned).
+template <class Bounds, class Stats>
+MULLS_HD float nn_search_walk_b(const GridView &g, float px, float py, float pz, float r2_prune, int start_level, bool defer_scan,
+                                float &best_d2, int &best_j, Stats &st) {
+    Bounds wb = Bounds();
     const float fx = (px - g.ox) * g.inv_h0, fy = (py - g.oy) * g.inv_h0, fz = (pz - g.oz) * g.inv_h0;
     const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     const int c0x = (int)flx, c0y = (int)fly, c0z = (int)flz;
@@ -309,7 +343,11 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
-                if (vx[i] && vy[j] && vz[m] && ex[i] + ey[j] + ez[m] <= bound0) live |= 1u << k;
+                const float dk = ex[i] + ey[j] + ez[m];
+                if (vx[i] && vy[j] && vz[m]) {
+                    if (dk <= bound0) live |= 1u << k;
+                    else wb.prune(dk);
+                }
             }
         }
 #pragma unroll 1
@@ -325,7 +363,10 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
             while (sp > 0) {
                 --sp;
                 // a cell farther than the best so far (or than the radius) cannot change the result
-                if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) continue;
+                if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) {
+                    wb.prune(st_d2[sp]);
+                    continue;
+                }
                 const uint32_t cell = st_cell[sp], meta = st_meta[sp];
                 uint32_t start, count, cmask;
                 st.probe();
@@ -338,7 +379,7 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
                         ++nq;
                     } else {
                         st.eval((int)count);
-                        walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j);
+                        walk_scan_leaf(g, px, py, pz, start, count, best_d2, best_j, wb);
                     }
                 } else {
                     st.expand();
@@ -358,8 +399,11 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
                     // children that exist and can still beat the bound, as a bit mask ...
                     uint32_t pass = 0;
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                        if (ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2] <= bound) pass |= 1u << ch;
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float dc = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
+                        if (dc <= bound) pass |= 1u << ch;
+                        else if ((cmask >> ch) & 1u) wb.prune(dc);
+                    }
                     pass &= cmask;
                     // ... re-indexed by c = ch ^ near_child (bit permutation by conditional swaps), so that the
                     // highest set bit is the farthest octant: pushed first, the nearest one last (popped first)
@@ -382,15 +426,20 @@ MULLS_HD void nn_search_walk(const GridView &g, float px, float py, float pz, fl
         // the queued small cells of this block
         for (int qi = 0; qi < nq; ++qi) {
             st.eval((int)q_count[qi]);
-            walk_scan_leaf(g, px, py, pz, q_start[qi], q_count[qi], best_d2, best_j);
+            walk_scan_leaf(g, px, py, pz, q_start[qi], q_count[qi], best_d2, best_j, wb);
         }
         nq = 0;
         const float cover = (l == 0) ? 0.998f * 0.5f * g.h0 : 0.999f * 0.5f * H; // every closer target has been examined
         const float cover2 = cover * cover;
-        if (best_d2 <= cover2) break;  // the best found is the global nearest
-        if (cover2 >= r2_prune) break; // whole search radius examined
-        if (l == L - 1) break;         // (n_levels is chosen so that the line above fires first)
+        // every target outside the block is farther than `cover`; inside it, what was not examined is behind `pruned`
+        if (best_d2 <= cover2 || cover2 >= r2_prune || l == L - 1) // (global nearest found / whole radius examined / top)
+            return wb.radius2(cover2);
     }
+}
+template <class Stats>
+MULLS_HD float nn_search_walk(const GridView &g, float px, float py, float pz, float r2_prune, int start_level, bool defer_scan,
+                              float &best_d2, int &best_j, Stats &st) {
+    return nn_search_walk_b<WalkBounds>(g, px, py, pz, r2_prune, start_level, defer_scan, best_d2, best_j, st);
 }
 
 } // namespace mulls

@@ -116,8 +116,9 @@ void sh_grid_info(void *h, uint64_t *out /*[3]: cells, table capacity, sum of in
 // q: m x 3 floats. seed: original target index of a candidate or -1 (may be null). Results as ORIGINAL target indices.
 // reseed_d2: a seeded query whose seed is farther than this also tries the greedy seed (negative: never) — the seeding
 // rule of k_search. stats[10] on entry: 1 = queue the small cells of a block (k_search from iteration defer_from_iter on).
-int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_prune, int start_level, float reseed_d2,
-              int *out_idx, float *out_d2, uint64_t *stats /*[12]*/, uint32_t *evals_per_query /*[m] or null*/) {
+// cert (may be null): the squared certificate radius of every query (nn_search_walk's return value).
+int sh_search_cert(void *h, const float *q, const int *seed, uint32_t m, float r2_prune, int start_level, float reseed_d2,
+                   int *out_idx, float *out_d2, uint64_t *stats /*[12]*/, uint32_t *evals_per_query /*[m] or null*/, float *cert) {
     HostGrid *G = (HostGrid *)h;
     const GridView &g = G->g;
     Counters C;
@@ -138,7 +139,8 @@ int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_pru
             if (j >= 0 && d2 < best_d2) best_d2 = d2, best_j = j;
         }
         C.cur_evals = 0;
-        nn_search_walk(g, px, py, pz, r2_prune, start_level, defer, best_d2, best_j, C);
+        const float c2 = nn_search_walk(g, px, py, pz, r2_prune, start_level, defer, best_d2, best_j, C);
+        if (cert) cert[i] = c2;
         C.max_evals_query = std::max(C.max_evals_query, C.cur_evals);
         if (evals_per_query) evals_per_query[i] = (uint32_t)C.cur_evals;
         out_d2[i] = best_d2;
@@ -153,6 +155,11 @@ int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_pru
     stats[0] = C.probes, stats[2] = C.evals, stats[3] = C.expands, stats[4] = C.levels;
     stats[6] = C.seed_probes, stats[7] = C.seed_evals, stats[8] = C.max_evals_query;
     return 0;
+}
+
+int sh_search(void *h, const float *q, const int *seed, uint32_t m, float r2_prune, int start_level, float reseed_d2,
+              int *out_idx, float *out_d2, uint64_t *stats /*[12]*/, uint32_t *evals_per_query /*[m] or null*/) {
+    return sh_search_cert(h, q, seed, m, r2_prune, start_level, reseed_d2, out_idx, out_d2, stats, evals_per_query, nullptr);
 }
 
 uint32_t sh_morton_roundtrip(uint32_t v) { return compact12(spread12(v)) == (v & 0xfffu) && compact12(spread12(v) << 1 >> 1) == (v & 0xfffu); }

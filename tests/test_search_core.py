@@ -31,6 +31,7 @@ def lib():
     lb.sh_free.argtypes = [C.c_void_p]
     lb.sh_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p]
+    lb.sh_search_cert.argtypes = lb.sh_search.argtypes + [C.c_void_p]
     lb.sh_morton_roundtrip.restype = C.c_uint32
     lb.sh_morton_roundtrip.argtypes = [C.c_uint32]
     return lb
@@ -43,7 +44,7 @@ def n_levels(h0, radius):
     return L
 
 
-def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0, mode=0):
+def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0, mode=0, want_cert=False):
     tgt_xyz = np.ascontiguousarray(tgt_xyz, np.float32)
     q_xyz = np.ascontiguousarray(q_xyz, np.float32)
     origin = (tgt_xyz.min(0) - 2 * h0).astype(np.float32)
@@ -58,10 +59,11 @@ def run(lib, tgt_xyz, q_xyz, radius, seeds=None, leaf=32, h0=0.125, reseed=-1.0,
     r = np.float32(radius)
     r2 = np.float32(np.float32(np.float64(r) * np.float64(r)) * np.float32(1.0001))
     sd = np.ascontiguousarray(seeds, np.int32) if seeds is not None else None
-    lib.sh_search(G, q_xyz.ctypes.data, sd.ctypes.data if sd is not None else None, m, float(r2), 5, float(reseed),
-                  idx.ctypes.data, d2.ctypes.data, stats.ctypes.data, None)
+    cert = np.empty(m, np.float32)
+    lib.sh_search_cert(G, q_xyz.ctypes.data, sd.ctypes.data if sd is not None else None, m, float(r2), 5, float(reseed),
+                       idx.ctypes.data, d2.ctypes.data, stats.ctypes.data, None, cert.ctypes.data)
     lib.sh_free(G)
-    return idx, d2
+    return (idx, d2, cert) if want_cert else (idx, d2)
 
 
 def brute(tgt_xyz, q_xyz):
@@ -149,3 +151,58 @@ def test_synthetic_pair_equals_oracle_kdtree(lib):
         oi2, od2 = oracle.nn(tgt, moved, 1e9)
         idx2, d22 = run(lib, tgt[:, :3], moved[:, :3], 1.25, seeds=oi, reseed=0.0625)
         check(idx2, d22, oi2, od2, 1.25)
+
+
+def second_nearest_sq(tgt_xyz, q_xyz, best):
+    """exact (float64) squared distance of the closest target other than `best` (or of the closest, where best < 0)"""
+    t = np.asarray(tgt_xyz, np.float64)
+    out = np.empty(len(q_xyz))
+    for k, p in enumerate(np.asarray(q_xyz, np.float64)):
+        d2 = ((t - p) ** 2).sum(1)
+        if best[k] >= 0:
+            d2[best[k]] = np.inf
+        out[k] = d2.min()
+    return out
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_certificate_is_a_lower_bound_on_every_other_target(lib, seed):
+    """nn_search_walk's return value: no target other than the answer is closer than it — what lets k_search keep a
+    match in a later iteration without searching (|p - q| + movement < certificate)."""
+    rng = np.random.default_rng(seed)
+    plane = np.c_[rng.uniform(-20, 20, 5000), rng.uniform(-20, 20, 5000), rng.normal(0, 0.02, 5000)]
+    wall = np.c_[rng.uniform(-20, 20, 3000), np.full(3000, 7.5) + rng.normal(0, 0.02, 3000), rng.uniform(0, 6, 3000)]
+    dense = rng.normal(0, 0.15, (3000, 3)) + [3.0, 2.0, 0.5]
+    tgt = np.concatenate([plane, wall, dense, plane[:100]]).astype(np.float32)
+    q = np.concatenate([tgt[rng.integers(0, len(tgt), 2000)] + rng.normal(0, 0.05, (2000, 3)),
+                        rng.uniform(-25, 25, (500, 3))]).astype(np.float32)
+    bi, _ = brute(tgt, q)
+    for radius in (3.5, 0.6):
+        for leaf in (32, 4):
+            for mode in (0, 1):
+                for seeds in (None, bi):
+                    idx, d2, cert = run(lib, tgt, q, radius, seeds=seeds, leaf=leaf, mode=mode, want_cert=True)
+                    others = second_nearest_sq(tgt, q, idx)
+                    assert np.all(cert.astype(np.float64) <= others * (1 + 1e-5) + 1e-9)
+                    useful = (idx >= 0) & (cert > d2 * 1.05)
+                    assert useful.mean() > 0.3  # and it is not vacuous: a real margin for a good share of the queries
+
+
+def test_a_kept_match_equals_a_fresh_search(lib):
+    """the skip rule of k_search on the host: queries move a little; where |p' - q| + |p' - p| stays below the
+    certificate the previous match must be what a fresh search (and brute force) returns"""
+    rng = np.random.default_rng(11)
+    pair = synth.make_pair(1000, "small")
+    tgt, src = pair["tgt"][0][:, :3], pair["src"][0][:, :3]
+    idx, d2, cert = run(lib, tgt, src, 1.5, want_cert=True)
+    kept_total = 0
+    for step in (0.002, 0.01, 0.05):
+        moved = (src + rng.normal(0, step, src.shape)).astype(np.float32)
+        bi, bd = brute(tgt, moved)
+        m = idx >= 0
+        d1 = np.sqrt(((moved[m].astype(np.float64) - tgt[idx[m]].astype(np.float64)) ** 2).sum(1))
+        delta = np.sqrt(((moved[m].astype(np.float64) - src[m].astype(np.float64)) ** 2).sum(1))
+        keep = (d1 + delta) * 1.0001 + 3e-5 < np.sqrt(cert[m].astype(np.float64)) * 0.9999
+        assert np.array_equal(bi[m][keep], idx[m][keep])
+        kept_total += int(keep.sum())
+    assert kept_total > 0.5 * len(src)
