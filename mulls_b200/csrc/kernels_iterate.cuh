@@ -82,6 +82,7 @@ __device__ __forceinline__ GridView grid_of(const DeviceArrays &A, const PairCon
     g.h0 = ps.h0, g.inv_h0 = ps.inv_h0;
     g.n_levels = ps.n_levels;
     g.leaf_count = leaf_count;
+    g.level_slack2 = 1.002001f;
     return g;
 }
 
@@ -228,7 +229,10 @@ __device__ __forceinline__ bool shoots(const PairConst &pc, int c) {
 //      result a search would return, bit for bit). Queries that cannot be kept are listed in shared memory;
 //   B  the listed queries, densely packed into the first threads of the block: seeded exact search, new certificate.
 //   Late iterations keep most matches (measured on the C2 pair: 41 / 54 / 86 % in iterations 3 / 4 / 5; ~100 % once
-//   converged), and what is kept costs the streaming pass A only.
+//   converged), and what is kept costs the streaming pass A only. (A variant with pass B fed from ONE queue in HBM —
+//   dense warps whatever chunk a source comes from, no barrier — measured slower: 0.58 / 0.46 / 0.28 ms against
+//   0.37 / 0.28 / 0.16 for iterations 3 / 4 / 5; the queue interleaves chunks, and the locality of a warp's 32 queries
+//   is worth more than its density.)
 constexpr int kKeepFromIter = 3;
 
 struct SearchArgs {

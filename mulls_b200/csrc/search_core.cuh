@@ -50,6 +50,7 @@ struct GridView {
     float ox, oy, oz, h0, inv_h0;
     int n_levels;
     int leaf_count; // cells with at most this many points are scanned, larger ones are split
+    float level_slack2; // >= 1.002001: the start level's coverage must reach sqrt(level_slack2) x the seed distance
 };
 
 struct NoStats {
@@ -131,6 +132,22 @@ MULLS_HD float slab_dist(float lo, float hi, float p, float margin) {
 MULLS_HD uint2 pack_cell(uint32_t x, uint32_t y, uint32_t z, int lv, uint32_t cmask) {
     return make_uint2(cell_key_lo(x, y, z), (z >> 8) | ((uint32_t)lv << 4) | (cmask << 8));
 }
+
+MULLS_HD float i2f_bits(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union {
+        uint32_t u;
+        float f;
+    } c;
+    c.u = u;
+    return c.f;
+#endif
+}
+// second key word of a cell (8 significant bits: z >> 8 | (level + 1) << 4) + the upper 24 bits of a non-negative float
+MULLS_HD uint32_t pack_meta(uint32_t khi, float d2) { return (khi & 0xffu) | ((uint32_t)f2i_bits(d2) & 0xffffff00u); }
+MULLS_HD float meta_d2(uint32_t packed) { return i2f_bits(packed & 0xffffff00u); }
 
 // index of the highest set bit (v != 0)
 MULLS_HD int highest_bit(uint32_t v) {
@@ -291,9 +308,9 @@ MULLS_HD float nn_search_walk_b(const GridView &g, float px, float py, float pz,
     const int c0x = (int)flx, c0y = (int)fly, c0z = (int)flz;
     const int L = g.n_levels;
     const float margin = 1e-3f * g.h0; // covers the float rounding of the cell assignment
-    // stack entry: the two key words of the cell (grid_key.cuh) and its box distance
+    // stack entry, 8 bytes: the first key word of the cell, and the second (its 8 significant bits) packed with the upper
+    // 24 bits of the cell's box distance — truncating a positive float only lowers it, so pruning stays conservative
     uint32_t st_cell[kWalkStack], st_meta[kWalkStack];
-    float st_d2[kWalkStack];
     uint32_t q_start[kWalkQueue], q_count[kWalkQueue];
     int nq = 0;
     int l = (start_level < 1) ? 1 : ((start_level < L - 1) ? start_level : L - 1);
@@ -301,8 +318,8 @@ MULLS_HD float nn_search_walk_b(const GridView &g, float px, float py, float pz,
         // Only a starting point — the stop test below is what makes the result exact — so the level comes from the
         // exponent of (need / cover_1)^2 instead of a square root and a division: floor(log2 t) = floor(log2 t^2) >> 1
         const float c1 = 0.999f * 0.5f * g.h0, c0 = 0.998f * 0.5f * g.h0;
-        const float t2 = (1.002001f * best_d2) * (1.0f / (c1 * c1));
-        if (t2 <= 1.0f) l = (1.002001f * best_d2 <= c0 * c0) ? 0 : 1;
+        const float t2 = (g.level_slack2 * best_d2) * (1.0f / (c1 * c1));
+        if (t2 <= 1.0f) l = (g.level_slack2 * best_d2 <= c0 * c0) ? 0 : 1;
         else l = ((int)((f2i_bits(t2) >> 23) & 0xff) - 127 >> 1) + 1;
         l = (l < L - 1) ? l : L - 1;
     }
@@ -357,17 +374,18 @@ MULLS_HD float nn_search_walk_b(const GridView &g, float px, float py, float pz,
             const int i = k & 1, j = (k >> 1) & 1, m = k >> 2;
             int sp = 0;
             st_cell[0] = cell_key_lo((uint32_t)xs[i], (uint32_t)ys[j], (uint32_t)zs[m]);
-            st_meta[0] = cell_key_hi((uint32_t)zs[m], l);
-            st_d2[0] = ex[i] + ey[j] + ez[m];
+            st_meta[0] = pack_meta(cell_key_hi((uint32_t)zs[m], l), ex[i] + ey[j] + ez[m]);
             sp = 1;
             while (sp > 0) {
                 --sp;
+                const uint32_t cell = st_cell[sp], packed = st_meta[sp];
+                const float cell_d2 = meta_d2(packed);
                 // a cell farther than the best so far (or than the radius) cannot change the result
-                if (st_d2[sp] > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) {
-                    wb.prune(st_d2[sp]);
+                if (cell_d2 > fminf(best_d2, r2_prune) * 1.0001f + 1e-12f) {
+                    wb.prune(cell_d2);
                     continue;
                 }
-                const uint32_t cell = st_cell[sp], meta = st_meta[sp];
+                const uint32_t meta = packed & 0xffu;
                 uint32_t start, count, cmask;
                 st.probe();
                 if (!probe_key(g, cell, meta, start, count, cmask)) continue;
@@ -416,8 +434,7 @@ MULLS_HD float nn_search_walk_b(const GridView &g, float px, float py, float pz,
                         const int ch = c ^ near_child;
                         const uint32_t x2 = (uint32_t)(2 * cx + (ch & 1)), y2 = (uint32_t)(2 * cy + ((ch >> 1) & 1)), z2 = (uint32_t)(2 * cz + (ch >> 2));
                         st_cell[sp] = cell_key_lo(x2, y2, z2);
-                        st_meta[sp] = cell_key_hi(z2, lv - 1);
-                        st_d2[sp] = ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2];
+                        st_meta[sp] = pack_meta(cell_key_hi(z2, lv - 1), ax[ch & 1] + ay[(ch >> 1) & 1] + az[ch >> 2]);
                         ++sp;
                     }
                 }

@@ -4,6 +4,7 @@
 // count its work (probes, candidate evaluations, expansions) per query. Built by tests/test_search_core.py with
 // nvcc (host code only; no CUDA call is made). The product never executes this instantiation.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -103,6 +104,11 @@ void *sh_build(const float *pts, uint32_t n, float ox, float oy, float oz, float
     G->g.ox = ox, G->g.oy = oy, G->g.oz = oz, G->g.h0 = h0, G->g.inv_h0 = inv_h0;
     G->g.n_levels = n_levels;
     G->g.leaf_count = leaf_count;
+    G->g.level_slack2 = 1.002001f;
+    if (const char *e = getenv("MULLS_LEVEL_SLACK")) { // (study switch: scripts/studies/skip_certificate_study.py)
+        const float sl = (float)atof(e);
+        if (sl >= 1.0f) G->g.level_slack2 = 1.002001f * sl * sl;
+    }
     return G;
 }
 

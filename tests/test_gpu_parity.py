@@ -473,3 +473,25 @@ def test_nn_query_stands_in_for_the_target_kdtrees(ctx, oracle_mod, small_pair):
     with pytest.raises(RuntimeError):
         fresh.nn_query(0, np.zeros((1, 3), np.float32))
     fresh.close()
+
+
+def test_kept_matches_over_twenty_forced_iterations(ctx, oracle_mod, small_pair):
+    """k_search keeps a match without searching once its certificate allows: with the convergence test
+    switched off every iteration from the fourth on runs in keep mode, the last ones keeping nearly everything — counts and
+    normal equations must still equal the oracle's in each of the 20 iterations, through the graph and the host loop."""
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.converge_translation, p.converge_rotation_d = 0.0, 0.0
+    pair = dict(small_pair, params=p)
+    o, ot = oracle_mod.icp_run(pair["tgt"], pair["src"], pair["params"], pair["init_guess"])
+    assert o["iters"] == 20
+    for use_graph in (1, 0):
+        ctx.set_tunable("use_graph", use_graph)
+        g, gt = ctx.run_batch([pair], want_trace=True)
+        assert_parity(g[0], gt[0], o, ot)
+    ctx.set_tunable("use_graph", 1)
+    # and with a wrong first guess: big early corrections, matches change for several iterations before they settle
+    init = np.array(small_pair["init_guess"], np.float64).copy()
+    init[0, 3] += 0.6
+    init[1, 3] -= 0.4
+    pair2 = dict(pair, init_guess=init)
+    assert_parity(*run_both(ctx, oracle_mod, pair2))
