@@ -67,7 +67,8 @@ enum {
     MULLS_E_ARG = -101,         /* invalid argument */
     MULLS_E_CAPACITY = -102,    /* more points / pairs than the context was created for */
     MULLS_E_UNSUPPORTED = -103, /* option of mm_lls_icp that this build does not implement */
-    MULLS_E_COMM = -104         /* the caller's all-reduce callback failed */
+    MULLS_E_COMM = -104,        /* the caller's all-reduce callback failed */
+    MULLS_E_IO = -105           /* a scan / pose file could not be opened or parsed */
 };
 
 #define MULLS_MAX_TRACE_ITERS 64
@@ -444,6 +445,26 @@ int mulls_extract_semantic_pts(mulls_ctx *ctx, mulls_cloud_view pc_raw, const mu
  * reads `curvature`): [n x (x y z intensity)] [n x (nx ny nz curvature)]. `out` (16-byte aligned) receives
  * 4n + 3n floats (format 1) or 8n floats (format 2). Exposed for callers that keep their clouds packed, and for tests. */
 int mulls_pack_rows(const float *aos48, size_t n, int format, float *out);
+
+/* Scans in, poses out — the reference's DataIo on the two sides of the hot path (csrc/scan_io.h, host
+ * code only). A scan is read straight into pcl::PointXYZINormal rows (48 bytes), i.e. into the buffer every registration
+ * and front-end entry point above takes; with mulls_host_alloc that buffer is pinned and crosses PCIe as it is.
+ *   mulls_scan_probe   rows the file holds (KITTI .bin: one more than its records — the reference's read loop appends a
+ *                      default point at end-of-file, include/common/dataio.hpp:366-373)
+ *   mulls_scan_read    DataIo::read_pc_cloud_block (dataio.hpp:1732-1756) over read_pcd_file (:279-287; PCD v0.7, DATA
+ *                      ascii | binary, float32 fields x y z intensity normal_x normal_y normal_z curvature, others are
+ *                      ignored; binary_compressed: MULLS_E_UNSUPPORTED) and read_bin_file (:357-377; by the .bin
+ *                      extension); local_bound (may be NULL) = CloudUtility::get_cloud_bbx (utility.hpp:817-848);
+ *                      normalize_intensity != 0: intensity rescaled to 0..255 in float (:1738-1750)
+ *   mulls_pose_write   DataIo::write_lo_pose_overwrite / write_lo_pose_append (dataio.hpp:1896-1926): the upper 3 x 4 of a
+ *                      row-major 4 x 4 pose, setprecision(8), one line
+ *   mulls_host_alloc / mulls_host_free   pinned host memory (cudaHostAlloc); NULL without a CUDA device */
+int mulls_scan_probe(const char *path, size_t *n_points);
+int mulls_scan_read(const char *path, float *rows48, size_t capacity_points, size_t *n_points, double local_bound[6],
+                    int normalize_intensity);
+int mulls_pose_write(const char *path, const double pose[16], int overwrite);
+void *mulls_host_alloc(size_t bytes);
+void mulls_host_free(void *p);
 
 /* Runtime tunables (integers), e.g. "start_level", "pairs_in_flight". Returns MULLS_E_ARG if unknown. */
 int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value);

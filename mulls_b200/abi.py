@@ -271,6 +271,11 @@ EXPORTED_SYMBOLS = (
     "mulls_fast_ground_filter",
     "mulls_voxel_downsample",
     "mulls_extract_semantic_pts",
+    "mulls_scan_probe",
+    "mulls_scan_read",
+    "mulls_pose_write",
+    "mulls_host_alloc",
+    "mulls_host_free",
 )
 
 _LIB = None
@@ -334,6 +339,16 @@ def load_library() -> C.CDLL:
     lib.mulls_extract_semantic_pts.argtypes = [vp, CloudView, C.POINTER(ExtractParams), C.POINTER(ExtractOut)]
     lib.mulls_pack_rows.restype = C.c_int
     lib.mulls_pack_rows.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+    lib.mulls_scan_probe.restype = C.c_int
+    lib.mulls_scan_probe.argtypes = [C.c_char_p, C.POINTER(C.c_size_t)]
+    lib.mulls_scan_read.restype = C.c_int
+    lib.mulls_scan_read.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double), C.c_int]
+    lib.mulls_pose_write.restype = C.c_int
+    lib.mulls_pose_write.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int]
+    lib.mulls_host_alloc.restype = C.c_void_p
+    lib.mulls_host_alloc.argtypes = [C.c_size_t]
+    lib.mulls_host_free.restype = None
+    lib.mulls_host_free.argtypes = [C.c_void_p]
     lib.mulls_nccl_unique_id.restype = C.c_int
     lib.mulls_nccl_unique_id.argtypes = [C.c_char_p]
     lib.mulls_nccl_init.restype = C.c_int

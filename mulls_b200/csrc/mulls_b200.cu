@@ -19,6 +19,7 @@
 
 #include "device_types.cuh"
 #include "host_pack.h"
+#include "scan_io.h"
 #include "kernels_ingest.cuh"
 #include "kernels_iterate.cuh"
 #include "kernels_pca.cuh"
@@ -471,6 +472,36 @@ int mulls_pack_rows(const float *aos48, size_t n, int format, float *out) {
     pack_rows(aos48, 0, n, format, out, out + 4 * n);
     _mm_sfence();
     return MULLS_OK;
+}
+
+// ---- scans in, poses out (csrc/scan_io.h: host code, no device involved) -------------------------------------
+static int io_code(int rc) {
+    switch (rc) {
+    case mulls_io::kOk: return MULLS_OK;
+    case mulls_io::kArg: return MULLS_E_ARG;
+    case mulls_io::kCapacity: return MULLS_E_CAPACITY;
+    case mulls_io::kUnsupported: return MULLS_E_UNSUPPORTED;
+    default: return MULLS_E_IO;
+    }
+}
+int mulls_scan_probe(const char *path, size_t *n_points) { return io_code(mulls_io::probe_scan(path, n_points)); }
+int mulls_scan_read(const char *path, float *rows48, size_t capacity_points, size_t *n_points, double local_bound[6],
+                    int normalize_intensity) {
+    return io_code(mulls_io::read_scan(path, rows48, capacity_points, n_points, local_bound, normalize_intensity));
+}
+int mulls_pose_write(const char *path, const double pose[16], int overwrite) {
+    return io_code(mulls_io::append_pose(path, pose, overwrite));
+}
+void *mulls_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void mulls_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int mulls_get_stats(const mulls_ctx *ctx, mulls_run_stats *out) {

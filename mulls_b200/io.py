@@ -8,6 +8,10 @@ H2D copy of `mulls_icp_run_batch` is a plain DMA. Semantics follow the reference
 * read_kitti_bin  <- DataIo::read_bin_file            include/common/dataio.hpp:357-377
 * read_cloud_block<- DataIo::read_pc_cloud_block      include/common/dataio.hpp:1732-1756
 * write_lo_pose_* <- DataIo::write_lo_pose_overwrite / _append   include/common/dataio.hpp:1896-1926
+
+The product's readers are the NATIVE ones of the C-ABI (mulls_scan_probe / mulls_scan_read / mulls_pose_write,
+csrc/scan_io.h), wrapped here as read_cloud_block_native / write_lo_pose_native; the numpy readers above are the
+independent second implementation the CPU tests compare them with.
 """
 from __future__ import annotations
 
@@ -124,3 +128,51 @@ def write_lo_pose_append(T: np.ndarray, path: str) -> bool:
     with open(path, "a") as f:
         f.write(_pose_line(T))
     return True
+
+
+class PinnedRows:
+    """(n, 12) float32 rows in pinned host memory of the library (mulls_host_alloc); freed with the object."""
+
+    def __init__(self, lib, n: int):
+        import ctypes as C
+
+        self._lib, self._ptr = lib, lib.mulls_host_alloc(max(n, 1) * 48)
+        if not self._ptr:
+            raise MemoryError("mulls_host_alloc failed (no CUDA device?)")
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(C.c_float)), shape=(max(n, 1), 12))[:n]
+
+    def __del__(self):
+        if getattr(self, "_ptr", None):
+            self._lib.mulls_host_free(self._ptr)
+            self._ptr = None
+
+
+def read_cloud_block_native(path: str, normalize_intensity: bool = False, pinned: bool = False) -> dict:
+    """DataIo::read_pc_cloud_block through the C-ABI: rows (optionally in pinned memory) + local_bound."""
+    import ctypes as C
+
+    from . import abi
+
+    lib = abi.load_library()
+    n = C.c_size_t(0)
+    rc = lib.mulls_scan_probe(path.encode(), C.byref(n))
+    if rc != 0:
+        raise IOError(f"mulls_scan_probe({path!r}) failed: {rc}")
+    keep = PinnedRows(lib, n.value) if pinned else None
+    rows = keep.array if pinned else np.empty((n.value, 12), np.float32)
+    bound = (C.c_double * 6)()
+    got = C.c_size_t(0)
+    rc = lib.mulls_scan_read(path.encode(), rows.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(got), bound,
+                             1 if normalize_intensity else 0)
+    if rc != 0:
+        raise IOError(f"mulls_scan_read({path!r}) failed: {rc}")
+    return {"pc_raw": rows[: got.value], "local_bound": tuple(bound), "_pinned": keep}
+
+
+def write_lo_pose_native(T: np.ndarray, path: str, overwrite: bool = False) -> bool:
+    import ctypes as C
+
+    from . import abi
+
+    pose = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+    return abi.load_library().mulls_pose_write(path.encode(), pose.ctypes.data_as(C.POINTER(C.c_double)), 1 if overwrite else 0) == 0
