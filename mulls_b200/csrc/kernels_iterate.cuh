@@ -540,9 +540,11 @@ __global__ void __launch_bounds__(kIterBlock) k_resolve(DeviceArrays A, int buf)
 //   [0..20]  lower triangle of ATPA, column by column: (0,0)(1,0)..(5,0)(1,1)(2,1)..(5,5)
 //   [21..26] ATPb
 // ------------------------------------------------------------------------------------------------
+// `t`: anything indexable that takes the 27 terms (k_accumulate: a column of the block's shared-memory term matrix)
+template <class Sink>
 __device__ __forceinline__ void terms_pt2pl(const float4 p, const float pi, const float4 q, const float4 qn,
                                             float weight, int iter_num, bool dist_w, bool resid_w, bool inten_w,
-                                            float window, double *t, float &w_out) {
+                                            float window, Sink t, float &w_out) {
     // cregistration.hpp:2080-2151
     const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
     const float ntx = qn.x, nty = qn.y, ntz = qn.z;
@@ -591,9 +593,10 @@ __device__ __forceinline__ int diag_index(int j) {
     return d[j];
 }
 
+template <class Sink>
 __device__ __forceinline__ void terms_pt2li(const float4 p, const float pi, const float4 q, const float4 qv,
                                             float weight, int iter_num, bool dist_w, bool resid_w, bool inten_w,
-                                            float window, double *t, float &w_out) {
+                                            float window, Sink t, float &w_out) {
     // cregistration.hpp:2174-2271; only the diagonal of this block survives the symmetrisation (Q1)
     const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
     const float vx = qv.x, vy = qv.y, vz = qv.z;
@@ -645,9 +648,10 @@ __device__ __forceinline__ void terms_pt2li(const float4 p, const float pi, cons
     }
 }
 
+template <class Sink>
 __device__ __forceinline__ void terms_pt2pt(const float4 p, const float pi, const float4 q, float weight,
                                             int iter_num, bool dist_w, bool resid_w, bool inten_w, float window,
-                                            double *t) {
+                                            Sink t) {
     // cregistration.hpp:1991-2058
     const float px = p.x, py = p.y, pz = p.z, qx = q.x, qy = q.y, qz = q.z;
     const float dx = px - qx, dy = py - qy, dz = pz - qz;
@@ -848,7 +852,8 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     const bool valid = (int)local < ns;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kIterBlock / 32;
-    __shared__ double s_red[kWarps][kTerms];
+    // the block's term matrix: 27 rows of 128 doubles, one column per thread (27 KB: 8 blocks per SM)
+    __shared__ double s_terms[27 * kIterBlock];
     __shared__ uint32_t s_off[kWarps + 1];
     __shared__ uint32_t s_base;
 
@@ -858,7 +863,10 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     uint8_t fl = 0;
     uint32_t gi = 0;
     bool kept = false, pass = false;
-    double t[32];
+    struct Column { // row k of this thread's column
+        double *base;
+        __device__ __forceinline__ double &operator[](int k) const { return base[k * kIterBlock]; }
+    } t = {s_terms + threadIdx.x};
     // (1) destination of the kept sources: blocks before this one in the same (pair, class)
     {
         uint32_t acc = 0;
@@ -895,8 +903,6 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
     dst_local = s_base + s_off[warp] + __popc(kb & ((1u << lane) - 1u));
 
     // (2) terms of the surviving correspondences
-#pragma unroll
-    for (int k = 0; k < 32; ++k) t[k] = 0.0;
     float w_store = 0.0f;
     int j = -1;
     float4 p = make_float4(0, 0, 0, 0), n = make_float4(0, 0, 0, 0);
@@ -928,6 +934,9 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
             terms_pt2pt(p, p.w, q, 1.0f, it, dist_w, resid_w, inten_w, pc.win_pt2pt, t);
             w_store = d2; // pt2pt never stores a weight: the posterior reads the squared NN distance (Q2)
         }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) t[k] = 0.0;
     }
     // (3) compaction into the other buffer (order preserved: :1776-1789)
     if (kept) {
@@ -939,28 +948,20 @@ __device__ __forceinline__ void accumulate_body(DeviceArrays &A, int buf, uint32
         A.corr_j[gd] = pass ? j : -1;
         A.corr_w[gd] = w_store;
     }
-    // (4) block reduction in a fixed order. Warp level: reduce-scatter butterfly — at every step a lane
-    // keeps half of the terms and receives the partner's sums of that half, so after 5 steps lane i holds
-    // the warp total of term i (31 shuffles instead of 27 x 5).
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool upper = (lane & half) != 0;
-#pragma unroll
-        for (int k = 0; k < half; ++k) {
-            const double send = upper ? t[k] : t[k + half];
-            const double keep = upper ? t[k + half] : t[k];
-            t[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-        }
-    }
-    if (lane < kTerms) s_red[warp][lane] = t[0];
+    // (4) block reduction in a fixed order: warp w sums rows w, w + 4, ... of the term matrix — four columns per lane,
+    // then a butterfly over the lanes (every lane ends with the same total): bit-reproducible, independent of the
+    // order in which blocks fetch chunks
     __syncthreads();
-    if (threadIdx.x < 27) {
-        double v = 0.0;
-        for (int w = 0; w < kWarps; ++w) v += s_red[w][threadIdx.x];
-        A.partials[(size_t)chunk * kTerms + threadIdx.x] = v;
+#pragma unroll 1
+    for (int k = warp; k < 27; k += kWarps) {
+        const double *row = s_terms + k * kIterBlock;
+        double v = ((row[lane] + row[lane + 32]) + row[lane + 64]) + row[lane + 96];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) A.partials[(size_t)chunk * kTerms + k] = v;
     }
 }
-__global__ void __launch_bounds__(kIterBlock) k_accumulate(DeviceArrays A, int buf) {
+__global__ void __launch_bounds__(kIterBlock, 8) k_accumulate(DeviceArrays A, int buf) {
     buf = loop_buf(A, buf);
     if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->work[0] = 0u; // the next iteration's k_search starts its list at 0
     for_each_live_chunk(A, buf, 2, [&](uint32_t chunk) { accumulate_body(A, buf, chunk); });

@@ -905,7 +905,7 @@ static void launch_search(mulls_ctx *ctx, cudaStream_t st, const DeviceArrays &A
     if (mode < 0 || mode == 1) k_search<1><<<grid, kIterBlock, 0, st>>>(A, buf, it, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
     if (mode < 0 || mode == 2) k_search<2><<<grid, kIterBlock, 0, st>>>(A, buf, it, ctx->start_level0, ctx->leaf_count, ctx->defer_from_iter, reseed);
 }
-constexpr int kShootBlocksPerSm = 8, kResolveBlocksPerSm = 16, kAccumulateBlocksPerSm = 5;
+constexpr int kShootBlocksPerSm = 8, kResolveBlocksPerSm = 16, kAccumulateBlocksPerSm = 8;
 
 // The iteration loop as a CUDA graph (CUDA 12.4+ conditional nodes): WHILE(handle) { k_search [, k_search_shoot],
 // k_resolve, k_accumulate, k_solve } followed by k_posterior, k_finalize, k_collect. Kernel nodes are recorded once per

@@ -1,9 +1,8 @@
 #!/bin/bash
-# GPU test-suite, per-iteration search times of one resident 64-pair batch, bench, racecheck with and without the graph
+# GPU test-suite, per-iteration search times of one resident 64-pair batch, bench
 T=${1:-r2c}
 mkdir -p gpurun_out
 (timeout 420 python -m pytest tests -x -q -m gpu 2>&1 | tail -8) > gpurun_out/${T}_tests.log 2>&1
 (timeout 400 python scripts/gpu_search_ab.py 64 c2 "defer_from_iter=3" 2>&1 | tail -4) > gpurun_out/${T}_ab.log 2>&1
 (timeout 400 python bench.py --no-cpu-baseline 2> gpurun_out/${T}_bench.err | tail -1) > gpurun_out/${T}_bench.json
-(echo "== racecheck, host launch loop"; MULLS_SANITIZE_GRAPH=0 timeout 400 compute-sanitizer --tool racecheck python scripts/sanitize_small.py 2>&1 | grep -v "^=========$" | tail -8) > gpurun_out/${T}_racecheck_loop.log 2>&1
-tail -3 gpurun_out/${T}_tests.log; cat gpurun_out/${T}_ab.log; cat gpurun_out/${T}_bench.json; cat gpurun_out/${T}_racecheck_loop.log
+tail -3 gpurun_out/${T}_tests.log; cat gpurun_out/${T}_ab.log; cat gpurun_out/${T}_bench.json

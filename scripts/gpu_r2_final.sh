@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 (timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv \
     python scripts/gpu_search_profile.py 64 2 > gpurun_out/${T}_ncu_launches.log 2>&1)
 N=$(grep -o "over [0-9]* launches" gpurun_out/${T}_search.log | head -1 | grep -o "[0-9]*")
-(timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_search|k_keep" -s $(( ${N:-10} + 3 )) -c 10 -f -o gpurun_out/${T}_search \
+(timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_search|k_accumulate" -s $(( 2 * ${N:-10} )) -c 12 -f -o gpurun_out/${T}_search \
     python scripts/gpu_search_profile.py 64 2 > gpurun_out/${T}_ncu_search.log 2>&1)
 (echo "== memcheck (iteration graph)"; timeout 300 compute-sanitizer --tool memcheck python scripts/sanitize_small.py 2>&1 | grep -v "^=========$" | tail -9;
  echo "== racecheck (host launch loop)"; MULLS_SANITIZE_GRAPH=0 timeout 400 compute-sanitizer --tool racecheck python scripts/sanitize_small.py 2>&1 | grep -v "^=========$" | tail -9) > gpurun_out/${T}_sanitizer.log 2>&1
