@@ -162,19 +162,22 @@ def cpu_reference_rate(pairs, budget_s, max_regs, all_cores=False):
     """The oracle (CPU restatement of the reference's algorithm) on the host cores.
     reference-shaped (default): kd-tree per class and 3 OpenMP sections per registration as cregistration.hpp:1268-1292,
     cores//3 registrations in flight so that every core the process may use is busy;
-    all_cores: one registration at a time, `parallel for` over the queries on all cores (BASELINE.md section 3 ii)."""
+    all_cores (BASELINE.md section 3 ii — the best the same algorithm does on the host): `parallel for` over the queries and
+    tree-parallel build, 8 threads per registration (more do not pay on one 120k-point registration: 2 s with 128 threads on
+    the 128-core box against 55 ms with 8), cores // 8 registrations in flight."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle
 
     oracle.load()
     cores = host_cores()
-    workers = 1 if all_cores else max(1, cores // 3)
-    n = min(max_regs, max(workers, 1) * 4) if not all_cores else max_regs
+    per_reg = min(8, cores)
+    workers = max(1, cores // per_reg) if all_cores else max(1, cores // 3)
+    n = min(max_regs, max(workers, 1) * 4)
     jobs = [pairs[i % len(pairs)] for i in range(n)]
 
     def one(p):
-        oracle.icp_run(p["tgt"], p["src"], p["params"], p["init_guess"], threads=(cores if all_cores else 0), want_trace=False)
+        oracle.icp_run(p["tgt"], p["src"], p["params"], p["init_guess"], threads=(per_reg if all_cores else 0), want_trace=False)
         return 1
 
     t0 = time.perf_counter()
@@ -185,7 +188,7 @@ def cpu_reference_rate(pairs, budget_s, max_regs, all_cores=False):
             if time.perf_counter() - t0 > budget_s and done >= workers:
                 break
     dt = time.perf_counter() - t0
-    return done / dt, (cores if all_cores else min(cores, workers * 3)), done, dt
+    return done / dt, (min(cores, workers * per_reg) if all_cores else min(cores, workers * 3)), done, dt
 
 
 def main():
@@ -230,7 +233,7 @@ def main():
             rates.append(rate)
         total = time.perf_counter() - t0
         value = regs / total
-        ac_rate, ac_cores, ac_done, ac_dt = cpu_reference_rate(pairs, 6.0, 64, all_cores=True)
+        ac_rate, ac_cores, ac_done, ac_dt = cpu_reference_rate(pairs, 6.0, 10 ** 9, all_cores=True)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 accumulation",
@@ -240,8 +243,8 @@ def main():
                                            f"(3 OpenMP sections each), {max(1, cores // 3)} in flight on {host_cores()} usable cores",
                                  "per_step": {"min": min(rates), "median": float(np.median(rates)), "max": max(rates)},
                                  "all_cores_variant": {"value": ac_rate, "cores": ac_cores,
-                                                       "sample": f"{ac_done} registrations one at a time, parallel-for over "
-                                                                 f"the queries, in {ac_dt:.1f} s"}},
+                                                       "sample": f"{ac_done} registrations, parallel-for over the queries with 8 threads "
+                                                                 f"each, {max(1, host_cores() // 8)} in flight, in {ac_dt:.1f} s"}},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -432,6 +435,23 @@ def main():
         for a, b in zip(res, res_e2e):
             assert np.array_equal(a["T"], b["T"])
         barrier()
+    # the link itself: one large pinned H2D copy (what bounds the e2e leg: bytes per step / this rate)
+    h2d_gbs = None
+    try:
+        hbuf = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            dbuf.copy_(hbuf, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * hbuf.numel() / (c0.elapsed_time(c1) * 1e6)
+        del hbuf, dbuf
+    except Exception:
+        pass
     best_hp = min(e2e_variants, key=e2e_variants.get)
     e2e_s = e2e_variants[best_hp]
     pipe.set_tunable("host_pack", 2)  # the library default (pack when a call ships >= 2^18 points)
@@ -476,11 +496,13 @@ def main():
                 peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
             except Exception:
                 pass
-        traffic = None
+        traffic, traffic_alg = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("k_search_dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("k_search_dram_bytes_per_launch")
+                traffic_alg = tj.get("k_search_algorithmic_bytes_per_launch_same_launches")
             except Exception:
                 pass
         # rank-0 figures for the dominant kernel (k_search): algorithmic bytes per launch / mean launch time
@@ -493,12 +515,17 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "host clock around the synchronous C-ABI calls (pinned host buffers)",
                     "host_pack": best_hp,
+                    "pinned_h2d_gbs": h2d_gbs,
+                    "link_bound_value": (world * args.pairs * h2d_gbs * 1e9 / h2d) if h2d_gbs else None,
                     "variants": {("rows48" if k == 0 else "host_packed28"): total_regs / world / v
                                  for k, v in e2e_variants.items()} if world == 1 else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_search (transform + NN + claim)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_algorithmic_same_launches": traffic_alg,
+                         "traffic_note": "ncu DRAM bytes of the first six k_search launches of one 64-pair run (profiles/traffic.json) next "
+                                         "to the algorithmic bytes of the SAME launches; bytes_per_launch below averages over all launches",
+                         "peak_source": peak_src,
                          "bytes_per_launch": st_alg / max(n_search_launches, 1),
                          "ms_per_launch": search_ms / max(n_search_launches, 1),
                          "whole_path_frac": (alg_bytes / 1e9) / (dev_ms / 1e3) / peak,
