@@ -138,6 +138,15 @@ struct mulls_ctx {
     // pipelined context (mulls_create_pipelined): the batch is split over independent lane contexts, each with
     // its own stream and buffers, driven by one host thread each
     std::vector<mulls_ctx *> lanes;
+    // one-shot batch calls with host buffers (mulls_icp_run_batch) are double-buffered: the second half of the batch is
+    // packed and copied on the twin's stream while the first half is being registered on this one
+    mulls_ctx *twin = nullptr;
+    int double_buffer = 1;
+    struct Pending {                 // a run that has been enqueued and not yet finished (run_finish)
+        uint64_t launches = 0;
+        int n_search_ev = 0;
+        bool graphed = false, hooked = false, active = false;
+    } pend;
     std::vector<size_t> lane_begin; // pair range of every lane for the resident batch
     // PCA scratch
     void *pca_buf = nullptr;
@@ -215,6 +224,7 @@ void mulls_destroy(mulls_ctx *ctx) {
     if (!ctx) return;
     for (mulls_ctx *l : ctx->lanes) mulls_destroy(l);
     ctx->lanes.clear();
+    if (ctx->twin) mulls_destroy(ctx->twin), ctx->twin = nullptr;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
@@ -440,6 +450,10 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
         const int rc = mulls_set_tunable(l, name, value);
         if (rc != MULLS_OK) return rc;
     }
+    if (ctx->twin) {
+        const int rc = mulls_set_tunable(ctx->twin, name, value);
+        if (rc != MULLS_OK) return rc;
+    }
     std::string n(name);
     if (n == "start_level") ctx->start_level0 = value;
     else if (n == "leaf_count") ctx->leaf_count = value;
@@ -447,6 +461,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "defer_from_iter") ctx->defer_from_iter = value;
     else if (n == "search_blocks") ctx->search_blocks = value; // (kept for old scripts: the instantiations are fixed now)
     else if (n == "sort_sources") ctx->sort_sources = value;
+    else if (n == "double_buffer") ctx->double_buffer = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
     else if (n == "use_graph") ctx->use_graph = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
@@ -950,16 +965,27 @@ static int build_iteration_graph(mulls_ctx *ctx) {
 
 // Launch the whole path on the resident inputs. If `hook` is given (sharded mode) it is called between
 // the phases that need a cross-rank exchange.
-static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user);
-static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
-    const int rc = run_impl_inner(ctx, out, trace, hook, user);
+static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user,
+                          bool finish_now);
+static int run_finish_inner(mulls_ctx *ctx, mulls_icp_result *out);
+// finish_now = false: everything is enqueued on the context's stream and the call returns; run_finish waits for it
+static int run_impl(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user,
+                    bool finish_now = true) {
+    const int rc = run_impl_inner(ctx, out, trace, hook, user, finish_now);
     // an error exit may leave async copies from / into the caller's buffers (clouds, trace, results) in flight:
     // nothing is handed back before the stream has drained
     if (rc != MULLS_OK && ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
     return rc;
 }
-static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user) {
+static int run_finish(mulls_ctx *ctx, mulls_icp_result *out) {
+    const int rc = run_finish_inner(ctx, out);
+    if (rc != MULLS_OK && ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace *trace, mulls_allreduce_fn hook, void *user,
+                          bool finish_now) {
     if (!ctx || !ctx->uploaded) return MULLS_E_ARG;
+    ctx->pend.active = false;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DeviceArrays A = ctx->A;
@@ -1069,9 +1095,24 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
     CK(cudaMemcpyAsync(ctx->h_flags, A.hash_used, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (trace) CK(cudaMemcpyAsync(trace, ctx->d_trace, np * sizeof(mulls_icp_trace), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev_end, st));
+    ctx->pend.launches = launches, ctx->pend.n_search_ev = n_search_ev, ctx->pend.graphed = graphed, ctx->pend.hooked = hook != nullptr;
+    ctx->pend.active = true;
+    if (!finish_now) return MULLS_OK;
+    return run_finish_inner(ctx, out);
+}
+
+static int run_finish_inner(mulls_ctx *ctx, mulls_icp_result *out) {
+    if (!ctx || !ctx->pend.active) return MULLS_E_ARG;
+    ctx->pend.active = false;
+    cudaStream_t st = ctx->stream;
+    const int np = (int)ctx->n_pairs;
+    uint64_t launches = ctx->pend.launches;
+    const int n_search_ev = ctx->pend.n_search_ev;
+    const bool graphed = ctx->pend.graphed;
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    if (graphed) launches += (uint64_t)ctx->h_ctl->it * (4u + (ctx->any_normal_shooting ? 1u : 0u)) + 3u;
+    // (graph: three k_search forms, k_resolve, k_accumulate, k_solve per executed iteration + posterior, finalize, collect)
+    if (graphed) launches += (uint64_t)ctx->h_ctl->it * (6u + (ctx->any_normal_shooting ? 1u : 0u)) + 3u;
     if (ctx->h_flags[1]) {
         ctx->err = "hash pool exhausted (target clouds produce more grid cells than the context reserves)";
         return MULLS_E_CAPACITY;
@@ -1102,7 +1143,7 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
         const uint64_t *ab = reinterpret_cast<const uint64_t *>(ctx->h_results + np);
         for (int p = 0; p < np; ++p) S.algorithmic_bytes += ab[p];
     }
-    ctx->grid_valid = !hook;
+    ctx->grid_valid = !ctx->pend.hooked;
     return MULLS_OK;
 }
 
@@ -1137,6 +1178,63 @@ int mulls_batch_run_resident(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_tr
     return run_impl(ctx, out, trace, nullptr, nullptr);
 }
 
+// One-shot batch on ONE context (host buffers in, results out). With >= 2 pairs and the iteration graph the batch is
+// double-buffered over the context and its twin (own stream and buffers, created on first use): the second half is
+// packed and copied while the first half is being registered; both halves are collected at the end.
+static int one_shot_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
+                          const mulls_icp_params *params, const double *init_guess, mulls_icp_result *out, mulls_icp_trace *trace) {
+    const double t0 = wall_ms();
+    const bool split = ctx->double_buffer && ctx->use_graph && n_pairs >= 2 && n_pairs <= ctx->max_pairs;
+    if (split && !ctx->twin) {
+        mulls_ctx *t = mulls_create(ctx->device, (ctx->max_pairs + 1) / 2, ctx->max_src, ctx->max_tgt);
+        if (t) { // (no memory for it: the call simply runs on one context)
+            t->start_level0 = ctx->start_level0, t->leaf_count = ctx->leaf_count, t->reseed_cells_x4 = ctx->reseed_cells_x4;
+            t->defer_from_iter = ctx->defer_from_iter, t->sort_sources = ctx->sort_sources, t->hash_slack = ctx->hash_slack;
+            t->use_graph = ctx->use_graph, t->zero_copy = ctx->zero_copy, t->host_pack = ctx->host_pack, t->poll_pause = ctx->poll_pause;
+            t->stage_wc = ctx->stage_wc, t->h0_min = ctx->h0_min, t->double_buffer = 0;
+            ctx->twin = t;
+        }
+    }
+    if (!split || !ctx->twin) {
+        int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr, /*resident=*/false);
+        if (rc != MULLS_OK) return rc;
+        rc = run_impl(ctx, out, trace, nullptr, nullptr);
+        ctx->uploaded = false; // nothing stays resident after a one-shot call
+        ctx->stats.ms_host_call = (float)(wall_ms() - t0);
+        return rc;
+    }
+    mulls_ctx *a = ctx, *b = ctx->twin;
+    const size_t n0 = (n_pairs + 1) / 2, n1 = n_pairs - n0;
+    int rc = upload_impl(a, n0, tgt, src, params, init_guess, nullptr, nullptr, /*resident=*/false);
+    if (rc == MULLS_OK) rc = run_impl(a, nullptr, trace, nullptr, nullptr, /*finish_now=*/false);
+    int rcb = MULLS_OK;
+    if (rc == MULLS_OK) {
+        rcb = upload_impl(b, n1, tgt + n0 * kNumClasses, src + n0 * kNumClasses, params + n0, init_guess + 16 * n0, nullptr, nullptr,
+                          /*resident=*/false);
+        if (rcb == MULLS_OK) rcb = run_impl(b, nullptr, trace ? trace + n0 : nullptr, nullptr, nullptr, /*finish_now=*/false);
+    }
+    // whatever happened, nothing is handed back while one of the two streams still works on the caller's buffers
+    if (rc == MULLS_OK) rc = run_finish(a, out);
+    else cudaStreamSynchronize(a->stream);
+    if (rc == MULLS_OK && rcb == MULLS_OK) rcb = run_finish(b, out ? out + n0 : nullptr);
+    else if (b->stream) cudaStreamSynchronize(b->stream), b->pend.active = false;
+    a->uploaded = b->uploaded = false;
+    if (rc == MULLS_OK && rcb != MULLS_OK) {
+        ctx->err = b->err;
+        rc = rcb;
+    }
+    if (rc == MULLS_OK) { // the call's statistics: both halves (device times overlap: the longer one is reported)
+        mulls_run_stats &S = a->stats;
+        const mulls_run_stats &T = b->stats;
+        S.kernel_launches += T.kernel_launches, S.algorithmic_bytes += T.algorithmic_bytes, S.iterations += T.iterations;
+        S.ms_ingest = std::max(S.ms_ingest, T.ms_ingest), S.ms_iterate = std::max(S.ms_iterate, T.ms_iterate);
+        S.ms_total = std::max(S.ms_total, T.ms_total);
+        S.ms_h2d += T.ms_h2d, S.ms_host_pack += T.ms_host_pack, S.ms_host_upload += T.ms_host_upload;
+    }
+    ctx->stats.ms_host_call = (float)(wall_ms() - t0);
+    return rc;
+}
+
 int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *tgt, const mulls_cloud_view *src,
                         const mulls_icp_params *params, const double *init_guess, mulls_icp_result *out,
                         mulls_icp_trace *trace) {
@@ -1151,25 +1249,14 @@ int mulls_icp_run_batch(mulls_ctx *ctx, size_t n_pairs, const mulls_cloud_view *
         ctx->n_pairs = n_pairs;
         ctx->uploaded = false;
         const int rc = for_each_lane(ctx, n_pairs, [&](mulls_ctx *lane, size_t b, size_t n) {
-            const double t0 = wall_ms();
-            int r = upload_impl(lane, n, tgt + b * kNumClasses, src + b * kNumClasses, params + b, init_guess + 16 * b, nullptr,
-                                nullptr, /*resident=*/false);
-            if (r != MULLS_OK) return r;
-            r = run_impl(lane, out ? out + b : nullptr, trace ? trace + b : nullptr, nullptr, nullptr);
-            lane->uploaded = false;
-            lane->stats.ms_host_call = (float)(wall_ms() - t0);
-            return r;
+            return one_shot_batch(lane, n, tgt + b * kNumClasses, src + b * kNumClasses, params + b, init_guess + 16 * b,
+                                  out ? out + b : nullptr, trace ? trace + b : nullptr);
         });
         merge_lane_stats(ctx);
         return rc;
     }
-    const double t0 = wall_ms();
-    int rc = upload_impl(ctx, n_pairs, tgt, src, params, init_guess, nullptr, nullptr, /*resident=*/false);
-    if (rc != MULLS_OK) return rc;
-    rc = run_impl(ctx, out, trace, nullptr, nullptr);
-    ctx->uploaded = false; // nothing stays resident after a one-shot call
-    ctx->stats.ms_host_call = (float)(wall_ms() - t0);
-    return rc;
+    if (!ctx || !tgt || !src || !params || !init_guess || n_pairs == 0) return MULLS_E_ARG;
+    return one_shot_batch(ctx, n_pairs, tgt, src, params, init_guess, out, trace);
 }
 
 int mulls_icp_run(mulls_ctx *ctx, const mulls_cloud_view tgt[MULLS_NUM_CLASSES], const mulls_cloud_view src[MULLS_NUM_CLASSES],
