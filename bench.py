@@ -129,7 +129,65 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 200"}
+
+
+class NvmlClockSampler:
+    """The same counters read in-process through NVML every 200 ms (no nvidia-smi process contending for the driver while
+    the host-API-heavy e2e leg runs). Same output as ClockSampler.stop()."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index):
+        import pynvml
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber the devices: resolve through the PCI bus id torch reports
+        try:
+            import torch
+
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
+            dom = getattr(torch.cuda.get_device_properties(gpu_index), "pci_domain_id", 0)
+            dev = torch.cuda.get_device_properties(gpu_index).pci_device_id
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        self.sm, self.mx, self.reasons, self._stop = [], 0.0, set(), threading.Event()
+        self.lines = self.sm  # (len(sampler.lines) is what the bench checks)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx = max(self.mx, float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        threading.Thread(target=self._loop, daemon=True).start()
+
+    def stop(self):
+        self._stop.set()
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+
+
+def make_clock_sampler(kind, gpu_index):
+    if kind == "off":
+        return None
+    if kind == "nvml":
+        try:
+            return NvmlClockSampler(gpu_index)
+        except Exception:
+            pass
+    return ClockSampler(gpu_index)
 
 
 def host_cores():
@@ -206,6 +264,9 @@ def main():
                     help="e2e leg: ship the clouds as 48-byte rows (0), repacked to the 28 B wire format on the host "
                          "cores (1), or measure both and report the faster (auto)")
     ap.add_argument("--pack-threads", type=int, default=0, help="host worker threads of the repacking (0: library default)")
+    ap.add_argument("--clock-sampler", default="smi", choices=["nvml", "smi", "off"],
+                    help="how SM clocks / throttle reasons are sampled during the timed regions: NVML in-process, "
+                         "the profiling recipe's nvidia-smi -lms 200 process (default), or not at all (A/B of the sampler's own cost: none measured)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -292,8 +353,9 @@ def main():
     pipe = PipelinedContext(local_rank, lanes, (args.pairs + lanes - 1) // lanes, max_src, max_tgt)
 
     # ---- (A) device-resident, one stream: per-kernel attribution for the roofline ----------------
-    sampler = ClockSampler(local_rank)  # samples every 200 ms (the recipe's interval; a 50 ms poll measurably slowed the host-API-heavy e2e leg) through all warm-up and timed regions below
-    sampler.start()
+    sampler = make_clock_sampler(args.clock_sampler, local_rank)  # samples every 200 ms (the recipe's interval; a 50 ms poll measurably slowed the host-API-heavy e2e leg) through all warm-up and timed regions below
+    if sampler:
+        sampler.start()
     ctx.upload(pairs)
     res = None
     for _ in range(args.warmup):
@@ -455,11 +517,11 @@ def main():
     best_hp = min(e2e_variants, key=e2e_variants.get)
     e2e_s = e2e_variants[best_hp]
     pipe.set_tunable("host_pack", 2)  # the library default (pack when a call ships >= 2^18 points)
-    if len(sampler.lines) < 3:  # very short runs: keep the GPU under the same load until a few samples exist
+    if sampler and len(sampler.lines) < 3:  # very short runs: keep the GPU under the same load until a few samples exist
         t_fill = time.perf_counter()
         while len(sampler.lines) < 3 and time.perf_counter() - t_fill < 2.0:
             pipe.run_resident()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "off"}
     h2d = sum(a.nbytes for p in pairs for side in ("tgt", "src") for a in p[side])
     if best_hp == 1:  # 28 of the 48 bytes of a row cross PCIe (16 B + 12 B per point, padded per cloud)
         h2d = sum(16 * (len(a) + (3 * len(a) + 3) // 4) for p in pairs for side in ("tgt", "src") for a in p[side])
