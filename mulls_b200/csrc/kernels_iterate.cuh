@@ -11,6 +11,8 @@
 // After the loop: k_posterior + k_finalize (:2518-2677, :1386). Source-sharded registrations (k_shard_*) insert the
 // caller's all-reduce between these phases.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "device_math.cuh"
 #include "device_types.cuh"
 #include "kernels_ingest.cuh"
@@ -1076,6 +1078,57 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DeviceArrays A, int buf
             const bool again = *(volatile int *)A.running > 0 && it < ctl.max_iter;
             cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, again ? 1u : 0u);
         }
+    }
+}
+
+// ---- k_icp_loop: the WHOLE iteration loop of a small batch as one cooperative kernel. For registrations whose chunks fit
+//      the co-resident grid (the reference's own operating point: a few thousand source points against a 20k-point local
+//      map, test/mulls_slam.cpp:477-482) an iteration is seven short kernels at the launch-latency floor; here the four
+//      phases are the same device functions over the same work lists, separated by grid-wide barriers instead of kernel
+//      boundaries. Every block executes the same number of barriers: the loop bounds (LoopCtl::max_iter, the running
+//      counter read after a barrier) are grid-uniform.
+__global__ void __launch_bounds__(kIterBlock, 4) k_icp_loop(DeviceArrays A, int start_level0, int leaf_count, int defer_from_iter,
+                                                           float reseed_cells) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    LoopCtl &ctl = *A.ctl;
+    const SearchArgs sa = {start_level0, leaf_count, defer_from_iter, reseed_cells};
+    __shared__ uint8_t s_need[kIterBlock];
+    __shared__ uint32_t s_n_need;
+    const int n_pairs = ctl.n_pairs, max_iter = ctl.max_iter;
+    for (int it = 0; it < max_iter; ++it) {
+        const int buf = it & 1;
+        const uint32_t *list = A.live_chunks + (size_t)buf * A.live_stride;
+        const uint32_t n_live = ctl.n_live[buf];
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl.n_live[buf ^ 1] = 0u; // (k_solve's phase fills it, three barriers later)
+        // phase 1: transform + search (+ keep) + claim
+        for (uint32_t w = blockIdx.x; w < n_live; w += gridDim.x) {
+            const uint32_t chunk = list[w];
+            if (it >= kKeepFromIter) search_keep_chunk(A, buf, chunk, sa, s_need, &s_n_need);
+            else if (it == kKeepFromIter - 1) search_quarter<WalkBounds>(A, buf, chunk, threadIdx.x >> 5, sa, true);
+            else search_quarter<NoBounds>(A, buf, chunk, threadIdx.x >> 5, sa, false);
+            __syncthreads();
+        }
+        grid.sync();
+        // phase 2: duplicate check, rejectors, counts
+        for (uint32_t w = blockIdx.x; w < n_live; w += gridDim.x) {
+            resolve_body(A, buf, list[w]);
+            __syncthreads();
+        }
+        grid.sync();
+        // phase 3: compaction + normal-equation partials
+        for (uint32_t w = blockIdx.x; w < n_live; w += gridDim.x) {
+            accumulate_body(A, buf, list[w]);
+            __syncthreads();
+        }
+        grid.sync();
+        // phase 4: per pair — sum, solve, advance, publish the next work list
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            solve_body(A, buf, (uint32_t)pair);
+            __syncthreads();
+        }
+        grid.sync();
+        if (*(volatile int *)A.running <= 0) break; // (grid-uniform: nothing writes it between this barrier and the next solve)
     }
 }
 

@@ -142,6 +142,8 @@ struct mulls_ctx {
     // packed and copied on the twin's stream while the first half is being registered on this one
     mulls_ctx *twin = nullptr;
     int double_buffer = 1;
+    int loop_kernel = 1;       // small batches: the whole iteration loop as one cooperative kernel (k_icp_loop)
+    int loop_kernel_blocks = 0; // co-resident blocks of k_icp_loop on this device (0: not yet queried, -1: unavailable)
     struct Pending {                 // a run that has been enqueued and not yet finished (run_finish)
         uint64_t launches = 0;
         int n_search_ev = 0;
@@ -462,6 +464,7 @@ int mulls_set_tunable(mulls_ctx *ctx, const char *name, int value) {
     else if (n == "search_blocks") ctx->search_blocks = value; // (kept for old scripts: the instantiations are fixed now)
     else if (n == "sort_sources") ctx->sort_sources = value;
     else if (n == "double_buffer") ctx->double_buffer = value;
+    else if (n == "loop_kernel") ctx->loop_kernel = value;
     else if (n == "hash_slack") ctx->hash_slack = std::max(2, value);
     else if (n == "use_graph") ctx->use_graph = value;
     else if (n == "zero_copy") ctx->zero_copy = value;
@@ -1007,14 +1010,37 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             ++launches;
         }
     }
-    const bool graphed = !hook && ctx->use_graph;
+    // small batches: one cooperative kernel runs the whole loop (every chunk and every pair must find a co-resident block)
+    bool looped = false;
+    if (!hook && ctx->use_graph && ctx->loop_kernel && !ctx->any_normal_shooting && n_itc > 0) {
+        if (ctx->loop_kernel_blocks == 0) {
+            int per_sm = 0, coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop, kIterBlock, 0) == cudaSuccess && per_sm > 0)
+                ctx->loop_kernel_blocks = per_sm * ctx->num_sms;
+            else
+                ctx->loop_kernel_blocks = -1, cudaGetLastError();
+        }
+        looped = ctx->loop_kernel_blocks > 0 && n_itc <= (unsigned)ctx->loop_kernel_blocks && np <= ctx->loop_kernel_blocks;
+    }
+    const bool graphed = !hook && ctx->use_graph && !looped;
     if (graphed) {
         const int rc = build_iteration_graph(ctx);
         if (rc != MULLS_OK) return rc;
     }
     CK(cudaEventRecord(ctx->ev_ingest, st));
     int n_search_ev = 0;
-    if (graphed) {
+    if (looped) {
+        DeviceArrays Aarg = A;
+        int a1 = ctx->start_level0, a2 = ctx->leaf_count, a3 = ctx->defer_from_iter;
+        float a4 = 0.25f * (float)ctx->reseed_cells_x4;
+        void *args[] = {&Aarg, &a1, &a2, &a3, &a4};
+        const unsigned grid = std::max(1u, std::min((unsigned)ctx->loop_kernel_blocks, std::max(n_itc, (unsigned)np)));
+        CK(cudaLaunchCooperativeKernel((const void *)k_icp_loop, dim3(grid), dim3(kIterBlock), args, 0, st));
+        k_posterior<<<n_itc, kIterBlock, 0, st>>>(A);
+        k_finalize<<<(unsigned)ceil_div(np, 64), 64, 0, st>>>(A, np);
+        launches += 3;
+    } else if (graphed) {
         CK(cudaGraphLaunch(ctx->graph_exec, st));
         CK(cudaMemcpyAsync(ctx->h_ctl, A.ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, st)); // iterations executed
     } else if (n_itc) {
