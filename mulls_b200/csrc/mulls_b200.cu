@@ -1021,7 +1021,9 @@ static int run_impl_inner(mulls_ctx *ctx, mulls_icp_result *out, mulls_icp_trace
             else
                 ctx->loop_kernel_blocks = -1, cudaGetLastError();
         }
-        looped = ctx->loop_kernel_blocks > 0 && n_itc <= (unsigned)ctx->loop_kernel_blocks && np <= ctx->loop_kernel_blocks;
+        // `loop_kernel` = how many chunks a co-resident block may have to walk per phase (1: every chunk has its block)
+        looped = ctx->loop_kernel_blocks > 0 && n_itc <= (unsigned)(ctx->loop_kernel * ctx->loop_kernel_blocks) &&
+                 np <= ctx->loop_kernel * ctx->loop_kernel_blocks;
     }
     const bool graphed = !hook && ctx->use_graph && !looped;
     if (graphed) {
