@@ -19,6 +19,10 @@
  *                               (BASELINE config 5); the per-iteration exchange is delegated to a
  *                               caller-supplied all-reduce; mulls_icp_run_sharded_nccl: the same over NCCL inside the
  *                               library (mulls_nccl_unique_id, mulls_nccl_init)
+ *   mulls_nn_query           <- block1->tree_*->nearestKSearch(pt, 1, ...): the kd-trees mm_lls_icp leaves behind
+ *                               (cregistration.hpp:1213-1232), read at src/map_manager.cpp:197-205
+ *   mulls_scan_read / _probe <- DataIo::read_pc_cloud_block, include/common/dataio.hpp:1732-1756 (read_pcd_file :279-287,
+ *                               read_bin_file :357-377); mulls_pose_write <- write_lo_pose_overwrite / _append :1896-1926
  *   mulls_pca_features       <- lo::PrincipleComponentAnalysis<PointT>::get_pc_pca_feature
  *                               include/common/pca.hpp:294-354 (+ get_pca_feature :390-434)
  *   mulls_map_update         <- lo::MapManager::update_local_map, src/map_manager.cpp:17-145
