@@ -580,6 +580,8 @@ def main():
                     "timing": "host clock around the synchronous C-ABI calls (pinned host buffers)",
                     "host_pack": best_hp,
                     "pinned_h2d_gbs": h2d_gbs,
+                    "link_note": "pinned_h2d_gbs = ONE 256 MB pinned copy at a time; link_bound_value = the e2e rate at that "
+                                 "copy rate. Concurrent copies of several lanes have measured above it (38.6 vs 33.3 GB/s)",
                     "link_bound_value": (world * args.pairs * h2d_gbs * 1e9 / h2d) if h2d_gbs else None,
                     "variants": {("rows48" if k == 0 else "host_packed28"): total_regs / world / v
                                  for k, v in e2e_variants.items()} if world == 1 else None},
