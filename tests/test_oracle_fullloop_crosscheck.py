@@ -152,6 +152,40 @@ def line_terms(S, T, s_i, t_i, it, weight, dist_w, resid_w, inten_w, window):
     return A, bv, w
 
 
+def point_terms(S, T, s_i, t_i, dd, it, weight, dist_w, resid_w, inten_w, window):
+    """pt2pt_lls_summation (:1976-2063): float products, double sums; no weight is stored back into the correspondence,
+    so the posterior reads the squared NN distance that shares its storage (Q2)."""
+    p, q = S[s_i, 0:3], T[t_i, 0:3]
+    px, py, pz = p[:, 0], p[:, 1], p[:, 2]
+    dx, dy, dz = px - q[:, 0], py - q[:, 1], pz - q[:, 2]
+    w = np.full(len(p), F32(weight), F32)
+    if dist_w:
+        w = w * w_dist(q, it)
+    if resid_w:
+        w = w * w_residual(np.sqrt((dx * dx + dy * dy) + dz * dz), window)
+    if inten_w:
+        w = w * w_intensity(S[s_i, 8], T[t_i, 8])
+    A, bv = np.zeros((6, 6)), np.zeros(6)
+    A[0, 0] = A[1, 1] = A[2, 2] = seq_sum(w)
+    A[4, 0] = seq_sum(w * pz)
+    A[5, 0] = seq_sum(-w * py)
+    A[3, 1] = seq_sum(-w * pz)
+    A[5, 1] = seq_sum(w * px)
+    A[3, 2] = seq_sum(w * py)
+    A[4, 2] = seq_sum(-w * px)
+    A[3, 3] = seq_sum((w * pz) * pz + (w * py) * py)
+    A[4, 3] = seq_sum((-w * px) * py)
+    A[5, 3] = seq_sum((-w * px) * pz)
+    A[4, 4] = seq_sum((w * pz) * pz + (w * px) * px)
+    A[5, 4] = seq_sum((-w * py) * pz)
+    A[5, 5] = seq_sum((w * py) * py + (w * px) * px)
+    bv[0], bv[1], bv[2] = seq_sum(-w * dx), seq_sum(-w * dy), seq_sum(-w * dz)
+    bv[3] = seq_sum((w * pz) * dy - (w * py) * dz)
+    bv[4] = seq_sum((w * px) * dz - (w * pz) * dx)
+    bv[5] = seq_sum((w * py) * dx - (w * px) * dy)
+    return A, bv, dd  # (the "weight" the residual pass will read: the squared NN distance)
+
+
 def increment_matrix(x):
     tx, ty, tz, al, be, ga = x
     T = np.eye(4)
@@ -227,7 +261,10 @@ def run_loop(pair):
                 a_, b_, weights[c] = line_terms(src[c], tgt[c], corr[c][0], corr[c][1], it, 1.0, dist_w, resid_w, inten_w,
                                                 P.pt2li_residual_window)
                 A, b = A + a_, b + b_
-        assert V not in corr or cnt[V] == 0, "vertex class: not part of this cross-check"
+        if V in corr:
+            a_, b_, weights[V] = point_terms(src[V], tgt[V], corr[V][0], corr[V][1], corr[V][2], it, 1.0, dist_w, resid_w, inten_w,
+                                             P.pt2pt_residual_window)
+            A, b = A + a_, b + b_
         A = np.tril(A) + np.tril(A, -1).T
         inv = np.linalg.inv(A)
         x = inv @ b
@@ -280,6 +317,22 @@ def run_loop(pair):
                     rk = s - bb[k].astype(F64)
                     tot = tot + rk * rk if k else rk * rk
                 vtpv += seq_sum(weights[c].astype(F64) * tot)
+                nobs += 3 * len(s_i)
+            if V in corr:  # :2546-2588
+                s_i, t_i, _ = corr[V]
+                p, q = src[V][s_i, 0:3], tgt[V][t_i, 0:3]
+                px, py, pz = (p[:, k].astype(F64) for k in range(3))
+                d = [(p[:, k] - q[:, k]).astype(F64) for k in range(3)]
+                one, zero = np.ones(len(p)), np.zeros(len(p))
+                rows = [[one, zero, zero, zero, pz, -py], [zero, one, zero, -pz, zero, px], [zero, zero, one, py, -px, zero]]
+                tot = np.zeros(len(p))
+                for k in range(3):
+                    sk = rows[k][0] * x[0]
+                    for jj in range(1, 6):
+                        sk = sk + rows[k][jj] * x[jj]
+                    rk = sk - (-d[k])
+                    tot = tot + rk * rk if k else rk * rk
+                vtpv += seq_sum(weights[V].astype(F64) * tot)
                 nobs += 3 * len(s_i)
             sigma2 = vtpv / (nobs - 6)
             code = 1 if math.sqrt(sigma2) < float(P.sigma_thre) else -3
@@ -342,3 +395,15 @@ def test_whole_loop_on_real_data(oracle_mod, golden_dir):
 
     pair, _ = load_golden_pair(os.path.join(golden_dir, "demo_pair.npz"))
     check_against_oracle(oracle_mod, pair, min_iters=4)
+
+
+def test_whole_loop_with_the_point_to_point_metric(oracle_mod, small_pair):
+    """vertex class on (off in the shipped configurations): pt2pt terms, and the posterior reading the squared NN distance
+    where the other metrics stored a weight"""
+    tgt, src = list(small_pair["tgt"]), list(small_pair["src"])
+    tgt[V] = small_pair["tgt"][PL][::3].copy()
+    src[V] = small_pair["src"][PL][::3].copy()
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.used_feature_type = b"111111"
+    _, log = check_against_oracle(oracle_mod, dict(small_pair, tgt=tgt, src=src, params=p), min_iters=5)
+    assert log[0]["n_corr"][V] > 50
