@@ -48,13 +48,38 @@ def nearest(tgt, src):
     return cand[rows, order], d2[rows, order]
 
 
-def correspondences(src, tgt, thre, normal_check, cos_thre):
+def shoot(tgt, src, max_distance):
+    """CorrespondenceEstimationNormalShooting, k = 10 (:1732-1737): among the 10 nearest targets the one closest to the
+    line through the source point along its normal; dropped if that squared line distance exceeds max_distance (not
+    squared); the correspondence carries the squared NN distance of the chosen target."""
+    k = min(10, len(tgt))
+    _, cand = cKDTree(tgt[:, 0:3].astype(F64)).query(src[:, 0:3].astype(F64), k=k)
+    cand = cand.reshape(len(src), k)
+    d2 = np.stack([l2_simple(src[:, 0:3], tgt[cand[:, j], 0:3]) for j in range(k)], axis=1)
+    order = np.lexsort((cand, d2), axis=1)  # the k-NN list in (distance, index) order: the first minimum wins ties
+    cand, d2 = np.take_along_axis(cand, order, 1), np.take_along_axis(d2, order, 1)
+    n = src[:, 4:7].astype(F64)
+    line = np.empty((len(src), k))
+    for j in range(k):
+        v = (tgt[cand[:, j], 0:3] - src[:, 0:3]).astype(F64)  # float difference, widened
+        c = np.cross(n, v)
+        line[:, j] = c[:, 0] * c[:, 0] + (c[:, 1] * c[:, 1] + c[:, 2] * c[:, 2])
+    best = np.argmin(line, axis=1)
+    rows = np.arange(len(src))
+    ok = line[rows, best] <= max_distance
+    return np.where(ok, cand[rows, best], -1), d2[rows, best], ok
+
+
+def correspondences(src, tgt, thre, normal_check, cos_thre, normal_shooting=False):
     """determine_corres (:1701-1835). Returns (shrunk source cloud, source rows, target rows, squared distances) or None."""
     if len(src) < 3 or len(tgt) < 3:
         return None
-    j, d2 = nearest(tgt, src)
     max_distance = float(F32(2.5) * F32(thre))
-    keep = d2.astype(F64) <= max_distance * max_distance
+    if normal_shooting:
+        j, d2, keep = shoot(tgt, src, max_distance)
+    else:
+        j, d2 = nearest(tgt, src)
+        keep = d2.astype(F64) <= max_distance * max_distance
     s_i, t_i, dd = np.flatnonzero(keep), j[keep], d2[keep]
     if len(src) >= 500:  # duplicate check: the first source in index order keeps the target; the cloud shrinks for good
         _, first = np.unique(t_i, return_index=True)
@@ -231,7 +256,8 @@ def run_loop(pair):
         corr = {}
         for c in range(6):
             if used[c] and len(src[c]) > 0:
-                out = correspondences(src[c], tgt[c], thre[c], c != V, cos_thre)
+                out = correspondences(src[c], tgt[c], thre[c], c != V, cos_thre,
+                                      normal_shooting=bool(P.normal_shooting_on) and c in (G, F, R))
                 if out is not None:
                     src[c], s_i, t_i, dd = out
                     corr[c] = (s_i, t_i, dd)
@@ -407,3 +433,11 @@ def test_whole_loop_with_the_point_to_point_metric(oracle_mod, small_pair):
     p.used_feature_type = b"111111"
     _, log = check_against_oracle(oracle_mod, dict(small_pair, tgt=tgt, src=src, params=p), min_iters=5)
     assert log[0]["n_corr"][V] > 50
+
+
+def test_whole_loop_with_normal_shooting(oracle_mod, small_pair):
+    """normal_shooting_on: ground, facade and roof pick, among their 10 nearest targets, the one closest to the source
+    normal's line (cregistration.hpp:1730-1739)"""
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.normal_shooting_on = 1
+    check_against_oracle(oracle_mod, dict(small_pair, params=p), min_iters=4)
