@@ -228,6 +228,19 @@ def euler_jacobian(e):
                            [-f(sr, cp, sy) - f(cr, sp, cy), -f(cr, sp, sy) - f(sr, cp, cy), f(cr, cp, cy) + f(sr, sp, sy)]])
 
 
+def undistort(cloud, Tinv):
+    """CFilter::apply_motion_compensation (cfilter.hpp:496-516): p <- slerp(I, q(Tinv), s) p + s t(Tinv), s = the timestamp
+    ratio kept in `curvature`; ratios outside [0, 1] leave the point alone; coordinates stored back as float."""
+    out = cloud.copy()
+    s = cloud[:, 9].astype(F64)
+    use = ~((cloud[:, 9] < F32(0.0)) | (s > 1.0))
+    rotvec = Rotation.from_matrix(Tinv[:3, :3]).as_rotvec()
+    Rs = Rotation.from_rotvec(s[use, None] * rotvec[None, :])  # the geodesic from the identity = Eigen's slerp
+    moved = Rs.apply(cloud[use, 0:3].astype(F64)) + s[use, None] * Tinv[:3, 3][None, :]
+    out[use, 0:3] = moved.astype(F32)
+    return out
+
+
 def run_loop(pair):
     P = pair["params"]
     used = [P.used_feature_type[c:c + 1] == b"1" for c in range(6)]
@@ -235,7 +248,8 @@ def run_loop(pair):
     guess = np.array(pair["init_guess"], F64).reshape(4, 4)
     tgt = [t.copy() for t in pair["tgt"]]
     src = [rigid(s, guess) for s in pair["src"]]
-    if P.apply_intersection_filter:  # :2894-2922, utility.hpp:858-890, cfilter.hpp:950-981
+    motion_variant = bool(P.apply_motion_undistortion_while_registration)  # :1248-1258
+    if P.apply_intersection_filter and not motion_variant:  # :2894-2922, utility.hpp:858-890, cfilter.hpp:950-981
         pts = np.concatenate([src[c][:, 0:3] for c in (G, PL, F)]).astype(F64)
         tb = np.array(P.target_bound[:])
         lo = np.maximum(tb[:3], pts.min(0)) - 1.0
@@ -252,7 +266,14 @@ def run_loop(pair):
     sigma2, info, ratio = 1.0, np.eye(6), 1.0
     corr = {}
     for it in range(P.max_iter_num):
-        src = [rigid(s, inc) for s in src]
+        if motion_variant and it == 0:
+            # the delivered clouds are undistorted with the inverse initial guess and moved by the initial guess; the vertex
+            # cloud is neither undistorted nor re-cloned, so it receives the initial guess a second time (as the reference)
+            ginv = np.linalg.inv(guess)
+            src = [undistort(pair["src"][c], ginv) for c in range(5)] + [src[V]]
+            src = [rigid(s_, guess) for s_ in src]
+        else:
+            src = [rigid(s, inc) for s in src]
         corr = {}
         for c in range(6):
             if used[c] and len(src[c]) > 0:
@@ -441,3 +462,23 @@ def test_whole_loop_with_normal_shooting(oracle_mod, small_pair):
     p = abi.IcpParams.from_buffer_copy(small_pair["params"])
     p.normal_shooting_on = 1
     check_against_oracle(oracle_mod, dict(small_pair, params=p), min_iters=4)
+
+
+def test_whole_loop_with_motion_undistortion(oracle_mod, small_pair):
+    """apply_motion_undistortion_while_registration (cregistration.hpp:1248-1258): per-point slerp by the timestamp ratio in
+    `curvature` (scipy's rotation-vector scaling here, Eigen's quaternion slerp restated in the oracle), no intersection
+    filter, the vertex cloud moved twice"""
+    rng = np.random.default_rng(7)
+    src = [s_.copy() for s_ in small_pair["src"]]
+    for s_ in src:
+        s_[:, 9] = rng.uniform(-0.05, 1.05, len(s_)).astype(np.float32)  # a few ratios outside [0, 1]: left untouched
+    tgt = list(small_pair["tgt"])
+    tgt[V] = small_pair["tgt"][PL][::3].copy()
+    src[V] = src[PL][::3].copy()
+    p = abi.IcpParams.from_buffer_copy(small_pair["params"])
+    p.apply_motion_undistortion_while_registration = 1
+    p.used_feature_type = b"111111"
+    init = np.eye(4)
+    init[:3, :3] = Rotation.from_euler("xyz", [0.002, -0.001, 0.012]).as_matrix()
+    init[:3, 3] = (0.9, 0.04, 0.01)
+    check_against_oracle(oracle_mod, dict(small_pair, tgt=tgt, src=src, params=p, init_guess=init), min_iters=4)
