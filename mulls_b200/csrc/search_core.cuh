@@ -21,8 +21,12 @@
 //            box distance — and a small cell is examined where it is met (or, once the seeds are good, queued and
 //            examined together with the block's other small cells in one go)
 //   stop     best <= cover_l^2 (the best found is the global nearest) or cover_l^2 >= r2_prune; else next level
-// The stack lives in thread-local arrays (local memory, L1-resident: measured faster than a shared-memory stack, and
-// faster than two warp-cooperative / round-based forms that were tried — DESIGN.md section 4.1).
+//   scan     a small cell's points four at a time: fused estimates of the squared distances, their minimum against the
+//            best so far, and only then the exact FLANN distances with the tie rule (walk_scan_leaf)
+//   bounds   optionally (WalkBounds) the search also returns a certificate: the squared radius inside which its answer
+//            is the only target — what lets k_search keep a match in later iterations without searching
+// The stack lives in thread-local arrays of 8-byte entries (local memory, L1-resident: measured faster than a
+// shared-memory stack, and faster than two warp-cooperative / round-based forms that were tried — DESIGN.md section 5.1).
 #pragma once
 #include <cfloat>
 #include <cmath>
