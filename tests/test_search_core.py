@@ -206,3 +206,47 @@ def test_a_kept_match_equals_a_fresh_search(lib):
         assert np.array_equal(bi[m][keep], idx[m][keep])
         kept_total += int(keep.sum())
     assert kept_total > 0.5 * len(src)
+
+
+def test_points_on_cell_boundaries_and_queries_outside_the_grid(lib):
+    """coordinates that are exact multiples of the cell size (every point sits on a cell boundary of every level), queries
+    on boundaries, far outside the grid, and at huge coordinates: answers = brute force, certificates stay lower bounds"""
+    h0 = 0.125
+    ax = np.arange(0, 24, dtype=np.float32) * np.float32(h0 / 2)  # lattice at half the cell size
+    gx, gy, gz = np.meshgrid(ax, ax, ax[:6], indexing="ij")
+    tgt = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1).astype(np.float32)
+    rng = np.random.default_rng(21)
+    q = np.concatenate([
+        tgt[rng.integers(0, len(tgt), 300)],                                             # on targets (distance 0, many ties around)
+        tgt[rng.integers(0, len(tgt), 300)] + np.float32(h0 / 4),                        # cell centres of the fine lattice: 8-way ties
+        (rng.integers(-8, 40, (300, 3)) * np.float32(h0)).astype(np.float32),            # on level-0 boundaries, partly outside
+        rng.uniform(-30, 30, (200, 3)).astype(np.float32),                               # far outside the grid
+        np.array([[1e4, 1e4, 1e4], [-1e4, 0, 0], [0.7, 0.7, 400.0]], np.float32)]).astype(np.float32)
+    bi, bd = brute(tgt, q)
+    for radius in (3.5, 0.2, 0.05):
+        for leaf in (32, 2):
+            for mode in (0, 1):
+                idx, d2, cert = run(lib, tgt, q, radius, leaf=leaf, mode=mode, want_cert=True)
+                check(idx, d2, bi, bd, radius)
+                others = second_nearest_sq(tgt, q, idx)
+                assert np.all(cert.astype(np.float64) <= others * (1 + 1e-5) + 1e-9)
+    # seeded with the answers and with wrong seeds
+    seeds = bi.copy()
+    seeds[::2] = rng.integers(0, len(tgt), len(seeds[::2]))
+    idx, d2 = run(lib, tgt, q, 3.5, seeds=seeds, reseed=0.0625)
+    check(idx, d2, bi, bd, 3.5)
+
+
+def test_single_dense_spot_with_a_stack_too_small_to_split_it(lib):
+    """thousands of points inside one level-0 cell next to a sparse halo: level-0 cells are scanned whatever they hold, and a
+    dense cell that cannot be split any further (stack full) is scanned as a whole — still exact"""
+    rng = np.random.default_rng(5)
+    dense = (rng.uniform(0, 0.1, (5000, 3)) + [1.0, 1.0, 1.0]).astype(np.float32)
+    halo = rng.uniform(-3, 5, (2000, 3)).astype(np.float32)
+    tgt = np.concatenate([dense, halo])
+    q = np.concatenate([dense[::50] + np.float32(0.001), halo[::10] + np.float32(0.01), rng.uniform(0.9, 1.2, (200, 3)).astype(np.float32)])
+    bi, bd = brute(tgt, q)
+    for leaf in (32, 1):
+        idx, d2, cert = run(lib, tgt, q, 3.5, leaf=leaf, want_cert=True)
+        check(idx, d2, bi, bd, 3.5)
+        assert np.all(cert.astype(np.float64) <= second_nearest_sq(tgt, q, idx) * (1 + 1e-5) + 1e-9)
